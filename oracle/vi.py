@@ -1,0 +1,169 @@
+"""Oracle (TEST INFRASTRUCTURE ONLY): MGVI / geoVI sampling and the sample-averaged KL.
+
+Restates
+
+* ``draw_linear_residual``          nifty/re/evi.py:88-150  (``sample_likelihood`` :77-80,
+                                    ``_ham_metric`` :83-85)
+* ``nonlinearly_update_residual``   nifty/re/evi.py:181-255 (residual functions :153-178)
+* ``_kl_vg`` / ``_kl_met``          nifty/re/optimize_kl.py:90-144 (``_StandardHamiltonian`` :67-87)
+
+The reference draws its white-noise inputs with ``jax.random`` *outside* of the
+arithmetic restated here (evi.py:121-123); the oracle takes those draws as
+explicit arrays so that oracle and GPU path can be fed identical inputs.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from .solvers import cg, newton_cg
+
+
+class Layout:
+    """Flat-vector view of a parameter dict in sorted-key (= JAX pytree) order."""
+
+    def __init__(self, domain: Dict[str, tuple]):
+        self.keys = sorted(domain)
+        self.shapes = {k: tuple(domain[k]) for k in self.keys}
+        self.offsets = {}
+        off = 0
+        for k in self.keys:
+            self.offsets[k] = off
+            off += int(np.prod(self.shapes[k], dtype=np.int64))
+        self.size = off
+
+    def pack(self, tree) -> np.ndarray:
+        out = np.empty(self.size, dtype=np.float64)
+        for k in self.keys:
+            n = int(np.prod(self.shapes[k], dtype=np.int64))
+            out[self.offsets[k]:self.offsets[k] + n] = np.ravel(np.asarray(tree[k], dtype=np.float64))
+        return out
+
+    def unpack(self, vec) -> Dict[str, np.ndarray]:
+        out = {}
+        for k in self.keys:
+            n = int(np.prod(self.shapes[k], dtype=np.int64))
+            out[k] = np.reshape(vec[self.offsets[k]:self.offsets[k] + n], self.shapes[k])
+        return out
+
+    def random(self, rng: np.random.Generator):
+        """Leaf-by-leaf N(0,1) draws in sorted-key order."""
+        return {k: rng.standard_normal(self.shapes[k]) for k in self.keys}
+
+
+def tree_size(domain) -> int:
+    return Layout(domain).size
+
+
+def _flat_ops(lh):
+    lay = Layout(lh.domain)
+
+    def metric(pos_v, t_v):
+        return lay.pack(lh.metric(lay.unpack(pos_v), lay.unpack(t_v)))
+
+    def ham_metric(pos_v, t_v):  # evi.py:83-85
+        return metric(pos_v, t_v) + t_v
+
+    def lsm(pos_v, eta):
+        return lay.pack(lh.left_sqrt_metric(lay.unpack(pos_v), eta))
+
+    def rsm(pos_v, t_v):
+        return lh.right_sqrt_metric(lay.unpack(pos_v), lay.unpack(t_v))
+
+    def trafo(pos_v):
+        return lh.transformation(lay.unpack(pos_v))
+
+    return lay, metric, ham_metric, lsm, rsm, trafo
+
+
+def draw_linear_residual(lh, pos, white_data, white_prior, *, from_inverse=True, cg_kwargs=None,
+                         _raise_nonposdef=False):
+    """One MGVI sample; returns ``(residual dict, info, CGResult|None)``.
+
+    ``white_data`` (data shape) and ``white_prior`` (latent dict) are the N(0,1)
+    draws of evi.py:122-123.
+    """
+    lay, _, ham_metric, lsm, _, _ = _flat_ops(lh)
+    pos_v = lay.pack(pos)
+    nll_smpl = lsm(pos_v, white_data)
+    prr = lay.pack(white_prior)
+    smpl = nll_smpl + prr
+    info, res = 0, None
+    if from_inverse:
+        kw = dict(cg_kwargs or {})
+        kw.pop("name", None)
+        res = cg(lambda v: ham_metric(pos_v, v), smpl, x0=prr,
+                 _raise_nonposdef=_raise_nonposdef, **kw)
+        smpl, info = res.x, res.info
+        if info < 0:
+            raise ValueError("conjugate gradient failed")
+    return lay.unpack(smpl), info, res
+
+
+def nonlinearly_update_residual(lh, pos, residual_sample, white_data, white_prior,
+                                metric_sample_sign=1.0, *, minimize_kwargs=None):
+    """geoVI update of one residual sample (evi.py:181-255); returns ``(residual, NewtonResult)``."""
+    lay, _, _, lsm, rsm, trafo = _flat_ops(lh)
+    e = lay.pack(pos)
+    sample = e + lay.pack(residual_sample)
+    ms, _, _ = draw_linear_residual(lh, pos, white_data, white_prior, from_inverse=False)
+    ms = metric_sample_sign * lay.pack(ms)
+    mk = dict(minimize_kwargs or {})
+    mk.pop("name", None)
+    if isinstance(mk.get("maxiter", None), int) and mk["maxiter"] == 0:
+        return lay.unpack(sample - e), None
+    trafo_at_p = trafo(e)
+
+    def residual_vg(x):  # evi.py:153-164
+        t = trafo(x) - trafo_at_p
+        g = x - e + lsm(e, t)
+        r = ms - g
+        val = 0.5 * float(np.vdot(r, r))
+        ngrad = r + lsm(x, rsm(e, r))
+        return val, -ngrad
+
+    def metric(x, t):  # evi.py:167-172
+        tm = lsm(e, rsm(x, t)) + t
+        return lsm(x, rsm(e, tm)) + tm
+
+    def sampnorm(natgrad):  # evi.py:175-178
+        fpp = rsm(e, natgrad)
+        return float(np.sqrt(np.vdot(natgrad, natgrad) + np.vdot(fpp, fpp)))
+
+    opt = newton_cg(sample, residual_vg, metric, custom_gradnorm=sampnorm, **mk)
+    return lay.unpack(opt.x - e), opt
+
+
+def _ham_vg(lh, lay, x_v):
+    e, g = lh.energy_and_gradient(lay.unpack(x_v))
+    return e + 0.5 * float(np.vdot(x_v, x_v)), lay.pack(g) + x_v
+
+
+def kl_value_and_grad(lh, pos, residuals: Sequence[dict]):
+    """Mean over samples of value_and_grad of the standard Hamiltonian (optimize_kl.py:90-114)."""
+    lay = Layout(lh.domain)
+    p = lay.pack(pos)
+    if len(residuals) == 0:
+        v, g = _ham_vg(lh, lay, p)
+        return v, lay.unpack(g)
+    vals, grads = [], []
+    for r in residuals:
+        v, g = _ham_vg(lh, lay, p + lay.pack(r))
+        vals.append(v)
+        grads.append(g)
+    return float(np.mean(vals)), lay.unpack(np.mean(np.stack(grads), axis=0))
+
+
+def kl_metric(lh, pos, tangents, residuals: Sequence[dict]):
+    """Mean over samples of ``metric(pos + r_i, t) + t`` (optimize_kl.py:117-144)."""
+    lay = Layout(lh.domain)
+    p, t = lay.pack(pos), lay.pack(tangents)
+    if len(residuals) == 0:
+        return lay.unpack(lay.pack(lh.metric(pos, tangents)) + t)
+    outs = []
+    for r in residuals:
+        x = lay.unpack(p + lay.pack(r))
+        outs.append(lay.pack(lh.metric(x, tangents)) + t)
+    return lay.unpack(np.mean(np.stack(outs), axis=0))

@@ -1,0 +1,161 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Runs only in the build container (needs /root/reference).  ``nifty.re`` needs JAX,
+which is not installed; the reference's second implementation of the same maths,
+``nifty.cl``, is importable through two throw-away shims created in a temp dir
+(a ``nifty-9.2.0.dist-info`` because ``nifty/__init__.py`` asks importlib.metadata
+for the version, and a ``ducc0`` stub without an ``fft`` sub-module so that
+``nifty/cl/ducc_dispatch.py:152-156`` falls back to ``scipy.fft``).  Nothing is
+copied from or written into the reference tree.
+
+The ``nifty.re`` <-> ``nifty.cl`` parameter mapping is the one of the reference's own
+parity test, test/test_re/test_correlated_field.py:116-192: identical keys, the
+``spectrum`` leaf transposed ((2, K-2) in cl, (K-2, 2) in re) and
+``non_parametric_kind="power"`` on the re side.
+
+Usage:  python tests/golden/make_golden.py        (rewrites tests/golden/*.npz)
+"""
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def _import_nifty_cl():
+    shim = tempfile.mkdtemp(prefix="nifty_shim_")
+    os.makedirs(os.path.join(shim, "nifty-9.2.0.dist-info"))
+    with open(os.path.join(shim, "nifty-9.2.0.dist-info", "METADATA"), "w") as f:
+        f.write("Metadata-Version: 2.1\nName: nifty\nVersion: 9.2.0\n")
+    os.makedirs(os.path.join(shim, "ducc0"))
+    with open(os.path.join(shim, "ducc0", "__init__.py"), "w") as f:
+        f.write("__version__ = '0.0'\nfrom . import misc\n")
+    with open(os.path.join(shim, "ducc0", "misc.py"), "w") as f:
+        f.write("import os\ndef resize_thread_pool(n): pass\n"
+                "def available_hardware_threads(): return os.cpu_count()\n")
+    sys.path.insert(0, REF)
+    sys.path.insert(0, shim)
+    import nifty.cl as ift
+    return ift
+
+
+CASES = {
+    # name: (shape, distances, offset_mean, offset_std, fluct-kwargs, likelihood, seed, scaling)
+    "g2d_16x16": dict(shape=(16, 16), distances=1.0 / 16, offset_mean=0.0, offset_std=(1e-3, 1e-4),
+                      fluctuations=(1e-1, 5e-3), loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5),
+                      asperity=(0.5, 0.05), lh="gauss", seed=42),
+    "g2d_8x32": dict(shape=(8, 32), distances=(0.3, 0.11), offset_mean=0.5, offset_std=(0.1, 0.1),
+                     fluctuations=(1.0, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.1),
+                     asperity=None, lh="gauss", seed=7),
+    "p2d_32x32": dict(shape=(32, 32), distances=1.0 / 32, offset_mean=2.0, offset_std=(0.1, 0.03),
+                      fluctuations=(1.0, 0.5), loglogavgslope=(-3.0, 0.2), flexibility=(1.0, 0.2),
+                      asperity=(0.5, 0.05), lh="poisson", seed=3),
+    "g3d_8x8x8": dict(shape=(8, 8, 8), distances=1.0 / 8, offset_mean=0.0, offset_std=(1e-3, 1e-4),
+                      fluctuations=(1e-1, 5e-3), loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5),
+                      asperity=(0.5, 0.05), lh="gauss", seed=11),
+    "g3d_4x8x16": dict(shape=(4, 8, 16), distances=(0.2, 0.1, 0.05), offset_mean=-0.3,
+                       offset_std=(0.2, 0.1), fluctuations=(0.5, 0.1), loglogavgslope=(-2.5, 0.5),
+                       flexibility=(2.0, 1.0), asperity=(0.2, 0.02), lh="gauss", seed=5),
+    "g1d_64": dict(shape=(64,), distances=0.1, offset_mean=0.0, offset_std=(0.1, 0.1),
+                   fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1),
+                   asperity=(0.2, 2e-2), lh="gauss", seed=0),
+    "g2d_3x3": dict(shape=(3, 3), distances=0.1, offset_mean=0.0, offset_std=(0.1, 0.1),
+                    fluctuations=(3.0, 2.0), loglogavgslope=(4.0, 1.0), flexibility=(3.0, 2.0),
+                    asperity=(0.2, 2e-2), lh="gauss", seed=42),
+}
+
+
+def build_cl(ift, c):
+    sp = ift.RGSpace(c["shape"], c["distances"])
+    cfm = ift.CorrelatedFieldMaker("cf")
+    cfm.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+    cfm.add_fluctuations(sp, c["fluctuations"], c["flexibility"], c["asperity"],
+                         c["loglogavgslope"], prefix="ax1")
+    cf = cfm.finalize(prior_info=0)
+    return cf
+
+
+def to_cl(ift, dom, tree):
+    d = {}
+    for k, v in tree.items():
+        v = np.asarray(v)
+        if k.endswith("spectrum"):
+            v = v.T
+        d[k] = ift.makeField(dom[k], np.array(v, order='C'))
+    return ift.MultiField.from_dict(d, dom)
+
+
+def from_cl(mf):
+    out = {}
+    for k, v in mf.to_dict().items():
+        a = np.asarray(v.asnumpy() if hasattr(v, "asnumpy") else v.val)
+        if k.endswith("spectrum"):
+            a = a.T
+        out[k] = np.array(a, order='C')
+    return out
+
+
+def main():
+    ift = _import_nifty_cl()
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import CorrelatedFieldOracle, Layout  # only to draw inputs in oracle key order
+
+    for name, c in CASES.items():
+        cf = build_cl(ift, c)
+        orc = CorrelatedFieldOracle("cf")
+        orc.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+        orc.add_fluctuations(c["shape"], c["distances"], c["fluctuations"], c["loglogavgslope"],
+                             c["flexibility"], c["asperity"], prefix="ax1", non_parametric_kind="power")
+        orc.finalize()
+        lay = Layout(orc.domain)
+        rng = np.random.default_rng(c["seed"])
+        pos = lay.random(rng)
+        tan = lay.random(rng)
+        cot = rng.standard_normal(c["shape"])
+        out = {}
+        for k in lay.keys:
+            out["pos/" + k] = pos[k]
+            out["tan/" + k] = tan[k]
+        out["cot"] = cot
+
+        npos = to_cl(ift, cf.domain, pos)
+        ntan = to_cl(ift, cf.domain, tan)
+        ncot = ift.makeField(cf.target, cot)
+        lin = cf(ift.Linearization.make_var(npos))
+        out["field"] = lin.val.asnumpy()
+        out["field_jvp"] = lin.jac(ntan).asnumpy()
+        for k, v in from_cl(lin.jac.adjoint(ncot)).items():
+            out["field_vjp/" + k] = v
+
+        signal = cf.exp()
+        slin = signal(ift.Linearization.make_var(npos, want_metric=True))
+        sig = slin.val.asnumpy()
+        out["signal"] = sig
+        if c["lh"] == "gauss":
+            noise_std = 0.1
+            data = sig + noise_std * rng.standard_normal(c["shape"])
+            out["data"] = data
+            out["noise_cov_inv"] = np.array(noise_std**-2)
+            N_inv = ift.ScalingOperator(cf.target, noise_std**-2, float)
+            lh = ift.GaussianEnergy(data=ift.makeField(cf.target, data), inverse_covariance=N_inv) @ signal
+        else:
+            data = rng.poisson(sig).astype(np.int64)
+            out["data"] = data
+            lh = ift.PoissonianEnergy(ift.makeField(cf.target, data)) @ signal
+        elin = lh(ift.Linearization.make_var(npos, want_metric=True))
+        out["energy"] = np.array(elin.val.asnumpy())
+        for k, v in from_cl(elin.gradient).items():
+            out["grad/" + k] = v
+        for k, v in from_cl(elin.metric(ntan)).items():
+            out["metric/" + k] = v
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print("wrote", name, "L =", lay.size)
+
+
+if __name__ == "__main__":
+    main()

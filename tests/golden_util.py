@@ -1,0 +1,70 @@
+"""Helpers shared by the CPU (oracle) and GPU parity tests: load the nifty.cl fixtures."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# must stay in sync with tests/golden/make_golden.py:CASES (the generator is the source of truth;
+# the hyper-parameters are repeated here because /root/reference is absent on the GPU box)
+CASES = {
+    "g2d_16x16": dict(shape=(16, 16), distances=1.0 / 16, offset_mean=0.0, offset_std=(1e-3, 1e-4),
+                      fluctuations=(1e-1, 5e-3), loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5),
+                      asperity=(0.5, 0.05), lh="gauss", seed=42),
+    "g2d_8x32": dict(shape=(8, 32), distances=(0.3, 0.11), offset_mean=0.5, offset_std=(0.1, 0.1),
+                     fluctuations=(1.0, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.1),
+                     asperity=None, lh="gauss", seed=7),
+    "p2d_32x32": dict(shape=(32, 32), distances=1.0 / 32, offset_mean=2.0, offset_std=(0.1, 0.03),
+                      fluctuations=(1.0, 0.5), loglogavgslope=(-3.0, 0.2), flexibility=(1.0, 0.2),
+                      asperity=(0.5, 0.05), lh="poisson", seed=3),
+    "g3d_8x8x8": dict(shape=(8, 8, 8), distances=1.0 / 8, offset_mean=0.0, offset_std=(1e-3, 1e-4),
+                      fluctuations=(1e-1, 5e-3), loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5),
+                      asperity=(0.5, 0.05), lh="gauss", seed=11),
+    "g3d_4x8x16": dict(shape=(4, 8, 16), distances=(0.2, 0.1, 0.05), offset_mean=-0.3,
+                       offset_std=(0.2, 0.1), fluctuations=(0.5, 0.1), loglogavgslope=(-2.5, 0.5),
+                       flexibility=(2.0, 1.0), asperity=(0.2, 0.02), lh="gauss", seed=5),
+    "g1d_64": dict(shape=(64,), distances=0.1, offset_mean=0.0, offset_std=(0.1, 0.1),
+                   fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1),
+                   asperity=(0.2, 2e-2), lh="gauss", seed=0),
+    "g2d_3x3": dict(shape=(3, 3), distances=0.1, offset_mean=0.0, offset_std=(0.1, 0.1),
+                    fluctuations=(3.0, 2.0), loglogavgslope=(4.0, 1.0), flexibility=(3.0, 2.0),
+                    asperity=(0.2, 2e-2), lh="gauss", seed=42),
+}
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    out = {"pos": {}, "tan": {}, "field_vjp": {}, "grad": {}, "metric": {}}
+    for k in z.files:
+        if "/" in k:
+            grp, key = k.split("/", 1)
+            out[grp][key] = z[k]
+        else:
+            out[k] = z[k]
+    return out
+
+
+def build_oracle(c):
+    from oracle import CorrelatedFieldOracle, GaussianOracle, PoissonianOracle, SignalOracle
+    cf = CorrelatedFieldOracle("cf")
+    cf.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+    cf.add_fluctuations(c["shape"], c["distances"], c["fluctuations"], c["loglogavgslope"],
+                        c["flexibility"], c["asperity"], prefix="ax1", non_parametric_kind="power")
+    cf.finalize()
+    return cf
+
+
+def build_oracle_lh(c, g):
+    from oracle import GaussianOracle, PoissonianOracle, SignalOracle
+    cf = build_oracle(c)
+    sig = SignalOracle(cf, "exp")
+    if c["lh"] == "gauss":
+        return GaussianOracle(g["data"], float(g["noise_cov_inv"]), sig)
+    return PoissonianOracle(g["data"], sig)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
