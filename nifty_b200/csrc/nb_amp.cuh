@@ -1,0 +1,409 @@
+// nifty_b200 -- the O(K) amplitude model on the device: forward, tangent and cotangent chains.
+//
+// Restates (not ports) nifty/re/correlated_field.py:481-516 (NonParametricAmplitude.__call__),
+// :297-299 (_remove_slope), :807-821 (get_normalized_amplitudes), nifty/re/gauss_markov.py:102-114
+// (integrated_wiener_process) and nifty/re/num/stats_distributions.py:42-98 (normal/lognormal
+// priors); the tangent / cotangent chains are hand-derived (the reference gets them from JAX AD).
+//
+// The two chained cumulative sums of the integrated Wiener process
+//     y_{j+1} = y_j + r1_j ,   x_{j+1} = x_j + dt_j y_j + r0_j
+// are ONE scan over affine maps (a,b,c): (x,y) -> (x + a y + b, y + c), composed associatively as
+// (a1+a2, b1+b2+a2 c1, c1+c2).  The cotangent chain is the same recurrence run backwards.
+// Scans are three launches (chunk aggregates, aggregate scan, apply) with fixed chunking, hence
+// bit-reproducible; global sums use per-block partials finished by the last block in fixed order.
+#pragma once
+#include "nb_common.cuh"
+
+namespace nb {
+
+// indices into the per-linearisation scalar block (device array of T)
+enum AmpScalIdx {
+  SC_FLU = 0, SC_SLOPE, SC_SIG, SC_ASP, SC_Z, SC_S, SC_CWL, SC_TWLAST,
+  SC_CJ = 8, SC_DA0 = 9,        // tangent side, consumed by ProMetric (must stay adjacent)
+  SC_DSLOPE = 10, SC_DTWLAST = 11,
+  SC_SG = 12, SC_SGL = 13, SC_ABAR0 = 14, SC_UBL = 15,   // cotangent side
+  SC_SCALING = 16,              // value of the multiplicative scaling (1 if absent)
+  SC_ENERGY = 17,               // likelihood energy of the last linearisation
+  SC_SUMCOT = 18,               // sum of dE/df (scaling gradient)
+  SC_DOT = 19,                  // <add, out> of the last adjoint application
+  SC_COUNT = 32
+};
+
+template <class T> struct AmpModel {
+  int K;                 // number of mode bins
+  int kind_power;        // 1: "power", 0: "amplitude"   (correlated_field.py:506-513)
+  int has_dev, has_flu, has_asp, has_scaling;
+  const T* ell;          // [K] relative log mode lengths
+  const T* mult;         // [K] multiplicities
+  const T* dt;           // [K-2] log volumes
+  T V;                   // total volume
+  T flu_a, flu_b, slp_a, slp_b, flx_a, flx_b, asp_a, asp_b, zm_a, zm_b, scl_a, scl_b;
+  long off_flu, off_slp, off_flx, off_asp, off_spec, off_zm, off_xi, off_scl;
+  long L;
+};
+
+template <class T> struct Aff { T a, b, c; };
+template <class T> NB_HD NB_INLINE Aff<T> aff_id() { Aff<T> e; e.a = 0; e.b = 0; e.c = 0; return e; }
+template <class T> NB_HD NB_INLINE Aff<T> aff_compose(Aff<T> f, Aff<T> s) {
+  Aff<T> r; r.a = f.a + s.a; r.b = f.b + s.b + s.a * f.c; r.c = f.c + s.c; return r;
+}
+
+constexpr int SCAN_NT = 256;
+constexpr int SCAN_E = 8;
+constexpr int SCAN_CH = SCAN_NT * SCAN_E;
+
+template <class T> inline size_t scan_smem_bytes() { return (size_t)(SCAN_CH + 2 * SCAN_NT + 64) * sizeof(Aff<T>); }
+
+// sum of partials[i*stride], i < n, by all threads of the calling block (fixed order -> deterministic)
+template <class T> NB_HD NB_INLINE T block_total(Ctx& ctx, const T* partials, int n, int stride, void* scratch) {
+  T s = 0;
+  NB_FOR(ctx, i, n) s += partials[(size_t)i * stride];
+  return ctx.block_sum(s, scratch);
+}
+
+// ---- generic three-kernel scan -------------------------------------------------------------
+template <class T, class Elem> struct ScanAggParams { long n; Elem elem; Aff<T>* agg; };
+template <class T, class Elem> struct ScanAggBody {
+  typedef ScanAggParams<T, Elem> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    Aff<T>* el = reinterpret_cast<Aff<T>*>(smem);
+    Aff<T>* tagg = el + SCAN_CH;
+    long p0 = (long)ctx.bid * SCAN_CH;
+    NB_FOR(ctx, i, SCAN_CH) el[i] = (p0 + i < p.n) ? p.elem.get(p0 + i) : aff_id<T>();
+    ctx.sync();
+    NB_FOR(ctx, t, SCAN_NT) {
+      Aff<T> a = el[t * SCAN_E];
+      for (int e = 1; e < SCAN_E; ++e) a = aff_compose(a, el[t * SCAN_E + e]);
+      tagg[t] = a;
+    }
+    ctx.sync();
+    if (ctx.tid == 0) {
+      Aff<T> a = tagg[0];
+      for (int t = 1; t < SCAN_NT; ++t) a = aff_compose(a, tagg[t]);
+      p.agg[ctx.bid] = a;
+    }
+  }
+};
+
+template <class T> struct ScanTopParams { int nchunks; const Aff<T>* agg; T* pre; /* [nchunks][2] */ T* total; /* [2] */ };
+template <class T> struct ScanTopBody {
+  typedef ScanTopParams<T> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void*) {
+    if (ctx.tid == 0 && ctx.bid == 0) {
+      T x = 0, y = 0;
+      for (int c = 0; c < p.nchunks; ++c) {
+        p.pre[2 * c] = x; p.pre[2 * c + 1] = y;
+        Aff<T> e = p.agg[c];
+        x = x + e.a * y + e.b; y = y + e.c;
+      }
+      p.total[0] = x; p.total[1] = y;
+    }
+  }
+};
+
+// Out::put(pos, x0, y0, x1, y1, acc[4]) is called once per element with the state before / after;
+// Out::finish(ctx, acc, scratch) runs in every block afterwards.
+template <class T, class Elem, class Out> struct ScanApplyParams { long n; Elem elem; Out out; const T* pre; };
+template <class T, class Elem, class Out> struct ScanApplyBody {
+  typedef ScanApplyParams<T, Elem, Out> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    Aff<T>* el = reinterpret_cast<Aff<T>*>(smem);
+    Aff<T>* tagg = el + SCAN_CH;
+    Aff<T>* tpre = tagg + SCAN_NT;
+    long p0 = (long)ctx.bid * SCAN_CH;
+    NB_FOR(ctx, i, SCAN_CH) el[i] = (p0 + i < p.n) ? p.elem.get(p0 + i) : aff_id<T>();
+    ctx.sync();
+    NB_FOR(ctx, t, SCAN_NT) {
+      Aff<T> a = el[t * SCAN_E];
+      for (int e = 1; e < SCAN_E; ++e) a = aff_compose(a, el[t * SCAN_E + e]);
+      tagg[t] = a;
+    }
+    ctx.sync();
+    if (ctx.tid == 0) {
+      T x = p.pre ? p.pre[2 * ctx.bid] : T(0), y = p.pre ? p.pre[2 * ctx.bid + 1] : T(0);
+      for (int t = 0; t < SCAN_NT; ++t) {
+        tpre[t].b = x; tpre[t].c = y;
+        Aff<T> e = tagg[t];
+        x = x + e.a * y + e.b; y = y + e.c;
+      }
+    }
+    ctx.sync();
+    T acc[4] = {0, 0, 0, 0};
+    NB_FOR(ctx, t, SCAN_NT) {
+      T x = tpre[t].b, y = tpre[t].c;
+      for (int e = 0; e < SCAN_E; ++e) {
+        long pos = p0 + t * SCAN_E + e;
+        if (pos >= p.n) break;
+        Aff<T> a = el[t * SCAN_E + e];
+        T x1 = x + a.a * y + a.b, y1 = y + a.c;
+        p.out.put(pos, x, y, x1, y1, acc);
+        x = x1; y = y1;
+      }
+    }
+    p.out.finish(ctx, acc, reinterpret_cast<void*>(tpre + SCAN_NT));
+  }
+};
+
+// ---- helpers ---------------------------------------------------------------------------------
+template <class T> NB_HD NB_INLINE T prior_ln(T a, T b, T xi) { return nb_exp(a + b * xi); }
+
+// scalars of the amplitude model at `pos` (every thread may call it; a handful of exps)
+template <class T> struct AmpPoint { T flu, slope, sig, asp, z, scl; };
+template <class T> NB_HD NB_INLINE AmpPoint<T> amp_point(const AmpModel<T>& m, const T* pos) {
+  AmpPoint<T> a;
+  a.flu = m.has_flu ? prior_ln(m.flu_a, m.flu_b, pos[m.off_flu]) : T(1);
+  a.slope = m.slp_a + m.slp_b * pos[m.off_slp];
+  a.sig = m.has_dev ? prior_ln(m.flx_a, m.flx_b, pos[m.off_flx]) : T(0);
+  a.asp = (m.has_dev && m.has_asp) ? prior_ln(m.asp_a, m.asp_b, pos[m.off_asp]) : T(0);
+  a.z = prior_ln(m.zm_a, m.zm_b, pos[m.off_zm]);
+  a.scl = m.has_scaling ? prior_ln(m.scl_a, m.scl_b, pos[m.off_scl]) : T(1);
+  return a;
+}
+
+// ---- forward chain ---------------------------------------------------------------------------
+// scan position p = bin b; elements are the IWP increments for b >= 2 (j = b-2), identity below
+template <class T> struct FwdElem {
+  AmpModel<T> m; const T* pos;
+  NB_HD NB_INLINE Aff<T> get(long b) const {
+    if (!m.has_dev || b < 2) return aff_id<T>();
+    long j = b - 2;
+    AmpPoint<T> ap = amp_point(m, pos);
+    T dt = m.dt[j], sd = ap.sig * nb_sqrt(dt), q = nb_sqrt(dt * dt / T(12) + ap.asp);
+    T x0 = pos[m.off_spec + 2 * j], x1 = pos[m.off_spec + 2 * j + 1];
+    T r1 = sd * x1, r0 = sd * x0 * q + T(0.5) * dt * r1;
+    Aff<T> e; e.a = dt; e.b = r0; e.c = r1; return e;
+  }
+};
+// P_b = exp(slope l_b + tw_b - tw_last l_b / l_last); partial S
+template <class T> struct FwdOut {
+  AmpModel<T> m; const T* pos; const T* total;   // total[0] = tw_{K-1}
+  T* P; T* partials; unsigned* counter; T* scal;
+  NB_HD NB_INLINE void put(long b, T, T, T x1, T, T* acc) const {
+    AmpPoint<T> ap = amp_point(m, pos);
+    T l = m.ell[b], llast = m.ell[m.K - 1];
+    T u = ap.slope * l;
+    if (m.has_dev) u += x1 - total[0] * (l / llast);
+    T Pb = nb_exp(u);
+    P[b] = Pb;
+    if (b >= 1) acc[0] += m.mult[b] * (m.kind_power ? Pb : Pb * Pb);
+  }
+  NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, void* scratch) const {
+    T s = ctx.block_sum(acc[0], scratch);
+    if (ctx.tid == 0) partials[ctx.bid] = s;
+    if (ctx.last_block(counter)) {
+      T S = block_total(ctx, partials, ctx.nblk, 1, scratch);
+      if (ctx.tid == 0) {
+        AmpPoint<T> ap = amp_point(m, pos);
+        scal[SC_S] = S; scal[SC_FLU] = ap.flu; scal[SC_SLOPE] = ap.slope; scal[SC_SIG] = ap.sig;
+        scal[SC_ASP] = ap.asp; scal[SC_Z] = ap.z; scal[SC_SCALING] = ap.scl;
+        scal[SC_TWLAST] = m.has_dev ? total[0] : T(0);
+      }
+    }
+  }
+};
+// A_b (with A_0 = z V), wS_b, sum wS_b l_b
+template <class T> struct AmpTabParams { AmpModel<T> m; const T* P; T* amp; T* wS; T* partials; unsigned* counter; T* scal; };
+template <class T> struct AmpTabBody {
+  typedef AmpTabParams<T> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    const AmpModel<T>& m = p.m;
+    T S = p.scal[SC_S], flu = p.scal[SC_FLU], z = p.scal[SC_Z];
+    T acc = 0;
+    long b0 = (long)ctx.bid * SCAN_CH;
+    NB_FOR(ctx, i, SCAN_CH) {
+      long b = b0 + i;
+      if (b >= m.K) break;
+      T Pb = p.P[b], A, w;
+      if (m.kind_power) { A = flu * m.V * nb_sqrt(Pb / S); w = m.mult[b] * Pb / S; }
+      else { A = flu * m.V * Pb / nb_sqrt(S); w = T(2) * m.mult[b] * Pb * Pb / S; }
+      if (b == 0) { A = z * m.V; w = 0; }
+      p.amp[b] = A; p.wS[b] = w;
+      acc += w * m.ell[b];
+    }
+    acc = ctx.block_sum(acc, smem);
+    if (ctx.tid == 0) p.partials[ctx.bid] = acc;
+    if (ctx.last_block(p.counter)) {
+      T c = block_total(ctx, p.partials, ctx.nblk, 1, smem);
+      if (ctx.tid == 0) p.scal[SC_CWL] = c;
+    }
+  }
+};
+
+// ---- tangent chain ---------------------------------------------------------------------------
+template <class T> struct JvpElem {
+  AmpModel<T> m; const T* pos; const T* t; const T* scal;
+  NB_HD NB_INLINE Aff<T> get(long b) const {
+    if (!m.has_dev || b < 2) return aff_id<T>();
+    long j = b - 2;
+    AmpPoint<T> ap; ap.sig = scal[SC_SIG]; ap.asp = scal[SC_ASP];
+    T dt = m.dt[j], sd = ap.sig * nb_sqrt(dt), q = nb_sqrt(dt * dt / T(12) + ap.asp);
+    T x0 = pos[m.off_spec + 2 * j], x1 = pos[m.off_spec + 2 * j + 1];
+    T d0 = t[m.off_spec + 2 * j], d1 = t[m.off_spec + 2 * j + 1];
+    T dsig_rel = m.flx_b * t[m.off_flx];
+    T dasp = m.has_asp ? ap.asp * m.asp_b * t[m.off_asp] : T(0);
+    T dr1 = sd * (dsig_rel * x1 + d1);
+    T dr0 = sd * q * (dsig_rel * x0 + d0) + sd * x0 * dasp / (T(2) * q) + T(0.5) * dt * dr1;
+    Aff<T> e; e.a = dt; e.b = dr0; e.c = dr1; return e;
+  }
+};
+template <class T> struct JvpOut {
+  AmpModel<T> m; const T* pos; const T* t; const T* total; const T* wS;
+  T* du; T* partials; unsigned* counter; T* scal;
+  NB_HD NB_INLINE void put(long b, T, T, T x1, T, T* acc) const {
+    T l = m.ell[b], llast = m.ell[m.K - 1];
+    T d = m.slp_b * t[m.off_slp] * l;
+    if (m.has_dev) d += x1 - total[0] * (l / llast);
+    du[b] = d;
+    acc[0] += wS[b] * d;
+  }
+  NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, void* scratch) const {
+    T s = ctx.block_sum(acc[0], scratch);
+    if (ctx.tid == 0) partials[ctx.bid] = s;
+    if (ctx.last_block(counter)) {
+      T sw = block_total(ctx, partials, ctx.nblk, 1, scratch);
+      if (ctx.tid == 0) {
+        T dflu_rel = m.has_flu ? m.flu_b * t[m.off_flu] : T(0);
+        scal[SC_CJ] = dflu_rel - T(0.5) * sw;
+        scal[SC_DA0] = m.V * scal[SC_Z] * m.zm_b * t[m.off_zm];
+      }
+    }
+  }
+};
+
+// ---- cotangent chain -------------------------------------------------------------------------
+// segment sum over the folded W array through a CSR of W positions per bin (fixed order), one
+// warp-sized group of threads per bin:  g_b = A_b * sum_{p in bin b} W[p]  (g_0 = 0)
+template <class T> struct SegSumParams {
+  AmpModel<T> m; const T* W; const int* order; const int* offs; const T* amp;
+  T* g; T* abar /* optional raw bin sums */; T* partials /* [nblk][2] */; unsigned* counter; T* scal;
+  int lg_lpb;   // log2(lanes per bin); 256 threads -> 256 >> lg_lpb bins per block
+};
+template <class T> struct SegSumBody {
+  typedef SegSumParams<T> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    T* sm = reinterpret_cast<T*>(smem);          // [256] lane partials, then reduction scratch
+    const AmpModel<T>& m = p.m;
+    const int lpb = 1 << p.lg_lpb, bpb = 256 >> p.lg_lpb;
+    long b0 = (long)ctx.bid * bpb;
+    NB_FOR(ctx, i, 256) {
+      long b = b0 + (i >> p.lg_lpb);
+      int lane = i & (lpb - 1);
+      T s = 0;
+      if (b < m.K) {
+        int beg = p.offs[b], end = p.offs[b + 1];
+        for (int q = beg + lane; q < end; q += lpb) s += p.W[p.order[q]];
+      }
+      sm[i] = s;
+    }
+    ctx.sync();
+    for (int half = lpb >> 1; half >= 1; half >>= 1) {   // fixed tree over the lanes of each bin
+      NB_FOR(ctx, i, bpb * half) {
+        int bin = i / half, l = i - bin * half;
+        sm[(bin << p.lg_lpb) + l] += sm[(bin << p.lg_lpb) + l + half];
+      }
+      ctx.sync();
+    }
+    T a0 = 0, a1 = 0;
+    NB_FOR(ctx, i, bpb) {
+      long b = b0 + i;
+      if (b < m.K) {
+        T abar = sm[i << p.lg_lpb];
+        if (p.abar) p.abar[b] = abar;
+        if (p.g) {
+          T gb = (b == 0) ? T(0) : abar * p.amp[b];
+          p.g[b] = gb;
+          if (b == 0) p.scal[SC_ABAR0] = abar;
+          a0 += gb; a1 += gb * m.ell[b];
+        }
+      }
+    }
+    if (!p.g) return;
+    void* scratch = reinterpret_cast<void*>(sm + 256);
+    a0 = ctx.block_sum(a0, scratch);
+    a1 = ctx.block_sum(a1, scratch);
+    if (ctx.tid == 0) { p.partials[2 * ctx.bid] = a0; p.partials[2 * ctx.bid + 1] = a1; }
+    if (ctx.last_block(p.counter)) {
+      T sg = block_total(ctx, p.partials, ctx.nblk, 2, scratch);
+      T sgl = block_total(ctx, p.partials + 1, ctx.nblk, 2, scratch);
+      if (ctx.tid == 0) {
+        T kappa = m.kind_power ? T(0.5) : T(1);
+        p.scal[SC_SG] = sg; p.scal[SC_SGL] = sgl;
+        p.scal[SC_UBL] = kappa * sgl - T(0.5) * sg * p.scal[SC_CWL];   // sum_b ubar_b l_b
+      }
+    }
+  }
+};
+
+// reverse scan over j' = (K-3) - j ; element c_j = twbar_{j+2}
+template <class T> NB_HD NB_INLINE T twbar_at(const AmpModel<T>& m, const T* g, const T* wS, const T* scal, long b) {
+  T kappa = m.kind_power ? T(0.5) : T(1);
+  T ub = kappa * g[b] - T(0.5) * scal[SC_SG] * wS[b];
+  if (b == m.K - 1) ub -= scal[SC_UBL] / m.ell[m.K - 1];
+  return ub;
+}
+template <class T> struct VjpElem {
+  AmpModel<T> m; const T* g; const T* wS; const T* scal;
+  NB_HD NB_INLINE Aff<T> get(long p) const {
+    long j = (m.K - 3) - p;
+    T dt = m.dt[j], c = twbar_at(m, g, wS, scal, j + 2);
+    Aff<T> e; e.a = dt; e.b = dt * c; e.c = c; return e;
+  }
+};
+
+// everything that finishes an adjoint application: spectrum cotangents from the reverse scan,
+// the scalar leaves, "+ add" and the dot product <add, out>
+template <class T> struct VjpOut {
+  AmpModel<T> m; const T* pos; const T* g; const T* wS; const T* scal_in;
+  T* out; const T* add;
+  T* partials /* [nblk][3] */; unsigned* counter; T* scal;
+  const T* p3_partials; int n_p3;       // [n_p3][2]: acc0 = sum of position-space cotangent
+  const T* p5_partials; int n_p5;       // [n_p5]: xi-block of <add, out>
+  T scl_factor;                         // factor applied to the p3 sum for the scaling leaf
+  NB_HD NB_INLINE void put(long p, T x0, T, T, T y1, T* acc) const {
+    long j = (m.K - 3) - p;
+    T sig = scal_in[SC_SIG], asp = scal_in[SC_ASP];
+    T dt = m.dt[j], sq = nb_sqrt(dt), sd = sig * sq, q = nb_sqrt(dt * dt / T(12) + asp);
+    T r0bar = y1, r1bar = x0 + T(0.5) * dt * r0bar;
+    T xi0 = pos[m.off_spec + 2 * j], xi1 = pos[m.off_spec + 2 * j + 1];
+    T o0 = r0bar * sd * q, o1 = r1bar * sd;
+    acc[0] += (r0bar * xi0 * q + r1bar * xi1) * sq;           // sigbar
+    acc[1] += r0bar * sd * xi0 / (T(2) * q);                  // aspbar
+    if (add) {
+      T a0 = add[m.off_spec + 2 * j], a1 = add[m.off_spec + 2 * j + 1];
+      o0 += a0; o1 += a1;
+      acc[2] += a0 * o0 + a1 * o1;
+    }
+    out[m.off_spec + 2 * j] = o0; out[m.off_spec + 2 * j + 1] = o1;
+  }
+  NB_HD NB_INLINE void leaf(long off, T v, T& dot) const {
+    if (add) { T a = add[off]; v += a; dot += a * v; }
+    out[off] = v;
+  }
+  NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, void* scratch) const {
+    T s0 = ctx.block_sum(acc[0], scratch), s1 = ctx.block_sum(acc[1], scratch), s2 = ctx.block_sum(acc[2], scratch);
+    if (ctx.tid == 0) { partials[3 * ctx.bid] = s0; partials[3 * ctx.bid + 1] = s1; partials[3 * ctx.bid + 2] = s2; }
+    if (ctx.last_block(counter)) {
+      T sigbar = block_total(ctx, partials, ctx.nblk, 3, scratch);
+      T aspbar = block_total(ctx, partials + 1, ctx.nblk, 3, scratch);
+      T dot = block_total(ctx, partials + 2, ctx.nblk, 3, scratch);
+      dot += block_total(ctx, p5_partials, n_p5, 1, scratch);
+      T sp = m.has_scaling ? block_total(ctx, p3_partials, n_p3, 2, scratch) : T(0);
+      if (ctx.tid == 0) {
+        if (m.has_flu) leaf(m.off_flu, scal_in[SC_SG] * m.flu_b, dot);
+        leaf(m.off_slp, scal_in[SC_UBL] * m.slp_b, dot);
+        if (m.has_dev) {
+          leaf(m.off_flx, sigbar * scal_in[SC_SIG] * m.flx_b, dot);
+          if (m.has_asp) leaf(m.off_asp, aspbar * scal_in[SC_ASP] * m.asp_b, dot);
+        }
+        leaf(m.off_zm, scal_in[SC_ABAR0] * m.V * scal_in[SC_Z] * m.zm_b, dot);
+        if (m.has_scaling) leaf(m.off_scl, sp * scl_factor, dot);
+        scal[SC_DOT] = dot;
+      }
+    }
+  }
+};
+
+// element functor for K <= 2 or no spectrum: nothing to scan
+template <class T> struct NoElem { NB_HD NB_INLINE Aff<T> get(long) const { return aff_id<T>(); } };
+
+}  // namespace nb

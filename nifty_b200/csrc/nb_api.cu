@@ -1,0 +1,411 @@
+// nifty_b200 -- C ABI (include/nifty_b200.h).  Compiled by nvcc for sm_100a into libniftyb200.so;
+// tests/emu compiles the same file with -DNB_EMU as plain C++ (sequential host execution of the
+// kernel bodies) to check host logic and index arithmetic where no GPU is available.
+#include "nb_model.cuh"
+#include "nb_vec.cuh"
+#include <limits>
+#include <memory>
+
+using namespace nb;
+
+struct nb200_plan { PlanBase* impl; };
+struct nb200_model { ModelBase* impl; nb200_plan* plan; int dtype; };
+struct nb200_lin { LinBase* impl; nb200_model* model; int dtype; };
+
+namespace nb {
+
+template <class T> void Model<T>::init(Plan<T>* plan_, const nb200_model_desc& d) {
+  P = plan_; plan = plan_;
+  const GridInfo& g = P->g;
+  std::memset(&am, 0, sizeof(am));
+  am.K = g.K; am.kind_power = d.kind_power; am.has_flu = d.has_fluctuations; am.has_asp = d.has_asperity;
+  am.has_dev = d.has_deviations && g.K > 2; am.has_scaling = d.has_scaling;
+  am.V = (T)g.V;
+  am.flu_a = (T)d.fluct_a; am.flu_b = (T)d.fluct_b; am.slp_a = (T)d.slope_a; am.slp_b = (T)d.slope_b;
+  am.flx_a = (T)d.flex_a; am.flx_b = (T)d.flex_b; am.asp_a = (T)d.asp_a; am.asp_b = (T)d.asp_b;
+  am.zm_a = (T)d.zeromode_a; am.zm_b = (T)d.zeromode_b; am.scl_a = (T)d.scaling_a; am.scl_b = (T)d.scaling_b;
+  am.off_flu = d.off_fluct; am.off_slp = d.off_slope; am.off_flx = d.off_flex; am.off_asp = d.off_asp;
+  am.off_spec = d.off_spectrum; am.off_zm = d.off_zeromode; am.off_xi = d.off_xi; am.off_scl = d.off_scaling;
+  am.L = d.latent_size;
+  if (d.has_deviations && g.K <= 2) throw Error{"nb200: has_deviations set but the grid has <= 2 unique modes"};
+  auto chk = [&](int64_t off, int64_t len, const char* nm) {
+    if (off < 0 || off + len > d.latent_size) throw Error{std::string("nb200: leaf offset out of range: ") + nm};
+  };
+  chk(d.off_xi, g.N, "xi"); chk(d.off_zeromode, 1, "zeromode"); chk(d.off_slope, 1, "loglogavgslope");
+  if (am.has_flu) chk(d.off_fluct, 1, "fluctuations");
+  if (am.has_dev) { chk(d.off_flex, 1, "flexibility"); chk(d.off_spectrum, 2 * (int64_t)(g.K - 2), "spectrum"); }
+  if (am.has_dev && am.has_asp) chk(d.off_asp, 1, "asperity");
+  if (am.has_scaling) chk(d.off_scaling, 1, "scaling");
+  offset_mean = (T)d.offset_mean;
+  std::vector<T> e(g.K), mu(g.K), dtv(g.logvol.size());
+  for (int b = 0; b < g.K; ++b) { e[b] = (T)g.rel[b]; mu[b] = (T)g.mult[b]; }
+  for (size_t j = 0; j < dtv.size(); ++j) dtv[j] = (T)g.logvol[j];
+  ell.upload(e); multT.upload(mu); dt.upload(dtv);
+  am.ell = ell.p; am.mult = multT.p; am.dt = dt.p;
+  nchunksK = (g.K + SCAN_CH - 1) / SCAN_CH;
+  nchunksJ = std::max(1, (g.K - 2 + SCAN_CH - 1) / SCAN_CH);
+  agg.alloc(nchunksK + 1); pre.alloc(2 * (size_t)nchunksK + 2); total.alloc(2);
+  du.alloc(g.K); gbuf.alloc(g.K);
+  size_t np = std::max<size_t>(3 * (size_t)nchunksK + 3, 2 * (size_t)P->seg_grid() + 2);
+  np = std::max<size_t>(np, 4 * 2048);
+  partials.alloc(np);
+  counters.alloc(16);
+  tmp_pos.alloc((size_t)g.N);
+  scratch_lin = new Lin<T>();
+  scratch_lin->init(this);
+}
+template <class T> Model<T>::~Model() { delete scratch_lin; }
+
+// ---- conjugate gradient driver ------------------------------------------------------------------
+template <class T> struct CgWork {
+  DevBuf<T> r, d, q, tm, cgs, partials;
+  DevBuf<int> cgi;
+  DevBuf<unsigned> counter;
+  long L = 0;
+  void ensure(long n) {
+    if (L == n) return;
+    r.alloc(n); d.alloc(n); q.alloc(n); tm.alloc(n); cgs.alloc(CG_NSCAL); partials.alloc(4 * 2048); cgi.alloc(CGI_NINT); counter.alloc(4);
+    L = n;
+  }
+};
+template <class T> CgWork<T>& cg_work() { static thread_local CgWork<T> w; return w; }
+
+template <class T>
+int cg_solve(Lin<T>* lin, Lin<T>* lin_b, stream_t st, const T* j, T* x, const nb200_cg_opts& o, nb200_cg_result* res) {
+  Model<T>& m = *lin->M;
+  const long L = m.am.L;
+  CgWork<T>& w = cg_work<T>();
+  w.ensure(L);
+  const int vgrid = (int)std::min<long>((L + 1023) / 1024, 148 * 8);
+  int norm_ord = o.norm_ord;
+  if (norm_ord != 0 && norm_ord != 1 && norm_ord != 2) return fail("nb200_cg_solve: norm_ord must be 1, 2 or 0 (inf)");
+  const long maxiter_fallback = 20 * L;
+  long miniter = o.miniter >= 0 ? o.miniter : std::min<long>(6, o.maxiter >= 0 ? o.maxiter : maxiter_fallback);
+  long maxiter = o.maxiter >= 0 ? o.maxiter : std::max<long>(std::min<long>(200, maxiter_fallback), miniter);
+  auto op = [&](const T* t, T* out) {
+    if (!lin_b) lin->metric(st, lin, t, out, true);
+    else { lin_b->metric(st, lin, t, w.tm.p, true); lin->metric(st, lin_b, w.tm.p, out, true); }
+  };
+  CgParams<T> p;
+  std::memset(&p, 0, sizeof(p));
+  p.n = L; p.pos = x; p.r = w.r.p; p.d = w.d.p; p.q = w.q.p; p.j = j; p.cgs = w.cgs.p; p.cgi = w.cgi.p;
+  p.partials = w.partials.p; p.counter = w.counter.p;
+  p.absdelta = o.absdelta >= 0 ? (T)o.absdelta : T(-1);
+  p.resnorm = o.resnorm >= 0 ? (T)o.resnorm : T(-1);
+  p.eps = T(6) * std::numeric_limits<T>::epsilon(); p.tiny = T(6) * std::numeric_limits<T>::min();
+  p.norm_ord = norm_ord; p.miniter = (int)miniter; p.raise_nonposdef = o.raise_nonposdef;
+  p.curv_ptr = lin_b ? w.cgs.p + CG_CURV : lin->scal.p + SC_DOT;
+  dev_zero(w.cgi.p, CGI_NINT * sizeof(int), st);
+  dev_zero(w.cgs.p, CG_NSCAL * sizeof(T), st);
+  if (o.absdelta < 0 && o.resnorm < 0) {
+    // resnorm = max(tol * norm(j), atol)  (conjugate_gradient.py:103-105); one-off host read
+    if (norm_ord != 2) return fail("nb200_cg_solve: default resnorm needs norm_ord=2 (pass resnorm explicitly)");
+    DotParams<T> dp; dp.n = L; dp.x = j; dp.y = j; dp.partials = w.partials.p; dp.counter = w.counter.p + 1; dp.out = w.cgs.p + CG_NORM;
+    launch<DotBody<T>>(vgrid, 256, 512, st, dp);
+    T jj = 0; d2h(&jj, w.cgs.p + CG_NORM, sizeof(T), st); stream_sync(st);
+    p.resnorm = (T)std::max((double)o.tol * std::sqrt((double)jj), (double)o.atol);
+  }
+  int nfev = 0;
+  if (o.x0_is_zero) { p.mode = CGM_INIT_ZERO; p.iter = 0; launch<CgStepBody<T>>(vgrid, 256, 512, st, p); }
+  else { op(x, w.q.p); ++nfev; p.mode = CGM_INIT; p.iter = 0; launch<CgStepBody<T>>(vgrid, 256, 512, st, p); }
+  int host_cgi[CGI_NINT] = {0};
+  const int every = std::max(1, o.check_every);
+  long i = 0;
+  d2h(host_cgi, w.cgi.p, sizeof(host_cgi), st); stream_sync(st);
+  if (host_cgi[CGI_STATUS] == CGS_RUNNING) {
+    for (i = 1; i <= maxiter; ++i) {
+      op(w.d.p, w.q.p);
+      if (lin_b) {
+        DotParams<T> dp; dp.n = L; dp.x = w.d.p; dp.y = w.q.p; dp.partials = w.partials.p; dp.counter = w.counter.p + 1; dp.out = w.cgs.p + CG_CURV;
+        launch<DotBody<T>>(vgrid, 256, 512, st, dp);
+      }
+      p.iter = (int)i;
+      if (i % 20 == 0) {   // N_RESET (conjugate_gradient.py:17,168-172)
+        p.mode = CGM_POS_ONLY; launch<CgStepBody<T>>(vgrid, 256, 512, st, p);
+        op(x, w.q.p);
+        p.mode = CGM_RESID; launch<CgStepBody<T>>(vgrid, 256, 512, st, p);
+      } else {
+        p.mode = CGM_NORMAL; launch<CgStepBody<T>>(vgrid, 256, 512, st, p);
+      }
+      launch<CgDirBody<T>>(vgrid, 256, 0, st, p);
+      if (i % every == 0 || i == maxiter) {
+        d2h(host_cgi, w.cgi.p, sizeof(host_cgi), st); stream_sync(st);
+        if (host_cgi[CGI_STATUS] != CGS_RUNNING) break;
+      }
+    }
+  }
+  T hs[CG_NSCAL];
+  d2h(hs, w.cgs.p, sizeof(hs), st); stream_sync(st);
+  int nit, info, err = 0;
+  if (host_cgi[CGI_STATUS] != CGS_RUNNING) { nit = host_cgi[CGI_ITER]; info = host_cgi[CGI_INFO]; err = host_cgi[CGI_ERROR]; }
+  else { nit = (int)maxiter; info = (int)maxiter; }
+  // POS_ONLY + bad curvature on a reset iteration leaves the status to the following RESID launch; covered above
+  res->info = info; res->nit = nit; res->nfev = nfev + nit + nit / 20; res->error = err;
+  res->energy = (double)hs[CG_ENERGY]; res->gamma = (double)hs[CG_GAMMA];
+  return 0;
+}
+
+}  // namespace nb
+
+// ---- dispatch helpers ------------------------------------------------------------------------------
+#define NB_TRY try {
+#define NB_CATCH                                             \
+  }                                                          \
+  catch (const nb::Error& e) { return nb::fail(e.msg); }     \
+  catch (const std::exception& e) { return nb::fail(e.what()); } \
+  catch (...) { return nb::fail("nb200: unknown error"); }
+
+template <class F64, class F32> static int by_dtype(int dtype, F64 f64, F32 f32) { return dtype == 1 ? f64() : f32(); }
+#define NB_DISPATCH(dtype, TT, ...)                                 \
+  if ((dtype) == 1) { typedef double TT; __VA_ARGS__ } else { typedef float TT; __VA_ARGS__ }
+
+extern "C" {
+
+const char* nb200_last_error(void) { return nb::last_error_ref().c_str(); }
+int nb200_version(void) { return 100; }
+
+int nb200_plan_create(nb200_plan** plan, int device, int ndim, const int64_t* shape_host, const double* distances_host,
+                      int dtype, int hartley_convention) {
+  NB_TRY
+  if (!plan) return fail("nb200_plan_create: null output");
+  if (dtype != 0 && dtype != 1) return fail("nb200_plan_create: dtype must be 0 (float32) or 1 (float64)");
+  if (hartley_convention != 0 && hartley_convention != 1) return fail("nb200_plan_create: invalid hartley convention");
+#ifndef NB_EMU
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device)
+    return fail("nb200_plan_create: no CUDA device available (there is no CPU fallback)");
+#endif
+  std::unique_ptr<nb200_plan> h(new nb200_plan{nullptr});
+  NB_DISPATCH(dtype, TT, { auto* p = new Plan<TT>(); h->impl = p; p->init(device, ndim, shape_host, distances_host, hartley_convention); })
+  *plan = h.release();
+  return 0;
+  NB_CATCH
+}
+void nb200_plan_destroy(nb200_plan* plan) { if (plan) { delete plan->impl; delete plan; } }
+int64_t nb200_plan_num_modes(const nb200_plan* plan) { return plan->impl->g.K; }
+int64_t nb200_plan_size(const nb200_plan* plan) { return plan->impl->g.N; }
+double nb200_plan_total_volume(const nb200_plan* plan) { return plan->impl->g.V; }
+int nb200_plan_mode_lengths(const nb200_plan* plan, double* out) { const auto& g = plan->impl->g; std::copy(g.um.begin(), g.um.end(), out); return 0; }
+int nb200_plan_mode_multiplicity(const nb200_plan* plan, int64_t* out) { const auto& g = plan->impl->g; std::copy(g.mult.begin(), g.mult.end(), out); return 0; }
+int nb200_plan_relative_log_mode_lengths(const nb200_plan* plan, double* out) { const auto& g = plan->impl->g; std::copy(g.rel.begin(), g.rel.end(), out); return 0; }
+int nb200_plan_log_volume(const nb200_plan* plan, double* out) { const auto& g = plan->impl->g; std::copy(g.logvol.begin(), g.logvol.end(), out); return 0; }
+int nb200_plan_power_distributor(const nb200_plan* plan, int32_t* out) {
+  const auto& g = plan->impl->g;
+  int64_t q = 0;
+  for (int i0 = 0; i0 < g.n0; ++i0)
+    for (int im = 0; im < g.nm; ++im)
+      for (int il = 0; il < g.nl; ++il, ++q) {
+        int f0 = std::min(i0, g.n0 - i0), fm = std::min(im, g.nm - im), fl = std::min(il, g.nl - il);
+        out[q] = g.idxf[((size_t)f0 * (g.hm + 1) + fm) * (g.hl + 1) + fl];
+      }
+  return 0;
+}
+
+int nb200_hartley(nb200_plan* plan, void* stream, const void* in, void* out) {
+  NB_TRY
+  NB_DISPATCH(plan->impl->dtype, TT, { static_cast<Plan<TT>*>(plan->impl)->hartley((stream_t)stream, (const TT*)in, (TT*)out); })
+  return 0;
+  NB_CATCH
+}
+int nb200_cf_apply(nb200_plan* plan, void* stream, const void* amp, const void* xi, double offset, void* out) {
+  NB_TRY
+  NB_DISPATCH(plan->impl->dtype, TT, { static_cast<Plan<TT>*>(plan->impl)->cf_apply((stream_t)stream, (const TT*)amp, (const TT*)xi, (TT)offset, (TT*)out); })
+  return 0;
+  NB_CATCH
+}
+int nb200_cf_apply_adjoint(nb200_plan* plan, void* stream, const void* amp, const void* xi, const void* cot, void* xi_bar, void* amp_bar) {
+  NB_TRY
+  if ((xi == nullptr) != (amp_bar == nullptr)) return fail("nb200_cf_apply_adjoint: xi and amp_bar must be given together");
+  NB_DISPATCH(plan->impl->dtype, TT, {
+    Plan<TT>& P = *static_cast<Plan<TT>*>(plan->impl);
+    stream_t st = (stream_t)stream;
+    PointOp<TT> op = P.make_op(PM_LOAD); op.natural = 1; op.in_pos = (const TT*)cot;
+    P.template run_p3<false, true>(st, op);
+    P.run_pc(st, true);
+    EpiAdjoint<TT> e; e.out = (TT*)xi_bar; e.add = nullptr; e.xi = (const TT*)xi; e.idxf = P.idxf.p; e.amp = (const TT*)amp;
+    e.W = xi ? P.W.p : nullptr; e.invV = TT(1.0 / P.g.V); e.partials = nullptr;
+    P.run_p5(st, e);
+    if (amp_bar) {
+      SegSumParams<TT> ps; std::memset(&ps, 0, sizeof(ps));
+      ps.m.K = P.g.K; ps.W = P.W.p; ps.order = P.w_order.p; ps.offs = P.w_offs.p; ps.abar = (TT*)amp_bar; ps.lg_lpb = P.seg_lg_lpb;
+      launch<SegSumBody<TT>>(P.seg_grid(), 256, (256 + 64) * sizeof(TT), st, ps);
+    }
+  })
+  return 0;
+  NB_CATCH
+}
+
+int nb200_model_create(nb200_model** model, nb200_plan* plan, const nb200_model_desc* d) {
+  NB_TRY
+  if (!model || !plan || !d) return fail("nb200_model_create: null argument");
+  std::unique_ptr<nb200_model> h(new nb200_model{nullptr, plan, plan->impl->dtype});
+  NB_DISPATCH(h->dtype, TT, { auto* m = new Model<TT>(); h->impl = m; m->init(static_cast<Plan<TT>*>(plan->impl), *d); })
+  *model = h.release();
+  return 0;
+  NB_CATCH
+}
+void nb200_model_destroy(nb200_model* model) { if (model) { delete model->impl; delete model; } }
+
+int nb200_model_set_likelihood(nb200_model* model, void* stream, int kind, int nonlinearity, const void* data,
+                               double noise_cov_inv_scalar, const void* noise_cov_inv_array) {
+  NB_TRY
+  if (kind != 0 && kind != 1) return fail("nb200_model_set_likelihood: kind must be 0 (Gaussian) or 1 (Poissonian)");
+  if (nonlinearity != 0 && nonlinearity != 1) return fail("nb200_model_set_likelihood: nonlinearity must be 0 or 1");
+  NB_DISPATCH(model->dtype, TT, {
+    Model<TT>& m = *static_cast<Model<TT>*>(model->impl);
+    if (nonlinearity == 0 && m.am.has_scaling) return fail("nb200: scaling requires the exp non-linearity");
+    stream_t st = (stream_t)stream;
+    m.lh_kind = kind; m.nl_exp = nonlinearity; m.w_scalar = (TT)noise_cov_inv_scalar;
+    m.data.alloc((size_t)m.P->g.N);
+    if (data) m.P->run_rev(st, (const TT*)data, m.data.p, true);
+    m.has_w_arr = noise_cov_inv_array != nullptr;
+    if (m.has_w_arr) { m.w_arr.alloc((size_t)m.P->g.N); m.P->run_rev(st, (const TT*)noise_cov_inv_array, m.w_arr.p, true); }
+    stream_sync(st);
+    m.have_lh = true;
+  })
+  return 0;
+  NB_CATCH
+}
+
+int nb200_lin_create(nb200_lin** lin, nb200_model* model) {
+  NB_TRY
+  std::unique_ptr<nb200_lin> h(new nb200_lin{nullptr, model, model->dtype});
+  NB_DISPATCH(h->dtype, TT, { auto* l = new Lin<TT>(); h->impl = l; l->init(static_cast<Model<TT>*>(model->impl)); })
+  *lin = h.release();
+  return 0;
+  NB_CATCH
+}
+void nb200_lin_destroy(nb200_lin* lin) { if (lin) { delete lin->impl; delete lin; } }
+
+int nb200_lin_update(nb200_lin* lin, void* stream, const void* pos, void* grad, int add_prior) {
+  NB_TRY
+  NB_DISPATCH(lin->dtype, TT, { static_cast<Lin<TT>*>(lin->impl)->update((stream_t)stream, (const TT*)pos, (TT*)grad, add_prior != 0); })
+  return 0;
+  NB_CATCH
+}
+int nb200_lin_energy(nb200_lin* lin, void* stream, double* energy_host) {
+  NB_TRY
+  NB_DISPATCH(lin->dtype, TT, {
+    Lin<TT>* l = static_cast<Lin<TT>*>(lin->impl);
+    TT e = 0; d2h(&e, l->scal.p + SC_ENERGY, sizeof(TT), (stream_t)stream); stream_sync((stream_t)stream);
+    *energy_host = (double)e;
+  })
+  return 0;
+  NB_CATCH
+}
+int nb200_lin_amplitude(nb200_lin* lin, void* stream, void* amp_out) {
+  NB_TRY
+  NB_DISPATCH(lin->dtype, TT, {
+    Lin<TT>* l = static_cast<Lin<TT>*>(lin->impl);
+    d2d(amp_out, l->amp.p, (size_t)l->M->am.K * sizeof(TT), (stream_t)stream);
+  })
+  return 0;
+  NB_CATCH
+}
+int nb200_lin_signal(nb200_lin* lin, void* stream, void* out) {
+  NB_TRY
+  NB_DISPATCH(lin->dtype, TT, { static_cast<Lin<TT>*>(lin->impl)->posmap((stream_t)stream, PMAP_COPY, (TT*)out); })
+  return 0;
+  NB_CATCH
+}
+int nb200_cf_forward(nb200_model* model, void* stream, const void* pos, void* field_out) {
+  NB_TRY
+  NB_DISPATCH(model->dtype, TT, {
+    Model<TT>& m = *static_cast<Model<TT>*>(model->impl);
+    Lin<TT>& l = *m.scratch_lin;
+    stream_t st = (stream_t)stream;
+    d2d(l.pos.p, pos, (size_t)m.am.L * sizeof(TT), st);
+    l.amp_forward(st);
+    m.P->cf_apply(st, l.amp.p, l.pos.p + m.am.off_xi, m.offset_mean, (TT*)field_out);
+  })
+  return 0;
+  NB_CATCH
+}
+int nb200_metric(nb200_lin* lin, void* stream, const void* t, void* out, int add_identity) {
+  NB_TRY
+  NB_DISPATCH(lin->dtype, TT, { Lin<TT>* l = static_cast<Lin<TT>*>(lin->impl); l->metric((stream_t)stream, l, (const TT*)t, (TT*)out, add_identity != 0); })
+  return 0;
+  NB_CATCH
+}
+int nb200_metric_pair(nb200_lin* lin_a, nb200_lin* lin_b, void* stream, const void* t, void* out, int add_identity) {
+  NB_TRY
+  if (lin_a->model != lin_b->model) return fail("nb200_metric_pair: linearisations of different models");
+  NB_DISPATCH(lin_a->dtype, TT, {
+    static_cast<Lin<TT>*>(lin_a->impl)->metric((stream_t)stream, static_cast<Lin<TT>*>(lin_b->impl), (const TT*)t, (TT*)out, add_identity != 0);
+  })
+  return 0;
+  NB_CATCH
+}
+int nb200_rsm(nb200_lin* lin, void* stream, const void* t, void* out_pos, int scaled) {
+  NB_TRY
+  NB_DISPATCH(lin->dtype, TT, { static_cast<Lin<TT>*>(lin->impl)->rsm((stream_t)stream, (const TT*)t, (TT*)out_pos, scaled != 0); })
+  return 0;
+  NB_CATCH
+}
+int nb200_lsm(nb200_lin* lin, void* stream, const void* u_pos, void* out, int scaled) {
+  NB_TRY
+  NB_DISPATCH(lin->dtype, TT, { static_cast<Lin<TT>*>(lin->impl)->lsm((stream_t)stream, (const TT*)u_pos, (TT*)out, scaled != 0); })
+  return 0;
+  NB_CATCH
+}
+int nb200_transformation(nb200_lin* lin, void* stream, void* out_pos) {
+  NB_TRY
+  NB_DISPATCH(lin->dtype, TT, { static_cast<Lin<TT>*>(lin->impl)->posmap((stream_t)stream, PMAP_TRAFO, (TT*)out_pos); })
+  return 0;
+  NB_CATCH
+}
+int nb200_normalized_residual(nb200_lin* lin, void* stream, void* out_pos) {
+  NB_TRY
+  NB_DISPATCH(lin->dtype, TT, { static_cast<Lin<TT>*>(lin->impl)->posmap((stream_t)stream, PMAP_NRES, (TT*)out_pos); })
+  return 0;
+  NB_CATCH
+}
+
+void nb200_cg_default_opts(nb200_cg_opts* o) {
+  o->absdelta = -1; o->resnorm = -1; o->tol = 1e-5; o->atol = 0; o->norm_ord = 2; o->miniter = -1; o->maxiter = -1;
+  o->raise_nonposdef = 1; o->check_every = 4; o->x0_is_zero = 0;
+}
+int nb200_cg_solve(nb200_lin* lin, nb200_lin* lin_b, void* stream, const void* j, void* x, const nb200_cg_opts* opts,
+                   nb200_cg_result* result_host) {
+  NB_TRY
+  if (!lin || !j || !x || !opts || !result_host) return fail("nb200_cg_solve: null argument");
+  if (lin_b && lin_b->model != lin->model) return fail("nb200_cg_solve: linearisations of different models");
+  NB_DISPATCH(lin->dtype, TT, {
+    return cg_solve<TT>(static_cast<Lin<TT>*>(lin->impl), lin_b ? static_cast<Lin<TT>*>(lin_b->impl) : nullptr, (stream_t)stream,
+                        (const TT*)j, (TT*)x, *opts, result_host);
+  })
+  NB_CATCH
+}
+
+int nb200_vec_axpby(nb200_plan* plan, void* stream, int64_t n, double a, const void* x, double b, const void* y, void* out) {
+  NB_TRY
+  NB_DISPATCH(plan->impl->dtype, TT, {
+    AxpbyParams<TT> p; p.n = n; p.a = (TT)a; p.b = (TT)b; p.x = (const TT*)x; p.y = (const TT*)y; p.out = (TT*)out;
+    launch<AxpbyBody<TT>>((int)std::min<int64_t>((n + 1023) / 1024 + 1, 148 * 8), 256, 0, (stream_t)stream, p);
+  })
+  return 0;
+  NB_CATCH
+}
+int nb200_vec_dot(nb200_plan* plan, void* stream, int64_t n, const void* x, const void* y, double* out_host) {
+  NB_TRY
+  NB_DISPATCH(plan->impl->dtype, TT, {
+    CgWork<TT>& w = cg_work<TT>();
+    if (w.partials.n == 0) { w.partials.alloc(4 * 2048); w.counter.alloc(4); w.cgs.alloc(CG_NSCAL); w.cgi.alloc(CGI_NINT); }
+    DotParams<TT> dp; dp.n = n; dp.x = (const TT*)x; dp.y = (const TT*)y; dp.partials = w.partials.p; dp.counter = w.counter.p + 1; dp.out = w.cgs.p + CG_NORM;
+    launch<DotBody<TT>>((int)std::min<int64_t>((n + 1023) / 1024 + 1, 148 * 8), 256, 512, (stream_t)stream, dp);
+    TT v = 0; d2h(&v, w.cgs.p + CG_NORM, sizeof(TT), (stream_t)stream); stream_sync((stream_t)stream);
+    *out_host = (double)v;
+  })
+  return 0;
+  NB_CATCH
+}
+
+unsigned long long nb200_launch_count(void) {
+#ifdef NB_EMU
+  return 0;
+#else
+  return nb::launch_counter();
+#endif
+}
+
+}  // extern "C"

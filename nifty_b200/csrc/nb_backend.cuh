@@ -1,0 +1,109 @@
+// nifty_b200 -- launch / memory shims.  CUDA build: real kernels, cudaMalloc, streams.
+// tests/emu build (-DNB_EMU): the same bodies run block after block on the host (see nb_common.cuh).
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "nb_common.cuh"
+
+namespace nb {
+
+struct Error { std::string msg; };
+inline std::string& last_error_ref() { static thread_local std::string s; return s; }
+inline int fail(const std::string& m) { last_error_ref() = m; return 1; }
+
+#ifdef NB_EMU
+typedef void* stream_t;
+inline int dev_set(int) { return 0; }
+inline void* dev_alloc(size_t bytes) { void* p = std::calloc(bytes ? bytes : 1, 1); if (!p) throw Error{"out of host memory (emulator)"}; return p; }
+inline void dev_free(void* p) { std::free(p); }
+inline void h2d(void* d, const void* h, size_t n, stream_t) { std::memcpy(d, h, n); }
+inline void d2h(void* h, const void* d, size_t n, stream_t) { std::memcpy(h, d, n); }
+inline void d2d(void* d, const void* s, size_t n, stream_t) { std::memmove(d, s, n); }
+inline void dev_zero(void* d, size_t n, stream_t) { std::memset(d, 0, n); }
+inline void stream_sync(stream_t) {}
+inline size_t max_smem_per_block() { return 227 * 1024; }
+inline int sm_count() { return 148; }
+
+template <class Body>
+inline void launch(int grid, int block, size_t smem, stream_t, const typename Body::Params& p) {
+  (void)block;
+  std::vector<char> sm(smem + 4096);
+  for (int b = 0; b < grid; ++b) {
+    Ctx ctx{0, 1, b, grid};
+    Body::run(ctx, p, sm.data());
+  }
+}
+#else
+typedef cudaStream_t stream_t;
+#define NB_CUDA_CHECK(expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess) throw ::nb::Error{std::string(#expr) + ": " + cudaGetErrorString(e_)}; \
+  } while (0)
+
+inline int dev_set(int d) { NB_CUDA_CHECK(cudaSetDevice(d)); return 0; }
+inline void* dev_alloc(size_t bytes) {
+  void* p = nullptr;
+  NB_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1));
+  NB_CUDA_CHECK(cudaMemset(p, 0, bytes ? bytes : 1));
+  return p;
+}
+inline void dev_free(void* p) { if (p) cudaFree(p); }
+inline void h2d(void* d, const void* h, size_t n, stream_t s) { NB_CUDA_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
+inline void d2h(void* h, const void* d, size_t n, stream_t s) { NB_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
+inline void d2d(void* d, const void* s_, size_t n, stream_t s) { NB_CUDA_CHECK(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s)); }
+inline void dev_zero(void* d, size_t n, stream_t s) { NB_CUDA_CHECK(cudaMemsetAsync(d, 0, n, s)); }
+inline void stream_sync(stream_t s) { NB_CUDA_CHECK(cudaStreamSynchronize(s)); }
+inline size_t max_smem_per_block() {
+  int dev = 0, v = 0;
+  NB_CUDA_CHECK(cudaGetDevice(&dev));
+  NB_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  return (size_t)v;
+}
+inline int sm_count() {
+  int dev = 0, v = 0;
+  NB_CUDA_CHECK(cudaGetDevice(&dev));
+  NB_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+  return v;
+}
+
+template <class Body>
+__global__ void __launch_bounds__(256) nb_kernel(const __grid_constant__ typename Body::Params p) {
+  extern __shared__ __align__(16) unsigned char nb_smem[];
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  Body::run(ctx, p, nb_smem);
+}
+
+// number of kernel launches issued by this library (bench.py reports it as gpu_launches)
+inline unsigned long long& launch_counter() { static unsigned long long c = 0; return c; }
+
+template <class Body>
+inline void launch(int grid, int block, size_t smem, stream_t s, const typename Body::Params& p) {
+  static size_t configured[64] = {0};
+  int dev = 0;
+  NB_CUDA_CHECK(cudaGetDevice(&dev));
+  smem += 512;   // reduction scratch behind the line buffers
+  if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+    NB_CUDA_CHECK(cudaFuncSetAttribute(nb_kernel<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = smem;
+  }
+  nb_kernel<Body><<<grid, block, smem, s>>>(p);
+  NB_CUDA_CHECK(cudaGetLastError());
+  ++launch_counter();
+}
+#endif
+
+template <class T> struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { dev_free(p); }
+  void alloc(size_t count) { dev_free(p); p = nullptr; p = reinterpret_cast<T*>(dev_alloc(count * sizeof(T))); n = count; }
+  void upload(const std::vector<T>& h, stream_t s = 0) { alloc(h.size()); if (!h.empty()) { h2d(p, h.data(), h.size() * sizeof(T), s); stream_sync(s); } }
+};
+
+}  // namespace nb

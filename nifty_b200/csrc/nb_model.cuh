@@ -1,0 +1,225 @@
+// nifty_b200 -- model (amplitude priors + likelihood) and linearisation objects; operator launch
+// sequences for linearise / value+gradient / metric / sqrt-metric applications.
+#pragma once
+#include "nb_plan.cuh"
+#include "../../include/nifty_b200.h"
+
+namespace nb {
+
+// small helper kernels -------------------------------------------------------------------------
+template <class T> struct ReduceColsParams { const T* partials; int n, ncol; T* out0; T* out1; };
+template <class T> struct ReduceColsBody {
+  typedef ReduceColsParams<T> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    T a0 = 0, a1 = 0;
+    NB_FOR(ctx, i, p.n) { a0 += p.partials[p.ncol * i]; if (p.ncol > 1) a1 += p.partials[p.ncol * i + 1]; }
+    a0 = ctx.block_sum(a0, smem);
+    a1 = ctx.block_sum(a1, smem);
+    if (ctx.tid == 0) { if (p.out0) *p.out0 = a0; if (p.out1) *p.out1 = a1; }
+  }
+};
+
+enum PosMapMode { PMAP_TRAFO = 0, PMAP_NRES = 1, PMAP_COPY = 2 };
+template <class T> struct PosMapParams {
+  int mode, lh_kind; long n; const T* s; const T* data; T w_scalar; const T* w_arr; T* out;
+};
+template <class T> struct PosMapBody {
+  typedef PosMapParams<T> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void*) {
+    for (long i = (long)ctx.bid * ctx.nthr + ctx.tid; i < p.n; i += (long)ctx.nblk * ctx.nthr) {
+      T s = p.s[i], r;
+      if (p.mode == PMAP_COPY) r = s;
+      else if (p.lh_kind == LH_GAUSS) {
+        T sw = nb_sqrt(p.w_arr ? p.w_arr[i] : p.w_scalar);
+        r = (p.mode == PMAP_TRAFO) ? sw * s : sw * ((p.data ? p.data[i] : T(0)) - s);
+      } else {
+        r = (p.mode == PMAP_TRAFO) ? T(2) * nb_sqrt(s) : ((p.data ? p.data[i] : T(0)) - s) / nb_sqrt(s);
+      }
+      p.out[i] = r;
+    }
+  }
+};
+
+struct ModelBase { PlanBase* plan = nullptr; virtual ~ModelBase() {} };
+struct LinBase { ModelBase* model = nullptr; virtual ~LinBase() {} };
+
+template <class T> struct Lin;
+
+template <class T> struct Model : ModelBase {
+  Plan<T>* P = nullptr;
+  AmpModel<T> am;
+  T offset_mean = 0;
+  int lh_kind = LH_GAUSS, nl_exp = 1;
+  bool have_lh = false;
+  T w_scalar = 1;
+  DevBuf<T> ell, multT, dt, data, w_arr;
+  bool has_w_arr = false;
+  // chain workspaces
+  DevBuf<Aff<T>> agg;
+  DevBuf<T> pre, total, du, gbuf, partials, tmp_pos;
+  DevBuf<unsigned> counters;
+  int nchunksK = 1, nchunksJ = 1;
+  Lin<T>* scratch_lin = nullptr;
+
+  void init(Plan<T>* plan_, const nb200_model_desc& d);
+  ~Model();
+
+  size_t scan_smem() const { return scan_smem_bytes<T>(); }
+};
+
+template <class T> struct Lin : LinBase {
+  Model<T>* M = nullptr;
+  DevBuf<T> pos, amp, wS, Pb, s, jl, scal;
+  bool valid = false;
+
+  void init(Model<T>* m) {
+    M = m; model = m;
+    const GridInfo& g = m->P->g;
+    pos.alloc((size_t)m->am.L); amp.alloc(g.K); wS.alloc(g.K); Pb.alloc(g.K);
+    s.alloc((size_t)g.N); jl.alloc((size_t)g.N); scal.alloc(SC_COUNT);
+  }
+
+  // forward amplitude chain at this->pos
+  void amp_forward(stream_t st) {
+    Model<T>& m = *M; const int K = m.am.K;
+    FwdElem<T> el; el.m = m.am; el.pos = pos.p;
+    if (m.am.has_dev) {
+      ScanAggParams<T, FwdElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p;
+      launch<ScanAggBody<T, FwdElem<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
+      ScanTopParams<T> pt; pt.nchunks = m.nchunksK; pt.agg = m.agg.p; pt.pre = m.pre.p; pt.total = m.total.p;
+      launch<ScanTopBody<T>>(1, 32, 0, st, pt);
+    }
+    FwdOut<T> fo; fo.m = m.am; fo.pos = pos.p; fo.total = m.total.p; fo.P = Pb.p; fo.partials = m.partials.p;
+    fo.counter = m.counters.p; fo.scal = scal.p;
+    ScanApplyParams<T, FwdElem<T>, FwdOut<T>> pc; pc.n = K; pc.elem = el; pc.out = fo; pc.pre = m.am.has_dev ? m.pre.p : nullptr;
+    launch<ScanApplyBody<T, FwdElem<T>, FwdOut<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
+    AmpTabParams<T> pt2; pt2.m = m.am; pt2.P = Pb.p; pt2.amp = amp.p; pt2.wS = wS.p; pt2.partials = m.partials.p;
+    pt2.counter = m.counters.p + 1; pt2.scal = scal.p;
+    launch<AmpTabBody<T>>(m.nchunksK, SCAN_NT, 512, st, pt2);
+  }
+
+  // tangent chain: du table + (cj, da0) scalars for ProMetric
+  void amp_tangent(stream_t st, const T* t) {
+    Model<T>& m = *M; const int K = m.am.K;
+    JvpElem<T> el; el.m = m.am; el.pos = pos.p; el.t = t; el.scal = scal.p;
+    if (m.am.has_dev) {
+      ScanAggParams<T, JvpElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p;
+      launch<ScanAggBody<T, JvpElem<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
+      ScanTopParams<T> pt; pt.nchunks = m.nchunksK; pt.agg = m.agg.p; pt.pre = m.pre.p; pt.total = m.total.p;
+      launch<ScanTopBody<T>>(1, 32, 0, st, pt);
+    }
+    JvpOut<T> jo; jo.m = m.am; jo.pos = pos.p; jo.t = t; jo.total = m.total.p; jo.wS = wS.p; jo.du = m.du.p;
+    jo.partials = m.partials.p; jo.counter = m.counters.p + 2; jo.scal = scal.p;
+    ScanApplyParams<T, JvpElem<T>, JvpOut<T>> pc; pc.n = K; pc.elem = el; pc.out = jo; pc.pre = m.am.has_dev ? m.pre.p : nullptr;
+    launch<ScanApplyBody<T, JvpElem<T>, JvpOut<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
+  }
+  ProMetric<T> pro_metric(const T* t) const {
+    const Model<T>& m = *M;
+    ProMetric<T> pro; pro.xi = pos.p + m.am.off_xi; pro.t = t + m.am.off_xi; pro.idxf = m.P->idxf.p; pro.amp = amp.p;
+    pro.du = m.du.p; pro.scal = scal.p + SC_CJ; pro.kappa = m.am.kind_power ? T(0.5) : T(1); pro.fg = m.P->fold_geom();
+    return pro;
+  }
+
+  // cotangent chain after P5 filled W: segment sum, reverse scan, scalar leaves, dot product
+  void amp_cotangent(stream_t st, T* out, const T* add, int p3_col, T scl_factor, bool use_p5_dot) {
+    Model<T>& m = *M; Plan<T>& P = *m.P; const int K = m.am.K;
+    SegSumParams<T> ps; ps.m = m.am; ps.W = P.W.p; ps.order = P.w_order.p; ps.offs = P.w_offs.p; ps.amp = amp.p;
+    ps.g = m.gbuf.p; ps.abar = nullptr; ps.partials = m.partials.p; ps.counter = m.counters.p + 3; ps.scal = scal.p;
+    ps.lg_lpb = P.seg_lg_lpb;
+    launch<SegSumBody<T>>(P.seg_grid(), 256, (256 + 64) * sizeof(T), st, ps);
+    const long nj = m.am.has_dev ? (long)K - 2 : 0;
+    VjpOut<T> vo; vo.m = m.am; vo.pos = pos.p; vo.g = m.gbuf.p; vo.wS = wS.p; vo.scal_in = scal.p; vo.out = out; vo.add = add;
+    vo.partials = m.partials.p; vo.counter = m.counters.p + 4; vo.scal = scal.p;
+    vo.p3_partials = P.p3part.p + p3_col; vo.n_p3 = P.c3.grid;
+    vo.p5_partials = P.p5part.p; vo.n_p5 = use_p5_dot ? P.c5.grid : 0; vo.scl_factor = scl_factor;
+    if (nj > 0) {
+      VjpElem<T> el; el.m = m.am; el.g = m.gbuf.p; el.wS = wS.p; el.scal = scal.p;
+      ScanAggParams<T, VjpElem<T>> pa; pa.n = nj; pa.elem = el; pa.agg = m.agg.p;
+      launch<ScanAggBody<T, VjpElem<T>>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pa);
+      ScanTopParams<T> pt; pt.nchunks = m.nchunksJ; pt.agg = m.agg.p; pt.pre = m.pre.p; pt.total = m.total.p;
+      launch<ScanTopBody<T>>(1, 32, 0, st, pt);
+      ScanApplyParams<T, VjpElem<T>, VjpOut<T>> pc; pc.n = nj; pc.elem = el; pc.out = vo; pc.pre = m.pre.p;
+      launch<ScanApplyBody<T, VjpElem<T>, VjpOut<T>>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pc);
+    } else {
+      ScanApplyParams<T, NoElem<T>, VjpOut<T>> pc; pc.n = 0; pc.out = vo; pc.pre = nullptr;
+      launch<ScanApplyBody<T, NoElem<T>, VjpOut<T>>>(1, SCAN_NT, m.scan_smem(), st, pc);
+    }
+  }
+  EpiAdjoint<T> epi_adjoint(T* out, const T* add, bool want_dot) const {
+    const Model<T>& m = *M;
+    EpiAdjoint<T> e; e.out = out + m.am.off_xi; e.add = add ? add + m.am.off_xi : nullptr; e.xi = pos.p + m.am.off_xi;
+    e.idxf = m.P->idxf.p; e.amp = amp.p; e.W = m.P->W.p; e.invV = T(1.0 / m.P->g.V);
+    e.partials = want_dot ? m.P->p5part.p : nullptr;
+    return e;
+  }
+
+  void update(stream_t st, const T* pos_in, T* grad, bool add_prior) {
+    Model<T>& m = *M; Plan<T>& P = *m.P;
+    if (!m.have_lh) throw Error{"nb200: likelihood not set on this model"};
+    d2d(pos.p, pos_in, (size_t)m.am.L * sizeof(T), st);
+    amp_forward(st);
+    ProAmp<T> pro; pro.xi = pos.p + m.am.off_xi; pro.idxf = P.idxf.p; pro.amp = amp.p; pro.fg = P.fold_geom();
+    P.run_p1(st, pro); P.run_pc(st, false);
+    PointOp<T> op = P.make_op(PM_LINEARIZE);
+    op.invV = T(1.0 / P.g.V); op.offset = m.offset_mean; op.sc_ptr = scal.p + SC_SCALING;
+    op.lh_kind = m.lh_kind; op.nl_exp = m.nl_exp; op.data = m.data.p; op.w_scalar = m.w_scalar;
+    op.w_arr = m.has_w_arr ? m.w_arr.p : nullptr; op.s_out = s.p; op.jl_out = jl.p; op.partials = P.p3part.p;
+    if (grad) P.template run_p3<true, true>(st, op); else P.template run_p3<true, false>(st, op);
+    ReduceColsParams<T> pr; pr.partials = P.p3part.p; pr.n = P.c3.grid; pr.ncol = 2;
+    pr.out0 = scal.p + SC_ENERGY; pr.out1 = scal.p + SC_SUMCOT;
+    launch<ReduceColsBody<T>>(1, 256, 512, st, pr);
+    if (grad) {
+      P.run_pc(st, true);
+      P.run_p5(st, epi_adjoint(grad, add_prior ? pos.p : nullptr, false));
+      amp_cotangent(st, grad, add_prior ? pos.p : nullptr, 1, m.am.scl_b, false);
+    }
+    valid = true;
+  }
+
+  // out = J_a^T l_a l_b J_b t (+ t); this == lin_a (cotangent side), b == tangent side
+  void metric(stream_t st, Lin<T>* b, const T* t, T* out, bool add_identity) {
+    Model<T>& m = *M; Plan<T>& P = *m.P;
+    if (!valid || !b->valid) throw Error{"nb200: linearisation not initialised (call nb200_lin_update)"};
+    b->amp_tangent(st, t);
+    P.run_p1(st, b->pro_metric(t)); P.run_pc(st, false);
+    PointOp<T> op = P.make_op(PM_METRIC);
+    op.invV = T(1.0 / P.g.V); op.jl_a = jl.p; op.jl_b = b->jl.p; op.partials = P.p3part.p;
+    if (m.am.has_scaling) { op.cshift_ptr = t + m.am.off_scl; op.cshift_scale = m.am.scl_b; }
+    P.template run_p3<true, true>(st, op);
+    P.run_pc(st, true);
+    P.run_p5(st, epi_adjoint(out, add_identity ? t : nullptr, add_identity));
+    amp_cotangent(st, out, add_identity ? t : nullptr, 0, m.am.scl_b, add_identity);
+  }
+
+  void rsm(stream_t st, const T* t, T* out_nat, bool scaled) {
+    Model<T>& m = *M; Plan<T>& P = *m.P;
+    if (!valid) throw Error{"nb200: linearisation not initialised (call nb200_lin_update)"};
+    amp_tangent(st, t);
+    P.run_p1(st, pro_metric(t)); P.run_pc(st, false);
+    PointOp<T> op = P.make_op(PM_JVP_OUT);
+    op.invV = T(1.0 / P.g.V); op.natural = 1; op.pos_out = out_nat; op.jl_a = scaled ? jl.p : nullptr;
+    if (scaled && m.am.has_scaling) { op.cshift_ptr = t + m.am.off_scl; op.cshift_scale = m.am.scl_b; }
+    P.template run_p3<true, false>(st, op);
+  }
+  void lsm(stream_t st, const T* u_nat, T* out, bool scaled) {
+    Model<T>& m = *M; Plan<T>& P = *m.P;
+    if (!valid) throw Error{"nb200: linearisation not initialised (call nb200_lin_update)"};
+    PointOp<T> op = P.make_op(PM_LOAD);
+    op.natural = 1; op.in_pos = u_nat; op.jl_a = scaled ? jl.p : nullptr; op.partials = P.p3part.p;
+    P.template run_p3<false, true>(st, op);
+    P.run_pc(st, true);
+    P.run_p5(st, epi_adjoint(out, nullptr, false));
+    amp_cotangent(st, out, nullptr, 0, scaled ? m.am.scl_b : T(0), false);
+  }
+  void posmap(stream_t st, int mode, T* out_nat) {
+    Model<T>& m = *M; Plan<T>& P = *m.P;
+    if (!valid) throw Error{"nb200: linearisation not initialised (call nb200_lin_update)"};
+    PosMapParams<T> pm; pm.mode = mode; pm.lh_kind = m.lh_kind; pm.n = (long)P.g.N; pm.s = s.p; pm.data = m.data.p;
+    pm.w_scalar = m.w_scalar; pm.w_arr = m.has_w_arr ? m.w_arr.p : nullptr; pm.out = m.tmp_pos.p;
+    int grid = (int)std::min<int64_t>((P.g.N + 255) / 256, 148 * 8);
+    launch<PosMapBody<T>>(grid, 256, 0, st, pm);
+    P.run_rev(st, m.tmp_pos.p, out_nat, false);
+  }
+};
+
+}  // namespace nb

@@ -1,0 +1,466 @@
+// nifty_b200 -- axis passes of the n-D Hartley transform and of the fused metric-vector product.
+//
+// Reference semantics: nifty/re/correlated_field.py:24-30 (`hartley` = Re(fftn) +/- Im(fftn)),
+// :882-887 (outer_harmonic_transform), :909-912 (correlated_field) and, for the fused product,
+// nifty/re/likelihood.py:613-621 (LikelihoodWithModel.metric).  Nothing here follows the
+// reference's implementation (jnp.fft.fftn of a complexified array); the decomposition is:
+//
+//   P1  real lines along the last axis  -> half spectrum (n/2+1), stored TRANSPOSED so that the
+//       next axis is contiguous (a CTA owns R adjacent lines and emits R-element pieces)
+//   PC  complex lines along a middle axis (3-D only), same transposed store
+//   P3  lines along axis 0.  The complex FFT of a line (k_last, k_mid) yields, by Hermitian
+//       symmetry, the two REAL position-space lines (k_last,k_mid) and (-k_last,-k_mid).  A
+//       pointwise operator acts on them (x 1/V, exp, noise weight ...), the two real lines are
+//       re-packed as one complex line and transformed again (first axis of the adjoint
+//       transform), split into the two half spectra and stored transposed.  Forward-only and
+//       adjoint-only variants exist for linearisation / JVP / VJP.
+//   P5  complex lines along the last axis + Hermitian combine -> two natural real rows, with the
+//       latent-space epilogue (amplitude gather, + t, mode-bin partial sums, dot products).
+//
+// Position-space arrays therefore live in REVERSED axis order ("T-layout": [x_last]..[x_0],
+// x_0 contiguous); latent-space (harmonic) arrays are in the reference's natural C order.
+// A 2-D product is P1 -> P3 -> P5 (10 array streams), a 3-D one P1 -> PC -> P3 -> PC -> P5 (14).
+#pragma once
+#include "nb_common.cuh"
+#include "nb_fft.cuh"
+
+namespace nb {
+
+template <class T> NB_HD NB_INLINE void load_pair(const T* p, T& a, T& b) {
+  if ((reinterpret_cast<uintptr_t>(p) & (2 * sizeof(T) - 1)) == 0) {
+    cplx<T> v = *reinterpret_cast<const cplx<T>*>(p);
+    a = v.x; b = v.y;
+  } else {
+    a = p[0]; b = p[1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// P1 prologues: value of the real input line (o, rr) at element j (harmonic-space coordinates)
+// ---------------------------------------------------------------------------------------------
+template <class T> struct ProPlain {
+  const T* x;
+  NB_HD NB_INLINE void load2(int, int, int, long off, T& a, T& b) const { load_pair(x + off, a, b); }
+};
+
+// folded mode-bin lookup shared by the amplitude prologues / epilogues
+struct FoldGeom {
+  int n_o, n_r, n;     // extents of (outer, row, last) axes of the natural array
+  int hr1, h1;         // n_r/2+1, n/2+1
+  NB_HD NB_INLINE long base(int o, int rr) const {
+    return ((long)fold_idx(o, n_o) * hr1 + fold_idx(rr, n_r)) * h1;
+  }
+};
+
+// a[b(k)] * xi_k   (forward model, correlated_field.py:911 with azm folded into the table)
+template <class T> struct ProAmp {
+  const T* xi; const int* idxf; const T* amp; FoldGeom fg;
+  NB_HD NB_INLINE void load2(int o, int rr, int j, long off, T& a, T& b) const {
+    long fb = fg.base(o, rr);
+    T x0, x1; load_pair(xi + off, x0, x1);
+    a = ldg(amp + ldg(idxf + fb + fold_idx(j, fg.n))) * x0;
+    b = ldg(amp + ldg(idxf + fb + fold_idx(j + 1, fg.n))) * x1;
+  }
+};
+
+// JVP input: A_b t_k + dA_b xi_k with dA_b = A_b (cj + kappa du_b) (b>=1), dA_0 = da0
+template <class T> struct ProMetric {
+  const T* xi; const T* t; const int* idxf; const T* amp; const T* du; const T* scal;  // scal[0]=cj, scal[1]=da0
+  T kappa; FoldGeom fg;
+  NB_HD NB_INLINE T one(int b, T xv, T tv, T cj, T da0) const {
+    T A = ldg(amp + b);
+    T dA = (b == 0) ? da0 : A * (cj + (du ? kappa * ldg(du + b) : T(0)));
+    return A * tv + dA * xv;
+  }
+  NB_HD NB_INLINE void load2(int o, int rr, int j, long off, T& a, T& b) const {
+    long fb = fg.base(o, rr);
+    T x0, x1, t0, t1; load_pair(xi + off, x0, x1); load_pair(t + off, t0, t1);
+    T cj = ldg(scal), da0 = ldg(scal + 1);
+    a = one(ldg(idxf + fb + fold_idx(j, fg.n)), x0, t0, cj, da0);
+    b = one(ldg(idxf + fb + fold_idx(j + 1, fg.n)), x1, t1, cj, da0);
+  }
+};
+
+template <class T, class Pro> struct P1Params {
+  int lg_n, lg_R;
+  int n_r, n_o;
+  long in_ostride, in_rstride, out_ostride, out_kstride;
+  int pitch;
+  const cplx<T>* tw; int lg_tw;   // table for the REAL length n (tw_n multiple of n)
+  cplx<T>* out;
+  Pro pro;
+};
+
+template <class T, class Pro> struct P1Body {
+  typedef P1Params<T, Pro> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    cplx<T>* s = reinterpret_cast<cplx<T>*>(smem);
+    const int R = 1 << p.lg_R, lg_h = p.lg_n - 1, h = 1 << lg_h;
+    const int gpo = (p.n_r + R - 1) >> p.lg_R;
+    const int o = ctx.bid / gpo, rr0 = (ctx.bid % gpo) << p.lg_R;
+    NB_FOR(ctx, i, R << lg_h) {
+      int r = i >> lg_h, j = i & (h - 1), rr = rr0 + r;
+      T a = 0, b = 0;
+      if (rr < p.n_r) p.pro.load2(o, rr, 2 * j, o * p.in_ostride + rr * p.in_rstride + 2 * j, a, b);
+      s[r * p.pitch + j] = cmake<T>(a, b);
+    }
+    ctx.sync();
+    fft_dif(ctx, s, lg_h, R, p.pitch, p.tw, p.lg_tw);   // w_h^j = w_n^{2j}: same table, larger stride
+    const T half = T(0.5);
+    NB_FOR(ctx, i, (h + 1) << p.lg_R) {
+      int k = i >> p.lg_R, r = i & (R - 1), rr = rr0 + r;
+      if (rr >= p.n_r) continue;
+      cplx<T> zk = s[r * p.pitch + fft_pos(k & (h - 1), lg_h)];
+      cplx<T> zc = cconj(s[r * p.pitch + fft_pos((h - k) & (h - 1), lg_h)]);
+      cplx<T> e = zk + zc, d = zk - zc;
+      cplx<T> w = ldg(p.tw + ((size_t)k << (p.lg_tw - p.lg_n)));
+      cplx<T> wd = cmul_mi(cmul(w, d));   // -i w (zk - zc)
+      p.out[o * p.out_ostride + k * p.out_kstride + rr] = cmake<T>(half * (e.x + wd.x), half * (e.y + wd.y));
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// PC: complex lines, FFT, transposed store
+// ---------------------------------------------------------------------------------------------
+template <class T> struct PCParams {
+  int lg_n, lg_R;
+  int n_r, n_o;
+  long in_ostride, in_rstride, out_ostride, out_kstride;
+  int pitch;
+  const cplx<T>* tw; int lg_tw;
+  const cplx<T>* in;
+  cplx<T>* out;
+};
+
+template <class T> struct PCBody {
+  typedef PCParams<T> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    cplx<T>* s = reinterpret_cast<cplx<T>*>(smem);
+    const int R = 1 << p.lg_R, n = 1 << p.lg_n;
+    const int gpo = (p.n_r + R - 1) >> p.lg_R;
+    const int o = ctx.bid / gpo, rr0 = (ctx.bid % gpo) << p.lg_R;
+    NB_FOR(ctx, i, R << p.lg_n) {
+      int r = i >> p.lg_n, x = i & (n - 1), rr = rr0 + r;
+      cplx<T> v = cmake<T>(0, 0);
+      if (rr < p.n_r) v = p.in[o * p.in_ostride + rr * p.in_rstride + x];
+      s[r * p.pitch + x] = v;
+    }
+    ctx.sync();
+    fft_dif(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw);
+    NB_FOR(ctx, i, n << p.lg_R) {
+      int k = i >> p.lg_R, r = i & (R - 1), rr = rr0 + r;
+      if (rr >= p.n_r) continue;
+      p.out[o * p.out_ostride + k * p.out_kstride + rr] = s[r * p.pitch + fft_pos(k, p.lg_n)];
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// mirror geometry shared by P3 and P5: lines l = a*n_mid + km with a in [0, h_a]; the partner
+// real line is (-a, -km).  n_mid is a power of two (1 for 2-D).
+// ---------------------------------------------------------------------------------------------
+struct MirrorGeom {
+  int n_a, h_a, lg_mid;
+  NB_HD NB_INLINE int nlines() const { return (h_a + 1) << lg_mid; }
+  // returns false if the line is handled by its (stored) partner; lB = -1 for self-mirrored lines
+  NB_HD NB_INLINE bool resolve(int l, int& lA, int& lB) const {
+    int a = l >> lg_mid, km = l & ((1 << lg_mid) - 1);
+    int ma = neg_idx(a, n_a), mkm = neg_idx(km, 1 << lg_mid);
+    lA = l;
+    lB = (ma << lg_mid) + mkm;
+    if (lB == lA) { lB = -1; return true; }
+    if (ma <= h_a && lB < lA) return false;
+    return true;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// P3 pointwise operator (position space, T-layout index ridx = line*n + x)
+// ---------------------------------------------------------------------------------------------
+enum PointMode {
+  PM_METRIC = 0,      // r = jl_a jl_b (v/V + cshift)                       acc0 += r
+  PM_LINEARIZE = 1,   // f = off + v/V; s = sc exp(f); store s, jl; r = dE/df   acc0 += E, acc1 += r
+  PM_JVP_OUT = 2,     // pos_out = (v/V + cshift) * (jl_a ? jl_a : 1)        (FWD only)
+  PM_FIELD_OUT = 3,   // pos_out = off + v/V                                 (FWD only)
+  PM_LOAD = 4,        // r = in_pos * (jl_a ? jl_a : 1)                      acc0 += r (ADJ only)
+};
+enum LhKind { LH_GAUSS = 0, LH_POISSON = 1 };
+
+template <class T> struct PointOp {
+  int mode;
+  int natural;          // PM_FIELD_OUT / PM_JVP_OUT / PM_LOAD address natural-layout arrays
+  int lh_kind, nl_exp;
+  T invV, offset, cshift_scale;   // cshift = cshift_scale * (*cshift_ptr) if cshift_ptr
+  const T* cshift_ptr;
+  T sc;                 // multiplicative scaling of the signal (1 if absent); read from sc_ptr if set
+  const T* sc_ptr;
+  T w_scalar; const T* w_arr;     // Gaussian inverse noise variance
+  const T* data;                  // T-layout
+  const T* jl_a; const T* jl_b;
+  const T* in_pos;
+  T* s_out; T* jl_out; T* pos_out;
+  T* partials;          // [nblk][2]
+  int n_a_full, n_mid, n;         // for natural addressing: T-layout (a, km, x) <-> natural (x, km, a)
+
+  NB_HD NB_INLINE long addr(int lfull, int x) const {
+    if (!natural) return (long)lfull * n + x;
+    int a = lfull / n_mid, km = lfull - a * n_mid;
+    return ((long)x * n_mid + km) * n_a_full + a;
+  }
+  NB_HD NB_INLINE T load(int lfull, int x, T& acc0) const {
+    long i = addr(lfull, x);
+    T r = in_pos[i];
+    if (jl_a) r *= jl_a[(long)lfull * n + x];
+    acc0 += r;
+    return r;
+  }
+  NB_HD NB_INLINE T point(int lfull, int x, T v, T cshift, T scv, T& acc0, T& acc1) const {
+    long i = (long)lfull * n + x;
+    switch (mode) {
+      case PM_METRIC: {
+        T r = jl_a[i] * jl_b[i] * (v * invV + cshift);
+        acc0 += r;
+        return r;
+      }
+      case PM_LINEARIZE: {
+        T f = offset + v * invV;
+        T s = nl_exp ? scv * nb_exp(f) : f;
+        T jd = nl_exp ? s : T(1);
+        T e, cot, l;
+        if (lh_kind == LH_GAUSS) {
+          T w = w_arr ? w_arr[i] : w_scalar;
+          T d = data ? data[i] : T(0);
+          T r = s - d;
+          e = T(0.5) * w * r * r;
+          cot = w * r * jd;
+          l = nb_sqrt(w);
+        } else {
+          T d = data ? data[i] : T(0);
+          e = s - d * nb_log(s);
+          cot = (T(1) - d / s) * jd;
+          l = T(1) / nb_sqrt(s);
+        }
+        if (s_out) s_out[i] = s;
+        if (jl_out) jl_out[i] = jd * l;
+        acc0 += e;
+        acc1 += cot;
+        return cot;
+      }
+      case PM_JVP_OUT: {
+        T r = v * invV + cshift;
+        if (jl_a) r *= jl_a[i];
+        pos_out[addr(lfull, x)] = r;
+        return r;
+      }
+      default: {  // PM_FIELD_OUT
+        T r = offset + v * invV;
+        pos_out[addr(lfull, x)] = r;
+        return r;
+      }
+    }
+  }
+};
+
+template <class T> struct P3Params {
+  int lg_n, lg_R;
+  MirrorGeom mg;
+  int pitch;
+  const cplx<T>* tw; int lg_tw;
+  T hsign;                 // +1: Re+Im (non_canonical_hartley), -1: Re-Im
+  const cplx<T>* in;       // [l][n]
+  cplx<T>* out;            // [k in 0..n/2][out_kstride]
+  long out_kstride;
+  PointOp<T> op;
+};
+
+template <class T, bool FWD, bool ADJ> struct P3Body {
+  typedef P3Params<T> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    cplx<T>* s = reinterpret_cast<cplx<T>*>(smem);
+    const int R = 1 << p.lg_R, n = 1 << p.lg_n, h = n >> 1;
+    const int l0 = ctx.bid << p.lg_R, nl = p.mg.nlines();
+    const T sg = p.hsign;
+    T acc0 = 0, acc1 = 0;
+    T cshift = p.op.cshift_ptr ? p.op.cshift_scale * ldg(p.op.cshift_ptr) : T(0);
+    T scv = p.op.sc_ptr ? ldg(p.op.sc_ptr) : p.op.sc;
+    if (FWD) {
+      NB_FOR(ctx, i, R << p.lg_n) {
+        int r = i >> p.lg_n, x = i & (n - 1), l = l0 + r, lA, lB;
+        cplx<T> v = cmake<T>(0, 0);
+        if (l < nl && p.mg.resolve(l, lA, lB)) v = p.in[(long)l * n + x];
+        s[r * p.pitch + x] = v;
+      }
+      ctx.sync();
+      fft_dif(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw);
+      // Hermitian combine + pointwise operator on the pair (x, y = -x)
+      NB_FOR(ctx, i, R * (h + 1)) {
+        int r = i / (h + 1), x = i - r * (h + 1), y = (n - x) & (n - 1), l = l0 + r, lA, lB;
+        if (l >= nl || !p.mg.resolve(l, lA, lB)) continue;
+        int px = fft_pos(x, p.lg_n), py = fft_pos(y, p.lg_n);
+        cplx<T> cx = s[r * p.pitch + px], cy = s[r * p.pitch + py];
+        T aX = cx.x + sg * cx.y, bY = cx.x - sg * cx.y;
+        T aY = cy.x + sg * cy.y, bX = cy.x - sg * cy.y;
+        T a2x = p.op.point(lA, x, aX, cshift, scv, acc0, acc1), b2x = 0, a2y = 0, b2y = 0;
+        if (y != x) a2y = p.op.point(lA, y, aY, cshift, scv, acc0, acc1);
+        if (lB >= 0) {
+          b2x = p.op.point(lB, x, bX, cshift, scv, acc0, acc1);
+          if (y != x) b2y = p.op.point(lB, y, bY, cshift, scv, acc0, acc1);
+        }
+        if (ADJ) {
+          s[r * p.pitch + px] = cmake<T>(a2x, b2x);
+          if (y != x) s[r * p.pitch + py] = cmake<T>(a2y, b2y);
+        }
+      }
+    } else {
+      NB_FOR(ctx, i, R << p.lg_n) {
+        int r = i >> p.lg_n, x = i & (n - 1), l = l0 + r, lA, lB;
+        cplx<T> v = cmake<T>(0, 0);
+        if (l < nl && p.mg.resolve(l, lA, lB)) {
+          v.x = p.op.load(lA, x, acc0);
+          if (lB >= 0) v.y = p.op.load(lB, x, acc0);
+        }
+        s[r * p.pitch + fft_pos(x, p.lg_n)] = v;
+      }
+    }
+    if (ADJ) {
+      ctx.sync();
+      fft_dit(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw);
+      const T half = T(0.5);
+      NB_FOR(ctx, i, (h + 1) << p.lg_R) {
+        int k = i >> p.lg_R, r = i & (R - 1), l = l0 + r, lA, lB;
+        if (l >= nl || !p.mg.resolve(l, lA, lB)) continue;
+        cplx<T> zk = s[r * p.pitch + k], zc = cconj(s[r * p.pitch + ((n - k) & (n - 1))]);
+        cplx<T> e = zk + zc, d = cmul_mi(zk - zc);
+        p.out[k * p.out_kstride + lA] = cmake<T>(half * e.x, half * e.y);
+        if (lB >= 0) p.out[k * p.out_kstride + lB] = cmake<T>(half * d.x, half * d.y);
+      }
+    }
+    if (p.op.partials) {
+      // scratch for the reduction lives behind the line buffers
+      void* scratch = reinterpret_cast<void*>(s + (size_t)R * p.pitch);
+      acc0 = ctx.block_sum(acc0, scratch);
+      acc1 = ctx.block_sum(acc1, scratch);
+      if (ctx.tid == 0) { p.op.partials[2 * ctx.bid] = acc0; p.op.partials[2 * ctx.bid + 1] = acc1; }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// P5 epilogues (latent space, natural layout)
+// ---------------------------------------------------------------------------------------------
+template <class T> struct EpiPlain {
+  T* out; T scale;
+  T* partials;   // unused
+  NB_HD NB_INLINE void emit(long rowA, long rowB, long, long, int x, int y, T gAx, T gAy, T gBx, T gBy, T&) const {
+    out[rowA + x] = gAx * scale;
+    if (y != x) out[rowA + y] = gAy * scale;
+    if (rowB >= 0) {
+      out[rowB + x] = gBx * scale;
+      if (y != x) out[rowB + y] = gBy * scale;
+    }
+  }
+};
+
+// out_k = A_b g_k / V (+ add_k); W[l][x] = sum over the (up to four) mirror points of xi_k g_k / V;
+// acc += add_k out_k  (the xi-block of <t, M t> for conjugate gradient)
+template <class T> struct EpiAdjoint {
+  T* out; const T* add; const T* xi; const int* idxf; const T* amp; T* W; T invV;
+  T* partials;   // [nblk]
+  NB_HD NB_INLINE void one(long i, T A, T g, T& ws, T& acc) const {
+    g *= invV;
+    T o = A * g;
+    if (add) { T a = add[i]; o += a; acc += a * o; }
+    out[i] = o;
+    if (xi) ws += xi[i] * g;
+  }
+  NB_HD NB_INLINE void emit(long rowA, long rowB, long fbase, long wbase, int x, int y, T gAx, T gAy, T gBx, T gBy,
+                            T& acc) const {
+    T A = ldg(amp + ldg(idxf + fbase + x));
+    T ws = 0;
+    one(rowA + x, A, gAx, ws, acc);
+    if (y != x) one(rowA + y, A, gAy, ws, acc);
+    if (rowB >= 0) {
+      one(rowB + x, A, gBx, ws, acc);
+      if (y != x) one(rowB + y, A, gBy, ws, acc);
+    }
+    if (W) W[wbase + x] = ws;
+  }
+};
+
+template <class T, class Epi> struct P5Params {
+  int lg_n, lg_R;
+  MirrorGeom mg;
+  int hmid1;      // n_mid/2 + 1 (folded extent of the middle axis)
+  int pitch;
+  const cplx<T>* tw; int lg_tw;
+  T hsign;
+  const cplx<T>* in;   // [l][n]
+  Epi epi;
+};
+
+template <class T, class Epi> struct P5Body {
+  typedef P5Params<T, Epi> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    cplx<T>* s = reinterpret_cast<cplx<T>*>(smem);
+    const int R = 1 << p.lg_R, n = 1 << p.lg_n, h = n >> 1;
+    const int l0 = ctx.bid << p.lg_R, nl = p.mg.nlines();
+    const T sg = p.hsign;
+    T acc = 0;
+    NB_FOR(ctx, i, R << p.lg_n) {
+      int r = i >> p.lg_n, x = i & (n - 1), l = l0 + r, lA, lB;
+      cplx<T> v = cmake<T>(0, 0);
+      if (l < nl && p.mg.resolve(l, lA, lB)) v = p.in[(long)l * n + x];
+      s[r * p.pitch + x] = v;
+    }
+    ctx.sync();
+    fft_dif(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw);
+    const int nmid = 1 << p.mg.lg_mid;
+    NB_FOR(ctx, i, R * (h + 1)) {
+      int r = i / (h + 1), x = i - r * (h + 1), y = (n - x) & (n - 1), l = l0 + r, lA, lB;
+      if (l >= nl || !p.mg.resolve(l, lA, lB)) continue;
+      cplx<T> cx = s[r * p.pitch + fft_pos(x, p.lg_n)], cy = s[r * p.pitch + fft_pos(y, p.lg_n)];
+      T gAx = cx.x + sg * cx.y, gBy = cx.x - sg * cx.y;
+      T gAy = cy.x + sg * cy.y, gBx = cy.x - sg * cy.y;
+      int a = lA >> p.mg.lg_mid, km = lA & (nmid - 1);
+      long fbase = ((long)a * p.hmid1 + fold_idx(km, nmid)) * (h + 1);   // a <= h_a is already folded
+      p.epi.emit((long)lA * n, lB >= 0 ? (long)lB * n : -1L, fbase, (long)lA * (h + 1), x, y, gAx, gAy, gBx, gBy, acc);
+    }
+    if (p.epi.partials) {
+      void* scratch = reinterpret_cast<void*>(s + (size_t)R * p.pitch);
+      acc = ctx.block_sum(acc, scratch);
+      if (ctx.tid == 0) p.epi.partials[ctx.bid] = acc;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// axis-reversing copy (natural <-> T-layout), used at the API boundary for data / noise arrays and
+// for user-visible position-space outputs.  dims (d0,d1,d2) natural -> out[x2][x1][x0].
+// ---------------------------------------------------------------------------------------------
+template <class T> struct RevParams { const T* in; T* out; int d0, d1, d2; };
+template <class T> struct RevBody {
+  typedef RevParams<T> Params;
+  // one block per (x1, 32x32 tile of (x0,x2)); smem 32*33 T
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    T* tile = reinterpret_cast<T*>(smem);
+    int t0 = (p.d0 + 31) / 32, t2 = (p.d2 + 31) / 32;
+    int b = ctx.bid;
+    int i2 = b % t2; b /= t2;
+    int i0 = b % t0; b /= t0;
+    int x1 = b;
+    NB_FOR(ctx, i, 1024) {
+      int r = i >> 5, c = i & 31;        // r: x0 offset, c: x2 offset (contiguous in the input)
+      int x0 = i0 * 32 + r, x2 = i2 * 32 + c;
+      if (x0 < p.d0 && x2 < p.d2) tile[r * 33 + c] = p.in[((long)x0 * p.d1 + x1) * p.d2 + x2];
+    }
+    ctx.sync();
+    NB_FOR(ctx, i, 1024) {
+      int r = i >> 5, c = i & 31;        // r: x2 offset, c: x0 offset (contiguous in the output)
+      int x0 = i0 * 32 + c, x2 = i2 * 32 + r;
+      if (x0 < p.d0 && x2 < p.d2) p.out[((long)x2 * p.d1 + x1) * p.d0 + x0] = tile[c * 33 + r];
+    }
+  }
+};
+
+}  // namespace nb

@@ -1,0 +1,310 @@
+// nifty_b200 -- transform plan: grid geometry, |k| mode bins, twiddles, scratch, pass launchers.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+#include "nb_backend.cuh"
+#include "nb_passes.cuh"
+#include "nb_amp.cuh"
+
+namespace nb {
+
+struct PassCfg { int lg_n = 0, lg_R = 0, pitch = 1, grid = 1, block = 64; size_t smem = 0; };
+
+inline int ilog2(int64_t v) { int l = 0; while ((int64_t(1) << l) < v) ++l; return l; }
+inline bool is_pow2(int64_t v) { return v >= 1 && (v & (v - 1)) == 0; }
+
+// host-side grid description shared by Plan<float> and Plan<double>
+struct GridInfo {
+  int ndim = 0;
+  int64_t shape[3] = {1, 1, 1};
+  double dist[3] = {1, 1, 1};
+  int n0 = 1, nm = 1, nl = 1;      // internal axes: first, middle (1 unless 3-D), last (contiguous)
+  int h0 = 0, hm = 0, hl = 0;
+  bool three = false;
+  int64_t N = 1;
+  double V = 1;
+  int K = 0;
+  std::vector<int> idxf;           // [h0+1][hm+1][hl+1] bin of the folded mode
+  std::vector<double> um, rel, logvol;
+  std::vector<int64_t> mult;
+  std::vector<int> w_order, w_offs;   // CSR of W positions per bin
+  int64_t nW = 0;
+
+  // Mode binning; follows the arithmetic of correlated_field.py:134-176 (mode lengths) and :55-67
+  // (unique with 1e-12 relative merge, mid-point binning) on the folded index range only: every
+  // |k| value of the full grid occurs there, with multiplicity prod_i (1 or 2).
+  int build(int ndim_, const int64_t* shp, const double* dst) {
+    ndim = ndim_;
+    if (ndim < 1 || ndim > 3) return fail("nb200: only 1-, 2- and 3-dimensional grids are supported");
+    N = 1; V = 1;
+    for (int i = 0; i < ndim; ++i) {
+      shape[i] = shp[i]; dist[i] = dst[i];
+      if (!is_pow2(shp[i]) || shp[i] < 2)
+        return fail("nb200: every grid extent must be a power of two >= 2 on the sm_100a path (got " + std::to_string(shp[i]) + ")");
+      if (shp[i] > (1 << 14)) return fail("nb200: grid extent too large for one shared-memory line");
+      if (!(dst[i] > 0)) return fail("nb200: distances must be positive");
+      N *= shp[i]; V *= (double)shp[i] * dst[i];
+    }
+    if (ndim == 1) { n0 = 1; nm = 1; nl = (int)shp[0]; }
+    else if (ndim == 2) { n0 = (int)shp[0]; nm = 1; nl = (int)shp[1]; }
+    else { n0 = (int)shp[0]; nm = (int)shp[1]; nl = (int)shp[2]; three = true; }
+    h0 = n0 / 2; hm = nm / 2; hl = nl / 2;
+    // per-axis folded lengths, user axis order
+    std::vector<double> ax[3];
+    for (int i = 0; i < ndim; ++i) {
+      double step = 1.0 / ((double)shp[i] * dst[i]);
+      ax[i].resize(shp[i] / 2 + 1);
+      for (int64_t k = 0; k <= shp[i] / 2; ++k) ax[i][k] = (double)k * step;
+    }
+    const size_t nf = (size_t)(h0 + 1) * (hm + 1) * (hl + 1);
+    std::vector<double> len(nf);
+    size_t q = 0;
+    for (int f0 = 0; f0 <= h0; ++f0)
+      for (int fm = 0; fm <= hm; ++fm)
+        for (int fl = 0; fl <= hl; ++fl, ++q) {
+          double v;
+          if (ndim == 1) v = ax[0][fl];
+          else if (ndim == 2) { double a = ax[0][f0], b = ax[1][fl]; v = std::sqrt(a * a + b * b); }
+          else { double a = ax[0][f0], b = ax[1][fm], c = ax[2][fl]; v = a * a; v = v + b * b; v = v + c * c; v = std::sqrt(v); }
+          len[q] = v;
+        }
+    std::vector<double> srt(len);
+    std::sort(srt.begin(), srt.end());
+    srt.erase(std::unique(srt.begin(), srt.end()), srt.end());
+    const double tol = 1e-12 * srt.back();
+    um.clear();
+    for (size_t i = 0; i < srt.size(); ++i) {
+      double nxt = (i + 1 < srt.size()) ? srt[i + 1] : 2.0 * srt.back();
+      if (nxt - srt[i] > tol) um.push_back(srt[i]);
+    }
+    K = (int)um.size();
+    if (K < 1) return fail("invalid harmonic mode(s) encountered");
+    std::vector<double> bounds(K > 0 ? K - 1 : 0);
+    for (int i = 0; i + 1 < K; ++i) bounds[i] = 0.5 * (um[i] + um[i + 1]);
+    idxf.resize(nf);
+    mult.assign(K, 0);
+    q = 0;
+    for (int f0 = 0; f0 <= h0; ++f0)
+      for (int fm = 0; fm <= hm; ++fm)
+        for (int fl = 0; fl <= hl; ++fl, ++q) {
+          int b = (int)(std::lower_bound(bounds.begin(), bounds.end(), len[q]) - bounds.begin());
+          idxf[q] = b;
+          int64_t w = 1;
+          if (f0 != 0 && 2 * f0 != n0) w *= 2;
+          if (fm != 0 && 2 * fm != nm) w *= 2;
+          if (fl != 0 && 2 * fl != nl) w *= 2;
+          mult[b] += w;
+        }
+    for (int b = 0; b < K; ++b)
+      if (mult[b] == 0) return fail("invalid harmonic mode(s) encountered");
+    // make_grid / _log_modes (correlated_field.py:228-265)
+    rel = um;
+    for (int b = 1; b < K; ++b) rel[b] = std::log(rel[b]);
+    if (K > 1) { double r1 = rel[1]; for (int b = 1; b < K; ++b) rel[b] -= r1; }
+    logvol.clear();
+    for (int b = 2; b < K; ++b) logvol.push_back(rel[b] - rel[b - 1]);
+    // CSR of the folded partial-sum array W[l = a*nm + km][x], a in [0,h0], km in [0,nm), x in [0,hl]
+    nW = (int64_t)(h0 + 1) * nm * (hl + 1);
+    if (nW >= (int64_t(1) << 31)) return fail("nb200: grid too large for 32-bit mode-bin indices");
+    w_offs.assign(K + 1, 0);
+    auto wbin = [&](int64_t p) {
+      int x = (int)(p % (hl + 1)); int64_t l = p / (hl + 1);
+      int km = (int)(l % nm), a = (int)(l / nm);
+      int fm = km <= nm - km ? km : nm - km;
+      return idxf[((size_t)a * (hm + 1) + fm) * (hl + 1) + x];
+    };
+    for (int64_t p = 0; p < nW; ++p) w_offs[wbin(p) + 1]++;
+    for (int b = 0; b < K; ++b) w_offs[b + 1] += w_offs[b];
+    w_order.resize(nW);
+    std::vector<int> cur(w_offs.begin(), w_offs.end() - 1);
+    for (int64_t p = 0; p < nW; ++p) w_order[cur[wbin(p)]++] = (int)p;
+    return 0;
+  }
+};
+
+struct PlanBase {
+  int dtype = 1, device = 0, hconv = 0;
+  GridInfo g;
+  virtual ~PlanBase() {}
+};
+
+template <class T> std::vector<cplx<T>> make_twiddles(int n) {
+  std::vector<cplx<T>> tw(n);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int j = 0; j < n; ++j) {
+    // exact octant symmetry: evaluate sin/cos on [0, pi/4] only
+    int jj = j % n; long double c, s;
+    int oct = (int)((8LL * jj) / n);           // 0..7
+    long double base;
+    switch (oct) {
+      case 0: base = two_pi * jj / n; c = cosl(base); s = sinl(base); break;
+      case 1: base = two_pi * (n / 4.0L - jj) / n; c = sinl(base); s = cosl(base); break;
+      case 2: base = two_pi * (jj - n / 4.0L) / n; c = -sinl(base); s = cosl(base); break;
+      case 3: base = two_pi * (n / 2.0L - jj) / n; c = -cosl(base); s = sinl(base); break;
+      case 4: base = two_pi * (jj - n / 2.0L) / n; c = -cosl(base); s = -sinl(base); break;
+      case 5: base = two_pi * (3 * n / 4.0L - jj) / n; c = -sinl(base); s = -cosl(base); break;
+      case 6: base = two_pi * (jj - 3 * n / 4.0L) / n; c = sinl(base); s = -cosl(base); break;
+      default: base = two_pi * (n - jj) / n; c = cosl(base); s = -sinl(base); break;
+    }
+    tw[j] = cmake<T>((T)c, (T)(-s));   // exp(-2 pi i j / n)
+  }
+  return tw;
+}
+
+template <class T> struct Plan : PlanBase {
+  int lg0 = 0, lgm = 0, lgl = 0;
+  T hsign = 1;
+  DevBuf<cplx<T>> tw0, twm, twl, S0, S1;
+  DevBuf<int> idxf, w_order, w_offs;
+  DevBuf<T> W, p3part, p5part;
+  PassCfg c1, cA, c3, cB, c5;
+  int seg_lg_lpb = 2;   // lanes per mode bin in the segment sum (power of two near the mean bin population)
+  int seg_grid() const { int bpb = 256 >> seg_lg_lpb; return (g.K + bpb - 1) / bpb; }
+
+  static PassCfg choose(int lg_n_line /*log2 complex elems per line*/, int64_t group_lines, int64_t n_groups_outer,
+                        bool sequential_lines, int64_t total_lines) {
+    PassCfg c;
+    const size_t line_bytes = (size_t(1) << lg_n_line) * sizeof(cplx<T>);
+    const size_t maxs = max_smem_per_block() - 2048;
+    if (line_bytes > maxs) throw Error{"nb200: grid extent too large for one shared-memory line"};
+    const size_t budget = 96 * 1024;
+    const int sms = sm_count();
+    auto ctas = [&](int lgR) {
+      int64_t R = int64_t(1) << lgR;
+      return sequential_lines ? (total_lines + R - 1) / R : n_groups_outer * ((group_lines + R - 1) / R);
+    };
+    int lgR = 0;
+    while (lgR < 4 && (int64_t(2) << lgR) <= (sequential_lines ? total_lines : group_lines) &&
+           (size_t(2) << lgR) * line_bytes <= budget)
+      ++lgR;
+    while (lgR > 0 && ctas(lgR) < 2 * sms) --lgR;
+    c.lg_R = lgR;
+    c.pitch = 1 << lg_n_line;
+    c.smem = (size_t(1) << lgR) * c.pitch * sizeof(cplx<T>);
+    c.grid = (int)ctas(lgR);
+    int64_t bf = (int64_t(1) << (lgR + lg_n_line)) / 8;
+    int blk = 64;
+    while (blk < 256 && blk < bf) blk *= 2;
+    c.block = blk;
+    return c;
+  }
+
+  void init(int device_, int ndim, const int64_t* shp, const double* dst, int hconv_) {
+    device = device_; hconv = hconv_;
+    dtype = sizeof(T) == 8 ? 1 : 0;
+    hsign = hconv ? T(-1) : T(1);
+    dev_set(device);
+    if (g.build(ndim, shp, dst)) throw Error{last_error_ref()};
+    lg0 = ilog2(g.n0); lgm = ilog2(g.nm); lgl = ilog2(g.nl);
+    tw0.upload(make_twiddles<T>(g.n0));
+    twm.upload(make_twiddles<T>(g.nm));
+    twl.upload(make_twiddles<T>(g.nl));
+    idxf.upload(g.idxf); w_order.upload(g.w_order); w_offs.upload(g.w_offs);
+    W.alloc((size_t)g.nW);
+    const int64_t n0 = g.n0, nm = g.nm, nl = g.nl, h0 = g.h0, hl = g.hl;
+    size_t sc = 0;
+    if (g.three) sc = (size_t)std::max(n0 * (hl + 1) * nm, (h0 + 1) * nl * nm);
+    else sc = (size_t)std::max((hl + 1) * n0, (h0 + 1) * nl);
+    S0.alloc(sc); S1.alloc(sc);
+    // P1: real lines of length nl -> complex FFT of nl/2
+    if (g.three) c1 = choose(lgl - 1, nm, n0, false, 0);
+    else c1 = choose(lgl - 1, n0, 1, false, 0);
+    c1.lg_n = lgl;
+    if (g.three) {
+      cA = choose(lgm, n0, hl + 1, false, 0); cA.lg_n = lgm;
+      cB = choose(lgm, nl, h0 + 1, false, 0); cB.lg_n = lgm;
+    }
+    c3 = choose(lg0, 0, 0, true, (hl + 1) * nm); c3.lg_n = lg0;
+    c5 = choose(lgl, 0, 0, true, (h0 + 1) * nm); c5.lg_n = lgl;
+    {
+      double avg = (double)g.nW / (double)g.K;
+      seg_lg_lpb = 0;
+      while (seg_lg_lpb < 8 && (1 << (seg_lg_lpb + 1)) <= avg * 1.5) ++seg_lg_lpb;
+    }
+    p3part.alloc((size_t)2 * c3.grid);
+    p5part.alloc((size_t)c5.grid);
+  }
+
+  FoldGeom fold_geom() const {
+    FoldGeom f;
+    if (g.three) { f.n_o = g.n0; f.n_r = g.nm; } else { f.n_o = 1; f.n_r = g.n0; }
+    f.n = g.nl; f.hr1 = f.n_r / 2 + 1; f.h1 = g.hl + 1;
+    return f;
+  }
+  MirrorGeom mg3() const { MirrorGeom m; m.n_a = g.nl; m.h_a = g.hl; m.lg_mid = lgm; return m; }
+  MirrorGeom mg5() const { MirrorGeom m; m.n_a = g.n0; m.h_a = g.h0; m.lg_mid = lgm; return m; }
+  cplx<T>* p3_in() { return g.three ? S1.p : S0.p; }
+  cplx<T>* p3_out() { return g.three ? S0.p : S1.p; }
+
+  PointOp<T> make_op(int mode) const {
+    PointOp<T> op;
+    std::memset(&op, 0, sizeof(op));
+    op.mode = mode; op.invV = T(1); op.sc = T(1); op.nl_exp = 1;
+    op.n_a_full = g.nl; op.n_mid = g.nm; op.n = g.n0;
+    return op;
+  }
+
+  template <class Pro> void run_p1(stream_t st, const Pro& pro) {
+    P1Params<T, Pro> p;
+    p.lg_n = lgl; p.lg_R = c1.lg_R; p.pitch = c1.pitch; p.tw = twl.p; p.lg_tw = lgl; p.out = S0.p; p.pro = pro;
+    if (g.three) {
+      p.n_o = g.n0; p.n_r = g.nm; p.in_ostride = (long)g.nm * g.nl; p.in_rstride = g.nl;
+      p.out_ostride = (long)(g.hl + 1) * g.nm; p.out_kstride = g.nm;
+    } else {
+      p.n_o = 1; p.n_r = g.n0; p.in_ostride = 0; p.in_rstride = g.nl; p.out_ostride = 0; p.out_kstride = g.n0;
+    }
+    launch<P1Body<T, Pro>>(c1.grid, c1.block, c1.smem, st, p);
+  }
+  void run_pc(stream_t st, bool second) {
+    if (!g.three) return;
+    PCParams<T> p;
+    const PassCfg& c = second ? cB : cA;
+    p.lg_n = lgm; p.lg_R = c.lg_R; p.pitch = c.pitch; p.tw = twm.p; p.lg_tw = lgm; p.in = S0.p; p.out = S1.p;
+    if (!second) {   // [j0][k2][j1] -> [k2][k1][j0]
+      p.n_o = g.hl + 1; p.n_r = g.n0; p.in_ostride = g.nm; p.in_rstride = (long)(g.hl + 1) * g.nm;
+      p.out_ostride = (long)g.nm * g.n0; p.out_kstride = g.n0;
+    } else {         // [k0][x2][x1] -> [k0][k1][x2]
+      p.n_o = g.h0 + 1; p.n_r = g.nl; p.in_ostride = (long)g.nl * g.nm; p.in_rstride = g.nm;
+      p.out_ostride = (long)g.nm * g.nl; p.out_kstride = g.nl;
+    }
+    launch<PCBody<T>>(c.grid, c.block, c.smem, st, p);
+  }
+  template <bool FWD, bool ADJ> void run_p3(stream_t st, const PointOp<T>& op) {
+    P3Params<T> p;
+    p.lg_n = lg0; p.lg_R = c3.lg_R; p.mg = mg3(); p.pitch = c3.pitch; p.tw = tw0.p; p.lg_tw = lg0; p.hsign = hsign;
+    p.in = p3_in(); p.out = p3_out(); p.out_kstride = (long)g.nl * g.nm; p.op = op;
+    launch<P3Body<T, FWD, ADJ>>(c3.grid, c3.block, c3.smem, st, p);
+  }
+  template <class Epi> void run_p5(stream_t st, const Epi& epi) {
+    P5Params<T, Epi> p;
+    p.lg_n = lgl; p.lg_R = c5.lg_R; p.mg = mg5(); p.hmid1 = g.hm + 1; p.pitch = c5.pitch; p.tw = twl.p; p.lg_tw = lgl;
+    p.hsign = hsign; p.in = S1.p; p.epi = epi;
+    launch<P5Body<T, Epi>>(c5.grid, c5.block, c5.smem, st, p);
+  }
+  // natural (d0,d1,d2) -> reversed axes; for the T-layout <-> natural conversions
+  void run_rev(stream_t st, const T* in, T* out, bool to_T) {
+    RevParams<T> p; p.in = in; p.out = out;
+    int a0 = g.n0, a1 = g.nm, a2 = g.nl;
+    if (to_T) { p.d0 = a0; p.d1 = a1; p.d2 = a2; } else { p.d0 = a2; p.d1 = a1; p.d2 = a0; }
+    int grid = p.d1 * ((p.d0 + 31) / 32) * ((p.d2 + 31) / 32);
+    launch<RevBody<T>>(grid, 256, 32 * 33 * sizeof(T), st, p);
+  }
+
+  // ---- raw operators ----
+  void hartley(stream_t st, const T* in, T* out) {
+    ProPlain<T> pro; pro.x = in;
+    run_p1(st, pro); run_pc(st, false);
+    PointOp<T> op = make_op(PM_FIELD_OUT); op.natural = 1; op.pos_out = out;
+    run_p3<true, false>(st, op);
+  }
+  void cf_apply(stream_t st, const T* amp, const T* xi, T offset, T* out) {
+    ProAmp<T> pro; pro.xi = xi; pro.idxf = idxf.p; pro.amp = amp; pro.fg = fold_geom();
+    run_p1(st, pro); run_pc(st, false);
+    PointOp<T> op = make_op(PM_FIELD_OUT); op.natural = 1; op.pos_out = out; op.invV = T(1.0 / g.V); op.offset = offset;
+    run_p3<true, false>(st, op);
+  }
+};
+
+}  // namespace nb
