@@ -39,6 +39,10 @@ const char* nb200_last_error(void);
 int nb200_version(void);
 /* number of kernel launches issued by this library in this process (instrumentation) */
 unsigned long long nb200_launch_count(void);
+/* per-kernel CUDA-event timing (instrumentation for bench.py): begin() arms it; end() synchronises the
+ * device and writes one "mangled_kernel_body_name launches total_ms" line per kernel into buf */
+int nb200_timing_begin(void);
+int nb200_timing_end(char* buf, int64_t buflen);
 
 /* ---- plan: grid, mode bins, transform ------------------------------------------------------ */
 

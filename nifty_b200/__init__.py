@@ -1,0 +1,13 @@
+"""nifty_b200 -- B200-native MGVI/geoVI inner loop behind the ``nifty.re`` interface.
+
+Host side (this package): the reference's names and call protocol.  Device side
+(``nifty_b200/csrc`` -> ``lib/libniftyb200.so``): hand-written sm_100a CUDA behind the C ABI of
+``include/nifty_b200.h``.  Importing the package does not need a GPU; using it does.
+"""
+
+from ._capi import NB200Error  # noqa: F401
+from ._runtime import Lin, ModelHandle, Plan, Runtime, default_runtime  # noqa: F401
+from .prior import LogNormalPrior, NormalPrior, lognormal_moments  # noqa: F401
+from .tree import Layout  # noqa: F401
+from .correlated_field import CorrelatedField, CorrelatedFieldMaker  # noqa: F401
+from .likelihood import Gaussian, Likelihood, LikelihoodWithModel, Poissonian, SignalModel  # noqa: F401

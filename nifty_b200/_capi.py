@@ -52,6 +52,8 @@ SIGNATURES = {
     "nb200_last_error": (C.c_char_p, []),
     "nb200_version": (C.c_int, []),
     "nb200_launch_count": (C.c_ulonglong, []),
+    "nb200_timing_begin": (C.c_int, []),
+    "nb200_timing_end": (C.c_int, [C.c_char_p, i64]),
     "nb200_plan_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(i64), C.POINTER(f64), C.c_int, C.c_int]),
     "nb200_plan_destroy": (None, [vp]),
     "nb200_plan_num_modes": (i64, [vp]),

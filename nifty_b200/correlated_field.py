@@ -1,0 +1,152 @@
+"""``CorrelatedFieldMaker`` -- host-side mirror of ``nifty/re/correlated_field.py:519-920``.
+
+Same builder protocol (``set_amplitude_total_offset``, ``add_fluctuations``, ``finalize``), same
+leaf names (``<prefix>xi``, ``<prefix>zeromode``, ``<prefix><sub>fluctuations`` ...), same error
+behaviour for malformed priors.  ``finalize()`` returns a :class:`CorrelatedField` whose forward /
+JVP / VJP run in the sm_100a kernels of libniftyb200.so; nothing is evaluated in Python.
+
+Scope of this round: one Fourier sub-grid (1-3 axes, power-of-two extents), non-parametric
+amplitude (``kind`` "amplitude" or "power").  Matern amplitudes, multiple sub-grids and
+``harmonic_type="spherical"`` raise ``NotImplementedError`` ("next").
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ._capi import ModelDesc
+from ._runtime import Lin, ModelHandle, Plan, Runtime, default_runtime
+from .prior import LogNormalPrior, NormalPrior, _as_prior
+from .tree import Layout
+
+
+class CorrelatedField:
+    """The finalised model: ``cf(pos)`` evaluates the field; mirrors ``jft.Model`` attributes."""
+
+    def __init__(self, plan: Plan, domain: dict, prefix: str, sub_prefix: str, desc_fields: dict, offset_mean: float):
+        self.plan, self.rt = plan, plan.rt
+        self.prefix, self.sub_prefix = prefix, sub_prefix
+        self.offset_mean = float(offset_mean)
+        self._desc_fields = dict(desc_fields)
+        self.domain = dict(sorted(domain.items()))
+        self.layout = Layout(self.domain)
+        self.target_shape = plan.shape
+        self.dtype = plan.dtype
+        self._handle: Optional[ModelHandle] = None
+
+    # -- jft.Model surface --------------------------------------------------------------------
+    @property
+    def target(self):
+        return self.target_shape
+
+    def init(self, seed):
+        """Random latent position (dict of tensors), N(0,1) per leaf as ``Model.init`` does."""
+        return self.layout.unpack(self.layout.random(seed, self.dtype, self.rt.device))
+
+    def _descriptor(self, layout: Layout, scaling=None, scaling_key="scaling") -> ModelDesc:
+        d = ModelDesc()
+        for k, v in self._desc_fields.items():
+            setattr(d, k, v)
+        p, sp = self.prefix, self.prefix + self.sub_prefix
+        off = lambda key: layout.offsets.get(key, -1)
+        d.off_xi, d.off_zeromode = off(p + "xi"), off(p + "zeromode")
+        d.off_fluct, d.off_slope = off(sp + "fluctuations"), off(sp + "loglogavgslope")
+        d.off_flex, d.off_asp, d.off_spectrum = off(sp + "flexibility"), off(sp + "asperity"), off(sp + "spectrum")
+        d.has_scaling, d.off_scaling = 0, -1
+        if scaling is not None:
+            a, b = scaling.ab()
+            d.has_scaling, d.scaling_a, d.scaling_b, d.off_scaling = 1, a, b, off(scaling_key)
+        d.latent_size = layout.size
+        d.offset_mean = self.offset_mean
+        return d
+
+    def handle(self) -> ModelHandle:
+        if self._handle is None:
+            self._handle = ModelHandle(self.plan, self._descriptor(self.layout))
+        return self._handle
+
+    def as_flat(self, pos) -> torch.Tensor:
+        if isinstance(pos, torch.Tensor):
+            return self.rt.asarray(pos.reshape(-1), self.dtype)
+        return self.layout.pack(pos, self.dtype, self.rt.device)
+
+    def __call__(self, pos) -> torch.Tensor:
+        return self.handle().cf_forward(self.as_flat(pos))
+
+
+class CorrelatedFieldMaker:
+    """Builder with the call protocol of ``jft.CorrelatedFieldMaker`` (correlated_field.py:519-920)."""
+
+    def __init__(self, prefix: str, *, dtype=torch.float64, hartley_convention="non_canonical_hartley",
+                 runtime: Optional[Runtime] = None):
+        self._prefix = prefix
+        self._dtype, self._conv, self._rt = dtype, hartley_convention, runtime
+        self._offset_mean = None
+        self._azm = None
+        self._fluct = []
+        self._parameter_tree = {}
+
+    def set_amplitude_total_offset(self, offset_mean, offset_std):
+        """correlated_field.py:583-659; ``offset_std`` is a ``(mean, std)`` log-normal prior."""
+        if offset_std is None or not isinstance(offset_std, (tuple, list, LogNormalPrior)):
+            raise TypeError(f"`offset_std` of invalid type {type(offset_std)!r}")
+        self._azm = _as_prior(offset_std, LogNormalPrior, "offset_std")
+        self._offset_mean = float(offset_mean)
+        self._parameter_tree[self._prefix + "zeromode"] = ()
+
+    def add_fluctuations(self, shape, distances, fluctuations, loglogavgslope, flexibility=None, asperity=None,
+                         prefix: str = "", harmonic_type: str = "fourier", non_parametric_kind: str = "amplitude"):
+        """correlated_field.py:661-755."""
+        if harmonic_type.lower() != "fourier":
+            if harmonic_type.lower() == "spherical":
+                raise NotImplementedError("harmonic_type='spherical' is outside the B200 hot path")
+            raise ValueError(f"invalid `harmonic_type` {harmonic_type!r}")
+        kind = non_parametric_kind.lower()
+        if kind not in ("amplitude", "power"):
+            raise ValueError(f"invalid `non_parametric_kind` {non_parametric_kind!r}")
+        if self._fluct:
+            raise NotImplementedError("outer products of several sub-grids are not on the B200 hot path yet")
+        shape = (int(shape),) if np.ndim(shape) == 0 else tuple(int(s) for s in shape)
+        flu = _as_prior(fluctuations, LogNormalPrior, "fluctuations", optional=True)
+        slp = _as_prior(loglogavgslope, NormalPrior, "loglogavgslope")
+        flx = _as_prior(flexibility, LogNormalPrior, "flexibility", optional=True)
+        asp = _as_prior(asperity, LogNormalPrior, "asperity", optional=True)
+        self._fluct.append(dict(shape=shape, distances=distances, flu=flu, slp=slp, flx=flx, asp=asp, prefix=prefix, kind=kind))
+
+    def add_fluctuations_matern(self, *args, **kwargs):
+        raise NotImplementedError("Matern amplitudes are not on the B200 hot path yet (SURVEY.md 8f)")
+
+    def finalize(self) -> CorrelatedField:
+        """correlated_field.py:850-920: builds the grid tables (on the C side) and the model."""
+        if self._azm is None:
+            raise ValueError("set_amplitude_total_offset must be called before finalize")
+        if not self._fluct:
+            raise ValueError("add_fluctuations must be called before finalize")
+        f = self._fluct[0]
+        plan = Plan(f["shape"], f["distances"], dtype=self._dtype, hartley_convention=self._conv, runtime=self._rt)
+        sp = self._prefix + f["prefix"]
+        has_dev = f["flx"] is not None and plan.K > 2
+        domain = dict(self._parameter_tree)
+        if f["flu"] is not None:
+            domain[sp + "fluctuations"] = ()
+        domain[sp + "loglogavgslope"] = ()
+        if has_dev:
+            domain[sp + "flexibility"] = ()
+            if f["asp"] is not None:
+                domain[sp + "asperity"] = ()
+            domain[sp + "spectrum"] = (plan.K - 2, 2)
+        domain[self._prefix + "xi"] = plan.shape
+        fields = dict(kind_power=int(f["kind"] == "power"), has_fluctuations=int(f["flu"] is not None),
+                      has_deviations=int(has_dev), has_asperity=int(has_dev and f["asp"] is not None))
+        fields["zeromode_a"], fields["zeromode_b"] = self._azm.ab()
+        if f["flu"] is not None:
+            fields["fluct_a"], fields["fluct_b"] = f["flu"].ab()
+        fields["slope_a"], fields["slope_b"] = f["slp"].ab()
+        if has_dev:
+            fields["flex_a"], fields["flex_b"] = f["flx"].ab()
+            if f["asp"] is not None:
+                fields["asp_a"], fields["asp_b"] = f["asp"].ab()
+        return CorrelatedField(plan, domain, self._prefix, f["prefix"], fields, self._offset_mean)

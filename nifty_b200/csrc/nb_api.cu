@@ -400,6 +400,36 @@ int nb200_vec_dot(nb200_plan* plan, void* stream, int64_t n, const void* x, cons
   NB_CATCH
 }
 
+// Per-kernel event timing: begin() arms it, end() synchronises and writes "name count total_ms" lines.
+int nb200_timing_begin(void) {
+#ifndef NB_EMU
+  nb::kernel_timer().recs.clear(); nb::kernel_timer().on = true;
+#endif
+  return 0;
+}
+int nb200_timing_end(char* buf, int64_t buflen) {
+  NB_TRY
+  std::string out;
+#ifndef NB_EMU
+  nb::KernelTimer& kt = nb::kernel_timer();
+  kt.on = false;
+  NB_CUDA_CHECK(cudaDeviceSynchronize());
+  std::vector<std::string> names; std::vector<double> tot; std::vector<long> cnt;
+  for (auto& r : kt.recs) {
+    float ms = 0; NB_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    size_t i = 0; for (; i < names.size(); ++i) if (names[i] == r.name) break;
+    if (i == names.size()) { names.push_back(r.name); tot.push_back(0); cnt.push_back(0); }
+    tot[i] += ms; cnt[i] += 1;
+  }
+  kt.recs.clear();
+  for (size_t i = 0; i < names.size(); ++i) out += names[i] + " " + std::to_string(cnt[i]) + " " + std::to_string(tot[i]) + "\n";
+#endif
+  if (buf && buflen > 0) { size_t n = std::min<size_t>(out.size(), (size_t)buflen - 1); std::memcpy(buf, out.data(), n); buf[n] = 0; }
+  return 0;
+  NB_CATCH
+}
+
 unsigned long long nb200_launch_count(void) {
 #ifdef NB_EMU
   return 0;

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <typeinfo>
 #include <vector>
 #include "nb_common.cuh"
 
@@ -80,6 +81,14 @@ __global__ void __launch_bounds__(256) nb_kernel(const __grid_constant__ typenam
 // number of kernel launches issued by this library (bench.py reports it as gpu_launches)
 inline unsigned long long& launch_counter() { static unsigned long long c = 0; return c; }
 
+// optional per-kernel CUDA-event timing (instrumentation for bench.py's roofline section)
+struct KernelTimer {
+  bool on = false;
+  struct Rec { const char* name; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+};
+inline KernelTimer& kernel_timer() { static KernelTimer t; return t; }
+
 template <class Body>
 inline void launch(int grid, int block, size_t smem, stream_t s, const typename Body::Params& p) {
   static size_t configured[64] = {0};
@@ -90,7 +99,17 @@ inline void launch(int grid, int block, size_t smem, stream_t s, const typename 
     NB_CUDA_CHECK(cudaFuncSetAttribute(nb_kernel<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[dev] = smem;
   }
-  nb_kernel<Body><<<grid, block, smem, s>>>(p);
+  KernelTimer& kt = kernel_timer();
+  if (kt.on) {
+    KernelTimer::Rec r; r.name = typeid(Body).name();
+    NB_CUDA_CHECK(cudaEventCreate(&r.a)); NB_CUDA_CHECK(cudaEventCreate(&r.b));
+    NB_CUDA_CHECK(cudaEventRecord(r.a, s));
+    nb_kernel<Body><<<grid, block, smem, s>>>(p);
+    NB_CUDA_CHECK(cudaEventRecord(r.b, s));
+    kt.recs.push_back(r);
+  } else {
+    nb_kernel<Body><<<grid, block, smem, s>>>(p);
+  }
   NB_CUDA_CHECK(cudaGetLastError());
   ++launch_counter();
 }

@@ -1,0 +1,201 @@
+"""Likelihoods amended with the correlated-field signal model.
+
+Host-side mirror of ``nifty/re/likelihood.py`` (``Likelihood``, ``LikelihoodWithModel``:546-658) and
+``nifty/re/likelihood_impl.py`` (``Gaussian``:83-138, ``Poissonian``:203-251) for the model family of
+the hot path: ``signal = [scaling *] nl(correlated_field)``, ``nl`` in {exp, identity}
+(demos/re/0_intro.py:39-57, misc/re/paper/minimal_benchmark.py:89).  Method names, argument order
+and error behaviour follow the reference; the arithmetic runs in libniftyb200.so:
+
+* ``metric(pos, t)`` is ONE fused sequence (JVP -> likelihood metric -> VJP with the middle axis pass
+  shared) against a cached linearisation, instead of ``jax.linearize`` + ``linear_transpose`` on
+  every call (likelihood.py:613-621).
+* latent positions may be dicts (pytrees, as in the reference) or flat tensors in sorted-key order.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ._runtime import Lin, ModelHandle
+from .correlated_field import CorrelatedField
+from .prior import LogNormalPrior, _as_prior
+from .tree import Layout
+
+
+class SignalModel:
+    """``signal(p) = scaling(p) * nl(cf(p))`` with an optional log-normal ``scaling`` leaf of shape (1,)."""
+
+    def __init__(self, cf: CorrelatedField, nonlinearity: str = "exp", scaling=None, scaling_key: str = "scaling"):
+        if nonlinearity not in ("exp", "identity"):
+            raise ValueError(f"unsupported nonlinearity {nonlinearity!r}")
+        self.cf, self.nonlinearity = cf, nonlinearity
+        self.scaling = _as_prior(scaling, LogNormalPrior, "scaling", optional=True)
+        if self.scaling is not None and nonlinearity != "exp":
+            raise ValueError("`scaling` requires the exp non-linearity")
+        self.scaling_key = scaling_key
+        domain = dict(cf.domain)
+        if self.scaling is not None:
+            domain[scaling_key] = (1,)
+        self.domain = dict(sorted(domain.items()))
+        self.layout = Layout(self.domain)
+        self.rt, self.dtype, self.target_shape = cf.rt, cf.dtype, cf.target_shape
+
+    @property
+    def target(self):
+        return self.target_shape
+
+    def init(self, seed):
+        return self.layout.unpack(self.layout.random(seed, self.dtype, self.rt.device))
+
+    def as_flat(self, pos) -> torch.Tensor:
+        if isinstance(pos, torch.Tensor):
+            if pos.numel() != self.layout.size:
+                raise ValueError(f"latent vector has {pos.numel()} entries, expected {self.layout.size}")
+            return self.rt.asarray(pos.reshape(-1), self.dtype)
+        return self.layout.pack(pos, self.dtype, self.rt.device)
+
+    def like(self, template, vec):
+        return vec if isinstance(template, torch.Tensor) else self.layout.unpack(vec)
+
+    def _new_handle(self) -> ModelHandle:
+        return ModelHandle(self.cf.plan, self.cf._descriptor(self.layout, self.scaling, self.scaling_key))
+
+
+class Likelihood:
+    """Data-space likelihood before ``amend``; see :class:`Gaussian`, :class:`Poissonian`."""
+    kind = -1
+
+    def amend(self, signal, **kwargs) -> "LikelihoodWithModel":
+        if isinstance(signal, CorrelatedField):
+            signal = SignalModel(signal, "identity")
+        if not isinstance(signal, SignalModel):
+            raise TypeError("the B200 path amends likelihoods with a `SignalModel` (or a `CorrelatedField`)")
+        return LikelihoodWithModel(self, signal)
+
+
+class Gaussian(Likelihood):
+    """``jft.Gaussian(data, noise_cov_inv=None, noise_std_inv=None)`` with a DIAGONAL inverse covariance.
+
+    ``noise_cov_inv`` may be a scalar, an array, or (as in the reference) a callable ``x -> w * x``;
+    callables are probed once with ones to extract the diagonal (likelihood_impl.py:35-80).
+    """
+    kind = 0
+
+    def __init__(self, data, noise_cov_inv=None, noise_std_inv=None):
+        self.data = data
+        shape = tuple(np.shape(data)) if not isinstance(data, torch.Tensor) else tuple(data.shape)
+        if noise_cov_inv is None and noise_std_inv is None:
+            w = 1.0
+        elif noise_cov_inv is not None:
+            w = noise_cov_inv
+        else:
+            w = noise_std_inv
+        if callable(w):
+            w = w(torch.ones(shape, dtype=torch.float64))
+        if noise_cov_inv is None and noise_std_inv is not None:
+            w = w * w
+        if np.ndim(w) == 0 if not isinstance(w, torch.Tensor) else w.ndim == 0:
+            self.w_scalar, self.w_array = float(w), None
+        else:
+            self.w_scalar, self.w_array = 1.0, w
+
+
+class Poissonian(Likelihood):
+    """``jft.Poissonian(data)``: integer, non-negative counts (likelihood_impl.py:226-233)."""
+    kind = 1
+
+    def __init__(self, data):
+        arr = data.cpu().numpy() if isinstance(data, torch.Tensor) else np.asarray(data)
+        if not np.issubdtype(arr.dtype, np.integer):
+            raise TypeError("`data` of invalid type")
+        if np.any(arr < 0):
+            raise ValueError("`data` must not be negative")
+        self.data = arr
+        self.w_scalar, self.w_array = 1.0, None
+
+
+class LikelihoodWithModel:
+    """``likelihood.amend(signal)``; energy / metric / sqrt-metrics of likelihood.py:599-633."""
+
+    def __init__(self, likelihood: Likelihood, signal: SignalModel):
+        self.likelihood, self.signal = likelihood, signal
+        self.rt, self.dtype = signal.rt, signal.dtype
+        self.layout, self.domain = signal.layout, signal.domain
+        if tuple(np.shape(likelihood.data)) != tuple(signal.target_shape):
+            raise ValueError(f"data shape {np.shape(likelihood.data)} does not match the model target {signal.target_shape}")
+        self.handle = signal._new_handle()
+        self.handle.set_likelihood(likelihood.kind, int(signal.nonlinearity == "exp"), likelihood.data,
+                                   likelihood.w_scalar, likelihood.w_array)
+        self._lins = []     # small cache of linearisations: [(key, Lin)]
+        self._max_lins = 3
+
+    # -- linearisation cache --------------------------------------------------------------------
+    @staticmethod
+    def _key(flat: torch.Tensor):
+        return (flat.data_ptr(), flat._version, flat.numel())
+
+    def lin_at(self, pos, want_grad=False, add_prior=False):
+        """Linearisation at ``pos`` (cached while the tensor is neither replaced nor modified in place)."""
+        flat = self.signal.as_flat(pos)
+        key = self._key(flat)
+        if not want_grad:
+            for k, lin in self._lins:
+                if k == key:
+                    return lin, None
+        lin = None
+        for i, (k, l) in enumerate(self._lins):
+            if k == key:
+                lin = l
+                self._lins.pop(i)
+                break
+        if lin is None:
+            lin = self._lins.pop(0)[1] if len(self._lins) >= self._max_lins else Lin(self.handle)
+        grad = lin.update(flat, want_grad=want_grad, add_prior=add_prior)
+        lin._pos_ref = flat          # keep the buffer alive so the (ptr, version) key stays unique
+        self._lins.append((key, lin))
+        return lin, grad
+
+    def new_lin(self) -> Lin:
+        return Lin(self.handle)
+
+    # -- reference API ------------------------------------------------------------------------------
+    def energy(self, pos) -> float:
+        lin, _ = self.lin_at(pos)
+        return lin.energy()
+
+    __call__ = energy
+
+    def energy_and_gradient(self, pos, add_prior=False):
+        flat = self.signal.as_flat(pos)
+        lin, grad = self.lin_at(flat, want_grad=True, add_prior=add_prior)
+        e = lin.energy()
+        if add_prior:
+            e += 0.5 * float(torch.dot(flat, flat))
+        return e, self.signal.like(pos, grad)
+
+    def metric(self, pos, tangents):
+        lin, _ = self.lin_at(pos)
+        return self.signal.like(tangents, lin.metric(self.signal.as_flat(tangents)))
+
+    def left_sqrt_metric(self, pos, tangents):
+        lin, _ = self.lin_at(pos)
+        return self.signal.like(pos, lin.lsm(tangents, scaled=True))
+
+    def right_sqrt_metric(self, pos, tangents):
+        lin, _ = self.lin_at(pos)
+        return lin.rsm(self.signal.as_flat(tangents), scaled=True)
+
+    def transformation(self, pos):
+        lin, _ = self.lin_at(pos)
+        return lin.transformation()
+
+    def normalized_residual(self, pos):
+        lin, _ = self.lin_at(pos)
+        return lin.normalized_residual()
+
+    def signal_response(self, pos):
+        lin, _ = self.lin_at(pos)
+        return lin.signal()

@@ -1,0 +1,194 @@
+"""Parity checks shared by the CPU tier (host emulation of the kernel sources, tests/emu) and the
+GPU tier (libniftyb200.so through the C ABI).  Every check compares the product path with the
+committed nifty.cl fixtures and / or the NumPy oracle on identical inputs.
+
+Tolerances: float64 1e-10 relative (north star), float32 1e-5, relative to the largest entry of
+the compared quantity (leaves that are structurally ~0 only carry cancellation noise).
+"""
+import numpy as np
+import torch
+
+import nifty_b200 as nb
+import oracle
+from golden_util import CASES, build_oracle, build_oracle_lh, load, rel_err
+
+TOL = {torch.float64: 1e-10, torch.float32: 2e-5}
+POW2_CASES = [n for n in sorted(CASES) if all((s & (s - 1)) == 0 for s in CASES[n]["shape"])]
+
+
+def build_product(c, rt, dtype=torch.float64, kind="power", convention="non_canonical_hartley"):
+    cfm = nb.CorrelatedFieldMaker("cf", runtime=rt, dtype=dtype, hartley_convention=convention)
+    cfm.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+    cfm.add_fluctuations(c["shape"], c["distances"], c["fluctuations"], c["loglogavgslope"], c["flexibility"],
+                         c["asperity"], prefix="ax1", non_parametric_kind=kind)
+    return cfm.finalize()
+
+
+def build_product_lh(c, g, rt, dtype=torch.float64, scaling=None):
+    cf = build_product(c, rt, dtype)
+    sig = nb.SignalModel(cf, "exp", scaling=scaling)
+    if c["lh"] == "gauss":
+        return nb.Gaussian(g["data"], noise_cov_inv=float(g["noise_cov_inv"])).amend(sig)
+    return nb.Poissonian(g["data"]).amend(sig)
+
+
+def tree_err(got, want):
+    scale = max(float(np.max(np.abs(v))) for v in want.values())
+    assert set(got) == set(want)
+    return max(float(np.max(np.abs(got[k].detach().cpu().numpy().astype(np.float64) - want[k]))) / scale for k in want)
+
+
+def t2n(x):
+    return x.detach().cpu().numpy().astype(np.float64)
+
+
+def check_mode_tables(rt, shape, distances):
+    plan = nb.Plan(shape, distances, runtime=rt)
+    idx, um, cnt = oracle.fourier_mode_distributor(shape, distances)
+    assert plan.K == um.size
+    assert np.array_equal(plan.power_distributor, idx)
+    assert np.array_equal(plan.mode_lengths, um)
+    assert np.array_equal(plan.mode_multiplicity, cnt)
+    grid = oracle.make_fourier_grid(shape, distances)
+    # libm vs numpy log differ in the last ulp
+    np.testing.assert_allclose(plan.relative_log_mode_lengths, grid.relative_log_mode_lengths, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(plan.log_volume, grid.log_volume, rtol=0, atol=1e-14)
+    assert plan.total_volume == grid.total_volume
+
+
+def check_hartley(rt, shape, dtype=torch.float64, convention="non_canonical_hartley", seed=0):
+    plan = nb.Plan(shape, 1.0, dtype=dtype, hartley_convention=convention, runtime=rt)
+    x = np.random.default_rng(seed).standard_normal(shape)
+    out = t2n(plan.hartley(torch.as_tensor(x)))
+    ref = oracle.hartley(x, convention=convention)
+    assert rel_err(out, ref) < TOL[dtype], (shape, rel_err(out, ref))
+    # H H = N (self-inverse up to N) -- size independent property
+    if dtype == torch.float64:
+        back = t2n(plan.hartley(plan.hartley(torch.as_tensor(x)))) / x.size
+        assert rel_err(back, x) < 1e-12
+
+
+def check_bilinear(rt, shape, distances, dtype=torch.float64, seed=1):
+    plan = nb.Plan(shape, distances, dtype=dtype, runtime=rt)
+    idx, um, _ = oracle.fourier_mode_distributor(shape, distances)
+    rng = np.random.default_rng(seed)
+    amp, xi, cot = rng.standard_normal(um.size) ** 2, rng.standard_normal(shape), rng.standard_normal(shape)
+    V = plan.total_volume
+    out = t2n(plan.cf_apply(torch.as_tensor(amp), torch.as_tensor(xi), 0.3))
+    ref = 0.3 + oracle.hartley(amp[idx] * xi) / V
+    assert rel_err(out, ref) < TOL[dtype]
+    xb, ab = plan.cf_apply_adjoint(torch.as_tensor(amp), torch.as_tensor(xi), torch.as_tensor(cot))
+    g = oracle.hartley(cot) / V
+    assert rel_err(t2n(xb), amp[idx] * g) < TOL[dtype]
+    assert rel_err(t2n(ab), np.bincount(idx.ravel(), weights=(xi * g).ravel(), minlength=um.size)) < 10 * TOL[dtype]
+    xb2, none = plan.cf_apply_adjoint(torch.as_tensor(amp), None, torch.as_tensor(cot))
+    assert none is None and rel_err(t2n(xb2), amp[idx] * g) < TOL[dtype]
+
+
+def check_golden(rt, name, dtype=torch.float64):
+    """field / signal / energy / gradient / metric against the nifty.cl fixtures; sqrt-metrics,
+    transformation and residual against the oracle."""
+    c, g = CASES[name], load(name)
+    tol = TOL[dtype]
+    lh = build_product_lh(c, g, rt, dtype)
+    pos = {k: torch.as_tensor(v) for k, v in g["pos"].items()}
+    tan = {k: torch.as_tensor(v) for k, v in g["tan"].items()}
+    assert rel_err(t2n(lh.signal.cf(pos)), g["field"]) < tol
+    assert rel_err(t2n(lh.signal_response(pos)), g["signal"]) < tol
+    e, grad = lh.energy_and_gradient(pos)
+    assert abs(e - float(g["energy"])) <= tol * abs(float(g["energy"]))
+    assert tree_err(grad, g["grad"]) < tol
+    assert tree_err(lh.metric(pos, tan), g["metric"]) < tol
+    olh = build_oracle_lh(c, g)
+    assert rel_err(t2n(lh.right_sqrt_metric(pos, tan)), olh.right_sqrt_metric(g["pos"], g["tan"])) < tol
+    assert tree_err(lh.left_sqrt_metric(pos, g["cot"]), olh.left_sqrt_metric(g["pos"], g["cot"])) < tol
+    assert rel_err(t2n(lh.transformation(pos)), olh.transformation(g["pos"])) < tol
+    assert rel_err(t2n(lh.normalized_residual(pos)), olh.normalized_residual(g["pos"])) < 100 * tol
+    # field JVP / VJP of the bare correlated field (fixtures field_jvp / field_vjp)
+    lin, _ = lh.lin_at(pos)
+    assert rel_err(t2n(lin.rsm(lh.signal.as_flat(tan), scaled=False)), g["field_jvp"]) < tol
+    assert tree_err(lh.layout.unpack(lin.lsm(torch.as_tensor(g["cot"]), scaled=False)), g["field_vjp"]) < tol
+
+
+def check_kind_and_scaling(rt, name="g2d_16x16", kind="amplitude", scaling=(3.0, 1.0)):
+    """'amplitude' kind, the multiplicative log-normal scaling leaf and the canonical convention
+    (not covered by the nifty.cl fixtures) against the oracle."""
+    c, g = CASES[name], load(name)
+    for conv in ("non_canonical_hartley", "canonical_hartley"):
+        ocf = oracle.CorrelatedFieldOracle("cf", hartley_convention=conv)
+        ocf.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+        ocf.add_fluctuations(c["shape"], c["distances"], c["fluctuations"], c["loglogavgslope"], c["flexibility"],
+                             c["asperity"], prefix="ax1", non_parametric_kind=kind)
+        ocf.finalize()
+        osig = oracle.SignalOracle(ocf, "exp", scaling=scaling)
+        olh = oracle.GaussianOracle(g["data"], float(g["noise_cov_inv"]), osig)
+        cf = build_product(c, rt, kind=kind, convention=conv)
+        lh = nb.Gaussian(g["data"], noise_cov_inv=float(g["noise_cov_inv"])).amend(nb.SignalModel(cf, "exp", scaling=scaling))
+        lay = oracle.Layout(olh.domain)
+        rng = np.random.default_rng(3)
+        pos, tan = lay.random(rng), lay.random(rng)
+        tp = {k: torch.as_tensor(v) for k, v in pos.items()}
+        tt = {k: torch.as_tensor(v) for k, v in tan.items()}
+        assert rel_err(t2n(lh.signal_response(tp)), osig(pos)) < 1e-10
+        e, grad = lh.energy_and_gradient(tp)
+        oe, ograd = olh.energy_and_gradient(pos)
+        assert abs(e - oe) <= 1e-10 * abs(oe)
+        assert tree_err(grad, ograd) < 1e-10
+        assert tree_err(lh.metric(tp, tt), olh.metric(pos, tan)) < 1e-10
+        assert rel_err(t2n(lh.right_sqrt_metric(tp, tt)), olh.right_sqrt_metric(pos, tan)) < 1e-10
+        u = rng.standard_normal(c["shape"])
+        assert tree_err(lh.left_sqrt_metric(tp, u), olh.left_sqrt_metric(pos, u)) < 1e-10
+
+
+def check_metric_properties(rt, shape, distances, seed=0, dtype=torch.float64, lh_kind="gauss"):
+    """Size-independent properties at sizes the oracle cannot reach: symmetry <u, M t> = <t, M u>,
+    positivity, metric == LSM(RSM(.)) (likelihood.py:263-282) and linearity."""
+    c = dict(shape=shape, distances=distances, offset_mean=0.0, offset_std=(1e-3, 1e-4), fluctuations=(1e-1, 5e-3),
+             loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5), asperity=(0.5, 0.05), lh=lh_kind)
+    cf = build_product(c, rt, dtype)
+    sig = nb.SignalModel(cf, "exp")
+    rng = np.random.default_rng(seed)
+    pos = sig.layout.random(rng, dtype, rt.device)
+    if lh_kind == "gauss":
+        data = torch.as_tensor(rng.standard_normal(shape))
+        lh = nb.Gaussian(data, noise_cov_inv=100.0).amend(sig)
+    else:
+        lh = nb.Poissonian(rng.poisson(1.0, size=shape)).amend(sig)
+    t, u = sig.layout.random(rng, dtype, rt.device), sig.layout.random(rng, dtype, rt.device)
+    lin, _ = lh.lin_at(pos)
+    Mt, Mu = lin.metric(t), lin.metric(u)
+    a, b = float(torch.dot(u, Mt)), float(torch.dot(t, Mu))
+    tol = 1e-10 if dtype == torch.float64 else 1e-3
+    assert abs(a - b) <= tol * max(abs(a), abs(b)), (a, b)
+    assert float(torch.dot(t, Mt)) > 0
+    M2 = lin.lsm(lin.rsm(t, scaled=True), scaled=True)
+    assert float((M2 - Mt).abs().max()) <= tol * float(Mt.abs().max())
+    lin_comb = lin.metric(2.0 * t - 3.0 * u)
+    assert float((lin_comb - (2.0 * Mt - 3.0 * Mu)).abs().max()) <= tol * float(lin_comb.abs().max())
+    return lh, lin, pos
+
+
+def check_cg(rt, name="g2d_16x16"):
+    """Device CG against the oracle restatement of `_cg` on a well-conditioned case: identical
+    iteration counts, info, and solutions to 1e-10."""
+    c, g = CASES[name], load(name)
+    lh = build_product_lh(c, g, rt)
+    olh = build_oracle_lh(c, g)
+    lay = oracle.Layout(olh.domain)
+    pos_v = lay.pack(g["pos"])
+    rng = np.random.default_rng(5)
+    j, x0 = rng.standard_normal(lay.size), rng.standard_normal(lay.size)
+
+    def mat(v):
+        return lay.pack(olh.metric(g["pos"], lay.unpack(v))) + v
+
+    lin, _ = lh.lin_at(torch.as_tensor(pos_v))
+    tj, tx0 = rt.asarray(j, torch.float64), rt.asarray(x0, torch.float64)
+    for kw in [dict(absdelta=1e-6, maxiter=100), dict(), dict(resnorm=1e-3, norm_ord=1, maxiter=50),
+               dict(absdelta=1e-8, maxiter=45), dict(absdelta=1e-30, maxiter=7, miniter=7),
+               dict(absdelta=1e-30, maxiter=23, miniter=23)]:
+        for use_x0 in (True, False):
+            ores = oracle.cg(mat, j, x0=x0 if use_x0 else None, **kw)
+            x, res = lin.cg_solve(tj, tx0 if use_x0 else None, check_every=3, **kw)
+            assert (res.nit, res.info, res.nfev) == (ores.nit, ores.info, ores.nfev), (kw, use_x0)
+            assert rel_err(t2n(x), ores.x) < 1e-10, (kw, use_x0)

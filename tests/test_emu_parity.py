@@ -1,0 +1,60 @@
+"""CPU tier: the kernel sources executed sequentially on the host (tests/emu) against the oracle and
+the nifty.cl fixtures.  Checks host logic, index arithmetic and call sequences without a GPU; the
+GPU tier (test_gpu_parity.py) runs the same checks through libniftyb200.so."""
+import pytest
+import torch
+
+import nifty_b200 as nb
+import parity_checks as pc
+from nifty_b200._capi import CApi
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from emu.build_emu import build
+    return nb.Runtime(CApi(build()), "cpu")
+
+
+@pytest.mark.parametrize("shape,dist", [((16,), 0.1), ((2,), 1.0), ((4, 4), 1.0), ((8, 32), (0.3, 0.11)),
+                                        ((2, 2), 1.0), ((4, 8, 16), (0.2, 0.1, 0.05)), ((2, 2, 2), 1.0),
+                                        ((32, 4), 1.0), ((4, 2, 32), 1.0), ((128, 128), 1.0 / 128)])
+def test_tables_hartley_bilinear(rt, shape, dist):
+    pc.check_mode_tables(rt, shape, dist)
+    pc.check_hartley(rt, shape)
+    pc.check_hartley(rt, shape, convention="canonical_hartley")
+    pc.check_bilinear(rt, shape, dist)
+
+
+def test_hartley_float32(rt):
+    pc.check_hartley(rt, (16, 32), dtype=torch.float32)
+    pc.check_bilinear(rt, (8, 4, 16), 0.5, dtype=torch.float32)
+
+
+@pytest.mark.parametrize("name", pc.POW2_CASES)
+def test_golden(rt, name):
+    pc.check_golden(rt, name)
+
+
+def test_golden_float32(rt):
+    pc.check_golden(rt, "g2d_16x16", dtype=torch.float32)
+
+
+@pytest.mark.parametrize("kind", ["amplitude", "power"])
+def test_kind_scaling_convention(rt, kind):
+    pc.check_kind_and_scaling(rt, kind=kind)
+
+
+def test_metric_properties(rt):
+    pc.check_metric_properties(rt, (32, 64), (0.1, 0.05))
+    pc.check_metric_properties(rt, (8, 16, 8), 0.3, lh_kind="poisson")
+
+
+def test_cg(rt):
+    pc.check_cg(rt)
+
+
+def test_unsupported_shapes_fail_loudly(rt):
+    with pytest.raises(nb.NB200Error, match="power of two"):
+        nb.Plan((3, 3), 0.1, runtime=rt)
+    with pytest.raises(nb.NB200Error):
+        nb.Plan((4, 4, 4, 4), 0.1, runtime=rt)

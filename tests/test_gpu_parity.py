@@ -1,0 +1,78 @@
+"""GPU tier (-m gpu): the product path -- hand-written sm_100a kernels through the C ABI -- against the
+nifty.cl fixtures, the oracle at sizes it finishes in seconds, and size-independent properties at
+BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+import nifty_b200 as nb
+import parity_checks as pc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rt():
+    return nb.default_runtime()
+
+
+@pytest.mark.parametrize("shape,dist", [((16,), 0.1), ((2,), 1.0), ((4, 4), 1.0), ((8, 32), (0.3, 0.11)),
+                                        ((2, 2), 1.0), ((4, 8, 16), (0.2, 0.1, 0.05)), ((2, 2, 2), 1.0),
+                                        ((32, 4), 1.0), ((4, 2, 32), 1.0), ((128, 128), 1.0 / 128),
+                                        ((512, 256), 1.0), ((64, 32, 16), 0.1), ((4096,), 1.0)])
+def test_tables_hartley_bilinear(rt, shape, dist):
+    pc.check_mode_tables(rt, shape, dist)
+    pc.check_hartley(rt, shape)
+    pc.check_hartley(rt, shape, convention="canonical_hartley")
+    pc.check_bilinear(rt, shape, dist)
+
+
+def test_hartley_float32(rt):
+    pc.check_hartley(rt, (16, 32), dtype=torch.float32)
+    pc.check_hartley(rt, (256, 512), dtype=torch.float32)
+    pc.check_bilinear(rt, (8, 4, 16), 0.5, dtype=torch.float32)
+
+
+@pytest.mark.parametrize("name", pc.POW2_CASES)
+def test_golden(rt, name):
+    pc.check_golden(rt, name)
+
+
+def test_golden_float32(rt):
+    pc.check_golden(rt, "g2d_16x16", dtype=torch.float32)
+
+
+@pytest.mark.parametrize("kind", ["amplitude", "power"])
+def test_kind_scaling_convention(rt, kind):
+    pc.check_kind_and_scaling(rt, kind=kind)
+
+
+def test_cg(rt):
+    pc.check_cg(rt)
+
+
+@pytest.mark.parametrize("shape,dist,kind", [((128, 128), 1.0 / 128, "gauss"), ((2048, 2048), 1.0 / 2048, "poisson"),
+                                             ((4096, 4096), 1.0 / 4096, "gauss"), ((256, 256, 256), 1.0 / 256, "gauss")])
+def test_full_size_properties(rt, shape, dist, kind):
+    """BASELINE.json configs 1-4 at full size: Hartley round trip, metric symmetry / positivity /
+    LSM.RSM factorisation / linearity; 256^3 and 4096^2 are far beyond what the oracle can check."""
+    plan = nb.Plan(shape, dist, runtime=rt)
+    x = torch.randn(shape, dtype=torch.float64, device=rt.device, generator=torch.Generator(rt.device).manual_seed(1))
+    back = plan.hartley(plan.hartley(x)) / x.numel()
+    assert float((back - x).abs().max()) < 1e-11
+    # Parseval for the orthonormalised Hartley transform
+    hx = plan.hartley(x)
+    assert abs(float((hx * hx).sum()) / x.numel() - float((x * x).sum())) < 1e-10 * float((x * x).sum())
+    del plan, hx, back
+    pc.check_metric_properties(rt, shape, dist, lh_kind=kind)
+
+
+def test_hartley_vs_torch_fft_large(rt):
+    """Independent check of the transform arithmetic at 1024^2 against torch.fft (cuFFT), rel 1e-10."""
+    shape = (1024, 1024)
+    plan = nb.Plan(shape, 1.0, runtime=rt)
+    x = torch.randn(shape, dtype=torch.float64, device=rt.device)
+    f = torch.fft.fftn(x)
+    ref = f.real + f.imag
+    out = plan.hartley(x)
+    assert float((out - ref).abs().max()) < 1e-10 * float(ref.abs().max())
