@@ -14,11 +14,13 @@
 
 #ifdef NB_EMU
 #define NB_HD
+#define NB_HH
 #define NB_DEV
 #define NB_INLINE inline
 #else
 #include <cuda_runtime.h>
 #define NB_HD __device__
+#define NB_HH __host__ __device__   // pure helpers also usable from host code
 #define NB_DEV __device__
 #define NB_INLINE __forceinline__
 #endif
@@ -30,15 +32,15 @@ struct alignas(2 * sizeof(T)) cplx {
   T x, y;
 };
 
-template <class T> NB_HD NB_INLINE cplx<T> cmake(T x, T y) { cplx<T> c; c.x = x; c.y = y; return c; }
-template <class T> NB_HD NB_INLINE cplx<T> operator+(cplx<T> a, cplx<T> b) { return cmake<T>(a.x + b.x, a.y + b.y); }
-template <class T> NB_HD NB_INLINE cplx<T> operator-(cplx<T> a, cplx<T> b) { return cmake<T>(a.x - b.x, a.y - b.y); }
-template <class T> NB_HD NB_INLINE cplx<T> cmul(cplx<T> a, cplx<T> b) {
+template <class T> NB_HH NB_INLINE cplx<T> cmake(T x, T y) { cplx<T> c; c.x = x; c.y = y; return c; }
+template <class T> NB_HH NB_INLINE cplx<T> operator+(cplx<T> a, cplx<T> b) { return cmake<T>(a.x + b.x, a.y + b.y); }
+template <class T> NB_HH NB_INLINE cplx<T> operator-(cplx<T> a, cplx<T> b) { return cmake<T>(a.x - b.x, a.y - b.y); }
+template <class T> NB_HH NB_INLINE cplx<T> cmul(cplx<T> a, cplx<T> b) {
   return cmake<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-template <class T> NB_HD NB_INLINE cplx<T> cconj(cplx<T> a) { return cmake<T>(a.x, -a.y); }
+template <class T> NB_HH NB_INLINE cplx<T> cconj(cplx<T> a) { return cmake<T>(a.x, -a.y); }
 // multiply by -i
-template <class T> NB_HD NB_INLINE cplx<T> cmul_mi(cplx<T> a) { return cmake<T>(a.y, -a.x); }
+template <class T> NB_HH NB_INLINE cplx<T> cmul_mi(cplx<T> a) { return cmake<T>(a.y, -a.x); }
 
 // ---------------------------------------------------------------------------------------------
 // execution contexts
@@ -129,8 +131,8 @@ template <> __device__ NB_INLINE cplx<float> ldg(const cplx<float>* p) {
 
 #define NB_FOR(ctx, i, count) for (int i = (ctx).tid; i < (int)(count); i += (ctx).nthr)
 
-NB_HD NB_INLINE int fold_idx(int x, int n) { return x <= n - x ? x : n - x; }
-NB_HD NB_INLINE int neg_idx(int x, int n) { return x == 0 ? 0 : n - x; }
+NB_HH NB_INLINE int fold_idx(int x, int n) { return x <= n - x ? x : n - x; }
+NB_HH NB_INLINE int neg_idx(int x, int n) { return x == 0 ? 0 : n - x; }
 
 template <class T> NB_HD NB_INLINE T nb_exp(T x);
 template <> NB_HD NB_INLINE double nb_exp(double x) { return exp(x); }

@@ -15,10 +15,10 @@
 namespace nb {
 
 // log2 of the radix used for a sub-transform of length 2^lm: 8 except for the 2/4/16 leftovers.
-NB_HD NB_INLINE int fft_radix_lg(int lm) { return lm == 1 ? 1 : ((lm == 2 || lm == 4) ? 2 : 3); }
+NB_HH NB_INLINE int fft_radix_lg(int lm) { return lm == 1 ? 1 : ((lm == 2 || lm == 4) ? 2 : 3); }
 
 // slot of output element k after fft_dif of length 2^lg (== slot where fft_dit expects input k)
-NB_HD NB_INLINE int fft_pos(int k, int lg) {
+NB_HH NB_INLINE int fft_pos(int k, int lg) {
   int pos = 0, lm = lg;
   while (lm > 0) {
     int lr = fft_radix_lg(lm);
