@@ -4,11 +4,22 @@
 //   fft_dif : natural order in  -> digit-reversed order out   (decimation in frequency)
 //   fft_dit : digit-reversed in -> natural order out          (decimation in time)
 // Both use radix(m) for the stage whose sub-transform length is m, so that the output order of
-// fft_dif is exactly the input order of fft_dit; `fft_pos(k, lg)` is the slot of element k.
-// Every butterfly reads and writes the same r slots, so no thread carries registers across a
-// barrier (which is also what lets tests/emu run the same code sequentially on the host).
-// Twiddles come from a table tw[j] = exp(-2 pi i j / tw_n) (tw_n a multiple of n) computed on the
-// host in extended precision.
+// fft_dif is exactly the input order of fft_dit; `fft_pos(k, lg)` is the LOGICAL slot of element k.
+//
+// Design points (each one answers a measured stall, see profiles/):
+//  * logical slot i lives at physical slot swz(i) = i ^ (xor of the 3-bit digits above the lowest):
+//    every access pattern in which the 8 threads of a quarter-warp differ in one octal digit --
+//    all radix-8 stages, and the digit-reversed reads of the combine / store phases -- is free of
+//    bank conflicts for 16-byte elements, without padding (a 4096-point f64 line stays 64 KB, so
+//    three CTAs fit one SM).  swz is GF(2)-linear: swz(b + (q << s)) = swz(b) ^ swz(q << s) when the
+//    bits are disjoint, i.e. one swizzle per butterfly plus one XOR per element.
+//  * the first DIF stage reads its inputs straight from global memory through a loader functor
+//    (8 independent coalesced loads per thread) -- one shared-memory round trip and one barrier
+//    less per line, and the prologue of a pass (amplitude gather etc.) is fused into it.
+//  * one twiddle load per butterfly (w_m^j, coalesced, L1/L2 resident table computed on the host
+//    in extended precision); w^2..w^7 are formed by multiplication (<= 3 roundings deep).
+//  * every butterfly reads and writes the same r slots, so no thread carries registers across a
+//    barrier (which is also what lets tests/emu run the same code sequentially on the host).
 #pragma once
 #include "nb_common.cuh"
 
@@ -17,7 +28,7 @@ namespace nb {
 // log2 of the radix used for a sub-transform of length 2^lm: 8 except for the 2/4/16 leftovers.
 NB_HH NB_INLINE int fft_radix_lg(int lm) { return lm == 1 ? 1 : ((lm == 2 || lm == 4) ? 2 : 3); }
 
-// slot of output element k after fft_dif of length 2^lg (== slot where fft_dit expects input k)
+// logical slot of output element k after fft_dif of length 2^lg (== slot where fft_dit expects input k)
 NB_HH NB_INLINE int fft_pos(int k, int lg) {
   int pos = 0, lm = lg;
   while (lm > 0) {
@@ -29,6 +40,9 @@ NB_HH NB_INLINE int fft_pos(int k, int lg) {
   }
   return pos;
 }
+
+// physical slot of logical slot i (within one line)
+NB_HH NB_INLINE int swz(int i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9) ^ (i >> 12)) & 7); }
 
 template <class T> struct FftConst;
 template <> struct FftConst<double> { static NB_HD NB_INLINE double rsqrt2() { return 0.70710678118654752440; } };
@@ -70,8 +84,25 @@ template <int LR, class T> NB_HD NB_INLINE void dftR(cplx<T>* a) {
   else dft8(a);
 }
 
-// One radix-2^LR stage over all lines.  lm = log2 of the sub-transform length of this stage.
-// DIF: y_p = (sum_q x_q w_R^{pq}) w_m^{jp};   DIT: y_p = sum_q (x_q w_m^{jq}) w_R^{pq}
+// a[q] *= w^q, q = 1..R-1, powers of w formed by multiplication
+template <int LR, class T> NB_HD NB_INLINE void twiddle_apply(cplx<T>* a, cplx<T> w) {
+  a[1] = cmul(a[1], w);
+  if (LR >= 2) {
+    cplx<T> w2 = cmul(w, w), w3 = cmul(w2, w);
+    a[2] = cmul(a[2], w2);
+    a[3] = cmul(a[3], w3);
+    if (LR >= 3) {
+      cplx<T> w4 = cmul(w2, w2);
+      a[4] = cmul(a[4], w4);
+      a[5] = cmul(a[5], cmul(w4, w));
+      a[6] = cmul(a[6], cmul(w3, w3));
+      a[7] = cmul(a[7], cmul(w4, w3));
+    }
+  }
+}
+
+// One radix-2^LR stage over all lines, data in shared memory.  lm = log2 of the sub-transform
+// length of this stage.  DIF: y_p = (sum_q x_q w_R^{pq}) w_m^{jp};  DIT: y_p = sum_q (x_q w_m^{jq}) w_R^{pq}
 template <int LR, bool DIT, class T>
 NB_HD NB_INLINE void fft_stage(Ctx& ctx, cplx<T>* s, int lg, int lm, int nlines, int pitch,
                                const cplx<T>* tw, int tw_shift /* log2(tw_n) - lm */) {
@@ -79,24 +110,51 @@ NB_HD NB_INLINE void fft_stage(Ctx& ctx, cplx<T>* s, int lg, int lm, int nlines,
   const int lmr = lm - LR;              // log2(m / R)
   const int lbf = lg - LR;              // log2(butterflies per line)
   const int total = nlines << lbf;
+  int off[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) off[q] = swz(q << lmr);
   NB_FOR(ctx, t, total) {
     int line = t >> lbf, u = t & ((1 << lbf) - 1);
     int blk = u >> lmr, j = u & ((1 << lmr) - 1);
-    cplx<T>* base = s + (size_t)line * pitch + (blk << lm) + j;
+    cplx<T> w = cmake<T>(T(1), T(0));
+    if (j != 0) w = ldg(tw + ((size_t)j << tw_shift));
+    cplx<T>* base = s + (size_t)line * pitch;
+    const int b0 = swz((blk << lm) + j);
     cplx<T> a[R];
 #pragma unroll
-    for (int q = 0; q < R; ++q) a[q] = base[q << lmr];
-    if (DIT && j != 0) {
-#pragma unroll
-      for (int q = 1; q < R; ++q) a[q] = cmul(a[q], ldg(tw + ((size_t)(j * q) << tw_shift)));
-    }
+    for (int q = 0; q < R; ++q) a[q] = base[b0 ^ off[q]];
+    if (DIT && j != 0) twiddle_apply<LR>(a, w);
     dftR<LR>(a);
-    if (!DIT && j != 0) {
+    if (!DIT && j != 0) twiddle_apply<LR>(a, w);
 #pragma unroll
-      for (int q = 1; q < R; ++q) a[q] = cmul(a[q], ldg(tw + ((size_t)(j * q) << tw_shift)));
-    }
+    for (int q = 0; q < R; ++q) base[b0 ^ off[q]] = a[q];
+  }
+  ctx.sync();
+}
+
+// First DIF stage (m = n) with the inputs taken from a loader: ld(line, x) -> cplx<T>
+template <int LR, class T, class Ld>
+NB_HD NB_INLINE void fft_stage_first(Ctx& ctx, cplx<T>* s, int lg, int nlines, int pitch,
+                                     const cplx<T>* tw, int tw_shift, const Ld& ld) {
+  constexpr int R = 1 << LR;
+  const int lmr = lg - LR;
+  const int total = nlines << lmr;
+  int off[R];
 #pragma unroll
-    for (int q = 0; q < R; ++q) base[q << lmr] = a[q];
+  for (int q = 0; q < R; ++q) off[q] = swz(q << lmr);
+  NB_FOR(ctx, t, total) {
+    int line = t >> lmr, j = t & ((1 << lmr) - 1);
+    cplx<T> a[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) a[q] = ld(line, j + (q << lmr));
+    cplx<T> w = cmake<T>(T(1), T(0));
+    if (j != 0) w = ldg(tw + ((size_t)j << tw_shift));
+    dftR<LR>(a);
+    if (j != 0) twiddle_apply<LR>(a, w);
+    cplx<T>* base = s + (size_t)line * pitch;
+    const int b0 = swz(j);
+#pragma unroll
+    for (int q = 0; q < R; ++q) base[b0 ^ off[q]] = a[q];
   }
   ctx.sync();
 }
@@ -110,21 +168,30 @@ NB_HD NB_INLINE void fft_stage_any(Ctx& ctx, cplx<T>* s, int lg, int lm, int nli
   else fft_stage<1, DIT>(ctx, s, lg, lm, nlines, pitch, tw, lg_tw - lm);
 }
 
-// natural -> digit-reversed.  Caller must have synchronised after filling `s`; returns synchronised.
-template <class T>
-NB_HD NB_INLINE void fft_dif(Ctx& ctx, cplx<T>* s, int lg, int nlines, int pitch, const cplx<T>* tw, int lg_tw) {
-  int lm = lg;
+// natural order from `ld` -> digit-reversed (swizzled) in shared memory; returns synchronised.
+template <class T, class Ld>
+NB_HD NB_INLINE void fft_dif_load(Ctx& ctx, cplx<T>* s, int lg, int nlines, int pitch, const cplx<T>* tw, int lg_tw,
+                                  const Ld& ld) {
+  if (lg == 0) {
+    NB_FOR(ctx, t, nlines) s[(size_t)t * pitch] = ld(t, 0);
+    ctx.sync();
+    return;
+  }
+  int lr = fft_radix_lg(lg);
+  if (lr == 3) fft_stage_first<3>(ctx, s, lg, nlines, pitch, tw, lg_tw - lg, ld);
+  else if (lr == 2) fft_stage_first<2>(ctx, s, lg, nlines, pitch, tw, lg_tw - lg, ld);
+  else fft_stage_first<1>(ctx, s, lg, nlines, pitch, tw, lg_tw - lg, ld);
+  int lm = lg - lr;
   while (lm > 0) {
     fft_stage_any<false>(ctx, s, lg, lm, nlines, pitch, tw, lg_tw);
     lm -= fft_radix_lg(lm);
   }
 }
 
-// digit-reversed -> natural
+// digit-reversed (swizzled) -> natural (swizzled); caller synchronised after filling; returns synchronised
 template <class T>
 NB_HD NB_INLINE void fft_dit(Ctx& ctx, cplx<T>* s, int lg, int nlines, int pitch, const cplx<T>* tw, int lg_tw) {
-  // the stage lengths of fft_dif in reverse order
-  int lms[32], ns = 0, lm = lg;
+  int lms[16], ns = 0, lm = lg;
   while (lm > 0) { lms[ns++] = lm; lm -= fft_radix_lg(lm); }
   for (int i = ns - 1; i >= 0; --i) fft_stage_any<true>(ctx, s, lg, lms[i], nlines, pitch, tw, lg_tw);
 }

@@ -98,20 +98,19 @@ template <class T, class Pro> struct P1Body {
     const int R = 1 << p.lg_R, lg_h = p.lg_n - 1, h = 1 << lg_h;
     const int gpo = (p.n_r + R - 1) >> p.lg_R;
     const int o = ctx.bid / gpo, rr0 = (ctx.bid % gpo) << p.lg_R;
-    NB_FOR(ctx, i, R << lg_h) {
-      int r = i >> lg_h, j = i & (h - 1), rr = rr0 + r;
+    auto ld = [&](int r, int j) {
+      int rr = rr0 + r;
       T a = 0, b = 0;
       if (rr < p.n_r) p.pro.load2(o, rr, 2 * j, o * p.in_ostride + rr * p.in_rstride + 2 * j, a, b);
-      s[r * p.pitch + j] = cmake<T>(a, b);
-    }
-    ctx.sync();
-    fft_dif(ctx, s, lg_h, R, p.pitch, p.tw, p.lg_tw);   // w_h^j = w_n^{2j}: same table, larger stride
+      return cmake<T>(a, b);
+    };
+    fft_dif_load(ctx, s, lg_h, R, p.pitch, p.tw, p.lg_tw, ld);   // w_h^j = w_n^{2j}: same table, larger stride
     const T half = T(0.5);
     NB_FOR(ctx, i, (h + 1) << p.lg_R) {
       int k = i >> p.lg_R, r = i & (R - 1), rr = rr0 + r;
       if (rr >= p.n_r) continue;
-      cplx<T> zk = s[r * p.pitch + fft_pos(k & (h - 1), lg_h)];
-      cplx<T> zc = cconj(s[r * p.pitch + fft_pos((h - k) & (h - 1), lg_h)]);
+      cplx<T> zk = s[r * p.pitch + swz(fft_pos(k & (h - 1), lg_h))];
+      cplx<T> zc = cconj(s[r * p.pitch + swz(fft_pos((h - k) & (h - 1), lg_h))]);
       cplx<T> e = zk + zc, d = zk - zc;
       cplx<T> w = ldg(p.tw + ((size_t)k << (p.lg_tw - p.lg_n)));
       cplx<T> wd = cmul_mi(cmul(w, d));   // -i w (zk - zc)
@@ -140,18 +139,17 @@ template <class T> struct PCBody {
     const int R = 1 << p.lg_R, n = 1 << p.lg_n;
     const int gpo = (p.n_r + R - 1) >> p.lg_R;
     const int o = ctx.bid / gpo, rr0 = (ctx.bid % gpo) << p.lg_R;
-    NB_FOR(ctx, i, R << p.lg_n) {
-      int r = i >> p.lg_n, x = i & (n - 1), rr = rr0 + r;
+    auto ld = [&](int r, int x) {
+      int rr = rr0 + r;
       cplx<T> v = cmake<T>(0, 0);
       if (rr < p.n_r) v = p.in[o * p.in_ostride + rr * p.in_rstride + x];
-      s[r * p.pitch + x] = v;
-    }
-    ctx.sync();
-    fft_dif(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw);
+      return v;
+    };
+    fft_dif_load(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw, ld);
     NB_FOR(ctx, i, n << p.lg_R) {
       int k = i >> p.lg_R, r = i & (R - 1), rr = rr0 + r;
       if (rr >= p.n_r) continue;
-      p.out[o * p.out_ostride + k * p.out_kstride + rr] = s[r * p.pitch + fft_pos(k, p.lg_n)];
+      p.out[o * p.out_ostride + k * p.out_kstride + rr] = s[r * p.pitch + swz(fft_pos(k, p.lg_n))];
     }
   }
 };
@@ -285,19 +283,18 @@ template <class T, bool FWD, bool ADJ> struct P3Body {
     T cshift = p.op.cshift_ptr ? p.op.cshift_scale * ldg(p.op.cshift_ptr) : T(0);
     T scv = p.op.sc_ptr ? ldg(p.op.sc_ptr) : p.op.sc;
     if (FWD) {
-      NB_FOR(ctx, i, R << p.lg_n) {
-        int r = i >> p.lg_n, x = i & (n - 1), l = l0 + r, lA, lB;
+      auto ld = [&](int r, int x) {
+        int l = l0 + r, lA, lB;
         cplx<T> v = cmake<T>(0, 0);
         if (l < nl && p.mg.resolve(l, lA, lB)) v = p.in[(long)l * n + x];
-        s[r * p.pitch + x] = v;
-      }
-      ctx.sync();
-      fft_dif(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw);
+        return v;
+      };
+      fft_dif_load(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw, ld);
       // Hermitian combine + pointwise operator on the pair (x, y = -x)
       NB_FOR(ctx, i, R * (h + 1)) {
         int r = i / (h + 1), x = i - r * (h + 1), y = (n - x) & (n - 1), l = l0 + r, lA, lB;
         if (l >= nl || !p.mg.resolve(l, lA, lB)) continue;
-        int px = fft_pos(x, p.lg_n), py = fft_pos(y, p.lg_n);
+        int px = swz(fft_pos(x, p.lg_n)), py = swz(fft_pos(y, p.lg_n));
         cplx<T> cx = s[r * p.pitch + px], cy = s[r * p.pitch + py];
         T aX = cx.x + sg * cx.y, bY = cx.x - sg * cx.y;
         T aY = cy.x + sg * cy.y, bX = cy.x - sg * cy.y;
@@ -320,7 +317,7 @@ template <class T, bool FWD, bool ADJ> struct P3Body {
           v.x = p.op.load(lA, x, acc0);
           if (lB >= 0) v.y = p.op.load(lB, x, acc0);
         }
-        s[r * p.pitch + fft_pos(x, p.lg_n)] = v;
+        s[r * p.pitch + swz(fft_pos(x, p.lg_n))] = v;
       }
     }
     if (ADJ) {
@@ -330,7 +327,7 @@ template <class T, bool FWD, bool ADJ> struct P3Body {
       NB_FOR(ctx, i, (h + 1) << p.lg_R) {
         int k = i >> p.lg_R, r = i & (R - 1), l = l0 + r, lA, lB;
         if (l >= nl || !p.mg.resolve(l, lA, lB)) continue;
-        cplx<T> zk = s[r * p.pitch + k], zc = cconj(s[r * p.pitch + ((n - k) & (n - 1))]);
+        cplx<T> zk = s[r * p.pitch + swz(k)], zc = cconj(s[r * p.pitch + swz((n - k) & (n - 1))]);
         cplx<T> e = zk + zc, d = cmul_mi(zk - zc);
         p.out[k * p.out_kstride + lA] = cmake<T>(half * e.x, half * e.y);
         if (lB >= 0) p.out[k * p.out_kstride + lB] = cmake<T>(half * d.x, half * d.y);
@@ -407,19 +404,18 @@ template <class T, class Epi> struct P5Body {
     const int l0 = ctx.bid << p.lg_R, nl = p.mg.nlines();
     const T sg = p.hsign;
     T acc = 0;
-    NB_FOR(ctx, i, R << p.lg_n) {
-      int r = i >> p.lg_n, x = i & (n - 1), l = l0 + r, lA, lB;
+    auto ld = [&](int r, int x) {
+      int l = l0 + r, lA, lB;
       cplx<T> v = cmake<T>(0, 0);
       if (l < nl && p.mg.resolve(l, lA, lB)) v = p.in[(long)l * n + x];
-      s[r * p.pitch + x] = v;
-    }
-    ctx.sync();
-    fft_dif(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw);
+      return v;
+    };
+    fft_dif_load(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw, ld);
     const int nmid = 1 << p.mg.lg_mid;
     NB_FOR(ctx, i, R * (h + 1)) {
       int r = i / (h + 1), x = i - r * (h + 1), y = (n - x) & (n - 1), l = l0 + r, lA, lB;
       if (l >= nl || !p.mg.resolve(l, lA, lB)) continue;
-      cplx<T> cx = s[r * p.pitch + fft_pos(x, p.lg_n)], cy = s[r * p.pitch + fft_pos(y, p.lg_n)];
+      cplx<T> cx = s[r * p.pitch + swz(fft_pos(x, p.lg_n))], cy = s[r * p.pitch + swz(fft_pos(y, p.lg_n))];
       T gAx = cx.x + sg * cx.y, gBy = cx.x - sg * cx.y;
       T gAy = cy.x + sg * cy.y, gBx = cy.x - sg * cy.y;
       int a = lA >> p.mg.lg_mid, km = lA & (nmid - 1);

@@ -168,27 +168,35 @@ def check_metric_properties(rt, shape, distances, seed=0, dtype=torch.float64, l
     return lh, lin, pos
 
 
-def check_cg(rt, name="g2d_16x16"):
-    """Device CG against the oracle restatement of `_cg` on a well-conditioned case: identical
-    iteration counts, info, and solutions to 1e-10."""
-    c, g = CASES[name], load(name)
-    lh = build_product_lh(c, g, rt)
-    olh = build_oracle_lh(c, g)
-    lay = oracle.Layout(olh.domain)
-    pos_v = lay.pack(g["pos"])
-    rng = np.random.default_rng(5)
-    j, x0 = rng.standard_normal(lay.size), rng.standard_normal(lay.size)
+def check_cg(rt):
+    """Device CG against the oracle restatement of `_cg`: identical iteration counts, info and nfev,
+    solutions to 1e-10 on a well-conditioned case; the N_RESET branch (iteration 20) on a case that
+    is not yet converged there (rounding differences grow with the iteration count, hence 1e-6)."""
+    runs = [("g2d_16x16", dict(absdelta=1e-6, maxiter=100), 1e-10), ("g2d_16x16", dict(), 1e-10),
+            ("g2d_16x16", dict(resnorm=1e-3, norm_ord=1, maxiter=50), 1e-10),
+            ("g2d_16x16", dict(absdelta=1e-8, maxiter=45), 1e-10),
+            ("g2d_16x16", dict(absdelta=1e-30, maxiter=7, miniter=7), 1e-10),
+            ("g3d_4x8x16", dict(absdelta=1e-30, maxiter=23, miniter=24), 1e-6),
+            ("g3d_4x8x16", dict(resnorm=10.0, norm_ord=np.inf, maxiter=60), 1e-7)]
+    cache = {}
+    for name, kw, tol in runs:
+        if name not in cache:
+            c, g = CASES[name], load(name)
+            lh = build_product_lh(c, g, rt)
+            olh = build_oracle_lh(c, g)
+            lay = oracle.Layout(olh.domain)
+            rng = np.random.default_rng(5)
+            j, x0 = rng.standard_normal(lay.size), rng.standard_normal(lay.size)
+            lin, _ = lh.lin_at(torch.as_tensor(lay.pack(g["pos"])))
+            cache[name] = (g, lh, olh, lay, j, x0, lin)
+        g, lh, olh, lay, j, x0, lin = cache[name]
 
-    def mat(v):
-        return lay.pack(olh.metric(g["pos"], lay.unpack(v))) + v
+        def mat(v):
+            return lay.pack(olh.metric(g["pos"], lay.unpack(v))) + v
 
-    lin, _ = lh.lin_at(torch.as_tensor(pos_v))
-    tj, tx0 = rt.asarray(j, torch.float64), rt.asarray(x0, torch.float64)
-    for kw in [dict(absdelta=1e-6, maxiter=100), dict(), dict(resnorm=1e-3, norm_ord=1, maxiter=50),
-               dict(absdelta=1e-8, maxiter=45), dict(absdelta=1e-30, maxiter=7, miniter=7),
-               dict(absdelta=1e-30, maxiter=23, miniter=23)]:
+        tj, tx0 = rt.asarray(j, torch.float64), rt.asarray(x0, torch.float64)
         for use_x0 in (True, False):
             ores = oracle.cg(mat, j, x0=x0 if use_x0 else None, **kw)
             x, res = lin.cg_solve(tj, tx0 if use_x0 else None, check_every=3, **kw)
-            assert (res.nit, res.info, res.nfev) == (ores.nit, ores.info, ores.nfev), (kw, use_x0)
-            assert rel_err(t2n(x), ores.x) < 1e-10, (kw, use_x0)
+            assert (res.nit, res.info, res.nfev) == (ores.nit, ores.info, ores.nfev), (name, kw, use_x0)
+            assert rel_err(t2n(x), ores.x) < tol, (name, kw, use_x0)
