@@ -1,0 +1,334 @@
+#!/usr/bin/env python3
+"""bench.py -- metric-vector products per second of the MGVI inner loop (BASELINE.json metric).
+
+A *step* is one application of M_p = F_p + 1 (``lh.metric(pos, t) + t``: Fisher metric of
+Gaussian(data, N^-1) o exp o CorrelatedField plus identity) on the configured grid -- the quantity
+the reference itself benchmarks (misc/re/paper/minimal_benchmark.py:93-114, paper.md:283-307) and
+the operation every CG iteration of an MGVI sample draw runs (nifty/re/evi.py:83-85,139-144).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+* N=1 workload: BASELINE.json configs[1], 2-D correlated field 4096x4096 float64.
+* N>1 (torchrun): the independent MGVI samples are sharded over the ranks (one CG solve per GPU, no
+  data-path collective) -> weak scaling; value = products of all ranks / max time.
+* ``value``: device-resident inputs, CUDA events.  ``e2e``: the public Python API with HOST (pinned)
+  buffers, H2D of the tangent and D2H of the result inside the timed region.
+* ``roofline``: the dominant kernel's algorithmic bytes / its CUDA-event duration against the
+  measured HBM peak of MEASURED_PEAKS.json; ``cpu_baseline``: the NumPy/scipy.fft oracle port on
+  the host cores (bounded sample).  ``--impl reference`` times that CPU path as its own arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (shape, description)
+    "cf2d_4096_f64": ((4096, 4096), "2D correlated field 4096x4096 float64 (BASELINE.json configs[1])"),
+    "cf2d_2048_f64": ((2048, 2048), "2D correlated field 2048x2048 float64"),
+    "cf3d_256_f64": ((256, 256, 256), "3D correlated field 256^3 float64 (BASELINE.json configs[2])"),
+    "cf2d_128_f64": ((128, 128), "2D correlated field 128x128 float64 (BASELINE.json configs[0])"),
+}
+CF_KW = dict(fluctuations=(1e-1, 5e-3), loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5), asperity=(0.5, 0.05))
+OFFSET = (0.0, (1e-3, 1e-4))
+NOISE_STD = 0.1
+
+
+def algorithmic_bytes_mvp(shape, w=8):
+    """w*N*[2(2d-1)+4]"""
+    d = max(len(shape), 2)
+    return w * int(np.prod(shape)) * (2 * (2 * d - 1) + 4)
+
+
+def kernel_bytes(name, shape, w=8):
+    """Algorithmic bytes of one launch of the named pass."""
+    N = int(np.prod(shape))
+    if "P1Body" in name:
+        return 3 * w * N      # read t, xi; write half spectrum
+    if "P3Body" in name:
+        return 3 * w * N      # read half spectrum, Jacobian weight; write half spectrum
+    if "P5Body" in name:
+        return 4 * w * N      # read half spectrum, t, xi; write out
+    if "PCBody" in name:
+        return 2 * w * N
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_inputs(shape, seed):
+    """Synthetic inputs of SURVEY.md 8(d): i.i.d. N(0,1) latents per leaf (sorted-key order)."""
+    rng = np.random.default_rng(seed)
+    return rng
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU arm: the NumPy/scipy.fft oracle port of the reference's path (nifty.re itself needs JAX, which
+# is not installed here or on the GPU box; /root/reference does not exist on the GPU box either).
+# -------------------------------------------------------------------------------------------------
+def cpu_setup(shape, seed=42):
+    import oracle
+    cores = os.cpu_count() or 1
+    oracle.correlated_field.set_nthreads(cores)
+    cf = oracle.CorrelatedFieldOracle("cf")
+    cf.set_amplitude_total_offset(*OFFSET)
+    cf.add_fluctuations(shape, 1.0 / shape[0], prefix="ax1", non_parametric_kind="power", **CF_KW)
+    cf.finalize()
+    sig = oracle.SignalOracle(cf, "exp")
+    lay = oracle.Layout(sig.domain)
+    rng = np.random.default_rng(seed)
+    truth = lay.random(rng)
+    data = sig(truth) + NOISE_STD * rng.standard_normal(shape)
+    lh = oracle.GaussianOracle(data, NOISE_STD**-2, sig)
+    pos = {k: 0.1 * v for k, v in lay.random(np.random.default_rng(seed + 2)).items()}
+    tan = lay.random(np.random.default_rng(seed + 3))
+    return lh, lay, pos, tan, cores
+
+
+def cpu_mvp_once(lh, lay, pos, tan):
+    out = lh.metric(pos, tan)          # J^T N^-1 J t, re-linearising like nifty.re (likelihood.py:613-621)
+    return {k: out[k] + tan[k] for k in out}
+
+
+def run_reference(args, shape, wname, rank, world):
+    if rank != 0:
+        return
+    t0 = time.time()
+    lh, lay, pos, tan, cores = cpu_setup(shape)
+    setup_s = time.time() - t0
+    for _ in range(max(args.warmup, 1) if np.prod(shape) <= 2**22 else 1):
+        cpu_mvp_once(lh, lay, pos, tan)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_mvp_once(lh, lay, pos, tan)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = 1.0 / dt
+    sample = f"{args.steps} full {wname} products on {cores} host threads (scipy.fft workers), setup {setup_s:.1f}s excluded"
+    line = {"impl": "reference", "metric": "metric_vector_products_per_sec", "value": val, "unit": "MVP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wname, "shape": list(shape), "what": WORKLOADS[wname][1],
+                       "cpu_path": "NumPy/scipy.fft oracle port of nifty.re (JAX not installable offline)"},
+            "cpu_baseline": {"value": val, "unit": "MVP/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "MVP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+# B200 arm
+# -------------------------------------------------------------------------------------------------
+def run_b200(args, shape, wname, rank, world, local_rank):
+    import torch
+    import nifty_b200 as nb
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    dtype = torch.float64
+    cfm = nb.CorrelatedFieldMaker("cf", dtype=dtype)
+    cfm.set_amplitude_total_offset(*OFFSET)
+    cfm.add_fluctuations(shape, 1.0 / shape[0], prefix="ax1", non_parametric_kind="power", **CF_KW)
+    cf = cfm.finalize()
+    sig = nb.SignalModel(cf, "exp")
+    rt = cf.rt
+    L = sig.layout.size
+    # synthetic data: signal(truth) + noise; every rank = one independent MGVI sample (own seed)
+    truth = sig.layout.random(42, dtype, dev)
+    tmp_lh = nb.Gaussian(torch.zeros(shape, dtype=dtype, device=dev), noise_cov_inv=NOISE_STD**-2).amend(sig)
+    s_truth = tmp_lh.signal_response(truth)
+    gen = torch.Generator(dev).manual_seed(43)
+    data = s_truth + NOISE_STD * torch.randn(shape, dtype=dtype, device=dev, generator=gen)
+    del tmp_lh
+    lh = nb.Gaussian(data, noise_cov_inv=NOISE_STD**-2).amend(sig)
+    pos = 0.1 * sig.layout.random(44, dtype, dev)
+    t = sig.layout.random(45 + rank, dtype, dev)
+    lin, _ = lh.lin_at(pos)
+    out = torch.empty_like(t)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        lin.metric(t, add_identity=True, out=out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = rt.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        lin.metric(t, add_identity=True, out=out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = rt.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax) / args.steps
+    value = world * 1e3 / ms_step
+
+    # per-kernel event timing over the same steps (instrumented pass; the library records events
+    # around each of its launches on the stream it launches on)
+    rt.timing_begin()
+    for _ in range(args.steps):
+        lin.metric(t, add_identity=True, out=out)
+    tm = rt.timing_end()
+    tot = sum(v[1] for v in tm.values())
+    dom = max(tm.items(), key=lambda kv: kv[1][1])
+    dom_name, (dom_cnt, dom_ms) = dom
+    kb = kernel_bytes(dom_name, shape)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    achieved = kb / (dom_ms / dom_cnt * 1e-3) / 1e9 if kb else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wname, {}).get(
+            "P1Body" if "P1Body" in dom_name else "P3Body" if "P3Body" in dom_name else "P5Body" if "P5Body" in dom_name else "PCBody")
+    except Exception:
+        pass
+    short = [k for k in ("P1Body", "P3Body", "P5Body", "PCBody", "SegSum", "ScanApply", "ScanAgg", "ScanTop") if k in dom_name][0]
+    roofline = {"bound": "hbm", "kernel": short, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "kernel_share_of_step": dom_ms / tot,
+                "whole_step": {"algorithmic_bytes": algorithmic_bytes_mvp(shape), "achieved": algorithmic_bytes_mvp(shape) / (ms_step * 1e-3) / 1e9,
+                               "frac": algorithmic_bytes_mvp(shape) / (ms_step * 1e-3) / 1e9 / peak},
+                "kernels_us": {k.split("nb")[-1][:40]: round(v[1] / v[0] * 1e3, 1) for k, v in sorted(tm.items(), key=lambda kv: -kv[1][1])}}
+
+    # end to end through the public API with host buffers: H2D tangent, product, D2H result
+    t_host = t.cpu().pin_memory()
+    out_host = torch.empty_like(t_host).pin_memory()
+    t_dev = torch.empty_like(t)
+    for _ in range(2):
+        t_dev.copy_(t_host, non_blocking=True)
+        out_host.copy_(lh.metric(pos, t_dev) + t_dev, non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        t_dev.copy_(t_host, non_blocking=True)
+        res = lin.metric(t_dev, add_identity=True, out=out)
+        out_host.copy_(res, non_blocking=True)
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * 1e3 / (float(te) / args.steps)
+    nbytes = t.numel() * t.element_size()
+
+    # sample-draw seconds (second half of the BASELINE metric): one draw_linear_residual-style CG
+    # solve with the demo's settings (absdelta = 1e-4 * L / 10, maxiter = 100; demos/re/0_intro.py:105-108)
+    j = sig.layout.random(1000 + rank, dtype, dev)
+    torch.cuda.synchronize()
+    ts = time.perf_counter()
+    x, cgres = lin.cg_solve(j, j.clone(), absdelta=1e-4 * L / 10, maxiter=100, raise_nonposdef=False)
+    torch.cuda.synchronize()
+    draw_s = time.perf_counter() - ts
+
+    if rank == 0:
+        cpu = None
+        if args.cpu_baseline:
+            t0 = time.time()
+            olh, lay, opos, otan, cores = cpu_setup(shape)
+            cpu_mvp_once(olh, lay, opos, otan)
+            nrep = 2
+            t1 = time.perf_counter()
+            for _ in range(nrep):
+                cpu_mvp_once(olh, lay, opos, otan)
+            dt = (time.perf_counter() - t1) / nrep
+            cpu = {"value": 1.0 / dt, "unit": "MVP/s", "cores": cores, "kind": "port",
+                   "sample": f"{nrep} full {wname} products with the NumPy/scipy.fft oracle port ({cores} threads), {time.time()-t0:.0f}s incl. setup"}
+        line = {"metric": "metric_vector_products_per_sec", "value": value, "unit": "MVP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wname, "shape": list(shape), "what": WORKLOADS[wname][1], "latent_size": L,
+                           "parallelism": f"sample-sharded x{world}" if world > 1 else "single GPU",
+                           "l2": f"working set per product {algorithmic_bytes_mvp(shape)/1e6:.0f} MB > 126 MB L2 (no explicit flush)"},
+                "clocks": clocks, "e2e": {"value": e2e_val, "unit": "MVP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "sample_draw": {"seconds": draw_s, "cg_iterations": int(cgres.nit), "info": int(cgres.info), "nfev": int(cgres.nfev)}}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cf2d_4096_f64", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    shape = WORKLOADS[args.workload][0]
+    if args.impl == "reference":
+        if args.steps > 3 and np.prod(shape) >= 2**24:
+            args.steps = 3      # bounded sample: ~1-3 s per product on the host
+        run_reference(args, shape, args.workload, rank, world)
+    else:
+        run_b200(args, shape, args.workload, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
