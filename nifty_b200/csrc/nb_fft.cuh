@@ -101,47 +101,69 @@ template <int LR, class T> NB_HD NB_INLINE void twiddle_apply(cplx<T>* a, cplx<T
   }
 }
 
-// One radix-2^LR stage over all lines, data in shared memory.  lm = log2 of the sub-transform
-// length of this stage.  DIF: y_p = (sum_q x_q w_R^{pq}) w_m^{jp};  DIT: y_p = sum_q (x_q w_m^{jq}) w_R^{pq}
+// Host-built description of one line FFT (passed by value inside kernel parameters, i.e. read
+// through the constant bank with uniform addresses): stage lengths / radices, the swizzled element
+// offsets swz(q << lmr) of every stage, and a device table pos[k] = swz(fft_pos(k)).
+struct FftDev {
+  int lg, ns;
+  int lm[6], lr[6];
+  int off[6][8];
+  const int* pos;
+};
+inline FftDev make_fft_dev(int lg, const int* pos_table) {
+  FftDev f;
+  f.lg = lg; f.ns = 0; f.pos = pos_table;
+  for (int s = 0; s < 6; ++s) { f.lm[s] = 0; f.lr[s] = 0; for (int q = 0; q < 8; ++q) f.off[s][q] = 0; }
+  int lm = lg;
+  while (lm > 0) {
+    int lr = fft_radix_lg(lm);
+    f.lm[f.ns] = lm; f.lr[f.ns] = lr;
+    for (int q = 0; q < (1 << lr); ++q) f.off[f.ns][q] = swz(q << (lm - lr));
+    ++f.ns;
+    lm -= lr;
+  }
+  return f;
+}
+inline void fill_pos_table(int lg, int* out) { for (int k = 0; k < (1 << lg); ++k) out[k] = swz(fft_pos(k, lg)); }
+
+// One radix-2^LR stage over all lines, data in shared memory (stage index st of `f`).
+// DIF: y_p = (sum_q x_q w_R^{pq}) w_m^{jp};  DIT: y_p = sum_q (x_q w_m^{jq}) w_R^{pq}
 template <int LR, bool DIT, class T>
-NB_HD NB_INLINE void fft_stage(Ctx& ctx, cplx<T>* s, int lg, int lm, int nlines, int pitch,
-                               const cplx<T>* tw, int tw_shift /* log2(tw_n) - lm */) {
+NB_HD NB_INLINE void fft_stage(Ctx& ctx, cplx<T>* s, const FftDev& f, int st, int nlines, int pitch,
+                               const cplx<T>* tw, int lg_tw) {
   constexpr int R = 1 << LR;
+  const int lm = f.lm[st];
   const int lmr = lm - LR;              // log2(m / R)
-  const int lbf = lg - LR;              // log2(butterflies per line)
+  const int lbf = f.lg - LR;            // log2(butterflies per line)
   const int total = nlines << lbf;
-  int off[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) off[q] = swz(q << lmr);
+  const int tw_shift = lg_tw - lm;
   NB_FOR(ctx, t, total) {
     int line = t >> lbf, u = t & ((1 << lbf) - 1);
     int blk = u >> lmr, j = u & ((1 << lmr) - 1);
     cplx<T> w = cmake<T>(T(1), T(0));
     if (j != 0) w = ldg(tw + ((size_t)j << tw_shift));
-    cplx<T>* base = s + (size_t)line * pitch;
+    cplx<T>* base = s + line * pitch;
     const int b0 = swz((blk << lm) + j);
     cplx<T> a[R];
 #pragma unroll
-    for (int q = 0; q < R; ++q) a[q] = base[b0 ^ off[q]];
+    for (int q = 0; q < R; ++q) a[q] = base[b0 ^ f.off[st][q]];
     if (DIT && j != 0) twiddle_apply<LR>(a, w);
     dftR<LR>(a);
     if (!DIT && j != 0) twiddle_apply<LR>(a, w);
 #pragma unroll
-    for (int q = 0; q < R; ++q) base[b0 ^ off[q]] = a[q];
+    for (int q = 0; q < R; ++q) base[b0 ^ f.off[st][q]] = a[q];
   }
   ctx.sync();
 }
 
 // First DIF stage (m = n) with the inputs taken from a loader: ld(line, x) -> cplx<T>
 template <int LR, class T, class Ld>
-NB_HD NB_INLINE void fft_stage_first(Ctx& ctx, cplx<T>* s, int lg, int nlines, int pitch,
-                                     const cplx<T>* tw, int tw_shift, const Ld& ld) {
+NB_HD NB_INLINE void fft_stage_first(Ctx& ctx, cplx<T>* s, const FftDev& f, int nlines, int pitch,
+                                     const cplx<T>* tw, int lg_tw, const Ld& ld) {
   constexpr int R = 1 << LR;
-  const int lmr = lg - LR;
+  const int lmr = f.lg - LR;
   const int total = nlines << lmr;
-  int off[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) off[q] = swz(q << lmr);
+  const int tw_shift = lg_tw - f.lg;
   NB_FOR(ctx, t, total) {
     int line = t >> lmr, j = t & ((1 << lmr) - 1);
     cplx<T> a[R];
@@ -151,49 +173,43 @@ NB_HD NB_INLINE void fft_stage_first(Ctx& ctx, cplx<T>* s, int lg, int nlines, i
     if (j != 0) w = ldg(tw + ((size_t)j << tw_shift));
     dftR<LR>(a);
     if (j != 0) twiddle_apply<LR>(a, w);
-    cplx<T>* base = s + (size_t)line * pitch;
+    cplx<T>* base = s + line * pitch;
     const int b0 = swz(j);
 #pragma unroll
-    for (int q = 0; q < R; ++q) base[b0 ^ off[q]] = a[q];
+    for (int q = 0; q < R; ++q) base[b0 ^ f.off[0][q]] = a[q];
   }
   ctx.sync();
 }
 
 template <bool DIT, class T>
-NB_HD NB_INLINE void fft_stage_any(Ctx& ctx, cplx<T>* s, int lg, int lm, int nlines, int pitch,
+NB_HD NB_INLINE void fft_stage_any(Ctx& ctx, cplx<T>* s, const FftDev& f, int st, int nlines, int pitch,
                                    const cplx<T>* tw, int lg_tw) {
-  int lr = fft_radix_lg(lm);
-  if (lr == 3) fft_stage<3, DIT>(ctx, s, lg, lm, nlines, pitch, tw, lg_tw - lm);
-  else if (lr == 2) fft_stage<2, DIT>(ctx, s, lg, lm, nlines, pitch, tw, lg_tw - lm);
-  else fft_stage<1, DIT>(ctx, s, lg, lm, nlines, pitch, tw, lg_tw - lm);
+  int lr = f.lr[st];
+  if (lr == 3) fft_stage<3, DIT>(ctx, s, f, st, nlines, pitch, tw, lg_tw);
+  else if (lr == 2) fft_stage<2, DIT>(ctx, s, f, st, nlines, pitch, tw, lg_tw);
+  else fft_stage<1, DIT>(ctx, s, f, st, nlines, pitch, tw, lg_tw);
 }
 
 // natural order from `ld` -> digit-reversed (swizzled) in shared memory; returns synchronised.
 template <class T, class Ld>
-NB_HD NB_INLINE void fft_dif_load(Ctx& ctx, cplx<T>* s, int lg, int nlines, int pitch, const cplx<T>* tw, int lg_tw,
-                                  const Ld& ld) {
-  if (lg == 0) {
-    NB_FOR(ctx, t, nlines) s[(size_t)t * pitch] = ld(t, 0);
+NB_HD NB_INLINE void fft_dif_load(Ctx& ctx, cplx<T>* s, const FftDev& f, int nlines, int pitch, const cplx<T>* tw,
+                                  int lg_tw, const Ld& ld) {
+  if (f.lg == 0) {
+    NB_FOR(ctx, t, nlines) s[t * pitch] = ld(t, 0);
     ctx.sync();
     return;
   }
-  int lr = fft_radix_lg(lg);
-  if (lr == 3) fft_stage_first<3>(ctx, s, lg, nlines, pitch, tw, lg_tw - lg, ld);
-  else if (lr == 2) fft_stage_first<2>(ctx, s, lg, nlines, pitch, tw, lg_tw - lg, ld);
-  else fft_stage_first<1>(ctx, s, lg, nlines, pitch, tw, lg_tw - lg, ld);
-  int lm = lg - lr;
-  while (lm > 0) {
-    fft_stage_any<false>(ctx, s, lg, lm, nlines, pitch, tw, lg_tw);
-    lm -= fft_radix_lg(lm);
-  }
+  int lr = f.lr[0];
+  if (lr == 3) fft_stage_first<3>(ctx, s, f, nlines, pitch, tw, lg_tw, ld);
+  else if (lr == 2) fft_stage_first<2>(ctx, s, f, nlines, pitch, tw, lg_tw, ld);
+  else fft_stage_first<1>(ctx, s, f, nlines, pitch, tw, lg_tw, ld);
+  for (int st = 1; st < f.ns; ++st) fft_stage_any<false>(ctx, s, f, st, nlines, pitch, tw, lg_tw);
 }
 
 // digit-reversed (swizzled) -> natural (swizzled); caller synchronised after filling; returns synchronised
 template <class T>
-NB_HD NB_INLINE void fft_dit(Ctx& ctx, cplx<T>* s, int lg, int nlines, int pitch, const cplx<T>* tw, int lg_tw) {
-  int lms[16], ns = 0, lm = lg;
-  while (lm > 0) { lms[ns++] = lm; lm -= fft_radix_lg(lm); }
-  for (int i = ns - 1; i >= 0; --i) fft_stage_any<true>(ctx, s, lg, lms[i], nlines, pitch, tw, lg_tw);
+NB_HD NB_INLINE void fft_dit(Ctx& ctx, cplx<T>* s, const FftDev& f, int nlines, int pitch, const cplx<T>* tw, int lg_tw) {
+  for (int st = f.ns - 1; st >= 0; --st) fft_stage_any<true>(ctx, s, f, st, nlines, pitch, tw, lg_tw);
 }
 
 }  // namespace nb

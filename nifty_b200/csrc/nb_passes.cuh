@@ -87,6 +87,7 @@ template <class T, class Pro> struct P1Params {
   long in_ostride, in_rstride, out_ostride, out_kstride;
   int pitch;
   const cplx<T>* tw; int lg_tw;   // table for the REAL length n (tw_n multiple of n)
+  FftDev fft;                     // complex FFT of length n/2
   cplx<T>* out;
   Pro pro;
 };
@@ -98,23 +99,27 @@ template <class T, class Pro> struct P1Body {
     const int R = 1 << p.lg_R, lg_h = p.lg_n - 1, h = 1 << lg_h;
     const int gpo = (p.n_r + R - 1) >> p.lg_R;
     const int o = ctx.bid / gpo, rr0 = (ctx.bid % gpo) << p.lg_R;
+    const long in0 = o * p.in_ostride;
     auto ld = [&](int r, int j) {
       int rr = rr0 + r;
       T a = 0, b = 0;
-      if (rr < p.n_r) p.pro.load2(o, rr, 2 * j, o * p.in_ostride + rr * p.in_rstride + 2 * j, a, b);
+      if (rr < p.n_r) p.pro.load2(o, rr, 2 * j, in0 + rr * p.in_rstride + 2 * j, a, b);
       return cmake<T>(a, b);
     };
-    fft_dif_load(ctx, s, lg_h, R, p.pitch, p.tw, p.lg_tw, ld);   // w_h^j = w_n^{2j}: same table, larger stride
+    fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);   // w_h^j = w_n^{2j}: same table, larger stride
     const T half = T(0.5);
+    cplx<T>* outp = p.out + o * p.out_ostride + rr0;
+    const int tsh = p.lg_tw - p.lg_n;
     NB_FOR(ctx, i, (h + 1) << p.lg_R) {
-      int k = i >> p.lg_R, r = i & (R - 1), rr = rr0 + r;
-      if (rr >= p.n_r) continue;
-      cplx<T> zk = s[r * p.pitch + swz(fft_pos(k & (h - 1), lg_h))];
-      cplx<T> zc = cconj(s[r * p.pitch + swz(fft_pos((h - k) & (h - 1), lg_h))]);
+      int k = i >> p.lg_R, r = i & (R - 1);
+      if (rr0 + r >= p.n_r) continue;
+      const cplx<T>* line = s + r * p.pitch;
+      cplx<T> zk = line[ldg(p.fft.pos + (k & (h - 1)))];
+      cplx<T> zc = cconj(line[ldg(p.fft.pos + ((h - k) & (h - 1)))]);
       cplx<T> e = zk + zc, d = zk - zc;
-      cplx<T> w = ldg(p.tw + ((size_t)k << (p.lg_tw - p.lg_n)));
+      cplx<T> w = ldg(p.tw + ((size_t)k << tsh));
       cplx<T> wd = cmul_mi(cmul(w, d));   // -i w (zk - zc)
-      p.out[o * p.out_ostride + k * p.out_kstride + rr] = cmake<T>(half * (e.x + wd.x), half * (e.y + wd.y));
+      outp[k * p.out_kstride + r] = cmake<T>(half * (e.x + wd.x), half * (e.y + wd.y));
     }
   }
 };
@@ -128,6 +133,7 @@ template <class T> struct PCParams {
   long in_ostride, in_rstride, out_ostride, out_kstride;
   int pitch;
   const cplx<T>* tw; int lg_tw;
+  FftDev fft;
   const cplx<T>* in;
   cplx<T>* out;
 };
@@ -139,17 +145,18 @@ template <class T> struct PCBody {
     const int R = 1 << p.lg_R, n = 1 << p.lg_n;
     const int gpo = (p.n_r + R - 1) >> p.lg_R;
     const int o = ctx.bid / gpo, rr0 = (ctx.bid % gpo) << p.lg_R;
+    const cplx<T>* inp = p.in + o * p.in_ostride + rr0 * p.in_rstride;
     auto ld = [&](int r, int x) {
-      int rr = rr0 + r;
       cplx<T> v = cmake<T>(0, 0);
-      if (rr < p.n_r) v = p.in[o * p.in_ostride + rr * p.in_rstride + x];
+      if (rr0 + r < p.n_r) v = inp[r * p.in_rstride + x];
       return v;
     };
-    fft_dif_load(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw, ld);
+    fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
+    cplx<T>* outp = p.out + o * p.out_ostride + rr0;
     NB_FOR(ctx, i, n << p.lg_R) {
-      int k = i >> p.lg_R, r = i & (R - 1), rr = rr0 + r;
-      if (rr >= p.n_r) continue;
-      p.out[o * p.out_ostride + k * p.out_kstride + rr] = s[r * p.pitch + swz(fft_pos(k, p.lg_n))];
+      int k = i >> p.lg_R, r = i & (R - 1);
+      if (rr0 + r >= p.n_r) continue;
+      outp[k * p.out_kstride + r] = s[r * p.pitch + ldg(p.fft.pos + k)];
     }
   }
 };
@@ -172,6 +179,19 @@ struct MirrorGeom {
     return true;
   }
 };
+
+// per-CTA table of the lines it owns (filled once, then read by every phase)
+struct LineInfo { int lA, lB, active, pad; };
+constexpr int LINEINFO_BYTES = 16 * 16;   // R <= 16
+
+NB_HD NB_INLINE void fill_line_info(Ctx& ctx, LineInfo* li, const MirrorGeom& mg, int l0, int R) {
+  NB_FOR(ctx, r, R) {
+    int l = l0 + r, lA = 0, lB = -1;
+    bool act = l < mg.nlines() && mg.resolve(l, lA, lB);
+    li[r].lA = lA; li[r].lB = lB; li[r].active = act ? 1 : 0; li[r].pad = 0;
+  }
+  ctx.sync();
+}
 
 // ---------------------------------------------------------------------------------------------
 // P3 pointwise operator (position space, T-layout index ridx = line*n + x)
@@ -213,49 +233,45 @@ template <class T> struct PointOp {
     acc0 += r;
     return r;
   }
+  template <int MODE>
   NB_HD NB_INLINE T point(int lfull, int x, T v, T cshift, T scv, T& acc0, T& acc1) const {
     long i = (long)lfull * n + x;
-    switch (mode) {
-      case PM_METRIC: {
-        T r = jl_a[i] * jl_b[i] * (v * invV + cshift);
-        acc0 += r;
-        return r;
+    if (MODE == PM_METRIC) {
+      T r = jl_a[i] * jl_b[i] * (v * invV + cshift);
+      acc0 += r;
+      return r;
+    } else if (MODE == PM_LINEARIZE) {
+      T f = offset + v * invV;
+      T s = nl_exp ? scv * nb_exp(f) : f;
+      T jd = nl_exp ? s : T(1);
+      T e, cot, l;
+      if (lh_kind == LH_GAUSS) {
+        T w = w_arr ? w_arr[i] : w_scalar;
+        T d = data ? data[i] : T(0);
+        T r = s - d;
+        e = T(0.5) * w * r * r;
+        cot = w * r * jd;
+        l = nb_sqrt(w);
+      } else {
+        T d = data ? data[i] : T(0);
+        e = s - d * nb_log(s);
+        cot = (T(1) - d / s) * jd;
+        l = T(1) / nb_sqrt(s);
       }
-      case PM_LINEARIZE: {
-        T f = offset + v * invV;
-        T s = nl_exp ? scv * nb_exp(f) : f;
-        T jd = nl_exp ? s : T(1);
-        T e, cot, l;
-        if (lh_kind == LH_GAUSS) {
-          T w = w_arr ? w_arr[i] : w_scalar;
-          T d = data ? data[i] : T(0);
-          T r = s - d;
-          e = T(0.5) * w * r * r;
-          cot = w * r * jd;
-          l = nb_sqrt(w);
-        } else {
-          T d = data ? data[i] : T(0);
-          e = s - d * nb_log(s);
-          cot = (T(1) - d / s) * jd;
-          l = T(1) / nb_sqrt(s);
-        }
-        if (s_out) s_out[i] = s;
-        if (jl_out) jl_out[i] = jd * l;
-        acc0 += e;
-        acc1 += cot;
-        return cot;
-      }
-      case PM_JVP_OUT: {
-        T r = v * invV + cshift;
-        if (jl_a) r *= jl_a[i];
-        pos_out[addr(lfull, x)] = r;
-        return r;
-      }
-      default: {  // PM_FIELD_OUT
-        T r = offset + v * invV;
-        pos_out[addr(lfull, x)] = r;
-        return r;
-      }
+      if (s_out) s_out[i] = s;
+      if (jl_out) jl_out[i] = jd * l;
+      acc0 += e;
+      acc1 += cot;
+      return cot;
+    } else if (MODE == PM_JVP_OUT) {
+      T r = v * invV + cshift;
+      if (jl_a) r *= jl_a[i];
+      pos_out[addr(lfull, x)] = r;
+      return r;
+    } else {  // PM_FIELD_OUT
+      T r = offset + v * invV;
+      pos_out[addr(lfull, x)] = r;
+      return r;
     }
   }
 };
@@ -265,6 +281,7 @@ template <class T> struct P3Params {
   MirrorGeom mg;
   int pitch;
   const cplx<T>* tw; int lg_tw;
+  FftDev fft;
   T hsign;                 // +1: Re+Im (non_canonical_hartley), -1: Re-Im
   const cplx<T>* in;       // [l][n]
   cplx<T>* out;            // [k in 0..n/2][out_kstride]
@@ -272,65 +289,78 @@ template <class T> struct P3Params {
   PointOp<T> op;
 };
 
-template <class T, bool FWD, bool ADJ> struct P3Body {
+template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
   typedef P3Params<T> Params;
-  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
-    cplx<T>* s = reinterpret_cast<cplx<T>*>(smem);
-    const int R = 1 << p.lg_R, n = 1 << p.lg_n, h = n >> 1;
-    const int l0 = ctx.bid << p.lg_R, nl = p.mg.nlines();
+  // Hermitian combine of the pair (x, y = -x) of one line + pointwise operator
+  static NB_HD NB_INLINE void pair(const Params& p, cplx<T>* line, const LineInfo& li, int x, int y, T cshift, T scv,
+                                   T& acc0, T& acc1) {
     const T sg = p.hsign;
+    int px = ldg(p.fft.pos + x), py = ldg(p.fft.pos + y);
+    cplx<T> cx = line[px], cy = line[py];
+    T aX = cx.x + sg * cx.y, bY = cx.x - sg * cx.y;
+    T aY = cy.x + sg * cy.y, bX = cy.x - sg * cy.y;
+    T a2x = p.op.template point<MODE>(li.lA, x, aX, cshift, scv, acc0, acc1), b2x = 0, a2y = 0, b2y = 0;
+    if (y != x) a2y = p.op.template point<MODE>(li.lA, y, aY, cshift, scv, acc0, acc1);
+    if (li.lB >= 0) {
+      b2x = p.op.template point<MODE>(li.lB, x, bX, cshift, scv, acc0, acc1);
+      if (y != x) b2y = p.op.template point<MODE>(li.lB, y, bY, cshift, scv, acc0, acc1);
+    }
+    if (ADJ) {
+      line[px] = cmake<T>(a2x, b2x);
+      if (y != x) line[py] = cmake<T>(a2y, b2y);
+    }
+  }
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    LineInfo* li = reinterpret_cast<LineInfo*>(smem);
+    cplx<T>* s = reinterpret_cast<cplx<T>*>(reinterpret_cast<unsigned char*>(smem) + LINEINFO_BYTES);
+    const int R = 1 << p.lg_R, n = 1 << p.lg_n, h = n >> 1, lg_h = p.lg_n - 1;
+    const int l0 = ctx.bid << p.lg_R;
+    fill_line_info(ctx, li, p.mg, l0, R);
     T acc0 = 0, acc1 = 0;
     T cshift = p.op.cshift_ptr ? p.op.cshift_scale * ldg(p.op.cshift_ptr) : T(0);
     T scv = p.op.sc_ptr ? ldg(p.op.sc_ptr) : p.op.sc;
     if (FWD) {
+      const cplx<T>* inp = p.in + (long)l0 * n;
       auto ld = [&](int r, int x) {
-        int l = l0 + r, lA, lB;
         cplx<T> v = cmake<T>(0, 0);
-        if (l < nl && p.mg.resolve(l, lA, lB)) v = p.in[(long)l * n + x];
+        if (li[r].active) v = inp[r * n + x];
         return v;
       };
-      fft_dif_load(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw, ld);
-      // Hermitian combine + pointwise operator on the pair (x, y = -x)
-      NB_FOR(ctx, i, R * (h + 1)) {
-        int r = i / (h + 1), x = i - r * (h + 1), y = (n - x) & (n - 1), l = l0 + r, lA, lB;
-        if (l >= nl || !p.mg.resolve(l, lA, lB)) continue;
-        int px = swz(fft_pos(x, p.lg_n)), py = swz(fft_pos(y, p.lg_n));
-        cplx<T> cx = s[r * p.pitch + px], cy = s[r * p.pitch + py];
-        T aX = cx.x + sg * cx.y, bY = cx.x - sg * cx.y;
-        T aY = cy.x + sg * cy.y, bX = cy.x - sg * cy.y;
-        T a2x = p.op.point(lA, x, aX, cshift, scv, acc0, acc1), b2x = 0, a2y = 0, b2y = 0;
-        if (y != x) a2y = p.op.point(lA, y, aY, cshift, scv, acc0, acc1);
-        if (lB >= 0) {
-          b2x = p.op.point(lB, x, bX, cshift, scv, acc0, acc1);
-          if (y != x) b2y = p.op.point(lB, y, bY, cshift, scv, acc0, acc1);
+      fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
+      if (n == 1) {
+        NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], 0, 0, cshift, scv, acc0, acc1);
+      } else {
+        // pairs (x, n-x) for x in [0, h) (x = 0 is its own partner), then the self-paired x = h
+        NB_FOR(ctx, i, R << lg_h) {
+          int r = i >> lg_h, x = i & (h - 1);
+          if (!li[r].active) continue;
+          pair(p, s + r * p.pitch, li[r], x, (n - x) & (n - 1), cshift, scv, acc0, acc1);
         }
-        if (ADJ) {
-          s[r * p.pitch + px] = cmake<T>(a2x, b2x);
-          if (y != x) s[r * p.pitch + py] = cmake<T>(a2y, b2y);
-        }
+        NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], h, h, cshift, scv, acc0, acc1);
       }
     } else {
       NB_FOR(ctx, i, R << p.lg_n) {
-        int r = i >> p.lg_n, x = i & (n - 1), l = l0 + r, lA, lB;
+        int r = i >> p.lg_n, x = i & (n - 1);
         cplx<T> v = cmake<T>(0, 0);
-        if (l < nl && p.mg.resolve(l, lA, lB)) {
-          v.x = p.op.load(lA, x, acc0);
-          if (lB >= 0) v.y = p.op.load(lB, x, acc0);
+        if (li[r].active) {
+          v.x = p.op.load(li[r].lA, x, acc0);
+          if (li[r].lB >= 0) v.y = p.op.load(li[r].lB, x, acc0);
         }
-        s[r * p.pitch + swz(fft_pos(x, p.lg_n))] = v;
+        s[r * p.pitch + ldg(p.fft.pos + x)] = v;
       }
     }
     if (ADJ) {
       ctx.sync();
-      fft_dit(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw);
+      fft_dit(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw);
       const T half = T(0.5);
       NB_FOR(ctx, i, (h + 1) << p.lg_R) {
-        int k = i >> p.lg_R, r = i & (R - 1), l = l0 + r, lA, lB;
-        if (l >= nl || !p.mg.resolve(l, lA, lB)) continue;
+        int k = i >> p.lg_R, r = i & (R - 1);
+        if (!li[r].active) continue;
         cplx<T> zk = s[r * p.pitch + swz(k)], zc = cconj(s[r * p.pitch + swz((n - k) & (n - 1))]);
         cplx<T> e = zk + zc, d = cmul_mi(zk - zc);
-        p.out[k * p.out_kstride + lA] = cmake<T>(half * e.x, half * e.y);
-        if (lB >= 0) p.out[k * p.out_kstride + lB] = cmake<T>(half * d.x, half * d.y);
+        cplx<T>* orow = p.out + k * p.out_kstride;
+        orow[li[r].lA] = cmake<T>(half * e.x, half * e.y);
+        if (li[r].lB >= 0) orow[li[r].lB] = cmake<T>(half * d.x, half * d.y);
       }
     }
     if (p.op.partials) {
@@ -391,6 +421,7 @@ template <class T, class Epi> struct P5Params {
   int hmid1;      // n_mid/2 + 1 (folded extent of the middle axis)
   int pitch;
   const cplx<T>* tw; int lg_tw;
+  FftDev fft;
   T hsign;
   const cplx<T>* in;   // [l][n]
   Epi epi;
@@ -398,29 +429,39 @@ template <class T, class Epi> struct P5Params {
 
 template <class T, class Epi> struct P5Body {
   typedef P5Params<T, Epi> Params;
-  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
-    cplx<T>* s = reinterpret_cast<cplx<T>*>(smem);
-    const int R = 1 << p.lg_R, n = 1 << p.lg_n, h = n >> 1;
-    const int l0 = ctx.bid << p.lg_R, nl = p.mg.nlines();
+  static NB_HD NB_INLINE void pair(const Params& p, const cplx<T>* line, const LineInfo& li, int x, int y, T& acc) {
     const T sg = p.hsign;
+    const int n = 1 << p.lg_n, h = n >> 1, nmid = 1 << p.mg.lg_mid;
+    cplx<T> cx = line[ldg(p.fft.pos + x)], cy = line[ldg(p.fft.pos + y)];
+    T gAx = cx.x + sg * cx.y, gBy = cx.x - sg * cx.y;
+    T gAy = cy.x + sg * cy.y, gBx = cy.x - sg * cy.y;
+    int a = li.lA >> p.mg.lg_mid, km = li.lA & (nmid - 1);
+    long fbase = ((long)a * p.hmid1 + fold_idx(km, nmid)) * (h + 1);   // a <= h_a is already folded
+    p.epi.emit((long)li.lA * n, li.lB >= 0 ? (long)li.lB * n : -1L, fbase, (long)li.lA * (h + 1), x, y, gAx, gAy, gBx, gBy, acc);
+  }
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    LineInfo* li = reinterpret_cast<LineInfo*>(smem);
+    cplx<T>* s = reinterpret_cast<cplx<T>*>(reinterpret_cast<unsigned char*>(smem) + LINEINFO_BYTES);
+    const int R = 1 << p.lg_R, n = 1 << p.lg_n, h = n >> 1, lg_h = p.lg_n - 1;
+    const int l0 = ctx.bid << p.lg_R;
+    fill_line_info(ctx, li, p.mg, l0, R);
     T acc = 0;
+    const cplx<T>* inp = p.in + (long)l0 * n;
     auto ld = [&](int r, int x) {
-      int l = l0 + r, lA, lB;
       cplx<T> v = cmake<T>(0, 0);
-      if (l < nl && p.mg.resolve(l, lA, lB)) v = p.in[(long)l * n + x];
+      if (li[r].active) v = inp[r * n + x];
       return v;
     };
-    fft_dif_load(ctx, s, p.lg_n, R, p.pitch, p.tw, p.lg_tw, ld);
-    const int nmid = 1 << p.mg.lg_mid;
-    NB_FOR(ctx, i, R * (h + 1)) {
-      int r = i / (h + 1), x = i - r * (h + 1), y = (n - x) & (n - 1), l = l0 + r, lA, lB;
-      if (l >= nl || !p.mg.resolve(l, lA, lB)) continue;
-      cplx<T> cx = s[r * p.pitch + swz(fft_pos(x, p.lg_n))], cy = s[r * p.pitch + swz(fft_pos(y, p.lg_n))];
-      T gAx = cx.x + sg * cx.y, gBy = cx.x - sg * cx.y;
-      T gAy = cy.x + sg * cy.y, gBx = cy.x - sg * cy.y;
-      int a = lA >> p.mg.lg_mid, km = lA & (nmid - 1);
-      long fbase = ((long)a * p.hmid1 + fold_idx(km, nmid)) * (h + 1);   // a <= h_a is already folded
-      p.epi.emit((long)lA * n, lB >= 0 ? (long)lB * n : -1L, fbase, (long)lA * (h + 1), x, y, gAx, gAy, gBx, gBy, acc);
+    fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
+    if (n == 1) {
+      NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], 0, 0, acc);
+    } else {
+      NB_FOR(ctx, i, R << lg_h) {
+        int r = i >> lg_h, x = i & (h - 1);
+        if (!li[r].active) continue;
+        pair(p, s + r * p.pitch, li[r], x, (n - x) & (n - 1), acc);
+      }
+      NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], h, h, acc);
     }
     if (p.epi.partials) {
       void* scratch = reinterpret_cast<void*>(s + (size_t)R * p.pitch);

@@ -157,7 +157,8 @@ template <class T> struct Plan : PlanBase {
   int lg0 = 0, lgm = 0, lgl = 0;
   T hsign = 1;
   DevBuf<cplx<T>> tw0, twm, twl, S0, S1;
-  DevBuf<int> idxf, w_order, w_offs;
+  DevBuf<int> idxf, w_order, w_offs, pos0, posm, posl, poslh;
+  FftDev f0, fm, fl, flh;   // line FFTs of length n0, nm, nl and nl/2
   DevBuf<T> W, p3part, p5part;
   PassCfg c1, cA, c3, cB, c5;
   int seg_lg_lpb = 2;   // lanes per mode bin in the segment sum (power of two near the mean bin population)
@@ -202,6 +203,13 @@ template <class T> struct Plan : PlanBase {
     twm.upload(make_twiddles<T>(g.nm));
     twl.upload(make_twiddles<T>(g.nl));
     idxf.upload(g.idxf); w_order.upload(g.w_order); w_offs.upload(g.w_offs);
+    auto mk = [&](int lg, DevBuf<int>& buf) {
+      std::vector<int> t(size_t(1) << lg);
+      fill_pos_table(lg, t.data());
+      buf.upload(t);
+      return make_fft_dev(lg, buf.p);
+    };
+    f0 = mk(lg0, pos0); fm = mk(lgm, posm); fl = mk(lgl, posl); flh = mk(lgl - 1, poslh);
     W.alloc((size_t)g.nW);
     const int64_t n0 = g.n0, nm = g.nm, nl = g.nl, h0 = g.h0, hl = g.hl;
     size_t sc = 0;
@@ -248,7 +256,7 @@ template <class T> struct Plan : PlanBase {
 
   template <class Pro> void run_p1(stream_t st, const Pro& pro) {
     P1Params<T, Pro> p;
-    p.lg_n = lgl; p.lg_R = c1.lg_R; p.pitch = c1.pitch; p.tw = twl.p; p.lg_tw = lgl; p.out = S0.p; p.pro = pro;
+    p.lg_n = lgl; p.lg_R = c1.lg_R; p.pitch = c1.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = flh; p.out = S0.p; p.pro = pro;
     if (g.three) {
       p.n_o = g.n0; p.n_r = g.nm; p.in_ostride = (long)g.nm * g.nl; p.in_rstride = g.nl;
       p.out_ostride = (long)(g.hl + 1) * g.nm; p.out_kstride = g.nm;
@@ -261,7 +269,7 @@ template <class T> struct Plan : PlanBase {
     if (!g.three) return;
     PCParams<T> p;
     const PassCfg& c = second ? cB : cA;
-    p.lg_n = lgm; p.lg_R = c.lg_R; p.pitch = c.pitch; p.tw = twm.p; p.lg_tw = lgm; p.in = S0.p; p.out = S1.p;
+    p.lg_n = lgm; p.lg_R = c.lg_R; p.pitch = c.pitch; p.tw = twm.p; p.lg_tw = lgm; p.fft = fm; p.in = S0.p; p.out = S1.p;
     if (!second) {   // [j0][k2][j1] -> [k2][k1][j0]
       p.n_o = g.hl + 1; p.n_r = g.n0; p.in_ostride = g.nm; p.in_rstride = (long)(g.hl + 1) * g.nm;
       p.out_ostride = (long)g.nm * g.n0; p.out_kstride = g.n0;
@@ -273,15 +281,28 @@ template <class T> struct Plan : PlanBase {
   }
   template <bool FWD, bool ADJ> void run_p3(stream_t st, const PointOp<T>& op) {
     P3Params<T> p;
-    p.lg_n = lg0; p.lg_R = c3.lg_R; p.mg = mg3(); p.pitch = c3.pitch; p.tw = tw0.p; p.lg_tw = lg0; p.hsign = hsign;
+    p.lg_n = lg0; p.lg_R = c3.lg_R; p.mg = mg3(); p.pitch = c3.pitch; p.tw = tw0.p; p.lg_tw = lg0; p.fft = f0; p.hsign = hsign;
     p.in = p3_in(); p.out = p3_out(); p.out_kstride = (long)g.nl * g.nm; p.op = op;
-    launch<P3Body<T, FWD, ADJ>>(c3.grid, c3.block, c3.smem, st, p);
+    const size_t sm = c3.smem + LINEINFO_BYTES;
+    if constexpr (FWD && ADJ) {
+      if (op.mode == PM_METRIC) launch<P3Body<T, true, true, PM_METRIC>>(c3.grid, c3.block, sm, st, p);
+      else if (op.mode == PM_LINEARIZE) launch<P3Body<T, true, true, PM_LINEARIZE>>(c3.grid, c3.block, sm, st, p);
+      else throw Error{"nb200: invalid pointwise mode for the fused pass"};
+    } else if constexpr (FWD) {
+      if (op.mode == PM_LINEARIZE) launch<P3Body<T, true, false, PM_LINEARIZE>>(c3.grid, c3.block, sm, st, p);
+      else if (op.mode == PM_JVP_OUT) launch<P3Body<T, true, false, PM_JVP_OUT>>(c3.grid, c3.block, sm, st, p);
+      else if (op.mode == PM_FIELD_OUT) launch<P3Body<T, true, false, PM_FIELD_OUT>>(c3.grid, c3.block, sm, st, p);
+      else throw Error{"nb200: invalid pointwise mode for the forward pass"};
+    } else {
+      if (op.mode != PM_LOAD) throw Error{"nb200: invalid pointwise mode for the adjoint pass"};
+      launch<P3Body<T, false, true, PM_LOAD>>(c3.grid, c3.block, sm, st, p);
+    }
   }
   template <class Epi> void run_p5(stream_t st, const Epi& epi) {
     P5Params<T, Epi> p;
-    p.lg_n = lgl; p.lg_R = c5.lg_R; p.mg = mg5(); p.hmid1 = g.hm + 1; p.pitch = c5.pitch; p.tw = twl.p; p.lg_tw = lgl;
+    p.lg_n = lgl; p.lg_R = c5.lg_R; p.mg = mg5(); p.hmid1 = g.hm + 1; p.pitch = c5.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = fl;
     p.hsign = hsign; p.in = S1.p; p.epi = epi;
-    launch<P5Body<T, Epi>>(c5.grid, c5.block, c5.smem, st, p);
+    launch<P5Body<T, Epi>>(c5.grid, c5.block, c5.smem + LINEINFO_BYTES, st, p);
   }
   // natural (d0,d1,d2) -> reversed axes; for the T-layout <-> natural conversions
   void run_rev(stream_t st, const T* in, T* out, bool to_T) {
