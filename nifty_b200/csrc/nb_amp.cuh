@@ -48,12 +48,6 @@ template <class T> NB_HD NB_INLINE Aff<T> aff_compose(Aff<T> f, Aff<T> s) {
   Aff<T> r; r.a = f.a + s.a; r.b = f.b + s.b + s.a * f.c; r.c = f.c + s.c; return r;
 }
 
-constexpr int SCAN_NT = 256;
-constexpr int SCAN_E = 8;
-constexpr int SCAN_CH = SCAN_NT * SCAN_E;
-
-template <class T> inline size_t scan_smem_bytes() { return (size_t)(SCAN_CH + 2 * SCAN_NT + 64) * sizeof(Aff<T>); }
-
 // sum of partials[i*stride], i < n, by all threads of the calling block (fixed order -> deterministic)
 template <class T> NB_HD NB_INLINE T block_total(Ctx& ctx, const T* partials, int n, int stride, void* scratch) {
   T s = 0;
@@ -61,86 +55,141 @@ template <class T> NB_HD NB_INLINE T block_total(Ctx& ctx, const T* partials, in
   return ctx.block_sum(s, scratch);
 }
 
-// ---- generic three-kernel scan -------------------------------------------------------------
+// ---- ordered block scan of affine maps -----------------------------------------------------------
+// Every thread contributes the composition `v` of its own (contiguous) elements.  Returns the
+// composition of all EARLIER threads (exclusive prefix) and, in `total`, of all threads.  Fixed
+// shuffle tree -> bit-reproducible.  `scratch` holds >= 2*32+2 Aff<T>.
+#ifdef NB_EMU
+template <class T> inline Aff<T> block_scan_aff(Ctx&, Aff<T> v, Aff<T>& total, void*) { total = v; return aff_id<T>(); }
+#else
+template <class T> __device__ NB_INLINE Aff<T> shfl_up_aff(Aff<T> v, int o) {
+  Aff<T> r; r.a = __shfl_up_sync(0xffffffffu, v.a, o); r.b = __shfl_up_sync(0xffffffffu, v.b, o); r.c = __shfl_up_sync(0xffffffffu, v.c, o);
+  return r;
+}
+template <class T> __device__ NB_INLINE Aff<T> block_scan_aff(Ctx& ctx, Aff<T> v, Aff<T>& total, void* scratch) {
+  Aff<T>* wagg = reinterpret_cast<Aff<T>*>(scratch);       // [32] inclusive warp totals, then their scan
+  const int lane = ctx.tid & 31, warp = ctx.tid >> 5, nw = (ctx.nthr + 31) >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Aff<T> n = shfl_up_aff(v, o);
+    if (lane >= o) v = aff_compose(n, v);
+  }
+  Aff<T> excl = shfl_up_aff(v, 1);
+  if (lane == 0) excl = aff_id<T>();
+  __syncthreads();
+  if (lane == 31) wagg[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    Aff<T> w = lane < nw ? wagg[lane] : aff_id<T>();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Aff<T> n = shfl_up_aff(w, o);
+      if (lane >= o) w = aff_compose(n, w);
+    }
+    Aff<T> we = shfl_up_aff(w, 1);
+    if (lane == 0) we = aff_id<T>();
+    wagg[32 + lane] = we;                 // exclusive prefix of each warp
+    if (lane == 31) wagg[64] = w;         // block total
+  }
+  __syncthreads();
+  Aff<T> res = aff_compose(wagg[32 + warp], excl);
+  total = wagg[64];
+  __syncthreads();
+  return res;
+}
+#endif
+
+// ordered composition of agg[lo..hi) by the whole block
+template <class T> NB_HD NB_INLINE Aff<T> block_compose_range(Ctx& ctx, const Aff<T>* agg, int lo, int hi, void* scratch) {
+  int n = hi - lo, per = (n + ctx.nthr - 1) / ctx.nthr;
+  Aff<T> v = aff_id<T>();
+  for (int i = lo + ctx.tid * per; i < lo + (ctx.tid + 1) * per && i < hi; ++i) v = aff_compose(v, agg[i]);
+  Aff<T> tot;
+  block_scan_aff(ctx, v, tot, scratch);
+  return tot;
+}
+
+constexpr int SCAN_NT = 256;
+constexpr int SCAN_E = 8;
+constexpr int SCAN_CH = SCAN_NT * SCAN_E;
+
+template <class T> inline size_t scan_smem_bytes() { return (size_t)(SCAN_CH + 80) * sizeof(Aff<T>); }
+
+// ---- generic scan: (1) per-chunk aggregates [skipped for a single chunk], (2) apply -----------------
 template <class T, class Elem> struct ScanAggParams { long n; Elem elem; Aff<T>* agg; };
 template <class T, class Elem> struct ScanAggBody {
   typedef ScanAggParams<T, Elem> Params;
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
     Aff<T>* el = reinterpret_cast<Aff<T>*>(smem);
-    Aff<T>* tagg = el + SCAN_CH;
     long p0 = (long)ctx.bid * SCAN_CH;
     NB_FOR(ctx, i, SCAN_CH) el[i] = (p0 + i < p.n) ? p.elem.get(p0 + i) : aff_id<T>();
     ctx.sync();
-    NB_FOR(ctx, t, SCAN_NT) {
-      Aff<T> a = el[t * SCAN_E];
-      for (int e = 1; e < SCAN_E; ++e) a = aff_compose(a, el[t * SCAN_E + e]);
-      tagg[t] = a;
-    }
-    ctx.sync();
-    if (ctx.tid == 0) {
-      Aff<T> a = tagg[0];
-      for (int t = 1; t < SCAN_NT; ++t) a = aff_compose(a, tagg[t]);
-      p.agg[ctx.bid] = a;
-    }
+#ifdef NB_EMU
+    Aff<T> tot = aff_id<T>();
+    for (int i = 0; i < SCAN_CH; ++i) tot = aff_compose(tot, el[i]);
+#else
+    Aff<T> a = el[ctx.tid * SCAN_E];
+    for (int e = 1; e < SCAN_E; ++e) a = aff_compose(a, el[ctx.tid * SCAN_E + e]);
+    Aff<T> tot;
+    block_scan_aff(ctx, a, tot, reinterpret_cast<void*>(el + SCAN_CH));
+#endif
+    if (ctx.tid == 0) p.agg[ctx.bid] = tot;
   }
 };
-
-template <class T> struct ScanTopParams { int nchunks; const Aff<T>* agg; T* pre; /* [nchunks][2] */ T* total; /* [2] */ };
-template <class T> struct ScanTopBody {
-  typedef ScanTopParams<T> Params;
-  static NB_HD void run(Ctx& ctx, const Params& p, void*) {
-    if (ctx.tid == 0 && ctx.bid == 0) {
-      T x = 0, y = 0;
-      for (int c = 0; c < p.nchunks; ++c) {
-        p.pre[2 * c] = x; p.pre[2 * c + 1] = y;
-        Aff<T> e = p.agg[c];
-        x = x + e.a * y + e.b; y = y + e.c;
-      }
-      p.total[0] = x; p.total[1] = y;
-    }
-  }
-};
-
-// Out::put(pos, x0, y0, x1, y1, acc[4]) is called once per element with the state before / after;
-// Out::finish(ctx, acc, scratch) runs in every block afterwards.
-template <class T, class Elem, class Out> struct ScanApplyParams { long n; Elem elem; Out out; const T* pre; };
+// Out::put(pos, x0, y0, x1, y1, total_x, acc[4]) is called once per element with the state before /
+// after; Out::finish(ctx, acc, total_x, scratch) runs in every block afterwards.
+template <class T, class Elem, class Out> struct ScanApplyParams { long n; Elem elem; Out out; const Aff<T>* agg; int nchunks; };
 template <class T, class Elem, class Out> struct ScanApplyBody {
   typedef ScanApplyParams<T, Elem, Out> Params;
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
     Aff<T>* el = reinterpret_cast<Aff<T>*>(smem);
-    Aff<T>* tagg = el + SCAN_CH;
-    Aff<T>* tpre = tagg + SCAN_NT;
+    void* scratch = reinterpret_cast<void*>(el + SCAN_CH);
     long p0 = (long)ctx.bid * SCAN_CH;
     NB_FOR(ctx, i, SCAN_CH) el[i] = (p0 + i < p.n) ? p.elem.get(p0 + i) : aff_id<T>();
     ctx.sync();
-    NB_FOR(ctx, t, SCAN_NT) {
-      Aff<T> a = el[t * SCAN_E];
-      for (int e = 1; e < SCAN_E; ++e) a = aff_compose(a, el[t * SCAN_E + e]);
-      tagg[t] = a;
+    // carry-in of this chunk and the grand total from the chunk aggregates (nchunks > 1)
+    Aff<T> carry = aff_id<T>(), grand = aff_id<T>();
+    if (p.nchunks > 1) {
+      carry = block_compose_range(ctx, p.agg, 0, ctx.bid, scratch);
+      grand = block_compose_range(ctx, p.agg, 0, p.nchunks, scratch);
     }
-    ctx.sync();
-    if (ctx.tid == 0) {
-      T x = p.pre ? p.pre[2 * ctx.bid] : T(0), y = p.pre ? p.pre[2 * ctx.bid + 1] : T(0);
-      for (int t = 0; t < SCAN_NT; ++t) {
-        tpre[t].b = x; tpre[t].c = y;
-        Aff<T> e = tagg[t];
-        x = x + e.a * y + e.b; y = y + e.c;
-      }
-    }
-    ctx.sync();
-    T acc[4] = {0, 0, 0, 0};
-    NB_FOR(ctx, t, SCAN_NT) {
-      T x = tpre[t].b, y = tpre[t].c;
-      for (int e = 0; e < SCAN_E; ++e) {
-        long pos = p0 + t * SCAN_E + e;
+#ifdef NB_EMU
+    {
+      // one host "thread": walk the whole chunk sequentially
+      Aff<T> blk = aff_id<T>();
+      for (int i = 0; i < SCAN_CH; ++i) blk = aff_compose(blk, el[i]);
+      if (p.nchunks <= 1) grand = blk;
+      T acc[4] = {0, 0, 0, 0};
+      T x = carry.b, y = carry.c;
+      for (int i = 0; i < SCAN_CH; ++i) {
+        long pos = p0 + i;
         if (pos >= p.n) break;
-        Aff<T> a = el[t * SCAN_E + e];
+        Aff<T> a = el[i];
         T x1 = x + a.a * y + a.b, y1 = y + a.c;
-        p.out.put(pos, x, y, x1, y1, acc);
+        p.out.put(pos, x, y, x1, y1, grand.b, acc);
         x = x1; y = y1;
       }
+      p.out.finish(ctx, acc, grand.b, scratch);
     }
-    p.out.finish(ctx, acc, reinterpret_cast<void*>(tpre + SCAN_NT));
+#else
+    Aff<T> mine = el[ctx.tid * SCAN_E];
+    for (int e = 1; e < SCAN_E; ++e) mine = aff_compose(mine, el[ctx.tid * SCAN_E + e]);
+    Aff<T> blk;
+    Aff<T> pre = block_scan_aff(ctx, mine, blk, scratch);
+    if (p.nchunks <= 1) grand = blk;
+    pre = aff_compose(carry, pre);
+    T acc[4] = {0, 0, 0, 0};
+    T x = pre.b, y = pre.c;          // state = prefix applied to the zero state
+    for (int e = 0; e < SCAN_E; ++e) {
+      long pos = p0 + ctx.tid * SCAN_E + e;
+      if (pos >= p.n) break;
+      Aff<T> a = el[ctx.tid * SCAN_E + e];
+      T x1 = x + a.a * y + a.b, y1 = y + a.c;
+      p.out.put(pos, x, y, x1, y1, grand.b, acc);
+      x = x1; y = y1;
+    }
+    p.out.finish(ctx, acc, grand.b, scratch);
+#endif
   }
 };
 
@@ -176,18 +225,18 @@ template <class T> struct FwdElem {
 };
 // P_b = exp(slope l_b + tw_b - tw_last l_b / l_last); partial S
 template <class T> struct FwdOut {
-  AmpModel<T> m; const T* pos; const T* total;   // total[0] = tw_{K-1}
+  AmpModel<T> m; const T* pos;
   T* P; T* partials; unsigned* counter; T* scal;
-  NB_HD NB_INLINE void put(long b, T, T, T x1, T, T* acc) const {
+  NB_HD NB_INLINE void put(long b, T, T, T x1, T, T total, T* acc) const {
     AmpPoint<T> ap = amp_point(m, pos);
     T l = m.ell[b], llast = m.ell[m.K - 1];
     T u = ap.slope * l;
-    if (m.has_dev) u += x1 - total[0] * (l / llast);
+    if (m.has_dev) u += x1 - total * (l / llast);
     T Pb = nb_exp(u);
     P[b] = Pb;
     if (b >= 1) acc[0] += m.mult[b] * (m.kind_power ? Pb : Pb * Pb);
   }
-  NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, void* scratch) const {
+  NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, T total, void* scratch) const {
     T s = ctx.block_sum(acc[0], scratch);
     if (ctx.tid == 0) partials[ctx.bid] = s;
     if (ctx.last_block(counter)) {
@@ -196,7 +245,7 @@ template <class T> struct FwdOut {
         AmpPoint<T> ap = amp_point(m, pos);
         scal[SC_S] = S; scal[SC_FLU] = ap.flu; scal[SC_SLOPE] = ap.slope; scal[SC_SIG] = ap.sig;
         scal[SC_ASP] = ap.asp; scal[SC_Z] = ap.z; scal[SC_SCALING] = ap.scl;
-        scal[SC_TWLAST] = m.has_dev ? total[0] : T(0);
+        scal[SC_TWLAST] = m.has_dev ? total : T(0);
       }
     }
   }
@@ -247,16 +296,16 @@ template <class T> struct JvpElem {
   }
 };
 template <class T> struct JvpOut {
-  AmpModel<T> m; const T* pos; const T* t; const T* total; const T* wS;
+  AmpModel<T> m; const T* pos; const T* t; const T* wS;
   T* du; T* partials; unsigned* counter; T* scal;
-  NB_HD NB_INLINE void put(long b, T, T, T x1, T, T* acc) const {
+  NB_HD NB_INLINE void put(long b, T, T, T x1, T, T total, T* acc) const {
     T l = m.ell[b], llast = m.ell[m.K - 1];
     T d = m.slp_b * t[m.off_slp] * l;
-    if (m.has_dev) d += x1 - total[0] * (l / llast);
+    if (m.has_dev) d += x1 - total * (l / llast);
     du[b] = d;
     acc[0] += wS[b] * d;
   }
-  NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, void* scratch) const {
+  NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, T, void* scratch) const {
     T s = ctx.block_sum(acc[0], scratch);
     if (ctx.tid == 0) partials[ctx.bid] = s;
     if (ctx.last_block(counter)) {
@@ -296,18 +345,12 @@ template <class T> struct SegSumBody {
       sm[i] = s;
     }
     ctx.sync();
-    for (int half = lpb >> 1; half >= 1; half >>= 1) {   // fixed tree over the lanes of each bin
-      NB_FOR(ctx, i, bpb * half) {
-        int bin = i / half, l = i - bin * half;
-        sm[(bin << p.lg_lpb) + l] += sm[(bin << p.lg_lpb) + l + half];
-      }
-      ctx.sync();
-    }
     T a0 = 0, a1 = 0;
     NB_FOR(ctx, i, bpb) {
       long b = b0 + i;
       if (b < m.K) {
-        T abar = sm[i << p.lg_lpb];
+        T abar = 0;
+        for (int l = 0; l < lpb; ++l) abar += sm[(i << p.lg_lpb) + l];   // fixed order
         if (p.abar) p.abar[b] = abar;
         if (p.g) {
           T gb = (b == 0) ? T(0) : abar * p.amp[b];
@@ -359,7 +402,7 @@ template <class T> struct VjpOut {
   const T* p3_partials; int n_p3;       // [n_p3][2]: acc0 = sum of position-space cotangent
   const T* p5_partials; int n_p5;       // [n_p5]: xi-block of <add, out>
   T scl_factor;                         // factor applied to the p3 sum for the scaling leaf
-  NB_HD NB_INLINE void put(long p, T x0, T, T, T y1, T* acc) const {
+  NB_HD NB_INLINE void put(long p, T x0, T, T, T y1, T, T* acc) const {
     long j = (m.K - 3) - p;
     T sig = scal_in[SC_SIG], asp = scal_in[SC_ASP];
     T dt = m.dt[j], sq = nb_sqrt(dt), sd = sig * sq, q = nb_sqrt(dt * dt / T(12) + asp);
@@ -379,7 +422,7 @@ template <class T> struct VjpOut {
     if (add) { T a = add[off]; v += a; dot += a * v; }
     out[off] = v;
   }
-  NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, void* scratch) const {
+  NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, T, void* scratch) const {
     T s0 = ctx.block_sum(acc[0], scratch), s1 = ctx.block_sum(acc[1], scratch), s2 = ctx.block_sum(acc[2], scratch);
     if (ctx.tid == 0) { partials[3 * ctx.bid] = s0; partials[3 * ctx.bid + 1] = s1; partials[3 * ctx.bid + 2] = s2; }
     if (ctx.last_block(counter)) {

@@ -83,15 +83,14 @@ template <class T> struct Lin : LinBase {
   void amp_forward(stream_t st) {
     Model<T>& m = *M; const int K = m.am.K;
     FwdElem<T> el; el.m = m.am; el.pos = pos.p;
-    if (m.am.has_dev) {
+    const int nch = m.am.has_dev ? m.nchunksK : 1;   // without deviations every element is the identity
+    if (m.am.has_dev && m.nchunksK > 1) {
       ScanAggParams<T, FwdElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p;
       launch<ScanAggBody<T, FwdElem<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
-      ScanTopParams<T> pt; pt.nchunks = m.nchunksK; pt.agg = m.agg.p; pt.pre = m.pre.p; pt.total = m.total.p;
-      launch<ScanTopBody<T>>(1, 32, 0, st, pt);
     }
-    FwdOut<T> fo; fo.m = m.am; fo.pos = pos.p; fo.total = m.total.p; fo.P = Pb.p; fo.partials = m.partials.p;
+    FwdOut<T> fo; fo.m = m.am; fo.pos = pos.p; fo.P = Pb.p; fo.partials = m.partials.p;
     fo.counter = m.counters.p; fo.scal = scal.p;
-    ScanApplyParams<T, FwdElem<T>, FwdOut<T>> pc; pc.n = K; pc.elem = el; pc.out = fo; pc.pre = m.am.has_dev ? m.pre.p : nullptr;
+    ScanApplyParams<T, FwdElem<T>, FwdOut<T>> pc; pc.n = K; pc.elem = el; pc.out = fo; pc.agg = m.agg.p; pc.nchunks = nch;
     launch<ScanApplyBody<T, FwdElem<T>, FwdOut<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
     AmpTabParams<T> pt2; pt2.m = m.am; pt2.P = Pb.p; pt2.amp = amp.p; pt2.wS = wS.p; pt2.partials = m.partials.p;
     pt2.counter = m.counters.p + 1; pt2.scal = scal.p;
@@ -102,15 +101,14 @@ template <class T> struct Lin : LinBase {
   void amp_tangent(stream_t st, const T* t) {
     Model<T>& m = *M; const int K = m.am.K;
     JvpElem<T> el; el.m = m.am; el.pos = pos.p; el.t = t; el.scal = scal.p;
-    if (m.am.has_dev) {
+    const int nch = m.am.has_dev ? m.nchunksK : 1;
+    if (m.am.has_dev && m.nchunksK > 1) {
       ScanAggParams<T, JvpElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p;
       launch<ScanAggBody<T, JvpElem<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
-      ScanTopParams<T> pt; pt.nchunks = m.nchunksK; pt.agg = m.agg.p; pt.pre = m.pre.p; pt.total = m.total.p;
-      launch<ScanTopBody<T>>(1, 32, 0, st, pt);
     }
-    JvpOut<T> jo; jo.m = m.am; jo.pos = pos.p; jo.t = t; jo.total = m.total.p; jo.wS = wS.p; jo.du = m.du.p;
+    JvpOut<T> jo; jo.m = m.am; jo.pos = pos.p; jo.t = t; jo.wS = wS.p; jo.du = m.du.p;
     jo.partials = m.partials.p; jo.counter = m.counters.p + 2; jo.scal = scal.p;
-    ScanApplyParams<T, JvpElem<T>, JvpOut<T>> pc; pc.n = K; pc.elem = el; pc.out = jo; pc.pre = m.am.has_dev ? m.pre.p : nullptr;
+    ScanApplyParams<T, JvpElem<T>, JvpOut<T>> pc; pc.n = K; pc.elem = el; pc.out = jo; pc.agg = m.agg.p; pc.nchunks = nch;
     launch<ScanApplyBody<T, JvpElem<T>, JvpOut<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
   }
   ProMetric<T> pro_metric(const T* t) const {
@@ -134,14 +132,14 @@ template <class T> struct Lin : LinBase {
     vo.p5_partials = P.p5part.p; vo.n_p5 = use_p5_dot ? P.c5.grid : 0; vo.scl_factor = scl_factor;
     if (nj > 0) {
       VjpElem<T> el; el.m = m.am; el.g = m.gbuf.p; el.wS = wS.p; el.scal = scal.p;
-      ScanAggParams<T, VjpElem<T>> pa; pa.n = nj; pa.elem = el; pa.agg = m.agg.p;
-      launch<ScanAggBody<T, VjpElem<T>>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pa);
-      ScanTopParams<T> pt; pt.nchunks = m.nchunksJ; pt.agg = m.agg.p; pt.pre = m.pre.p; pt.total = m.total.p;
-      launch<ScanTopBody<T>>(1, 32, 0, st, pt);
-      ScanApplyParams<T, VjpElem<T>, VjpOut<T>> pc; pc.n = nj; pc.elem = el; pc.out = vo; pc.pre = m.pre.p;
+      if (m.nchunksJ > 1) {
+        ScanAggParams<T, VjpElem<T>> pa; pa.n = nj; pa.elem = el; pa.agg = m.agg.p;
+        launch<ScanAggBody<T, VjpElem<T>>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pa);
+      }
+      ScanApplyParams<T, VjpElem<T>, VjpOut<T>> pc; pc.n = nj; pc.elem = el; pc.out = vo; pc.agg = m.agg.p; pc.nchunks = m.nchunksJ;
       launch<ScanApplyBody<T, VjpElem<T>, VjpOut<T>>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pc);
     } else {
-      ScanApplyParams<T, NoElem<T>, VjpOut<T>> pc; pc.n = 0; pc.out = vo; pc.pre = nullptr;
+      ScanApplyParams<T, NoElem<T>, VjpOut<T>> pc; pc.n = 0; pc.out = vo; pc.agg = nullptr; pc.nchunks = 1;
       launch<ScanApplyBody<T, NoElem<T>, VjpOut<T>>>(1, SCAN_NT, m.scan_smem(), st, pc);
     }
   }

@@ -229,7 +229,7 @@ template <class T> struct Plan : PlanBase {
     {
       double avg = (double)g.nW / (double)g.K;
       seg_lg_lpb = 0;
-      while (seg_lg_lpb < 8 && (1 << (seg_lg_lpb + 1)) <= avg * 1.5) ++seg_lg_lpb;
+      while (seg_lg_lpb < 6 && (1 << (seg_lg_lpb + 1)) <= avg / 3.0) ++seg_lg_lpb;   // ~3-6 entries per lane
     }
     p3part.alloc((size_t)2 * c3.grid);
     p5part.alloc((size_t)c5.grid);

@@ -200,3 +200,36 @@ def check_cg(rt):
             x, res = lin.cg_solve(tj, tx0 if use_x0 else None, check_every=3, **kw)
             assert (res.nit, res.info, res.nfev) == (ores.nit, ores.info, ores.nfev), (name, kw, use_x0)
             assert rel_err(t2n(x), ores.x) < tol, (name, kw, use_x0)
+
+
+def check_against_oracle(rt, shape, distances, lh_kind="gauss", seed=11, tol=1e-10, **cf_kw):
+    """Energy / gradient / metric / sqrt-metrics against the oracle on a grid without fixture
+    (used for grids with several scan chunks, K > 2048, and other shapes)."""
+    c = dict(shape=shape, distances=distances, offset_mean=0.3, offset_std=(0.2, 0.1), fluctuations=(0.5, 0.1),
+             loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05), lh=lh_kind)
+    c.update(cf_kw)
+    ocf = build_oracle(c)
+    osig = oracle.SignalOracle(ocf, "exp")
+    lay = oracle.Layout(osig.domain)
+    rng = np.random.default_rng(seed)
+    pos, tan = lay.random(rng), lay.random(rng)
+    pos = {k: 0.5 * v for k, v in pos.items()}
+    if lh_kind == "gauss":
+        data = osig(pos) + 0.3 * rng.standard_normal(shape)
+        olh = oracle.GaussianOracle(data, 1.0 / 0.09, osig)
+        g = dict(data=data, noise_cov_inv=1.0 / 0.09)
+    else:
+        data = rng.poisson(osig(pos)).astype(np.int64)
+        olh = oracle.PoissonianOracle(data, osig)
+        g = dict(data=data)
+    lh = build_product_lh(c, g, rt)
+    tp = {k: torch.as_tensor(v) for k, v in pos.items()}
+    tt = {k: torch.as_tensor(v) for k, v in tan.items()}
+    e, grad = lh.energy_and_gradient(tp)
+    oe, ograd = olh.energy_and_gradient(pos)
+    assert abs(e - oe) <= tol * abs(oe)
+    assert tree_err(grad, ograd) < tol
+    assert tree_err(lh.metric(tp, tt), olh.metric(pos, tan)) < tol
+    u = rng.standard_normal(shape)
+    assert tree_err(lh.left_sqrt_metric(tp, u), olh.left_sqrt_metric(pos, u)) < tol
+    assert rel_err(t2n(lh.right_sqrt_metric(tp, tt)), olh.right_sqrt_metric(pos, tan)) < tol

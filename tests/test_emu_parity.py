@@ -53,6 +53,13 @@ def test_cg(rt):
     pc.check_cg(rt)
 
 
+def test_multichunk_amplitude_chain(rt):
+    """K > 2048 mode bins: the amplitude scans span several chunks (carry-in from chunk aggregates)."""
+    pc.check_against_oracle(rt, (128, 256), (0.01, 0.02))
+    pc.check_against_oracle(rt, (256, 256), 1.0 / 256, lh_kind="poisson", asperity=None)
+    pc.check_against_oracle(rt, (64, 64), 0.1, flexibility=None, asperity=None)
+
+
 def test_unsupported_shapes_fail_loudly(rt):
     with pytest.raises(nb.NB200Error, match="power of two"):
         nb.Plan((3, 3), 0.1, runtime=rt)

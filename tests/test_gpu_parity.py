@@ -51,6 +51,13 @@ def test_cg(rt):
     pc.check_cg(rt)
 
 
+def test_multichunk_amplitude_chain(rt):
+    """K > 2048 mode bins: the amplitude scans span several chunks (carry-in from chunk aggregates)."""
+    pc.check_against_oracle(rt, (128, 256), (0.01, 0.02))
+    pc.check_against_oracle(rt, (256, 256), 1.0 / 256, lh_kind="poisson", asperity=None)
+    pc.check_against_oracle(rt, (64, 64), 0.1, flexibility=None, asperity=None)
+
+
 @pytest.mark.parametrize("shape,dist,kind", [((128, 128), 1.0 / 128, "gauss"), ((2048, 2048), 1.0 / 2048, "poisson"),
                                              ((4096, 4096), 1.0 / 4096, "gauss"), ((256, 256, 256), 1.0 / 256, "gauss")])
 def test_full_size_properties(rt, shape, dist, kind):
