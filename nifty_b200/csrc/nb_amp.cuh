@@ -296,13 +296,13 @@ template <class T> struct JvpElem {
   }
 };
 template <class T> struct JvpOut {
-  AmpModel<T> m; const T* pos; const T* t; const T* wS;
-  T* du; T* partials; unsigned* counter; T* scal;
+  AmpModel<T> m; const T* pos; const T* t; const T* wS; const T* amp;
+  cplx<T>* ad; T* partials; unsigned* counter; T* scal;   // ad[b] = (A_b, du_b)
   NB_HD NB_INLINE void put(long b, T, T, T x1, T, T total, T* acc) const {
     T l = m.ell[b], llast = m.ell[m.K - 1];
     T d = m.slp_b * t[m.off_slp] * l;
     if (m.has_dev) d += x1 - total * (l / llast);
-    du[b] = d;
+    ad[b] = cmake<T>(amp[b], d);
     acc[0] += wS[b] * d;
   }
   NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, T, void* scratch) const {

@@ -45,7 +45,7 @@ template <class T> void Model<T>::init(Plan<T>* plan_, const nb200_model_desc& d
   nchunksK = (g.K + SCAN_CH - 1) / SCAN_CH;
   nchunksJ = std::max(1, (g.K - 2 + SCAN_CH - 1) / SCAN_CH);
   agg.alloc(nchunksK + 1); pre.alloc(2 * (size_t)nchunksK + 2); total.alloc(2);
-  du.alloc(g.K); gbuf.alloc(g.K);
+  ad.alloc(g.K); gbuf.alloc(g.K);
   size_t np = std::max<size_t>(3 * (size_t)nchunksK + 3, 2 * (size_t)P->seg_grid() + 2);
   np = std::max<size_t>(np, 4 * 2048);
   partials.alloc(np);

@@ -129,6 +129,17 @@ template <> __device__ NB_INLINE cplx<float> ldg(const cplx<float>* p) {
 }
 #endif
 
+// cooperative L2 prefetch of [p, p+bytes): turns the DRAM latency of a later phase into an L2 hit
+#ifdef NB_EMU
+inline void prefetch_l2(Ctx&, const void*, size_t) {}
+#else
+__device__ NB_INLINE void prefetch_l2(Ctx& ctx, const void* p, size_t bytes) {
+  const char* c = reinterpret_cast<const char*>(p);
+  for (size_t o = (size_t)ctx.tid * 128; o < bytes; o += (size_t)ctx.nthr * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+}
+#endif
+
 #define NB_FOR(ctx, i, count) for (int i = (ctx).tid; i < (int)(count); i += (ctx).nthr)
 
 NB_HH NB_INLINE int fold_idx(int x, int n) { return x <= n - x ? x : n - x; }

@@ -156,7 +156,8 @@ NB_HD NB_INLINE void fft_stage(Ctx& ctx, cplx<T>* s, const FftDev& f, int st, in
   ctx.sync();
 }
 
-// First DIF stage (m = n) with the inputs taken from a loader: ld(line, x) -> cplx<T>
+// First DIF stage (m = n) with the inputs taken from a loader: ld.batch<R>(line, j, lmr, a) fills
+// a[q] = x[j + (q << lmr)], q < R, issuing all of its loads before any use
 template <int LR, class T, class Ld>
 NB_HD NB_INLINE void fft_stage_first(Ctx& ctx, cplx<T>* s, const FftDev& f, int nlines, int pitch,
                                      const cplx<T>* tw, int lg_tw, const Ld& ld) {
@@ -167,8 +168,7 @@ NB_HD NB_INLINE void fft_stage_first(Ctx& ctx, cplx<T>* s, const FftDev& f, int 
   NB_FOR(ctx, t, total) {
     int line = t >> lmr, j = t & ((1 << lmr) - 1);
     cplx<T> a[R];
-#pragma unroll
-    for (int q = 0; q < R; ++q) a[q] = ld(line, j + (q << lmr));
+    ld.template batch<R>(line, j, lmr, a);
     cplx<T> w = cmake<T>(T(1), T(0));
     if (j != 0) w = ldg(tw + ((size_t)j << tw_shift));
     dftR<LR>(a);
@@ -195,7 +195,7 @@ template <class T, class Ld>
 NB_HD NB_INLINE void fft_dif_load(Ctx& ctx, cplx<T>* s, const FftDev& f, int nlines, int pitch, const cplx<T>* tw,
                                   int lg_tw, const Ld& ld) {
   if (f.lg == 0) {
-    NB_FOR(ctx, t, nlines) s[t * pitch] = ld(t, 0);
+    NB_FOR(ctx, t, nlines) { cplx<T> a[1]; ld.template batch<1>(t, 0, 0, a); s[t * pitch] = a[0]; }
     ctx.sync();
     return;
   }

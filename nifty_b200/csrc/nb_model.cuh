@@ -56,7 +56,8 @@ template <class T> struct Model : ModelBase {
   bool has_w_arr = false;
   // chain workspaces
   DevBuf<Aff<T>> agg;
-  DevBuf<T> pre, total, du, gbuf, partials, tmp_pos;
+  DevBuf<T> pre, total, gbuf, partials, tmp_pos;
+  DevBuf<cplx<T>> ad;
   DevBuf<unsigned> counters;
   int nchunksK = 1, nchunksJ = 1;
   Lin<T>* scratch_lin = nullptr;
@@ -106,15 +107,15 @@ template <class T> struct Lin : LinBase {
       ScanAggParams<T, JvpElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p;
       launch<ScanAggBody<T, JvpElem<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
     }
-    JvpOut<T> jo; jo.m = m.am; jo.pos = pos.p; jo.t = t; jo.wS = wS.p; jo.du = m.du.p;
+    JvpOut<T> jo; jo.m = m.am; jo.pos = pos.p; jo.t = t; jo.wS = wS.p; jo.amp = amp.p; jo.ad = m.ad.p;
     jo.partials = m.partials.p; jo.counter = m.counters.p + 2; jo.scal = scal.p;
     ScanApplyParams<T, JvpElem<T>, JvpOut<T>> pc; pc.n = K; pc.elem = el; pc.out = jo; pc.agg = m.agg.p; pc.nchunks = nch;
     launch<ScanApplyBody<T, JvpElem<T>, JvpOut<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
   }
   ProMetric<T> pro_metric(const T* t) const {
     const Model<T>& m = *M;
-    ProMetric<T> pro; pro.xi = pos.p + m.am.off_xi; pro.t = t + m.am.off_xi; pro.idxf = m.P->idxf.p; pro.amp = amp.p;
-    pro.du = m.du.p; pro.scal = scal.p + SC_CJ; pro.kappa = m.am.kind_power ? T(0.5) : T(1); pro.fg = m.P->fold_geom();
+    ProMetric<T> pro; pro.xi = pos.p + m.am.off_xi; pro.t = t + m.am.off_xi; pro.idxf = m.P->idxf.p;
+    pro.ad = m.ad.p; pro.scal = scal.p + SC_CJ; pro.kappa = m.am.kind_power ? T(0.5) : T(1); pro.fg = m.P->fold_geom();
     return pro;
   }
 

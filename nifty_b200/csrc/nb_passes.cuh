@@ -26,22 +26,15 @@
 
 namespace nb {
 
-template <class T> NB_HD NB_INLINE void load_pair(const T* p, T& a, T& b) {
-  if ((reinterpret_cast<uintptr_t>(p) & (2 * sizeof(T) - 1)) == 0) {
+// pair load: one 2*sizeof(T)-byte access when the caller guarantees alignment (compile time)
+template <bool ALIGNED, class T> NB_HD NB_INLINE void load_pair(const T* p, T& a, T& b) {
+  if (ALIGNED) {
     cplx<T> v = *reinterpret_cast<const cplx<T>*>(p);
     a = v.x; b = v.y;
   } else {
     a = p[0]; b = p[1];
   }
 }
-
-// ---------------------------------------------------------------------------------------------
-// P1 prologues: value of the real input line (o, rr) at element j (harmonic-space coordinates)
-// ---------------------------------------------------------------------------------------------
-template <class T> struct ProPlain {
-  const T* x;
-  NB_HD NB_INLINE void load2(int, int, int, long off, T& a, T& b) const { load_pair(x + off, a, b); }
-};
 
 // folded mode-bin lookup shared by the amplitude prologues / epilogues
 struct FoldGeom {
@@ -52,32 +45,79 @@ struct FoldGeom {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// P1 prologues: `batch<NQ, ALIGNED>` produces the NQ complex inputs z = x[2e] + i x[2e+1] of one
+// butterfly (elements e_q = j + (q << lmr)) of the real line (o, rr).  All loads of a batch are
+// issued before anything depends on them (first the streaming loads and bin indices, then the
+// table gathers), with no control flow in between -- the per-element dependent chain
+// index -> amplitude used to be paid 16 times in a row per thread.
+// ---------------------------------------------------------------------------------------------
+template <class T> NB_HH NB_INLINE bool ptr_aligned2(const T* p) { return (reinterpret_cast<uintptr_t>(p) & (2 * sizeof(T) - 1)) == 0; }
+
+template <class T> struct ProPlain {
+  const T* x;
+  bool aligned() const { return ptr_aligned2(x); }
+  template <int NQ, bool AL> NB_HD NB_INLINE void batch(int, int, long off, int j, int lmr, cplx<T>* a) const {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) { T u, v; load_pair<AL>(x + off + 2 * (j + (q << lmr)), u, v); a[q] = cmake<T>(u, v); }
+  }
+  NB_HD NB_INLINE void prefetch(Ctx& ctx, int, int, long off, long count) const { prefetch_l2(ctx, x + off, count * sizeof(T)); }
+};
+
 // a[b(k)] * xi_k   (forward model, correlated_field.py:911 with azm folded into the table)
 template <class T> struct ProAmp {
   const T* xi; const int* idxf; const T* amp; FoldGeom fg;
-  NB_HD NB_INLINE void load2(int o, int rr, int j, long off, T& a, T& b) const {
-    long fb = fg.base(o, rr);
-    T x0, x1; load_pair(xi + off, x0, x1);
-    a = ldg(amp + ldg(idxf + fb + fold_idx(j, fg.n))) * x0;
-    b = ldg(amp + ldg(idxf + fb + fold_idx(j + 1, fg.n))) * x1;
+  bool aligned() const { return ptr_aligned2(xi); }
+  template <int NQ, bool AL> NB_HD NB_INLINE void batch(int o, int rr, long off, int j, int lmr, cplx<T>* a) const {
+    const int* ip = idxf + fg.base(o, rr);
+    int b0[NQ], b1[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      int e = 2 * (j + (q << lmr));
+      T u, v; load_pair<AL>(xi + off + e, u, v); a[q] = cmake<T>(u, v);
+      b0[q] = ldg(ip + fold_idx(e, fg.n)); b1[q] = ldg(ip + fold_idx(e + 1, fg.n));
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) { a[q].x *= ldg(amp + b0[q]); a[q].y *= ldg(amp + b1[q]); }
+  }
+  NB_HD NB_INLINE void prefetch(Ctx& ctx, int o, int rr, long off, long count) const {
+    prefetch_l2(ctx, xi + off, count * sizeof(T));
+    prefetch_l2(ctx, idxf + fg.base(o, rr), (size_t)fg.h1 * sizeof(int));
   }
 };
 
-// JVP input: A_b t_k + dA_b xi_k with dA_b = A_b (cj + kappa du_b) (b>=1), dA_0 = da0
+// JVP input: A_b t_k + dA_b xi_k with dA_b = A_b (cj + kappa du_b) (b>=1), dA_0 = da0.
+// `ad` interleaves (A_b, du_b) so that one 2*sizeof(T) gather serves both.
 template <class T> struct ProMetric {
-  const T* xi; const T* t; const int* idxf; const T* amp; const T* du; const T* scal;  // scal[0]=cj, scal[1]=da0
+  const T* xi; const T* t; const int* idxf; const cplx<T>* ad; const T* scal;  // scal[0]=cj, scal[1]=da0
   T kappa; FoldGeom fg;
-  NB_HD NB_INLINE T one(int b, T xv, T tv, T cj, T da0) const {
-    T A = ldg(amp + b);
-    T dA = (b == 0) ? da0 : A * (cj + (du ? kappa * ldg(du + b) : T(0)));
-    return A * tv + dA * xv;
+  bool aligned() const { return ptr_aligned2(xi) && ptr_aligned2(t); }
+  NB_HD NB_INLINE T one(int b, cplx<T> g, T xv, T tv, T cj, T da0) const {
+    T dA = (b == 0) ? da0 : g.x * (cj + kappa * g.y);
+    return g.x * tv + dA * xv;
   }
-  NB_HD NB_INLINE void load2(int o, int rr, int j, long off, T& a, T& b) const {
-    long fb = fg.base(o, rr);
-    T x0, x1, t0, t1; load_pair(xi + off, x0, x1); load_pair(t + off, t0, t1);
-    T cj = ldg(scal), da0 = ldg(scal + 1);
-    a = one(ldg(idxf + fb + fold_idx(j, fg.n)), x0, t0, cj, da0);
-    b = one(ldg(idxf + fb + fold_idx(j + 1, fg.n)), x1, t1, cj, da0);
+  template <int NQ, bool AL> NB_HD NB_INLINE void batch(int o, int rr, long off, int j, int lmr, cplx<T>* a) const {
+    const int* ip = idxf + fg.base(o, rr);
+    const T cj = ldg(scal), da0 = ldg(scal + 1);
+    int b0[NQ], b1[NQ];
+    cplx<T> tv[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      int e = 2 * (j + (q << lmr));
+      T u, v; load_pair<AL>(xi + off + e, u, v); a[q] = cmake<T>(u, v);
+      load_pair<AL>(t + off + e, u, v); tv[q] = cmake<T>(u, v);
+      b0[q] = ldg(ip + fold_idx(e, fg.n)); b1[q] = ldg(ip + fold_idx(e + 1, fg.n));
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      cplx<T> g0 = ldg(ad + b0[q]), g1 = ldg(ad + b1[q]);
+      a[q] = cmake<T>(one(b0[q], g0, a[q].x, tv[q].x, cj, da0), one(b1[q], g1, a[q].y, tv[q].y, cj, da0));
+    }
+  }
+  NB_HD NB_INLINE void prefetch(Ctx& ctx, int o, int rr, long off, long count) const {
+    prefetch_l2(ctx, xi + off, count * sizeof(T));
+    prefetch_l2(ctx, t + off, count * sizeof(T));
+    prefetch_l2(ctx, idxf + fg.base(o, rr), (size_t)fg.h1 * sizeof(int));
   }
 };
 
@@ -89,35 +129,42 @@ template <class T, class Pro> struct P1Params {
   const cplx<T>* tw; int lg_tw;   // table for the REAL length n (tw_n multiple of n)
   FftDev fft;                     // complex FFT of length n/2
   cplx<T>* out;
+  int ahead;                      // CTAs resident on the device: prefetch distance (0 = off)
   Pro pro;
 };
 
-template <class T, class Pro> struct P1Body {
+template <class T, class Pro, bool AL> struct P1Body {
   typedef P1Params<T, Pro> Params;
+  struct Loader {
+    const Params& p; int o, rr0; long in0;
+    template <int NQ> NB_HD NB_INLINE void batch(int r, int j, int lmr, cplx<T>* a) const {
+      const int rr = rr0 + r;
+      p.pro.template batch<NQ, AL>(o, rr, in0 + rr * p.in_rstride, j, lmr, a);
+    }
+  };
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
     cplx<T>* s = reinterpret_cast<cplx<T>*>(smem);
     const int R = 1 << p.lg_R, lg_h = p.lg_n - 1, h = 1 << lg_h;
-    const int gpo = (p.n_r + R - 1) >> p.lg_R;
+    const int gpo = p.n_r >> p.lg_R;          // R divides n_r (both powers of two, checked by the host)
     const int o = ctx.bid / gpo, rr0 = (ctx.bid % gpo) << p.lg_R;
     const long in0 = o * p.in_ostride;
-    auto ld = [&](int r, int j) {
-      int rr = rr0 + r;
-      T a = 0, b = 0;
-      if (rr < p.n_r) p.pro.load2(o, rr, 2 * j, in0 + rr * p.in_rstride + 2 * j, a, b);
-      return cmake<T>(a, b);
-    };
+    if (p.ahead > 0 && ctx.bid + p.ahead < ctx.nblk) {   // inputs of the CTA that will follow on this SM
+      const int b2 = ctx.bid + p.ahead, o2 = b2 / gpo, r2 = (b2 % gpo) << p.lg_R;
+      if (p.in_rstride == (1 << p.lg_n)) p.pro.prefetch(ctx, o2, r2, o2 * p.in_ostride + r2 * p.in_rstride, (long)R << p.lg_n);
+    }
+    Loader ld{p, o, rr0, in0};
     fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);   // w_h^j = w_n^{2j}: same table, larger stride
     const T half = T(0.5);
     cplx<T>* outp = p.out + o * p.out_ostride + rr0;
     const int tsh = p.lg_tw - p.lg_n;
     NB_FOR(ctx, i, (h + 1) << p.lg_R) {
       int k = i >> p.lg_R, r = i & (R - 1);
-      if (rr0 + r >= p.n_r) continue;
       const cplx<T>* line = s + r * p.pitch;
-      cplx<T> zk = line[ldg(p.fft.pos + (k & (h - 1)))];
-      cplx<T> zc = cconj(line[ldg(p.fft.pos + ((h - k) & (h - 1)))]);
-      cplx<T> e = zk + zc, d = zk - zc;
+      int pk = ldg(p.fft.pos + (k & (h - 1))), pc = ldg(p.fft.pos + ((h - k) & (h - 1)));
       cplx<T> w = ldg(p.tw + ((size_t)k << tsh));
+      cplx<T> zk = line[pk];
+      cplx<T> zc = cconj(line[pc]);
+      cplx<T> e = zk + zc, d = zk - zc;
       cplx<T> wd = cmul_mi(cmul(w, d));   // -i w (zk - zc)
       outp[k * p.out_kstride + r] = cmake<T>(half * (e.x + wd.x), half * (e.y + wd.y));
     }
@@ -138,24 +185,25 @@ template <class T> struct PCParams {
   cplx<T>* out;
 };
 
+// raw complex lines (stride `rstride` between the lines of a CTA); inactive lines read as zero
+template <class T> struct RawLoader {
+  const cplx<T>* base; long rstride; const struct LineInfo* li;
+  template <int NQ> NB_HD NB_INLINE void batch(int r, int j, int lmr, cplx<T>* a) const;
+};
+
 template <class T> struct PCBody {
   typedef PCParams<T> Params;
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
     cplx<T>* s = reinterpret_cast<cplx<T>*>(smem);
     const int R = 1 << p.lg_R, n = 1 << p.lg_n;
-    const int gpo = (p.n_r + R - 1) >> p.lg_R;
+    const int gpo = p.n_r >> p.lg_R;
     const int o = ctx.bid / gpo, rr0 = (ctx.bid % gpo) << p.lg_R;
     const cplx<T>* inp = p.in + o * p.in_ostride + rr0 * p.in_rstride;
-    auto ld = [&](int r, int x) {
-      cplx<T> v = cmake<T>(0, 0);
-      if (rr0 + r < p.n_r) v = inp[r * p.in_rstride + x];
-      return v;
-    };
+    RawLoader<T> ld{inp, p.in_rstride, nullptr};          // R divides n_r: no bounds check
     fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
     cplx<T>* outp = p.out + o * p.out_ostride + rr0;
     NB_FOR(ctx, i, n << p.lg_R) {
       int k = i >> p.lg_R, r = i & (R - 1);
-      if (rr0 + r >= p.n_r) continue;
       outp[k * p.out_kstride + r] = s[r * p.pitch + ldg(p.fft.pos + k)];
     }
   }
@@ -183,6 +231,18 @@ struct MirrorGeom {
 // per-CTA table of the lines it owns (filled once, then read by every phase)
 struct LineInfo { int lA, lB, active, pad; };
 constexpr int LINEINFO_BYTES = 16 * 16;   // R <= 16
+
+template <class T> template <int NQ>
+NB_HD NB_INLINE void RawLoader<T>::batch(int r, int j, int lmr, cplx<T>* a) const {
+  const cplx<T>* lp = base + r * rstride + j;
+  if (li && !li[r].active) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) a[q] = cmake<T>(0, 0);
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) a[q] = lp[q << lmr];
+}
 
 NB_HD NB_INLINE void fill_line_info(Ctx& ctx, LineInfo* li, const MirrorGeom& mg, int l0, int R) {
   NB_FOR(ctx, r, R) {
@@ -286,6 +346,7 @@ template <class T> struct P3Params {
   const cplx<T>* in;       // [l][n]
   cplx<T>* out;            // [k in 0..n/2][out_kstride]
   long out_kstride;
+  int ahead;
   PointOp<T> op;
 };
 
@@ -319,13 +380,22 @@ template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
     T acc0 = 0, acc1 = 0;
     T cshift = p.op.cshift_ptr ? p.op.cshift_scale * ldg(p.op.cshift_ptr) : T(0);
     T scv = p.op.sc_ptr ? ldg(p.op.sc_ptr) : p.op.sc;
+    if (FWD && MODE == PM_METRIC) {
+      for (int r = 0; r < R; ++r) {
+        if (!li[r].active) continue;
+        prefetch_l2(ctx, p.op.jl_a + (long)li[r].lA * n, (size_t)n * sizeof(T));
+        if (p.op.jl_b != p.op.jl_a) prefetch_l2(ctx, p.op.jl_b + (long)li[r].lA * n, (size_t)n * sizeof(T));
+        if (li[r].lB >= 0) {
+          prefetch_l2(ctx, p.op.jl_a + (long)li[r].lB * n, (size_t)n * sizeof(T));
+          if (p.op.jl_b != p.op.jl_a) prefetch_l2(ctx, p.op.jl_b + (long)li[r].lB * n, (size_t)n * sizeof(T));
+        }
+      }
+    }
     if (FWD) {
+      if (p.ahead > 0 && ctx.bid + p.ahead < ctx.nblk)
+        prefetch_l2(ctx, p.in + ((long)(ctx.bid + p.ahead) << (p.lg_R + p.lg_n)), sizeof(cplx<T>) << (p.lg_R + p.lg_n));
       const cplx<T>* inp = p.in + (long)l0 * n;
-      auto ld = [&](int r, int x) {
-        cplx<T> v = cmake<T>(0, 0);
-        if (li[r].active) v = inp[r * n + x];
-        return v;
-      };
+      RawLoader<T> ld{inp, (long)n, li};
       fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
       if (n == 1) {
         NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], 0, 0, cshift, scv, acc0, acc1);
@@ -379,6 +449,7 @@ template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
 template <class T> struct EpiPlain {
   T* out; T scale;
   T* partials;   // unused
+  NB_HD NB_INLINE void prefetch(Ctx&, long, long, long, int) const {}
   NB_HD NB_INLINE void emit(long rowA, long rowB, long, long, int x, int y, T gAx, T gAy, T gBx, T gBy, T&) const {
     out[rowA + x] = gAx * scale;
     if (y != x) out[rowA + y] = gAy * scale;
@@ -394,24 +465,40 @@ template <class T> struct EpiPlain {
 template <class T> struct EpiAdjoint {
   T* out; const T* add; const T* xi; const int* idxf; const T* amp; T* W; T invV;
   T* partials;   // [nblk]
-  NB_HD NB_INLINE void one(long i, T A, T g, T& ws, T& acc) const {
-    g *= invV;
-    T o = A * g;
-    if (add) { T a = add[i]; o += a; acc += a * o; }
-    out[i] = o;
-    if (xi) ws += xi[i] * g;
-  }
+  // all loads first (the outputs may alias the inputs as far as the compiler knows), then the stores
   NB_HD NB_INLINE void emit(long rowA, long rowB, long fbase, long wbase, int x, int y, T gAx, T gAy, T gBx, T gBy,
                             T& acc) const {
-    T A = ldg(amp + ldg(idxf + fbase + x));
-    T ws = 0;
-    one(rowA + x, A, gAx, ws, acc);
-    if (y != x) one(rowA + y, A, gAy, ws, acc);
-    if (rowB >= 0) {
-      one(rowB + x, A, gBx, ws, acc);
-      if (y != x) one(rowB + y, A, gBy, ws, acc);
+    const bool two = (y != x), hasB = rowB >= 0;
+    int b = ldg(idxf + fbase + x);
+    T a0 = 0, a1 = 0, a2 = 0, a3 = 0, x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+    if (add) {
+      a0 = add[rowA + x];
+      if (two) a1 = add[rowA + y];
+      if (hasB) { a2 = add[rowB + x]; if (two) a3 = add[rowB + y]; }
+    }
+    if (xi) {
+      x0 = xi[rowA + x];
+      if (two) x1 = xi[rowA + y];
+      if (hasB) { x2 = xi[rowB + x]; if (two) x3 = xi[rowB + y]; }
+    }
+    T A = ldg(amp + b);
+    gAx *= invV; gAy *= invV; gBx *= invV; gBy *= invV;
+    T o0 = A * gAx + a0, o1 = A * gAy + a1, o2 = A * gBx + a2, o3 = A * gBy + a3;
+    T ws = x0 * gAx;
+    acc += a0 * o0;
+    out[rowA + x] = o0;
+    if (two) { out[rowA + y] = o1; ws += x1 * gAy; acc += a1 * o1; }
+    if (hasB) {
+      out[rowB + x] = o2; ws += x2 * gBx; acc += a2 * o2;
+      if (two) { out[rowB + y] = o3; ws += x3 * gBy; acc += a3 * o3; }
     }
     if (W) W[wbase + x] = ws;
+  }
+  // rows touched by the epilogue of a line (for L2 prefetch at CTA start)
+  NB_HD NB_INLINE void prefetch(Ctx& ctx, long rowA, long rowB, long fbase, int n) const {
+    if (add) { prefetch_l2(ctx, add + rowA, (size_t)n * sizeof(T)); if (rowB >= 0) prefetch_l2(ctx, add + rowB, (size_t)n * sizeof(T)); }
+    if (xi) { prefetch_l2(ctx, xi + rowA, (size_t)n * sizeof(T)); if (rowB >= 0) prefetch_l2(ctx, xi + rowB, (size_t)n * sizeof(T)); }
+    prefetch_l2(ctx, idxf + fbase, (size_t)(n / 2 + 1) * sizeof(int));
   }
 };
 
@@ -424,6 +511,7 @@ template <class T, class Epi> struct P5Params {
   FftDev fft;
   T hsign;
   const cplx<T>* in;   // [l][n]
+  int ahead;
   Epi epi;
 };
 
@@ -446,12 +534,17 @@ template <class T, class Epi> struct P5Body {
     const int l0 = ctx.bid << p.lg_R;
     fill_line_info(ctx, li, p.mg, l0, R);
     T acc = 0;
+    for (int r = 0; r < R; ++r) {
+      if (!li[r].active) continue;
+      const int nmid = 1 << p.mg.lg_mid;
+      int a = li[r].lA >> p.mg.lg_mid, km = li[r].lA & (nmid - 1);
+      long fbase = ((long)a * p.hmid1 + fold_idx(km, nmid)) * (h + 1);
+      p.epi.prefetch(ctx, (long)li[r].lA * n, li[r].lB >= 0 ? (long)li[r].lB * n : -1L, fbase, n);
+    }
+    if (p.ahead > 0 && ctx.bid + p.ahead < ctx.nblk)
+      prefetch_l2(ctx, p.in + ((long)(ctx.bid + p.ahead) << (p.lg_R + p.lg_n)), sizeof(cplx<T>) << (p.lg_R + p.lg_n));
     const cplx<T>* inp = p.in + (long)l0 * n;
-    auto ld = [&](int r, int x) {
-      cplx<T> v = cmake<T>(0, 0);
-      if (li[r].active) v = inp[r * n + x];
-      return v;
-    };
+    RawLoader<T> ld{inp, (long)n, li};
     fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
     if (n == 1) {
       NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], 0, 0, acc);

@@ -10,7 +10,7 @@
 
 namespace nb {
 
-struct PassCfg { int lg_n = 0, lg_R = 0, pitch = 1, grid = 1, block = 64; size_t smem = 0; };
+struct PassCfg { int lg_n = 0, lg_R = 0, pitch = 1, grid = 1, block = 64, ahead = 0; size_t smem = 0; };
 
 inline int ilog2(int64_t v) { int l = 0; while ((int64_t(1) << l) < v) ++l; return l; }
 inline bool is_pow2(int64_t v) { return v >= 1 && (v & (v - 1)) == 0; }
@@ -153,6 +153,8 @@ template <class T> std::vector<cplx<T>> make_twiddles(int n) {
   return tw;
 }
 
+inline bool prefetch_disabled() { const char* e = std::getenv("NB200_NO_PREFETCH"); return e && e[0] == '1'; }
+
 template <class T> struct Plan : PlanBase {
   int lg0 = 0, lgm = 0, lgl = 0;
   T hsign = 1;
@@ -189,6 +191,12 @@ template <class T> struct Plan : PlanBase {
     int blk = 64;
     while (blk < 256 && blk < bf) blk *= 2;
     c.block = blk;
+    {   // CTAs resident on the whole device (shared-memory limited): distance of the input prefetch
+      size_t per = c.smem + 2048;
+      int per_sm = (int)std::min<size_t>(8, (228 * 1024) / per);
+      c.ahead = std::max(1, per_sm) * sms;
+      if (prefetch_disabled()) c.ahead = 0;
+    }
     return c;
   }
 
@@ -256,14 +264,15 @@ template <class T> struct Plan : PlanBase {
 
   template <class Pro> void run_p1(stream_t st, const Pro& pro) {
     P1Params<T, Pro> p;
-    p.lg_n = lgl; p.lg_R = c1.lg_R; p.pitch = c1.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = flh; p.out = S0.p; p.pro = pro;
+    p.lg_n = lgl; p.lg_R = c1.lg_R; p.pitch = c1.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = flh; p.out = S0.p; p.ahead = c1.ahead; p.pro = pro;
     if (g.three) {
       p.n_o = g.n0; p.n_r = g.nm; p.in_ostride = (long)g.nm * g.nl; p.in_rstride = g.nl;
       p.out_ostride = (long)(g.hl + 1) * g.nm; p.out_kstride = g.nm;
     } else {
       p.n_o = 1; p.n_r = g.n0; p.in_ostride = 0; p.in_rstride = g.nl; p.out_ostride = 0; p.out_kstride = g.n0;
     }
-    launch<P1Body<T, Pro>>(c1.grid, c1.block, c1.smem, st, p);
+    if (pro.aligned()) launch<P1Body<T, Pro, true>>(c1.grid, c1.block, c1.smem, st, p);
+    else launch<P1Body<T, Pro, false>>(c1.grid, c1.block, c1.smem, st, p);
   }
   void run_pc(stream_t st, bool second) {
     if (!g.three) return;
@@ -281,7 +290,7 @@ template <class T> struct Plan : PlanBase {
   }
   template <bool FWD, bool ADJ> void run_p3(stream_t st, const PointOp<T>& op) {
     P3Params<T> p;
-    p.lg_n = lg0; p.lg_R = c3.lg_R; p.mg = mg3(); p.pitch = c3.pitch; p.tw = tw0.p; p.lg_tw = lg0; p.fft = f0; p.hsign = hsign;
+    p.lg_n = lg0; p.lg_R = c3.lg_R; p.mg = mg3(); p.pitch = c3.pitch; p.tw = tw0.p; p.lg_tw = lg0; p.fft = f0; p.hsign = hsign; p.ahead = c3.ahead;
     p.in = p3_in(); p.out = p3_out(); p.out_kstride = (long)g.nl * g.nm; p.op = op;
     const size_t sm = c3.smem + LINEINFO_BYTES;
     if constexpr (FWD && ADJ) {
@@ -300,7 +309,7 @@ template <class T> struct Plan : PlanBase {
   }
   template <class Epi> void run_p5(stream_t st, const Epi& epi) {
     P5Params<T, Epi> p;
-    p.lg_n = lgl; p.lg_R = c5.lg_R; p.mg = mg5(); p.hmid1 = g.hm + 1; p.pitch = c5.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = fl;
+    p.lg_n = lgl; p.lg_R = c5.lg_R; p.mg = mg5(); p.hmid1 = g.hm + 1; p.pitch = c5.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = fl; p.ahead = c5.ahead;
     p.hsign = hsign; p.in = S1.p; p.epi = epi;
     launch<P5Body<T, Epi>>(c5.grid, c5.block, c5.smem + LINEINFO_BYTES, st, p);
   }
