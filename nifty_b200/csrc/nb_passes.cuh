@@ -157,16 +157,32 @@ template <class T, class Pro, bool AL> struct P1Body {
     const T half = T(0.5);
     cplx<T>* outp = p.out + o * p.out_ostride + rr0;
     const int tsh = p.lg_tw - p.lg_n;
-    NB_FOR(ctx, i, (h + 1) << p.lg_R) {
-      int k = i >> p.lg_R, r = i & (R - 1);
-      const cplx<T>* line = s + r * p.pitch;
-      int pk = ldg(p.fft.pos + (k & (h - 1))), pc = ldg(p.fft.pos + ((h - k) & (h - 1)));
-      cplx<T> w = ldg(p.tw + ((size_t)k << tsh));
-      cplx<T> zk = line[pk];
-      cplx<T> zc = cconj(line[pc]);
-      cplx<T> e = zk + zc, d = zk - zc;
-      cplx<T> wd = cmul_mi(cmul(w, d));   // -i w (zk - zc)
-      outp[k * p.out_kstride + r] = cmake<T>(half * (e.x + wd.x), half * (e.y + wd.y));
+    constexpr int U = 4;
+    const int total = (h + 1) << p.lg_R;
+    for (int i0 = ctx.tid; i0 < total; i0 += ctx.nthr * U) {
+      int pk[U], pc[U];
+      cplx<T> w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        int i = i0 + u * ctx.nthr;
+        i = i < total ? i : 0;
+        int k = i >> p.lg_R;
+        pk[u] = ldg(p.fft.pos + (k & (h - 1)));
+        pc[u] = ldg(p.fft.pos + ((h - k) & (h - 1)));
+        w[u] = ldg(p.tw + ((size_t)k << tsh));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        int i = i0 + u * ctx.nthr;
+        if (i >= total) break;
+        int k = i >> p.lg_R, r = i & (R - 1);
+        const cplx<T>* line = s + r * p.pitch;
+        cplx<T> zk = line[pk[u]];
+        cplx<T> zc = cconj(line[pc[u]]);
+        cplx<T> e = zk + zc, d = zk - zc;
+        cplx<T> wd = cmul_mi(cmul(w[u], d));   // -i w (zk - zc)
+        outp[k * p.out_kstride + r] = cmake<T>(half * (e.x + wd.x), half * (e.y + wd.y));
+      }
     }
   }
 };
@@ -399,6 +415,54 @@ template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
       fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
       if (n == 1) {
         NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], 0, 0, cshift, scv, acc0, acc1);
+      } else if (MODE == PM_METRIC && ADJ) {
+        // hot path: pairs (x, n-x), 0 < x < h, of lines that have a partner; every load of a batch
+        // of U pairs is issued (from always-valid addresses) before anything depends on it
+        constexpr int U = 2;
+        const T* ja = p.op.jl_a; const T* jb = p.op.jl_b;
+        const bool same = (ja == jb);
+        const T sg = p.hsign, iv = p.op.invV;
+        const int cnt = R << lg_h;
+        for (int i0 = ctx.tid; i0 < cnt; i0 += ctx.nthr * U) {
+          int px[U], py[U]; bool ok[U];
+          T mAx[U], mAy[U], mBx[U], mBy[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            int i = i0 + u * ctx.nthr;
+            bool in = i < cnt;
+            i = in ? i : 0;
+            int r = i >> lg_h, x = i & (h - 1);
+            ok[u] = in && li[r].active && li[r].lB >= 0 && x != 0;
+            x = x != 0 ? x : 1;
+            int y = n - x;
+            long iA = (long)li[r].lA * n, iB = (long)(li[r].lB >= 0 ? li[r].lB : li[r].lA) * n;
+            px[u] = ldg(p.fft.pos + x); py[u] = ldg(p.fft.pos + y);
+            mAx[u] = ja[iA + x]; mAy[u] = ja[iA + y]; mBx[u] = ja[iB + x]; mBy[u] = ja[iB + y];
+            if (!same) { mAx[u] *= jb[iA + x]; mAy[u] *= jb[iA + y]; mBx[u] *= jb[iB + x]; mBy[u] *= jb[iB + y]; }
+            else { mAx[u] *= mAx[u]; mAy[u] *= mAy[u]; mBx[u] *= mBx[u]; mBy[u] *= mBy[u]; }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            int i = i0 + u * ctx.nthr;
+            cplx<T>* line = s + (i >> lg_h) * p.pitch;
+            cplx<T> cx = line[px[u]], cy = line[py[u]];
+            T aX = mAx[u] * ((cx.x + sg * cx.y) * iv + cshift), bY = mBy[u] * ((cx.x - sg * cx.y) * iv + cshift);
+            T aY = mAy[u] * ((cy.x + sg * cy.y) * iv + cshift), bX = mBx[u] * ((cy.x - sg * cy.y) * iv + cshift);
+            acc0 += (aX + aY) + (bX + bY);
+            line[px[u]] = cmake<T>(aX, bX);
+            line[py[u]] = cmake<T>(aY, bY);
+          }
+        }
+        // the self-paired columns x = 0 and x = h, and lines without a partner
+        NB_FOR(ctx, i, 2 * R) {
+          int r = i >> 1;
+          if (li[r].active) { int x = (i & 1) ? h : 0; pair(p, s + r * p.pitch, li[r], x, x, cshift, scv, acc0, acc1); }
+        }
+        for (int r = 0; r < R; ++r) {
+          if (!li[r].active || li[r].lB >= 0) continue;
+          NB_FOR(ctx, x, h) if (x != 0) pair(p, s + r * p.pitch, li[r], x, n - x, cshift, scv, acc0, acc1);
+        }
       } else {
         // pairs (x, n-x) for x in [0, h) (x = 0 is its own partner), then the self-paired x = h
         NB_FOR(ctx, i, R << lg_h) {
@@ -447,6 +511,11 @@ template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
 // P5 epilogues (latent space, natural layout)
 // ---------------------------------------------------------------------------------------------
 template <class T> struct EpiPlain {
+  static constexpr bool BATCHED = false;
+  struct Pre {};
+  NB_HD NB_INLINE void preload(long, long, long, int, int, Pre&) const {}
+  NB_HD NB_INLINE void gather(Pre&) const {}
+  NB_HD NB_INLINE void finish(long, long, long, int, int, T, T, T, T, const Pre&, T&) const {}
   T* out; T scale;
   T* partials;   // unused
   NB_HD NB_INLINE void prefetch(Ctx&, long, long, long, int) const {}
@@ -463,8 +532,27 @@ template <class T> struct EpiPlain {
 // out_k = A_b g_k / V (+ add_k); W[l][x] = sum over the (up to four) mirror points of xi_k g_k / V;
 // acc += add_k out_k  (the xi-block of <t, M t> for conjugate gradient)
 template <class T> struct EpiAdjoint {
+  static constexpr bool BATCHED = true;
   T* out; const T* add; const T* xi; const int* idxf; const T* amp; T* W; T invV;
   T* partials;   // [nblk]
+  // split form of emit() for a pair with distinct x != y and a partner row: preload (streaming
+  // loads + bin index), gather (amplitude table), finish (arithmetic + stores)
+  struct Pre { int b; T A, a0, a1, a2, a3, x0, x1, x2, x3; };
+  NB_HD NB_INLINE void preload(long rowA, long rowB, long fbase, int x, int y, Pre& q) const {
+    q.b = ldg(idxf + fbase + x);
+    q.a0 = q.a1 = q.a2 = q.a3 = q.x0 = q.x1 = q.x2 = q.x3 = 0;
+    if (add) { q.a0 = add[rowA + x]; q.a1 = add[rowA + y]; q.a2 = add[rowB + x]; q.a3 = add[rowB + y]; }
+    if (xi) { q.x0 = xi[rowA + x]; q.x1 = xi[rowA + y]; q.x2 = xi[rowB + x]; q.x3 = xi[rowB + y]; }
+  }
+  NB_HD NB_INLINE void gather(Pre& q) const { q.A = ldg(amp + q.b); }
+  NB_HD NB_INLINE void finish(long rowA, long rowB, long wbase, int x, int y, T gAx, T gAy, T gBx, T gBy, const Pre& q,
+                              T& acc) const {
+    gAx *= invV; gAy *= invV; gBx *= invV; gBy *= invV;
+    T o0 = q.A * gAx + q.a0, o1 = q.A * gAy + q.a1, o2 = q.A * gBx + q.a2, o3 = q.A * gBy + q.a3;
+    acc += (q.a0 * o0 + q.a1 * o1) + (q.a2 * o2 + q.a3 * o3);
+    out[rowA + x] = o0; out[rowA + y] = o1; out[rowB + x] = o2; out[rowB + y] = o3;
+    if (W) W[wbase + x] = (q.x0 * gAx + q.x1 * gAy) + (q.x2 * gBx + q.x3 * gBy);
+  }
   // all loads first (the outputs may alias the inputs as far as the compiler knows), then the stores
   NB_HD NB_INLINE void emit(long rowA, long rowB, long fbase, long wbase, int x, int y, T gAx, T gAy, T gBx, T gBy,
                             T& acc) const {
@@ -548,6 +636,48 @@ template <class T, class Epi> struct P5Body {
     fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
     if (n == 1) {
       NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], 0, 0, acc);
+    } else if (Epi::BATCHED) {
+      // hot path: pairs (x, n-x), 0 < x < h, of lines with a partner row, U pairs per batch
+      constexpr int U = 2;
+      const T sg = p.hsign;
+      const int cnt = R << lg_h, nmid = 1 << p.mg.lg_mid;
+      for (int i0 = ctx.tid; i0 < cnt; i0 += ctx.nthr * U) {
+        int px[U], py[U]; bool ok[U];
+        typename Epi::Pre pre[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          int i = i0 + u * ctx.nthr;
+          bool in = i < cnt;
+          i = in ? i : 0;
+          int r = i >> lg_h, x = i & (h - 1);
+          ok[u] = in && li[r].active && li[r].lB >= 0 && x != 0;
+          x = x != 0 ? x : 1;
+          int a = li[r].lA >> p.mg.lg_mid, km = li[r].lA & (nmid - 1);
+          long fbase = ((long)a * p.hmid1 + fold_idx(km, nmid)) * (h + 1);
+          px[u] = ldg(p.fft.pos + x); py[u] = ldg(p.fft.pos + (n - x));
+          p.epi.preload((long)li[r].lA * n, (long)(li[r].lB >= 0 ? li[r].lB : li[r].lA) * n, fbase, x, n - x, pre[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) p.epi.gather(pre[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!ok[u]) continue;
+          int i = i0 + u * ctx.nthr;
+          int r = i >> lg_h, x = i & (h - 1);
+          const cplx<T>* line = s + r * p.pitch;
+          cplx<T> cx = line[px[u]], cy = line[py[u]];
+          p.epi.finish((long)li[r].lA * n, (long)li[r].lB * n, (long)li[r].lA * (h + 1), x, n - x, cx.x + sg * cx.y, cy.x + sg * cy.y,
+                       cy.x - sg * cy.y, cx.x - sg * cx.y, pre[u], acc);
+        }
+      }
+      NB_FOR(ctx, i, 2 * R) {
+        int r = i >> 1;
+        if (li[r].active) { int x = (i & 1) ? h : 0; pair(p, s + r * p.pitch, li[r], x, x, acc); }
+      }
+      for (int r = 0; r < R; ++r) {
+        if (!li[r].active || li[r].lB >= 0) continue;
+        NB_FOR(ctx, x, h) if (x != 0) pair(p, s + r * p.pitch, li[r], x, n - x, acc);
+      }
     } else {
       NB_FOR(ctx, i, R << lg_h) {
         int r = i >> lg_h, x = i & (h - 1);
