@@ -396,7 +396,7 @@ template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
     T acc0 = 0, acc1 = 0;
     T cshift = p.op.cshift_ptr ? p.op.cshift_scale * ldg(p.op.cshift_ptr) : T(0);
     T scv = p.op.sc_ptr ? ldg(p.op.sc_ptr) : p.op.sc;
-    if (FWD && MODE == PM_METRIC) {
+    if (FWD && MODE == PM_METRIC && p.ahead > 0) {
       for (int r = 0; r < R; ++r) {
         if (!li[r].active) continue;
         prefetch_l2(ctx, p.op.jl_a + (long)li[r].lA * n, (size_t)n * sizeof(T));
@@ -622,7 +622,7 @@ template <class T, class Epi> struct P5Body {
     const int l0 = ctx.bid << p.lg_R;
     fill_line_info(ctx, li, p.mg, l0, R);
     T acc = 0;
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < R && p.ahead > 0; ++r) {
       if (!li[r].active) continue;
       const int nmid = 1 << p.mg.lg_mid;
       int a = li[r].lA >> p.mg.lg_mid, km = li[r].lA & (nmid - 1);

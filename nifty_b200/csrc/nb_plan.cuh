@@ -153,7 +153,9 @@ template <class T> std::vector<cplx<T>> make_twiddles(int n) {
   return tw;
 }
 
-inline bool prefetch_disabled() { const char* e = std::getenv("NB200_NO_PREFETCH"); return e && e[0] == '1'; }
+// L2 prefetch of later-phase / next-wave rows is OFF by default: measured on B200 it added 30-50 % DRAM
+// read traffic (lines evicted before use) for no gain (profiles/r1_notes.md); NB200_PREFETCH=1 re-enables it.
+inline bool prefetch_disabled() { const char* e = std::getenv("NB200_PREFETCH"); return !(e && e[0] == '1'); }
 
 template <class T> struct Plan : PlanBase {
   int lg0 = 0, lgm = 0, lgl = 0;
