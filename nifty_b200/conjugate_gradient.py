@@ -1,0 +1,157 @@
+"""Conjugate gradient with the call protocol of ``nifty/re/conjugate_gradient.py`` (``cg``:28-41,
+``_cg``:77-214, ``static_cg``:45-50).
+
+Two execution paths, same semantics (``info``: 0 converged, i > 0 stopped at iteration i, < 0 failed):
+
+* ``mat`` is a :class:`HamiltonianMetric` (``lh.metric(pos, .) + .`` at a fixed ``pos``, i.e. what
+  ``draw_linear_residual`` and ``newton_cg`` pass): the whole solve runs on the device through
+  ``nb200_cg_solve`` -- fused step kernels, curvature from the epilogue of the metric kernels, all
+  stopping rules evaluated on the GPU, the host polls a status word every few iterations.  This is
+  the B200 counterpart of ``static_cg`` (``lax.while_loop``).
+* any other callable: the generic host loop below (one host sync per scalar, like ``_cg``); used for
+  the sample-averaged KL metric, whose operator spans several linearisations / ranks.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+N_RESET = 20  # conjugate_gradient.py:17
+
+
+class CGResults(NamedTuple):
+    x: torch.Tensor
+    nit: int
+    nfev: int
+    info: int
+    success: bool
+
+
+class HamiltonianMetric:
+    """``t -> lh.metric(pos, t) + t`` bound to a cached linearisation (evi.py:83-85 ``_ham_metric``).
+
+    ``other`` (a second linearisation) selects the geoVI operator of evi.py:167-172."""
+
+    def __init__(self, lin, other=None):
+        self.lin, self.other = lin, other
+
+    def __call__(self, t: torch.Tensor) -> torch.Tensor:
+        if self.other is None:
+            return self.lin.metric(t, add_identity=True)
+        tm = self.other.metric_pair(self.lin, t, add_identity=True)
+        return self.lin.metric_pair(self.other, tm, add_identity=True)
+
+
+def _norm(v: torch.Tensor, ord) -> float:
+    if ord == 1:
+        return float(v.abs().sum())
+    if ord == 2:
+        return float(torch.linalg.vector_norm(v))
+    if ord in (np.inf, float("inf")):
+        return float(v.abs().max())
+    return float(torch.linalg.vector_norm(v, ord=ord))
+
+
+def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, absdelta=None, resnorm=None,
+        norm_ord=None, tol=1e-5, atol=0.0, miniter=None, maxiter=None, name=None, time_threshold=None,
+        _raise_nonposdef=True, check_every=4) -> CGResults:
+    norm_ord = 2 if norm_ord is None else norm_ord
+    if isinstance(mat, HamiltonianMetric):
+        x, res = mat.lin.cg_solve(j, x0, other=mat.other, absdelta=absdelta, resnorm=resnorm, norm_ord=norm_ord, tol=tol,
+                                  atol=atol, miniter=miniter, maxiter=maxiter, raise_nonposdef=_raise_nonposdef,
+                                  check_every=check_every)
+        nm = "CG" if name is None else name
+        if res.error == 1:
+            raise ValueError(f"{nm}: zero curvature")
+        if res.error == 2:
+            raise ValueError(f"{nm}: negative curvature")
+        if res.error == 3:
+            raise ValueError(f"{nm}: WARNING: energy increased")
+        return CGResults(x, int(res.nit), int(res.nfev), int(res.info), res.info == 0)
+
+    # generic host loop, statement by statement the recurrence of conjugate_gradient.py:107-214
+    maxiter_fallback = 20 * j.numel()
+    if miniter is None:
+        miniter = min(6, maxiter if maxiter is not None else maxiter_fallback)
+    if maxiter is None:
+        maxiter = max(min(200, maxiter_fallback), miniter)
+    if absdelta is None and resnorm is None:
+        resnorm = max(tol * _norm(j, norm_ord), atol)
+    fi = torch.finfo(j.dtype)
+    eps, tiny = 6.0 * fi.eps, 6.0 * fi.tiny
+    nm = "CG" if name is None else name
+    if x0 is None:
+        pos = torch.zeros_like(j)
+        r = -j
+        d = r.clone()
+        energy, nfev = 0.0, 0
+    else:
+        pos = x0.clone()
+        r = mat(pos) - j
+        d = r.clone()
+        energy = float(torch.dot((r - j) / 2, pos))
+        nfev = 1
+    previous_gamma = float(torch.dot(r, r))
+    if previous_gamma == 0:
+        return CGResults(pos, 0, nfev, 0, True)
+    info, i = -1, 0
+    for i in range(1, maxiter + 1):
+        q = mat(d)
+        nfev += 1
+        curv = float(torch.dot(d, q))
+        if curv == 0.0:
+            if _raise_nonposdef:
+                raise ValueError(f"{nm}: zero curvature")
+            info = 0
+            break
+        if curv < 0.0:
+            if _raise_nonposdef:
+                raise ValueError(f"{nm}: negative curvature")
+            if i == 1:
+                pos = previous_gamma / (-curv) * (-j)
+            info = 0
+            break
+        alpha = previous_gamma / curv
+        pos = pos - alpha * d
+        if i % N_RESET == 0:
+            r = mat(pos) - j
+            nfev += 1
+        else:
+            r = r - q * alpha
+        gamma = float(torch.dot(r, r))
+        if 0.0 <= gamma <= tiny:
+            info = 0
+            break
+        if resnorm is not None and _norm(r, norm_ord) < resnorm and i >= miniter:
+            info = 0
+            break
+        new_energy = float(torch.dot((r - j) / 2, pos))
+        energy_diff = energy - new_energy
+        if energy_diff < -eps * abs(new_energy):
+            if _raise_nonposdef:
+                raise ValueError(f"{nm}: WARNING: energy increased")
+            info = i
+            break
+        if absdelta is not None and energy_diff < absdelta and i >= miniter:
+            info = 0
+            break
+        energy = new_energy
+        d = d * max(0.0, gamma / previous_gamma) + r
+        previous_gamma = gamma
+    info = i if info == -1 else info
+    return CGResults(pos, i, nfev, info, info == 0)
+
+
+def cg(mat, j, x0=None, *args, **kwargs):
+    """``jft.cg``: returns ``(x, info)`` (conjugate_gradient.py:28-41)."""
+    res = _cg(mat, j, x0, *args, **kwargs)
+    return res.x, res.info
+
+
+def static_cg(mat, j, x0=None, *args, **kwargs):
+    """``jft.static_cg``: same contract; with a :class:`HamiltonianMetric` the loop already runs on the device."""
+    res = _cg(mat, j, x0, *args, **kwargs)
+    return res.x, res.info

@@ -1,0 +1,196 @@
+"""MGVI / geoVI sampling with the call protocol of ``nifty/re/evi.py``.
+
+``draw_linear_residual`` (:88-150), ``nonlinearly_update_residual`` (:181-255), ``draw_residual``
+(:258-297) and the ``Samples`` container (:300-396) on flat device vectors.  Every arithmetic step
+on the latent / data space runs in libniftyb200.so; Python only sequences the calls.
+
+PRNG keys: the reference splits ``jax.random`` keys (evi.py:121-123); JAX is not available here, so
+a key is a ``numpy.random.SeedSequence`` (or an int) and ``random_split`` mirrors ``random.split``.
+The white-noise draws happen *outside* the boundary exactly as in the reference, so a caller who
+has the reference's draws can pass them in through ``_white=(data_shaped, latent_shaped)``.
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import conjugate_gradient
+from .conjugate_gradient import HamiltonianMetric
+from .likelihood import LikelihoodWithModel
+from .optimize import OptimizeResults, _newton_cg
+
+
+# ---- keys ----------------------------------------------------------------------------------------
+def as_key(key):
+    return key if isinstance(key, np.random.SeedSequence) else np.random.SeedSequence(int(key))
+
+
+def random_split(key, n: int = 2):
+    """``jax.random.split`` stand-in: n statistically independent child keys, reproducible."""
+    key = as_key(key)
+    return [np.random.SeedSequence(entropy=key.entropy, spawn_key=tuple(key.spawn_key) + (i,)) for i in range(n)]
+
+
+def _seed_of(key) -> int:
+    return int(as_key(key).generate_state(2, dtype=np.uint32).astype(np.uint64) @ np.array([1, 2**32], dtype=np.uint64) % (2**63 - 1))
+
+
+def random_normal(key, shape, dtype, device) -> torch.Tensor:
+    gen = torch.Generator(device=device)
+    gen.manual_seed(_seed_of(key))
+    return torch.randn(shape, dtype=dtype, device=device, generator=gen)
+
+
+def random_like(key, lh: LikelihoodWithModel) -> torch.Tensor:
+    """``jft.random_like(key, pos)``: standard-normal latent vector (tree_math/forest_math.py:60-72)."""
+    return random_normal(key, (lh.layout.size,), lh.dtype, lh.rt.device)
+
+
+# ---- Samples -------------------------------------------------------------------------------------------
+class Samples:
+    """Residual samples around an expansion point (evi.py:300-396): ``samples = pos + residuals``."""
+
+    def __init__(self, *, pos: Optional[torch.Tensor], samples: Optional[torch.Tensor], keys=None):
+        self._pos, self._samples, self._keys = pos, samples, keys
+
+    @property
+    def pos(self):
+        return self._pos
+
+    @property
+    def keys(self):
+        return self._keys
+
+    @property
+    def samples(self):
+        """pos + residuals, leading sample axis (evi.py:334-343)."""
+        if self._samples is None:
+            raise ValueError(f"{self.__class__.__name__} has no samples")
+        return self._samples if self._pos is None else self._pos[None] + self._samples
+
+    @property
+    def residuals(self):
+        return self._samples
+
+    def __len__(self):
+        return 0 if self._samples is None else int(self._samples.shape[0])
+
+    def __getitem__(self, i):
+        r = self._samples[i]
+        return r if self._pos is None else self._pos + r
+
+    def at(self, pos, old_pos=None):
+        """Same residuals around a new expansion point (evi.py:360-372)."""
+        return Samples(pos=pos, samples=self._samples, keys=self._keys)
+
+    def squeeze(self):
+        return Samples(pos=self._pos, samples=None if self._samples is None else self._samples.reshape((-1,) + tuple(self._samples.shape[2:])), keys=self._keys)
+
+
+def concatenate_zip(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Interleave along the sample axis: [a0, b0, a1, b1, ...] (evi.py:53-57)."""
+    return torch.stack((a, b), dim=1).reshape((-1,) + tuple(a.shape[1:]))
+
+
+# ---- MGVI -------------------------------------------------------------------------------------------------
+def sample_likelihood(likelihood: LikelihoodWithModel, primals, key, _white_data=None):
+    """evi.py:77-80: ``left_sqrt_metric(primals, N(0,1)[data shape])``."""
+    lin, _ = likelihood.lin_at(primals)
+    white = _white_data if _white_data is not None else random_normal(key, likelihood.signal.target_shape, likelihood.dtype,
+                                                                    likelihood.rt.device)
+    return lin.lsm(white, scaled=True)
+
+
+def draw_linear_residual(likelihood: LikelihoodWithModel, pos, key, *, from_inverse: bool = True, point_estimates=(),
+                         cg=conjugate_gradient.cg, cg_name=None, cg_kwargs: Optional[dict] = None,
+                         _raise_nonposdef: bool = False, _white=None):
+    """One MGVI residual sample at ``pos`` (evi.py:88-150); returns ``(residual, info)``."""
+    if point_estimates:
+        raise NotImplementedError("point_estimates are not supported on the B200 path yet")
+    pos = likelihood.signal.as_flat(pos)
+    lin, _ = likelihood.lin_at(pos)
+    k_nll, k_prr = random_split(key, 2)
+    w_data, w_prior = (None, None) if _white is None else _white
+    nll_smpl = sample_likelihood(likelihood, pos, k_nll, _white_data=w_data)
+    prr_smpl = random_like(k_prr, likelihood) if w_prior is None else likelihood.signal.as_flat(w_prior)
+    smpl = nll_smpl + prr_smpl
+    info = 0
+    if from_inverse:
+        smpl, info = cg(HamiltonianMetric(lin), smpl, x0=prr_smpl, name=cg_name, _raise_nonposdef=_raise_nonposdef,
+                        **(cg_kwargs or {}))
+        if info is not None and info < 0:
+            raise ValueError("conjugate gradient failed")
+    return smpl, info
+
+
+# ---- geoVI --------------------------------------------------------------------------------------------------
+def nonlinearly_update_residual(likelihood: LikelihoodWithModel, pos, residual_sample, metric_sample_key,
+                                metric_sample_sign=1.0, *, point_estimates=(), minimize=_newton_cg,
+                                minimize_kwargs: Optional[dict] = None, _raise_notconverged: bool = False, _white=None):
+    """geoVI update of one residual sample (evi.py:181-255); returns ``(residual, OptimizeResults|None)``."""
+    if point_estimates:
+        raise NotImplementedError("point_estimates are not supported on the B200 path yet")
+    e = likelihood.signal.as_flat(pos)
+    sample = e + likelihood.signal.as_flat(residual_sample)
+    ms, _ = draw_linear_residual(likelihood, e, metric_sample_key, from_inverse=False, _white=_white)
+    ms = metric_sample_sign * ms
+    mk = dict(minimize_kwargs or {})
+    if isinstance(mk.get("maxiter", None), int) and mk["maxiter"] == 0:
+        return sample - e, None
+    lin_e = likelihood.new_lin()
+    lin_e.update(e)
+    trafo_at_p = lin_e.transformation()
+    lin_x = likelihood.new_lin()
+
+    def residual_vg(x):  # evi.py:153-164
+        lin_x.update(x)
+        t = lin_x.transformation() - trafo_at_p
+        g = x - e + lin_e.lsm(t, scaled=True)
+        r = ms - g
+        val = 0.5 * float(torch.dot(r, r))
+        ngrad = r + lin_x.lsm(lin_e.rsm(r, scaled=True), scaled=True)
+        return val, -ngrad
+
+    def metric_at(x):  # evi.py:167-172 at the point of the last residual_vg evaluation (== x)
+        return HamiltonianMetric(lin_x, other=lin_e)
+
+    def sampnorm(natgrad):  # evi.py:175-178
+        fpp = lin_e.rsm(natgrad, scaled=True)
+        return float(torch.sqrt(torch.dot(natgrad, natgrad) + (fpp * fpp).sum()))
+
+    # Newton-CG evaluates hessp at `pos` right after fun_and_grad(pos) accepted it, so lin_x is current;
+    # after a rejected line-search trial it is re-linearised by the wrapper below.
+    state = {"x": None}
+
+    def fg(x):
+        state["x"] = x
+        return residual_vg(x)
+
+    def op_at(x):
+        if state["x"] is None or state["x"].data_ptr() != x.data_ptr():
+            lin_x.update(x)
+            state["x"] = x
+        return metric_at(x)
+
+    opt = minimize(None, x0=sample, fun_and_grad=fg, hessp_at=op_at, custom_gradnorm=sampnorm, **mk)
+    if _raise_notconverged and (opt.status is None or opt.status < 0):
+        raise ValueError("S: failed to invert map")
+    return opt.x - e, opt
+
+
+def draw_residual(likelihood: LikelihoodWithModel, pos, key, *, point_estimates=(), cg=conjugate_gradient.cg, cg_name=None,
+                  cg_kwargs=None, minimize=_newton_cg, minimize_kwargs=None, _raise_nonposdef=False, _raise_notconverged=False):
+    """Antithetic pair of (optionally non-linearly updated) residuals for one key (evi.py:258-297)."""
+    residual, _ = draw_linear_residual(likelihood, pos, key, point_estimates=point_estimates, cg=cg, cg_name=cg_name,
+                                       cg_kwargs=cg_kwargs, _raise_nonposdef=_raise_nonposdef)
+    out, states = [], []
+    for sign in (1.0, -1.0):
+        r, st = nonlinearly_update_residual(likelihood, pos, sign * residual, key, sign, point_estimates=point_estimates,
+                                            minimize=minimize, minimize_kwargs=minimize_kwargs,
+                                            _raise_notconverged=_raise_notconverged)
+        out.append(r)
+        states.append(st)
+    return torch.stack(out), states

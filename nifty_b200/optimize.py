@@ -1,0 +1,105 @@
+"""Newton-CG with the call protocol of ``nifty/re/optimize.py`` (``_newton_cg``:271-411,
+``_line_search_successive_halving``:583-654, ``OptimizeResults``:31-72) on flat device vectors."""
+
+from __future__ import annotations
+
+from typing import Callable, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from .conjugate_gradient import _cg, _norm
+
+
+class OptimizeResults(NamedTuple):
+    x: torch.Tensor
+    success: bool
+    status: int
+    fun: float
+    jac: torch.Tensor
+    nit: int
+    nfev: int
+    njev: int
+    nhev: int
+
+
+def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reduction_factor=0.1, old_fval=None, absdelta=None,
+               norm_ord=None, xtol=1e-5, fun_and_grad: Optional[Callable] = None, hessp: Optional[Callable] = None,
+               cg=_cg, name=None, time_threshold=None, cg_kwargs=None, custom_gradnorm: Optional[Callable] = None,
+               hessp_at: Optional[Callable] = None) -> OptimizeResults:
+    """``hessp(pos, v)`` as in the reference; ``hessp_at(pos)`` may instead return an operator object
+    (e.g. a :class:`~nifty_b200.conjugate_gradient.HamiltonianMetric`) so that the inner CG runs on the device."""
+    norm_ord = 1 if norm_ord is None else norm_ord
+    miniter = 0 if miniter is None else miniter
+    maxiter = 200 if maxiter is None else maxiter
+    pos = x0.clone()
+    xtol = xtol * pos.numel()
+    cg_kwargs = {} if cg_kwargs is None else dict(cg_kwargs)
+    cg_name = cg_kwargs.pop("name", None)
+    gradnorm = (lambda v: _norm(v, norm_ord)) if custom_gradnorm is None else custom_gradnorm
+    if fun_and_grad is None:
+        raise ValueError("`fun_and_grad` is required on the B200 path (no automatic differentiation)")
+    energy, g = fun_and_grad(pos)
+    nfev, njev, nhev = 1, 1, 0
+    if np.isnan(energy):
+        raise ValueError("energy is Nan")
+    status, i = -1, 0
+    for i in range(1, maxiter + 1):
+        if old_fval and energy_reduction_factor:
+            cg_absdelta = energy_reduction_factor * (old_fval - energy)
+        else:
+            cg_absdelta = None if absdelta is None else absdelta / 100.0
+        mag_g = _norm(g, cg_kwargs.get("norm_ord", 1))
+        cg_resnorm = min(0.5, np.sqrt(mag_g)) * mag_g
+        kw = dict(absdelta=cg_absdelta, resnorm=cg_resnorm, norm_ord=1, name=cg_name, _raise_nonposdef=False)
+        kw.update(cg_kwargs)
+        op = hessp_at(pos) if hessp_at is not None else (lambda v, _p=pos: hessp(_p, v))
+        res = cg(op, g, **kw)
+        nat_g, info = res.x, res.info
+        nhev += res.nfev
+        if info is not None and info < 0:
+            raise ValueError("conjugate gradient failed")
+        dd, grad_scaling, accepted = nat_g, 1.0, False
+        ls_it = 0
+        for ls_it in range(9):
+            new_pos = pos - grad_scaling * dd
+            new_energy, new_g = fun_and_grad(new_pos)
+            nfev, njev = nfev + 1, njev + 1
+            if new_energy <= energy:
+                accepted = True
+                break
+            grad_scaling /= 2
+            if ls_it == 5:
+                gam = float(torch.dot(g, g))
+                hv = hessp_at(pos)(g) if hessp_at is not None else hessp(pos, g)   # re-linearise at pos
+                curv = float(torch.dot(g, hv))
+                nhev += 1
+                grad_scaling = 1.0
+                dd = gam / curv * g
+        if not accepted:
+            status = -1
+            break
+        energy_diff = energy - new_energy
+        old_fval = energy
+        energy, pos, g = new_energy, new_pos, new_g
+        descent_norm = grad_scaling * gradnorm(dd)
+        if np.isnan(new_energy):
+            raise ValueError("energy is NaN")
+        min_cond = ls_it < 2 and i > miniter
+        if absdelta is not None and 0.0 <= energy_diff < absdelta and min_cond:
+            status = 0
+            break
+        if descent_norm <= xtol and i > miniter:
+            status = 0
+            break
+    else:
+        status = i
+    return OptimizeResults(pos, True, status, float(energy), g, i, nfev, njev, nhev)
+
+
+def newton_cg(*args, **kwargs):
+    """``jft.newton_cg``: returns only the optimal position."""
+    return _newton_cg(*args, **kwargs).x
+
+
+static_newton_cg = newton_cg

@@ -1,0 +1,272 @@
+"""``OptimizeVI`` / ``optimize_kl`` with the call protocol of ``nifty/re/optimize_kl.py``.
+
+* ``_kl_vg`` (:90-114) / ``_kl_met`` (:117-144): sample-averaged value+gradient and metric of the
+  standard Hamiltonian (:67-87).  One linearisation per sample point is cached for the whole
+  Newton step, so every KL-CG iteration is ``2*n_samples`` fused metric products.
+* sample sharding (:317-320, :397-476): instead of a JAX device mesh, the independent sample solves
+  are distributed over the ranks of a ``torch.distributed`` process group (one process per GPU, NCCL
+  over NVLink on a B200 box, gloo in the CPU tests).  ``pos`` is replicated, rank r draws the keys
+  ``r, r+W, r+2W, ...``; the KL value / gradient / metric-vector products are summed with one
+  all-reduce each (the only collective of the path) and divided by the global count.
+* checkpoint / resume: ``last.pkl`` with ``(Samples, OptimizeVIState)`` after every iteration
+  (:871-875, :835-839), written by rank 0 with every rank's residuals gathered.
+"""
+
+from __future__ import annotations
+
+import os
+import pickle
+from typing import Callable, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from .conjugate_gradient import HamiltonianMetric, _cg
+from .evi import Samples, as_key, concatenate_zip, draw_linear_residual, nonlinearly_update_residual, random_split
+from .likelihood import LikelihoodWithModel
+from .optimize import OptimizeResults, _newton_cg
+
+SAMPLE_MODES = ("linear_sample", "linear_resample", "nonlinear_sample", "nonlinear_resample", "nonlinear_update")
+
+
+class OptimizeVIState(NamedTuple):
+    nit: int
+    key: object
+    sample_state: object = None
+    minimization_state: object = None
+    config: dict = {}
+
+
+def _getitem_at_nit(config, key, nit):
+    """Most kwargs may be callables of the iteration index (optimize_kl.py:166-170)."""
+    c = config[key]
+    return c(nit) if callable(c) and not isinstance(c, (dict,)) else c
+
+
+class _Comm:
+    """Thin view of a torch.distributed process group (None = single process)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        if group is None or not dist.is_available() or not dist.is_initialized():
+            self.group, self.rank, self.world = None, 0, 1
+        else:
+            self.group = None if group is True else group
+            self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+
+    def allreduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def allgather(self, t: torch.Tensor):
+        if self.world == 1:
+            return [t]
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t.contiguous(), group=self.group)
+        return out
+
+
+class OptimizeVI:
+    """State-less MGVI / geoVI driver (optimize_kl.py:173-741)."""
+
+    def __init__(self, likelihood: LikelihoodWithModel, n_total_iterations: int, *, comm=None,
+                 _kl_value_and_grad: Optional[Callable] = None, _kl_metric: Optional[Callable] = None,
+                 _draw_linear_residual: Callable = draw_linear_residual,
+                 _nonlinearly_update_residual: Callable = nonlinearly_update_residual):
+        self.likelihood = likelihood
+        self.n_total_iterations = n_total_iterations
+        self.comm = _Comm(comm)
+        self._draw_linear_residual = _draw_linear_residual
+        self._nonlinearly_update_residual = _nonlinearly_update_residual
+        self._kl_vg_override, self._kl_met_override = _kl_value_and_grad, _kl_metric
+        self._lins = []      # one linearisation per local sample point, reused across KL evaluations
+
+    # -- sample bookkeeping -----------------------------------------------------------------------
+    def _local_keys(self, keys):
+        return keys[self.comm.rank::self.comm.world]
+
+    def _n_global(self, n_local_points):
+        t = torch.tensor([float(n_local_points)], dtype=torch.float64, device=self.likelihood.rt.device)
+        return int(round(float(self.comm.allreduce_sum(t))))
+
+    # -- sampling ------------------------------------------------------------------------------------
+    def draw_linear_samples(self, primals, keys, **kwargs):
+        """optimize_kl.py:391-444: local keys only; mirrored pairs interleaved [s0, -s0, s1, -s1, ...]."""
+        res, infos = [], []
+        for k in self._local_keys(keys):
+            r, info = self._draw_linear_residual(self.likelihood, primals, k, **kwargs)
+            res.append(r)
+            infos.append(info)
+        L = self.likelihood.layout.size
+        smpls = torch.stack(res) if res else torch.empty((0, L), dtype=self.likelihood.dtype, device=self.likelihood.rt.device)
+        smpls = concatenate_zip(smpls, -smpls)
+        return Samples(pos=primals, samples=smpls, keys=keys), infos
+
+    def nonlinearly_update_samples(self, samples: Samples, **kwargs):
+        """optimize_kl.py:446-476: the same key for both signs, metric_sample_sign = +1 / -1."""
+        local = self._local_keys(samples.keys)
+        assert len(samples) == 2 * len(local)
+        out, states = [], []
+        for i, k in enumerate(local):
+            for s, sign in enumerate((1.0, -1.0)):
+                r, st = self._nonlinearly_update_residual(self.likelihood, samples.pos, samples.residuals[2 * i + s], k, sign, **kwargs)
+                out.append(r)
+                states.append(st)
+        smpls = torch.stack(out) if out else samples.residuals
+        return Samples(pos=samples.pos, samples=smpls, keys=samples.keys), states
+
+    def draw_samples(self, samples: Samples, *, key, sample_mode: str, n_samples: int, point_estimates=(),
+                     draw_linear_kwargs=None, nonlinearly_update_kwargs=None, **kwargs):
+        """State machine of optimize_kl.py:478-538."""
+        if sample_mode not in SAMPLE_MODES:
+            raise ValueError(f"`sample_mode` must be one of {SAMPLE_MODES}; got {sample_mode!r}")
+        draw_linear_kwargs = dict(draw_linear_kwargs or {})
+        nonlinearly_update_kwargs = dict(nonlinearly_update_kwargs or {})
+        st_smpls = None
+        n_keys = 0 if samples.keys is None else len(samples.keys)
+        if n_samples != n_keys and sample_mode.lower() == "nonlinear_update":
+            sample_mode = "nonlinear_resample"       # :490-497
+        elif n_samples != n_keys and sample_mode.lower().endswith("_sample"):
+            sample_mode = sample_mode.replace("_sample", "_resample")
+        if n_samples == 0:
+            return Samples(pos=samples.pos, samples=None, keys=None), None
+        if sample_mode.lower() in ("linear_resample", "nonlinear_resample"):
+            k_smpls = random_split(key, n_samples)       # :507
+            samples, st_smpls = self.draw_linear_samples(samples.pos, k_smpls, point_estimates=point_estimates, **draw_linear_kwargs)
+            if sample_mode.lower() == "nonlinear_resample":
+                samples, st_smpls = self.nonlinearly_update_samples(samples, point_estimates=point_estimates, **nonlinearly_update_kwargs)
+        elif sample_mode.lower() in ("linear_sample", "nonlinear_sample"):
+            samples, st_smpls = self.draw_linear_samples(samples.pos, samples.keys, point_estimates=point_estimates, **draw_linear_kwargs)
+            if sample_mode.lower() == "nonlinear_sample":
+                samples, st_smpls = self.nonlinearly_update_samples(samples, point_estimates=point_estimates, **nonlinearly_update_kwargs)
+        else:   # nonlinear_update
+            samples, st_smpls = self.nonlinearly_update_samples(samples, point_estimates=point_estimates, **nonlinearly_update_kwargs)
+        return samples, st_smpls
+
+    # -- KL ----------------------------------------------------------------------------------------------
+    def _ensure_lins(self, n):
+        while len(self._lins) < n:
+            self._lins.append(self.likelihood.new_lin())
+
+    def kl_value_and_grad(self, pos: torch.Tensor, residuals: Optional[torch.Tensor]):
+        """``_kl_vg``: mean over all sample points of value_and_grad of the Hamiltonian; also
+        (re)linearises the cached per-sample linearisations used by :meth:`kl_metric`."""
+        lh = self.likelihood
+        pts = [pos] if residuals is None or (len(residuals) == 0 and self.comm.world == 1) else [pos + r for r in residuals]
+        if residuals is not None and len(residuals) == 0 and self.comm.world > 1:
+            pts = []
+        self._ensure_lins(len(pts))
+        acc = torch.zeros(lh.layout.size + 2, dtype=torch.float64, device=lh.rt.device)
+        for lin, x in zip(self._lins, pts):
+            g = lin.update(x, want_grad=True, add_prior=True)
+            acc[2:] += g.to(torch.float64)
+            acc[0] += lin.energy() + 0.5 * float(torch.dot(x, x))
+            acc[1] += 1.0
+        self._n_active = len(pts)
+        acc = self.comm.allreduce_sum(acc)
+        n = float(acc[1])
+        return float(acc[0]) / n, (acc[2:] / n).to(lh.dtype)
+
+    def kl_metric(self, tangents: torch.Tensor) -> torch.Tensor:
+        """``_kl_met`` at the points of the last :meth:`kl_value_and_grad`: mean of metric(x_i, t) + t."""
+        lh = self.likelihood
+        acc = torch.zeros(lh.layout.size + 1, dtype=torch.float64, device=lh.rt.device)
+        for lin in self._lins[:self._n_active]:
+            acc[1:] += lin.metric(tangents, add_identity=True).to(torch.float64)
+            acc[0] += 1.0
+        acc = self.comm.allreduce_sum(acc)
+        return (acc[1:] / float(acc[0])).to(lh.dtype)
+
+    def kl_minimize(self, samples: Samples, minimize: Callable = _newton_cg, minimize_kwargs=None, **kwargs) -> OptimizeResults:
+        """optimize_kl.py:540-591."""
+        res = samples.residuals
+        state = {"x": None}
+
+        def fg(x):
+            state["x"] = x
+            return self.kl_value_and_grad(x, res)
+
+        def hessp(x, t):
+            if state["x"] is None or state["x"].data_ptr() != x.data_ptr():
+                fg(x)
+            return self.kl_metric(t)
+
+        return minimize(None, x0=samples.pos, fun_and_grad=fg, hessp=hessp, **(minimize_kwargs or {}))
+
+    # -- driver -------------------------------------------------------------------------------------------
+    def init_state(self, key, *, n_samples, draw_linear_kwargs=None, nonlinearly_update_kwargs=None, kl_kwargs=None,
+                   sample_mode="nonlinear_resample", point_estimates=(), constants=()) -> OptimizeVIState:
+        if constants or point_estimates:
+            raise NotImplementedError("constants / point_estimates are not supported on the B200 path yet")
+        config = dict(n_samples=n_samples, sample_mode=sample_mode, point_estimates=point_estimates, constants=constants,
+                      draw_linear_kwargs=draw_linear_kwargs or dict(cg_name="SL", cg_kwargs=dict()),
+                      nonlinearly_update_kwargs=nonlinearly_update_kwargs or dict(minimize_kwargs=dict(name="SN", cg_kwargs=dict(name="SNCG"))),
+                      kl_kwargs=kl_kwargs or dict(minimize_kwargs=dict(name="M", cg_kwargs=dict(name="MCG"))))
+        return OptimizeVIState(0, as_key(key), None, None, config)
+
+    def update(self, samples: Samples, state: OptimizeVIState, **kwargs):
+        """One VI iteration (optimize_kl.py:672-729)."""
+        nit = state.nit + 1
+        cfg = state.config
+        key, sk = random_split(state.key, 2)           # :703, ticks every iteration
+        kw = {k: _getitem_at_nit(cfg, k, nit) for k in ("n_samples", "sample_mode", "point_estimates", "draw_linear_kwargs",
+                                                      "nonlinearly_update_kwargs", "kl_kwargs")}
+        kl_kwargs = dict(kw.pop("kl_kwargs"))
+        samples, st_smpls = self.draw_samples(samples, key=sk, **kw)
+        kl_opt = self.kl_minimize(samples, **kl_kwargs)
+        samples = samples.at(kl_opt.x)
+        state = state._replace(nit=nit, key=key, sample_state=st_smpls, minimization_state=kl_opt._replace(x=None, jac=None))
+        return samples, state
+
+    def run(self, samples: Samples, *, key, **kwargs):
+        state = self.init_state(key, **kwargs)
+        for _ in range(self.n_total_iterations):
+            samples, state = self.update(samples, state)
+        return samples, state
+
+
+def optimize_kl(likelihood: LikelihoodWithModel, position_or_samples, *, key, n_total_iterations: int, n_samples,
+                point_estimates=(), constants=(), draw_linear_kwargs=None, nonlinearly_update_kwargs=None, kl_kwargs=None,
+                sample_mode="nonlinear_resample", resume=False, callback: Optional[Callable] = None, odir: Optional[str] = None,
+                comm=None, _optimize_vi=None, _optimize_vi_state=None):
+    """``jft.optimize_kl`` (optimize_kl.py:744-879): returns ``(Samples, OptimizeVIState)``."""
+    opt_vi = _optimize_vi if _optimize_vi is not None else OptimizeVI(likelihood, n_total_iterations, comm=comm)
+    rank = opt_vi.comm.rank
+    last_fn = os.path.join(odir, "last.pkl") if odir is not None else None
+    samples = None
+    state = _optimize_vi_state
+    if resume and last_fn is not None and os.path.isfile(last_fn):
+        with open(last_fn, "rb") as f:
+            s_pos, s_res_all, s_keys, st = pickle.load(f)
+        dev, dt = likelihood.rt.device, likelihood.dtype
+        pos = torch.as_tensor(s_pos, dtype=dt, device=dev)
+        res = None
+        if s_res_all is not None:
+            res = torch.as_tensor(s_res_all[rank], dtype=dt, device=dev)
+        samples = Samples(pos=pos, samples=res, keys=s_keys)
+        state = st._replace(config=None)
+    if samples is None:
+        if isinstance(position_or_samples, Samples):
+            samples = position_or_samples
+        else:
+            samples = Samples(pos=likelihood.signal.as_flat(position_or_samples), samples=None, keys=None)
+    fresh = opt_vi.init_state(key, n_samples=n_samples, draw_linear_kwargs=draw_linear_kwargs,
+                              nonlinearly_update_kwargs=nonlinearly_update_kwargs, kl_kwargs=kl_kwargs, sample_mode=sample_mode,
+                              point_estimates=point_estimates, constants=constants)
+    state = fresh if state is None else state._replace(config=fresh.config)
+    if odir is not None and rank == 0:
+        os.makedirs(odir, exist_ok=True)
+    for _ in range(state.nit, n_total_iterations):
+        samples, state = opt_vi.update(samples, state)
+        if last_fn is not None:
+            gathered = None
+            if samples.residuals is not None:
+                gathered = [t.cpu().numpy() for t in opt_vi.comm.allgather(samples.residuals)]
+            if rank == 0:
+                with open(last_fn, "wb") as f:   # config is not pickled (callables), as in the reference (:871-875)
+                    pickle.dump((samples.pos.cpu().numpy(), gathered, samples.keys, state._replace(config={})), f)
+        if callback is not None:
+            callback(samples, state)
+    return samples, state

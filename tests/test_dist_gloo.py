@@ -1,0 +1,80 @@
+"""Multi-process path on CPU: world_size-2 gloo, emulator runtime.  The sample-sharded driver must
+give the same KL value / gradient / metric and the same set of samples as a single process."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, outdir):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import nifty_b200 as nb
+    from nifty_b200._capi import CApi
+    from emu.build_emu import build
+    import vi_checks as vc
+    rt = nb.Runtime(CApi(build()), "cpu")
+    c, g, lh, olh, lay = vc._setup(rt, "g2d_16x16")
+    pos = 0.1 * lh.layout.random(7, torch.float64, rt.device)
+    vi = nb.OptimizeVI(lh, 1, comm=True)
+    keys = nb.random_split(123, 4)
+    samples, infos = vi.draw_linear_samples(pos, keys, cg_kwargs=dict(absdelta=1e-8, maxiter=60))
+    v, gr = vi.kl_value_and_grad(pos, samples.residuals)
+    t = lh.layout.random(9, torch.float64, rt.device)
+    m = vi.kl_metric(t)
+    # one full (sharded) optimize_kl iteration incl. checkpoint gather
+    s2, st = nb.optimize_kl(lh, pos, key=5, n_total_iterations=1, n_samples=2, odir=os.path.join(outdir, "ckpt"), comm=True,
+                            sample_mode="linear_resample", draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=60)),
+                            kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=30))))
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), res=samples.residuals.numpy(), v=v, g=gr.numpy(), m=m.numpy(),
+             pos2=s2.pos.numpy(), nloc=len(samples))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sample_sharding_matches_single_process(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / f"rank{i}.npz") for i in range(world)]
+    # single-process reference in this process
+    sys.path.insert(0, HERE)
+    import nifty_b200 as nb
+    from nifty_b200._capi import CApi
+    from emu.build_emu import build
+    import vi_checks as vc
+    rt = nb.Runtime(CApi(build()), "cpu")
+    c, g, lh, olh, lay = vc._setup(rt, "g2d_16x16")
+    pos = 0.1 * lh.layout.random(7, torch.float64, rt.device)
+    vi = nb.OptimizeVI(lh, 1)
+    keys = nb.random_split(123, 4)
+    samples, _ = vi.draw_linear_samples(pos, keys, cg_kwargs=dict(absdelta=1e-8, maxiter=60))
+    v, gr = vi.kl_value_and_grad(pos, samples.residuals)
+    m = vi.kl_metric(lh.layout.random(9, torch.float64, rt.device))
+    assert r[0]["nloc"] == 4 and r[1]["nloc"] == 4            # 2 keys x mirrored pair per rank
+    # rank r holds keys r, r+2 -> global order [k0, k1, k2, k3] = [r0[0:2], r1[0:2], r0[2:4], r1[2:4]]
+    glob = np.concatenate([r[0]["res"][0:2], r[1]["res"][0:2], r[0]["res"][2:4], r[1]["res"][2:4]])
+    np.testing.assert_allclose(glob, samples.residuals.numpy(), rtol=0, atol=1e-13)
+    for i in range(world):
+        assert abs(r[i]["v"] - v) <= 1e-12 * abs(v)
+        np.testing.assert_allclose(r[i]["g"], gr.numpy(), rtol=0, atol=1e-12 * np.abs(gr.numpy()).max())
+        np.testing.assert_allclose(r[i]["m"], m.numpy(), rtol=0, atol=1e-12 * np.abs(m.numpy()).max())
+    np.testing.assert_array_equal(r[0]["pos2"], r[1]["pos2"])   # replicated position stays bit-identical across ranks
+    assert os.path.isfile(tmp_path / "ckpt" / "last.pkl")

@@ -1,0 +1,29 @@
+"""CPU tier: MGVI / geoVI host drivers on the host emulation of the kernels, against the oracle."""
+import pytest
+
+import nifty_b200 as nb
+import vi_checks as vc
+from nifty_b200._capi import CApi
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from emu.build_emu import build
+    return nb.Runtime(CApi(build()), "cpu")
+
+
+def test_draw_linear_residual(rt):
+    vc.check_draw_linear_residual(rt)
+
+
+def test_nonlinear_update(rt):
+    vc.check_nonlinear_update(rt)
+
+
+def test_kl_value_grad_metric(rt):
+    vc.check_kl(rt)
+    vc.check_kl(rt, "p2d_32x32")
+
+
+def test_optimize_kl_and_resume(rt, tmp_path):
+    vc.check_optimize_kl(rt, tmp_path)

@@ -1,0 +1,66 @@
+"""GPU tier (-m gpu): MGVI / geoVI drivers through the C ABI on the B200 against the oracle, plus a
+config-1 sized end-to-end optimize_kl run (BASELINE.json configs[0]: 128x128, 4 samples, 1 iteration)."""
+import numpy as np
+import pytest
+import torch
+
+import nifty_b200 as nb
+import vi_checks as vc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rt():
+    return nb.default_runtime()
+
+
+def test_draw_linear_residual(rt):
+    vc.check_draw_linear_residual(rt)
+
+
+def test_nonlinear_update(rt):
+    vc.check_nonlinear_update(rt)
+
+
+def test_kl_value_grad_metric(rt):
+    vc.check_kl(rt)
+    vc.check_kl(rt, "p2d_32x32")
+
+
+def test_optimize_kl_and_resume(rt, tmp_path):
+    vc.check_optimize_kl(rt, tmp_path)
+
+
+def test_config1_demo_shape(rt):
+    """demos/re/0_intro.py shape: 128x128 correlated field with scaling * exp(cf), Gaussian noise 0.1,
+    4 MGVI samples, one optimize_kl iteration with the demo's solver settings."""
+    shape = (128, 128)
+    cfm = nb.CorrelatedFieldMaker("cf")
+    cfm.set_amplitude_total_offset(0.0, (1e-3, 1e-4))
+    cfm.add_fluctuations(shape, 1.0 / shape[0], fluctuations=(1e-1, 5e-3), loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5),
+                         asperity=(0.5, 0.05), prefix="ax1", non_parametric_kind="power")
+    sig = nb.SignalModel(cfm.finalize(), "exp", scaling=(3.0, 1.0))
+    truth = sig.layout.random(42, torch.float64, rt.device)
+    lh0 = nb.Gaussian(torch.zeros(shape, dtype=torch.float64), noise_cov_inv=100.0).amend(sig)
+    data = lh0.signal_response(truth) + 0.1 * torch.randn(shape, dtype=torch.float64, device=rt.device,
+                                                          generator=torch.Generator(rt.device).manual_seed(43))
+    lh = nb.Gaussian(data, noise_cov_inv=lambda x: x / 0.01).amend(sig)
+    L = sig.layout.size
+    pos0 = 0.1 * sig.layout.random(44, torch.float64, rt.device)
+    samples, state = nb.optimize_kl(
+        lh, pos0, key=42, n_total_iterations=1, n_samples=4,
+        draw_linear_kwargs=dict(cg_name="SL", cg_kwargs=dict(absdelta=1e-4 * L / 10.0, maxiter=100)),
+        nonlinearly_update_kwargs=dict(minimize_kwargs=dict(name="SN", xtol=1e-4, cg_kwargs=dict(name=None), maxiter=5)),
+        kl_kwargs=dict(minimize_kwargs=dict(name="M", xtol=1e-4, cg_kwargs=dict(name=None), maxiter=35)),
+        sample_mode="linear_resample")
+    assert state.nit == 1 and len(samples) == 8
+    res = samples.residuals
+    assert float((res[0] + res[1]).abs().max()) == 0.0          # antithetic pairs, interleaved
+    vi = nb.OptimizeVI(lh, 1)
+    e1, g1 = vi.kl_value_and_grad(samples.pos, res)
+    e0, _ = vi.kl_value_and_grad(pos0, res)
+    assert np.isfinite(e1) and e1 < e0
+    # reduced chi^2 of the data residual at the posterior mean is O(1) after one iteration
+    chi2 = float((lh.normalized_residual(samples.pos) ** 2).mean())
+    assert chi2 < 50.0

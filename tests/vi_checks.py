@@ -1,0 +1,96 @@
+"""Sampling / KL checks shared by the CPU (emulator) and GPU tiers: the product's host drivers
+(nifty_b200.evi / optimize_kl, mirrors of nifty.re) against the oracle restatement on identical
+white-noise inputs."""
+import numpy as np
+import torch
+
+import nifty_b200 as nb
+import oracle
+from golden_util import CASES, build_oracle_lh, load, rel_err
+from parity_checks import build_product_lh, t2n
+
+CG_KW = dict(absdelta=1e-8, maxiter=60)
+
+
+def _setup(rt, name):
+    c, g = CASES[name], load(name)
+    lh = build_product_lh(c, g, rt)
+    olh = build_oracle_lh(c, g)
+    lay = oracle.Layout(olh.domain)
+    return c, g, lh, olh, lay
+
+
+def check_draw_linear_residual(rt, name="g2d_16x16"):
+    c, g, lh, olh, lay = _setup(rt, name)
+    rng = np.random.default_rng(21)
+    pos = {k: 0.3 * v for k, v in lay.random(rng).items()}
+    wd, wp = rng.standard_normal(c["shape"]), lay.random(rng)
+    ores, oinfo, ocg = oracle.draw_linear_residual(olh, pos, wd, wp, cg_kwargs=CG_KW)
+    tpos = rt.asarray(lay.pack(pos), torch.float64)
+    white = (rt.asarray(wd, torch.float64), rt.asarray(lay.pack(wp), torch.float64))
+    res, info = nb.draw_linear_residual(lh, tpos, 0, cg_kwargs=CG_KW, _white=white)
+    assert info == oinfo
+    assert rel_err(t2n(res), lay.pack(ores)) < 1e-9
+    # from_inverse=False is the metric sample itself
+    ms, _ = nb.draw_linear_residual(lh, tpos, 0, from_inverse=False, _white=white)
+    oms, _, _ = oracle.draw_linear_residual(olh, pos, wd, wp, from_inverse=False)
+    assert rel_err(t2n(ms), lay.pack(oms)) < 1e-11
+    return lh, olh, lay, pos, tpos, white, (wd, wp), res, ores
+
+
+def check_nonlinear_update(rt, name="g2d_16x16"):
+    lh, olh, lay, pos, tpos, white, (wd, wp), res, ores = check_draw_linear_residual(rt, name)
+    mk = dict(xtol=1e-6, maxiter=4, cg_kwargs=dict(maxiter=40))
+    for sign in (1.0, -1.0):
+        onew, oopt = oracle.nonlinearly_update_residual(olh, pos, {k: sign * v for k, v in ores.items()}, wd, wp, sign, minimize_kwargs=mk)
+        new, opt = nb.nonlinearly_update_residual(lh, tpos, sign * res, 0, sign, minimize_kwargs=mk, _white=white)
+        assert opt.nit == oopt.nit and opt.status == oopt.status
+        assert abs(opt.fun - oopt.fun) <= 1e-6 * max(abs(oopt.fun), 1e-12) + 1e-12
+        assert rel_err(t2n(new), lay.pack(onew)) < 1e-6
+
+
+def check_kl(rt, name="g2d_16x16"):
+    c, g, lh, olh, lay = _setup(rt, name)
+    rng = np.random.default_rng(5)
+    pos = {k: 0.3 * v for k, v in lay.random(rng).items()}
+    residuals = [{k: 0.1 * v for k, v in lay.random(rng).items()} for _ in range(3)]
+    residuals = [r for pair in ((r, {k: -v for k, v in r.items()}) for r in residuals) for r in pair]
+    tan = lay.random(rng)
+    ov, og = oracle.kl_value_and_grad(olh, pos, residuals)
+    om = oracle.kl_metric(olh, pos, tan, residuals)
+    vi = nb.OptimizeVI(lh, 1)
+    tpos = rt.asarray(lay.pack(pos), torch.float64)
+    tres = rt.asarray(np.stack([lay.pack(r) for r in residuals]), torch.float64)
+    v, gr = vi.kl_value_and_grad(tpos, tres)
+    assert abs(v - ov) <= 1e-11 * abs(ov)
+    assert rel_err(t2n(gr), lay.pack(og)) < 1e-10
+    m = vi.kl_metric(rt.asarray(lay.pack(tan), torch.float64))
+    assert rel_err(t2n(m), lay.pack(om)) < 1e-10
+    # no samples: the Hamiltonian at pos itself (optimize_kl.py:99-103)
+    ov0, og0 = oracle.kl_value_and_grad(olh, pos, [])
+    v0, g0 = vi.kl_value_and_grad(tpos, None)
+    assert abs(v0 - ov0) <= 1e-11 * abs(ov0) and rel_err(t2n(g0), lay.pack(og0)) < 1e-10
+
+
+def check_optimize_kl(rt, tmpdir, name="g2d_16x16", comm=None):
+    """Two VI iterations: the KL decreases, samples are interleaved antithetic pairs, resume continues."""
+    c, g, lh, olh, lay = _setup(rt, name)
+    pos0 = 0.1 * lh.layout.random(7, torch.float64, rt.device)
+    kw = dict(n_samples=2, key=42, draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=60)),
+              nonlinearly_update_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=30))),
+              kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=4, cg_kwargs=dict(maxiter=30))), sample_mode="nonlinear_resample")
+    vi = nb.OptimizeVI(lh, 2, comm=comm)
+    samples, state = nb.optimize_kl(lh, pos0, n_total_iterations=1, odir=str(tmpdir), comm=comm, **kw)
+    assert state.nit == 1
+    nloc = len(samples)
+    assert nloc % 2 == 0
+    r = samples.residuals
+    e1, _ = vi.kl_value_and_grad(samples.pos, r)
+    e0, _ = vi.kl_value_and_grad(pos0, r)       # same residuals around the start position
+    assert np.isfinite(e1) and e1 < e0
+    # resume: picks up at iteration 1 and runs the second one
+    samples2, state2 = nb.optimize_kl(lh, pos0, n_total_iterations=2, odir=str(tmpdir), resume=True, comm=comm, **kw)
+    assert state2.nit == 2 and len(samples2) == nloc
+    e2, _ = vi.kl_value_and_grad(samples2.pos, samples2.residuals)
+    assert np.isfinite(e2)
+    return samples2, state2
