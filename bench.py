@@ -63,40 +63,65 @@ def kernel_bytes(name, shape, w=8):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled through NVML while the GPU is under load (the recipe's
+    clocks line of B200_PROFILING.md; NVML instead of a piped `nvidia-smi -lms`, whose stdout is block
+    buffered).  Runs from the first warm-up step to the end of the end-to-end region."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index=0, period=0.01):
+        self.index, self.period, self.rows, self.stop_flag, self.thread, self.err = index, period, [], False, None, None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = torch.cuda.get_device_properties(self.index).uuid
+            except Exception:
+                pass
+            h = None
+            if uuid is not None:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv, self.h = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _loop(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(mhz), int(mask)))
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                break
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + str(self.err)]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({name for _, m in self.rows for bit, name in self.REASONS.items() if m & bit})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "window": "warm-up + timed + instrumented + end-to-end regions"}
 
 
 def make_inputs(shape, seed):
@@ -197,12 +222,12 @@ def run_b200(args, shape, wname, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        lin.metric(t, add_identity=True, out=out)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        lin.metric(t, add_identity=True, out=out)
+    barrier()
     n0 = rt.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -213,7 +238,6 @@ def run_b200(args, shape, wname, rank, world, local_rank):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = rt.launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -271,6 +295,7 @@ def run_b200(args, shape, wname, rank, world, local_rank):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * 1e3 / (float(te) / args.steps)
+    clocks = sampler.stop() if rank == 0 else None
     nbytes = t.numel() * t.element_size()
 
     # sample-draw seconds (second half of the BASELINE metric): one draw_linear_residual-style CG
@@ -312,7 +337,7 @@ def run_b200(args, shape, wname, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cf2d_4096_f64", choices=sorted(WORKLOADS))
@@ -323,8 +348,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     shape = WORKLOADS[args.workload][0]
     if args.impl == "reference":
-        if args.steps > 3 and np.prod(shape) >= 2**24:
-            args.steps = 3      # bounded sample: ~1-3 s per product on the host
+        if args.steps > 10 and np.prod(shape) >= 2**24:
+            args.steps = 10     # bounded sample: ~1-3 s per product on the host cores
         run_reference(args, shape, args.workload, rank, world)
     else:
         run_b200(args, shape, args.workload, rank, world, local_rank)
