@@ -116,13 +116,29 @@ constexpr int SCAN_CH = SCAN_NT * SCAN_E;
 template <class T> inline size_t scan_smem_bytes() { return (size_t)(SCAN_CH + 80) * sizeof(Aff<T>); }
 
 // ---- generic scan: (1) per-chunk aggregates [skipped for a single chunk], (2) apply -----------------
-template <class T, class Elem> struct ScanAggParams { long n; Elem elem; Aff<T>* agg; };
+template <class T, class Elem> struct ScanAggParams { long n; Elem elem; Aff<T>* agg; Aff<T>* pre; unsigned* counter; };
 template <class T, class Elem> struct ScanAggBody {
   typedef ScanAggParams<T, Elem> Params;
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
     Aff<T>* el = reinterpret_cast<Aff<T>*>(smem);
     long p0 = (long)ctx.bid * SCAN_CH;
+#if defined(NB_EMU) || !defined(NB_SCAN_BATCH)   // batching the SCAN_E evaluations measured 8-25 % slower (registers)
     NB_FOR(ctx, i, SCAN_CH) el[i] = (p0 + i < p.n) ? p.elem.get(p0 + i) : aff_id<T>();
+#else
+    {   // all SCAN_E element evaluations of a thread are independent: issue their loads together
+      Aff<T> v[SCAN_E];
+#pragma unroll
+      for (int e = 0; e < SCAN_E; ++e) {
+        long pos = p0 + ctx.tid + e * SCAN_NT;
+        v[e] = p.elem.get(pos < p.n ? pos : (p.n > 0 ? p.n - 1 : 0));
+      }
+#pragma unroll
+      for (int e = 0; e < SCAN_E; ++e) {
+        long pos = p0 + ctx.tid + e * SCAN_NT;
+        el[ctx.tid + e * SCAN_NT] = pos < p.n ? v[e] : aff_id<T>();
+      }
+    }
+#endif
     ctx.sync();
 #ifdef NB_EMU
     Aff<T> tot = aff_id<T>();
@@ -134,25 +150,52 @@ template <class T, class Elem> struct ScanAggBody {
     block_scan_aff(ctx, a, tot, reinterpret_cast<void*>(el + SCAN_CH));
 #endif
     if (ctx.tid == 0) p.agg[ctx.bid] = tot;
+    // the last block to finish turns the chunk aggregates into exclusive prefixes (pre[c], state
+    // before chunk c) and the grand total pre[nblk] -- one ordered block scan instead of two per
+    // apply block
+    if (ctx.last_block(p.counter)) {
+      void* scratch = reinterpret_cast<void*>(el + SCAN_CH);
+      const int n = ctx.nblk, per = (n + ctx.nthr - 1) / ctx.nthr;
+      const int lo = ctx.tid * per, hi = (lo + per < n) ? lo + per : n;
+      Aff<T> v = aff_id<T>();
+      for (int i = lo; i < hi; ++i) v = aff_compose(v, p.agg[i]);
+      Aff<T> total;
+      Aff<T> pre = block_scan_aff(ctx, v, total, scratch);
+      for (int i = lo; i < hi; ++i) { p.pre[i] = pre; pre = aff_compose(pre, p.agg[i]); }
+      if (ctx.tid == 0) p.pre[n] = total;
+    }
   }
 };
 // Out::put(pos, x0, y0, x1, y1, total_x, acc[4]) is called once per element with the state before /
 // after; Out::finish(ctx, acc, total_x, scratch) runs in every block afterwards.
-template <class T, class Elem, class Out> struct ScanApplyParams { long n; Elem elem; Out out; const Aff<T>* agg; int nchunks; };
+template <class T, class Elem, class Out> struct ScanApplyParams { long n; Elem elem; Out out; const Aff<T>* pre; int nchunks; };
 template <class T, class Elem, class Out> struct ScanApplyBody {
   typedef ScanApplyParams<T, Elem, Out> Params;
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
     Aff<T>* el = reinterpret_cast<Aff<T>*>(smem);
     void* scratch = reinterpret_cast<void*>(el + SCAN_CH);
     long p0 = (long)ctx.bid * SCAN_CH;
+#if defined(NB_EMU) || !defined(NB_SCAN_BATCH)   // batching the SCAN_E evaluations measured 8-25 % slower (registers)
     NB_FOR(ctx, i, SCAN_CH) el[i] = (p0 + i < p.n) ? p.elem.get(p0 + i) : aff_id<T>();
+#else
+    {   // all SCAN_E element evaluations of a thread are independent: issue their loads together
+      Aff<T> v[SCAN_E];
+#pragma unroll
+      for (int e = 0; e < SCAN_E; ++e) {
+        long pos = p0 + ctx.tid + e * SCAN_NT;
+        v[e] = p.elem.get(pos < p.n ? pos : (p.n > 0 ? p.n - 1 : 0));
+      }
+#pragma unroll
+      for (int e = 0; e < SCAN_E; ++e) {
+        long pos = p0 + ctx.tid + e * SCAN_NT;
+        el[ctx.tid + e * SCAN_NT] = pos < p.n ? v[e] : aff_id<T>();
+      }
+    }
+#endif
     ctx.sync();
     // carry-in of this chunk and the grand total from the chunk aggregates (nchunks > 1)
     Aff<T> carry = aff_id<T>(), grand = aff_id<T>();
-    if (p.nchunks > 1) {
-      carry = block_compose_range(ctx, p.agg, 0, ctx.bid, scratch);
-      grand = block_compose_range(ctx, p.agg, 0, p.nchunks, scratch);
-    }
+    if (p.nchunks > 1) { carry = p.pre[ctx.bid]; grand = p.pre[p.nchunks]; }
 #ifdef NB_EMU
     {
       // one host "thread": walk the whole chunk sequentially
@@ -214,13 +257,15 @@ template <class T> NB_HD NB_INLINE AmpPoint<T> amp_point(const AmpModel<T>& m, c
 template <class T> struct FwdElem {
   AmpModel<T> m; const T* pos;
   NB_HD NB_INLINE Aff<T> get(long b) const {
-    if (!m.has_dev || b < 2) return aff_id<T>();
-    long j = b - 2;
+    if (!m.has_dev) return aff_id<T>();
+    long j = b >= 2 ? b - 2 : 0;
     AmpPoint<T> ap = amp_point(m, pos);
     T dt = m.dt[j], sd = ap.sig * nb_sqrt(dt), q = nb_sqrt(dt * dt / T(12) + ap.asp);
     T x0 = pos[m.off_spec + 2 * j], x1 = pos[m.off_spec + 2 * j + 1];
     T r1 = sd * x1, r0 = sd * x0 * q + T(0.5) * dt * r1;
-    Aff<T> e; e.a = dt; e.b = r0; e.c = r1; return e;
+    Aff<T> e; e.a = dt; e.b = r0; e.c = r1;
+    if (b < 2) e = aff_id<T>();
+    return e;
   }
 };
 // P_b = exp(slope l_b + tw_b - tw_last l_b / l_last); partial S
@@ -282,8 +327,8 @@ template <class T> struct AmpTabBody {
 template <class T> struct JvpElem {
   AmpModel<T> m; const T* pos; const T* t; const T* scal;
   NB_HD NB_INLINE Aff<T> get(long b) const {
-    if (!m.has_dev || b < 2) return aff_id<T>();
-    long j = b - 2;
+    if (!m.has_dev) return aff_id<T>();
+    long j = b >= 2 ? b - 2 : 0;
     AmpPoint<T> ap; ap.sig = scal[SC_SIG]; ap.asp = scal[SC_ASP];
     T dt = m.dt[j], sd = ap.sig * nb_sqrt(dt), q = nb_sqrt(dt * dt / T(12) + ap.asp);
     T x0 = pos[m.off_spec + 2 * j], x1 = pos[m.off_spec + 2 * j + 1];
@@ -292,7 +337,9 @@ template <class T> struct JvpElem {
     T dasp = m.has_asp ? ap.asp * m.asp_b * t[m.off_asp] : T(0);
     T dr1 = sd * (dsig_rel * x1 + d1);
     T dr0 = sd * q * (dsig_rel * x0 + d0) + sd * x0 * dasp / (T(2) * q) + T(0.5) * dt * dr1;
-    Aff<T> e; e.a = dt; e.b = dr0; e.c = dr1; return e;
+    Aff<T> e; e.a = dt; e.b = dr0; e.c = dr1;
+    if (b < 2) e = aff_id<T>();
+    return e;
   }
 };
 template <class T> struct JvpOut {
@@ -340,7 +387,13 @@ template <class T> struct SegSumBody {
       T s = 0;
       if (b < m.K) {
         int beg = p.offs[b], end = p.offs[b + 1];
-        for (int q = beg + lane; q < end; q += lpb) s += p.W[p.order[q]];
+        int q = beg + lane;
+        for (; q + 3 * lpb < end; q += 4 * lpb) {     // four independent index -> value chains in flight
+          int o0 = p.order[q], o1 = p.order[q + lpb], o2 = p.order[q + 2 * lpb], o3 = p.order[q + 3 * lpb];
+          T w0 = p.W[o0], w1 = p.W[o1], w2 = p.W[o2], w3 = p.W[o3];
+          s += w0; s += w1; s += w2; s += w3;
+        }
+        for (; q < end; q += lpb) s += p.W[p.order[q]];
       }
       sm[i] = s;
     }
@@ -362,8 +415,7 @@ template <class T> struct SegSumBody {
     }
     if (!p.g) return;
     void* scratch = reinterpret_cast<void*>(sm + 256);
-    a0 = ctx.block_sum(a0, scratch);
-    a1 = ctx.block_sum(a1, scratch);
+    { T v2[2] = {a0, a1}; ctx.template block_sum_n<2>(v2, scratch); a0 = v2[0]; a1 = v2[1]; }
     if (ctx.tid == 0) { p.partials[2 * ctx.bid] = a0; p.partials[2 * ctx.bid + 1] = a1; }
     if (ctx.last_block(p.counter)) {
       T sg = block_total(ctx, p.partials, ctx.nblk, 2, scratch);
@@ -423,8 +475,8 @@ template <class T> struct VjpOut {
     out[off] = v;
   }
   NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, T, void* scratch) const {
-    T s0 = ctx.block_sum(acc[0], scratch), s1 = ctx.block_sum(acc[1], scratch), s2 = ctx.block_sum(acc[2], scratch);
-    if (ctx.tid == 0) { partials[3 * ctx.bid] = s0; partials[3 * ctx.bid + 1] = s1; partials[3 * ctx.bid + 2] = s2; }
+    ctx.template block_sum_n<3>(acc, scratch);
+    if (ctx.tid == 0) { partials[3 * ctx.bid] = acc[0]; partials[3 * ctx.bid + 1] = acc[1]; partials[3 * ctx.bid + 2] = acc[2]; }
     if (ctx.last_block(counter)) {
       T sigbar = block_total(ctx, partials, ctx.nblk, 3, scratch);
       T aspbar = block_total(ctx, partials + 1, ctx.nblk, 3, scratch);

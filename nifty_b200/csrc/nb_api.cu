@@ -44,7 +44,7 @@ template <class T> void Model<T>::init(Plan<T>* plan_, const nb200_model_desc& d
   am.ell = ell.p; am.mult = multT.p; am.dt = dt.p;
   nchunksK = (g.K + SCAN_CH - 1) / SCAN_CH;
   nchunksJ = std::max(1, (g.K - 2 + SCAN_CH - 1) / SCAN_CH);
-  agg.alloc(nchunksK + 1); pre.alloc(2 * (size_t)nchunksK + 2); total.alloc(2);
+  agg.alloc(nchunksK + 1); preaff.alloc(nchunksK + 2); pre.alloc(2 * (size_t)nchunksK + 2); total.alloc(2);
   ad.alloc(g.K); gbuf.alloc(g.K);
   size_t np = std::max<size_t>(3 * (size_t)nchunksK + 3, 2 * (size_t)P->seg_grid() + 2);
   np = std::max<size_t>(np, 4 * 2048);
@@ -106,8 +106,8 @@ int cg_solve(Lin<T>* lin, Lin<T>* lin_b, stream_t st, const T* j, T* x, const nb
     p.resnorm = (T)std::max((double)o.tol * std::sqrt((double)jj), (double)o.atol);
   }
   int nfev = 0;
-  if (o.x0_is_zero) { p.mode = CGM_INIT_ZERO; p.iter = 0; launch<CgStepBody<T>>(vgrid, 256, 512, st, p); }
-  else { op(x, w.q.p); ++nfev; p.mode = CGM_INIT; p.iter = 0; launch<CgStepBody<T>>(vgrid, 256, 512, st, p); }
+  if (o.x0_is_zero) { p.mode = CGM_INIT_ZERO; p.iter = 0; launch<CgStepBody<T>>(vgrid, 256, 1024, st, p); }
+  else { op(x, w.q.p); ++nfev; p.mode = CGM_INIT; p.iter = 0; launch<CgStepBody<T>>(vgrid, 256, 1024, st, p); }
   int host_cgi[CGI_NINT] = {0};
   const int every = std::max(1, o.check_every);
   long i = 0;
@@ -121,11 +121,11 @@ int cg_solve(Lin<T>* lin, Lin<T>* lin_b, stream_t st, const T* j, T* x, const nb
       }
       p.iter = (int)i;
       if (i % 20 == 0) {   // N_RESET (conjugate_gradient.py:17,168-172)
-        p.mode = CGM_POS_ONLY; launch<CgStepBody<T>>(vgrid, 256, 512, st, p);
+        p.mode = CGM_POS_ONLY; launch<CgStepBody<T>>(vgrid, 256, 1024, st, p);
         op(x, w.q.p);
-        p.mode = CGM_RESID; launch<CgStepBody<T>>(vgrid, 256, 512, st, p);
+        p.mode = CGM_RESID; launch<CgStepBody<T>>(vgrid, 256, 1024, st, p);
       } else {
-        p.mode = CGM_NORMAL; launch<CgStepBody<T>>(vgrid, 256, 512, st, p);
+        p.mode = CGM_NORMAL; launch<CgStepBody<T>>(vgrid, 256, 1024, st, p);
       }
       launch<CgDirBody<T>>(vgrid, 256, 0, st, p);
       if (i % every == 0 || i == maxiter) {

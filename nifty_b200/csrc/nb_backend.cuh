@@ -71,8 +71,12 @@ inline int sm_count() {
   return v;
 }
 
+// bodies may define `static constexpr int kMinBlocks` (register budget hint for ptxas)
+template <class B, class = void> struct MinBlocks { static constexpr int value = 1; };
+template <class B> struct MinBlocks<B, decltype((void)B::kMinBlocks)> { static constexpr int value = B::kMinBlocks; };
+
 template <class Body>
-__global__ void __launch_bounds__(256) nb_kernel(const __grid_constant__ typename Body::Params p) {
+__global__ void __launch_bounds__(256, MinBlocks<Body>::value) nb_kernel(const __grid_constant__ typename Body::Params p) {
   extern __shared__ __align__(16) unsigned char nb_smem[];
   Ctx ctx{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   Body::run(ctx, p, nb_smem);

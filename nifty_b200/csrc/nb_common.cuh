@@ -50,6 +50,7 @@ struct Ctx {
   int tid, nthr, bid, nblk;
   void sync() {}
   template <class T> T block_sum(T v, void*) { return v; }
+  template <int N, class T> void block_sum_n(T*, void*) {}
   template <class T> T block_max(T v, void*) { return v; }
   // true for exactly one block: the one that finishes last (blocks run in order in the emulator)
   bool last_block(unsigned* counter) {
@@ -84,6 +85,36 @@ struct Ctx {
     r = s[0];
     __syncthreads();
     return r;
+  }
+  // N sums at once (same barrier count as one): v[0..N) reduced in place, result in every thread.
+  // `scratch` must hold >= 32*N values of T.
+  template <int N, class T> __device__ NB_INLINE void block_sum_n(T* v, void* scratch) {
+    T* s = reinterpret_cast<T*>(scratch);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    }
+    int w = tid >> 5, l = tid & 31, nw = (nthr + 31) >> 5;
+    __syncthreads();
+    if (l == 0) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) s[k * 32 + w] = v[k];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        T r = (l < nw) ? s[k * 32 + l] : T(0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+        if (l == 0) s[k * 32] = r;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = s[k * 32];
+    __syncthreads();
   }
   template <class T> __device__ NB_INLINE T block_max(T v, void* scratch) {
     T* s = reinterpret_cast<T*>(scratch);

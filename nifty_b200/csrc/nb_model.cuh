@@ -55,7 +55,7 @@ template <class T> struct Model : ModelBase {
   DevBuf<T> ell, multT, dt, data, w_arr;
   bool has_w_arr = false;
   // chain workspaces
-  DevBuf<Aff<T>> agg;
+  DevBuf<Aff<T>> agg, preaff;
   DevBuf<T> pre, total, gbuf, partials, tmp_pos;
   DevBuf<cplx<T>> ad;
   DevBuf<unsigned> counters;
@@ -86,12 +86,12 @@ template <class T> struct Lin : LinBase {
     FwdElem<T> el; el.m = m.am; el.pos = pos.p;
     const int nch = m.am.has_dev ? m.nchunksK : 1;   // without deviations every element is the identity
     if (m.am.has_dev && m.nchunksK > 1) {
-      ScanAggParams<T, FwdElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p;
+      ScanAggParams<T, FwdElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p; pa.pre = m.preaff.p; pa.counter = m.counters.p + 5;
       launch<ScanAggBody<T, FwdElem<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
     }
     FwdOut<T> fo; fo.m = m.am; fo.pos = pos.p; fo.P = Pb.p; fo.partials = m.partials.p;
     fo.counter = m.counters.p; fo.scal = scal.p;
-    ScanApplyParams<T, FwdElem<T>, FwdOut<T>> pc; pc.n = K; pc.elem = el; pc.out = fo; pc.agg = m.agg.p; pc.nchunks = nch;
+    ScanApplyParams<T, FwdElem<T>, FwdOut<T>> pc; pc.n = K; pc.elem = el; pc.out = fo; pc.pre = m.preaff.p; pc.nchunks = nch;
     launch<ScanApplyBody<T, FwdElem<T>, FwdOut<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
     AmpTabParams<T> pt2; pt2.m = m.am; pt2.P = Pb.p; pt2.amp = amp.p; pt2.wS = wS.p; pt2.partials = m.partials.p;
     pt2.counter = m.counters.p + 1; pt2.scal = scal.p;
@@ -104,12 +104,12 @@ template <class T> struct Lin : LinBase {
     JvpElem<T> el; el.m = m.am; el.pos = pos.p; el.t = t; el.scal = scal.p;
     const int nch = m.am.has_dev ? m.nchunksK : 1;
     if (m.am.has_dev && m.nchunksK > 1) {
-      ScanAggParams<T, JvpElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p;
+      ScanAggParams<T, JvpElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p; pa.pre = m.preaff.p; pa.counter = m.counters.p + 5;
       launch<ScanAggBody<T, JvpElem<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
     }
     JvpOut<T> jo; jo.m = m.am; jo.pos = pos.p; jo.t = t; jo.wS = wS.p; jo.amp = amp.p; jo.ad = m.ad.p;
     jo.partials = m.partials.p; jo.counter = m.counters.p + 2; jo.scal = scal.p;
-    ScanApplyParams<T, JvpElem<T>, JvpOut<T>> pc; pc.n = K; pc.elem = el; pc.out = jo; pc.agg = m.agg.p; pc.nchunks = nch;
+    ScanApplyParams<T, JvpElem<T>, JvpOut<T>> pc; pc.n = K; pc.elem = el; pc.out = jo; pc.pre = m.preaff.p; pc.nchunks = nch;
     launch<ScanApplyBody<T, JvpElem<T>, JvpOut<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
   }
   ProMetric<T> pro_metric(const T* t) const {
@@ -134,13 +134,13 @@ template <class T> struct Lin : LinBase {
     if (nj > 0) {
       VjpElem<T> el; el.m = m.am; el.g = m.gbuf.p; el.wS = wS.p; el.scal = scal.p;
       if (m.nchunksJ > 1) {
-        ScanAggParams<T, VjpElem<T>> pa; pa.n = nj; pa.elem = el; pa.agg = m.agg.p;
+        ScanAggParams<T, VjpElem<T>> pa; pa.n = nj; pa.elem = el; pa.agg = m.agg.p; pa.pre = m.preaff.p; pa.counter = m.counters.p + 5;
         launch<ScanAggBody<T, VjpElem<T>>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pa);
       }
-      ScanApplyParams<T, VjpElem<T>, VjpOut<T>> pc; pc.n = nj; pc.elem = el; pc.out = vo; pc.agg = m.agg.p; pc.nchunks = m.nchunksJ;
+      ScanApplyParams<T, VjpElem<T>, VjpOut<T>> pc; pc.n = nj; pc.elem = el; pc.out = vo; pc.pre = m.preaff.p; pc.nchunks = m.nchunksJ;
       launch<ScanApplyBody<T, VjpElem<T>, VjpOut<T>>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pc);
     } else {
-      ScanApplyParams<T, NoElem<T>, VjpOut<T>> pc; pc.n = 0; pc.out = vo; pc.agg = nullptr; pc.nchunks = 1;
+      ScanApplyParams<T, NoElem<T>, VjpOut<T>> pc; pc.n = 0; pc.out = vo; pc.pre = nullptr; pc.nchunks = 1;
       launch<ScanApplyBody<T, NoElem<T>, VjpOut<T>>>(1, SCAN_NT, m.scan_smem(), st, pc);
     }
   }

@@ -135,6 +135,9 @@ template <class T, class Pro> struct P1Params {
 
 template <class T, class Pro, bool AL> struct P1Body {
   typedef P1Params<T, Pro> Params;
+#ifdef NB_P1_MINB
+  static constexpr int kMinBlocks = NB_P1_MINB;
+#endif
   struct Loader {
     const Params& p; int o, rr0; long in0;
     template <int NQ> NB_HD NB_INLINE void batch(int r, int j, int lmr, cplx<T>* a) const {
@@ -368,6 +371,9 @@ template <class T> struct P3Params {
 
 template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
   typedef P3Params<T> Params;
+#ifdef NB_P3_MINB
+  static constexpr int kMinBlocks = NB_P3_MINB;
+#endif
   // Hermitian combine of the pair (x, y = -x) of one line + pointwise operator
   static NB_HD NB_INLINE void pair(const Params& p, cplx<T>* line, const LineInfo& li, int x, int y, T cshift, T scv,
                                    T& acc0, T& acc1) {

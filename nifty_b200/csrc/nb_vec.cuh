@@ -74,7 +74,7 @@ template <class T> struct CgStepBody {
       if (ctx.bid == 0 && ctx.tid == 0) p.cgs[CG_ALPHA] = alpha;
       return;
     }
-    a_g = ctx.block_sum(a_g, smem); a_1 = ctx.block_sum(a_1, smem); a_e = ctx.block_sum(a_e, smem);
+    { T v3[3] = {a_g, a_1, a_e}; ctx.template block_sum_n<3>(v3, smem); a_g = v3[0]; a_1 = v3[1]; a_e = v3[2]; }
     a_m = ctx.block_max(a_m, smem);
     if (ctx.tid == 0) {
       p.partials[4 * ctx.bid] = a_g; p.partials[4 * ctx.bid + 1] = a_1;

@@ -44,16 +44,20 @@ def main():
     out = torch.empty_like(t)
     torch.cuda.synchronize()
     print(f"setup {time.time()-t0:.1f}s  N={np.prod(shape)} K={lh.signal.cf.plan.K} L={L}")
-    for _ in range(3):
+    t_w = time.time()
+    while time.time() - t_w < 0.5:          # clocks ramp up on a fresh box
         lin.metric(t, add_identity=True, out=out)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        lin.metric(t, add_identity=True, out=out)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.steps
+    best = 1e9
+    for _ in range(3):
+        e0.record()
+        for _ in range(a.steps):
+            lin.metric(t, add_identity=True, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / a.steps)
+    ms = best
     w = 8 if dtype == torch.float64 else 4
     d = len(shape) if len(shape) > 1 else 2
     bytes_mvp = w * np.prod(shape) * (2 * (2 * d - 1) + 4)
@@ -71,7 +75,10 @@ def main():
         lin.update(pos, want_grad=True, add_prior=True)
     e1.record()
     torch.cuda.synchronize()
-    print(f"linearise+grad {e0.elapsed_time(e1)/5:.4f} ms")
+    try:
+        print(f"linearise+grad {e0.elapsed_time(e1)/5:.4f} ms")
+    except BrokenPipeError:
+        pass
 
 
 if __name__ == "__main__":
