@@ -169,7 +169,7 @@ template <class T> struct Plan : PlanBase {
   int seg_grid() const { int bpb = 256 >> seg_lg_lpb; return (g.K + bpb - 1) / bpb; }
 
   static PassCfg choose(int lg_n_line /*log2 complex elems per line*/, int64_t group_lines, int64_t n_groups_outer,
-                        bool sequential_lines, int64_t total_lines, const char* env_R = "NB200_LGR_NONE") {
+                        bool sequential_lines, int64_t total_lines, const char* env_R = "NB200_LGR_NONE", int cap_shift = 0) {
     PassCfg c;
     const size_t line_bytes = (size_t(1) << lg_n_line) * sizeof(cplx<T>);
     const size_t maxs = max_smem_per_block() - 2048;
@@ -182,10 +182,11 @@ template <class T> struct Plan : PlanBase {
     };
     // complex elements per CTA: 4096 for long lines, 1024 for short ones (measured optimum on B200:
     // 256^3 runs 9 % faster with R = 4 than with R = 16, 2048^2 / 4096^2 are best at 4096 elements)
-    const int64_t elems = (lg_n_line >= 10) ? 4096 : 1024;
+    // P1 (cap_shift = 1) counts its REAL line length: 8192 reals for long lines, 1024 for short ones
+    const int64_t elems = (lg_n_line + cap_shift >= 10) ? (int64_t(4096) << cap_shift) : 1024;
     int lgR = 0;
     while (lgR < 4 && (int64_t(2) << lgR) <= (sequential_lines ? total_lines : group_lines) &&
-           (size_t(2) << lgR) * line_bytes <= budget && ((int64_t(2) << lgR) << lg_n_line) <= elems)
+           (size_t(2) << lgR) * line_bytes <= budget && ((int64_t(2) << lgR) << (lg_n_line + cap_shift)) <= elems)
       ++lgR;
     while (lgR > 0 && ctas(lgR) < 2 * sms) --lgR;
     if (const char* e = std::getenv(env_R)) {   // tuning override (developer knob)
@@ -235,8 +236,8 @@ template <class T> struct Plan : PlanBase {
     else sc = (size_t)std::max((hl + 1) * n0, (h0 + 1) * nl);
     S0.alloc(sc); S1.alloc(sc);
     // P1: real lines of length nl -> complex FFT of nl/2
-    if (g.three) c1 = choose(lgl - 1, nm, n0, false, 0, "NB200_LGR1");
-    else c1 = choose(lgl - 1, n0, 1, false, 0, "NB200_LGR1");
+    if (g.three) c1 = choose(lgl - 1, nm, n0, false, 0, "NB200_LGR1", 1);
+    else c1 = choose(lgl - 1, n0, 1, false, 0, "NB200_LGR1", 1);
     c1.lg_n = lgl;
     if (g.three) {
       cA = choose(lgm, n0, hl + 1, false, 0, "NB200_LGRC"); cA.lg_n = lgm;

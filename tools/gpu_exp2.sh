@@ -1,19 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-P="python tools/gpu_probe.py --shape 256,256,256"
-run() { echo "== $1"; env $1 $P 2>/dev/null | sed -n 2,7p; }
 {
-run "NB200_LGR1=2 NB200_LGR3=2 NB200_LGR5=2 NB200_LGRC=4"
-run "NB200_LGR1=2 NB200_LGR3=2 NB200_LGR5=2 NB200_LGRC=2"
-run "NB200_LGR1=2 NB200_LGR3=2 NB200_LGR5=2 NB200_LGRC=3"
-run "NB200_LGR1=1 NB200_LGR3=1 NB200_LGR5=1 NB200_LGRC=2"
-run "NB200_LGR1=2 NB200_LGR3=2 NB200_LGR5=2 NB200_LGRC=2 NB200_BLOCK=128"
-run "NB200_LGR1=3 NB200_LGR3=2 NB200_LGR5=2 NB200_LGRC=2"
-run "NB200_LGR1=2 NB200_LGR3=3 NB200_LGR5=2 NB200_LGRC=2"
-run "NB200_LGR1=2 NB200_LGR3=2 NB200_LGR5=3 NB200_LGRC=2"
-P="python tools/gpu_probe.py --shape 2048,2048"
-run "NB200_NONE=1"
-run "NB200_LGR1=1 NB200_LGR3=0 NB200_LGR5=0"
-run "NB200_LGR1=2 NB200_LGR3=1 NB200_LGR5=1"
-run "NB200_LGR1=3 NB200_LGR3=2 NB200_LGR5=2"
+for s in 4096,4096 2048,2048 256,256,256 1024,1024 128,128,128 512,512; do python tools/gpu_probe.py --shape $s 2>/dev/null | sed -n 1,5p; done
+python tools/gpu_probe.py --shape 4096,4096 --dtype f32 2>/dev/null | sed -n 1,6p
+python tools/gpu_probe.py --shape 256,256,256 --dtype f32 2>/dev/null | sed -n 1,6p
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 } > gpurun_out/exp2.log 2>&1
