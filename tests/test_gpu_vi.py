@@ -64,3 +64,55 @@ def test_config1_demo_shape(rt):
     # reduced chi^2 of the data residual at the posterior mean is O(1) after one iteration
     chi2 = float((lh.normalized_residual(samples.pos) ** 2).mean())
     assert chi2 < 50.0
+
+
+def test_config4_geovi_poisson_2048(rt):
+    """BASELINE.json configs[3]: geoVI non-linear sample update, 2-D 2048^2 field, Poissonian likelihood
+    (hyper-parameters of misc/re/paper/minimal_benchmark.py:94-105).  At this size the oracle is out of
+    reach; checked properties: the update runs its Newton-CG steps on the device operator of
+    evi.py:167-172, decreases the geoVI objective, and the antithetic update differs from the mirror."""
+    import time
+    shape = (2048, 2048)
+    cfm = nb.CorrelatedFieldMaker("cf")
+    cfm.set_amplitude_total_offset(2.0, (0.1, 0.03))
+    cfm.add_fluctuations(shape, 1.0 / shape[0], fluctuations=(1.0, 0.5), loglogavgslope=(-3.0, 0.2), flexibility=(1.0, 0.2),
+                         asperity=(0.5, 0.05), prefix="ax1", non_parametric_kind="power")
+    sig = nb.SignalModel(cfm.finalize(), "exp")
+    truth = sig.layout.random(1, torch.float64, rt.device)
+    lam = nb.Gaussian(torch.zeros(shape, dtype=torch.float64), noise_cov_inv=1.0).amend(sig).signal_response(truth)
+    data = torch.poisson(lam, generator=torch.Generator(rt.device).manual_seed(2)).to(torch.int64)
+    lh = nb.Poissonian(data.cpu().numpy()).amend(sig)
+    pos = truth + 0.05 * sig.layout.random(3, torch.float64, rt.device)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res, info = nb.draw_linear_residual(lh, pos, 11, cg_kwargs=dict(absdelta=1e-4 * sig.layout.size / 10.0, maxiter=100))
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    vals = []
+    for sign in (1.0, -1.0):
+        new, opt = nb.nonlinearly_update_residual(lh, pos, sign * res, 11, sign,
+                                                  minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=30)))
+        assert opt.nit >= 1 and np.isfinite(opt.fun)
+        vals.append((new, opt))
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"2048^2 Poisson: linear draw {t1-t0:.3f}s (info {info}), two geoVI updates {t2-t1:.3f}s, "
+          f"nit {[o.nit for _, o in vals]}, nhev {[o.nhev for _, o in vals]}")
+    # geoVI objective at the start (linear residual) is larger than after the update
+    e = pos
+    lin_e = lh.new_lin(); lin_e.update(e)
+    lin_x = lh.new_lin()
+    ms, _ = nb.draw_linear_residual(lh, pos, 11, from_inverse=False)
+
+    def objective(x, sign):
+        lin_x.update(x)
+        t = lin_x.transformation() - lin_e.transformation()
+        g = x - e + lin_e.lsm(t, scaled=True)
+        r = sign * ms - g
+        return 0.5 * float(torch.dot(r, r))
+
+    for (new, opt), sign in zip(vals, (1.0, -1.0)):
+        f0 = objective(e + sign * res, sign)
+        assert abs(objective(e + new, sign) - opt.fun) <= 1e-8 * max(1.0, abs(opt.fun))
+        assert opt.fun < f0
+    assert float((vals[0][0] + vals[1][0]).abs().max()) > 0.0      # non-linear updates break the exact mirror symmetry
