@@ -65,6 +65,24 @@ int nb200_plan_log_volume(const nb200_plan* plan, double* out_host /*K-2*/);
 /* full power_distributor (int32, natural order, N entries) for API compatibility */
 int nb200_plan_power_distributor(const nb200_plan* plan, int32_t* out_host /*N*/);
 
+/* ---- slab-decomposed 3-D grids (no reference counterpart: SURVEY.md 8e.2; fields too large for one GPU) ----
+ * One process per GPU.  Axis 0 of the latent array and the last axis of position space are cut into slabs such
+ * that the Hermitian partner of every line is local.  The library runs the local passes;
+ * the HOST performs the two all-to-all exchanges and one all-reduce per product with its own communicator
+ * (torch.distributed / NCCL) on the buffers it registered with nb200_plan_set_scratch. */
+int nb200_plan_create_dist(nb200_plan** plan, int device, int ndim, const int64_t* shape_host, const double* distances_host,
+                           int dtype, int hartley_convention, int rank, int world);
+/* out = {rank, world, local latent rows (padded), local position planes (padded), scratch elements (complex),
+ *        n0, n1, n2, K, rows per rank [world], planes per rank [world], half-range rows per rank [world], half-range planes per rank [world]} */
+int nb200_plan_dist_info(const nb200_plan* plan, int64_t* out_host, int64_t nout);
+/* local -> global index of the owned rows (axis = 0) or position planes (axis = 2); -1 marks zero padding */
+int nb200_plan_local_map(const nb200_plan* plan, int axis, int32_t* out_host);
+/* two device buffers of `scratch elements` complex numbers each: pass buffers and all-to-all send / receive space */
+int nb200_plan_set_scratch(nb200_plan* plan, void* s0, void* s1);
+/* one segment of an operator between exchanges; codes and the exchange after each are listed in DESIGN.md section 7 */
+int nb200_dist_phase(nb200_lin* lin_a, nb200_lin* lin_b, void* stream, int code, const void* in, void* out, void* abar, void* xs,
+                     int flag);
+
 /* hartley(p, axes=all) (correlated_field.py:24-30): out = Re(fftn(in)) +/- Im(fftn(in)), unnormalised */
 int nb200_hartley(nb200_plan* plan, void* stream, const void* in, void* out);
 

@@ -85,12 +85,48 @@ def default_runtime() -> Runtime:
     return _default_rt
 
 
+class SlabComm:
+    """The collectives the slab-decomposed path needs, on a torch.distributed process group."""
+
+    def __init__(self, group=True):
+        import torch.distributed as dist
+        self.dist = dist
+        if not dist.is_available() or not dist.is_initialized():
+            self.group, self.rank, self.world = None, 0, 1
+        else:
+            self.group = None if group is True else group
+            self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+
+    def all_to_all(self, out, inp, out_splits, in_splits):
+        n_out, n_in = sum(out_splits), sum(in_splits)
+        self.dist.all_to_all_single(out[:n_out], inp[:n_in], out_splits, in_splits, group=self.group)
+
+    def allreduce_sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_gather(self, t):
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t.contiguous(), group=self.group)
+        return out
+
+    def all_gather_obj(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+
 class Plan:
     """``nb200_plan``: regular Fourier grid + transform plan."""
 
     def __init__(self, shape: Sequence[int], distances, dtype=torch.float64, hartley_convention="non_canonical_hartley",
-                 runtime: Optional[Runtime] = None):
+                 runtime: Optional[Runtime] = None, comm=None):
+        """``comm``: a ``torch.distributed`` process group (or True for the default group) -> the 3-D grid is
+        slab-decomposed over its ranks (one process per GPU); None -> the whole grid lives on this GPU."""
         self.rt = runtime or default_runtime()
+        self.comm = SlabComm(comm) if comm is not None else None
+        self.dist = self.comm is not None and self.comm.world > 1
         self.shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
         self.distances = tuple(float(d) for d in np.broadcast_to(distances, (len(self.shape),)))
         if dtype not in _DTYPES:
@@ -102,12 +138,98 @@ class Plan:
         self._h = C.c_void_p()
         shp = (C.c_int64 * len(self.shape))(*self.shape)
         dst = (C.c_double * len(self.shape))(*self.distances)
-        self.rt.api.call("nb200_plan_create", C.byref(self._h), self.rt.device_index(), len(self.shape), shp, dst,
-                         _DTYPES[dtype], 0 if hartley_convention == "non_canonical_hartley" else 1)
+        conv = 0 if hartley_convention == "non_canonical_hartley" else 1
+        if self.dist:
+            self.rt.api.call("nb200_plan_create_dist", C.byref(self._h), self.rt.device_index(), len(self.shape), shp, dst,
+                             _DTYPES[dtype], conv, self.comm.rank, self.comm.world)
+        else:
+            self.rt.api.call("nb200_plan_create", C.byref(self._h), self.rt.device_index(), len(self.shape), shp, dst,
+                             _DTYPES[dtype], conv)
         lib = self.rt.api.lib
         self.K = int(lib.nb200_plan_num_modes(self._h))
         self.N = int(lib.nb200_plan_size(self._h))
         self.total_volume = float(lib.nb200_plan_total_volume(self._h))
+        self.local_shape = self.shape              # latent xi block held by this rank
+        self.local_pos_shape = self.shape          # position-space block (API layout)
+        if self.dist:
+            self._init_dist()
+
+    # -- slab decomposition -----------------------------------------------------------------------
+    def _init_dist(self):
+        W = self.comm.world
+        info = (C.c_int64 * (9 + 4 * W))()
+        self.rt.api.call("nb200_plan_dist_info", self._h, info, len(info))
+        v = list(info)
+        self.rows0, self.planes2, self.scratch_elems = int(v[2]), int(v[3]), int(v[4])
+        n0, n1, n2 = int(v[5]), int(v[6]), int(v[7])
+        npad0, npad2 = v[9:9 + W], v[9 + W:9 + 2 * W]
+        cA0, cA2 = v[9 + 2 * W:9 + 3 * W], v[9 + 3 * W:9 + 4 * W]
+        me = self.comm.rank
+        self.local_shape = (self.rows0, n1, n2)
+        self.local_pos_shape = (self.planes2, n1, n0)      # internal reversed-axis layout [x2][x1][x0]
+        # exchange 1 (after the middle-axis pass): to rank q the k2 planes of q's half-range piece
+        self.x1_send = [2 * int(cA2[q] * n1 * npad0[me]) for q in range(W)]
+        self.x1_recv = [2 * int(cA2[me] * n1 * npad0[p]) for p in range(W)]
+        # exchange 2 (after the second middle-axis pass): to rank r the k0 planes of r's piece
+        self.x2_send = [2 * int(cA0[r] * n1 * npad2[me]) for r in range(W)]
+        self.x2_recv = [2 * int(cA0[me] * n1 * npad2[q]) for q in range(W)]
+        self._s0 = self.rt.zeros((2 * self.scratch_elems,), self.dtype)
+        self._s1 = self.rt.zeros((2 * self.scratch_elems,), self.dtype)
+        self.rt.api.call("nb200_plan_set_scratch", self._h, self.rt.ptr(self._s0), self.rt.ptr(self._s1))
+        rows = np.zeros(self.rows0, dtype=np.int32)
+        planes = np.zeros(self.planes2, dtype=np.int32)
+        self.rt.api.call("nb200_plan_local_map", self._h, 0, rows.ctypes.data_as(C.c_void_p))
+        self.rt.api.call("nb200_plan_local_map", self._h, 2, planes.ctypes.data_as(C.c_void_p))
+        self.row_map, self.plane_map = rows, planes          # local -> global index, -1 = zero padding
+
+    def exchange(self, which: int):
+        """All-to-all between the local passes: 1 = S1 -> S0 (before the axis-0 pass), 2 = S0 -> S1."""
+        if which == 1:
+            self.comm.all_to_all(self._s0, self._s1, self.x1_recv, self.x1_send)
+        else:
+            self.comm.all_to_all(self._s1, self._s0, self.x2_recv, self.x2_send)
+
+    def scatter_latent(self, xi_global) -> torch.Tensor:
+        """Rows of a global natural-order grid array owned by this rank (zero padding rows)."""
+        g = self.rt.asarray(xi_global, self.dtype)
+        out = self.rt.zeros(self.local_shape, self.dtype)
+        idx = torch.as_tensor(self.row_map.astype(np.int64), device=self.rt.device)
+        ok = idx >= 0
+        out[ok] = g[idx[ok]]
+        return out
+
+    def scatter_position(self, pos_global) -> torch.Tensor:
+        """Planes x2 of a global natural-order position array owned by this rank, in [x2][x1][x0] layout."""
+        g = self.rt.asarray(pos_global, self.dtype).permute(2, 1, 0)
+        out = self.rt.zeros(self.local_pos_shape, self.dtype)
+        idx = torch.as_tensor(self.plane_map.astype(np.int64), device=self.rt.device)
+        ok = idx >= 0
+        out[ok] = g[idx[ok]]
+        return out.contiguous()
+
+    def gather_latent(self, local) -> torch.Tensor:
+        """Inverse of scatter_latent on every rank (all-gather; for tests and small grids)."""
+        return self._gather(local.reshape(self.local_shape), 0)
+
+    def gather_position(self, local) -> torch.Tensor:
+        return self._gather(local.reshape(self.local_pos_shape), 2).permute(2, 1, 0).contiguous()
+
+    def _gather(self, local, axis):
+        W = self.comm.world
+        n = self.shape[axis]
+        nloc = torch.tensor([local.shape[0]], dtype=torch.int64, device=self.rt.device)
+        sizes = [int(x) for x in self.comm.all_gather_obj(int(local.shape[0]))]
+        maps = self.comm.all_gather_obj((self.row_map if axis == 0 else self.plane_map).tolist())
+        mx = max(sizes)
+        pad = self.rt.zeros((mx,) + tuple(local.shape[1:]), self.dtype)
+        pad[:local.shape[0]] = local
+        parts = self.comm.all_gather(pad)
+        out = self.rt.zeros((n,) + tuple(local.shape[1:]), self.dtype)
+        for p in range(W):
+            m = torch.as_tensor(np.asarray(maps[p], dtype=np.int64), device=self.rt.device)
+            ok = m >= 0
+            out[m[ok]] = parts[p][:sizes[p]][ok]
+        return out
 
     def __del__(self):
         try:
@@ -197,6 +319,8 @@ class ModelHandle:
                          float(w_scalar), self.rt.ptr(w))
 
     def cf_forward(self, pos: torch.Tensor) -> torch.Tensor:
+        if self.plan.dist:
+            raise NB200Error("cf_forward is not available on slab-decomposed plans; linearise and read the signal")
         out = self.rt.empty(self.plan.shape, self.plan.dtype)
         self.rt.api.call("nb200_cf_forward", self._h, self.rt.stream(), self.rt.ptr(pos), self.rt.ptr(out))
         return out
@@ -222,9 +346,35 @@ class Lin:
         return self.rt.empty((self.model.L,), self.model.plan.dtype)
 
     def _pos(self):
-        return self.rt.empty(self.model.plan.shape, self.model.plan.dtype)
+        return self.rt.empty(self.model.plan.local_pos_shape, self.model.plan.dtype)
+
+    # -- slab-decomposed sequences: local phases (nb200_dist_phase) + host collectives ------------------
+    def _phase(self, code, other=None, inp=None, out=None, flag=0):
+        self.rt.api.call("nb200_dist_phase", self._h, None if other is None else other._h, self.rt.stream(), int(code),
+                         self.rt.ptr(inp), self.rt.ptr(out), self.rt.ptr(self._abar), self.rt.ptr(self._xs), int(flag))
+
+    def _dist_buffers(self):
+        if not hasattr(self, "_abar"):
+            self._abar = self.rt.zeros((self.model.plan.K,), self.model.plan.dtype)
+            self._xs = self.rt.zeros((4,), self.model.plan.dtype)
+
+    def _dist_adjoint_tail(self, t, out, add_identity, scaled):
+        plan = self.model.plan
+        self._phase(5, inp=t if add_identity else None, out=out, flag=int(add_identity))
+        plan.comm.allreduce_sum(self._abar)
+        plan.comm.allreduce_sum(self._xs)
+        self._phase(6, inp=t if add_identity else None, out=out, flag=int(add_identity) | (2 if scaled else 0))
+        return out
 
     def update(self, pos: torch.Tensor, want_grad=False, add_prior=False):
+        if self.model.plan.dist:
+            if want_grad:
+                raise NB200Error("gradients are not available on slab-decomposed plans yet")
+            self._dist_buffers()
+            self._phase(0, inp=pos)
+            self.model.plan.exchange(1)
+            self._phase(1)
+            return None
         grad = self._vec() if want_grad else None
         self.rt.api.call("nb200_lin_update", self._h, self.rt.stream(), self.rt.ptr(pos), self.rt.ptr(grad), int(add_prior))
         return grad
@@ -232,6 +382,9 @@ class Lin:
     def energy(self) -> float:
         e = C.c_double()
         self.rt.api.call("nb200_lin_energy", self._h, self.rt.stream(), C.byref(e))
+        if self.model.plan.dist:
+            t = torch.tensor([e.value], dtype=torch.float64, device=self.rt.device)
+            return float(self.model.plan.comm.allreduce_sum(t))
         return e.value
 
     def amplitude(self):
@@ -246,6 +399,13 @@ class Lin:
 
     def metric(self, t, add_identity=False, out=None):
         out = self._vec() if out is None else out
+        if self.model.plan.dist:
+            plan = self.model.plan
+            self._phase(2, inp=t)
+            plan.exchange(1)
+            self._phase(3, inp=t)
+            plan.exchange(2)
+            return self._dist_adjoint_tail(t, out, add_identity, True)
         self.rt.api.call("nb200_metric", self._h, self.rt.stream(), self.rt.ptr(t), self.rt.ptr(out), int(add_identity))
         return out
 
@@ -263,6 +423,10 @@ class Lin:
     def lsm(self, u, scaled=True):
         out = self._vec()
         u = self.rt.asarray(u, self.model.plan.dtype)
+        if self.model.plan.dist:      # u: local planes in the internal [x2][x1][x0] layout
+            self._phase(4, inp=u, flag=int(scaled))
+            self.model.plan.exchange(2)
+            return self._dist_adjoint_tail(None, out, False, scaled)
         self.rt.api.call("nb200_lsm", self._h, self.rt.stream(), self.rt.ptr(u), self.rt.ptr(out), int(scaled))
         return out
 

@@ -33,7 +33,7 @@ class CorrelatedField:
         self._desc_fields = dict(desc_fields)
         self.domain = dict(sorted(domain.items()))
         self.layout = Layout(self.domain)
-        self.target_shape = plan.shape
+        self.target_shape = plan.local_pos_shape
         self.dtype = plan.dtype
         self._handle: Optional[ModelHandle] = None
 
@@ -81,9 +81,10 @@ class CorrelatedFieldMaker:
     """Builder with the call protocol of ``jft.CorrelatedFieldMaker`` (correlated_field.py:519-920)."""
 
     def __init__(self, prefix: str, *, dtype=torch.float64, hartley_convention="non_canonical_hartley",
-                 runtime: Optional[Runtime] = None):
+                 runtime: Optional[Runtime] = None, comm=None):
+        """``comm``: torch.distributed group over which a 3-D grid is slab-decomposed (one process per GPU)."""
         self._prefix = prefix
-        self._dtype, self._conv, self._rt = dtype, hartley_convention, runtime
+        self._dtype, self._conv, self._rt, self._comm = dtype, hartley_convention, runtime, comm
         self._offset_mean = None
         self._azm = None
         self._fluct = []
@@ -126,7 +127,8 @@ class CorrelatedFieldMaker:
         if not self._fluct:
             raise ValueError("add_fluctuations must be called before finalize")
         f = self._fluct[0]
-        plan = Plan(f["shape"], f["distances"], dtype=self._dtype, hartley_convention=self._conv, runtime=self._rt)
+        plan = Plan(f["shape"], f["distances"], dtype=self._dtype, hartley_convention=self._conv, runtime=self._rt,
+                    comm=self._comm)
         sp = self._prefix + f["prefix"]
         has_dev = f["flx"] is not None and plan.K > 2
         domain = dict(self._parameter_tree)
@@ -138,7 +140,7 @@ class CorrelatedFieldMaker:
             if f["asp"] is not None:
                 domain[sp + "asperity"] = ()
             domain[sp + "spectrum"] = (plan.K - 2, 2)
-        domain[self._prefix + "xi"] = plan.shape
+        domain[self._prefix + "xi"] = plan.local_shape     # the rows this rank owns when slab-decomposed
         fields = dict(kind_power=int(f["kind"] == "power"), has_fluctuations=int(f["flu"] is not None),
                       has_deviations=int(has_dev), has_asperity=int(has_dev and f["asp"] is not None))
         fields["zeromode_a"], fields["zeromode_b"] = self._azm.ab()

@@ -372,6 +372,7 @@ template <class T> struct JvpOut {
 template <class T> struct SegSumParams {
   AmpModel<T> m; const T* W; const int* order; const int* offs; const T* amp;
   T* g; T* abar /* optional raw bin sums */; T* partials /* [nblk][2] */; unsigned* counter; T* scal;
+  const T* abar_in;   // if set: skip the gather, take the (all-reduced) bin sums from here
   int lg_lpb;   // log2(lanes per bin); 256 threads -> 256 >> lg_lpb bins per block
 };
 template <class T> struct SegSumBody {
@@ -385,7 +386,9 @@ template <class T> struct SegSumBody {
       long b = b0 + (i >> p.lg_lpb);
       int lane = i & (lpb - 1);
       T s = 0;
-      if (b < m.K) {
+      if (p.abar_in) {
+        if (b < m.K && lane == 0) s = p.abar_in[b];
+      } else if (b < m.K) {
         int beg = p.offs[b], end = p.offs[b + 1];
         int q = beg + lane;
         for (; q + 3 * lpb < end; q += 4 * lpb) {     // four independent index -> value chains in flight

@@ -31,7 +31,7 @@ template <class T> void Model<T>::init(Plan<T>* plan_, const nb200_model_desc& d
   auto chk = [&](int64_t off, int64_t len, const char* nm) {
     if (off < 0 || off + len > d.latent_size) throw Error{std::string("nb200: leaf offset out of range: ") + nm};
   };
-  chk(d.off_xi, g.N, "xi"); chk(d.off_zeromode, 1, "zeromode"); chk(d.off_slope, 1, "loglogavgslope");
+  chk(d.off_xi, P->local_latent_grid(), "xi"); chk(d.off_zeromode, 1, "zeromode"); chk(d.off_slope, 1, "loglogavgslope");
   if (am.has_flu) chk(d.off_fluct, 1, "fluctuations");
   if (am.has_dev) { chk(d.off_flex, 1, "flexibility"); chk(d.off_spectrum, 2 * (int64_t)(g.K - 2), "spectrum"); }
   if (am.has_dev && am.has_asp) chk(d.off_asp, 1, "asperity");
@@ -50,7 +50,7 @@ template <class T> void Model<T>::init(Plan<T>* plan_, const nb200_model_desc& d
   np = std::max<size_t>(np, 4 * 2048);
   partials.alloc(np);
   counters.alloc(16);
-  tmp_pos.alloc((size_t)g.N);
+  tmp_pos.alloc((size_t)P->local_position_grid());
   scratch_lin = new Lin<T>();
   scratch_lin->init(this);
 }
@@ -201,6 +201,63 @@ int nb200_plan_power_distributor(const nb200_plan* plan, int32_t* out) {
   return 0;
 }
 
+int nb200_plan_create_dist(nb200_plan** plan, int device, int ndim, const int64_t* shape_host, const double* distances_host,
+                           int dtype, int hartley_convention, int rank, int world) {
+  NB_TRY
+  if (!plan) return fail("nb200_plan_create_dist: null output");
+  if (dtype != 0 && dtype != 1) return fail("nb200_plan_create_dist: dtype must be 0 (float32) or 1 (float64)");
+  if (ndim != 3) return fail("nb200_plan_create_dist: slab decomposition needs a 3-D grid");
+  if (world < 1 || rank < 0 || rank >= world) return fail("nb200_plan_create_dist: invalid rank / world");
+#ifndef NB_EMU
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device)
+    return fail("nb200_plan_create_dist: no CUDA device available (there is no CPU fallback)");
+#endif
+  std::unique_ptr<nb200_plan> h(new nb200_plan{nullptr});
+  NB_DISPATCH(dtype, TT, { auto* p = new Plan<TT>(); h->impl = p; p->init(device, ndim, shape_host, distances_host, hartley_convention, rank, world); })
+  *plan = h.release();
+  return 0;
+  NB_CATCH
+}
+int nb200_plan_dist_info(const nb200_plan* plan, int64_t* out, int64_t nout) {
+  const PlanBase& p = *plan->impl;
+  std::vector<int64_t> v = {p.rank, p.world, p.rows0, p.planes2, p.scratch_elems, p.g.n0, p.g.nm, p.g.nl, p.g.K};
+  for (int r = 0; r < p.world; ++r) v.push_back(p.dist ? p.d0.npad[r] : p.g.n0);
+  for (int r = 0; r < p.world; ++r) v.push_back(p.dist ? p.d2.npad[r] : p.g.nl);
+  for (int r = 0; r < p.world; ++r) v.push_back(p.dist ? p.d0.cA[r] : p.g.h0 + 1);
+  for (int r = 0; r < p.world; ++r) v.push_back(p.dist ? p.d2.cA[r] : p.g.hl + 1);
+  if ((int64_t)v.size() > nout) return fail("nb200_plan_dist_info: output too small");
+  std::copy(v.begin(), v.end(), out);
+  return 0;
+}
+int nb200_plan_local_map(const nb200_plan* plan, int axis, int32_t* out_host) {
+  const PlanBase& p = *plan->impl;
+  if (!p.dist) return fail("nb200_plan_local_map: not a slab-decomposed plan");
+  std::vector<int> m = (axis == 0) ? p.d0.loc2glob(p.rank) : p.d2.loc2glob(p.rank);
+  std::copy(m.begin(), m.end(), out_host);
+  return 0;
+}
+int nb200_plan_set_scratch(nb200_plan* plan, void* s0, void* s1) {
+  NB_TRY
+  NB_DISPATCH(plan->impl->dtype, TT, { auto* P = static_cast<Plan<TT>*>(plan->impl); P->xS0 = (cplx<TT>*)s0; P->xS1 = (cplx<TT>*)s1; })
+  return 0;
+  NB_CATCH
+}
+int nb200_dist_phase(nb200_lin* lin_a, nb200_lin* lin_b, void* stream, int code, const void* in, void* out, void* abar, void* xs,
+                     int flag) {
+  NB_TRY
+  if (!lin_a) return fail("nb200_dist_phase: null linearisation");
+  if (lin_b && lin_b->model != lin_a->model) return fail("nb200_dist_phase: linearisations of different models");
+  NB_DISPATCH(lin_a->dtype, TT, {
+    Lin<TT>* a = static_cast<Lin<TT>*>(lin_a->impl);
+    Lin<TT>* b = lin_b ? static_cast<Lin<TT>*>(lin_b->impl) : a;
+    if (code == 2) b->dist_phase((stream_t)stream, code, b, (const TT*)in, (TT*)out, (TT*)abar, (TT*)xs, flag);   // tangent side
+    else a->dist_phase((stream_t)stream, code, b, (const TT*)in, (TT*)out, (TT*)abar, (TT*)xs, flag);
+  })
+  return 0;
+  NB_CATCH
+}
+
 int nb200_hartley(nb200_plan* plan, void* stream, const void* in, void* out) {
   NB_TRY
   NB_DISPATCH(plan->impl->dtype, TT, { static_cast<Plan<TT>*>(plan->impl)->hartley((stream_t)stream, (const TT*)in, (TT*)out); })
@@ -256,10 +313,17 @@ int nb200_model_set_likelihood(nb200_model* model, void* stream, int kind, int n
     if (nonlinearity == 0 && m.am.has_scaling) return fail("nb200: scaling requires the exp non-linearity");
     stream_t st = (stream_t)stream;
     m.lh_kind = kind; m.nl_exp = nonlinearity; m.w_scalar = (TT)noise_cov_inv_scalar;
-    m.data.alloc((size_t)m.P->g.N);
-    if (data) m.P->run_rev(st, (const TT*)data, m.data.p, true);
+    const size_t npos = (size_t)m.P->local_position_grid();
+    m.data.alloc(npos);
     m.has_w_arr = noise_cov_inv_array != nullptr;
-    if (m.has_w_arr) { m.w_arr.alloc((size_t)m.P->g.N); m.P->run_rev(st, (const TT*)noise_cov_inv_array, m.w_arr.p, true); }
+    if (m.has_w_arr) m.w_arr.alloc(npos);
+    if (m.P->dist) {   // slab-decomposed plans take the LOCAL planes in the internal reversed-axis layout
+      if (data) d2d(m.data.p, data, npos * sizeof(TT), st);
+      if (m.has_w_arr) d2d(m.w_arr.p, noise_cov_inv_array, npos * sizeof(TT), st);
+    } else {
+      if (data) m.P->run_rev(st, (const TT*)data, m.data.p, true);
+      if (m.has_w_arr) m.P->run_rev(st, (const TT*)noise_cov_inv_array, m.w_arr.p, true);
+    }
     stream_sync(st);
     m.have_lh = true;
   })

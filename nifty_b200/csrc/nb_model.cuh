@@ -77,7 +77,7 @@ template <class T> struct Lin : LinBase {
     M = m; model = m;
     const GridInfo& g = m->P->g;
     pos.alloc((size_t)m->am.L); amp.alloc(g.K); wS.alloc(g.K); Pb.alloc(g.K);
-    s.alloc((size_t)g.N); jl.alloc((size_t)g.N); scal.alloc(SC_COUNT);
+    s.alloc((size_t)m->P->local_position_grid()); jl.alloc((size_t)m->P->local_position_grid()); scal.alloc(SC_COUNT);
   }
 
   // forward amplitude chain at this->pos
@@ -119,18 +119,22 @@ template <class T> struct Lin : LinBase {
     return pro;
   }
 
-  // cotangent chain after P5 filled W: segment sum, reverse scan, scalar leaves, dot product
-  void amp_cotangent(stream_t st, T* out, const T* add, int p3_col, T scl_factor, bool use_p5_dot) {
-    Model<T>& m = *M; Plan<T>& P = *m.P; const int K = m.am.K;
+  // cotangent chain after P5 filled W: segment sum, reverse scan, scalar leaves, dot product.
+  // Distributed plans run it in two halves around an all-reduce of the bin sums (abar) and of the two
+  // scalars xs = {sum of the position-space cotangent, xi-block of <add, out>}.
+  void seg_sum(stream_t st, T* abar_out, const T* abar_in) {
+    Model<T>& m = *M; Plan<T>& P = *m.P;
     SegSumParams<T> ps; ps.m = m.am; ps.W = P.W.p; ps.order = P.w_order.p; ps.offs = P.w_offs.p; ps.amp = amp.p;
-    ps.g = m.gbuf.p; ps.abar = nullptr; ps.partials = m.partials.p; ps.counter = m.counters.p + 3; ps.scal = scal.p;
-    ps.lg_lpb = P.seg_lg_lpb;
+    ps.g = abar_out ? nullptr : m.gbuf.p; ps.abar = abar_out; ps.abar_in = abar_in; ps.partials = m.partials.p;
+    ps.counter = m.counters.p + 3; ps.scal = scal.p; ps.lg_lpb = P.seg_lg_lpb;
     launch<SegSumBody<T>>(P.seg_grid(), 256, (256 + 64) * sizeof(T), st, ps);
+  }
+  void vjp_chain(stream_t st, T* out, const T* add, const T* p3_src, int n_p3, const T* p5_src, int n_p5, T scl_factor) {
+    Model<T>& m = *M; const int K = m.am.K;
     const long nj = m.am.has_dev ? (long)K - 2 : 0;
     VjpOut<T> vo; vo.m = m.am; vo.pos = pos.p; vo.g = m.gbuf.p; vo.wS = wS.p; vo.scal_in = scal.p; vo.out = out; vo.add = add;
     vo.partials = m.partials.p; vo.counter = m.counters.p + 4; vo.scal = scal.p;
-    vo.p3_partials = P.p3part.p + p3_col; vo.n_p3 = P.c3.grid;
-    vo.p5_partials = P.p5part.p; vo.n_p5 = use_p5_dot ? P.c5.grid : 0; vo.scl_factor = scl_factor;
+    vo.p3_partials = p3_src; vo.n_p3 = n_p3; vo.p5_partials = p5_src; vo.n_p5 = n_p5; vo.scl_factor = scl_factor;
     if (nj > 0) {
       VjpElem<T> el; el.m = m.am; el.g = m.gbuf.p; el.wS = wS.p; el.scal = scal.p;
       if (m.nchunksJ > 1) {
@@ -143,6 +147,11 @@ template <class T> struct Lin : LinBase {
       ScanApplyParams<T, NoElem<T>, VjpOut<T>> pc; pc.n = 0; pc.out = vo; pc.pre = nullptr; pc.nchunks = 1;
       launch<ScanApplyBody<T, NoElem<T>, VjpOut<T>>>(1, SCAN_NT, m.scan_smem(), st, pc);
     }
+  }
+  void amp_cotangent(stream_t st, T* out, const T* add, int p3_col, T scl_factor, bool use_p5_dot) {
+    Plan<T>& P = *M->P;
+    seg_sum(st, nullptr, nullptr);
+    vjp_chain(st, out, add, P.p3part.p + p3_col, P.c3.grid, P.p5part.p, use_p5_dot ? P.c5.grid : 0, scl_factor);
   }
   EpiAdjoint<T> epi_adjoint(T* out, const T* add, bool want_dot) const {
     const Model<T>& m = *M;
@@ -210,14 +219,81 @@ template <class T> struct Lin : LinBase {
     P.run_p5(st, epi_adjoint(out, nullptr, false));
     amp_cotangent(st, out, nullptr, 0, scaled ? m.am.scl_b : T(0), false);
   }
+  // ---- slab-decomposed plans: the operator sequences cut at the two exchanges / the all-reduce -------------
+  // code: 0 update.1 (amplitude, P1, PCa) | 1 update.2 (P3 linearise; local energy) | 2 metric.1 (tangent chain, P1, PCa)
+  //       3 metric.2 (P3 fused, PCb) | 4 lsm.2 (P3 adjoint-only from local T-layout `in`, PCb) | 5 adjoint.3 (P5, local bin sums,
+  //       xs = {p3 sum, xi dot}) | 6 adjoint.4 (finish with all-reduced abar / xs: hyper-parameter leaves, <add,out>)
+  void dist_phase(stream_t st, int code, Lin<T>* b, const T* in, T* out, T* abar, T* xs, int flag) {
+    Model<T>& m = *M; Plan<T>& P = *m.P;
+    if (!P.dist) throw Error{"nb200_dist_phase: not a slab-decomposed plan"};
+    if (!P.xS0 || !P.xS1) throw Error{"nb200_dist_phase: exchange buffers not set (nb200_plan_set_scratch)"};
+    switch (code) {
+      case 0: {
+        if (!m.have_lh) throw Error{"nb200: likelihood not set on this model"};
+        d2d(pos.p, in, (size_t)m.am.L * sizeof(T), st);
+        amp_forward(st);
+        ProAmp<T> pro; pro.xi = pos.p + m.am.off_xi; pro.idxf = P.idxf.p; pro.amp = amp.p; pro.fg = P.fold_geom();
+        P.run_p1(st, pro); P.run_pc(st, false);
+      } break;
+      case 1: {
+        PointOp<T> op = P.make_op(PM_LINEARIZE);
+        op.invV = T(1.0 / P.g.V); op.offset = m.offset_mean; op.sc_ptr = scal.p + SC_SCALING;
+        op.lh_kind = m.lh_kind; op.nl_exp = m.nl_exp; op.data = m.data.p; op.w_scalar = m.w_scalar;
+        op.w_arr = m.has_w_arr ? m.w_arr.p : nullptr; op.s_out = s.p; op.jl_out = jl.p; op.partials = P.p3part.p;
+        P.template run_p3<true, false>(st, op);
+        ReduceColsParams<T> pr; pr.partials = P.p3part.p; pr.n = P.c3.grid; pr.ncol = 2;
+        pr.out0 = scal.p + SC_ENERGY; pr.out1 = scal.p + SC_SUMCOT;
+        launch<ReduceColsBody<T>>(1, 256, 512, st, pr);
+        valid = true;
+      } break;
+      case 2: {
+        if (!valid) throw Error{"nb200: linearisation not initialised"};
+        amp_tangent(st, in);
+        P.run_p1(st, pro_metric(in)); P.run_pc(st, false);
+      } break;
+      case 3: {
+        PointOp<T> op = P.make_op(PM_METRIC);
+        op.invV = T(1.0 / P.g.V); op.jl_a = jl.p; op.jl_b = b->jl.p; op.partials = P.p3part.p;
+        if (m.am.has_scaling) { op.cshift_ptr = in + m.am.off_scl; op.cshift_scale = m.am.scl_b; }
+        P.template run_p3<true, true>(st, op);
+        P.run_pc(st, true);
+      } break;
+      case 4: {
+        PointOp<T> op = P.make_op(PM_LOAD);
+        op.in_pos = in; op.jl_a = flag ? jl.p : nullptr; op.partials = P.p3part.p;
+        P.template run_p3<false, true>(st, op);
+        P.run_pc(st, true);
+      } break;
+      case 5: {
+        P.run_p5(st, epi_adjoint(out, flag ? in : nullptr, flag != 0));
+        seg_sum(st, abar, nullptr);
+        ReduceColsParams<T> pr; pr.partials = P.p3part.p; pr.n = P.c3.grid; pr.ncol = 2; pr.out0 = xs; pr.out1 = nullptr;
+        launch<ReduceColsBody<T>>(1, 256, 512, st, pr);
+        if (flag) {
+          ReduceColsParams<T> pd; pd.partials = P.p5part.p; pd.n = P.c5.grid; pd.ncol = 1; pd.out0 = xs + 1; pd.out1 = nullptr;
+          launch<ReduceColsBody<T>>(1, 256, 512, st, pd);
+        } else {
+          dev_zero(xs + 1, sizeof(T), st);
+        }
+      } break;
+      case 6: {
+        seg_sum(st, nullptr, abar);
+        T sf = (flag & 2) ? m.am.scl_b : T(0);
+        vjp_chain(st, out, (flag & 1) ? in : nullptr, xs, 1, xs + 1, 1, sf);
+      } break;
+      default: throw Error{"nb200_dist_phase: unknown phase code"};
+    }
+  }
+
   void posmap(stream_t st, int mode, T* out_nat) {
     Model<T>& m = *M; Plan<T>& P = *m.P;
     if (!valid) throw Error{"nb200: linearisation not initialised (call nb200_lin_update)"};
     PosMapParams<T> pm; pm.mode = mode; pm.lh_kind = m.lh_kind; pm.n = (long)P.g.N; pm.s = s.p; pm.data = m.data.p;
     pm.w_scalar = m.w_scalar; pm.w_arr = m.has_w_arr ? m.w_arr.p : nullptr; pm.out = m.tmp_pos.p;
     int grid = (int)std::min<int64_t>((P.g.N + 255) / 256, 148 * 8);
+    if (P.dist) pm.out = out_nat;      // slab-decomposed plans hand out the local planes in the internal layout
     launch<PosMapBody<T>>(grid, 256, 0, st, pm);
-    P.run_rev(st, m.tmp_pos.p, out_nat, false);
+    if (!P.dist) P.run_rev(st, m.tmp_pos.p, out_nat, false);
   }
 };
 

@@ -40,8 +40,10 @@ template <bool ALIGNED, class T> NB_HD NB_INLINE void load_pair(const T* p, T& a
 struct FoldGeom {
   int n_o, n_r, n;     // extents of (outer, row, last) axes of the natural array
   int hr1, h1;         // n_r/2+1, n/2+1
+  const int* plane_loc;   // slab-decomposed grids: folded plane of the LOCAL bin table for local row o (else null)
   NB_HD NB_INLINE long base(int o, int rr) const {
-    return ((long)fold_idx(o, n_o) * hr1 + fold_idx(rr, n_r)) * h1;
+    int pl = plane_loc ? ldg(plane_loc + o) : fold_idx(o, n_o);
+    return ((long)pl * hr1 + fold_idx(rr, n_r)) * h1;
   }
 };
 
@@ -207,6 +209,9 @@ template <class T> struct PCParams {
 // raw complex lines (stride `rstride` between the lines of a CTA); inactive lines read as zero
 template <class T> struct RawLoader {
   const cplx<T>* base; long rstride; const struct LineInfo* li;
+  // slab-decomposed grids: after the all-to-all a line is a sequence of per-rank chunks; element x of
+  // line l lives at chunk_base[src_off[x]] + l * src_mul[x]  (src_off includes the offset inside the chunk)
+  const long* src_off; const int* src_mul; const cplx<T>* chunk_base; int l0;
   template <int NQ> NB_HD NB_INLINE void batch(int r, int j, int lmr, cplx<T>* a) const;
 };
 
@@ -218,7 +223,7 @@ template <class T> struct PCBody {
     const int gpo = p.n_r >> p.lg_R;
     const int o = ctx.bid / gpo, rr0 = (ctx.bid % gpo) << p.lg_R;
     const cplx<T>* inp = p.in + o * p.in_ostride + rr0 * p.in_rstride;
-    RawLoader<T> ld{inp, p.in_rstride, nullptr};          // R divides n_r: no bounds check
+    RawLoader<T> ld{inp, p.in_rstride, nullptr, nullptr, nullptr, nullptr, 0};          // R divides n_r: no bounds check
     fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
     cplx<T>* outp = p.out + o * p.out_ostride + rr0;
     NB_FOR(ctx, i, n << p.lg_R) {
@@ -234,15 +239,31 @@ template <class T> struct PCBody {
 // ---------------------------------------------------------------------------------------------
 struct MirrorGeom {
   int n_a, h_a, lg_mid;
-  NB_HD NB_INLINE int nlines() const { return (h_a + 1) << lg_mid; }
-  // returns false if the line is handled by its (stored) partner; lB = -1 for self-mirrored lines
+  // slab decomposition of the `a` axis (dist != 0): this rank owns the planes a = a0 .. a0+cA-1 of the
+  // half range [0, h_a] ("A" planes, stored first) and their mirrors n_a - a ("B" planes, stored behind
+  // them in the same order; a = 0 and a = h_a have none).  skip = 1 if a = 0 is owned (its B is missing).
+  int dist, a0, cA, skip;
+  NB_HD NB_INLINE int nlines() const { return (dist ? cA : (h_a + 1)) << lg_mid; }
+  // returns false if the line is handled by its (stored) partner; lB = -1 for self-mirrored lines.
+  // lA / lB index real lines of the (local) position / latent array: plane * n_mid + km.
   NB_HD NB_INLINE bool resolve(int l, int& lA, int& lB) const {
     int a = l >> lg_mid, km = l & ((1 << lg_mid) - 1);
-    int ma = neg_idx(a, n_a), mkm = neg_idx(km, 1 << lg_mid);
+    int mkm = neg_idx(km, 1 << lg_mid);
     lA = l;
-    lB = (ma << lg_mid) + mkm;
-    if (lB == lA) { lB = -1; return true; }
-    if (ma <= h_a && lB < lA) return false;
+    if (!dist) {
+      int ma = neg_idx(a, n_a);
+      lB = (ma << lg_mid) + mkm;
+      if (lB == lA) { lB = -1; return true; }
+      if (ma <= h_a && lB < lA) return false;
+      return true;
+    }
+    int ga = a0 + a;
+    if (ga == 0 || 2 * ga == n_a) {          // self-mirrored plane: the partner line lives in the same plane
+      lB = (a << lg_mid) + mkm;
+      if (lB == lA) { lB = -1; return true; }
+      return lB > lA;
+    }
+    lB = ((cA + a - skip) << lg_mid) + mkm;
     return true;
   }
 };
@@ -257,6 +278,12 @@ NB_HD NB_INLINE void RawLoader<T>::batch(int r, int j, int lmr, cplx<T>* a) cons
   if (li && !li[r].active) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) a[q] = cmake<T>(0, 0);
+    return;
+  }
+  if (src_off) {
+    const long l = l0 + r;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) { int x = j + (q << lmr); a[q] = chunk_base[ldg(src_off + x) + l * ldg(src_mul + x)]; }
     return;
   }
 #pragma unroll
@@ -362,7 +389,8 @@ template <class T> struct P3Params {
   const cplx<T>* tw; int lg_tw;
   FftDev fft;
   T hsign;                 // +1: Re+Im (non_canonical_hartley), -1: Re-Im
-  const cplx<T>* in;       // [l][n]
+  const cplx<T>* in;       // [l][n]   (or the all-to-all receive buffer when src_off != null)
+  const long* src_off; const int* src_mul;
   cplx<T>* out;            // [k in 0..n/2][out_kstride]
   long out_kstride;
   int ahead;
@@ -417,7 +445,7 @@ template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
       if (p.ahead > 0 && ctx.bid + p.ahead < ctx.nblk)
         prefetch_l2(ctx, p.in + ((long)(ctx.bid + p.ahead) << (p.lg_R + p.lg_n)), sizeof(cplx<T>) << (p.lg_R + p.lg_n));
       const cplx<T>* inp = p.in + (long)l0 * n;
-      RawLoader<T> ld{inp, (long)n, li};
+      RawLoader<T> ld{inp, (long)n, li, p.src_off, p.src_mul, p.in, l0};
       fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
       if (n == 1) {
         NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], 0, 0, cshift, scv, acc0, acc1);
@@ -604,7 +632,8 @@ template <class T, class Epi> struct P5Params {
   const cplx<T>* tw; int lg_tw;
   FftDev fft;
   T hsign;
-  const cplx<T>* in;   // [l][n]
+  const cplx<T>* in;   // [l][n]   (or the all-to-all receive buffer when src_off != null)
+  const long* src_off; const int* src_mul;
   int ahead;
   Epi epi;
 };
@@ -638,7 +667,7 @@ template <class T, class Epi> struct P5Body {
     if (p.ahead > 0 && ctx.bid + p.ahead < ctx.nblk)
       prefetch_l2(ctx, p.in + ((long)(ctx.bid + p.ahead) << (p.lg_R + p.lg_n)), sizeof(cplx<T>) << (p.lg_R + p.lg_n));
     const cplx<T>* inp = p.in + (long)l0 * n;
-    RawLoader<T> ld{inp, (long)n, li};
+    RawLoader<T> ld{inp, (long)n, li, p.src_off, p.src_mul, p.in, l0};
     fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
     if (n == 1) {
       NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], 0, 0, acc);

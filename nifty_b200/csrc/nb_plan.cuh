@@ -124,9 +124,46 @@ struct GridInfo {
   }
 };
 
+// Slab ownership of one axis of extent n over P ranks (3-D grids too large for one GPU).  The half range
+// [0, n/2] is cut into P contiguous pieces of c = n/(2P) indices (the last piece also takes n/2); a rank
+// owns its piece ("A" planes) and the mirrors n - a of those planes ("B" planes, a = 0 and n/2 have none),
+// so the Hermitian partner of every line it transforms is local.  Local order: A planes ascending, then the
+// B planes in the order of their partners; the count is padded to a multiple of 16 with zero planes.
+struct AxisDist {
+  int n = 0, P = 1, c = 0;
+  std::vector<int> a0, cA, cB, skip, npad;   // per rank
+  std::vector<int> owner, lidx;              // per global index
+  void build(int n_, int P_) {
+    n = n_; P = P_; c = n / (2 * P);
+    a0.resize(P); cA.resize(P); cB.resize(P); skip.resize(P); npad.resize(P);
+    owner.assign(n, -1); lidx.assign(n, -1);
+    for (int r = 0; r < P; ++r) {
+      a0[r] = r * c; cA[r] = c + (r == P - 1 ? 1 : 0); skip[r] = (r == 0) ? 1 : 0; cB[r] = c - skip[r];
+      npad[r] = ((cA[r] + cB[r] + 15) / 16) * 16;
+      for (int i = 0; i < cA[r]; ++i) {
+        int a = a0[r] + i;
+        owner[a] = r; lidx[a] = i;
+        if (a != 0 && 2 * a != n) { owner[n - a] = r; lidx[n - a] = cA[r] + i - skip[r]; }
+      }
+    }
+  }
+  // local -> global index of rank r (-1 for padding)
+  std::vector<int> loc2glob(int r) const {
+    std::vector<int> m(npad[r], -1);
+    for (int x = 0; x < n; ++x) if (owner[x] == r) m[lidx[x]] = x;
+    return m;
+  }
+};
+
 struct PlanBase {
   int dtype = 1, device = 0, hconv = 0;
   GridInfo g;
+  // slab decomposition (3-D only): axis 0 of the latent array, last axis (= x2 planes) of position space
+  bool dist = false;
+  int rank = 0, world = 1;
+  AxisDist d0, d2;
+  int rows0 = 0, planes2 = 0;        // local (padded) extents; = n0 / nl when not distributed
+  int64_t scratch_elems = 0;         // complex elements each exchange / scratch buffer must hold
   virtual ~PlanBase() {}
 };
 
@@ -161,7 +198,9 @@ template <class T> struct Plan : PlanBase {
   int lg0 = 0, lgm = 0, lgl = 0;
   T hsign = 1;
   DevBuf<cplx<T>> tw0, twm, twl, S0, S1;
-  DevBuf<int> idxf, w_order, w_offs, pos0, posm, posl, poslh;
+  DevBuf<int> idxf, w_order, w_offs, pos0, posm, posl, poslh, plane_loc0, src_mul3, src_mul5;
+  DevBuf<long> src_off3, src_off5;
+  cplx<T>* xS0 = nullptr; cplx<T>* xS1 = nullptr;   // host-provided exchange buffers (distributed plans)
   FftDev f0, fm, fl, flh;   // line FFTs of length n0, nm, nl and nl/2
   DevBuf<T> W, p3part, p5part;
   PassCfg c1, cA, c3, cB, c5;
@@ -211,17 +250,60 @@ template <class T> struct Plan : PlanBase {
     return c;
   }
 
-  void init(int device_, int ndim, const int64_t* shp, const double* dst, int hconv_) {
+  void init(int device_, int ndim, const int64_t* shp, const double* dst, int hconv_, int rank_ = 0, int world_ = 1) {
     device = device_; hconv = hconv_;
     dtype = sizeof(T) == 8 ? 1 : 0;
     hsign = hconv ? T(-1) : T(1);
+    rank = rank_; world = world_; dist = world_ > 1;
     dev_set(device);
     if (g.build(ndim, shp, dst)) throw Error{last_error_ref()};
     lg0 = ilog2(g.n0); lgm = ilog2(g.nm); lgl = ilog2(g.nl);
+    rows0 = g.n0; planes2 = g.nl;
+    int cA0 = g.h0 + 1, cA2 = g.hl + 1;      // planes of the half ranges handled by P5 / P3
+    std::vector<int> idxf_loc = g.idxf, w_order_loc = g.w_order, w_offs_loc = g.w_offs;
+    int64_t nW_loc = g.nW;
+    if (dist) {
+      if (!g.three) throw Error{"nb200: slab decomposition needs a 3-D grid"};
+      if (!is_pow2(world) || g.n0 < 2 * world || g.nl < 2 * world) throw Error{"nb200: world size must be a power of two <= n0/2 and <= n2/2"};
+      d0.build(g.n0, world); d2.build(g.nl, world);
+      rows0 = d0.npad[rank]; planes2 = d2.npad[rank];
+      cA0 = d0.cA[rank]; cA2 = d2.cA[rank];
+      const size_t plane = (size_t)(g.hm + 1) * (g.hl + 1);
+      idxf_loc.assign(g.idxf.begin() + (size_t)d0.a0[rank] * plane, g.idxf.begin() + (size_t)(d0.a0[rank] + cA0) * plane);
+      // CSR of the LOCAL partial sums W[(a_loc*nm + km)][x]
+      nW_loc = (int64_t)cA0 * g.nm * (g.hl + 1);
+      w_offs_loc.assign(g.K + 1, 0);
+      auto wbin = [&](int64_t p) {
+        int x = (int)(p % (g.hl + 1)); int64_t l = p / (g.hl + 1);
+        int km = (int)(l % g.nm), a = (int)(l / g.nm);
+        int fm = km <= g.nm - km ? km : g.nm - km;
+        return idxf_loc[((size_t)a * (g.hm + 1) + fm) * (g.hl + 1) + x];
+      };
+      for (int64_t p = 0; p < nW_loc; ++p) w_offs_loc[wbin(p) + 1]++;
+      for (int b = 0; b < g.K; ++b) w_offs_loc[b + 1] += w_offs_loc[b];
+      w_order_loc.resize(nW_loc);
+      std::vector<int> cur(w_offs_loc.begin(), w_offs_loc.end() - 1);
+      for (int64_t p = 0; p < nW_loc; ++p) w_order_loc[cur[wbin(p)]++] = (int)p;
+      // folded plane of the local bin table for every local latent row
+      std::vector<int> pl(rows0, 0);
+      for (int i = 0; i < d0.cA[rank]; ++i) pl[i] = i;
+      for (int i = 0; i < d0.cB[rank]; ++i) pl[d0.cA[rank] + i] = i + d0.skip[rank];
+      plane_loc0.upload(pl);
+      // chunk tables of the two exchanges (element x of line l: recv[src_off[x] + l * src_mul[x]])
+      auto tables = [&](const AxisDist& ax, int my_lines_planes, DevBuf<long>& off, DevBuf<int>& mul) {
+        std::vector<long> roff(world, 0);
+        for (int p = 1; p < world; ++p) roff[p] = roff[p - 1] + (long)my_lines_planes * g.nm * ax.npad[p - 1];
+        std::vector<long> o(ax.n); std::vector<int> m(ax.n);
+        for (int x = 0; x < ax.n; ++x) { o[x] = roff[ax.owner[x]] + ax.lidx[x]; m[x] = ax.npad[ax.owner[x]]; }
+        off.upload(o); mul.upload(m);
+      };
+      tables(d0, cA2, src_off3, src_mul3);   // X1: lines (k2 in my half-range piece, k1) along global j0
+      tables(d2, cA0, src_off5, src_mul5);   // X2: lines (k0 in my piece, k1) along global x2
+    }
     tw0.upload(make_twiddles<T>(g.n0));
     twm.upload(make_twiddles<T>(g.nm));
     twl.upload(make_twiddles<T>(g.nl));
-    idxf.upload(g.idxf); w_order.upload(g.w_order); w_offs.upload(g.w_offs);
+    idxf.upload(idxf_loc); w_order.upload(w_order_loc); w_offs.upload(w_offs_loc);
     auto mk = [&](int lg, DevBuf<int>& buf) {
       std::vector<int> t(size_t(1) << lg);
       fill_pos_table(lg, t.data());
@@ -229,41 +311,62 @@ template <class T> struct Plan : PlanBase {
       return make_fft_dev(lg, buf.p);
     };
     f0 = mk(lg0, pos0); fm = mk(lgm, posm); fl = mk(lgl, posl); flh = mk(lgl - 1, poslh);
-    W.alloc((size_t)g.nW);
+    W.alloc((size_t)nW_loc);
     const int64_t n0 = g.n0, nm = g.nm, nl = g.nl, h0 = g.h0, hl = g.hl;
     size_t sc = 0;
-    if (g.three) sc = (size_t)std::max(n0 * (hl + 1) * nm, (h0 + 1) * nl * nm);
-    else sc = (size_t)std::max((hl + 1) * n0, (h0 + 1) * nl);
-    S0.alloc(sc); S1.alloc(sc);
+    if (dist) {
+      int64_t sum0 = 0, sum2 = 0;
+      for (int p = 0; p < world; ++p) { sum0 += d0.npad[p]; sum2 += d2.npad[p]; }
+      sc = (size_t)std::max(std::max((int64_t)rows0 * (hl + 1) * nm, (int64_t)cA2 * nm * sum0),
+                            std::max((h0 + 1) * (int64_t)planes2 * nm, (int64_t)cA0 * nm * sum2));
+      scratch_elems = (int64_t)sc;           // buffers come from the host (torch tensors, for the all-to-all)
+    } else {
+      if (g.three) sc = (size_t)std::max(n0 * (hl + 1) * nm, (h0 + 1) * nl * nm);
+      else sc = (size_t)std::max((hl + 1) * n0, (h0 + 1) * nl);
+      S0.alloc(sc); S1.alloc(sc);
+      scratch_elems = (int64_t)sc;
+    }
     // P1: real lines of length nl -> complex FFT of nl/2
-    if (g.three) c1 = choose(lgl - 1, nm, n0, false, 0, "NB200_LGR1", 1);
+    if (g.three) c1 = choose(lgl - 1, nm, rows0, false, 0, "NB200_LGR1", 1);
     else c1 = choose(lgl - 1, n0, 1, false, 0, "NB200_LGR1", 1);
     c1.lg_n = lgl;
     if (g.three) {
-      cA = choose(lgm, n0, hl + 1, false, 0, "NB200_LGRC"); cA.lg_n = lgm;
-      cB = choose(lgm, nl, h0 + 1, false, 0, "NB200_LGRC"); cB.lg_n = lgm;
+      cA = choose(lgm, rows0, hl + 1, false, 0, "NB200_LGRC"); cA.lg_n = lgm;
+      cB = choose(lgm, planes2, h0 + 1, false, 0, "NB200_LGRC"); cB.lg_n = lgm;
     }
-    c3 = choose(lg0, 0, 0, true, (hl + 1) * nm, "NB200_LGR3"); c3.lg_n = lg0;
-    c5 = choose(lgl, 0, 0, true, (h0 + 1) * nm, "NB200_LGR5"); c5.lg_n = lgl;
+    c3 = choose(lg0, 0, 0, true, (int64_t)cA2 * nm, "NB200_LGR3"); c3.lg_n = lg0;
+    c5 = choose(lgl, 0, 0, true, (int64_t)cA0 * nm, "NB200_LGR5"); c5.lg_n = lgl;
     {
-      double avg = (double)g.nW / (double)g.K;
+      double avg = (double)nW_loc / (double)g.K;
       seg_lg_lpb = 0;
       while (seg_lg_lpb < 6 && (1 << (seg_lg_lpb + 1)) <= avg / 3.0) ++seg_lg_lpb;   // ~3-6 entries per lane
     }
     p3part.alloc((size_t)2 * c3.grid);
     p5part.alloc((size_t)c5.grid);
   }
+  cplx<T>* s0() { return dist ? xS0 : S0.p; }
+  cplx<T>* s1() { return dist ? xS1 : S1.p; }
+  int64_t local_latent_grid() const { return (int64_t)rows0 * g.nm * g.nl; }     // xi entries held by this rank
+  int64_t local_position_grid() const { return (int64_t)planes2 * g.nm * g.n0; }
 
   FoldGeom fold_geom() const {
     FoldGeom f;
     if (g.three) { f.n_o = g.n0; f.n_r = g.nm; } else { f.n_o = 1; f.n_r = g.n0; }
     f.n = g.nl; f.hr1 = f.n_r / 2 + 1; f.h1 = g.hl + 1;
+    f.plane_loc = dist ? plane_loc0.p : nullptr;
     return f;
   }
-  MirrorGeom mg3() const { MirrorGeom m; m.n_a = g.nl; m.h_a = g.hl; m.lg_mid = lgm; return m; }
-  MirrorGeom mg5() const { MirrorGeom m; m.n_a = g.n0; m.h_a = g.h0; m.lg_mid = lgm; return m; }
-  cplx<T>* p3_in() { return g.three ? S1.p : S0.p; }
-  cplx<T>* p3_out() { return g.three ? S0.p : S1.p; }
+  MirrorGeom mgeom(int n_a, int h_a, const AxisDist& ax) const {
+    MirrorGeom m; m.n_a = n_a; m.h_a = h_a; m.lg_mid = lgm; m.dist = dist ? 1 : 0; m.a0 = 0; m.cA = 0; m.skip = 0;
+    if (dist) { m.a0 = ax.a0[rank]; m.cA = ax.cA[rank]; m.skip = ax.skip[rank]; }
+    return m;
+  }
+  MirrorGeom mg3() const { return mgeom(g.nl, g.hl, d2); }
+  MirrorGeom mg5() const { return mgeom(g.n0, g.h0, d0); }
+  // buffer roles.  single GPU: P1->S0, PCa S0->S1, P3 S1->S0 (2-D: S0->S1), PCb S0->S1, P5 reads S1.
+  // distributed:  P1->S0, PCa S0->S1, [all-to-all S1->S0], P3 S0->S1, PCb S1->S0, [all-to-all S0->S1], P5 reads S1.
+  cplx<T>* p3_in() { return dist ? s0() : (g.three ? s1() : s0()); }
+  cplx<T>* p3_out() { return dist ? s1() : (g.three ? s0() : s1()); }
 
   PointOp<T> make_op(int mode) const {
     PointOp<T> op;
@@ -275,9 +378,9 @@ template <class T> struct Plan : PlanBase {
 
   template <class Pro> void run_p1(stream_t st, const Pro& pro) {
     P1Params<T, Pro> p;
-    p.lg_n = lgl; p.lg_R = c1.lg_R; p.pitch = c1.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = flh; p.out = S0.p; p.ahead = c1.ahead; p.pro = pro;
+    p.lg_n = lgl; p.lg_R = c1.lg_R; p.pitch = c1.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = flh; p.out = s0(); p.ahead = c1.ahead; p.pro = pro;
     if (g.three) {
-      p.n_o = g.n0; p.n_r = g.nm; p.in_ostride = (long)g.nm * g.nl; p.in_rstride = g.nl;
+      p.n_o = rows0; p.n_r = g.nm; p.in_ostride = (long)g.nm * g.nl; p.in_rstride = g.nl;
       p.out_ostride = (long)(g.hl + 1) * g.nm; p.out_kstride = g.nm;
     } else {
       p.n_o = 1; p.n_r = g.n0; p.in_ostride = 0; p.in_rstride = g.nl; p.out_ostride = 0; p.out_kstride = g.n0;
@@ -289,20 +392,22 @@ template <class T> struct Plan : PlanBase {
     if (!g.three) return;
     PCParams<T> p;
     const PassCfg& c = second ? cB : cA;
-    p.lg_n = lgm; p.lg_R = c.lg_R; p.pitch = c.pitch; p.tw = twm.p; p.lg_tw = lgm; p.fft = fm; p.in = S0.p; p.out = S1.p;
-    if (!second) {   // [j0][k2][j1] -> [k2][k1][j0]
-      p.n_o = g.hl + 1; p.n_r = g.n0; p.in_ostride = g.nm; p.in_rstride = (long)(g.hl + 1) * g.nm;
-      p.out_ostride = (long)g.nm * g.n0; p.out_kstride = g.n0;
-    } else {         // [k0][x2][x1] -> [k0][k1][x2]
-      p.n_o = g.h0 + 1; p.n_r = g.nl; p.in_ostride = (long)g.nl * g.nm; p.in_rstride = g.nm;
-      p.out_ostride = (long)g.nm * g.nl; p.out_kstride = g.nl;
+    p.lg_n = lgm; p.lg_R = c.lg_R; p.pitch = c.pitch; p.tw = twm.p; p.lg_tw = lgm; p.fft = fm; p.in = s0(); p.out = s1();
+    if (!second) {   // [j0][k2][j1] -> [k2][k1][j0]   (j0: local rows when distributed)
+      p.n_o = g.hl + 1; p.n_r = rows0; p.in_ostride = g.nm; p.in_rstride = (long)(g.hl + 1) * g.nm;
+      p.out_ostride = (long)g.nm * rows0; p.out_kstride = rows0;
+    } else {         // [k0][x2][x1] -> [k0][k1][x2]   (x2: local planes when distributed)
+      if (dist) { p.in = s1(); p.out = s0(); }
+      p.n_o = g.h0 + 1; p.n_r = planes2; p.in_ostride = (long)planes2 * g.nm; p.in_rstride = g.nm;
+      p.out_ostride = (long)g.nm * planes2; p.out_kstride = planes2;
     }
     launch<PCBody<T>>(c.grid, c.block, c.smem, st, p);
   }
   template <bool FWD, bool ADJ> void run_p3(stream_t st, const PointOp<T>& op) {
     P3Params<T> p;
     p.lg_n = lg0; p.lg_R = c3.lg_R; p.mg = mg3(); p.pitch = c3.pitch; p.tw = tw0.p; p.lg_tw = lg0; p.fft = f0; p.hsign = hsign; p.ahead = c3.ahead;
-    p.in = p3_in(); p.out = p3_out(); p.out_kstride = (long)g.nl * g.nm; p.op = op;
+    p.in = p3_in(); p.out = p3_out(); p.out_kstride = (long)planes2 * g.nm; p.op = op;
+    p.src_off = dist ? src_off3.p : nullptr; p.src_mul = dist ? src_mul3.p : nullptr;
     const size_t sm = c3.smem + LINEINFO_BYTES;
     if constexpr (FWD && ADJ) {
       if (op.mode == PM_METRIC) launch<P3Body<T, true, true, PM_METRIC>>(c3.grid, c3.block, sm, st, p);
@@ -321,7 +426,8 @@ template <class T> struct Plan : PlanBase {
   template <class Epi> void run_p5(stream_t st, const Epi& epi) {
     P5Params<T, Epi> p;
     p.lg_n = lgl; p.lg_R = c5.lg_R; p.mg = mg5(); p.hmid1 = g.hm + 1; p.pitch = c5.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = fl; p.ahead = c5.ahead;
-    p.hsign = hsign; p.in = S1.p; p.epi = epi;
+    p.hsign = hsign; p.in = s1(); p.epi = epi;
+    p.src_off = dist ? src_off5.p : nullptr; p.src_mul = dist ? src_mul5.p : nullptr;
     launch<P5Body<T, Epi>>(c5.grid, c5.block, c5.smem + LINEINFO_BYTES, st, p);
   }
   // natural (d0,d1,d2) -> reversed axes; for the T-layout <-> natural conversions

@@ -1,0 +1,114 @@
+"""Slab-decomposed 3-D grids on CPU: world_size 2 and 4 with gloo, the kernels on the host
+emulator.  Every rank checks its part of signal / energy / metric / left-sqrt-metric against the oracle
+evaluated on the GLOBAL grid."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def slab_check(rt, shape, dist_, lh_kind="gauss", seed=3, tol=1e-10):
+    """Runs inside an initialised process group; returns the max relative errors found."""
+    import nifty_b200 as nb
+    import oracle
+    c = dict(shape=shape, distances=dist_, offset_mean=0.3, offset_std=(0.2, 0.1), fluctuations=(0.5, 0.1),
+             loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05))
+    ocf = oracle.CorrelatedFieldOracle("cf")
+    ocf.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+    ocf.add_fluctuations(shape, dist_, c["fluctuations"], c["loglogavgslope"], c["flexibility"], c["asperity"], prefix="ax1",
+                         non_parametric_kind="power")
+    ocf.finalize()
+    osig = oracle.SignalOracle(ocf, "exp")
+    lay = oracle.Layout(osig.domain)
+    rng = np.random.default_rng(seed)
+    pos = {k: 0.5 * v for k, v in lay.random(rng).items()}
+    tan = lay.random(rng)
+    if lh_kind == "gauss":
+        data = osig(pos) + 0.3 * rng.standard_normal(shape)
+        olh = oracle.GaussianOracle(data, 1.0 / 0.09, osig)
+    else:
+        data = rng.poisson(osig(pos)).astype(np.int64)
+        olh = oracle.PoissonianOracle(data, osig)
+    u = rng.standard_normal(shape)
+
+    cfm = nb.CorrelatedFieldMaker("cf", runtime=rt, comm=True)
+    cfm.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+    cfm.add_fluctuations(shape, dist_, c["fluctuations"], c["loglogavgslope"], c["flexibility"], c["asperity"], prefix="ax1",
+                         non_parametric_kind="power")
+    cf = cfm.finalize()
+    plan = cf.plan
+    assert plan.dist
+    sig = nb.SignalModel(cf, "exp")
+    dloc = plan.scatter_position(data.astype(np.float64))
+    if lh_kind == "gauss":
+        lh = nb.Gaussian(dloc, noise_cov_inv=1.0 / 0.09).amend(sig)
+    else:
+        lh = nb.Poissonian(np.rint(dloc.cpu().numpy()).astype(np.int64)).amend(sig)
+
+    def localise(tree):
+        d = {k: torch.as_tensor(v) for k, v in tree.items()}
+        d["cfxi"] = plan.scatter_latent(tree["cfxi"])
+        return sig.layout.pack(d, torch.float64, rt.device)
+
+    def globalise(vec):
+        d = sig.layout.unpack(vec)
+        out = {k: v.cpu().numpy() for k, v in d.items() if k != "cfxi"}
+        out["cfxi"] = plan.gather_latent(d["cfxi"]).cpu().numpy()
+        return out
+
+    errs = {}
+    pl, tl = localise(pos), localise(tan)
+    lin, _ = lh.lin_at(pl)
+    s_glob = plan.gather_position(lin.signal()).cpu().numpy()
+    ref = osig(pos)
+    errs["signal"] = float(np.max(np.abs(s_glob - ref)) / np.max(np.abs(ref)))
+    e, oe = lin.energy(), olh.energy(pos)
+    errs["energy"] = abs(e - oe) / abs(oe)
+    met = globalise(lin.metric(tl))
+    omet = olh.metric(pos, tan)
+    scale = max(np.max(np.abs(v)) for v in omet.values())
+    errs["metric"] = max(float(np.max(np.abs(met[k] - omet[k]))) / scale for k in omet)
+    met1 = globalise(lin.metric(tl, add_identity=True))
+    errs["metric+1"] = max(float(np.max(np.abs(met1[k] - omet[k] - tan[k]))) / scale for k in omet)
+    ls = globalise(lin.lsm(plan.scatter_position(u), scaled=True))
+    ols = olh.left_sqrt_metric(pos, u)
+    scale = max(np.max(np.abs(v)) for v in ols.values())
+    errs["lsm"] = max(float(np.max(np.abs(ls[k] - ols[k]))) / scale for k in ols)
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, bad
+    return errs
+
+
+def _worker(rank, world, port, shape):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import nifty_b200 as nb
+    from nifty_b200._capi import CApi
+    from emu.build_emu import build
+    rt = nb.Runtime(CApi(build()), "cpu")
+    slab_check(rt, shape, (0.2, 0.1, 0.05))
+    slab_check(rt, shape, 0.1, lh_kind="poisson", seed=5)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world,shape", [(2, (8, 4, 16)), (4, (16, 8, 8)), (2, (4, 4, 4))])
+def test_slab_decomposition_matches_global_oracle(world, shape):
+    mp.spawn(_worker, args=(world, _free_port(), shape), nprocs=world, join=True)
