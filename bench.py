@@ -35,6 +35,10 @@ WORKLOADS = {
     "cf2d_2048_f64": ((2048, 2048), "2D correlated field 2048x2048 float64"),
     "cf3d_256_f64": ((256, 256, 256), "3D correlated field 256^3 float64 (BASELINE.json configs[2])"),
     "cf2d_128_f64": ((128, 128), "2D correlated field 128x128 float64 (BASELINE.json configs[0])"),
+    # slab-decomposed over the ranks (needs --gpus >= 2 under torchrun): ONE field spread over all GPUs
+    "cf3d_1024_f64_slab": ((1024, 1024, 1024), "3D correlated field 1024^3 float64, slab-decomposed (BASELINE.json configs[4])"),
+    "cf3d_512_f64_slab": ((512, 512, 512), "3D correlated field 512^3 float64, slab-decomposed"),
+    "cf3d_256_f64_slab": ((256, 256, 256), "3D correlated field 256^3 float64, slab-decomposed"),
 }
 CF_KW = dict(fluctuations=(1e-1, 5e-3), loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5), asperity=(0.5, 0.05))
 OFFSET = (0.0, (1e-3, 1e-4))
@@ -351,6 +355,111 @@ def run_b200(args, shape, wname, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_b200_slab(args, shape, wname, rank, world, local_rank):
+    """One field slab-decomposed over all ranks (strong scaling): step = one metric-vector product with its two
+    NCCL all-to-all exchanges and one all-reduce; value = products per second of the whole job."""
+    import torch
+    import torch.distributed as dist
+    import nifty_b200 as nb
+    if world < 2:
+        raise SystemExit("slab workloads need --gpus >= 2 under torchrun (one field spread over the ranks)")
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    dtype = torch.float64
+    cfm = nb.CorrelatedFieldMaker("cf", dtype=dtype, comm=True)
+    cfm.set_amplitude_total_offset(*OFFSET)
+    cfm.add_fluctuations(shape, 1.0 / shape[0], prefix="ax1", non_parametric_kind="power", **CF_KW)
+    cf = cfm.finalize()
+    plan, rt = cf.plan, cf.rt
+    sig = nb.SignalModel(cf, "exp")
+    gen = torch.Generator(dev).manual_seed(100 + rank)
+    data = torch.randn(plan.local_pos_shape, dtype=dtype, device=dev, generator=gen)
+    lh = nb.Gaussian(data, noise_cov_inv=NOISE_STD**-2).amend(sig)
+    L = sig.layout.size
+    hyper = torch.Generator(dev).manual_seed(7)          # hyper-parameter leaves are replicated: same seed on every rank
+    pos = 0.1 * torch.randn(L, dtype=dtype, device=dev, generator=hyper)
+    t = torch.randn(L, dtype=dtype, device=dev, generator=hyper)
+    o, n_xi = sig.layout.offsets["cfxi"], sig.layout.numel("cfxi")
+    rows_ok = torch.as_tensor(plan.row_map >= 0, device=dev)
+    for v in (pos, t):
+        blk = v[o:o + n_xi].view(plan.local_shape)
+        blk.copy_(0.1 * torch.randn(plan.local_shape, dtype=dtype, device=dev, generator=gen))
+        blk[~rows_ok] = 0
+    lin, _ = lh.lin_at(pos)
+    out = torch.empty_like(t)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        lin.metric(t, add_identity=True, out=out)
+    n0 = rt.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        lin.metric(t, add_identity=True, out=out)
+    e1.record()
+    barrier()
+    launches = rt.launch_count() - n0
+    tmax = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax) / args.steps
+    rt.timing_begin()
+    for _ in range(args.steps):
+        lin.metric(t, add_identity=True, out=out)
+    tm = rt.timing_end()
+    kern_ms = sum(v[1] for v in tm.values()) / args.steps
+    # end to end: host tangent (local block) -> device -> product -> host
+    t_host, out_host = t.cpu().pin_memory(), torch.empty_like(t, device="cpu").pin_memory()
+    t_dev = torch.empty_like(t)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        t_dev.copy_(t_host, non_blocking=True)
+        out_host.copy_(lin.metric(t_dev, add_identity=True, out=out), non_blocking=True)
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        N = int(np.prod(shape))
+        ab = algorithmic_bytes_mvp(shape)
+        nv = 2 * 8 * (N / world) * (world - 1) / world
+        nbytes = t.numel() * t.element_size()
+        line = {"metric": "metric_vector_products_per_sec", "value": 1e3 / ms_step, "unit": "MVP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wname, "shape": list(shape), "what": WORKLOADS[wname][1], "latent_size_per_rank": L,
+                           "parallelism": f"slab-decomposed x{world} (2 NCCL all-to-all + 1 all-reduce per product)",
+                           "l2": "working set per product per GPU >> 126 MB L2 (no explicit flush)"},
+                "clocks": clocks, "e2e": {"value": 1e3 / (float(te) / args.steps), "unit": "MVP/s", "h2d_bytes_per_step": nbytes * world,
+                                          "d2h_bytes_per_step": nbytes * world},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "whole product (aggregate over ranks)", "achieved": ab / (ms_step * 1e-3) / 1e9,
+                             "peak": peak * world, "unit": "GB/s", "frac": ab / (ms_step * 1e-3) / 1e9 / (peak * world), "traffic": None,
+                             "peak_source": "measured (MEASURED_PEAKS.json) x n_gpus", "kernel_ms_rank0": kern_ms,
+                             "exchange_and_host_ms": ms_step - kern_ms,
+                             "nvlink": {"bytes_per_gpu_per_direction": nv, "achieved_GBps": nv / ((ms_step - kern_ms) * 1e-3) / 1e9,
+                                        "peak_GBps": 770.0, "note": "exchanges are not yet overlapped with the passes"}},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -368,6 +477,8 @@ def main():
         if args.steps > 10 and np.prod(shape) >= 2**24:
             args.steps = 10     # bounded sample: ~1-3 s per product on the host cores
         run_reference(args, shape, args.workload, rank, world)
+    elif args.workload.endswith("_slab"):
+        run_b200_slab(args, shape, args.workload, rank, world, local_rank)
     else:
         run_b200(args, shape, args.workload, rank, world, local_rank)
 

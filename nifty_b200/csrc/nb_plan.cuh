@@ -35,7 +35,7 @@ struct GridInfo {
   // Mode binning; follows the arithmetic of correlated_field.py:134-176 (mode lengths) and :55-67
   // (unique with 1e-12 relative merge, mid-point binning) on the folded index range only: every
   // |k| value of the full grid occurs there, with multiplicity prod_i (1 or 2).
-  int build(int ndim_, const int64_t* shp, const double* dst) {
+  int build(int ndim_, const int64_t* shp, const double* dst, bool want_csr = true) {
     ndim = ndim_;
     if (ndim < 1 || ndim > 3) return fail("nb200: only 1-, 2- and 3-dimensional grids are supported");
     N = 1; V = 1;
@@ -107,6 +107,7 @@ struct GridInfo {
     for (int b = 2; b < K; ++b) logvol.push_back(rel[b] - rel[b - 1]);
     // CSR of the folded partial-sum array W[l = a*nm + km][x], a in [0,h0], km in [0,nm), x in [0,hl]
     nW = (int64_t)(h0 + 1) * nm * (hl + 1);
+    if (!want_csr) return 0;          // slab-decomposed plans build the CSR of their local planes only
     if (nW >= (int64_t(1) << 31)) return fail("nb200: grid too large for 32-bit mode-bin indices");
     w_offs.assign(K + 1, 0);
     auto wbin = [&](int64_t p) {
@@ -256,7 +257,7 @@ template <class T> struct Plan : PlanBase {
     hsign = hconv ? T(-1) : T(1);
     rank = rank_; world = world_; dist = world_ > 1;
     dev_set(device);
-    if (g.build(ndim, shp, dst)) throw Error{last_error_ref()};
+    if (g.build(ndim, shp, dst, !dist)) throw Error{last_error_ref()};
     lg0 = ilog2(g.n0); lgm = ilog2(g.nm); lgl = ilog2(g.nl);
     rows0 = g.n0; planes2 = g.nl;
     int cA0 = g.h0 + 1, cA2 = g.hl + 1;      // planes of the half ranges handled by P5 / P3

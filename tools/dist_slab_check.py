@@ -1,0 +1,102 @@
+"""Multi-GPU check + timing of the slab-decomposed 3-D path (run under torchrun, one rank per B200).
+1. parity against the oracle on a small global grid (every rank evaluates the oracle);
+2. metric-vector product timing on a large grid (synthetic data generated per rank), max over ranks."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import nifty_b200 as nb  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="256,256,256")
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--no-parity", action="store_true")
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rt = nb.default_runtime()
+    if not a.no_parity:
+        from test_dist_slab import slab_check
+        errs = slab_check(rt, (32, 16, 32), (0.2, 0.1, 0.05))
+        errs2 = slab_check(rt, (16, 32, 64), 0.1, lh_kind="poisson", seed=5)
+        if rank == 0:
+            print("slab parity (gauss 32x16x32):", {k: f"{v:.1e}" for k, v in errs.items()}, flush=True)
+            print("slab parity (poisson 16x32x64):", {k: f"{v:.1e}" for k, v in errs2.items()}, flush=True)
+    shape = tuple(int(s) for s in a.shape.split(","))
+    t0 = time.time()
+    cfm = nb.CorrelatedFieldMaker("cf", comm=True)
+    cfm.set_amplitude_total_offset(0.0, (1e-3, 1e-4))
+    cfm.add_fluctuations(shape, 1.0 / shape[0], fluctuations=(1e-1, 5e-3), loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5),
+                         asperity=(0.5, 0.05), prefix="ax1", non_parametric_kind="power")
+    cf = cfm.finalize()
+    plan = cf.plan
+    sig = nb.SignalModel(cf, "exp")
+    gen = torch.Generator(rt.device).manual_seed(100 + rank)
+    data = torch.randn(plan.local_pos_shape, dtype=torch.float64, device=rt.device, generator=gen)
+    lh = nb.Gaussian(data, noise_cov_inv=100.0).amend(sig)
+    L = sig.layout.size
+    # hyper-parameters replicated (same seed), excitations per rank; padding rows stay zero
+    hyper = torch.Generator(rt.device).manual_seed(7)
+    pos = 0.1 * torch.randn(L, dtype=torch.float64, device=rt.device, generator=hyper)
+    t = torch.randn(L, dtype=torch.float64, device=rt.device, generator=hyper)
+    o = sig.layout.offsets["cfxi"]
+    n_xi = sig.layout.numel("cfxi")
+    rows_ok = torch.as_tensor(plan.row_map >= 0, device=rt.device)
+    for v in (pos, t):
+        blk = v[o:o + n_xi].view(plan.local_shape)
+        blk.copy_(0.1 * torch.randn(plan.local_shape, dtype=torch.float64, device=rt.device, generator=gen))
+        blk[~rows_ok] = 0
+    lin, _ = lh.lin_at(pos)
+    out = torch.empty_like(t)
+    torch.cuda.synchronize(); dist.barrier()
+    setup = time.time() - t0
+    for _ in range(3):
+        lin.metric(t, add_identity=True, out=out)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        lin.metric(t, add_identity=True, out=out)
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / a.steps], dtype=torch.float64, device=rt.device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # split: local compute only (no exchange) for the same phases
+    rt.timing_begin()
+    for _ in range(a.steps):
+        lin.metric(t, add_identity=True, out=out)
+    tm = rt.timing_end()
+    kern_ms = sum(v[1] for v in tm.values()) / a.steps
+    N = int(np.prod(shape))
+    bytes_mvp = 8 * N * 14
+    peak = 6462.7
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    nv = 2 * 8 * (N / world) * (world - 1) / world      # bytes per GPU per direction over NVLink per product
+    if rank == 0:
+        m = float(ms)
+        print(json.dumps({"what": "slab-decomposed metric-vector product", "shape": list(shape), "n_gpus": world, "ms_per_product": m,
+                          "products_per_s": 1e3 / m, "algorithmic_GB": bytes_mvp / 1e9,
+                          "aggregate_GBps": bytes_mvp / m / 1e6, "frac_of_aggregate_hbm_peak": bytes_mvp / m / 1e6 / (peak * world),
+                          "kernel_ms_rank0": kern_ms, "exchange_and_host_ms": m - kern_ms,
+                          "nvlink_bytes_per_gpu_per_dir_GB": nv / 1e9, "setup_s": setup, "latent_local": L}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
