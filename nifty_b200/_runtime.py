@@ -343,6 +343,8 @@ class Lin:
             pass
 
     def _vec(self):
+        if self.model.plan.dist:      # padding rows of the local xi block are never written by the kernels
+            return self.rt.zeros((self.model.L,), self.model.plan.dtype)
         return self.rt.empty((self.model.L,), self.model.plan.dtype)
 
     def _pos(self):

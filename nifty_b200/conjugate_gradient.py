@@ -35,8 +35,12 @@ class HamiltonianMetric:
 
     ``other`` (a second linearisation) selects the geoVI operator of evi.py:167-172."""
 
-    def __init__(self, lin, other=None):
-        self.lin, self.other = lin, other
+    def __init__(self, lin, other=None, likelihood=None):
+        self.lin, self.other, self.likelihood = lin, other, likelihood
+
+    @property
+    def distributed(self):
+        return bool(self.lin.model.plan.dist)
 
     def __call__(self, t: torch.Tensor) -> torch.Tensor:
         if self.other is None:
@@ -59,7 +63,14 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
         norm_ord=None, tol=1e-5, atol=0.0, miniter=None, maxiter=None, name=None, time_threshold=None,
         _raise_nonposdef=True, check_every=4) -> CGResults:
     norm_ord = 2 if norm_ord is None else norm_ord
-    if isinstance(mat, HamiltonianMetric):
+    vdot = lambda a, b: float(torch.dot(a, b))
+    vnorm = _norm
+    if isinstance(mat, HamiltonianMetric) and mat.distributed:
+        # slab-decomposed field: the recurrences run in the host loop below, reductions are all-reduced
+        if mat.likelihood is None:
+            raise ValueError("a slab-decomposed HamiltonianMetric needs its likelihood (for the distributed reductions)")
+        vdot, vnorm = mat.likelihood.vdot, mat.likelihood.vnorm
+    elif isinstance(mat, HamiltonianMetric):
         x, res = mat.lin.cg_solve(j, x0, other=mat.other, absdelta=absdelta, resnorm=resnorm, norm_ord=norm_ord, tol=tol,
                                   atol=atol, miniter=miniter, maxiter=maxiter, raise_nonposdef=_raise_nonposdef,
                                   check_every=check_every)
@@ -79,7 +90,7 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
     if maxiter is None:
         maxiter = max(min(200, maxiter_fallback), miniter)
     if absdelta is None and resnorm is None:
-        resnorm = max(tol * _norm(j, norm_ord), atol)
+        resnorm = max(tol * vnorm(j, norm_ord), atol)
     fi = torch.finfo(j.dtype)
     eps, tiny = 6.0 * fi.eps, 6.0 * fi.tiny
     nm = "CG" if name is None else name
@@ -92,16 +103,16 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
         pos = x0.clone()
         r = mat(pos) - j
         d = r.clone()
-        energy = float(torch.dot((r - j) / 2, pos))
+        energy = vdot((r - j) / 2, pos)
         nfev = 1
-    previous_gamma = float(torch.dot(r, r))
+    previous_gamma = vdot(r, r)
     if previous_gamma == 0:
         return CGResults(pos, 0, nfev, 0, True)
     info, i = -1, 0
     for i in range(1, maxiter + 1):
         q = mat(d)
         nfev += 1
-        curv = float(torch.dot(d, q))
+        curv = vdot(d, q)
         if curv == 0.0:
             if _raise_nonposdef:
                 raise ValueError(f"{nm}: zero curvature")
@@ -121,14 +132,14 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
             nfev += 1
         else:
             r = r - q * alpha
-        gamma = float(torch.dot(r, r))
+        gamma = vdot(r, r)
         if 0.0 <= gamma <= tiny:
             info = 0
             break
-        if resnorm is not None and _norm(r, norm_ord) < resnorm and i >= miniter:
+        if resnorm is not None and vnorm(r, norm_ord) < resnorm and i >= miniter:
             info = 0
             break
-        new_energy = float(torch.dot((r - j) / 2, pos))
+        new_energy = vdot((r - j) / 2, pos)
         energy_diff = energy - new_energy
         if energy_diff < -eps * abs(new_energy):
             if _raise_nonposdef:

@@ -45,8 +45,17 @@ def random_normal(key, shape, dtype, device) -> torch.Tensor:
 
 
 def random_like(key, lh: LikelihoodWithModel) -> torch.Tensor:
-    """``jft.random_like(key, pos)``: standard-normal latent vector (tree_math/forest_math.py:60-72)."""
-    return random_normal(key, (lh.layout.size,), lh.dtype, lh.rt.device)
+    """``jft.random_like(key, pos)``: standard-normal latent vector (tree_math/forest_math.py:60-72).
+    Slab-decomposed fields: the replicated hyper-parameter leaves come from the shared key, the local
+    excitation rows from a per-rank child key; padding rows are zero."""
+    v = random_normal(key, (lh.layout.size,), lh.dtype, lh.rt.device)
+    plan = lh.signal.cf.plan
+    if plan.dist:
+        lo, hi = lh._xi_slice()
+        k_rank = random_split(key, plan.comm.world + 1)[plan.comm.rank + 1]
+        v[lo:hi] = random_normal(k_rank, (hi - lo,), lh.dtype, lh.rt.device)
+        lh.zero_padding(v)
+    return v
 
 
 # ---- Samples -------------------------------------------------------------------------------------------
@@ -99,6 +108,9 @@ def concatenate_zip(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 def sample_likelihood(likelihood: LikelihoodWithModel, primals, key, _white_data=None):
     """evi.py:77-80: ``left_sqrt_metric(primals, N(0,1)[data shape])``."""
     lin, _ = likelihood.lin_at(primals)
+    plan = likelihood.signal.cf.plan
+    if plan.dist:      # independent white noise per rank for its local planes
+        key = random_split(key, plan.comm.world + 1)[plan.comm.rank + 1]
     white = _white_data if _white_data is not None else random_normal(key, likelihood.signal.target_shape, likelihood.dtype,
                                                                     likelihood.rt.device)
     return lin.lsm(white, scaled=True)
@@ -119,7 +131,7 @@ def draw_linear_residual(likelihood: LikelihoodWithModel, pos, key, *, from_inve
     smpl = nll_smpl + prr_smpl
     info = 0
     if from_inverse:
-        smpl, info = cg(HamiltonianMetric(lin), smpl, x0=prr_smpl, name=cg_name, _raise_nonposdef=_raise_nonposdef,
+        smpl, info = cg(HamiltonianMetric(lin, likelihood=likelihood), smpl, x0=prr_smpl, name=cg_name, _raise_nonposdef=_raise_nonposdef,
                         **(cg_kwargs or {}))
         if info is not None and info < 0:
             raise ValueError("conjugate gradient failed")

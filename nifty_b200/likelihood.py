@@ -161,6 +161,51 @@ class LikelihoodWithModel:
     def new_lin(self) -> Lin:
         return Lin(self.handle)
 
+    # -- vector algebra on latent vectors (tree_math.vdot / norm); slab-decomposed: xi block summed over ranks ------
+    @property
+    def _plan(self):
+        return self.signal.cf.plan
+
+    def _xi_slice(self):
+        key = self.signal.cf.prefix + "xi"
+        o = self.layout.offsets[key]
+        return o, o + self.layout.numel(key)
+
+    def vdot(self, a: torch.Tensor, b: torch.Tensor) -> float:
+        if not self._plan.dist:
+            return float(torch.dot(a, b))
+        lo, hi = self._xi_slice()
+        d_xi = torch.dot(a[lo:hi], b[lo:hi]).to(torch.float64).reshape(1)
+        # replicated hyper-parameter leaves: counted once, from the replicated entries only so that every
+        # rank gets bit-identical scalars (and the replicated leaves stay bit-identical through CG)
+        d_rep = float(torch.dot(a[:lo], b[:lo])) + float(torch.dot(a[hi:], b[hi:]))
+        return float(self._plan.comm.allreduce_sum(d_xi)) + d_rep
+
+    def vnorm(self, v: torch.Tensor, ord=2) -> float:
+        if not self._plan.dist:
+            from .conjugate_gradient import _norm
+            return _norm(v, ord)
+        lo, hi = self._xi_slice()
+        rep = torch.cat((v[:lo], v[hi:]))
+        if ord == 2:
+            return float(np.sqrt(self.vdot(v, v)))
+        if ord == 1:
+            t = v[lo:hi].abs().sum().to(torch.float64).reshape(1)
+            return float(self._plan.comm.allreduce_sum(t)) + float(rep.abs().sum())
+        if ord in (np.inf, float("inf")):
+            t = v[lo:hi].abs().max().to(torch.float64).reshape(1)
+            self._plan.comm.dist.all_reduce(t, op=self._plan.comm.dist.ReduceOp.MAX, group=self._plan.comm.group)
+            return max(float(t), float(rep.abs().max()) if rep.numel() else 0.0)
+        raise ValueError(f"unsupported norm order {ord!r} on slab-decomposed vectors")
+
+    def zero_padding(self, v: torch.Tensor) -> torch.Tensor:
+        """Zero the padding rows of the xi block of a slab-decomposed latent vector (no-op otherwise)."""
+        if self._plan.dist:
+            lo, hi = self._xi_slice()
+            blk = v[lo:hi].view(self._plan.local_shape)
+            blk[torch.as_tensor(self._plan.row_map < 0, device=v.device)] = 0
+        return v
+
     # -- reference API ------------------------------------------------------------------------------
     def energy(self, pos) -> float:
         lin, _ = self.lin_at(pos)
