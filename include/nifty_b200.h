@@ -77,11 +77,14 @@ int nb200_plan_create_dist(nb200_plan** plan, int device, int ndim, const int64_
 int nb200_plan_dist_info(const nb200_plan* plan, int64_t* out_host, int64_t nout);
 /* local -> global index of the owned rows (axis = 0) or position planes (axis = 2); -1 marks zero padding */
 int nb200_plan_local_map(const nb200_plan* plan, int axis, int32_t* out_host);
-/* two device buffers of `scratch elements` complex numbers each: pass buffers and all-to-all send / receive space */
-int nb200_plan_set_scratch(nb200_plan* plan, void* s0, void* s1);
-/* one segment of an operator between exchanges; codes and the exchange after each are listed in DESIGN.md section 7 */
-int nb200_dist_phase(nb200_lin* lin_a, nb200_lin* lin_b, void* stream, int code, const void* in, void* out, void* abar, void* xs,
-                     int flag);
+/* three device buffers of `scratch elements` complex numbers each: pass buffers and all-to-all send / receive space */
+int nb200_plan_set_scratch(nb200_plan* plan, void* s0, void* s1, void* s2);
+/* cut every rank's half-range piece into `nchunks` pieces so that the host can pipeline an exchange with the
+ * passes before / after it (chunk c of pass X, then exchange chunk c while pass X works on chunk c+1, ...) */
+int nb200_plan_set_chunks(nb200_plan* plan, int nchunks);
+/* one segment of an operator between exchanges (chunk < 0: whole range); codes are listed in DESIGN.md section 7 */
+int nb200_dist_phase(nb200_lin* lin_a, nb200_lin* lin_b, void* stream, int code, int chunk, const void* in, void* out, void* abar,
+                     void* xs, int flag);
 
 /* hartley(p, axes=all) (correlated_field.py:24-30): out = Re(fftn(in)) +/- Im(fftn(in)), unnormalised */
 int nb200_hartley(nb200_plan* plan, void* stream, const void* in, void* out);

@@ -67,8 +67,9 @@ SIGNATURES = {
     "nb200_plan_create_dist": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(i64), C.POINTER(f64), C.c_int, C.c_int, C.c_int, C.c_int]),
     "nb200_plan_dist_info": (C.c_int, [vp, C.POINTER(i64), i64]),
     "nb200_plan_local_map": (C.c_int, [vp, C.c_int, vp]),
-    "nb200_plan_set_scratch": (C.c_int, [vp, vp, vp]),
-    "nb200_dist_phase": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int]),
+    "nb200_plan_set_scratch": (C.c_int, [vp, vp, vp, vp]),
+    "nb200_plan_set_chunks": (C.c_int, [vp, C.c_int]),
+    "nb200_dist_phase": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]),
     "nb200_hartley": (C.c_int, [vp, vp, vp, vp]),
     "nb200_cf_apply": (C.c_int, [vp, vp, vp, vp, f64, vp]),
     "nb200_cf_apply_adjoint": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),

@@ -9,6 +9,7 @@ library and raises otherwise -- there is no CPU fallback.  (The test-suite may c
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -101,6 +102,25 @@ class SlabComm:
         n_out, n_in = sum(out_splits), sum(in_splits)
         self.dist.all_to_all_single(out[:n_out], inp[:n_in], out_splits, in_splits, group=self.group)
 
+    def p2p_exchange(self, out, inp, recv, send):
+        """Asynchronous personalised exchange: peer p gets inp[send[p]], out[recv[p]] is filled from peer p.
+        (offset, count) pairs in elements of the tensors; the own block is a device copy."""
+        ops = []
+        for p in range(self.world):
+            (so, sn), (ro, rn) = send[p], recv[p]
+            if p == self.rank:
+                if sn:
+                    out[ro:ro + rn].copy_(inp[so:so + sn])
+                continue
+            if sn:
+                ops.append(self.dist.P2POp(self.dist.isend, inp[so:so + sn], self._global_rank(p), group=self.group))
+            if rn:
+                ops.append(self.dist.P2POp(self.dist.irecv, out[ro:ro + rn], self._global_rank(p), group=self.group))
+        return self.dist.batch_isend_irecv(ops) if ops else []
+
+    def _global_rank(self, p):
+        return p if self.group is None else self.dist.get_global_rank(self.group, p)
+
     def allreduce_sum(self, t):
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
@@ -175,7 +195,13 @@ class Plan:
         self.x2_recv = [2 * int(cA0[me] * n1 * npad2[q]) for q in range(W)]
         self._s0 = self.rt.zeros((2 * self.scratch_elems,), self.dtype)
         self._s1 = self.rt.zeros((2 * self.scratch_elems,), self.dtype)
-        self.rt.api.call("nb200_plan_set_scratch", self._h, self.rt.ptr(self._s0), self.rt.ptr(self._s1))
+        self._s2 = self.rt.zeros((2 * self.scratch_elems,), self.dtype)
+        self.rt.api.call("nb200_plan_set_scratch", self._h, self.rt.ptr(self._s0), self.rt.ptr(self._s1), self.rt.ptr(self._s2))
+        self._dist_tabs = (n1, [int(x) for x in npad0], [int(x) for x in npad2], [int(x) for x in cA0], [int(x) for x in cA2])
+        self.nchunks = 1
+        nch = int(os.environ.get("NB200_SLAB_CHUNKS", "1"))
+        if nch > 1:
+            self.set_chunks(nch)
         rows = np.zeros(self.rows0, dtype=np.int32)
         planes = np.zeros(self.planes2, dtype=np.int32)
         self.rt.api.call("nb200_plan_local_map", self._h, 0, rows.ctypes.data_as(C.c_void_p))
@@ -188,6 +214,46 @@ class Plan:
             self.comm.all_to_all(self._s0, self._s1, self.x1_recv, self.x1_send)
         else:
             self.comm.all_to_all(self._s1, self._s0, self.x2_recv, self.x2_send)
+
+    def set_chunks(self, nchunks: int):
+        """Pipeline every exchange in `nchunks` pieces (point-to-point sends of chunk c overlap the passes
+        that produce chunk c+1 and consume chunk c-1)."""
+        self.rt.api.call("nb200_plan_set_chunks", self._h, int(nchunks))
+        self.nchunks = int(nchunks)
+        n1, npad0, npad2, cA0, cA2 = self._dist_tabs
+        W, me = self.comm.world, self.comm.rank
+
+        def split(start, count, c):
+            return start + (count * c) // nchunks
+
+        def tables(cA, npad):
+            a0 = [sum(cA[:q]) for q in range(W)]
+            roff = [sum(cA[me] * n1 * npad[p2] for p2 in range(p)) for p in range(W)]
+            send, recv = [], []
+            for c in range(nchunks):
+                sc, rc = [], []
+                for q in range(W):
+                    s, e = split(a0[q], cA[q], c), split(a0[q], cA[q], c + 1)
+                    sc.append((2 * s * n1 * npad[me], 2 * (e - s) * n1 * npad[me]))
+                    ls, le = split(0, cA[me], c), split(0, cA[me], c + 1)
+                    rc.append((2 * (roff[q] + ls * n1 * npad[q]), 2 * (le - ls) * n1 * npad[q]))
+                send.append(sc)
+                recv.append(rc)
+            return send, recv
+        # exchange 1 moves k2 planes (ownership of the last axis), rows padded per the axis-0 decomposition
+        self._x1 = tables(cA2, npad0)
+        self._x2 = tables(cA0, npad2)
+
+    def exchange_chunk(self, which: int, c: int):
+        """Start chunk c of exchange `which`; returns a handle for :meth:`wait`."""
+        src, dst = (self._s1, self._s0) if which == 1 else (self._s0, self._s1)
+        send, recv = self._x1 if which == 1 else self._x2
+        return self.comm.p2p_exchange(dst, src, recv[c], send[c])
+
+    @staticmethod
+    def wait(handle):
+        for w in handle:
+            w.wait()
 
     def scatter_latent(self, xi_global) -> torch.Tensor:
         """Rows of a global natural-order grid array owned by this rank (zero padding rows)."""
@@ -351,9 +417,20 @@ class Lin:
         return self.rt.empty(self.model.plan.local_pos_shape, self.model.plan.dtype)
 
     # -- slab-decomposed sequences: local phases (nb200_dist_phase) + host collectives ------------------
-    def _phase(self, code, other=None, inp=None, out=None, flag=0):
-        self.rt.api.call("nb200_dist_phase", self._h, None if other is None else other._h, self.rt.stream(), int(code),
+    def _phase(self, code, other=None, inp=None, out=None, flag=0, chunk=-1):
+        self.rt.api.call("nb200_dist_phase", self._h, None if other is None else other._h, self.rt.stream(), int(code), int(chunk),
                          self.rt.ptr(inp), self.rt.ptr(out), self.rt.ptr(self._abar), self.rt.ptr(self._xs), int(flag))
+
+    def _pipelined(self, which, produce_code, consume, **produce_kw):
+        """chunk c: produce (PCa / PCb) -> start exchange c; then for every chunk: wait -> consume (P3 / P5)."""
+        plan = self.model.plan
+        handles = []
+        for c in range(plan.nchunks):
+            self._phase(produce_code, chunk=c, **produce_kw)
+            handles.append(plan.exchange_chunk(which, c))
+        for c in range(plan.nchunks):
+            plan.wait(handles[c])
+            consume(c)
 
     def _dist_buffers(self):
         if not hasattr(self, "_abar"):
@@ -362,7 +439,13 @@ class Lin:
 
     def _dist_adjoint_tail(self, t, out, add_identity, scaled):
         plan = self.model.plan
-        self._phase(5, inp=t if add_identity else None, out=out, flag=int(add_identity))
+        tin = t if add_identity else None
+        if plan.nchunks > 1:      # PCb chunk -> exchange 2 chunk -> P5 chunk, then the bin sums
+            self._pipelined(2, 13, lambda c: self._phase(23, inp=tin, out=out, flag=int(add_identity), chunk=c))
+            self._phase(24, inp=tin, out=out, flag=int(add_identity))
+        else:
+            plan.exchange(2)
+            self._phase(5, inp=tin, out=out, flag=int(add_identity))
         plan.comm.allreduce_sum(self._abar)
         plan.comm.allreduce_sum(self._xs)
         self._phase(6, inp=t if add_identity else None, out=out, flag=int(add_identity) | (2 if scaled else 0))
@@ -373,9 +456,15 @@ class Lin:
             if want_grad:
                 raise NB200Error("gradients are not available on slab-decomposed plans yet")
             self._dist_buffers()
-            self._phase(0, inp=pos)
-            self.model.plan.exchange(1)
-            self._phase(1)
+            plan = self.model.plan
+            if plan.nchunks > 1:
+                self._phase(10, inp=pos)
+                self._pipelined(1, 11, lambda c: self._phase(12, chunk=c))
+                self._phase(14)
+            else:
+                self._phase(0, inp=pos)
+                plan.exchange(1)
+                self._phase(1)
             return None
         grad = self._vec() if want_grad else None
         self.rt.api.call("nb200_lin_update", self._h, self.rt.stream(), self.rt.ptr(pos), self.rt.ptr(grad), int(add_prior))
@@ -403,10 +492,13 @@ class Lin:
         out = self._vec() if out is None else out
         if self.model.plan.dist:
             plan = self.model.plan
-            self._phase(2, inp=t)
-            plan.exchange(1)
-            self._phase(3, inp=t)
-            plan.exchange(2)
+            if plan.nchunks > 1:
+                self._phase(20, inp=t)
+                self._pipelined(1, 11, lambda c: self._phase(21, inp=t, chunk=c))
+            else:
+                self._phase(2, inp=t)
+                plan.exchange(1)
+                self._phase(3, inp=t)
             return self._dist_adjoint_tail(t, out, add_identity, True)
         self.rt.api.call("nb200_metric", self._h, self.rt.stream(), self.rt.ptr(t), self.rt.ptr(out), int(add_identity))
         return out
@@ -426,8 +518,11 @@ class Lin:
         out = self._vec()
         u = self.rt.asarray(u, self.model.plan.dtype)
         if self.model.plan.dist:      # u: local planes in the internal [x2][x1][x0] layout
-            self._phase(4, inp=u, flag=int(scaled))
-            self.model.plan.exchange(2)
+            if self.model.plan.nchunks > 1:
+                for c in range(self.model.plan.nchunks):
+                    self._phase(22, inp=u, flag=int(scaled), chunk=c)
+            else:
+                self._phase(4, inp=u, flag=int(scaled))
             return self._dist_adjoint_tail(None, out, False, scaled)
         self.rt.api.call("nb200_lsm", self._h, self.rt.stream(), self.rt.ptr(u), self.rt.ptr(out), int(scaled))
         return out

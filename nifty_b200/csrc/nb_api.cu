@@ -237,22 +237,28 @@ int nb200_plan_local_map(const nb200_plan* plan, int axis, int32_t* out_host) {
   std::copy(m.begin(), m.end(), out_host);
   return 0;
 }
-int nb200_plan_set_scratch(nb200_plan* plan, void* s0, void* s1) {
+int nb200_plan_set_scratch(nb200_plan* plan, void* s0, void* s1, void* s2) {
   NB_TRY
-  NB_DISPATCH(plan->impl->dtype, TT, { auto* P = static_cast<Plan<TT>*>(plan->impl); P->xS0 = (cplx<TT>*)s0; P->xS1 = (cplx<TT>*)s1; })
+  NB_DISPATCH(plan->impl->dtype, TT, { auto* P = static_cast<Plan<TT>*>(plan->impl); P->xS0 = (cplx<TT>*)s0; P->xS1 = (cplx<TT>*)s1; P->xS2 = (cplx<TT>*)s2; })
   return 0;
   NB_CATCH
 }
-int nb200_dist_phase(nb200_lin* lin_a, nb200_lin* lin_b, void* stream, int code, const void* in, void* out, void* abar, void* xs,
-                     int flag) {
+int nb200_plan_set_chunks(nb200_plan* plan, int nchunks) {
+  NB_TRY
+  NB_DISPATCH(plan->impl->dtype, TT, { static_cast<Plan<TT>*>(plan->impl)->set_chunks(nchunks); })
+  return 0;
+  NB_CATCH
+}
+int nb200_dist_phase(nb200_lin* lin_a, nb200_lin* lin_b, void* stream, int code, int chunk, const void* in, void* out, void* abar,
+                     void* xs, int flag) {
   NB_TRY
   if (!lin_a) return fail("nb200_dist_phase: null linearisation");
   if (lin_b && lin_b->model != lin_a->model) return fail("nb200_dist_phase: linearisations of different models");
   NB_DISPATCH(lin_a->dtype, TT, {
     Lin<TT>* a = static_cast<Lin<TT>*>(lin_a->impl);
     Lin<TT>* b = lin_b ? static_cast<Lin<TT>*>(lin_b->impl) : a;
-    if (code == 2) b->dist_phase((stream_t)stream, code, b, (const TT*)in, (TT*)out, (TT*)abar, (TT*)xs, flag);   // tangent side
-    else a->dist_phase((stream_t)stream, code, b, (const TT*)in, (TT*)out, (TT*)abar, (TT*)xs, flag);
+    if (code == 2 || code == 20) b->dist_phase((stream_t)stream, code, b, (const TT*)in, (TT*)out, (TT*)abar, (TT*)xs, flag, chunk);   // tangent side
+    else a->dist_phase((stream_t)stream, code, b, (const TT*)in, (TT*)out, (TT*)abar, (TT*)xs, flag, chunk);
   })
   return 0;
   NB_CATCH

@@ -223,52 +223,67 @@ template <class T> struct Lin : LinBase {
   // code: 0 update.1 (amplitude, P1, PCa) | 1 update.2 (P3 linearise; local energy) | 2 metric.1 (tangent chain, P1, PCa)
   //       3 metric.2 (P3 fused, PCb) | 4 lsm.2 (P3 adjoint-only from local T-layout `in`, PCb) | 5 adjoint.3 (P5, local bin sums,
   //       xs = {p3 sum, xi dot}) | 6 adjoint.4 (finish with all-reduced abar / xs: hyper-parameter leaves, <add,out>)
-  void dist_phase(stream_t st, int code, Lin<T>* b, const T* in, T* out, T* abar, T* xs, int flag) {
+  void dist_phase(stream_t st, int code, Lin<T>* b, const T* in, T* out, T* abar, T* xs, int flag, int chunk = -1) {
     Model<T>& m = *M; Plan<T>& P = *m.P;
     if (!P.dist) throw Error{"nb200_dist_phase: not a slab-decomposed plan"};
-    if (!P.xS0 || !P.xS1) throw Error{"nb200_dist_phase: exchange buffers not set (nb200_plan_set_scratch)"};
+    if (!P.xS0 || !P.xS1 || !P.xS2) throw Error{"nb200_dist_phase: exchange buffers not set (nb200_plan_set_scratch)"};
+    if (chunk >= P.nchunks) throw Error{"nb200_dist_phase: chunk index out of range"};
+    // chunk < 0: the whole range in one launch
+    auto pc = [&](bool second) {
+      if (chunk < 0) { P.run_pc(st, second); return; }
+      const std::vector<int>& off = second ? P.omapB_off : P.omapA_off;
+      P.run_pc(st, second, (second ? P.omapB.p : P.omapA.p) + off[chunk], off[chunk + 1] - off[chunk]);
+    };
+    const int l3 = chunk < 0 ? 0 : P.p3_line0[chunk], n3 = chunk < 0 ? -1 : P.p3_nlines[chunk];
+    const int l5 = chunk < 0 ? 0 : P.p5_line0[chunk], n5 = chunk < 0 ? -1 : P.p5_nlines[chunk];
+    auto reduce_p3 = [&](T* o0, T* o1) {
+      ReduceColsParams<T> pr; pr.partials = P.p3part.p; pr.n = P.c3.grid; pr.ncol = 2; pr.out0 = o0; pr.out1 = o1;
+      launch<ReduceColsBody<T>>(1, 256, 512, st, pr);
+    };
     switch (code) {
-      case 0: {
+      case 0: case 10: {     // update.1: amplitude chain + P1 (+ PCa for code 0)
         if (!m.have_lh) throw Error{"nb200: likelihood not set on this model"};
         d2d(pos.p, in, (size_t)m.am.L * sizeof(T), st);
         amp_forward(st);
         ProAmp<T> pro; pro.xi = pos.p + m.am.off_xi; pro.idxf = P.idxf.p; pro.amp = amp.p; pro.fg = P.fold_geom();
-        P.run_p1(st, pro); P.run_pc(st, false);
+        P.run_p1(st, pro);
+        if (code == 0) P.run_pc(st, false);
       } break;
-      case 1: {
+      case 11: pc(false); break;                        // PCa (chunk)
+      case 13: pc(true); break;                         // PCb (chunk)
+      case 1: case 12: {     // update.2: P3 linearise (chunk); code 1 also reduces the local energy
         PointOp<T> op = P.make_op(PM_LINEARIZE);
         op.invV = T(1.0 / P.g.V); op.offset = m.offset_mean; op.sc_ptr = scal.p + SC_SCALING;
         op.lh_kind = m.lh_kind; op.nl_exp = m.nl_exp; op.data = m.data.p; op.w_scalar = m.w_scalar;
         op.w_arr = m.has_w_arr ? m.w_arr.p : nullptr; op.s_out = s.p; op.jl_out = jl.p; op.partials = P.p3part.p;
-        P.template run_p3<true, false>(st, op);
-        ReduceColsParams<T> pr; pr.partials = P.p3part.p; pr.n = P.c3.grid; pr.ncol = 2;
-        pr.out0 = scal.p + SC_ENERGY; pr.out1 = scal.p + SC_SUMCOT;
-        launch<ReduceColsBody<T>>(1, 256, 512, st, pr);
-        valid = true;
+        P.template run_p3<true, false>(st, op, l3, n3);
+        if (code == 1) { reduce_p3(scal.p + SC_ENERGY, scal.p + SC_SUMCOT); valid = true; }
       } break;
-      case 2: {
+      case 14: reduce_p3(scal.p + SC_ENERGY, scal.p + SC_SUMCOT); valid = true; break;
+      case 2: case 20: {     // metric.1: tangent chain + P1 (+ PCa for code 2)
         if (!valid) throw Error{"nb200: linearisation not initialised"};
         amp_tangent(st, in);
-        P.run_p1(st, pro_metric(in)); P.run_pc(st, false);
+        P.run_p1(st, pro_metric(in));
+        if (code == 2) P.run_pc(st, false);
       } break;
-      case 3: {
+      case 3: case 21: {     // metric.2: fused P3 (chunk) (+ PCb for code 3)
         PointOp<T> op = P.make_op(PM_METRIC);
         op.invV = T(1.0 / P.g.V); op.jl_a = jl.p; op.jl_b = b->jl.p; op.partials = P.p3part.p;
         if (m.am.has_scaling) { op.cshift_ptr = in + m.am.off_scl; op.cshift_scale = m.am.scl_b; }
-        P.template run_p3<true, true>(st, op);
-        P.run_pc(st, true);
+        P.template run_p3<true, true>(st, op, l3, n3);
+        if (code == 3) P.run_pc(st, true);
       } break;
-      case 4: {
+      case 4: case 22: {     // lsm.2: adjoint-only P3 from the local planes `in` (chunk) (+ PCb for code 4)
         PointOp<T> op = P.make_op(PM_LOAD);
         op.in_pos = in; op.jl_a = flag ? jl.p : nullptr; op.partials = P.p3part.p;
-        P.template run_p3<false, true>(st, op);
-        P.run_pc(st, true);
+        P.template run_p3<false, true>(st, op, l3, n3);
+        if (code == 4) P.run_pc(st, true);
       } break;
-      case 5: {
-        P.run_p5(st, epi_adjoint(out, flag ? in : nullptr, flag != 0));
+      case 23: P.run_p5(st, epi_adjoint(out, flag ? in : nullptr, flag != 0), l5, n5); break;   // P5 (chunk)
+      case 5: case 24: {     // adjoint.3: (P5 for code 5) local bin sums, xs = {p3 sum, xi dot}
+        if (code == 5) P.run_p5(st, epi_adjoint(out, flag ? in : nullptr, flag != 0));
         seg_sum(st, abar, nullptr);
-        ReduceColsParams<T> pr; pr.partials = P.p3part.p; pr.n = P.c3.grid; pr.ncol = 2; pr.out0 = xs; pr.out1 = nullptr;
-        launch<ReduceColsBody<T>>(1, 256, 512, st, pr);
+        reduce_p3(xs, nullptr);
         if (flag) {
           ReduceColsParams<T> pd; pd.partials = P.p5part.p; pd.n = P.c5.grid; pd.ncol = 1; pd.out0 = xs + 1; pd.out1 = nullptr;
           launch<ReduceColsBody<T>>(1, 256, 512, st, pd);
@@ -276,7 +291,7 @@ template <class T> struct Lin : LinBase {
           dev_zero(xs + 1, sizeof(T), st);
         }
       } break;
-      case 6: {
+      case 6: {              // adjoint.4: finish with the all-reduced abar / xs
         seg_sum(st, nullptr, abar);
         T sf = (flag & 2) ? m.am.scl_b : T(0);
         vjp_chain(st, out, (flag & 1) ? in : nullptr, xs, 1, xs + 1, 1, sf);

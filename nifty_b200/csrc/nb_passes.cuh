@@ -204,6 +204,7 @@ template <class T> struct PCParams {
   FftDev fft;
   const cplx<T>* in;
   cplx<T>* out;
+  const int* omap;   // optional: outer index of the bid-th group (chunked launches of the slab pipeline)
 };
 
 // raw complex lines (stride `rstride` between the lines of a CTA); inactive lines read as zero
@@ -221,7 +222,7 @@ template <class T> struct PCBody {
     cplx<T>* s = reinterpret_cast<cplx<T>*>(smem);
     const int R = 1 << p.lg_R, n = 1 << p.lg_n;
     const int gpo = p.n_r >> p.lg_R;
-    const int o = ctx.bid / gpo, rr0 = (ctx.bid % gpo) << p.lg_R;
+    const int o = p.omap ? ldg(p.omap + ctx.bid / gpo) : ctx.bid / gpo, rr0 = (ctx.bid % gpo) << p.lg_R;
     const cplx<T>* inp = p.in + o * p.in_ostride + rr0 * p.in_rstride;
     RawLoader<T> ld{inp, p.in_rstride, nullptr, nullptr, nullptr, nullptr, 0};          // R divides n_r: no bounds check
     fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
@@ -394,6 +395,7 @@ template <class T> struct P3Params {
   cplx<T>* out;            // [k in 0..n/2][out_kstride]
   long out_kstride;
   int ahead;
+  int line0;               // first line of this launch (chunked launches); multiple of R
   PointOp<T> op;
 };
 
@@ -425,7 +427,8 @@ template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
     LineInfo* li = reinterpret_cast<LineInfo*>(smem);
     cplx<T>* s = reinterpret_cast<cplx<T>*>(reinterpret_cast<unsigned char*>(smem) + LINEINFO_BYTES);
     const int R = 1 << p.lg_R, n = 1 << p.lg_n, h = n >> 1, lg_h = p.lg_n - 1;
-    const int l0 = ctx.bid << p.lg_R;
+    const int l0 = p.line0 + (ctx.bid << p.lg_R);
+    const int pbid = (p.line0 >> p.lg_R) + ctx.bid;   // slot of this CTA's partial sums
     fill_line_info(ctx, li, p.mg, l0, R);
     T acc0 = 0, acc1 = 0;
     T cshift = p.op.cshift_ptr ? p.op.cshift_scale * ldg(p.op.cshift_ptr) : T(0);
@@ -536,7 +539,7 @@ template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
       void* scratch = reinterpret_cast<void*>(s + (size_t)R * p.pitch);
       acc0 = ctx.block_sum(acc0, scratch);
       acc1 = ctx.block_sum(acc1, scratch);
-      if (ctx.tid == 0) { p.op.partials[2 * ctx.bid] = acc0; p.op.partials[2 * ctx.bid + 1] = acc1; }
+      if (ctx.tid == 0) { p.op.partials[2 * pbid] = acc0; p.op.partials[2 * pbid + 1] = acc1; }
     }
   }
 };
@@ -635,6 +638,7 @@ template <class T, class Epi> struct P5Params {
   const cplx<T>* in;   // [l][n]   (or the all-to-all receive buffer when src_off != null)
   const long* src_off; const int* src_mul;
   int ahead;
+  int line0;
   Epi epi;
 };
 
@@ -654,7 +658,8 @@ template <class T, class Epi> struct P5Body {
     LineInfo* li = reinterpret_cast<LineInfo*>(smem);
     cplx<T>* s = reinterpret_cast<cplx<T>*>(reinterpret_cast<unsigned char*>(smem) + LINEINFO_BYTES);
     const int R = 1 << p.lg_R, n = 1 << p.lg_n, h = n >> 1, lg_h = p.lg_n - 1;
-    const int l0 = ctx.bid << p.lg_R;
+    const int l0 = p.line0 + (ctx.bid << p.lg_R);
+    const int pbid = (p.line0 >> p.lg_R) + ctx.bid;
     fill_line_info(ctx, li, p.mg, l0, R);
     T acc = 0;
     for (int r = 0; r < R && p.ahead > 0; ++r) {
@@ -724,7 +729,7 @@ template <class T, class Epi> struct P5Body {
     if (p.epi.partials) {
       void* scratch = reinterpret_cast<void*>(s + (size_t)R * p.pitch);
       acc = ctx.block_sum(acc, scratch);
-      if (ctx.tid == 0) p.epi.partials[ctx.bid] = acc;
+      if (ctx.tid == 0) p.epi.partials[pbid] = acc;
     }
   }
 };

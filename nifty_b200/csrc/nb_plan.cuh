@@ -201,7 +201,12 @@ template <class T> struct Plan : PlanBase {
   DevBuf<cplx<T>> tw0, twm, twl, S0, S1;
   DevBuf<int> idxf, w_order, w_offs, pos0, posm, posl, poslh, plane_loc0, src_mul3, src_mul5;
   DevBuf<long> src_off3, src_off5;
-  cplx<T>* xS0 = nullptr; cplx<T>* xS1 = nullptr;   // host-provided exchange buffers (distributed plans)
+  cplx<T>* xS0 = nullptr; cplx<T>* xS1 = nullptr; cplx<T>* xS2 = nullptr;   // host-provided buffers (distributed plans)
+  // chunked pipeline of the distributed plans: chunk c of every rank's half-range piece
+  int nchunks = 1;
+  DevBuf<int> omapA, omapB;                 // outer indices (k2 / k0) of PCa / PCb chunk launches, concatenated
+  std::vector<int> omapA_off, omapB_off;    // [nchunks+1]
+  std::vector<int> p3_line0, p3_nlines, p5_line0, p5_nlines;   // [nchunks] line ranges of this rank
   FftDev f0, fm, fl, flh;   // line FFTs of length n0, nm, nl and nl/2
   DevBuf<T> W, p3part, p5part;
   PassCfg c1, cA, c3, cB, c5;
@@ -342,8 +347,9 @@ template <class T> struct Plan : PlanBase {
       seg_lg_lpb = 0;
       while (seg_lg_lpb < 6 && (1 << (seg_lg_lpb + 1)) <= avg / 3.0) ++seg_lg_lpb;   // ~3-6 entries per lane
     }
-    p3part.alloc((size_t)2 * c3.grid);
-    p5part.alloc((size_t)c5.grid);
+    p3part.alloc((size_t)2 * c3.grid + 64);
+    p5part.alloc((size_t)c5.grid + 32);
+    if (dist) set_chunks(1);
   }
   cplx<T>* s0() { return dist ? xS0 : S0.p; }
   cplx<T>* s1() { return dist ? xS1 : S1.p; }
@@ -365,9 +371,30 @@ template <class T> struct Plan : PlanBase {
   MirrorGeom mg3() const { return mgeom(g.nl, g.hl, d2); }
   MirrorGeom mg5() const { return mgeom(g.n0, g.h0, d0); }
   // buffer roles.  single GPU: P1->S0, PCa S0->S1, P3 S1->S0 (2-D: S0->S1), PCb S0->S1, P5 reads S1.
-  // distributed:  P1->S0, PCa S0->S1, [all-to-all S1->S0], P3 S0->S1, PCb S1->S0, [all-to-all S0->S1], P5 reads S1.
+  // distributed (three buffers so that an exchange can overlap the passes around it):
+  //   P1->S2, PCa S2->S1, [all-to-all S1->S0], P3 S0->S2, PCb S2->S0, [all-to-all S0->S1], P5 reads S1.
   cplx<T>* p3_in() { return dist ? s0() : (g.three ? s1() : s0()); }
-  cplx<T>* p3_out() { return dist ? s1() : (g.three ? s0() : s1()); }
+  cplx<T>* p3_out() { return dist ? xS2 : (g.three ? s0() : s1()); }
+  // split [start, start+count) into nchunks contiguous pieces; piece c = [split(c), split(c+1))
+  static int split_at(int start, int count, int c, int nch) { return start + (int)((int64_t)count * c / nch); }
+  void set_chunks(int nch) {
+    if (!dist) throw Error{"nb200_plan_set_chunks: not a slab-decomposed plan"};
+    if (nch < 1 || nch > 16) throw Error{"nb200_plan_set_chunks: 1 <= nchunks <= 16"};
+    nchunks = nch;
+    auto build = [&](const AxisDist& ax, DevBuf<int>& dev, std::vector<int>& off, std::vector<int>& l0, std::vector<int>& nl) {
+      std::vector<int> all; off.assign(nch + 1, 0); l0.assign(nch, 0); nl.assign(nch, 0);
+      for (int c = 0; c < nch; ++c) {
+        for (int q = 0; q < world; ++q)
+          for (int a = split_at(ax.a0[q], ax.cA[q], c, nch); a < split_at(ax.a0[q], ax.cA[q], c + 1, nch); ++a) all.push_back(a);
+        off[c + 1] = (int)all.size();
+        int s = split_at(0, ax.cA[rank], c, nch), e = split_at(0, ax.cA[rank], c + 1, nch);
+        l0[c] = s * g.nm; nl[c] = (e - s) * g.nm;
+      }
+      dev.upload(all);
+    };
+    build(d2, omapA, omapA_off, p3_line0, p3_nlines);   // exchange 1: k2 planes, consumed by P3
+    build(d0, omapB, omapB_off, p5_line0, p5_nlines);   // exchange 2: k0 planes, consumed by P5
+  }
 
   PointOp<T> make_op(int mode) const {
     PointOp<T> op;
@@ -379,7 +406,7 @@ template <class T> struct Plan : PlanBase {
 
   template <class Pro> void run_p1(stream_t st, const Pro& pro) {
     P1Params<T, Pro> p;
-    p.lg_n = lgl; p.lg_R = c1.lg_R; p.pitch = c1.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = flh; p.out = s0(); p.ahead = c1.ahead; p.pro = pro;
+    p.lg_n = lgl; p.lg_R = c1.lg_R; p.pitch = c1.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = flh; p.out = dist ? xS2 : s0(); p.ahead = c1.ahead; p.pro = pro;
     if (g.three) {
       p.n_o = rows0; p.n_r = g.nm; p.in_ostride = (long)g.nm * g.nl; p.in_rstride = g.nl;
       p.out_ostride = (long)(g.hl + 1) * g.nm; p.out_kstride = g.nm;
@@ -389,47 +416,56 @@ template <class T> struct Plan : PlanBase {
     if (pro.aligned()) launch<P1Body<T, Pro, true>>(c1.grid, c1.block, c1.smem, st, p);
     else launch<P1Body<T, Pro, false>>(c1.grid, c1.block, c1.smem, st, p);
   }
-  void run_pc(stream_t st, bool second) {
+  void run_pc(stream_t st, bool second, const int* omap = nullptr, int n_o_chunk = -1) {
     if (!g.three) return;
     PCParams<T> p;
     const PassCfg& c = second ? cB : cA;
-    p.lg_n = lgm; p.lg_R = c.lg_R; p.pitch = c.pitch; p.tw = twm.p; p.lg_tw = lgm; p.fft = fm; p.in = s0(); p.out = s1();
+    p.omap = omap;
+    p.lg_n = lgm; p.lg_R = c.lg_R; p.pitch = c.pitch; p.tw = twm.p; p.lg_tw = lgm; p.fft = fm; p.in = dist ? xS2 : s0(); p.out = s1();
     if (!second) {   // [j0][k2][j1] -> [k2][k1][j0]   (j0: local rows when distributed)
       p.n_o = g.hl + 1; p.n_r = rows0; p.in_ostride = g.nm; p.in_rstride = (long)(g.hl + 1) * g.nm;
       p.out_ostride = (long)g.nm * rows0; p.out_kstride = rows0;
     } else {         // [k0][x2][x1] -> [k0][k1][x2]   (x2: local planes when distributed)
-      if (dist) { p.in = s1(); p.out = s0(); }
+      if (dist) { p.in = xS2; p.out = s0(); }
       p.n_o = g.h0 + 1; p.n_r = planes2; p.in_ostride = (long)planes2 * g.nm; p.in_rstride = g.nm;
       p.out_ostride = (long)g.nm * planes2; p.out_kstride = planes2;
     }
-    launch<PCBody<T>>(c.grid, c.block, c.smem, st, p);
+    int grid = c.grid;
+    if (omap) { if (n_o_chunk <= 0) return; grid = n_o_chunk * (p.n_r >> p.lg_R); }
+    launch<PCBody<T>>(grid, c.block, c.smem, st, p);
   }
-  template <bool FWD, bool ADJ> void run_p3(stream_t st, const PointOp<T>& op) {
+  template <bool FWD, bool ADJ> void run_p3(stream_t st, const PointOp<T>& op, int line0 = 0, int nlines = -1) {
     P3Params<T> p;
+    p.line0 = line0;
+    int grid3 = c3.grid;
+    if (nlines >= 0) { if (nlines == 0) return; grid3 = (nlines + (1 << c3.lg_R) - 1) >> c3.lg_R; }
     p.lg_n = lg0; p.lg_R = c3.lg_R; p.mg = mg3(); p.pitch = c3.pitch; p.tw = tw0.p; p.lg_tw = lg0; p.fft = f0; p.hsign = hsign; p.ahead = c3.ahead;
     p.in = p3_in(); p.out = p3_out(); p.out_kstride = (long)planes2 * g.nm; p.op = op;
     p.src_off = dist ? src_off3.p : nullptr; p.src_mul = dist ? src_mul3.p : nullptr;
     const size_t sm = c3.smem + LINEINFO_BYTES;
     if constexpr (FWD && ADJ) {
-      if (op.mode == PM_METRIC) launch<P3Body<T, true, true, PM_METRIC>>(c3.grid, c3.block, sm, st, p);
-      else if (op.mode == PM_LINEARIZE) launch<P3Body<T, true, true, PM_LINEARIZE>>(c3.grid, c3.block, sm, st, p);
+      if (op.mode == PM_METRIC) launch<P3Body<T, true, true, PM_METRIC>>(grid3, c3.block, sm, st, p);
+      else if (op.mode == PM_LINEARIZE) launch<P3Body<T, true, true, PM_LINEARIZE>>(grid3, c3.block, sm, st, p);
       else throw Error{"nb200: invalid pointwise mode for the fused pass"};
     } else if constexpr (FWD) {
-      if (op.mode == PM_LINEARIZE) launch<P3Body<T, true, false, PM_LINEARIZE>>(c3.grid, c3.block, sm, st, p);
-      else if (op.mode == PM_JVP_OUT) launch<P3Body<T, true, false, PM_JVP_OUT>>(c3.grid, c3.block, sm, st, p);
-      else if (op.mode == PM_FIELD_OUT) launch<P3Body<T, true, false, PM_FIELD_OUT>>(c3.grid, c3.block, sm, st, p);
+      if (op.mode == PM_LINEARIZE) launch<P3Body<T, true, false, PM_LINEARIZE>>(grid3, c3.block, sm, st, p);
+      else if (op.mode == PM_JVP_OUT) launch<P3Body<T, true, false, PM_JVP_OUT>>(grid3, c3.block, sm, st, p);
+      else if (op.mode == PM_FIELD_OUT) launch<P3Body<T, true, false, PM_FIELD_OUT>>(grid3, c3.block, sm, st, p);
       else throw Error{"nb200: invalid pointwise mode for the forward pass"};
     } else {
       if (op.mode != PM_LOAD) throw Error{"nb200: invalid pointwise mode for the adjoint pass"};
-      launch<P3Body<T, false, true, PM_LOAD>>(c3.grid, c3.block, sm, st, p);
+      launch<P3Body<T, false, true, PM_LOAD>>(grid3, c3.block, sm, st, p);
     }
   }
-  template <class Epi> void run_p5(stream_t st, const Epi& epi) {
+  template <class Epi> void run_p5(stream_t st, const Epi& epi, int line0 = 0, int nlines = -1) {
     P5Params<T, Epi> p;
+    p.line0 = line0;
+    int grid5 = c5.grid;
+    if (nlines >= 0) { if (nlines == 0) return; grid5 = (nlines + (1 << c5.lg_R) - 1) >> c5.lg_R; }
     p.lg_n = lgl; p.lg_R = c5.lg_R; p.mg = mg5(); p.hmid1 = g.hm + 1; p.pitch = c5.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = fl; p.ahead = c5.ahead;
     p.hsign = hsign; p.in = s1(); p.epi = epi;
     p.src_off = dist ? src_off5.p : nullptr; p.src_mul = dist ? src_mul5.p : nullptr;
-    launch<P5Body<T, Epi>>(c5.grid, c5.block, c5.smem + LINEINFO_BYTES, st, p);
+    launch<P5Body<T, Epi>>(grid5, c5.block, c5.smem + LINEINFO_BYTES, st, p);
   }
   // natural (d0,d1,d2) -> reversed axes; for the T-layout <-> natural conversions
   void run_rev(stream_t st, const T* in, T* out, bool to_T) {

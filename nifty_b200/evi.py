@@ -48,13 +48,19 @@ def random_like(key, lh: LikelihoodWithModel) -> torch.Tensor:
     """``jft.random_like(key, pos)``: standard-normal latent vector (tree_math/forest_math.py:60-72).
     Slab-decomposed fields: the replicated hyper-parameter leaves come from the shared key, the local
     excitation rows from a per-rank child key; padding rows are zero."""
-    v = random_normal(key, (lh.layout.size,), lh.dtype, lh.rt.device)
     plan = lh.signal.cf.plan
-    if plan.dist:
-        lo, hi = lh._xi_slice()
-        k_rank = random_split(key, plan.comm.world + 1)[plan.comm.rank + 1]
-        v[lo:hi] = random_normal(k_rank, (hi - lo,), lh.dtype, lh.rt.device)
-        lh.zero_padding(v)
+    if not plan.dist:
+        return random_normal(key, (lh.layout.size,), lh.dtype, lh.rt.device)
+    lo, hi = lh._xi_slice()
+    L = lh.layout.size
+    keys = random_split(key, plan.comm.world + 1)
+    v = torch.empty(L, dtype=lh.dtype, device=lh.rt.device)
+    # replicated leaves: a draw whose SIZE is the same on every rank (device generators are size dependent)
+    rep = random_normal(keys[0], (L - (hi - lo),), lh.dtype, lh.rt.device)
+    v[:lo] = rep[:lo]
+    v[hi:] = rep[lo:]
+    v[lo:hi] = random_normal(keys[plan.comm.rank + 1], (hi - lo,), lh.dtype, lh.rt.device)
+    lh.zero_padding(v)
     return v
 
 

@@ -108,10 +108,10 @@ def slab_check(rt, shape, dist_, lh_kind="gauss", seed=3, tol=1e-10):
     return errs
 
 
-def _worker(rank, world, port, shape):
+def _worker(rank, world, port, shape, chunks):
     sys.path.insert(0, os.path.dirname(HERE))
     sys.path.insert(0, HERE)
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NB200_SLAB_CHUNKS=str(chunks))
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import nifty_b200 as nb
@@ -124,6 +124,8 @@ def _worker(rank, world, port, shape):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("world,shape", [(2, (8, 4, 16)), (4, (16, 8, 8)), (2, (4, 4, 4))])
-def test_slab_decomposition_matches_global_oracle(world, shape):
-    mp.spawn(_worker, args=(world, _free_port(), shape), nprocs=world, join=True)
+@pytest.mark.parametrize("world,shape,chunks", [(2, (8, 4, 16), 1), (4, (16, 8, 8), 1), (2, (4, 4, 4), 1),
+                                                (2, (16, 4, 16), 2), (4, (32, 4, 16), 3), (2, (8, 8, 8), 4)])
+def test_slab_decomposition_matches_global_oracle(world, shape, chunks):
+    """chunks > 1: every exchange is pipelined in point-to-point pieces between chunked pass launches."""
+    mp.spawn(_worker, args=(world, _free_port(), shape, chunks), nprocs=world, join=True)

@@ -25,6 +25,9 @@ def main():
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_P2P_NVL_CHUNKSIZE", "4194304")   # measured: exchanges 4.9 -> 3.9 ms at 1024^3 x 8
+    os.environ.setdefault("NCCL_BUFFSIZE", "16777216")
+    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")       # lets the exchange kernels run beside the passes (3.98 vs 4.54 ms at 512^3 x 2)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rt = nb.default_runtime()
     if not a.no_parity:
@@ -93,7 +96,7 @@ def main():
                           "products_per_s": 1e3 / m, "algorithmic_GB": bytes_mvp / 1e9,
                           "aggregate_GBps": bytes_mvp / m / 1e6, "frac_of_aggregate_hbm_peak": bytes_mvp / m / 1e6 / (peak * world),
                           "kernel_ms_rank0": kern_ms, "exchange_and_host_ms": m - kern_ms,
-                          "nvlink_bytes_per_gpu_per_dir_GB": nv / 1e9, "setup_s": setup, "latent_local": L}), flush=True)
+                          "nvlink_bytes_per_gpu_per_dir_GB": nv / 1e9, "setup_s": setup, "latent_local": L, "chunks": plan.nchunks}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
