@@ -448,7 +448,7 @@ def run_b200_slab(args, shape, wname, rank, world, local_rank):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wname, "shape": list(shape), "what": WORKLOADS[wname][1], "latent_size_per_rank": L,
-                           "parallelism": f"slab-decomposed x{world} (2 NCCL all-to-all + 1 all-reduce per product)",
+                           "parallelism": f"slab-decomposed x{world} (2 chunked NCCL exchanges + 1 all-reduce per product)",
                            "l2": "working set per product per GPU >> 126 MB L2 (no explicit flush)"},
                 "clocks": clocks, "e2e": {"value": 1e3 / (float(te) / args.steps), "unit": "MVP/s", "h2d_bytes_per_step": nbytes * world,
                                           "d2h_bytes_per_step": nbytes * world},
@@ -457,8 +457,10 @@ def run_b200_slab(args, shape, wname, rank, world, local_rank):
                              "peak": peak * world, "unit": "GB/s", "frac": ab / (ms_step * 1e-3) / 1e9 / (peak * world), "traffic": None,
                              "peak_source": "measured (MEASURED_PEAKS.json) x n_gpus", "kernel_ms_rank0": kern_ms,
                              "exchange_and_host_ms": ms_step - kern_ms,
-                             "nvlink": {"bytes_per_gpu_per_direction": nv, "achieved_GBps": nv / ((ms_step - kern_ms) * 1e-3) / 1e9,
-                                        "peak_GBps": 770.0, "note": "exchanges are not yet overlapped with the passes"}},
+                             "nvlink": {"bytes_per_gpu_per_direction": nv, "achieved_GBps_over_whole_step": nv / (ms_step * 1e-3) / 1e9,
+                                        "peak_GBps": 770.0, "chunks": plan.nchunks,
+                                        "note": "exchanges are pipelined in chunks beside the passes (kernel_ms is measured "
+                                                "with per-kernel events, i.e. under contention with the exchange kernels)"}},
                 "cpu_baseline": None}
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
