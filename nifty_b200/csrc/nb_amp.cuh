@@ -209,7 +209,7 @@ template <class T, class Elem, class Out> struct ScanApplyBody {
         if (pos >= p.n) break;
         Aff<T> a = el[i];
         T x1 = x + a.a * y + a.b, y1 = y + a.c;
-        p.out.put(pos, x, y, x1, y1, grand.b, acc);
+        p.out.put(pos, p.out.load(pos), x, y, x1, y1, grand.b, acc);
         x = x1; y = y1;
       }
       p.out.finish(ctx, acc, grand.b, scratch);
@@ -223,13 +223,24 @@ template <class T, class Elem, class Out> struct ScanApplyBody {
     pre = aff_compose(carry, pre);
     T acc[4] = {0, 0, 0, 0};
     T x = pre.b, y = pre.c;          // state = prefix applied to the zero state
+    // all global loads of the SCAN_E outputs of this thread are issued before the sequential walk
+    typename Out::Pre pl[SCAN_E];
+    if (p.n > 0) {
+#pragma unroll
+      for (int e = 0; e < SCAN_E; ++e) {
+        long pos = p0 + ctx.tid * SCAN_E + e;
+        pl[e] = p.out.load(pos < p.n ? pos : p.n - 1);
+      }
+    }
+#pragma unroll
     for (int e = 0; e < SCAN_E; ++e) {
       long pos = p0 + ctx.tid * SCAN_E + e;
-      if (pos >= p.n) break;
-      Aff<T> a = el[ctx.tid * SCAN_E + e];
-      T x1 = x + a.a * y + a.b, y1 = y + a.c;
-      p.out.put(pos, x, y, x1, y1, grand.b, acc);
-      x = x1; y = y1;
+      if (pos < p.n) {
+        Aff<T> a = el[ctx.tid * SCAN_E + e];
+        T x1 = x + a.a * y + a.b, y1 = y + a.c;
+        p.out.put(pos, pl[e], x, y, x1, y1, grand.b, acc);
+        x = x1; y = y1;
+      }
     }
     p.out.finish(ctx, acc, grand.b, scratch);
 #endif
@@ -272,14 +283,16 @@ template <class T> struct FwdElem {
 template <class T> struct FwdOut {
   AmpModel<T> m; const T* pos;
   T* P; T* partials; unsigned* counter; T* scal;
-  NB_HD NB_INLINE void put(long b, T, T, T x1, T, T total, T* acc) const {
+  struct Pre { T l, mu; };
+  NB_HD NB_INLINE Pre load(long b) const { Pre q; q.l = m.ell[b]; q.mu = m.mult[b]; return q; }
+  NB_HD NB_INLINE void put(long b, const Pre& q, T, T, T x1, T, T total, T* acc) const {
     AmpPoint<T> ap = amp_point(m, pos);
-    T l = m.ell[b], llast = m.ell[m.K - 1];
+    T l = q.l, llast = m.ell[m.K - 1];
     T u = ap.slope * l;
     if (m.has_dev) u += x1 - total * (l / llast);
     T Pb = nb_exp(u);
     P[b] = Pb;
-    if (b >= 1) acc[0] += m.mult[b] * (m.kind_power ? Pb : Pb * Pb);
+    if (b >= 1) acc[0] += q.mu * (m.kind_power ? Pb : Pb * Pb);
   }
   NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, T total, void* scratch) const {
     T s = ctx.block_sum(acc[0], scratch);
@@ -345,12 +358,14 @@ template <class T> struct JvpElem {
 template <class T> struct JvpOut {
   AmpModel<T> m; const T* pos; const T* t; const T* wS; const T* amp;
   cplx<T>* ad; T* partials; unsigned* counter; T* scal;   // ad[b] = (A_b, du_b)
-  NB_HD NB_INLINE void put(long b, T, T, T x1, T, T total, T* acc) const {
-    T l = m.ell[b], llast = m.ell[m.K - 1];
+  struct Pre { T l, w, A; };
+  NB_HD NB_INLINE Pre load(long b) const { Pre q; q.l = m.ell[b]; q.w = wS[b]; q.A = amp[b]; return q; }
+  NB_HD NB_INLINE void put(long b, const Pre& q, T, T, T x1, T, T total, T* acc) const {
+    T l = q.l, llast = m.ell[m.K - 1];
     T d = m.slp_b * t[m.off_slp] * l;
     if (m.has_dev) d += x1 - total * (l / llast);
-    ad[b] = cmake<T>(amp[b], d);
-    acc[0] += wS[b] * d;
+    ad[b] = cmake<T>(q.A, d);
+    acc[0] += q.w * d;
   }
   NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, T, void* scratch) const {
     T s = ctx.block_sum(acc[0], scratch);
@@ -457,17 +472,24 @@ template <class T> struct VjpOut {
   const T* p3_partials; int n_p3;       // [n_p3][2]: acc0 = sum of position-space cotangent
   const T* p5_partials; int n_p5;       // [n_p5]: xi-block of <add, out>
   T scl_factor;                         // factor applied to the p3 sum for the scaling leaf
-  NB_HD NB_INLINE void put(long p, T x0, T, T, T y1, T, T* acc) const {
+  struct Pre { T dt, xi0, xi1, a0, a1; };
+  NB_HD NB_INLINE Pre load(long p) const {
+    long j = (m.K - 3) - p;
+    Pre q; q.dt = m.dt[j]; q.xi0 = pos[m.off_spec + 2 * j]; q.xi1 = pos[m.off_spec + 2 * j + 1]; q.a0 = 0; q.a1 = 0;
+    if (add) { q.a0 = add[m.off_spec + 2 * j]; q.a1 = add[m.off_spec + 2 * j + 1]; }
+    return q;
+  }
+  NB_HD NB_INLINE void put(long p, const Pre& pq, T x0, T, T, T y1, T, T* acc) const {
     long j = (m.K - 3) - p;
     T sig = scal_in[SC_SIG], asp = scal_in[SC_ASP];
-    T dt = m.dt[j], sq = nb_sqrt(dt), sd = sig * sq, q = nb_sqrt(dt * dt / T(12) + asp);
+    T dt = pq.dt, sq = nb_sqrt(dt), sd = sig * sq, q = nb_sqrt(dt * dt / T(12) + asp);
     T r0bar = y1, r1bar = x0 + T(0.5) * dt * r0bar;
-    T xi0 = pos[m.off_spec + 2 * j], xi1 = pos[m.off_spec + 2 * j + 1];
+    T xi0 = pq.xi0, xi1 = pq.xi1;
     T o0 = r0bar * sd * q, o1 = r1bar * sd;
     acc[0] += (r0bar * xi0 * q + r1bar * xi1) * sq;           // sigbar
     acc[1] += r0bar * sd * xi0 / (T(2) * q);                  // aspbar
     if (add) {
-      T a0 = add[m.off_spec + 2 * j], a1 = add[m.off_spec + 2 * j + 1];
+      T a0 = pq.a0, a1 = pq.a1;
       o0 += a0; o1 += a1;
       acc[2] += a0 * o0 + a1 * o1;
     }
