@@ -99,16 +99,6 @@ template <class T> __device__ NB_INLINE Aff<T> block_scan_aff(Ctx& ctx, Aff<T> v
 }
 #endif
 
-// ordered composition of agg[lo..hi) by the whole block
-template <class T> NB_HD NB_INLINE Aff<T> block_compose_range(Ctx& ctx, const Aff<T>* agg, int lo, int hi, void* scratch) {
-  int n = hi - lo, per = (n + ctx.nthr - 1) / ctx.nthr;
-  Aff<T> v = aff_id<T>();
-  for (int i = lo + ctx.tid * per; i < lo + (ctx.tid + 1) * per && i < hi; ++i) v = aff_compose(v, agg[i]);
-  Aff<T> tot;
-  block_scan_aff(ctx, v, tot, scratch);
-  return tot;
-}
-
 constexpr int SCAN_NT = 256;
 constexpr int SCAN_E = 8;
 constexpr int SCAN_CH = SCAN_NT * SCAN_E;

@@ -44,7 +44,7 @@ template <class T> void Model<T>::init(Plan<T>* plan_, const nb200_model_desc& d
   am.ell = ell.p; am.mult = multT.p; am.dt = dt.p;
   nchunksK = (g.K + SCAN_CH - 1) / SCAN_CH;
   nchunksJ = std::max(1, (g.K - 2 + SCAN_CH - 1) / SCAN_CH);
-  agg.alloc(nchunksK + 1); preaff.alloc(nchunksK + 2); pre.alloc(2 * (size_t)nchunksK + 2); total.alloc(2);
+  agg.alloc(nchunksK + 1); preaff.alloc(nchunksK + 2);
   ad.alloc(g.K); gbuf.alloc(g.K);
   size_t np = std::max<size_t>(3 * (size_t)nchunksK + 3, 2 * (size_t)P->seg_grid() + 2);
   np = std::max<size_t>(np, 4 * 2048);

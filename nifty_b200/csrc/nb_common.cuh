@@ -2,7 +2,7 @@
 //
 // Kernel *bodies* are written once as templates over an execution context `Ctx` that supplies
 // (tid, nthr, bid, nblk), a block barrier and block reductions.  The CUDA build instantiates them
-// with `DevCtx` inside `__global__` wrappers (this is the only thing the product library
+// with the device `Ctx` inside `__global__` wrappers (this is the only thing the product library
 // libniftyb200.so contains).  tests/emu compiles the very same bodies with `-DNB_EMU` for a
 // sequential host context (one "thread" per block, blocks run one after the other) so that index
 // arithmetic, mirror logic and epilogues can be checked against the oracle in a container without

@@ -56,7 +56,7 @@ template <class T> struct Model : ModelBase {
   bool has_w_arr = false;
   // chain workspaces
   DevBuf<Aff<T>> agg, preaff;
-  DevBuf<T> pre, total, gbuf, partials, tmp_pos;
+  DevBuf<T> gbuf, partials, tmp_pos;
   DevBuf<cplx<T>> ad;
   DevBuf<unsigned> counters;
   int nchunksK = 1, nchunksJ = 1;

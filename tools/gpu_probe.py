@@ -69,6 +69,21 @@ def main():
     tot = sum(v[1] for v in tm.values())
     for k, (c, msk) in sorted(tm.items(), key=lambda kv: -kv[1][1]):
         print(f"  {msk/c*1e3:9.1f} us x{c//a.steps}  {100*msk/tot:5.1f}%  {k}")
+    # one MGVI-style CG solve with per-kernel timing
+    j = torch.randn(L, dtype=dtype, device=rt.device, generator=gen)
+    x, res = lin.cg_solve(j, j.clone(), absdelta=1e-4 * L / 10, maxiter=100, raise_nonposdef=False)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    x, res = lin.cg_solve(j, j.clone(), absdelta=1e-4 * L / 10, maxiter=100, raise_nonposdef=False)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"CG solve: {res.nit} iterations, {1e3*(t2-t1):.2f} ms wall -> {1e3*(t2-t1)/max(res.nit,1):.3f} ms / iteration")
+    rt.timing_begin()
+    x, res = lin.cg_solve(j, j.clone(), absdelta=1e-4 * L / 10, maxiter=100, raise_nonposdef=False)
+    tm = rt.timing_end()
+    for k, (c, msk) in sorted(tm.items(), key=lambda kv: -kv[1][1]):
+        if "Cg" in k or "Dot" in k:
+            print(f"  {msk/c*1e3:9.1f} us x{c}  {k}")
     # update (linearise + gradient)
     e0.record()
     for _ in range(5):
