@@ -121,6 +121,12 @@ typedef struct nb200_model_desc {
   /* offsets of the leaves in the flat latent vector (elements); -1 if the leaf is absent */
   int64_t off_xi, off_zeromode, off_fluct, off_slope, off_flex, off_asp, off_spectrum, off_scaling;
   int64_t latent_size;
+  /* add_fluctuations_matern / MaternAmplitude (correlated_field.py:302-395, 661-755): amplitude_type 1.
+   * Leaves: <prefix>scale -> fluct_a/b + off_fluct, <prefix>loglogslope -> slope_a/b + off_slope, <prefix>cutoff (lognormal) */
+  int32_t amplitude_type;         /* 0 non-parametric, 1 Matern */
+  int32_t renormalize_amplitude;  /* Matern only */
+  double cutoff_a, cutoff_b;
+  int64_t off_cutoff;
 } nb200_model_desc;
 
 int nb200_model_create(nb200_model** model, nb200_plan* plan, const nb200_model_desc* desc_host);

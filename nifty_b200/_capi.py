@@ -32,6 +32,7 @@ class ModelDesc(C.Structure):
         ("off_xi", i64), ("off_zeromode", i64), ("off_fluct", i64), ("off_slope", i64), ("off_flex", i64),
         ("off_asp", i64), ("off_spectrum", i64), ("off_scaling", i64),
         ("latent_size", i64),
+        ("amplitude_type", i32), ("renormalize_amplitude", i32), ("cutoff_a", f64), ("cutoff_b", f64), ("off_cutoff", i64),
     ]
 
 

@@ -26,8 +26,10 @@ from .tree import Layout
 class CorrelatedField:
     """The finalised model: ``cf(pos)`` evaluates the field; mirrors ``jft.Model`` attributes."""
 
-    def __init__(self, plan: Plan, domain: dict, prefix: str, sub_prefix: str, desc_fields: dict, offset_mean: float):
+    def __init__(self, plan: Plan, domain: dict, prefix: str, sub_prefix: str, desc_fields: dict, offset_mean: float,
+                 matern: bool = False):
         self.plan, self.rt = plan, plan.rt
+        self.matern = matern
         self.prefix, self.sub_prefix = prefix, sub_prefix
         self.offset_mean = float(offset_mean)
         self._desc_fields = dict(desc_fields)
@@ -54,6 +56,9 @@ class CorrelatedField:
         off = lambda key: layout.offsets.get(key, -1)
         d.off_xi, d.off_zeromode = off(p + "xi"), off(p + "zeromode")
         d.off_fluct, d.off_slope = off(sp + "fluctuations"), off(sp + "loglogavgslope")
+        d.off_cutoff = -1
+        if self.matern:
+            d.off_fluct, d.off_slope, d.off_cutoff = off(sp + "scale"), off(sp + "loglogslope"), off(sp + "cutoff")
         d.off_flex, d.off_asp, d.off_spectrum = off(sp + "flexibility"), off(sp + "asperity"), off(sp + "spectrum")
         d.has_scaling, d.off_scaling = 0, -1
         if scaling is not None:
@@ -117,8 +122,25 @@ class CorrelatedFieldMaker:
         asp = _as_prior(asperity, LogNormalPrior, "asperity", optional=True)
         self._fluct.append(dict(shape=shape, distances=distances, flu=flu, slp=slp, flx=flx, asp=asp, prefix=prefix, kind=kind))
 
-    def add_fluctuations_matern(self, *args, **kwargs):
-        raise NotImplementedError("Matern amplitudes are not on the B200 hot path yet (SURVEY.md 8f)")
+    def add_fluctuations_matern(self, shape, distances, scale, cutoff, loglogslope, renormalize_amplitude: bool,
+                                prefix: str = "", harmonic_type: str = "fourier", non_parametric_kind: str = "amplitude"):
+        """correlated_field.py:661-755 (``MaternAmplitude`` :302-395): leaves ``<prefix>scale`` (log-normal),
+        ``<prefix>cutoff`` (log-normal), ``<prefix>loglogslope`` (normal)."""
+        if harmonic_type.lower() != "fourier":
+            if harmonic_type.lower() == "spherical":
+                raise NotImplementedError("harmonic_type='spherical' is outside the B200 hot path")
+            raise ValueError(f"invalid `harmonic_type` {harmonic_type!r}")
+        kind = non_parametric_kind.lower()
+        if kind not in ("amplitude", "power"):
+            raise ValueError(f"invalid `non_parametric_kind` {non_parametric_kind!r}")
+        if self._fluct:
+            raise NotImplementedError("outer products of several sub-grids are not on the B200 hot path yet")
+        shape = (int(shape),) if np.ndim(shape) == 0 else tuple(int(s) for s in shape)
+        scl = _as_prior(scale, LogNormalPrior, "scale")
+        ctf = _as_prior(cutoff, LogNormalPrior, "cutoff")
+        slp = _as_prior(loglogslope, NormalPrior, "loglogslope")
+        self._fluct.append(dict(shape=shape, distances=distances, matern=True, scl=scl, ctf=ctf, slp=slp,
+                                renorm=bool(renormalize_amplitude), prefix=prefix, kind=kind))
 
     def finalize(self) -> CorrelatedField:
         """correlated_field.py:850-920: builds the grid tables (on the C side) and the model."""
@@ -130,6 +152,19 @@ class CorrelatedFieldMaker:
         plan = Plan(f["shape"], f["distances"], dtype=self._dtype, hartley_convention=self._conv, runtime=self._rt,
                     comm=self._comm)
         sp = self._prefix + f["prefix"]
+        if f.get("matern"):
+            domain = dict(self._parameter_tree)
+            domain[sp + "scale"] = ()
+            domain[sp + "cutoff"] = ()
+            domain[sp + "loglogslope"] = ()
+            domain[self._prefix + "xi"] = plan.local_shape
+            fields = dict(kind_power=int(f["kind"] == "power"), has_fluctuations=1, has_deviations=0, has_asperity=0,
+                          amplitude_type=1, renormalize_amplitude=int(f["renorm"]))
+            fields["zeromode_a"], fields["zeromode_b"] = self._azm.ab()
+            fields["fluct_a"], fields["fluct_b"] = f["scl"].ab()
+            fields["slope_a"], fields["slope_b"] = f["slp"].ab()
+            fields["cutoff_a"], fields["cutoff_b"] = f["ctf"].ab()
+            return CorrelatedField(plan, domain, self._prefix, f["prefix"], fields, self._offset_mean, matern=True)
         has_dev = f["flx"] is not None and plan.K > 2
         domain = dict(self._parameter_tree)
         if f["flu"] is not None:

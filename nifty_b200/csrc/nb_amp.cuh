@@ -26,6 +26,7 @@ enum AmpScalIdx {
   SC_ENERGY = 17,               // likelihood energy of the last linearisation
   SC_SUMCOT = 18,               // sum of dE/df (scaling gradient)
   SC_DOT = 19,                  // <add, out> of the last adjoint application
+  SC_CTF = 20, SC_CWC = 21, SC_SGC = 22, SC_UBC = 23,   // Matern: cutoff value, sum wS c, sum g c, sum ubar c
   SC_COUNT = 32
 };
 
@@ -33,6 +34,9 @@ template <class T> struct AmpModel {
   int K;                 // number of mode bins
   int kind_power;        // 1: "power", 0: "amplitude"   (correlated_field.py:506-513)
   int has_dev, has_flu, has_asp, has_scaling;
+  int matern, renorm;    // Matern amplitude (correlated_field.py:302-395): u_b = slope/4 log1p((k_b/cutoff)^2), optional renormalisation
+  const T* modes;        // [K] mode lengths k_b (Matern)
+  T ctf_a, ctf_b; long off_ctf;
   const T* ell;          // [K] relative log mode lengths
   const T* mult;         // [K] multiplicities
   const T* dt;           // [K-2] log volumes
@@ -241,7 +245,7 @@ template <class T, class Elem, class Out> struct ScanApplyBody {
 template <class T> NB_HD NB_INLINE T prior_ln(T a, T b, T xi) { return nb_exp(a + b * xi); }
 
 // scalars of the amplitude model at `pos` (every thread may call it; a handful of exps)
-template <class T> struct AmpPoint { T flu, slope, sig, asp, z, scl; };
+template <class T> struct AmpPoint { T flu, slope, sig, asp, z, scl, ctf; };
 template <class T> NB_HD NB_INLINE AmpPoint<T> amp_point(const AmpModel<T>& m, const T* pos) {
   AmpPoint<T> a;
   a.flu = m.has_flu ? prior_ln(m.flu_a, m.flu_b, pos[m.off_flu]) : T(1);
@@ -250,6 +254,7 @@ template <class T> NB_HD NB_INLINE AmpPoint<T> amp_point(const AmpModel<T>& m, c
   a.asp = (m.has_dev && m.has_asp) ? prior_ln(m.asp_a, m.asp_b, pos[m.off_asp]) : T(0);
   a.z = prior_ln(m.zm_a, m.zm_b, pos[m.off_zm]);
   a.scl = m.has_scaling ? prior_ln(m.scl_a, m.scl_b, pos[m.off_scl]) : T(1);
+  a.ctf = m.matern ? prior_ln(m.ctf_a, m.ctf_b, pos[m.off_ctf]) : T(1);
   return a;
 }
 
@@ -273,13 +278,22 @@ template <class T> struct FwdElem {
 template <class T> struct FwdOut {
   AmpModel<T> m; const T* pos;
   T* P; T* partials; unsigned* counter; T* scal;
+  T* ellv; T* cv;     // Matern: per-linearisation tables a_b = du_b/dslope and c_b = du_b/dcutoff
   struct Pre { T l, mu; };
-  NB_HD NB_INLINE Pre load(long b) const { Pre q; q.l = m.ell[b]; q.mu = m.mult[b]; return q; }
+  NB_HD NB_INLINE Pre load(long b) const { Pre q; q.l = m.matern ? m.modes[b] : m.ell[b]; q.mu = m.mult[b]; return q; }
   NB_HD NB_INLINE void put(long b, const Pre& q, T, T, T x1, T, T total, T* acc) const {
     AmpPoint<T> ap = amp_point(m, pos);
-    T l = q.l, llast = m.ell[m.K - 1];
-    T u = ap.slope * l;
-    if (m.has_dev) u += x1 - total * (l / llast);
+    T u;
+    if (m.matern) {
+      T kk = q.l / ap.ctf, lg = log1p(kk * kk);
+      u = T(0.25) * ap.slope * lg;
+      ellv[b] = T(0.25) * lg;
+      cv[b] = T(0.25) * ap.slope * (T(-2) * q.l * q.l / (ap.ctf * ap.ctf * ap.ctf)) / (T(1) + kk * kk);
+    } else {
+      T l = q.l, llast = m.ell[m.K - 1];
+      u = ap.slope * l;
+      if (m.has_dev) u += x1 - total * (l / llast);
+    }
     T Pb = nb_exp(u);
     P[b] = Pb;
     if (b >= 1) acc[0] += q.mu * (m.kind_power ? Pb : Pb * Pb);
@@ -291,6 +305,8 @@ template <class T> struct FwdOut {
       T S = block_total(ctx, partials, ctx.nblk, 1, scratch);
       if (ctx.tid == 0) {
         AmpPoint<T> ap = amp_point(m, pos);
+        if (m.matern && !m.renorm) S = m.V;       // norm = 1: amp = scale sqrt(V) shape (see AmpTabBody)
+        scal[SC_CTF] = ap.ctf;
         scal[SC_S] = S; scal[SC_FLU] = ap.flu; scal[SC_SLOPE] = ap.slope; scal[SC_SIG] = ap.sig;
         scal[SC_ASP] = ap.asp; scal[SC_Z] = ap.z; scal[SC_SCALING] = ap.scl;
         scal[SC_TWLAST] = m.has_dev ? total : T(0);
@@ -299,13 +315,14 @@ template <class T> struct FwdOut {
   }
 };
 // A_b (with A_0 = z V), wS_b, sum wS_b l_b
-template <class T> struct AmpTabParams { AmpModel<T> m; const T* P; T* amp; T* wS; T* partials; unsigned* counter; T* scal; };
+template <class T> struct AmpTabParams { AmpModel<T> m; const T* P; T* amp; T* wS; T* partials; unsigned* counter; T* scal; const T* ellv; const T* cv; };
 template <class T> struct AmpTabBody {
   typedef AmpTabParams<T> Params;
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
     const AmpModel<T>& m = p.m;
     T S = p.scal[SC_S], flu = p.scal[SC_FLU], z = p.scal[SC_Z];
-    T acc = 0;
+    T acc = 0, acc2 = 0;
+    const bool norm = !m.matern || m.renorm;
     long b0 = (long)ctx.bid * SCAN_CH;
     NB_FOR(ctx, i, SCAN_CH) {
       long b = b0 + i;
@@ -313,15 +330,18 @@ template <class T> struct AmpTabBody {
       T Pb = p.P[b], A, w;
       if (m.kind_power) { A = flu * m.V * nb_sqrt(Pb / S); w = m.mult[b] * Pb / S; }
       else { A = flu * m.V * Pb / nb_sqrt(S); w = T(2) * m.mult[b] * Pb * Pb / S; }
+      if (!norm) w = 0;
       if (b == 0) { A = z * m.V; w = 0; }
       p.amp[b] = A; p.wS[b] = w;
-      acc += w * m.ell[b];
+      acc += w * p.ellv[b];
+      if (p.cv) acc2 += w * p.cv[b];
     }
-    acc = ctx.block_sum(acc, smem);
-    if (ctx.tid == 0) p.partials[ctx.bid] = acc;
+    { T v2[2] = {acc, acc2}; ctx.template block_sum_n<2>(v2, smem); acc = v2[0]; acc2 = v2[1]; }
+    if (ctx.tid == 0) { p.partials[2 * ctx.bid] = acc; p.partials[2 * ctx.bid + 1] = acc2; }
     if (ctx.last_block(p.counter)) {
-      T c = block_total(ctx, p.partials, ctx.nblk, 1, smem);
-      if (ctx.tid == 0) p.scal[SC_CWL] = c;
+      T c = block_total(ctx, p.partials, ctx.nblk, 2, smem);
+      T c2 = block_total(ctx, p.partials + 1, ctx.nblk, 2, smem);
+      if (ctx.tid == 0) { p.scal[SC_CWL] = c; p.scal[SC_CWC] = c2; }
     }
   }
 };
@@ -346,14 +366,15 @@ template <class T> struct JvpElem {
   }
 };
 template <class T> struct JvpOut {
-  AmpModel<T> m; const T* pos; const T* t; const T* wS; const T* amp;
+  AmpModel<T> m; const T* pos; const T* t; const T* wS; const T* amp; const T* ellv; const T* cv;
   cplx<T>* ad; T* partials; unsigned* counter; T* scal;   // ad[b] = (A_b, du_b)
-  struct Pre { T l, w, A; };
-  NB_HD NB_INLINE Pre load(long b) const { Pre q; q.l = m.ell[b]; q.w = wS[b]; q.A = amp[b]; return q; }
+  struct Pre { T l, w, A, c; };
+  NB_HD NB_INLINE Pre load(long b) const { Pre q; q.l = ellv[b]; q.w = wS[b]; q.A = amp[b]; q.c = cv ? cv[b] : T(0); return q; }
   NB_HD NB_INLINE void put(long b, const Pre& q, T, T, T x1, T, T total, T* acc) const {
-    T l = q.l, llast = m.ell[m.K - 1];
+    T l = q.l;
     T d = m.slp_b * t[m.off_slp] * l;
-    if (m.has_dev) d += x1 - total * (l / llast);
+    if (m.matern) d += q.c * (scal[SC_CTF] * m.ctf_b * t[m.off_ctf]);
+    if (m.has_dev) d += x1 - total * (l / m.ell[m.K - 1]);
     ad[b] = cmake<T>(q.A, d);
     acc[0] += q.w * d;
   }
@@ -378,6 +399,7 @@ template <class T> struct SegSumParams {
   AmpModel<T> m; const T* W; const int* order; const int* offs; const T* amp;
   T* g; T* abar /* optional raw bin sums */; T* partials /* [nblk][2] */; unsigned* counter; T* scal;
   const T* abar_in;   // if set: skip the gather, take the (all-reduced) bin sums from here
+  const T* ellv; const T* cv;
   int lg_lpb;   // log2(lanes per bin); 256 threads -> 256 >> lg_lpb bins per block
 };
 template <class T> struct SegSumBody {
@@ -406,7 +428,7 @@ template <class T> struct SegSumBody {
       sm[i] = s;
     }
     ctx.sync();
-    T a0 = 0, a1 = 0;
+    T a0 = 0, a1 = 0, a2 = 0;
     NB_FOR(ctx, i, bpb) {
       long b = b0 + i;
       if (b < m.K) {
@@ -417,21 +439,24 @@ template <class T> struct SegSumBody {
           T gb = (b == 0) ? T(0) : abar * p.amp[b];
           p.g[b] = gb;
           if (b == 0) p.scal[SC_ABAR0] = abar;
-          a0 += gb; a1 += gb * m.ell[b];
+          a0 += gb; a1 += gb * p.ellv[b];
+          if (p.cv) a2 += gb * p.cv[b];
         }
       }
     }
     if (!p.g) return;
     void* scratch = reinterpret_cast<void*>(sm + 256);
-    { T v2[2] = {a0, a1}; ctx.template block_sum_n<2>(v2, scratch); a0 = v2[0]; a1 = v2[1]; }
-    if (ctx.tid == 0) { p.partials[2 * ctx.bid] = a0; p.partials[2 * ctx.bid + 1] = a1; }
+    { T v3[3] = {a0, a1, a2}; ctx.template block_sum_n<3>(v3, scratch); a0 = v3[0]; a1 = v3[1]; a2 = v3[2]; }
+    if (ctx.tid == 0) { p.partials[3 * ctx.bid] = a0; p.partials[3 * ctx.bid + 1] = a1; p.partials[3 * ctx.bid + 2] = a2; }
     if (ctx.last_block(p.counter)) {
-      T sg = block_total(ctx, p.partials, ctx.nblk, 2, scratch);
-      T sgl = block_total(ctx, p.partials + 1, ctx.nblk, 2, scratch);
+      T sg = block_total(ctx, p.partials, ctx.nblk, 3, scratch);
+      T sgl = block_total(ctx, p.partials + 1, ctx.nblk, 3, scratch);
+      T sgc = block_total(ctx, p.partials + 2, ctx.nblk, 3, scratch);
       if (ctx.tid == 0) {
         T kappa = m.kind_power ? T(0.5) : T(1);
-        p.scal[SC_SG] = sg; p.scal[SC_SGL] = sgl;
+        p.scal[SC_SG] = sg; p.scal[SC_SGL] = sgl; p.scal[SC_SGC] = sgc;
         p.scal[SC_UBL] = kappa * sgl - T(0.5) * sg * p.scal[SC_CWL];   // sum_b ubar_b l_b
+        p.scal[SC_UBC] = kappa * sgc - T(0.5) * sg * p.scal[SC_CWC];   // sum_b ubar_b c_b (Matern cutoff)
       }
     }
   }
@@ -501,6 +526,7 @@ template <class T> struct VjpOut {
       if (ctx.tid == 0) {
         if (m.has_flu) leaf(m.off_flu, scal_in[SC_SG] * m.flu_b, dot);
         leaf(m.off_slp, scal_in[SC_UBL] * m.slp_b, dot);
+        if (m.matern) leaf(m.off_ctf, scal_in[SC_UBC] * scal_in[SC_CTF] * m.ctf_b, dot);
         if (m.has_dev) {
           leaf(m.off_flx, sigbar * scal_in[SC_SIG] * m.flx_b, dot);
           if (m.has_asp) leaf(m.off_asp, aspbar * scal_in[SC_ASP] * m.asp_b, dot);

@@ -20,6 +20,10 @@ template <class T> void Model<T>::init(Plan<T>* plan_, const nb200_model_desc& d
   std::memset(&am, 0, sizeof(am));
   am.K = g.K; am.kind_power = d.kind_power; am.has_flu = d.has_fluctuations; am.has_asp = d.has_asperity;
   am.has_dev = d.has_deviations && g.K > 2; am.has_scaling = d.has_scaling;
+  am.matern = d.amplitude_type == 1; am.renorm = d.renormalize_amplitude;
+  am.ctf_a = (T)d.cutoff_a; am.ctf_b = (T)d.cutoff_b; am.off_ctf = d.off_cutoff;
+  if (d.amplitude_type != 0 && d.amplitude_type != 1) throw Error{"nb200: amplitude_type must be 0 (non-parametric) or 1 (Matern)"};
+  if (am.matern && am.has_dev) throw Error{"nb200: the Matern amplitude has no spectrum deviations"};
   am.V = (T)g.V;
   am.flu_a = (T)d.fluct_a; am.flu_b = (T)d.fluct_b; am.slp_a = (T)d.slope_a; am.slp_b = (T)d.slope_b;
   am.flx_a = (T)d.flex_a; am.flx_b = (T)d.flex_b; am.asp_a = (T)d.asp_a; am.asp_b = (T)d.asp_b;
@@ -36,17 +40,19 @@ template <class T> void Model<T>::init(Plan<T>* plan_, const nb200_model_desc& d
   if (am.has_dev) { chk(d.off_flex, 1, "flexibility"); chk(d.off_spectrum, 2 * (int64_t)(g.K - 2), "spectrum"); }
   if (am.has_dev && am.has_asp) chk(d.off_asp, 1, "asperity");
   if (am.has_scaling) chk(d.off_scaling, 1, "scaling");
+  if (am.matern) chk(d.off_cutoff, 1, "cutoff");
   offset_mean = (T)d.offset_mean;
   std::vector<T> e(g.K), mu(g.K), dtv(g.logvol.size());
   for (int b = 0; b < g.K; ++b) { e[b] = (T)g.rel[b]; mu[b] = (T)g.mult[b]; }
   for (size_t j = 0; j < dtv.size(); ++j) dtv[j] = (T)g.logvol[j];
   ell.upload(e); multT.upload(mu); dt.upload(dtv);
   am.ell = ell.p; am.mult = multT.p; am.dt = dt.p;
+  { std::vector<T> kk(g.K); for (int b = 0; b < g.K; ++b) kk[b] = (T)g.um[b]; modes.upload(kk); am.modes = modes.p; }
   nchunksK = (g.K + SCAN_CH - 1) / SCAN_CH;
   nchunksJ = std::max(1, (g.K - 2 + SCAN_CH - 1) / SCAN_CH);
   agg.alloc(nchunksK + 1); preaff.alloc(nchunksK + 2);
   ad.alloc(g.K); gbuf.alloc(g.K);
-  size_t np = std::max<size_t>(3 * (size_t)nchunksK + 3, 2 * (size_t)P->seg_grid() + 2);
+  size_t np = std::max<size_t>(3 * (size_t)nchunksK + 3, 3 * (size_t)P->seg_grid() + 3);
   np = std::max<size_t>(np, 4 * 2048);
   partials.alloc(np);
   counters.alloc(16);
@@ -290,7 +296,7 @@ int nb200_cf_apply_adjoint(nb200_plan* plan, void* stream, const void* amp, cons
     P.run_p5(st, e);
     if (amp_bar) {
       SegSumParams<TT> ps; std::memset(&ps, 0, sizeof(ps));
-      ps.m.K = P.g.K; ps.W = P.W.p; ps.order = P.w_order.p; ps.offs = P.w_offs.p; ps.abar = (TT*)amp_bar; ps.lg_lpb = P.seg_lg_lpb;
+      ps.m.K = P.g.K; ps.W = P.W.p; ps.order = P.w_order.p; ps.offs = P.w_offs.p; ps.abar = (TT*)amp_bar; ps.lg_lpb = P.seg_lg_lpb; ps.ellv = nullptr; ps.cv = nullptr;
       launch<SegSumBody<TT>>(P.seg_grid(), 256, (256 + 64) * sizeof(TT), st, ps);
     }
   })

@@ -52,7 +52,7 @@ template <class T> struct Model : ModelBase {
   int lh_kind = LH_GAUSS, nl_exp = 1;
   bool have_lh = false;
   T w_scalar = 1;
-  DevBuf<T> ell, multT, dt, data, w_arr;
+  DevBuf<T> ell, multT, dt, modes, data, w_arr;
   bool has_w_arr = false;
   // chain workspaces
   DevBuf<Aff<T>> agg, preaff;
@@ -70,7 +70,8 @@ template <class T> struct Model : ModelBase {
 
 template <class T> struct Lin : LinBase {
   Model<T>* M = nullptr;
-  DevBuf<T> pos, amp, wS, Pb, s, jl, scal;
+  DevBuf<T> pos, amp, wS, Pb, s, jl, scal, ellv_buf, cv_buf;
+  const T* ellv = nullptr; const T* cv = nullptr;   // effective du/dslope and du/dcutoff tables (Matern: per linearisation)
   bool valid = false;
 
   void init(Model<T>* m) {
@@ -78,6 +79,8 @@ template <class T> struct Lin : LinBase {
     const GridInfo& g = m->P->g;
     pos.alloc((size_t)m->am.L); amp.alloc(g.K); wS.alloc(g.K); Pb.alloc(g.K);
     s.alloc((size_t)m->P->local_position_grid()); jl.alloc((size_t)m->P->local_position_grid()); scal.alloc(SC_COUNT);
+    if (m->am.matern) { ellv_buf.alloc(g.K); cv_buf.alloc(g.K); ellv = ellv_buf.p; cv = cv_buf.p; }
+    else { ellv = m->am.ell; cv = nullptr; }
   }
 
   // forward amplitude chain at this->pos
@@ -90,11 +93,11 @@ template <class T> struct Lin : LinBase {
       launch<ScanAggBody<T, FwdElem<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
     }
     FwdOut<T> fo; fo.m = m.am; fo.pos = pos.p; fo.P = Pb.p; fo.partials = m.partials.p;
-    fo.counter = m.counters.p; fo.scal = scal.p;
+    fo.counter = m.counters.p; fo.scal = scal.p; fo.ellv = ellv_buf.p; fo.cv = cv_buf.p;
     ScanApplyParams<T, FwdElem<T>, FwdOut<T>> pc; pc.n = K; pc.elem = el; pc.out = fo; pc.pre = m.preaff.p; pc.nchunks = nch;
     launch<ScanApplyBody<T, FwdElem<T>, FwdOut<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
     AmpTabParams<T> pt2; pt2.m = m.am; pt2.P = Pb.p; pt2.amp = amp.p; pt2.wS = wS.p; pt2.partials = m.partials.p;
-    pt2.counter = m.counters.p + 1; pt2.scal = scal.p;
+    pt2.counter = m.counters.p + 1; pt2.scal = scal.p; pt2.ellv = ellv; pt2.cv = cv;
     launch<AmpTabBody<T>>(m.nchunksK, SCAN_NT, 512, st, pt2);
   }
 
@@ -107,7 +110,7 @@ template <class T> struct Lin : LinBase {
       ScanAggParams<T, JvpElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p; pa.pre = m.preaff.p; pa.counter = m.counters.p + 5;
       launch<ScanAggBody<T, JvpElem<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
     }
-    JvpOut<T> jo; jo.m = m.am; jo.pos = pos.p; jo.t = t; jo.wS = wS.p; jo.amp = amp.p; jo.ad = m.ad.p;
+    JvpOut<T> jo; jo.m = m.am; jo.pos = pos.p; jo.t = t; jo.wS = wS.p; jo.amp = amp.p; jo.ellv = ellv; jo.cv = cv; jo.ad = m.ad.p;
     jo.partials = m.partials.p; jo.counter = m.counters.p + 2; jo.scal = scal.p;
     ScanApplyParams<T, JvpElem<T>, JvpOut<T>> pc; pc.n = K; pc.elem = el; pc.out = jo; pc.pre = m.preaff.p; pc.nchunks = nch;
     launch<ScanApplyBody<T, JvpElem<T>, JvpOut<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
@@ -126,7 +129,7 @@ template <class T> struct Lin : LinBase {
     Model<T>& m = *M; Plan<T>& P = *m.P;
     SegSumParams<T> ps; ps.m = m.am; ps.W = P.W.p; ps.order = P.w_order.p; ps.offs = P.w_offs.p; ps.amp = amp.p;
     ps.g = abar_out ? nullptr : m.gbuf.p; ps.abar = abar_out; ps.abar_in = abar_in; ps.partials = m.partials.p;
-    ps.counter = m.counters.p + 3; ps.scal = scal.p; ps.lg_lpb = P.seg_lg_lpb;
+    ps.counter = m.counters.p + 3; ps.scal = scal.p; ps.lg_lpb = P.seg_lg_lpb; ps.ellv = ellv; ps.cv = cv;
     launch<SegSumBody<T>>(P.seg_grid(), 256, (256 + 64) * sizeof(T), st, ps);
   }
   void vjp_chain(stream_t st, T* out, const T* add, const T* p3_src, int n_p3, const T* p5_src, int n_p5, T scl_factor) {

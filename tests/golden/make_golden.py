@@ -67,6 +67,12 @@ CASES = {
     "g2d_3x3": dict(shape=(3, 3), distances=0.1, offset_mean=0.0, offset_std=(0.1, 0.1),
                     fluctuations=(3.0, 2.0), loglogavgslope=(4.0, 1.0), flexibility=(3.0, 2.0),
                     asperity=(0.2, 2e-2), lh="gauss", seed=42),
+    # Matern amplitude (test/test_re/test_correlated_field.py:195-228: re kind="amplitude",
+    # renormalize_amplitude=False == cl add_fluctuations_matern defaults)
+    "m2d_16x8": dict(shape=(16, 8), distances=(0.1, 0.3), offset_mean=0.2, offset_std=(0.1, 0.1),
+                     matern=dict(scale=(1.0, 1.0), cutoff=(1.0, 0.5), loglogslope=(-3.0, 0.5)), lh="gauss", seed=9),
+    "m3d_8x4x8": dict(shape=(8, 4, 8), distances=0.5, offset_mean=0.0, offset_std=(0.1, 0.1),
+                      matern=dict(scale=(3.0, 2.0), cutoff=(0.3, 0.05), loglogslope=(-4.0, 0.5)), lh="poisson", seed=10),
 }
 
 
@@ -74,8 +80,11 @@ def build_cl(ift, c):
     sp = ift.RGSpace(c["shape"], c["distances"])
     cfm = ift.CorrelatedFieldMaker("cf")
     cfm.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
-    cfm.add_fluctuations(sp, c["fluctuations"], c["flexibility"], c["asperity"],
-                         c["loglogavgslope"], prefix="ax1")
+    if "matern" in c:
+        cfm.add_fluctuations_matern(sp, prefix="ax1", **c["matern"])
+    else:
+        cfm.add_fluctuations(sp, c["fluctuations"], c["flexibility"], c["asperity"],
+                             c["loglogavgslope"], prefix="ax1")
     cf = cfm.finalize(prior_info=0)
     return cf
 
@@ -109,8 +118,12 @@ def main():
         cf = build_cl(ift, c)
         orc = CorrelatedFieldOracle("cf")
         orc.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
-        orc.add_fluctuations(c["shape"], c["distances"], c["fluctuations"], c["loglogavgslope"],
-                             c["flexibility"], c["asperity"], prefix="ax1", non_parametric_kind="power")
+        if "matern" in c:
+            orc.add_fluctuations_matern(c["shape"], c["distances"], renormalize_amplitude=False, prefix="ax1",
+                                        non_parametric_kind="amplitude", **c["matern"])
+        else:
+            orc.add_fluctuations(c["shape"], c["distances"], c["fluctuations"], c["loglogavgslope"],
+                                 c["flexibility"], c["asperity"], prefix="ax1", non_parametric_kind="power")
         orc.finalize()
         lay = Layout(orc.domain)
         rng = np.random.default_rng(c["seed"])

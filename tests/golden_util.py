@@ -30,6 +30,10 @@ CASES = {
     "g2d_3x3": dict(shape=(3, 3), distances=0.1, offset_mean=0.0, offset_std=(0.1, 0.1),
                     fluctuations=(3.0, 2.0), loglogavgslope=(4.0, 1.0), flexibility=(3.0, 2.0),
                     asperity=(0.2, 2e-2), lh="gauss", seed=42),
+    "m2d_16x8": dict(shape=(16, 8), distances=(0.1, 0.3), offset_mean=0.2, offset_std=(0.1, 0.1),
+                     matern=dict(scale=(1.0, 1.0), cutoff=(1.0, 0.5), loglogslope=(-3.0, 0.5)), lh="gauss", seed=9),
+    "m3d_8x4x8": dict(shape=(8, 4, 8), distances=0.5, offset_mean=0.0, offset_std=(0.1, 0.1),
+                      matern=dict(scale=(3.0, 2.0), cutoff=(0.3, 0.05), loglogslope=(-4.0, 0.5)), lh="poisson", seed=10),
 }
 
 
@@ -49,8 +53,12 @@ def build_oracle(c):
     from oracle import CorrelatedFieldOracle, GaussianOracle, PoissonianOracle, SignalOracle
     cf = CorrelatedFieldOracle("cf")
     cf.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
-    cf.add_fluctuations(c["shape"], c["distances"], c["fluctuations"], c["loglogavgslope"],
-                        c["flexibility"], c["asperity"], prefix="ax1", non_parametric_kind="power")
+    if "matern" in c:
+        cf.add_fluctuations_matern(c["shape"], c["distances"], renormalize_amplitude=False, prefix="ax1",
+                                   non_parametric_kind="amplitude", **c["matern"])
+    else:
+        cf.add_fluctuations(c["shape"], c["distances"], c["fluctuations"], c["loglogavgslope"],
+                            c["flexibility"], c["asperity"], prefix="ax1", non_parametric_kind="power")
     cf.finalize()
     return cf
 

@@ -19,8 +19,12 @@ POW2_CASES = [n for n in sorted(CASES) if all((s & (s - 1)) == 0 for s in CASES[
 def build_product(c, rt, dtype=torch.float64, kind="power", convention="non_canonical_hartley"):
     cfm = nb.CorrelatedFieldMaker("cf", runtime=rt, dtype=dtype, hartley_convention=convention)
     cfm.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
-    cfm.add_fluctuations(c["shape"], c["distances"], c["fluctuations"], c["loglogavgslope"], c["flexibility"],
-                         c["asperity"], prefix="ax1", non_parametric_kind=kind)
+    if "matern" in c:
+        cfm.add_fluctuations_matern(c["shape"], c["distances"], renormalize_amplitude=c.get("renorm", False), prefix="ax1",
+                                    non_parametric_kind=c.get("kind", "amplitude"), **c["matern"])
+    else:
+        cfm.add_fluctuations(c["shape"], c["distances"], c["fluctuations"], c["loglogavgslope"], c["flexibility"],
+                             c["asperity"], prefix="ax1", non_parametric_kind=kind)
     return cfm.finalize()
 
 
@@ -233,3 +237,31 @@ def check_against_oracle(rt, shape, distances, lh_kind="gauss", seed=11, tol=1e-
     u = rng.standard_normal(shape)
     assert tree_err(lh.left_sqrt_metric(tp, u), olh.left_sqrt_metric(pos, u)) < tol
     assert rel_err(t2n(lh.right_sqrt_metric(tp, tt)), olh.right_sqrt_metric(pos, tan)) < tol
+
+
+def check_matern_variants(rt):
+    """Matern amplitude with renormalisation and both kinds (no nifty.cl fixture: cl has no such switch) vs the oracle."""
+    for kind in ("amplitude", "power"):
+        for renorm in (True, False):
+            c = dict(shape=(16, 16), distances=0.2, offset_mean=0.1, offset_std=(0.1, 0.1), lh="gauss", kind=kind, renorm=renorm,
+                     matern=dict(scale=(1.0, 0.5), cutoff=(0.8, 0.3), loglogslope=(-3.0, 0.5)))
+            ocf = oracle.CorrelatedFieldOracle("cf")
+            ocf.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+            ocf.add_fluctuations_matern(c["shape"], c["distances"], renormalize_amplitude=renorm, prefix="ax1",
+                                        non_parametric_kind=kind, **c["matern"])
+            ocf.finalize()
+            osig = oracle.SignalOracle(ocf, "exp")
+            lay = oracle.Layout(osig.domain)
+            rng = np.random.default_rng(17)
+            pos, tan = lay.random(rng), lay.random(rng)
+            pos = {k: 0.5 * v for k, v in pos.items()}
+            data = osig(pos) + 0.3 * rng.standard_normal(c["shape"])
+            olh = oracle.GaussianOracle(data, 4.0, osig)
+            lh = build_product_lh(c, dict(data=data, noise_cov_inv=4.0), rt)
+            tp = {k: torch.as_tensor(v) for k, v in pos.items()}
+            tt = {k: torch.as_tensor(v) for k, v in tan.items()}
+            e, grad = lh.energy_and_gradient(tp)
+            oe, ograd = olh.energy_and_gradient(pos)
+            assert abs(e - oe) <= 1e-10 * abs(oe), (kind, renorm)
+            assert tree_err(grad, ograd) < 1e-10, (kind, renorm)
+            assert tree_err(lh.metric(tp, tt), olh.metric(pos, tan)) < 1e-10, (kind, renorm)

@@ -53,6 +53,10 @@ def test_cg(rt):
     pc.check_cg(rt)
 
 
+def test_matern_variants(rt):
+    pc.check_matern_variants(rt)
+
+
 def test_multichunk_amplitude_chain(rt):
     """K > 2048 mode bins: the amplitude scans span several chunks (carry-in from chunk aggregates)."""
     pc.check_against_oracle(rt, (128, 256), (0.01, 0.02))
