@@ -437,15 +437,16 @@ class Lin:
             self._abar = self.rt.zeros((self.model.plan.K,), self.model.plan.dtype)
             self._xs = self.rt.zeros((4,), self.model.plan.dtype)
 
-    def _dist_adjoint_tail(self, t, out, add_identity, scaled):
+    def _dist_adjoint_tail(self, t, out, add_identity, scaled, grad=False):
         plan = self.model.plan
         tin = t if add_identity else None
+        f5 = int(add_identity) | (4 if grad else 0)
         if plan.nchunks > 1:      # PCb chunk -> exchange 2 chunk -> P5 chunk, then the bin sums
             self._pipelined(2, 13, lambda c: self._phase(23, inp=tin, out=out, flag=int(add_identity), chunk=c))
-            self._phase(24, inp=tin, out=out, flag=int(add_identity))
+            self._phase(24, inp=tin, out=out, flag=f5)
         else:
             plan.exchange(2)
-            self._phase(5, inp=tin, out=out, flag=int(add_identity))
+            self._phase(5, inp=tin, out=out, flag=f5)
         plan.comm.allreduce_sum(self._abar)
         plan.comm.allreduce_sum(self._xs)
         self._phase(6, inp=t if add_identity else None, out=out, flag=int(add_identity) | (2 if scaled else 0))
@@ -453,19 +454,24 @@ class Lin:
 
     def update(self, pos: torch.Tensor, want_grad=False, add_prior=False):
         if self.model.plan.dist:
-            if want_grad:
-                raise NB200Error("gradients are not available on slab-decomposed plans yet")
             self._dist_buffers()
             plan = self.model.plan
+            g = int(bool(want_grad))
             if plan.nchunks > 1:
                 self._phase(10, inp=pos)
-                self._pipelined(1, 11, lambda c: self._phase(12, chunk=c))
+                self._pipelined(1, 11, lambda c: self._phase(12, chunk=c, flag=g))
                 self._phase(14)
             else:
                 self._phase(0, inp=pos)
                 plan.exchange(1)
-                self._phase(1)
-            return None
+                self._phase(1, flag=g)
+            if not want_grad:
+                return None
+            if plan.nchunks == 1:
+                self._phase(13)                   # PCb of dE/df (code 1 stops after P3)
+            grad = self._vec()
+            # gradient = J^T dE/ds (+ pos): the adjoint tail with `pos` as the additive term
+            return self._dist_adjoint_tail(pos, grad, bool(add_prior), True, grad=True)
         grad = self._vec() if want_grad else None
         self.rt.api.call("nb200_lin_update", self._h, self.rt.stream(), self.rt.ptr(pos), self.rt.ptr(grad), int(add_prior))
         return grad

@@ -61,10 +61,11 @@ def _norm(v: torch.Tensor, ord) -> float:
 
 def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, absdelta=None, resnorm=None,
         norm_ord=None, tol=1e-5, atol=0.0, miniter=None, maxiter=None, name=None, time_threshold=None,
-        _raise_nonposdef=True, check_every=4) -> CGResults:
+        _raise_nonposdef=True, check_every=4, vdot=None, vnorm=None) -> CGResults:
+    """``vdot`` / ``vnorm``: reductions to use in the host loop (slab-decomposed vectors: all-reduced ones)."""
     norm_ord = 2 if norm_ord is None else norm_ord
-    vdot = lambda a, b: float(torch.dot(a, b))
-    vnorm = _norm
+    vdot = (lambda a, b: float(torch.dot(a, b))) if vdot is None else vdot
+    vnorm = _norm if vnorm is None else vnorm
     if isinstance(mat, HamiltonianMetric) and mat.distributed:
         # slab-decomposed field: the recurrences run in the host loop below, reductions are all-reduced
         if mat.likelihood is None:

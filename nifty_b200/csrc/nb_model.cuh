@@ -259,7 +259,8 @@ template <class T> struct Lin : LinBase {
         op.invV = T(1.0 / P.g.V); op.offset = m.offset_mean; op.sc_ptr = scal.p + SC_SCALING;
         op.lh_kind = m.lh_kind; op.nl_exp = m.nl_exp; op.data = m.data.p; op.w_scalar = m.w_scalar;
         op.w_arr = m.has_w_arr ? m.w_arr.p : nullptr; op.s_out = s.p; op.jl_out = jl.p; op.partials = P.p3part.p;
-        P.template run_p3<true, false>(st, op, l3, n3);
+        if (flag & 1) P.template run_p3<true, true>(st, op, l3, n3);      // + first adjoint pass of dE/df (gradient)
+        else P.template run_p3<true, false>(st, op, l3, n3);
         if (code == 1) { reduce_p3(scal.p + SC_ENERGY, scal.p + SC_SUMCOT); valid = true; }
       } break;
       case 14: reduce_p3(scal.p + SC_ENERGY, scal.p + SC_SUMCOT); valid = true; break;
@@ -282,12 +283,12 @@ template <class T> struct Lin : LinBase {
         P.template run_p3<false, true>(st, op, l3, n3);
         if (code == 4) P.run_pc(st, true);
       } break;
-      case 23: P.run_p5(st, epi_adjoint(out, flag ? in : nullptr, flag != 0), l5, n5); break;   // P5 (chunk)
+      case 23: P.run_p5(st, epi_adjoint(out, (flag & 1) ? in : nullptr, (flag & 1) != 0), l5, n5); break;   // P5 (chunk)
       case 5: case 24: {     // adjoint.3: (P5 for code 5) local bin sums, xs = {p3 sum, xi dot}
-        if (code == 5) P.run_p5(st, epi_adjoint(out, flag ? in : nullptr, flag != 0));
+        if (code == 5) P.run_p5(st, epi_adjoint(out, (flag & 1) ? in : nullptr, (flag & 1) != 0));
         seg_sum(st, abar, nullptr);
-        reduce_p3(xs, nullptr);
-        if (flag) {
+        if (flag & 4) reduce_p3(nullptr, xs); else reduce_p3(xs, nullptr);   // bit 2: the gradient needs sum dE/df (column 1)
+        if (flag & 1) {
           ReduceColsParams<T> pd; pd.partials = P.p5part.p; pd.n = P.c5.grid; pd.ncol = 1; pd.out0 = xs + 1; pd.out1 = nullptr;
           launch<ReduceColsBody<T>>(1, 256, 512, st, pd);
         } else {

@@ -218,7 +218,7 @@ class LikelihoodWithModel:
         lin, grad = self.lin_at(flat, want_grad=True, add_prior=add_prior)
         e = lin.energy()
         if add_prior:
-            e += 0.5 * float(torch.dot(flat, flat))
+            e += 0.5 * self.vdot(flat, flat)
         return e, self.signal.like(pos, grad)
 
     def metric(self, pos, tangents):

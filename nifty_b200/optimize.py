@@ -26,17 +26,20 @@ class OptimizeResults(NamedTuple):
 def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reduction_factor=0.1, old_fval=None, absdelta=None,
                norm_ord=None, xtol=1e-5, fun_and_grad: Optional[Callable] = None, hessp: Optional[Callable] = None,
                cg=_cg, name=None, time_threshold=None, cg_kwargs=None, custom_gradnorm: Optional[Callable] = None,
-               hessp_at: Optional[Callable] = None) -> OptimizeResults:
+               hessp_at: Optional[Callable] = None, vdot: Optional[Callable] = None,
+               vnorm: Optional[Callable] = None) -> OptimizeResults:
     """``hessp(pos, v)`` as in the reference; ``hessp_at(pos)`` may instead return an operator object
     (e.g. a :class:`~nifty_b200.conjugate_gradient.HamiltonianMetric`) so that the inner CG runs on the device."""
     norm_ord = 1 if norm_ord is None else norm_ord
+    _dot = (lambda a, b: float(torch.dot(a, b))) if vdot is None else vdot
+    _nrm = _norm if vnorm is None else vnorm
     miniter = 0 if miniter is None else miniter
     maxiter = 200 if maxiter is None else maxiter
     pos = x0.clone()
     xtol = xtol * pos.numel()
     cg_kwargs = {} if cg_kwargs is None else dict(cg_kwargs)
     cg_name = cg_kwargs.pop("name", None)
-    gradnorm = (lambda v: _norm(v, norm_ord)) if custom_gradnorm is None else custom_gradnorm
+    gradnorm = (lambda v: _nrm(v, norm_ord)) if custom_gradnorm is None else custom_gradnorm
     if fun_and_grad is None:
         raise ValueError("`fun_and_grad` is required on the B200 path (no automatic differentiation)")
     energy, g = fun_and_grad(pos)
@@ -49,9 +52,11 @@ def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reductio
             cg_absdelta = energy_reduction_factor * (old_fval - energy)
         else:
             cg_absdelta = None if absdelta is None else absdelta / 100.0
-        mag_g = _norm(g, cg_kwargs.get("norm_ord", 1))
+        mag_g = _nrm(g, cg_kwargs.get("norm_ord", 1))
         cg_resnorm = min(0.5, np.sqrt(mag_g)) * mag_g
         kw = dict(absdelta=cg_absdelta, resnorm=cg_resnorm, norm_ord=1, name=cg_name, _raise_nonposdef=False)
+        if vdot is not None:
+            kw.update(vdot=vdot, vnorm=vnorm)
         kw.update(cg_kwargs)
         op = hessp_at(pos) if hessp_at is not None else (lambda v, _p=pos: hessp(_p, v))
         res = cg(op, g, **kw)
@@ -70,9 +75,9 @@ def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reductio
                 break
             grad_scaling /= 2
             if ls_it == 5:
-                gam = float(torch.dot(g, g))
+                gam = _dot(g, g)
                 hv = hessp_at(pos)(g) if hessp_at is not None else hessp(pos, g)   # re-linearise at pos
-                curv = float(torch.dot(g, hv))
+                curv = _dot(g, hv)
                 nhev += 1
                 grad_scaling = 1.0
                 dd = gam / curv * g

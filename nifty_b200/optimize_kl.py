@@ -162,7 +162,7 @@ class OptimizeVI:
         for lin, x in zip(self._lins, pts):
             g = lin.update(x, want_grad=True, add_prior=True)
             acc[2:] += g.to(torch.float64)
-            acc[0] += lin.energy() + 0.5 * float(torch.dot(x, x))
+            acc[0] += lin.energy() + 0.5 * lh.vdot(x, x)
             acc[1] += 1.0
         self._n_active = len(pts)
         acc = self.comm.allreduce_sum(acc)
@@ -193,7 +193,11 @@ class OptimizeVI:
                 fg(x)
             return self.kl_metric(t)
 
-        return minimize(None, x0=samples.pos, fun_and_grad=fg, hessp=hessp, **(minimize_kwargs or {}))
+        kw = dict(minimize_kwargs or {})
+        if self.likelihood.signal.cf.plan.dist:      # slab-decomposed latent vectors: all-reduced reductions
+            kw.setdefault("vdot", self.likelihood.vdot)
+            kw.setdefault("vnorm", self.likelihood.vnorm)
+        return minimize(None, x0=samples.pos, fun_and_grad=fg, hessp=hessp, **kw)
 
     # -- driver -------------------------------------------------------------------------------------------
     def init_state(self, key, *, n_samples, draw_linear_kwargs=None, nonlinearly_update_kwargs=None, kl_kwargs=None,

@@ -88,6 +88,13 @@ def slab_check(rt, shape, dist_, lh_kind="gauss", seed=3, tol=1e-10):
     ols = olh.left_sqrt_metric(pos, u)
     scale = max(np.max(np.abs(v)) for v in ols.values())
     errs["lsm"] = max(float(np.max(np.abs(ls[k] - ols[k]))) / scale for k in ols)
+    ee, gg = lh.energy_and_gradient(pl, add_prior=True)
+    oe2, og = olh.energy_and_gradient(pos)
+    flat = lay.pack(pos)
+    assert abs(ee - (oe2 + 0.5 * flat @ flat)) <= tol * abs(oe2 + 0.5 * flat @ flat)
+    gg = globalise(gg)
+    scale = max(np.max(np.abs(og[k] + pos[k])) for k in og)
+    errs["gradient"] = max(float(np.max(np.abs(gg[k] - og[k] - pos[k]))) / scale for k in og)
     # MGVI sample draw: distributed CG (host recurrences, all-reduced dot products) against the oracle's
     if lh_kind == "gauss":
         wd, wp = rng.standard_normal(shape), lay.random(rng)
@@ -101,6 +108,16 @@ def slab_check(rt, shape, dist_, lh_kind="gauss", seed=3, tol=1e-10):
         # stochastic draw path (per-rank keys): runs, hyper-parameter leaves identical on all ranks
         r2, _ = nb.draw_linear_residual(lh, pl, 123, cg_kwargs=cgkw)
         hyp = torch.cat((r2[:lh._xi_slice()[0]], r2[lh._xi_slice()[1]:])).to(torch.float64)
+        allh = plan.comm.all_gather(hyp)
+        assert all(torch.equal(allh[0], h) for h in allh)
+        # one KL (Newton-CG) step over the mirrored pair of that sample: energy decreases, replicated leaves stay identical
+        vi = nb.OptimizeVI(lh, 1)
+        smp = nb.Samples(pos=pl, samples=torch.stack((r2, -r2)), keys=None)
+        e0, _ = vi.kl_value_and_grad(pl, smp.residuals)
+        opt = vi.kl_minimize(smp, minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=10)))
+        e1, _ = vi.kl_value_and_grad(opt.x, smp.residuals)
+        assert e1 < e0
+        hyp = torch.cat((opt.x[:lh._xi_slice()[0]], opt.x[lh._xi_slice()[1]:])).to(torch.float64)
         allh = plan.comm.all_gather(hyp)
         assert all(torch.equal(allh[0], h) for h in allh)
     bad = {k: v for k, v in errs.items() if not v < (1e-7 if k == "mgvi_draw" else tol)}
