@@ -11,6 +11,8 @@ the operation every CG iteration of an MGVI sample draw runs (nifty/re/evi.py:83
 * N=1 workload: BASELINE.json configs[1], 2-D correlated field 4096x4096 float64.
 * N>1 (torchrun): the independent MGVI samples are sharded over the ranks (one CG solve per GPU, no
   data-path collective) -> weak scaling; value = products of all ranks / max time.
+* ``--workload cf3d_1024_f64_slab`` (BASELINE.json configs[4], needs --gpus >= 2): ONE field slab-decomposed
+  over the ranks, two pipelined NCCL exchanges + one all-reduce per product -> strong scaling.
 * ``value``: device-resident inputs, CUDA events.  ``e2e``: the public Python API with HOST (pinned)
   buffers, H2D of the tangent and D2H of the result inside the timed region.
 * ``roofline``: the dominant kernel's algorithmic bytes / its CUDA-event duration against the
