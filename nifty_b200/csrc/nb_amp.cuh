@@ -9,10 +9,11 @@
 //     y_{j+1} = y_j + r1_j ,   x_{j+1} = x_j + dt_j y_j + r0_j
 // are ONE scan over affine maps (a,b,c): (x,y) -> (x + a y + b, y + c), composed associatively as
 // (a1+a2, b1+b2+a2 c1, c1+c2).  The cotangent chain is the same recurrence run backwards.
-// Scans are three launches (chunk aggregates, aggregate scan, apply) with fixed chunking, hence
-// bit-reproducible; global sums use per-block partials finished by the last block in fixed order.
+// Scans are two launches (chunk aggregates + their ordered scan in the last block to finish, apply) with
+// fixed chunking, hence bit-reproducible; global sums use per-block partials finished by the last block in fixed order.
 #pragma once
 #include "nb_common.cuh"
+#include <cstdlib>
 
 namespace nb {
 
@@ -104,51 +105,46 @@ template <class T> __device__ NB_INLINE Aff<T> block_scan_aff(Ctx& ctx, Aff<T> v
 #endif
 
 constexpr int SCAN_NT = 256;
-constexpr int SCAN_E = 8;
-constexpr int SCAN_CH = SCAN_NT * SCAN_E;
-
-template <class T> inline size_t scan_smem_bytes() { return (size_t)(SCAN_CH + 80) * sizeof(Aff<T>); }
+// A chunk is SCAN_NT * E elements (E = 4 or 8 per thread, chosen by the host: E = 4 keeps more blocks
+// resident and measured 2-4 % faster per product on large tables; E = 8 lets a table of <= 2048 bins run
+// as a single chunk, i.e. without the aggregate kernel).
+// Staging slot of chunk element i: one pad element per thread run of E, so that the thread-strided
+// accesses el[tid*(E+1) + e] (stride 54 or 30 words: an odd multiple of 2) are free of bank conflicts;
+// without the pad the stride is 48 / 24 words and 8-byte accesses collide 16 / 8 ways.
+template <int E> NB_HH NB_INLINE int sidx(int i) { return i + i / E; }
+template <class T> inline size_t scan_smem_bytes(int E) { return (size_t)(SCAN_NT * E + SCAN_NT + 80) * sizeof(Aff<T>); }
+inline int scan_pick_e(long n) {
+  if (const char* e = std::getenv("NB200_SCAN_E")) { if (e[0] == '4') return 4; if (e[0] == '8') return 8; }   // test / tuning knob
+  return n <= SCAN_NT * 8 ? 8 : 4;
+}
 
 // ---- generic scan: (1) per-chunk aggregates [skipped for a single chunk], (2) apply -----------------
 template <class T, class Elem> struct ScanAggParams { long n; Elem elem; Aff<T>* agg; Aff<T>* pre; unsigned* counter; };
-template <class T, class Elem> struct ScanAggBody {
+template <class T, class Elem, int E> struct ScanAggBody {
   typedef ScanAggParams<T, Elem> Params;
+  static constexpr int CH = SCAN_NT * E, STAGE = CH + SCAN_NT;
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
     Aff<T>* el = reinterpret_cast<Aff<T>*>(smem);
-    long p0 = (long)ctx.bid * SCAN_CH;
-#if defined(NB_EMU) || !defined(NB_SCAN_BATCH)   // batching the SCAN_E evaluations measured 8-25 % slower (registers)
-    NB_FOR(ctx, i, SCAN_CH) el[i] = (p0 + i < p.n) ? p.elem.get(p0 + i) : aff_id<T>();
-#else
-    {   // all SCAN_E element evaluations of a thread are independent: issue their loads together
-      Aff<T> v[SCAN_E];
-#pragma unroll
-      for (int e = 0; e < SCAN_E; ++e) {
-        long pos = p0 + ctx.tid + e * SCAN_NT;
-        v[e] = p.elem.get(pos < p.n ? pos : (p.n > 0 ? p.n - 1 : 0));
-      }
-#pragma unroll
-      for (int e = 0; e < SCAN_E; ++e) {
-        long pos = p0 + ctx.tid + e * SCAN_NT;
-        el[ctx.tid + e * SCAN_NT] = pos < p.n ? v[e] : aff_id<T>();
-      }
-    }
-#endif
+    long p0 = (long)ctx.bid * CH;
+    NB_FOR(ctx, i, CH) el[sidx<E>(i)] = (p0 + i < p.n) ? p.elem.get(p0 + i) : aff_id<T>();
     ctx.sync();
 #ifdef NB_EMU
     Aff<T> tot = aff_id<T>();
-    for (int i = 0; i < SCAN_CH; ++i) tot = aff_compose(tot, el[i]);
+    for (int i = 0; i < CH; ++i) tot = aff_compose(tot, el[sidx<E>(i)]);
 #else
-    Aff<T> a = el[ctx.tid * SCAN_E];
-    for (int e = 1; e < SCAN_E; ++e) a = aff_compose(a, el[ctx.tid * SCAN_E + e]);
+    const Aff<T>* mine_el = el + ctx.tid * (E + 1);
+    Aff<T> a = mine_el[0];
+#pragma unroll
+    for (int e = 1; e < E; ++e) a = aff_compose(a, mine_el[e]);
     Aff<T> tot;
-    block_scan_aff(ctx, a, tot, reinterpret_cast<void*>(el + SCAN_CH));
+    block_scan_aff(ctx, a, tot, reinterpret_cast<void*>(el + STAGE));
 #endif
     if (ctx.tid == 0) p.agg[ctx.bid] = tot;
     // the last block to finish turns the chunk aggregates into exclusive prefixes (pre[c], state
     // before chunk c) and the grand total pre[nblk] -- one ordered block scan instead of two per
     // apply block
     if (ctx.last_block(p.counter)) {
-      void* scratch = reinterpret_cast<void*>(el + SCAN_CH);
+      void* scratch = reinterpret_cast<void*>(el + STAGE);
       const int n = ctx.nblk, per = (n + ctx.nthr - 1) / ctx.nthr;
       const int lo = ctx.tid * per, hi = (lo + per < n) ? lo + per : n;
       Aff<T> v = aff_id<T>();
@@ -160,32 +156,17 @@ template <class T, class Elem> struct ScanAggBody {
     }
   }
 };
-// Out::put(pos, x0, y0, x1, y1, total_x, acc[4]) is called once per element with the state before /
+// Out::put(pos, pre, x0, y0, x1, y1, total_x, acc[4]) is called once per element with the state before /
 // after; Out::finish(ctx, acc, total_x, scratch) runs in every block afterwards.
 template <class T, class Elem, class Out> struct ScanApplyParams { long n; Elem elem; Out out; const Aff<T>* pre; int nchunks; };
-template <class T, class Elem, class Out> struct ScanApplyBody {
+template <class T, class Elem, class Out, int E> struct ScanApplyBody {
   typedef ScanApplyParams<T, Elem, Out> Params;
+  static constexpr int CH = SCAN_NT * E, STAGE = CH + SCAN_NT;
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
     Aff<T>* el = reinterpret_cast<Aff<T>*>(smem);
-    void* scratch = reinterpret_cast<void*>(el + SCAN_CH);
-    long p0 = (long)ctx.bid * SCAN_CH;
-#if defined(NB_EMU) || !defined(NB_SCAN_BATCH)   // batching the SCAN_E evaluations measured 8-25 % slower (registers)
-    NB_FOR(ctx, i, SCAN_CH) el[i] = (p0 + i < p.n) ? p.elem.get(p0 + i) : aff_id<T>();
-#else
-    {   // all SCAN_E element evaluations of a thread are independent: issue their loads together
-      Aff<T> v[SCAN_E];
-#pragma unroll
-      for (int e = 0; e < SCAN_E; ++e) {
-        long pos = p0 + ctx.tid + e * SCAN_NT;
-        v[e] = p.elem.get(pos < p.n ? pos : (p.n > 0 ? p.n - 1 : 0));
-      }
-#pragma unroll
-      for (int e = 0; e < SCAN_E; ++e) {
-        long pos = p0 + ctx.tid + e * SCAN_NT;
-        el[ctx.tid + e * SCAN_NT] = pos < p.n ? v[e] : aff_id<T>();
-      }
-    }
-#endif
+    void* scratch = reinterpret_cast<void*>(el + STAGE);
+    long p0 = (long)ctx.bid * CH;
+    NB_FOR(ctx, i, CH) el[sidx<E>(i)] = (p0 + i < p.n) ? p.elem.get(p0 + i) : aff_id<T>();
     ctx.sync();
     // carry-in of this chunk and the grand total from the chunk aggregates (nchunks > 1)
     Aff<T> carry = aff_id<T>(), grand = aff_id<T>();
@@ -194,14 +175,14 @@ template <class T, class Elem, class Out> struct ScanApplyBody {
     {
       // one host "thread": walk the whole chunk sequentially
       Aff<T> blk = aff_id<T>();
-      for (int i = 0; i < SCAN_CH; ++i) blk = aff_compose(blk, el[i]);
+      for (int i = 0; i < CH; ++i) blk = aff_compose(blk, el[sidx<E>(i)]);
       if (p.nchunks <= 1) grand = blk;
       T acc[4] = {0, 0, 0, 0};
       T x = carry.b, y = carry.c;
-      for (int i = 0; i < SCAN_CH; ++i) {
+      for (int i = 0; i < CH; ++i) {
         long pos = p0 + i;
         if (pos >= p.n) break;
-        Aff<T> a = el[i];
+        Aff<T> a = el[sidx<E>(i)];
         T x1 = x + a.a * y + a.b, y1 = y + a.c;
         p.out.put(pos, p.out.load(pos), x, y, x1, y1, grand.b, acc);
         x = x1; y = y1;
@@ -209,28 +190,30 @@ template <class T, class Elem, class Out> struct ScanApplyBody {
       p.out.finish(ctx, acc, grand.b, scratch);
     }
 #else
-    Aff<T> mine = el[ctx.tid * SCAN_E];
-    for (int e = 1; e < SCAN_E; ++e) mine = aff_compose(mine, el[ctx.tid * SCAN_E + e]);
+    const Aff<T>* mine_el = el + ctx.tid * (E + 1);
+    Aff<T> mine = mine_el[0];
+#pragma unroll
+    for (int e = 1; e < E; ++e) mine = aff_compose(mine, mine_el[e]);
     Aff<T> blk;
     Aff<T> pre = block_scan_aff(ctx, mine, blk, scratch);
     if (p.nchunks <= 1) grand = blk;
     pre = aff_compose(carry, pre);
     T acc[4] = {0, 0, 0, 0};
     T x = pre.b, y = pre.c;          // state = prefix applied to the zero state
-    // all global loads of the SCAN_E outputs of this thread are issued before the sequential walk
-    typename Out::Pre pl[SCAN_E];
+    // all global loads of the E outputs of this thread are issued before the sequential walk
+    typename Out::Pre pl[E];
     if (p.n > 0) {
 #pragma unroll
-      for (int e = 0; e < SCAN_E; ++e) {
-        long pos = p0 + ctx.tid * SCAN_E + e;
+      for (int e = 0; e < E; ++e) {
+        long pos = p0 + ctx.tid * E + e;
         pl[e] = p.out.load(pos < p.n ? pos : p.n - 1);
       }
     }
 #pragma unroll
-    for (int e = 0; e < SCAN_E; ++e) {
-      long pos = p0 + ctx.tid * SCAN_E + e;
+    for (int e = 0; e < E; ++e) {
+      long pos = p0 + ctx.tid * E + e;
       if (pos < p.n) {
-        Aff<T> a = el[ctx.tid * SCAN_E + e];
+        Aff<T> a = mine_el[e];
         T x1 = x + a.a * y + a.b, y1 = y + a.c;
         p.out.put(pos, pl[e], x, y, x1, y1, grand.b, acc);
         x = x1; y = y1;
@@ -315,7 +298,7 @@ template <class T> struct FwdOut {
   }
 };
 // A_b (with A_0 = z V), wS_b, sum wS_b l_b
-template <class T> struct AmpTabParams { AmpModel<T> m; const T* P; T* amp; T* wS; T* partials; unsigned* counter; T* scal; const T* ellv; const T* cv; };
+template <class T> struct AmpTabParams { int ch; AmpModel<T> m; const T* P; T* amp; T* wS; T* partials; unsigned* counter; T* scal; const T* ellv; const T* cv; };
 template <class T> struct AmpTabBody {
   typedef AmpTabParams<T> Params;
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
@@ -323,8 +306,8 @@ template <class T> struct AmpTabBody {
     T S = p.scal[SC_S], flu = p.scal[SC_FLU], z = p.scal[SC_Z];
     T acc = 0, acc2 = 0;
     const bool norm = !m.matern || m.renorm;
-    long b0 = (long)ctx.bid * SCAN_CH;
-    NB_FOR(ctx, i, SCAN_CH) {
+    long b0 = (long)ctx.bid * p.ch;
+    NB_FOR(ctx, i, p.ch) {
       long b = b0 + i;
       if (b >= m.K) break;
       T Pb = p.P[b], A, w;
@@ -381,20 +364,23 @@ template <class T> struct JvpOut {
   NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, T, void* scratch) const {
     T s = ctx.block_sum(acc[0], scratch);
     if (ctx.tid == 0) partials[ctx.bid] = s;
+    T tflu = 0, tzm = 0, z = 0;      // fetched ahead of the grid-wide handshake (latency off the serial tail)
+    if (ctx.tid == 0) { if (m.has_flu) tflu = t[m.off_flu]; tzm = t[m.off_zm]; z = scal[SC_Z]; }
     if (ctx.last_block(counter)) {
       T sw = block_total(ctx, partials, ctx.nblk, 1, scratch);
       if (ctx.tid == 0) {
-        T dflu_rel = m.has_flu ? m.flu_b * t[m.off_flu] : T(0);
+        T dflu_rel = m.has_flu ? m.flu_b * tflu : T(0);
         scal[SC_CJ] = dflu_rel - T(0.5) * sw;
-        scal[SC_DA0] = m.V * scal[SC_Z] * m.zm_b * t[m.off_zm];
+        scal[SC_DA0] = m.V * z * m.zm_b * tzm;
       }
     }
   }
 };
 
 // ---- cotangent chain -------------------------------------------------------------------------
-// segment sum over the folded W array through a CSR of W positions per bin (fixed order), one
-// warp-sized group of threads per bin:  g_b = A_b * sum_{p in bin b} W[p]  (g_0 = 0)
+// segment sum over the folded W array through a CSR of W positions per bin (fixed order), a power-of-two
+// group of lanes per bin:  g_b = A_b * sum_{p in bin b} W[p]  (g_0 = 0).  (Storing W in bin order instead,
+// i.e. scattering in the last adjoint pass, was measured: the segment sum gained 12 us, that pass lost 32.)
 template <class T> struct SegSumParams {
   AmpModel<T> m; const T* W; const int* order; const int* offs; const T* amp;
   T* g; T* abar /* optional raw bin sums */; T* partials /* [nblk][2] */; unsigned* counter; T* scal;
@@ -416,6 +402,8 @@ template <class T> struct SegSumBody {
       if (p.abar_in) {
         if (b < m.K && lane == 0) s = p.abar_in[b];
       } else if (b < m.K) {
+        // measured alternatives (profiles/r2_notes.md): branch-free rounds of 4 or 8 entries were 8-16 % slower
+        // than this loop (bins hold 3.5 entries on average in 2-D), storing W in bin order cost the producer 32 us
         int beg = p.offs[b], end = p.offs[b + 1];
         int q = beg + lane;
         for (; q + 3 * lpb < end; q += 4 * lpb) {     // four independent index -> value chains in flight
@@ -448,15 +436,18 @@ template <class T> struct SegSumBody {
     void* scratch = reinterpret_cast<void*>(sm + 256);
     { T v3[3] = {a0, a1, a2}; ctx.template block_sum_n<3>(v3, scratch); a0 = v3[0]; a1 = v3[1]; a2 = v3[2]; }
     if (ctx.tid == 0) { p.partials[3 * ctx.bid] = a0; p.partials[3 * ctx.bid + 1] = a1; p.partials[3 * ctx.bid + 2] = a2; }
+    T cwl = 0, cwc = 0;
+    if (ctx.tid == 0) { cwl = p.scal[SC_CWL]; cwc = p.scal[SC_CWC]; }
     if (ctx.last_block(p.counter)) {
-      T sg = block_total(ctx, p.partials, ctx.nblk, 3, scratch);
-      T sgl = block_total(ctx, p.partials + 1, ctx.nblk, 3, scratch);
-      T sgc = block_total(ctx, p.partials + 2, ctx.nblk, 3, scratch);
+      T v[3] = {0, 0, 0};
+      NB_FOR(ctx, i, ctx.nblk) { v[0] += p.partials[3 * (size_t)i]; v[1] += p.partials[3 * (size_t)i + 1]; v[2] += p.partials[3 * (size_t)i + 2]; }
+      ctx.template block_sum_n<3>(v, scratch);
+      T sg = v[0], sgl = v[1], sgc = v[2];
       if (ctx.tid == 0) {
         T kappa = m.kind_power ? T(0.5) : T(1);
         p.scal[SC_SG] = sg; p.scal[SC_SGL] = sgl; p.scal[SC_SGC] = sgc;
-        p.scal[SC_UBL] = kappa * sgl - T(0.5) * sg * p.scal[SC_CWL];   // sum_b ubar_b l_b
-        p.scal[SC_UBC] = kappa * sgc - T(0.5) * sg * p.scal[SC_CWC];   // sum_b ubar_b c_b (Matern cutoff)
+        p.scal[SC_UBL] = kappa * sgl - T(0.5) * sg * cwl;   // sum_b ubar_b l_b
+        p.scal[SC_UBC] = kappa * sgc - T(0.5) * sg * cwc;   // sum_b ubar_b c_b (Matern cutoff)
       }
     }
   }
@@ -510,29 +501,46 @@ template <class T> struct VjpOut {
     }
     out[m.off_spec + 2 * j] = o0; out[m.off_spec + 2 * j + 1] = o1;
   }
-  NB_HD NB_INLINE void leaf(long off, T v, T& dot) const {
-    if (add) { T a = add[off]; v += a; dot += a * v; }
+  NB_HD NB_INLINE void leaf(long off, T v, T a, T& dot) const {
+    if (add) { v += a; dot += a * v; }
     out[off] = v;
   }
   NB_HD NB_INLINE void finish(Ctx& ctx, T* acc, T, void* scratch) const {
     ctx.template block_sum_n<3>(acc, scratch);
     if (ctx.tid == 0) { partials[3 * ctx.bid] = acc[0]; partials[3 * ctx.bid + 1] = acc[1]; partials[3 * ctx.bid + 2] = acc[2]; }
+    // inputs of the scalar leaves: fetched before the grid-wide handshake so that their latency is
+    // not paid serially (seven dependent global round trips) by the last block's thread 0
+    T la[7] = {0, 0, 0, 0, 0, 0, 0}, sg = 0, ubl = 0, ubc = 0, ctf = 0, sig = 0, asp = 0, ab0 = 0, z = 0;
+    if (ctx.tid == 0) {
+      if (add) {
+        if (m.has_flu) la[0] = add[m.off_flu];
+        la[1] = add[m.off_slp];
+        if (m.matern) la[2] = add[m.off_ctf];
+        if (m.has_dev) { la[3] = add[m.off_flx]; if (m.has_asp) la[4] = add[m.off_asp]; }
+        la[5] = add[m.off_zm];
+        if (m.has_scaling) la[6] = add[m.off_scl];
+      }
+      sg = scal_in[SC_SG]; ubl = scal_in[SC_UBL]; ubc = scal_in[SC_UBC]; ctf = scal_in[SC_CTF];
+      sig = scal_in[SC_SIG]; asp = scal_in[SC_ASP]; ab0 = scal_in[SC_ABAR0]; z = scal_in[SC_Z];
+    }
     if (ctx.last_block(counter)) {
-      T sigbar = block_total(ctx, partials, ctx.nblk, 3, scratch);
-      T aspbar = block_total(ctx, partials + 1, ctx.nblk, 3, scratch);
-      T dot = block_total(ctx, partials + 2, ctx.nblk, 3, scratch);
-      dot += block_total(ctx, p5_partials, n_p5, 1, scratch);
-      T sp = m.has_scaling ? block_total(ctx, p3_partials, n_p3, 2, scratch) : T(0);
+      // all five totals in ONE reduction (each used to cost its own pair of barriers)
+      T v[5] = {0, 0, 0, 0, 0};
+      NB_FOR(ctx, i, ctx.nblk) { v[0] += partials[3 * (size_t)i]; v[1] += partials[3 * (size_t)i + 1]; v[2] += partials[3 * (size_t)i + 2]; }
+      NB_FOR(ctx, i, n_p5) v[3] += p5_partials[i];
+      if (m.has_scaling) { NB_FOR(ctx, i, n_p3) v[4] += p3_partials[2 * (size_t)i]; }
+      ctx.template block_sum_n<5>(v, scratch);
       if (ctx.tid == 0) {
-        if (m.has_flu) leaf(m.off_flu, scal_in[SC_SG] * m.flu_b, dot);
-        leaf(m.off_slp, scal_in[SC_UBL] * m.slp_b, dot);
-        if (m.matern) leaf(m.off_ctf, scal_in[SC_UBC] * scal_in[SC_CTF] * m.ctf_b, dot);
+        T sigbar = v[0], aspbar = v[1], dot = v[2] + v[3], sp = v[4];
+        if (m.has_flu) leaf(m.off_flu, sg * m.flu_b, la[0], dot);
+        leaf(m.off_slp, ubl * m.slp_b, la[1], dot);
+        if (m.matern) leaf(m.off_ctf, ubc * ctf * m.ctf_b, la[2], dot);
         if (m.has_dev) {
-          leaf(m.off_flx, sigbar * scal_in[SC_SIG] * m.flx_b, dot);
-          if (m.has_asp) leaf(m.off_asp, aspbar * scal_in[SC_ASP] * m.asp_b, dot);
+          leaf(m.off_flx, sigbar * sig * m.flx_b, la[3], dot);
+          if (m.has_asp) leaf(m.off_asp, aspbar * asp * m.asp_b, la[4], dot);
         }
-        leaf(m.off_zm, scal_in[SC_ABAR0] * m.V * scal_in[SC_Z] * m.zm_b, dot);
-        if (m.has_scaling) leaf(m.off_scl, sp * scl_factor, dot);
+        leaf(m.off_zm, ab0 * m.V * z * m.zm_b, la[5], dot);
+        if (m.has_scaling) leaf(m.off_scl, sp * scl_factor, la[6], dot);
         scal[SC_DOT] = dot;
       }
     }

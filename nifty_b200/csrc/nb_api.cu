@@ -48,8 +48,10 @@ template <class T> void Model<T>::init(Plan<T>* plan_, const nb200_model_desc& d
   ell.upload(e); multT.upload(mu); dt.upload(dtv);
   am.ell = ell.p; am.mult = multT.p; am.dt = dt.p;
   { std::vector<T> kk(g.K); for (int b = 0; b < g.K; ++b) kk[b] = (T)g.um[b]; modes.upload(kk); am.modes = modes.p; }
-  nchunksK = (g.K + SCAN_CH - 1) / SCAN_CH;
-  nchunksJ = std::max(1, (g.K - 2 + SCAN_CH - 1) / SCAN_CH);
+  scan_e = scan_pick_e(g.K);
+  const int scan_ch = SCAN_NT * scan_e;
+  nchunksK = (g.K + scan_ch - 1) / scan_ch;
+  nchunksJ = std::max(1, (g.K - 2 + scan_ch - 1) / scan_ch);
   agg.alloc(nchunksK + 1); preaff.alloc(nchunksK + 2);
   ad.alloc(g.K); gbuf.alloc(g.K);
   size_t np = std::max<size_t>(3 * (size_t)nchunksK + 3, 3 * (size_t)P->seg_grid() + 3);
@@ -297,7 +299,7 @@ int nb200_cf_apply_adjoint(nb200_plan* plan, void* stream, const void* amp, cons
     if (amp_bar) {
       SegSumParams<TT> ps; std::memset(&ps, 0, sizeof(ps));
       ps.m.K = P.g.K; ps.W = P.W.p; ps.order = P.w_order.p; ps.offs = P.w_offs.p; ps.abar = (TT*)amp_bar; ps.lg_lpb = P.seg_lg_lpb; ps.ellv = nullptr; ps.cv = nullptr;
-      launch<SegSumBody<TT>>(P.seg_grid(), 256, (256 + 64) * sizeof(TT), st, ps);
+      launch<SegSumBody<TT>>(P.seg_grid(), 256, (256 + 96) * sizeof(TT), st, ps);
     }
   })
   return 0;

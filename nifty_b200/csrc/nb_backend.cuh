@@ -31,6 +31,8 @@ inline int sm_count() { return 148; }
 template <class Body>
 inline void launch(int grid, int block, size_t smem, stream_t, const typename Body::Params& p) {
   (void)block;
+  static const bool trace = std::getenv("NB200_EMU_TRACE") != nullptr;    // which bodies ran (test aid)
+  if (trace) std::fprintf(stderr, "[emu] %s grid=%d\n", typeid(Body).name(), grid);
   std::vector<char> sm(smem + 4096);
   for (int b = 0; b < grid; ++b) {
     Ctx ctx{0, 1, b, grid};

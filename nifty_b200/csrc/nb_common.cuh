@@ -160,6 +160,25 @@ template <> __device__ NB_INLINE cplx<float> ldg(const cplx<float>* p) {
 }
 #endif
 
+// Streaming load: data that is read once per pass bypasses L1 (ld.global.cg).  The passes keep 3 x 64 KB of
+// shared memory per SM, which leaves ~25 KB of L1 for the twiddle / slot tables every butterfly reads; with
+// the line data allocating in L1 as well those tables kept missing (ncu: 19 % L1 hit rate in P3).
+#if defined(NB_EMU)
+template <class T> inline T ld_stream(const T* p) { return *p; }
+#elif defined(NB_NO_STREAM_LD)
+template <class T> __device__ NB_INLINE T ld_stream(const T* p) { return *p; }
+#else
+template <class T> __device__ NB_INLINE T ld_stream(const T* p) { return __ldcg(p); }
+template <> __device__ NB_INLINE cplx<double> ld_stream(const cplx<double>* p) {
+  double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return cmake<double>(v.x, v.y);
+}
+template <> __device__ NB_INLINE cplx<float> ld_stream(const cplx<float>* p) {
+  float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+  return cmake<float>(v.x, v.y);
+}
+#endif
+
 // cooperative L2 prefetch of [p, p+bytes): turns the DRAM latency of a later phase into an L2 hit
 #ifdef NB_EMU
 inline void prefetch_l2(Ctx&, const void*, size_t) {}

@@ -16,23 +16,31 @@
 //  * the first DIF stage reads its inputs straight from global memory through a loader functor
 //    (8 independent coalesced loads per thread) -- one shared-memory round trip and one barrier
 //    less per line, and the prologue of a pass (amplitude gather etc.) is fused into it.
-//  * one twiddle load per butterfly (w_m^j, coalesced, L1/L2 resident table computed on the host
-//    in extended precision); w^2..w^7 are formed by multiplication (<= 3 roundings deep).
+//  * one twiddle load per butterfly (w_m^j, coalesced, from a COMPACT per-stage table computed on the
+//    host in extended precision: stage s owns the contiguous run w_m^0 .. w_m^{m/R-1}, 9 KB in all for
+//    a 4096-point line, so the tables survive in the ~25 KB of L1 that three 64 KB CTAs leave);
+//    w^2..w^7 are formed by multiplication (<= 3 roundings deep).
 //  * every butterfly reads and writes the same r slots, so no thread carries registers across a
 //    barrier (which is also what lets tests/emu run the same code sequentially on the host).
 #pragma once
 #include "nb_common.cuh"
+#include <vector>
 
 namespace nb {
 
 // log2 of the radix used for a sub-transform of length 2^lm: 8 except for the 2/4/16 leftovers.
-NB_HH NB_INLINE int fft_radix_lg(int lm) { return lm == 1 ? 1 : ((lm == 2 || lm == 4) ? 2 : 3); }
+// order = 1 puts the radix-4 leftover of lengths 2^(3m+2) FIRST (4*8*8*.. instead of 8*8*..*4): the first
+// stage is the one fused with the global loads, and a radix-4 batch needs half the registers.
+NB_HH NB_INLINE int fft_radix_lg(int lm, int order = 0) {
+  if (order == 1 && lm > 2 && lm % 3 == 2) return 2;
+  return lm == 1 ? 1 : ((lm == 2 || lm == 4) ? 2 : 3);
+}
 
 // logical slot of output element k after fft_dif of length 2^lg (== slot where fft_dit expects input k)
-NB_HH NB_INLINE int fft_pos(int k, int lg) {
+NB_HH NB_INLINE int fft_pos(int k, int lg, int order = 0) {
   int pos = 0, lm = lg;
   while (lm > 0) {
-    int lr = fft_radix_lg(lm);
+    int lr = fft_radix_lg(lm, order);
     int p = k & ((1 << lr) - 1);
     k >>= lr;
     lm -= lr;
@@ -104,27 +112,41 @@ template <int LR, class T> NB_HD NB_INLINE void twiddle_apply(cplx<T>* a, cplx<T
 // Host-built description of one line FFT (passed by value inside kernel parameters, i.e. read
 // through the constant bank with uniform addresses): stage lengths / radices, the swizzled element
 // offsets swz(q << lmr) of every stage, and a device table pos[k] = swz(fft_pos(k)).
+typedef unsigned short fft_slot_t;     // physical slot within a line (lines are <= 2^14 elements: 227 KB of shared memory)
 struct FftDev {
   int lg, ns;
   int lm[6], lr[6];
   int off[6][8];
-  const int* pos;
+  int tw_off[6];              // first entry of stage s in the compact twiddle table
+  const fft_slot_t* pos;
+  const void* ctw;            // cplx<T>[tw_off[ns-1] + ...]: stage s holds w_{2^lm}^j, j < 2^(lm-lr)
 };
-inline FftDev make_fft_dev(int lg, const int* pos_table) {
+inline FftDev make_fft_dev(int lg, const fft_slot_t* pos_table, const void* ctw, int order = 0) {
   FftDev f;
-  f.lg = lg; f.ns = 0; f.pos = pos_table;
-  for (int s = 0; s < 6; ++s) { f.lm[s] = 0; f.lr[s] = 0; for (int q = 0; q < 8; ++q) f.off[s][q] = 0; }
-  int lm = lg;
+  f.lg = lg; f.ns = 0; f.pos = pos_table; f.ctw = ctw;
+  for (int s = 0; s < 6; ++s) { f.lm[s] = 0; f.lr[s] = 0; f.tw_off[s] = 0; for (int q = 0; q < 8; ++q) f.off[s][q] = 0; }
+  int lm = lg, toff = 0;
   while (lm > 0) {
-    int lr = fft_radix_lg(lm);
-    f.lm[f.ns] = lm; f.lr[f.ns] = lr;
+    int lr = fft_radix_lg(lm, order);
+    f.lm[f.ns] = lm; f.lr[f.ns] = lr; f.tw_off[f.ns] = toff;
+    toff += 1 << (lm - lr);
     for (int q = 0; q < (1 << lr); ++q) f.off[f.ns][q] = swz(q << (lm - lr));
     ++f.ns;
     lm -= lr;
   }
   return f;
 }
-inline void fill_pos_table(int lg, int* out) { for (int k = 0; k < (1 << lg); ++k) out[k] = swz(fft_pos(k, lg)); }
+inline void fill_pos_table(int lg, fft_slot_t* out, int order = 0) { for (int k = 0; k < (1 << lg); ++k) out[k] = (fft_slot_t)swz(fft_pos(k, lg, order)); }
+// compact twiddle table of a line FFT of length 2^lg from the full table full[k] = w_{2^lg}^k
+template <class C> inline void fill_compact_twiddles(int lg, const C* full, std::vector<C>& out, int order = 0) {
+  out.clear();
+  int lm = lg;
+  while (lm > 0) {
+    int lr = fft_radix_lg(lm, order);
+    for (int j = 0; j < (1 << (lm - lr)); ++j) out.push_back(full[(size_t)j << (lg - lm)]);
+    lm -= lr;
+  }
+}
 
 // One radix-2^LR stage over all lines, data in shared memory (stage index st of `f`).
 // DIF: y_p = (sum_q x_q w_R^{pq}) w_m^{jp};  DIT: y_p = sum_q (x_q w_m^{jq}) w_R^{pq}
@@ -136,12 +158,13 @@ NB_HD NB_INLINE void fft_stage(Ctx& ctx, cplx<T>* s, const FftDev& f, int st, in
   const int lmr = lm - LR;              // log2(m / R)
   const int lbf = f.lg - LR;            // log2(butterflies per line)
   const int total = nlines << lbf;
-  const int tw_shift = lg_tw - lm;
+  const cplx<T>* ctw = reinterpret_cast<const cplx<T>*>(f.ctw) + f.tw_off[st];
+  (void)tw; (void)lg_tw;
   NB_FOR(ctx, t, total) {
     int line = t >> lbf, u = t & ((1 << lbf) - 1);
     int blk = u >> lmr, j = u & ((1 << lmr) - 1);
     cplx<T> w = cmake<T>(T(1), T(0));
-    if (j != 0) w = ldg(tw + ((size_t)j << tw_shift));
+    if (j != 0) w = ldg(ctw + j);
     cplx<T>* base = s + line * pitch;
     const int b0 = swz((blk << lm) + j);
     cplx<T> a[R];
@@ -164,13 +187,14 @@ NB_HD NB_INLINE void fft_stage_first(Ctx& ctx, cplx<T>* s, const FftDev& f, int 
   constexpr int R = 1 << LR;
   const int lmr = f.lg - LR;
   const int total = nlines << lmr;
-  const int tw_shift = lg_tw - f.lg;
+  const cplx<T>* ctw = reinterpret_cast<const cplx<T>*>(f.ctw);      // stage 0 starts the compact table
+  (void)tw; (void)lg_tw;
   NB_FOR(ctx, t, total) {
     int line = t >> lmr, j = t & ((1 << lmr) - 1);
     cplx<T> a[R];
     ld.template batch<R>(line, j, lmr, a);
     cplx<T> w = cmake<T>(T(1), T(0));
-    if (j != 0) w = ldg(tw + ((size_t)j << tw_shift));
+    if (j != 0) w = ldg(ctw + j);
     dftR<LR>(a);
     if (j != 0) twiddle_apply<LR>(a, w);
     cplx<T>* base = s + line * pitch;

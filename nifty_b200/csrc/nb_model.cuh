@@ -65,7 +65,8 @@ template <class T> struct Model : ModelBase {
   void init(Plan<T>* plan_, const nb200_model_desc& d);
   ~Model();
 
-  size_t scan_smem() const { return scan_smem_bytes<T>(); }
+  int scan_e = 8;      // elements per thread of the scan kernels (scan_pick_e)
+  size_t scan_smem() const { return scan_smem_bytes<T>(scan_e); }
 };
 
 template <class T> struct Lin : LinBase {
@@ -90,13 +91,13 @@ template <class T> struct Lin : LinBase {
     const int nch = m.am.has_dev ? m.nchunksK : 1;   // without deviations every element is the identity
     if (m.am.has_dev && m.nchunksK > 1) {
       ScanAggParams<T, FwdElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p; pa.pre = m.preaff.p; pa.counter = m.counters.p + 5;
-      launch<ScanAggBody<T, FwdElem<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
+      if (m.scan_e == 8) launch<ScanAggBody<T, FwdElem<T>, 8>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa); else launch<ScanAggBody<T, FwdElem<T>, 4>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
     }
     FwdOut<T> fo; fo.m = m.am; fo.pos = pos.p; fo.P = Pb.p; fo.partials = m.partials.p;
     fo.counter = m.counters.p; fo.scal = scal.p; fo.ellv = ellv_buf.p; fo.cv = cv_buf.p;
     ScanApplyParams<T, FwdElem<T>, FwdOut<T>> pc; pc.n = K; pc.elem = el; pc.out = fo; pc.pre = m.preaff.p; pc.nchunks = nch;
-    launch<ScanApplyBody<T, FwdElem<T>, FwdOut<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
-    AmpTabParams<T> pt2; pt2.m = m.am; pt2.P = Pb.p; pt2.amp = amp.p; pt2.wS = wS.p; pt2.partials = m.partials.p;
+    if (m.scan_e == 8) launch<ScanApplyBody<T, FwdElem<T>, FwdOut<T>, 8>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc); else launch<ScanApplyBody<T, FwdElem<T>, FwdOut<T>, 4>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
+    AmpTabParams<T> pt2; pt2.ch = SCAN_NT * m.scan_e; pt2.m = m.am; pt2.P = Pb.p; pt2.amp = amp.p; pt2.wS = wS.p; pt2.partials = m.partials.p;
     pt2.counter = m.counters.p + 1; pt2.scal = scal.p; pt2.ellv = ellv; pt2.cv = cv;
     launch<AmpTabBody<T>>(m.nchunksK, SCAN_NT, 512, st, pt2);
   }
@@ -108,12 +109,12 @@ template <class T> struct Lin : LinBase {
     const int nch = m.am.has_dev ? m.nchunksK : 1;
     if (m.am.has_dev && m.nchunksK > 1) {
       ScanAggParams<T, JvpElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p; pa.pre = m.preaff.p; pa.counter = m.counters.p + 5;
-      launch<ScanAggBody<T, JvpElem<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
+      if (m.scan_e == 8) launch<ScanAggBody<T, JvpElem<T>, 8>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa); else launch<ScanAggBody<T, JvpElem<T>, 4>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pa);
     }
     JvpOut<T> jo; jo.m = m.am; jo.pos = pos.p; jo.t = t; jo.wS = wS.p; jo.amp = amp.p; jo.ellv = ellv; jo.cv = cv; jo.ad = m.ad.p;
     jo.partials = m.partials.p; jo.counter = m.counters.p + 2; jo.scal = scal.p;
     ScanApplyParams<T, JvpElem<T>, JvpOut<T>> pc; pc.n = K; pc.elem = el; pc.out = jo; pc.pre = m.preaff.p; pc.nchunks = nch;
-    launch<ScanApplyBody<T, JvpElem<T>, JvpOut<T>>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
+    if (m.scan_e == 8) launch<ScanApplyBody<T, JvpElem<T>, JvpOut<T>, 8>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc); else launch<ScanApplyBody<T, JvpElem<T>, JvpOut<T>, 4>>(m.nchunksK, SCAN_NT, m.scan_smem(), st, pc);
   }
   ProMetric<T> pro_metric(const T* t) const {
     const Model<T>& m = *M;
@@ -130,7 +131,7 @@ template <class T> struct Lin : LinBase {
     SegSumParams<T> ps; ps.m = m.am; ps.W = P.W.p; ps.order = P.w_order.p; ps.offs = P.w_offs.p; ps.amp = amp.p;
     ps.g = abar_out ? nullptr : m.gbuf.p; ps.abar = abar_out; ps.abar_in = abar_in; ps.partials = m.partials.p;
     ps.counter = m.counters.p + 3; ps.scal = scal.p; ps.lg_lpb = P.seg_lg_lpb; ps.ellv = ellv; ps.cv = cv;
-    launch<SegSumBody<T>>(P.seg_grid(), 256, (256 + 64) * sizeof(T), st, ps);
+    launch<SegSumBody<T>>(P.seg_grid(), 256, (256 + 96) * sizeof(T), st, ps);
   }
   void vjp_chain(stream_t st, T* out, const T* add, const T* p3_src, int n_p3, const T* p5_src, int n_p5, T scl_factor) {
     Model<T>& m = *M; const int K = m.am.K;
@@ -142,13 +143,13 @@ template <class T> struct Lin : LinBase {
       VjpElem<T> el; el.m = m.am; el.g = m.gbuf.p; el.wS = wS.p; el.scal = scal.p;
       if (m.nchunksJ > 1) {
         ScanAggParams<T, VjpElem<T>> pa; pa.n = nj; pa.elem = el; pa.agg = m.agg.p; pa.pre = m.preaff.p; pa.counter = m.counters.p + 5;
-        launch<ScanAggBody<T, VjpElem<T>>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pa);
+        if (m.scan_e == 8) launch<ScanAggBody<T, VjpElem<T>, 8>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pa); else launch<ScanAggBody<T, VjpElem<T>, 4>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pa);
       }
       ScanApplyParams<T, VjpElem<T>, VjpOut<T>> pc; pc.n = nj; pc.elem = el; pc.out = vo; pc.pre = m.preaff.p; pc.nchunks = m.nchunksJ;
-      launch<ScanApplyBody<T, VjpElem<T>, VjpOut<T>>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pc);
+      if (m.scan_e == 8) launch<ScanApplyBody<T, VjpElem<T>, VjpOut<T>, 8>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pc); else launch<ScanApplyBody<T, VjpElem<T>, VjpOut<T>, 4>>(m.nchunksJ, SCAN_NT, m.scan_smem(), st, pc);
     } else {
       ScanApplyParams<T, NoElem<T>, VjpOut<T>> pc; pc.n = 0; pc.out = vo; pc.pre = nullptr; pc.nchunks = 1;
-      launch<ScanApplyBody<T, NoElem<T>, VjpOut<T>>>(1, SCAN_NT, m.scan_smem(), st, pc);
+      if (m.scan_e == 8) launch<ScanApplyBody<T, NoElem<T>, VjpOut<T>, 8>>(1, SCAN_NT, m.scan_smem(), st, pc); else launch<ScanApplyBody<T, NoElem<T>, VjpOut<T>, 4>>(1, SCAN_NT, m.scan_smem(), st, pc);
     }
   }
   void amp_cotangent(stream_t st, T* out, const T* add, int p3_col, T scl_factor, bool use_p5_dot) {

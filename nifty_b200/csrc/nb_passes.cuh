@@ -29,10 +29,10 @@ namespace nb {
 // pair load: one 2*sizeof(T)-byte access when the caller guarantees alignment (compile time)
 template <bool ALIGNED, class T> NB_HD NB_INLINE void load_pair(const T* p, T& a, T& b) {
   if (ALIGNED) {
-    cplx<T> v = *reinterpret_cast<const cplx<T>*>(p);
+    cplx<T> v = ld_stream(reinterpret_cast<const cplx<T>*>(p));
     a = v.x; b = v.y;
   } else {
-    a = p[0]; b = p[1];
+    a = ld_stream(p); b = ld_stream(p + 1);
   }
 }
 
@@ -57,6 +57,7 @@ struct FoldGeom {
 template <class T> NB_HH NB_INLINE bool ptr_aligned2(const T* p) { return (reinterpret_cast<uintptr_t>(p) & (2 * sizeof(T) - 1)) == 0; }
 
 template <class T> struct ProPlain {
+  static constexpr bool kUsesBins = false;
   const T* x;
   bool aligned() const { return ptr_aligned2(x); }
   template <int NQ, bool AL> NB_HD NB_INLINE void batch(int, int, long off, int j, int lmr, cplx<T>* a) const {
@@ -64,10 +65,20 @@ template <class T> struct ProPlain {
     for (int q = 0; q < NQ; ++q) { T u, v; load_pair<AL>(x + off + 2 * (j + (q << lmr)), u, v); a[q] = cmake<T>(u, v); }
   }
   NB_HD NB_INLINE void prefetch(Ctx& ctx, int, int, long off, long count) const { prefetch_l2(ctx, x + off, count * sizeof(T)); }
+  // mirror-quad interface of P1MBody (see there)
+  struct Pre { T x0, x1, x2, x3; };
+  NB_HD NB_INLINE void preload(long offA, long offB, const int*, int e, int ne, Pre& q) const {
+    q.x0 = ld_stream(x + offA + e); q.x1 = ld_stream(x + offA + ne); q.x2 = ld_stream(x + offB + e); q.x3 = ld_stream(x + offB + ne);
+  }
+  NB_HD NB_INLINE void gather(Pre&) const {}
+  NB_HD NB_INLINE void finish(const Pre& q, T* v) const { v[0] = q.x0; v[1] = q.x1; v[2] = q.x2; v[3] = q.x3; }
+  NB_HD NB_INLINE T single(long off, const int*, int e) const { return x[off + e]; }
+  NB_HD NB_INLINE const int* bins(int, int) const { return nullptr; }
 };
 
 // a[b(k)] * xi_k   (forward model, correlated_field.py:911 with azm folded into the table)
 template <class T> struct ProAmp {
+  static constexpr bool kUsesBins = true;
   const T* xi; const int* idxf; const T* amp; FoldGeom fg;
   bool aligned() const { return ptr_aligned2(xi); }
   template <int NQ, bool AL> NB_HD NB_INLINE void batch(int o, int rr, long off, int j, int lmr, cplx<T>* a) const {
@@ -86,11 +97,21 @@ template <class T> struct ProAmp {
     prefetch_l2(ctx, xi + off, count * sizeof(T));
     prefetch_l2(ctx, idxf + fg.base(o, rr), (size_t)fg.h1 * sizeof(int));
   }
+  struct Pre { int b; T A, x0, x1, x2, x3; };
+  NB_HD NB_INLINE void preload(long offA, long offB, const int* ip, int e, int ne, Pre& q) const {
+    q.b = ldg(ip + e);
+    q.x0 = ld_stream(xi + offA + e); q.x1 = ld_stream(xi + offA + ne); q.x2 = ld_stream(xi + offB + e); q.x3 = ld_stream(xi + offB + ne);
+  }
+  NB_HD NB_INLINE void gather(Pre& q) const { q.A = ldg(amp + q.b); }
+  NB_HD NB_INLINE void finish(const Pre& q, T* v) const { v[0] = q.A * q.x0; v[1] = q.A * q.x1; v[2] = q.A * q.x2; v[3] = q.A * q.x3; }
+  NB_HD NB_INLINE T single(long off, const int* ip, int e) const { return ldg(amp + ldg(ip + fold_idx(e, fg.n))) * xi[off + e]; }
+  NB_HD NB_INLINE const int* bins(int o, int rr) const { return idxf + fg.base(o, rr); }
 };
 
 // JVP input: A_b t_k + dA_b xi_k with dA_b = A_b (cj + kappa du_b) (b>=1), dA_0 = da0.
 // `ad` interleaves (A_b, du_b) so that one 2*sizeof(T) gather serves both.
 template <class T> struct ProMetric {
+  static constexpr bool kUsesBins = true;
   const T* xi; const T* t; const int* idxf; const cplx<T>* ad; const T* scal;  // scal[0]=cj, scal[1]=da0
   T kappa; FoldGeom fg;
   bool aligned() const { return ptr_aligned2(xi) && ptr_aligned2(t); }
@@ -121,6 +142,24 @@ template <class T> struct ProMetric {
     prefetch_l2(ctx, t + off, count * sizeof(T));
     prefetch_l2(ctx, idxf + fg.base(o, rr), (size_t)fg.h1 * sizeof(int));
   }
+  struct Pre { int b; cplx<T> g; T x0, x1, x2, x3, t0, t1, t2, t3; };
+  NB_HD NB_INLINE void preload(long offA, long offB, const int* ip, int e, int ne, Pre& q) const {
+    q.b = ldg(ip + e);
+    q.x0 = ld_stream(xi + offA + e); q.x1 = ld_stream(xi + offA + ne); q.x2 = ld_stream(xi + offB + e); q.x3 = ld_stream(xi + offB + ne);
+    q.t0 = ld_stream(t + offA + e); q.t1 = ld_stream(t + offA + ne); q.t2 = ld_stream(t + offB + e); q.t3 = ld_stream(t + offB + ne);
+  }
+  NB_HD NB_INLINE void gather(Pre& q) const { q.g = ldg(ad + q.b); }
+  NB_HD NB_INLINE void finish(const Pre& q, T* v) const {
+    const T cj = ldg(scal), da0 = ldg(scal + 1);
+    const T dA = (q.b == 0) ? da0 : q.g.x * (cj + kappa * q.g.y);
+    v[0] = q.g.x * q.t0 + dA * q.x0; v[1] = q.g.x * q.t1 + dA * q.x1;
+    v[2] = q.g.x * q.t2 + dA * q.x2; v[3] = q.g.x * q.t3 + dA * q.x3;
+  }
+  NB_HD NB_INLINE T single(long off, const int* ip, int e) const {
+    int b = ldg(ip + fold_idx(e, fg.n));
+    return one(b, ldg(ad + b), xi[off + e], t[off + e], ldg(scal), ldg(scal + 1));
+  }
+  NB_HD NB_INLINE const int* bins(int o, int rr) const { return idxf + fg.base(o, rr); }
 };
 
 template <class T, class Pro> struct P1Params {
@@ -187,6 +226,120 @@ template <class T, class Pro, bool AL> struct P1Body {
         cplx<T> e = zk + zc, d = zk - zc;
         cplx<T> wd = cmul_mi(cmul(w[u], d));   // -i w (zk - zc)
         outp[k * p.out_kstride + r] = cmake<T>(half * (e.x + wd.x), half * (e.y + wd.y));
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// P1M: P1 for prologues that look up the mode-bin table.  Rows rr and n_r - rr of one plane and the
+// elements e and n - e of a row all fall into the SAME bin, so a CTA owns R/2 mirror pairs of rows
+// (pair i >= 1: rows i and n_r - i; pair 0: the two self-mirrored rows 0 and n_r/2) and fetches ONE
+// bin index and ONE table entry per quad {e, n-e} x {row, mirror row}.  ncu (profiles/r2_notes.md):
+// with one dependent 16-byte gather per element P1 moved 917 MB from L2 to the SMs for 541 MB of
+// payload (every gather drags a 32-byte sector) and spent 55 % of its samples waiting in the load
+// phase.  The scaled inputs are written to shared memory first (the first FFT stage is therefore not
+// fused with the loads here); everything after the load phase is P1Body's.
+// ---------------------------------------------------------------------------------------------
+// MINB = CTAs per SM the register budget is cut for: 3 pays when the lines are short (256^3: 138 vs 156 us),
+// 2 when three CTAs' shared memory would squeeze L1 (4096^2: 204 vs 229 us) -- chosen by the host.
+template <class T, class Pro, int MINB> struct P1MBody {
+  typedef P1Params<T, Pro> Params;
+  static constexpr int kMinBlocks = MINB;
+  // row of line r of the CTA whose first pair is i0 (R/2 pairs: lines [0,R/2) are the rows i, lines [R/2,R) their mirrors)
+  static NB_HD NB_INLINE int row_of(int r, int i0, int hR, int n_r) {
+    int i = i0 + (r < hR ? r : r - hR);
+    if (r < hR) return i;
+    return i == 0 ? (n_r >> 1) : n_r - i;
+  }
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    cplx<T>* s = reinterpret_cast<cplx<T>*>(smem);
+    T* sr = reinterpret_cast<T*>(smem);
+    const int R = 1 << p.lg_R, hR = R >> 1, lg_hR = p.lg_R - 1;
+    const int n = 1 << p.lg_n, lg_h = p.lg_n - 1, h = 1 << lg_h;
+    const int gpo = p.n_r >> p.lg_R;
+    const int o = ctx.bid / gpo, i0 = (ctx.bid % gpo) << lg_hR;
+    const long in0 = o * p.in_ostride;
+    // real element x of line L lives at sr[2 * (L * pitch + swz(x >> 1)) + (x & 1)]
+#define NB_P1M_SLOT(L, x) ((((L) * p.pitch + swz((x) >> 1)) << 1) + ((x) & 1))
+    {   // quads (e, n-e), 0 < e < h, of the pairs i >= 1
+      constexpr int U = 2;
+      const int cnt = hR << lg_h;
+      for (int q0 = ctx.tid; q0 < cnt; q0 += ctx.nthr * U) {
+        typename Pro::Pre pre[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          int q = q0 + u * ctx.nthr;
+          bool in = q < cnt;
+          q = in ? q : 0;
+          int rp = q >> lg_h, e = q & (h - 1);
+          int i = i0 + rp;
+          ok[u] = in && i != 0 && e != 0;
+          e = e != 0 ? e : 1;
+          int ra = (i != 0) ? i : 1, rb = p.n_r - ra;          // safe rows for the masked-out slots
+          p.pro.preload(in0 + ra * p.in_rstride, in0 + rb * p.in_rstride, p.pro.bins(o, ra), e, n - e, pre[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) p.pro.gather(pre[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!ok[u]) continue;
+          int q = q0 + u * ctx.nthr;
+          int rp = q >> lg_h, e = q & (h - 1);
+          T v[4];
+          p.pro.finish(pre[u], v);
+          sr[NB_P1M_SLOT(rp, e)] = v[0]; sr[NB_P1M_SLOT(rp, n - e)] = v[1];
+          sr[NB_P1M_SLOT(rp + hR, e)] = v[2]; sr[NB_P1M_SLOT(rp + hR, n - e)] = v[3];
+        }
+      }
+    }
+    {   // self-mirrored elements e = 0 and e = h of every line
+      NB_FOR(ctx, k, 2 * R) {
+        int r = k >> 1, e = (k & 1) ? h : 0;
+        int rr = row_of(r, i0, hR, p.n_r);
+        sr[NB_P1M_SLOT(r, e)] = p.pro.single(in0 + rr * p.in_rstride, p.pro.bins(o, rr), e);
+      }
+    }
+    if (i0 == 0) {   // pair 0 = rows 0 and n_r/2: different bins, no sharing (one CTA per plane)
+      NB_FOR(ctx, k, 2 * (n - 2)) {
+        int r = (k & 1) ? hR : 0, x = (k >> 1) + 1;
+        if (x >= h) ++x;                                  // x in [1, n) without h
+        int rr = row_of(r, 0, hR, p.n_r);
+        sr[NB_P1M_SLOT(r, x)] = p.pro.single(in0 + rr * p.in_rstride, p.pro.bins(o, rr), x);
+      }
+    }
+#undef NB_P1M_SLOT
+    ctx.sync();
+    for (int st = 0; st < p.fft.ns; ++st) fft_stage_any<false>(ctx, s, p.fft, st, R, p.pitch, p.tw, p.lg_tw);
+    const T half = T(0.5);
+    cplx<T>* outp = p.out + o * p.out_ostride;
+    const int tsh = p.lg_tw - p.lg_n;
+    constexpr int U = 4;
+    const int total = (h + 1) << p.lg_R;
+    for (int j0 = ctx.tid; j0 < total; j0 += ctx.nthr * U) {
+      int pk[U], pc[U];
+      cplx<T> w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        int i = j0 + u * ctx.nthr;
+        i = i < total ? i : 0;
+        int k = i >> p.lg_R;
+        pk[u] = ldg(p.fft.pos + (k & (h - 1)));
+        pc[u] = ldg(p.fft.pos + ((h - k) & (h - 1)));
+        w[u] = ldg(p.tw + ((size_t)k << tsh));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        int i = j0 + u * ctx.nthr;
+        if (i >= total) break;
+        int k = i >> p.lg_R, r = i & (R - 1);
+        const cplx<T>* line = s + r * p.pitch;
+        cplx<T> zk = line[pk[u]];
+        cplx<T> zc = cconj(line[pc[u]]);
+        cplx<T> e = zk + zc, d = zk - zc;
+        cplx<T> wd = cmul_mi(cmul(w[u], d));   // -i w (zk - zc)
+        outp[k * p.out_kstride + row_of(r, i0, hR, p.n_r)] = cmake<T>(half * (e.x + wd.x), half * (e.y + wd.y));
       }
     }
   }
@@ -284,11 +437,11 @@ NB_HD NB_INLINE void RawLoader<T>::batch(int r, int j, int lmr, cplx<T>* a) cons
   if (src_off) {
     const long l = l0 + r;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) { int x = j + (q << lmr); a[q] = chunk_base[ldg(src_off + x) + l * ldg(src_mul + x)]; }
+    for (int q = 0; q < NQ; ++q) { int x = j + (q << lmr); a[q] = ld_stream(chunk_base + ldg(src_off + x) + l * ldg(src_mul + x)); }
     return;
   }
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) a[q] = lp[q << lmr];
+  for (int q = 0; q < NQ; ++q) a[q] = ld_stream(lp + (q << lmr));
 }
 
 NB_HD NB_INLINE void fill_line_info(Ctx& ctx, LineInfo* li, const MirrorGeom& mg, int l0, int R) {
@@ -474,8 +627,8 @@ template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
             int y = n - x;
             long iA = (long)li[r].lA * n, iB = (long)(li[r].lB >= 0 ? li[r].lB : li[r].lA) * n;
             px[u] = ldg(p.fft.pos + x); py[u] = ldg(p.fft.pos + y);
-            mAx[u] = ja[iA + x]; mAy[u] = ja[iA + y]; mBx[u] = ja[iB + x]; mBy[u] = ja[iB + y];
-            if (!same) { mAx[u] *= jb[iA + x]; mAy[u] *= jb[iA + y]; mBx[u] *= jb[iB + x]; mBy[u] *= jb[iB + y]; }
+            mAx[u] = ld_stream(ja + iA + x); mAy[u] = ld_stream(ja + iA + y); mBx[u] = ld_stream(ja + iB + x); mBy[u] = ld_stream(ja + iB + y);
+            if (!same) { mAx[u] *= ld_stream(jb + iA + x); mAy[u] *= ld_stream(jb + iA + y); mBx[u] *= ld_stream(jb + iB + x); mBy[u] *= ld_stream(jb + iB + y); }
             else { mAx[u] *= mAx[u]; mAy[u] *= mAy[u]; mBx[u] *= mBx[u]; mBy[u] *= mBy[u]; }
           }
 #pragma unroll
@@ -578,8 +731,8 @@ template <class T> struct EpiAdjoint {
   NB_HD NB_INLINE void preload(long rowA, long rowB, long fbase, int x, int y, Pre& q) const {
     q.b = ldg(idxf + fbase + x);
     q.a0 = q.a1 = q.a2 = q.a3 = q.x0 = q.x1 = q.x2 = q.x3 = 0;
-    if (add) { q.a0 = add[rowA + x]; q.a1 = add[rowA + y]; q.a2 = add[rowB + x]; q.a3 = add[rowB + y]; }
-    if (xi) { q.x0 = xi[rowA + x]; q.x1 = xi[rowA + y]; q.x2 = xi[rowB + x]; q.x3 = xi[rowB + y]; }
+    if (add) { q.a0 = ld_stream(add + rowA + x); q.a1 = ld_stream(add + rowA + y); q.a2 = ld_stream(add + rowB + x); q.a3 = ld_stream(add + rowB + y); }
+    if (xi) { q.x0 = ld_stream(xi + rowA + x); q.x1 = ld_stream(xi + rowA + y); q.x2 = ld_stream(xi + rowB + x); q.x3 = ld_stream(xi + rowB + y); }
   }
   NB_HD NB_INLINE void gather(Pre& q) const { q.A = ldg(amp + q.b); }
   NB_HD NB_INLINE void finish(long rowA, long rowB, long wbase, int x, int y, T gAx, T gAy, T gBx, T gBy, const Pre& q,

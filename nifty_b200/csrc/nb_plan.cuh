@@ -193,13 +193,16 @@ template <class T> std::vector<cplx<T>> make_twiddles(int n) {
 
 // L2 prefetch of later-phase / next-wave rows is OFF by default: measured on B200 it added 30-50 % DRAM
 // read traffic (lines evicted before use) for no gain (profiles/r1_notes.md); NB200_PREFETCH=1 re-enables it.
+inline bool p1m_enabled() { const char* e = std::getenv("NB200_P1M"); return !(e && e[0] == '0'); }   // developer knob: 0 = old P1 for every prologue
 inline bool prefetch_disabled() { const char* e = std::getenv("NB200_PREFETCH"); return !(e && e[0] == '1'); }
 
 template <class T> struct Plan : PlanBase {
   int lg0 = 0, lgm = 0, lgl = 0;
   T hsign = 1;
   DevBuf<cplx<T>> tw0, twm, twl, S0, S1;
-  DevBuf<int> idxf, w_order, w_offs, pos0, posm, posl, poslh, plane_loc0, src_mul3, src_mul5;
+  DevBuf<fft_slot_t> pos0, posm, posl, poslh;
+  DevBuf<cplx<T>> ctw0, ctwm, ctwl, ctwlh;     // compact per-stage twiddle tables of the four line FFTs
+  DevBuf<int> idxf, w_order, w_offs, plane_loc0, src_mul3, src_mul5;
   DevBuf<long> src_off3, src_off5;
   cplx<T>* xS0 = nullptr; cplx<T>* xS1 = nullptr; cplx<T>* xS2 = nullptr;   // host-provided buffers (distributed plans)
   // chunked pipeline of the distributed plans: chunk c of every rank's half-range piece
@@ -310,13 +313,19 @@ template <class T> struct Plan : PlanBase {
     twm.upload(make_twiddles<T>(g.nm));
     twl.upload(make_twiddles<T>(g.nl));
     idxf.upload(idxf_loc); w_order.upload(w_order_loc); w_offs.upload(w_offs_loc);
-    auto mk = [&](int lg, DevBuf<int>& buf) {
-      std::vector<int> t(size_t(1) << lg);
-      fill_pos_table(lg, t.data());
+    auto mk = [&](int lg, DevBuf<fft_slot_t>& buf, DevBuf<cplx<T>>& ctw, int order) {
+      if (lg > 14) throw Error{"nb200: line length above 2^14 is not supported"};
+      std::vector<fft_slot_t> t(size_t(1) << lg);
+      fill_pos_table(lg, t.data(), order);
       buf.upload(t);
-      return make_fft_dev(lg, buf.p);
+      std::vector<cplx<T>> full = make_twiddles<T>(1 << lg), compact;
+      fill_compact_twiddles(lg, full.data(), compact, order);
+      ctw.upload(compact);
+      return make_fft_dev(lg, buf.p, ctw.p, order);
     };
-    f0 = mk(lg0, pos0); fm = mk(lgm, posm); fl = mk(lgl, posl); flh = mk(lgl - 1, poslh);
+    int order1 = 0;
+    if (const char* e = std::getenv("NB200_P1_R4")) order1 = (e[0] == '1');   // developer knob: radix-4 stage first in P1
+    f0 = mk(lg0, pos0, ctw0, 0); fm = mk(lgm, posm, ctwm, 0); fl = mk(lgl, posl, ctwl, 0); flh = mk(lgl - 1, poslh, ctwlh, order1);
     W.alloc((size_t)nW_loc);
     const int64_t n0 = g.n0, nm = g.nm, nl = g.nl, h0 = g.h0, hl = g.hl;
     size_t sc = 0;
@@ -412,6 +421,16 @@ template <class T> struct Plan : PlanBase {
       p.out_ostride = (long)(g.hl + 1) * g.nm; p.out_kstride = g.nm;
     } else {
       p.n_o = 1; p.n_r = g.n0; p.in_ostride = 0; p.in_rstride = g.nl; p.out_ostride = 0; p.out_kstride = g.n0;
+    }
+    // prologues that read the mode-bin table share one lookup per mirror quad (P1MBody); needs >= 1 pair of rows per CTA
+    if constexpr (Pro::kUsesBins) {
+      if (c1.lg_R >= 1 && p.n_r >= 2 && p1m_enabled()) {
+        bool three = 3 * (c1.smem + 2048) <= size_t(100) * 1024;
+        if (const char* e = std::getenv("NB200_P1M_MINB")) three = (e[0] == '3');     // developer knob
+        if (three) launch<P1MBody<T, Pro, 3>>(c1.grid, c1.block, c1.smem, st, p);
+        else launch<P1MBody<T, Pro, 2>>(c1.grid, c1.block, c1.smem, st, p);
+        return;
+      }
     }
     if (pro.aligned()) launch<P1Body<T, Pro, true>>(c1.grid, c1.block, c1.smem, st, p);
     else launch<P1Body<T, Pro, false>>(c1.grid, c1.block, c1.smem, st, p);

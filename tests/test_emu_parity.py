@@ -64,6 +64,19 @@ def test_multichunk_amplitude_chain(rt):
     pc.check_against_oracle(rt, (64, 64), 0.1, flexibility=None, asperity=None)
 
 
+@pytest.mark.parametrize("lg_r", ["1", "2", "3"])
+def test_p1_mirror_quads(rt, monkeypatch, lg_r):
+    """P1MBody (one bin lookup per mirror quad) needs >= 2 lines per CTA, which the launch heuristic only picks
+    for grids with many lines: force it (developer knob read at plan creation) on small grids."""
+    monkeypatch.setenv("NB200_LGR1", lg_r)
+    for shape, dist in [((8, 32), (0.3, 0.11)), ((16, 16), 1.0), ((8, 8, 16), 0.2), ((64, 2), 1.0)]:
+        pc.check_bilinear(rt, shape, dist)
+    pc.check_against_oracle(rt, (32, 64), (0.1, 0.05))
+    pc.check_against_oracle(rt, (8, 16, 8), 0.3, lh_kind="poisson")
+    monkeypatch.setenv("NB200_SCAN_E", "4")
+    pc.check_against_oracle(rt, (64, 128), (0.01, 0.02))
+
+
 def test_unsupported_shapes_fail_loudly(rt):
     with pytest.raises(nb.NB200Error, match="power of two"):
         nb.Plan((3, 3), 0.1, runtime=rt)

@@ -62,6 +62,20 @@ def test_multichunk_amplitude_chain(rt):
     pc.check_against_oracle(rt, (64, 64), 0.1, flexibility=None, asperity=None)
 
 
+@pytest.mark.parametrize("lg_r", ["1", "2"])
+def test_p1_mirror_quads(rt, monkeypatch, lg_r):
+    """P1MBody (one bin lookup per mirror quad): the launch heuristic only gives a CTA >= 2 lines on large grids
+    (covered by the property tests below); force it on oracle-sized grids through the plan-creation knob."""
+    monkeypatch.setenv("NB200_LGR1", lg_r)
+    for shape, dist in [((8, 32), (0.3, 0.11)), ((16, 16), 1.0), ((8, 8, 16), 0.2), ((64, 2), 1.0)]:
+        pc.check_bilinear(rt, shape, dist)
+    pc.check_against_oracle(rt, (32, 64), (0.1, 0.05))
+    pc.check_against_oracle(rt, (8, 16, 8), 0.3, lh_kind="poisson")
+    pc.check_against_oracle(rt, (512, 1024), (0.01, 0.02))
+    monkeypatch.setenv("NB200_SCAN_E", "4")
+    pc.check_against_oracle(rt, (64, 128), (0.01, 0.02))
+
+
 @pytest.mark.parametrize("shape,dist,kind", [((128, 128), 1.0 / 128, "gauss"), ((2048, 2048), 1.0 / 2048, "poisson"),
                                              ((4096, 4096), 1.0 / 4096, "gauss"), ((256, 256, 256), 1.0 / 256, "gauss")])
 def test_full_size_properties(rt, shape, dist, kind):

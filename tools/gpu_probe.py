@@ -10,6 +10,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nifty_b200 as nb  # noqa: E402
+import nifty_b200._capi as _capi  # noqa: E402
+
+if os.environ.get("NB200_PROBE_LIB"):      # tuning variants built by tools/build_variant.sh
+    _capi.DEFAULT_LIB = os.path.abspath(os.environ["NB200_PROBE_LIB"])
 
 
 def build(shape, dist, dtype, lh="gauss"):
@@ -30,6 +34,7 @@ def main():
     ap.add_argument("--shape", default="4096,4096")
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--quick", action="store_true", help="product timing only")
     a = ap.parse_args()
     shape = tuple(int(s) for s in a.shape.split(","))
     dtype = torch.float64 if a.dtype == "f64" else torch.float32
@@ -69,6 +74,9 @@ def main():
     tot = sum(v[1] for v in tm.values())
     for k, (c, msk) in sorted(tm.items(), key=lambda kv: -kv[1][1]):
         print(f"  {msk/c*1e3:9.1f} us x{c//a.steps}  {100*msk/tot:5.1f}%  {k}")
+    print(f"  checksum: sum {out.double().sum().item():.12e}  |out| {out.double().norm().item():.12e}")
+    if a.quick:
+        return
     # one MGVI-style CG solve with per-kernel timing
     j = torch.randn(L, dtype=dtype, device=rt.device, generator=gen)
     x, res = lin.cg_solve(j, j.clone(), absdelta=1e-4 * L / 10, maxiter=100, raise_nonposdef=False)
