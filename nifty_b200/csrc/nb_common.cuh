@@ -190,6 +190,36 @@ __device__ NB_INLINE void prefetch_l2(Ctx& ctx, const void* p, size_t bytes) {
 }
 #endif
 
+// Batched strided loop over [0, cnt): a thread handles the items i0 + u * nthr, u < U, per round.
+//   issue(i0, slot)    every independent global load of the round (from always-valid addresses)
+//   gather(slot)       loads that depend on those (table lookups)
+//   consume(i0, slot)  arithmetic, shared memory, stores
+// PIPE = true issues round k+1 before round k is consumed (one round of loads always in flight; costs a
+// second set of slot registers).  Measured per loop (profiles/r2_notes.md): it pays in the P5 epilogue only.
+template <bool PIPE, int U, class Slot, class Issue, class Gather, class Consume>
+NB_HD NB_INLINE void batched_loop(Ctx& ctx, int cnt, const Issue& issue, const Gather& gather, const Consume& consume) {
+  const int step = ctx.nthr * U;
+  Slot cur[U];
+  int i0 = ctx.tid;
+  if (i0 < cnt) { issue(i0, cur); gather(cur); }
+  for (; i0 < cnt; i0 += step) {
+    const bool more = i0 + step < cnt;
+    if (PIPE) {
+      Slot nxt[U];
+      if (more) issue(i0 + step, nxt);
+      consume(i0, cur);
+      if (more) {
+        gather(nxt);
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+      }
+    } else {
+      consume(i0, cur);
+      if (more) { issue(i0 + step, cur); gather(cur); }
+    }
+  }
+}
+
 #define NB_FOR(ctx, i, count) for (int i = (ctx).tid; i < (int)(count); i += (ctx).nthr)
 
 NB_HH NB_INLINE int fold_idx(int x, int n) { return x <= n - x ? x : n - x; }

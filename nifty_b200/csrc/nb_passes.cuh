@@ -265,9 +265,8 @@ template <class T, class Pro, int MINB> struct P1MBody {
     {   // quads (e, n-e), 0 < e < h, of the pairs i >= 1
       constexpr int U = 2;
       const int cnt = hR << lg_h;
-      for (int q0 = ctx.tid; q0 < cnt; q0 += ctx.nthr * U) {
-        typename Pro::Pre pre[U];
-        bool ok[U];
+      struct Slot { int rp, e; bool ok; typename Pro::Pre pre; };
+      auto issue = [&](int q0, Slot* sl) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           int q = q0 + u * ctx.nthr;
@@ -275,24 +274,29 @@ template <class T, class Pro, int MINB> struct P1MBody {
           q = in ? q : 0;
           int rp = q >> lg_h, e = q & (h - 1);
           int i = i0 + rp;
-          ok[u] = in && i != 0 && e != 0;
+          sl[u].ok = in && i != 0 && e != 0;
+          sl[u].rp = rp; sl[u].e = e;
           e = e != 0 ? e : 1;
           int ra = (i != 0) ? i : 1, rb = p.n_r - ra;          // safe rows for the masked-out slots
-          p.pro.preload(in0 + ra * p.in_rstride, in0 + rb * p.in_rstride, p.pro.bins(o, ra), e, n - e, pre[u]);
+          p.pro.preload(in0 + ra * p.in_rstride, in0 + rb * p.in_rstride, p.pro.bins(o, ra), e, n - e, sl[u].pre);
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) p.pro.gather(pre[u]);
+      };
+      auto consume = [&](int, const Slot* sl) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (!ok[u]) continue;
-          int q = q0 + u * ctx.nthr;
-          int rp = q >> lg_h, e = q & (h - 1);
+          if (!sl[u].ok) continue;
+          const int rp = sl[u].rp, e = sl[u].e;
           T v[4];
-          p.pro.finish(pre[u], v);
+          p.pro.finish(sl[u].pre, v);
           sr[NB_P1M_SLOT(rp, e)] = v[0]; sr[NB_P1M_SLOT(rp, n - e)] = v[1];
           sr[NB_P1M_SLOT(rp + hR, e)] = v[2]; sr[NB_P1M_SLOT(rp + hR, n - e)] = v[3];
         }
-      }
+      };
+      auto gather = [&](Slot* sl) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) p.pro.gather(sl[u].pre);
+      };
+      batched_loop<false, U, Slot>(ctx, cnt, issue, gather, consume);
     }
     {   // self-mirrored elements e = 0 and e = h of every line
       NB_FOR(ctx, k, 2 * R) {
@@ -312,36 +316,45 @@ template <class T, class Pro, int MINB> struct P1MBody {
 #undef NB_P1M_SLOT
     ctx.sync();
     for (int st = 0; st < p.fft.ns; ++st) fft_stage_any<false>(ctx, s, p.fft, st, R, p.pitch, p.tw, p.lg_tw);
+    // split of the half-length complex FFT Z into the spectrum of the real line:
+    //   X[k] = (e - i w^k d)/2,  X[h-k] = conj(e + i w^k d)/2   with e = Z[k] + conj Z[h-k], d = Z[k] - conj Z[h-k],
+    // i.e. both outputs of the pair (k, h-k) come from one pair of shared-memory reads, one twiddle and
+    // one complex product; k runs over [0, h/2] (k = h/2 pairs with itself, k = 0 with h).
     const T half = T(0.5);
     cplx<T>* outp = p.out + o * p.out_ostride;
     const int tsh = p.lg_tw - p.lg_n;
     constexpr int U = 4;
-    const int total = (h + 1) << p.lg_R;
-    for (int j0 = ctx.tid; j0 < total; j0 += ctx.nthr * U) {
-      int pk[U], pc[U];
-      cplx<T> w[U];
+    const int hh = h >> 1;
+    const int total = (hh + 1) << p.lg_R;
+    struct PSlot { int pk, pc; cplx<T> w; };
+    auto pissue = [&](int j0, PSlot* sl) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         int i = j0 + u * ctx.nthr;
         i = i < total ? i : 0;
         int k = i >> p.lg_R;
-        pk[u] = ldg(p.fft.pos + (k & (h - 1)));
-        pc[u] = ldg(p.fft.pos + ((h - k) & (h - 1)));
-        w[u] = ldg(p.tw + ((size_t)k << tsh));
+        sl[u].pk = ldg(p.fft.pos + (k & (h - 1)));
+        sl[u].pc = ldg(p.fft.pos + ((h - k) & (h - 1)));
+        sl[u].w = ldg(p.tw + ((size_t)k << tsh));
       }
+    };
+    auto pconsume = [&](int j0, const PSlot* sl) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         int i = j0 + u * ctx.nthr;
         if (i >= total) break;
         int k = i >> p.lg_R, r = i & (R - 1);
         const cplx<T>* line = s + r * p.pitch;
-        cplx<T> zk = line[pk[u]];
-        cplx<T> zc = cconj(line[pc[u]]);
+        cplx<T> zk = line[sl[u].pk];
+        cplx<T> zc = cconj(line[sl[u].pc]);
         cplx<T> e = zk + zc, d = zk - zc;
-        cplx<T> wd = cmul_mi(cmul(w[u], d));   // -i w (zk - zc)
-        outp[k * p.out_kstride + row_of(r, i0, hR, p.n_r)] = cmake<T>(half * (e.x + wd.x), half * (e.y + wd.y));
+        cplx<T> m = cmul_mi(cmul(sl[u].w, d));   // -i w (zk - zc)
+        const int row = row_of(r, i0, hR, p.n_r);
+        outp[k * p.out_kstride + row] = cmake<T>(half * (e.x + m.x), half * (e.y + m.y));
+        if (h - k != k) outp[(h - k) * p.out_kstride + row] = cmake<T>(half * (e.x - m.x), -half * (e.y - m.y));
       }
-    }
+    };
+    batched_loop<false, U, PSlot>(ctx, total, pissue, [](PSlot*) {}, pconsume);
   }
 };
 
@@ -552,11 +565,12 @@ template <class T> struct P3Params {
   PointOp<T> op;
 };
 
-template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
+// MINB = CTAs per SM the register budget is cut for (80 registers at 3, ~106 at 2).  Three 64 KB CTAs leave
+// only ~25 KB of L1 for the slot / twiddle tables every phase reads; which side wins was measured per shape
+// (profiles/r2_notes.md) and is chosen by the host for the fused metric pass.
+template <class T, bool FWD, bool ADJ, int MODE, int MINB = 2> struct P3Body {
   typedef P3Params<T> Params;
-#ifdef NB_P3_MINB
-  static constexpr int kMinBlocks = NB_P3_MINB;
-#endif
+  static constexpr int kMinBlocks = MINB;
   // Hermitian combine of the pair (x, y = -x) of one line + pointwise operator
   static NB_HD NB_INLINE void pair(const Params& p, cplx<T>* line, const LineInfo& li, int x, int y, T cshift, T scv,
                                    T& acc0, T& acc1) {
@@ -606,44 +620,47 @@ template <class T, bool FWD, bool ADJ, int MODE> struct P3Body {
       if (n == 1) {
         NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], 0, 0, cshift, scv, acc0, acc1);
       } else if (MODE == PM_METRIC && ADJ) {
-        // hot path: pairs (x, n-x), 0 < x < h, of lines that have a partner; every load of a batch
-        // of U pairs is issued (from always-valid addresses) before anything depends on it
+        // hot path: pairs (x, n-x), 0 < x < h, of lines that have a partner; every load of a batch of U
+        // pairs is issued (from always-valid addresses) before anything depends on it
         constexpr int U = 2;
         const T* ja = p.op.jl_a; const T* jb = p.op.jl_b;
         const bool same = (ja == jb);
         const T sg = p.hsign, iv = p.op.invV;
         const int cnt = R << lg_h;
-        for (int i0 = ctx.tid; i0 < cnt; i0 += ctx.nthr * U) {
-          int px[U], py[U]; bool ok[U];
-          T mAx[U], mAy[U], mBx[U], mBy[U];
+        struct Slot { int px, py, r; bool ok; T mAx, mAy, mBx, mBy; };
+        auto issue = [&](int i0, Slot* sl) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             int i = i0 + u * ctx.nthr;
             bool in = i < cnt;
             i = in ? i : 0;
             int r = i >> lg_h, x = i & (h - 1);
-            ok[u] = in && li[r].active && li[r].lB >= 0 && x != 0;
+            sl[u].ok = in && li[r].active && li[r].lB >= 0 && x != 0;
+            sl[u].r = r;
             x = x != 0 ? x : 1;
             int y = n - x;
             long iA = (long)li[r].lA * n, iB = (long)(li[r].lB >= 0 ? li[r].lB : li[r].lA) * n;
-            px[u] = ldg(p.fft.pos + x); py[u] = ldg(p.fft.pos + y);
-            mAx[u] = ld_stream(ja + iA + x); mAy[u] = ld_stream(ja + iA + y); mBx[u] = ld_stream(ja + iB + x); mBy[u] = ld_stream(ja + iB + y);
-            if (!same) { mAx[u] *= ld_stream(jb + iA + x); mAy[u] *= ld_stream(jb + iA + y); mBx[u] *= ld_stream(jb + iB + x); mBy[u] *= ld_stream(jb + iB + y); }
-            else { mAx[u] *= mAx[u]; mAy[u] *= mAy[u]; mBx[u] *= mBx[u]; mBy[u] *= mBy[u]; }
+            sl[u].px = ldg(p.fft.pos + x); sl[u].py = ldg(p.fft.pos + y);
+            T aX = ld_stream(ja + iA + x), aY = ld_stream(ja + iA + y), bX = ld_stream(ja + iB + x), bY = ld_stream(ja + iB + y);
+            if (!same) { aX *= ld_stream(jb + iA + x); aY *= ld_stream(jb + iA + y); bX *= ld_stream(jb + iB + x); bY *= ld_stream(jb + iB + y); }
+            else { aX *= aX; aY *= aY; bX *= bX; bY *= bY; }
+            sl[u].mAx = aX; sl[u].mAy = aY; sl[u].mBx = bX; sl[u].mBy = bY;
           }
+        };
+        auto consume = [&](int, const Slot* sl) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            if (!ok[u]) continue;
-            int i = i0 + u * ctx.nthr;
-            cplx<T>* line = s + (i >> lg_h) * p.pitch;
-            cplx<T> cx = line[px[u]], cy = line[py[u]];
-            T aX = mAx[u] * ((cx.x + sg * cx.y) * iv + cshift), bY = mBy[u] * ((cx.x - sg * cx.y) * iv + cshift);
-            T aY = mAy[u] * ((cy.x + sg * cy.y) * iv + cshift), bX = mBx[u] * ((cy.x - sg * cy.y) * iv + cshift);
+            if (!sl[u].ok) continue;
+            cplx<T>* line = s + sl[u].r * p.pitch;
+            cplx<T> cx = line[sl[u].px], cy = line[sl[u].py];
+            T aX = sl[u].mAx * ((cx.x + sg * cx.y) * iv + cshift), bY = sl[u].mBy * ((cx.x - sg * cx.y) * iv + cshift);
+            T aY = sl[u].mAy * ((cy.x + sg * cy.y) * iv + cshift), bX = sl[u].mBx * ((cy.x - sg * cy.y) * iv + cshift);
             acc0 += (aX + aY) + (bX + bY);
-            line[px[u]] = cmake<T>(aX, bX);
-            line[py[u]] = cmake<T>(aY, bY);
+            line[sl[u].px] = cmake<T>(aX, bX);
+            line[sl[u].py] = cmake<T>(aY, bY);
           }
-        }
+        };
+        batched_loop<false, U, Slot>(ctx, cnt, issue, [](Slot*) {}, consume);
         // the self-paired columns x = 0 and x = h, and lines without a partner
         NB_FOR(ctx, i, 2 * R) {
           int r = i >> 1;
@@ -797,6 +814,7 @@ template <class T, class Epi> struct P5Params {
 
 template <class T, class Epi> struct P5Body {
   typedef P5Params<T, Epi> Params;
+  static constexpr int kMinBlocks = 2;     // 128 registers: the pipelined epilogue spills at the 80 of three CTAs per SM (251 vs 151 us)
   static NB_HD NB_INLINE void pair(const Params& p, const cplx<T>* line, const LineInfo& li, int x, int y, T& acc) {
     const T sg = p.hsign;
     const int n = 1 << p.lg_n, h = n >> 1, nmid = 1 << p.mg.lg_mid;
@@ -830,39 +848,47 @@ template <class T, class Epi> struct P5Body {
     if (n == 1) {
       NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], 0, 0, acc);
     } else if (Epi::BATCHED) {
-      // hot path: pairs (x, n-x), 0 < x < h, of lines with a partner row, U pairs per batch
+      // hot path: pairs (x, n-x), 0 < x < h, of lines with a partner row, U pairs per batch.  The loop is
+      // software-pipelined: the streaming loads and bin indices of batch k+1 are issued before batch k is
+      // finished (arithmetic + stores), its table gathers right after, so that a thread always has one
+      // batch of global loads in flight (ncu r2a: 52 % of this pass's samples sat in this loop, 37 % of
+      // them waiting on the two dependent load rounds of the unpipelined form).
       constexpr int U = 2;
       const T sg = p.hsign;
       const int cnt = R << lg_h, nmid = 1 << p.mg.lg_mid;
-      for (int i0 = ctx.tid; i0 < cnt; i0 += ctx.nthr * U) {
-        int px[U], py[U]; bool ok[U];
-        typename Epi::Pre pre[U];
+      struct Slot { int px, py, r, x; bool ok; typename Epi::Pre pre; };
+      auto issue = [&](int i0, Slot* sl) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           int i = i0 + u * ctx.nthr;
           bool in = i < cnt;
           i = in ? i : 0;
           int r = i >> lg_h, x = i & (h - 1);
-          ok[u] = in && li[r].active && li[r].lB >= 0 && x != 0;
+          sl[u].ok = in && li[r].active && li[r].lB >= 0 && x != 0;
           x = x != 0 ? x : 1;
+          sl[u].r = r; sl[u].x = x;
           int a = li[r].lA >> p.mg.lg_mid, km = li[r].lA & (nmid - 1);
           long fbase = ((long)a * p.hmid1 + fold_idx(km, nmid)) * (h + 1);
-          px[u] = ldg(p.fft.pos + x); py[u] = ldg(p.fft.pos + (n - x));
-          p.epi.preload((long)li[r].lA * n, (long)(li[r].lB >= 0 ? li[r].lB : li[r].lA) * n, fbase, x, n - x, pre[u]);
+          sl[u].px = ldg(p.fft.pos + x); sl[u].py = ldg(p.fft.pos + (n - x));
+          p.epi.preload((long)li[r].lA * n, (long)(li[r].lB >= 0 ? li[r].lB : li[r].lA) * n, fbase, x, n - x, sl[u].pre);
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) p.epi.gather(pre[u]);
+      };
+      auto consume = [&](int, const Slot* sl) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (!ok[u]) continue;
-          int i = i0 + u * ctx.nthr;
-          int r = i >> lg_h, x = i & (h - 1);
+          if (!sl[u].ok) continue;
+          const int r = sl[u].r, x = sl[u].x;
           const cplx<T>* line = s + r * p.pitch;
-          cplx<T> cx = line[px[u]], cy = line[py[u]];
+          cplx<T> cx = line[sl[u].px], cy = line[sl[u].py];
           p.epi.finish((long)li[r].lA * n, (long)li[r].lB * n, (long)li[r].lA * (h + 1), x, n - x, cx.x + sg * cx.y, cy.x + sg * cy.y,
-                       cy.x - sg * cy.y, cx.x - sg * cx.y, pre[u], acc);
+                       cy.x - sg * cy.y, cx.x - sg * cx.y, sl[u].pre, acc);
         }
-      }
+      };
+      auto gather = [&](Slot* sl) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) p.epi.gather(sl[u].pre);
+      };
+      batched_loop<true, U, Slot>(ctx, cnt, issue, gather, consume);
       NB_FOR(ctx, i, 2 * R) {
         int r = i >> 1;
         if (li[r].active) { int x = (i & 1) ? h : 0; pair(p, s + r * p.pitch, li[r], x, x, acc); }

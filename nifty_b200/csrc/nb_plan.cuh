@@ -463,7 +463,14 @@ template <class T> struct Plan : PlanBase {
     p.src_off = dist ? src_off3.p : nullptr; p.src_mul = dist ? src_mul3.p : nullptr;
     const size_t sm = c3.smem + LINEINFO_BYTES;
     if constexpr (FWD && ADJ) {
-      if (op.mode == PM_METRIC) launch<P3Body<T, true, true, PM_METRIC>>(grid3, c3.block, sm, st, p);
+      if (op.mode == PM_METRIC) {
+        // measured: 3 CTAs/SM win for short lines (256^3: 145 vs 166 us) and for 4096-point lines (204 vs 213 us),
+        // 2 CTAs/SM for two 2048-point lines per CTA (56 vs 60 us)
+        bool three = 3 * (sm + 2048) <= size_t(100) * 1024 || lg0 >= 12;
+        if (const char* e = std::getenv("NB200_P3_MINB")) three = (e[0] == '3');     // developer knob
+        if (three) launch<P3Body<T, true, true, PM_METRIC, 3>>(grid3, c3.block, sm, st, p);
+        else launch<P3Body<T, true, true, PM_METRIC, 2>>(grid3, c3.block, sm, st, p);
+      }
       else if (op.mode == PM_LINEARIZE) launch<P3Body<T, true, true, PM_LINEARIZE>>(grid3, c3.block, sm, st, p);
       else throw Error{"nb200: invalid pointwise mode for the fused pass"};
     } else if constexpr (FWD) {
