@@ -263,7 +263,7 @@ template <class T, class Pro, int MINB> struct P1MBody {
     // real element x of line L lives at sr[2 * (L * pitch + swz(x >> 1)) + (x & 1)]
 #define NB_P1M_SLOT(L, x) ((((L) * p.pitch + swz((x) >> 1)) << 1) + ((x) & 1))
     {   // quads (e, n-e), 0 < e < h, of the pairs i >= 1
-      constexpr int U = 2;
+      constexpr int U = MINB == 2 ? 4 : 2;     // measured: 4 quads per round pay with the 128-register budget only
       const int cnt = hR << lg_h;
       struct Slot { int rp, e; bool ok; typename Pro::Pre pre; };
       auto issue = [&](int q0, Slot* sl) {
@@ -323,7 +323,7 @@ template <class T, class Pro, int MINB> struct P1MBody {
     const T half = T(0.5);
     cplx<T>* outp = p.out + o * p.out_ostride;
     const int tsh = p.lg_tw - p.lg_n;
-    constexpr int U = 4;
+    constexpr int U = 2;
     const int hh = h >> 1;
     const int total = (hh + 1) << p.lg_R;
     struct PSlot { int pk, pc; cplx<T> w; };
@@ -758,7 +758,7 @@ template <class T> struct EpiAdjoint {
     T o0 = q.A * gAx + q.a0, o1 = q.A * gAy + q.a1, o2 = q.A * gBx + q.a2, o3 = q.A * gBy + q.a3;
     acc += (q.a0 * o0 + q.a1 * o1) + (q.a2 * o2 + q.a3 * o3);
     out[rowA + x] = o0; out[rowA + y] = o1; out[rowB + x] = o2; out[rowB + y] = o3;
-    if (W) W[wbase + x] = (q.x0 * gAx + q.x1 * gAy) + (q.x2 * gBx + q.x3 * gBy);
+    if (W) W[wbase + x] = (q.x0 * gAx + q.x1 * gAy) + (q.x2 * gBx + q.x3 * gBy);   // (an L2 evict_last hint here did not help the segment sum)
   }
   // all loads first (the outputs may alias the inputs as far as the compiler knows), then the stores
   NB_HD NB_INLINE void emit(long rowA, long rowB, long fbase, long wbase, int x, int y, T gAx, T gAy, T gBx, T gBy,

@@ -125,10 +125,12 @@ def slab_check(rt, shape, dist_, lh_kind="gauss", seed=3, tol=1e-10):
     return errs
 
 
-def _worker(rank, world, port, shape, chunks):
+def _worker(rank, world, port, shape, chunks, lg_r1=None):
     sys.path.insert(0, os.path.dirname(HERE))
     sys.path.insert(0, HERE)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NB200_SLAB_CHUNKS=str(chunks))
+    if lg_r1 is not None:          # several lines per CTA in the first pass -> the mirror-quad body (P1MBody)
+        os.environ["NB200_LGR1"] = str(lg_r1)
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import nifty_b200 as nb
@@ -146,3 +148,11 @@ def _worker(rank, world, port, shape, chunks):
 def test_slab_decomposition_matches_global_oracle(world, shape, chunks):
     """chunks > 1: every exchange is pipelined in point-to-point pieces between chunked pass launches."""
     mp.spawn(_worker, args=(world, _free_port(), shape, chunks), nprocs=world, join=True)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world,shape,chunks,lg_r1", [(2, (8, 4, 16), 1, 1), (2, (16, 8, 8), 2, 2)])
+def test_slab_with_mirror_quad_first_pass(world, shape, chunks, lg_r1):
+    """The launch heuristic gives the first pass >= 2 lines per CTA only on large grids; force it here so that the
+    mirror-quad body runs on the local slabs of a distributed plan."""
+    mp.spawn(_worker, args=(world, _free_port(), shape, chunks, lg_r1), nprocs=world, join=True)
