@@ -56,7 +56,7 @@ def algorithmic_bytes_mvp(shape, w=8):
 def kernel_bytes(name, shape, w=8):
     """Algorithmic bytes of one launch of the named pass."""
     N = int(np.prod(shape))
-    if "P1Body" in name:
+    if "P1Body" in name or "P1MBody" in name:
         return 3 * w * N      # read t, xi; write half spectrum
     if "P3Body" in name:
         return 3 * w * N      # read half spectrum, Jacobian weight; write half spectrum
@@ -65,6 +65,14 @@ def kernel_bytes(name, shape, w=8):
     if "PCBody" in name:
         return 2 * w * N
     return None
+
+
+def short_kernel_name(name):
+    """Body name of a mangled kernel name as recorded by the library's launch timer."""
+    for k in ("P1MBody", "P1Body", "P3Body", "P5Body", "PCBody", "SegSum", "ScanApply", "ScanAgg", "CgStep", "CgDir"):
+        if k in name:
+            return k
+    return name[:40]
 
 
 class ClockSampler:
@@ -263,11 +271,10 @@ def run_b200(args, shape, wname, rank, world, local_rank):
     achieved = kb / (dom_ms / dom_cnt * 1e-3) / 1e9 if kb else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wname, {}).get(
-            "P1Body" if "P1Body" in dom_name else "P3Body" if "P3Body" in dom_name else "P5Body" if "P5Body" in dom_name else "PCBody")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wname, {}).get(short_kernel_name(dom_name))
     except Exception:
         pass
-    short = [k for k in ("P1Body", "P3Body", "P5Body", "PCBody", "SegSum", "ScanApply", "ScanAgg", "ScanTop") if k in dom_name][0]
+    short = short_kernel_name(dom_name)
     roofline = {"bound": "hbm", "kernel": short, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "kernel_share_of_step": dom_ms / tot,

@@ -20,22 +20,26 @@ METRICS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.
            'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
            'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
            'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
-           'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'smsp__inst_executed.sum']
+           'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'smsp__inst_executed.sum',
+           'l1tex__m_xbar2l1tex_read_bytes.sum', 'l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct', 'lts__t_sector_op_read_hit_rate.pct',
+           'launch__shared_mem_config_size']
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 lines = [f"# ncu summary `{name}` ({workload}, one B200, `ncu --set full --clock-control none`)", "",
-         "Source: `tools/gpu_prof.sh` -> `gpurun_out/prof_%s.ncu-rep`; values per launch.  Times under ncu are cold-cache and" % tag,
+         "Source: `tools/gpu_prof2.sh` -> `gpurun_out/prof_%s.ncu-rep`; values per launch.  Times under ncu are cold-cache and" % tag,
          "serialised: compare SHARES with bench.py's CUDA-event timings, not absolutes.", ""]
 traffic = {}
 seen = set()
 for r in rows[2:]:
     kn = r[idx['Kernel Name']]
-    short = [k for k in ("P1Body", "P3Body", "P5Body", "PCBody") if k in kn]
+    short = [k for k in ("P1MBody", "P1Body", "P3Body", "P5Body", "PCBody", "SegSum", "ScanApplyBody<double, Vjp", "ScanApplyBody<double, Jvp",
+                         "ScanAggBody<double, Vjp", "ScanAggBody<double, Jvp") if k in kn]
     if not short or short[0] in seen:
         continue
     seen.add(short[0])
+    short[0] = short[0].replace("Body<double, ", "_")
     lines += [f"## {kn}", "", "| metric | value | unit |", "|---|---|---|"]
     for m in METRICS:
         if m in idx:
@@ -47,7 +51,7 @@ for r in rows[2:]:
     traffic[short[0]] = tobytes(r[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) + \
         tobytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
 if os.path.exists(launches):
-    lines += ["## launch list (gpu__time_duration.sum, one product = the kernels between two P1Body launches)", "", "```"]
+    lines += ["## launch list (gpu__time_duration.sum, one product = the kernels between two first-pass launches)", "", "```"]
     txt = [l for l in open(launches).read().splitlines() if l and not l.startswith("==")]
     rd = list(csv.reader(txt))
     h = rd[0]
@@ -57,12 +61,13 @@ if os.path.exists(launches):
         if len(r) > vi:
             lines.append(f"{r[vi]:>12s} ns  {r[ki][:110]}")
             n += 1
-            if n >= 24:
+            if n >= 32:
                 break
     lines += ["```", ""]
 open(out_md, "w").write("\n".join(lines))
 tj = os.path.join(ROOT, "profiles", "traffic.json")
 allt = json.load(open(tj)) if os.path.exists(tj) else {}
 allt[workload] = traffic
+allt["_source"] = f"ncu --set full, profiles/{name}_ncu_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
 json.dump(allt, open(tj, "w"), indent=1)
 print("wrote", out_md, traffic)
