@@ -331,6 +331,7 @@ def run_b200(args, shape, wname, rank, world, local_rank):
     # sample-draw seconds (second half of the BASELINE metric): one draw_linear_residual-style CG
     # solve with the demo's settings (absdelta = 1e-4 * L / 10, maxiter = 100; demos/re/0_intro.py:105-108)
     j = sig.layout.random(1000 + rank, dtype, dev)
+    lin.cg_solve(j, j.clone(), absdelta=1e-4 * L / 10, maxiter=2, raise_nonposdef=False)   # untimed: allocates the CG work vectors
     torch.cuda.synchronize()
     ts = time.perf_counter()
     x, cgres = lin.cg_solve(j, j.clone(), absdelta=1e-4 * L / 10, maxiter=100, raise_nonposdef=False)
