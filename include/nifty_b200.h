@@ -208,6 +208,8 @@ int nb200_cg_solve(nb200_lin* lin, nb200_lin* lin_b, void* stream, const void* j
 /* ---- fused vector algebra on flat latent vectors (tree_math vdot/norm/axpy; evi.py:136) ---------- */
 int nb200_vec_axpby(nb200_plan* plan, void* stream, int64_t n, double a, const void* x, double b, const void* y, void* out);
 int nb200_vec_dot(nb200_plan* plan, void* stream, int64_t n, const void* x, const void* y, double* out_host);
+/* out_host[0] = sum x_i, out_host[1] = sum x_i^2: the moments of reduced_residual_stats (minisanity.py:17-21, 30-82) */
+int nb200_vec_stats(nb200_plan* plan, void* stream, int64_t n, const void* x, double* out_host);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,7 @@ SIGNATURES = {
     "nb200_cg_solve": (C.c_int, [vp, vp, vp, vp, vp, C.POINTER(CgOpts), C.POINTER(CgResult)]),
     "nb200_vec_axpby": (C.c_int, [vp, vp, i64, f64, vp, f64, vp, vp]),
     "nb200_vec_dot": (C.c_int, [vp, vp, i64, vp, vp, C.POINTER(f64)]),
+    "nb200_vec_stats": (C.c_int, [vp, vp, i64, vp, C.POINTER(f64)]),
 }
 
 

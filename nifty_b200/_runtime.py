@@ -331,6 +331,13 @@ class Plan:
         return self._table("nb200_plan_power_distributor", self.N, np.int32).reshape(self.shape)
 
     # -- raw operators --------------------------------------------------------------------------
+    def vec_stats(self, x: torch.Tensor):
+        """(sum x, sum x^2) of a contiguous device vector of this plan's dtype (``nb200_vec_stats``)."""
+        x = self.rt.asarray(x, self.dtype).reshape(-1)
+        out = (C.c_double * 2)()
+        self.rt.api.call("nb200_vec_stats", self._h, self.rt.stream(), int(x.numel()), self.rt.ptr(x), out)
+        return float(out[0]), float(out[1])
+
     def hartley(self, x: torch.Tensor) -> torch.Tensor:
         x = self.rt.asarray(x, self.dtype)
         if tuple(x.shape) != self.shape:

@@ -478,6 +478,20 @@ int nb200_vec_dot(nb200_plan* plan, void* stream, int64_t n, const void* x, cons
   NB_CATCH
 }
 
+int nb200_vec_stats(nb200_plan* plan, void* stream, int64_t n, const void* x, double* out_host) {
+  NB_TRY
+  NB_DISPATCH(plan->impl->dtype, TT, {
+    CgWork<TT>& w = cg_work<TT>();
+    if (w.partials.n == 0) { w.partials.alloc(4 * 2048); w.counter.alloc(4); w.cgs.alloc(CG_NSCAL); w.cgi.alloc(CGI_NINT); }
+    StatsParams<TT> sp; sp.n = n; sp.x = (const TT*)x; sp.partials = w.partials.p; sp.counter = w.counter.p + 1; sp.out = w.cgs.p + CG_NORM;
+    launch<StatsBody<TT>>((int)std::min<int64_t>((n + 1023) / 1024 + 1, 148 * 8), 256, 1024, (stream_t)stream, sp);
+    TT v[2] = {0, 0}; d2h(v, w.cgs.p + CG_NORM, 2 * sizeof(TT), (stream_t)stream); stream_sync((stream_t)stream);
+    out_host[0] = (double)v[0]; out_host[1] = (double)v[1];
+  })
+  return 0;
+  NB_CATCH
+}
+
 // Per-kernel event timing: begin() arms it, end() synchronises and writes "name count total_ms" lines.
 int nb200_timing_begin(void) {
 #ifndef NB_EMU

@@ -160,4 +160,23 @@ template <class T> struct DotBody {
   }
 };
 
+// (sum x, sum x^2): the two moments behind reduced_residual_stats (nifty/re/minisanity.py:17-21)
+template <class T> struct StatsParams { long n; const T* x; T* partials; unsigned* counter; T* out; };
+template <class T> struct StatsBody {
+  typedef StatsParams<T> Params;
+  static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    T v[2] = {0, 0};
+    const long stride = (long)ctx.nblk * ctx.nthr;
+    for (long i = (long)ctx.bid * ctx.nthr + ctx.tid; i < p.n; i += stride) { T x = p.x[i]; v[0] += x; v[1] += x * x; }
+    ctx.template block_sum_n<2>(v, smem);
+    if (ctx.tid == 0) { p.partials[2 * ctx.bid] = v[0]; p.partials[2 * ctx.bid + 1] = v[1]; }
+    if (ctx.last_block(p.counter)) {
+      T t[2] = {0, 0};
+      NB_FOR(ctx, i, ctx.nblk) { t[0] += p.partials[2 * (size_t)i]; t[1] += p.partials[2 * (size_t)i + 1]; }
+      ctx.template block_sum_n<2>(t, smem);
+      if (ctx.tid == 0) { p.out[0] = t[0]; p.out[1] = t[1]; }
+    }
+  }
+};
+
 }  // namespace nb

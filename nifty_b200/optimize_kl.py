@@ -14,8 +14,10 @@
 
 from __future__ import annotations
 
+import logging
 import os
 import pickle
+from functools import partial
 from typing import Callable, NamedTuple, Optional
 
 import numpy as np
@@ -68,14 +70,52 @@ class _Comm:
         return out
 
 
+def get_status_message(samples, state, residual=None, *, name="", plan=None, layout=None, map="lmap") -> str:
+    """Per-iteration report (optimize_kl.py:40-61): energy, sampling status, KL steps and the minisanity tables of
+    the likelihood residuals and of the latent parameters over the samples."""
+    from .minisanity import minisanity
+    energy = state.minimization_state.fun
+    msg_smpl = ""
+    ss = state.sample_state
+    if isinstance(ss, OptimizeResults):
+        ss = [ss]
+    if isinstance(ss, (list, tuple)) and len(ss) > 0 and all(isinstance(el, OptimizeResults) for el in ss):
+        nlsi = tuple(int(n) for el in ss for n in np.atleast_1d(el.nit))       # one result per sample on this path
+        msg_smpl = f"\n{name}: #(Nonlinear sampling steps) {nlsi}"
+    elif isinstance(ss, (np.ndarray, list, tuple)) and len(ss) > 0:
+        nlsi = tuple(int(el) for el in ss)
+        msg_smpl = f"\n{name}: Linear sampling status {nlsi}"
+    mini_res = ""
+    if residual is not None:
+        _, mini_res = minisanity(samples, residual, plan=plan, map=map)
+    _, mini_pr = minisanity(samples, plan=plan, layout=layout, map=map)
+    return (f"{name}: Iteration {state.nit:04d} E:{energy:+2.4e}"
+            f"{msg_smpl}"
+            f"\n{name}: #(KL minimization steps) {state.minimization_state.nit}"
+            f"\n{name}: Likelihood residual(s):\n{mini_res}"
+            f"\n{name}: Prior residual(s):\n{mini_pr}"
+            f"\n")
+
+
 class OptimizeVI:
     """State-less MGVI / geoVI driver (optimize_kl.py:173-741)."""
 
     def __init__(self, likelihood: LikelihoodWithModel, n_total_iterations: int, *, comm=None,
                  _kl_value_and_grad: Optional[Callable] = None, _kl_metric: Optional[Callable] = None,
                  _draw_linear_residual: Callable = draw_linear_residual,
-                 _nonlinearly_update_residual: Callable = nonlinearly_update_residual):
+                 _nonlinearly_update_residual: Callable = nonlinearly_update_residual,
+                 _get_status_message: Optional[Callable] = None):
         self.likelihood = likelihood
+        if _get_status_message is None:        # optimize_kl.py:376-389
+            plan = likelihood.signal.cf.plan
+            if plan.dist:     # per-leaf moments of a slab-decomposed field would need their own reduction: tables left out
+                def _get_status_message(samples, state, *, name="", **kw):
+                    return (f"{name}: Iteration {state.nit:04d} E:{state.minimization_state.fun:+2.4e}"
+                            f"\n{name}: #(KL minimization steps) {state.minimization_state.nit}\n")
+            else:
+                _get_status_message = partial(get_status_message, residual=likelihood.normalized_residual, plan=plan,
+                                              layout=likelihood.layout)
+        self.get_status_message = _get_status_message
         self.n_total_iterations = n_total_iterations
         self.comm = _Comm(comm)
         self._draw_linear_residual = _draw_linear_residual
@@ -262,8 +302,18 @@ def optimize_kl(likelihood: LikelihoodWithModel, position_or_samples, *, key, n_
     state = fresh if state is None else state._replace(config=fresh.config)
     if odir is not None and rank == 0:
         os.makedirs(odir, exist_ok=True)
-    for _ in range(state.nit, n_total_iterations):
+    sanity_fn = os.path.join(odir, "minisanity.txt") if odir is not None else None       # optimize_kl.py:803, 827
+    if not resume and sanity_fn is not None and rank == 0:
+        open(sanity_fn, "w").close()
+    logger = logging.getLogger("nifty_b200")
+    for i in range(state.nit, n_total_iterations):
+        logger.info(f"OPTIMIZE_KL: Starting {i + 1:04d}")
         samples, state = opt_vi.update(samples, state)
+        msg = opt_vi.get_status_message(samples, state, name="OPTIMIZE_KL")      # :866-870 (rank-local samples)
+        logger.info(msg)
+        if sanity_fn is not None and rank == 0:
+            with open(sanity_fn, "a") as f:
+                f.write("\n" + msg)
         if last_fn is not None:
             gathered = None
             if samples.residuals is not None:

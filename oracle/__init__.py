@@ -41,6 +41,7 @@ from .likelihood import GaussianOracle, PoissonianOracle, SignalOracle  # noqa: 
 from .solvers import cg, newton_cg, CGResult, NewtonResult  # noqa: F401
 from .vi import (  # noqa: F401
     draw_linear_residual,
+    wiener_filter_posterior_mean,
     nonlinearly_update_residual,
     kl_value_and_grad,
     kl_metric,

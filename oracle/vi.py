@@ -102,6 +102,23 @@ def draw_linear_residual(lh, pos, white_data, white_prior, *, from_inverse=True,
     return lay.unpack(smpl), info, res
 
 
+def wiener_filter_posterior_mean(lh, pos, *, cg_kwargs=None):
+    """Posterior mean of the model linearised at ``pos``; signal-space branch of
+    ``wiener_filter_posterior`` (evi.py:453-476 with the linearised data of :457-458):
+    ``j = J^T M (d - f(pos) + J pos)``, ``mean = (J^T M J + 1)^-1 j`` by conjugate gradient.
+    Returns ``(mean dict, info, CGResult)``."""
+    lay, _, ham_metric, lsm, rsm, _ = _flat_ops(lh)
+    pos_v = lay.pack(pos)
+    d_lin = lh.normalized_residual(pos) + rsm(pos_v, pos_v)      # M^(1/2) (d - f(pos) + J pos), M diagonal
+    j = lsm(pos_v, d_lin)
+    kw = dict(cg_kwargs or {})
+    kw.pop("name", None)
+    res = cg(lambda v: ham_metric(pos_v, v), j, **kw)
+    if res.info < 0:
+        raise ValueError("conjugate gradient failed")
+    return lay.unpack(res.x), res.info, res
+
+
 def nonlinearly_update_residual(lh, pos, residual_sample, white_data, white_prior,
                                 metric_sample_sign=1.0, *, minimize_kwargs=None):
     """geoVI update of one residual sample (evi.py:181-255); returns ``(residual, NewtonResult)``."""

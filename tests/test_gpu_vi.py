@@ -19,6 +19,17 @@ def test_draw_linear_residual(rt):
     vc.check_draw_linear_residual(rt)
 
 
+def test_wiener_filter(rt):
+    vc.check_wiener_filter(rt)
+    vc.check_wiener_filter(rt, "g3d_8x8x8")
+    vc.check_wiener_filter(rt, "m2d_16x8")
+
+
+def test_minisanity(rt):
+    vc.check_minisanity(rt)
+    vc.check_minisanity(rt, "g3d_8x8x8")
+
+
 def test_nonlinear_update(rt):
     vc.check_nonlinear_update(rt)
 

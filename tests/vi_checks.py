@@ -38,6 +38,75 @@ def check_draw_linear_residual(rt, name="g2d_16x16"):
     return lh, olh, lay, pos, tpos, white, (wd, wp), res, ores
 
 
+def check_wiener_filter(rt, name="g2d_16x16"):
+    """wiener_filter_posterior (evi.py:399-517, signal-space branch) against the oracle restatement and, through the
+    oracle's operators, against the DENSE solve of the linearised problem (the reference's own check,
+    test/test_re/test_evi.py:206-232, compares with a dense Wiener filter)."""
+    c, g, lh, olh, lay = _setup(rt, name)
+    rng = np.random.default_rng(33)
+    pos = {k: 0.3 * v for k, v in lay.random(rng).items()}
+    kw = dict(resnorm=1e-9, maxiter=400)      # (tighter: the N_RESET residual refresh at iteration 20 trips "energy increased")
+    omean, oinfo, ores = oracle.wiener_filter_posterior_mean(olh, pos, cg_kwargs=kw)
+    # dense cross-check of the oracle: (J^T M J + 1) mean = J^T M (d - f + J p)
+    L = lay.size
+    pv = lay.pack(pos)
+    H = np.stack([lay.pack(olh.metric(pos, lay.unpack(e))) + e for e in np.eye(L)], axis=1)
+    rhs = lay.pack(olh.left_sqrt_metric(pos, olh.normalized_residual(pos) + olh.right_sqrt_metric(pos, pos)))
+    dense = np.linalg.solve(H, rhs)
+    assert rel_err(lay.pack(omean), dense) < 1e-7
+    tpos = rt.asarray(pv, torch.float64)
+    smp, (info, sinfo) = nb.wiener_filter_posterior(lh, tpos, key=5, n_samples=2, model_is_linear=False,
+                                                    draw_linear_kwargs=dict(cg_kwargs=kw))
+    assert info == oinfo and sinfo == [0, 0]
+    assert rel_err(t2n(smp.pos), dense) < 1e-7
+    assert rel_err(t2n(smp.pos), lay.pack(omean)) < 1e-9
+    s, r = smp.samples, smp.residuals
+    assert s.shape == (4, L) and torch.equal(r[0], -r[1]) and torch.equal(r[2], -r[3])     # mirrored pairs around the mean
+    assert torch.equal(s[2], smp.pos + r[2])
+    # the draws are MGVI samples at the posterior mean: same as draw_linear_residual with the same key
+    k0 = nb.random_split(5, 2)[0]
+    r0, _ = nb.draw_linear_residual(lh, smp.pos, k0, cg_kwargs=kw)
+    assert torch.equal(r[0], r0)
+    # error behaviour of the reference
+    import pytest
+    with pytest.raises(ValueError, match="position to linearize"):
+        nb.wiener_filter_posterior(lh, key=1, model_is_linear=False)
+    with pytest.raises(NotImplementedError):
+        nb.wiener_filter_posterior(lh, tpos, key=1, signal_space=False)
+    with pytest.raises(TypeError):
+        nb.wiener_filter_posterior(object(), tpos, key=1)
+
+
+def check_minisanity(rt, name="g2d_16x16"):
+    """reduced_residual_stats / minisanity (minisanity.py:17-129) against the formulas evaluated with NumPy on the
+    oracle's residuals: mean = sum/size, reduced chi^2 = <x,x>/size per leaf, [mean, std] over the samples."""
+    c, g, lh, olh, lay = _setup(rt, name)
+    rng = np.random.default_rng(8)
+    pos = lay.pack({k: 0.3 * v for k, v in lay.random(rng).items()})
+    res = 0.1 * np.stack([lay.pack(lay.random(rng)) for _ in range(3)])
+    smp = nb.Samples(pos=rt.asarray(pos, torch.float64), samples=rt.asarray(res, torch.float64))
+    plan, layout = lh.signal.cf.plan, lh.layout
+    # prior residuals: per latent leaf
+    st, msg = nb.minisanity(smp, plan=plan, layout=layout)
+    pts = pos[None] + res
+    for k in lay.keys:
+        leaf = np.stack([lay.unpack(p)[k].reshape(-1) for p in pts])
+        m, rx = leaf.sum(1) / leaf.shape[1], (leaf * leaf).sum(1) / leaf.shape[1]
+        assert st[k].ndof == leaf.shape[1]
+        np.testing.assert_allclose(st[k].mean, [m.mean(), m.std()], rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(st[k].reduced_chisq, [rx.mean(), rx.std()], rtol=1e-10, atol=1e-14)
+    assert msg.count("reduced Chi²:") == len(lay.keys) and all(f"{k:24s}::" in msg for k in lay.keys)
+    # likelihood residuals through func
+    st_r, msg_r = nb.minisanity(smp, lh.normalized_residual, plan=plan)
+    r = np.stack([olh.normalized_residual(lay.unpack(p)).reshape(-1) for p in pts])
+    np.testing.assert_allclose(st_r.mean[0], (r.sum(1) / r.shape[1]).mean(), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(st_r.reduced_chisq, [((r * r).sum(1) / r.shape[1]).mean(), ((r * r).sum(1) / r.shape[1]).std()], rtol=1e-9)
+    assert st_r.ndof == r.shape[1] and msg_r.startswith("reduced Chi²:")
+    # a bare position: the sample std is zero (minisanity.py:52-53)
+    st0 = nb.reduced_residual_stats(rt.asarray(pos, torch.float64), plan=plan, layout=layout)
+    assert all(v.mean[1] == 0 and v.reduced_chisq[1] == 0 for v in st0.values())
+
+
 def check_nonlinear_update(rt, name="g2d_16x16"):
     lh, olh, lay, pos, tpos, white, (wd, wp), res, ores = check_draw_linear_residual(rt, name)
     mk = dict(xtol=1e-6, maxiter=4, cg_kwargs=dict(maxiter=40))
@@ -93,4 +162,11 @@ def check_optimize_kl(rt, tmpdir, name="g2d_16x16", comm=None):
     assert state2.nit == 2 and len(samples2) == nloc
     e2, _ = vi.kl_value_and_grad(samples2.pos, samples2.residuals)
     assert np.isfinite(e2)
+    # minisanity.txt (optimize_kl.py:803, 866-870): one report per iteration, appended on resume
+    import os
+    if vi.comm.rank == 0:
+        txt = open(os.path.join(str(tmpdir), "minisanity.txt")).read()
+        assert txt.count("OPTIMIZE_KL: Iteration") == 2 and "Iteration 0001" in txt and "Iteration 0002" in txt
+        assert "#(Nonlinear sampling steps)" in txt and "Likelihood residual(s):" in txt and "Prior residual(s):" in txt
+        assert txt.count("reduced Chi²:") == 2 * (1 + len(lh.layout.keys))
     return samples2, state2
