@@ -187,6 +187,12 @@ typedef struct nb200_cg_opts {
   int32_t raise_nonposdef;
   int32_t check_every; /* host polls the device status every this many iterations (>=1) */
   int32_t x0_is_zero;  /* x0 = None in the reference */
+  /* point estimates / constants (likelihood.py:399-499 LikelihoodPartial, evi.py:62-85): n_frozen half-open
+   * ranges [lo, hi) of the flat latent vector on which the operator acts as the identity, i.e. the solve runs
+   * in the subspace of the other ("liquid") entries.  j and x0 must be zero there; x stays zero there. */
+  int32_t n_frozen;
+  int32_t reserved;
+  const int64_t* frozen;   /* host array of 2*n_frozen entries, or NULL */
 } nb200_cg_opts;
 
 typedef struct nb200_cg_result {

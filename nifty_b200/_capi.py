@@ -40,7 +40,7 @@ class CgOpts(C.Structure):
     """``nb200_cg_opts``"""
     _fields_ = [("absdelta", f64), ("resnorm", f64), ("tol", f64), ("atol", f64), ("norm_ord", i32),
                 ("miniter", i32), ("maxiter", i32), ("raise_nonposdef", i32), ("check_every", i32),
-                ("x0_is_zero", i32)]
+                ("x0_is_zero", i32), ("n_frozen", i32), ("reserved", i32), ("frozen", C.POINTER(i64))]
 
 
 class CgResult(C.Structure):

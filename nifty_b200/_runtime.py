@@ -551,8 +551,10 @@ class Lin:
         return out
 
     def cg_solve(self, j, x0=None, other: Optional["Lin"] = None, *, absdelta=None, resnorm=None, norm_ord=None,
-                 tol=1e-5, atol=0.0, miniter=None, maxiter=None, raise_nonposdef=True, check_every=4):
-        """Solve (metric + 1) x = j on the device (``_cg`` semantics); returns (x, CgResult)."""
+                 tol=1e-5, atol=0.0, miniter=None, maxiter=None, raise_nonposdef=True, check_every=4, frozen=None):
+        """Solve (metric + 1) x = j on the device (``_cg`` semantics); returns (x, CgResult).
+        ``frozen``: ``[(lo, hi), ...]`` ranges of the flat latent vector held fixed (point estimates / constants):
+        the solve runs in the subspace of the other entries; ``j`` / ``x0`` must be zero on them."""
         o = CgOpts()
         self.rt.api.lib.nb200_cg_default_opts(C.byref(o))
         o.absdelta = -1.0 if absdelta is None else float(absdelta)
@@ -566,6 +568,11 @@ class Lin:
         o.raise_nonposdef = int(bool(raise_nonposdef))
         o.check_every = int(check_every)
         o.x0_is_zero = int(x0 is None)
+        fr = None
+        if frozen:
+            flat = [int(v) for r in frozen for v in r]
+            fr = (C.c_int64 * len(flat))(*flat)
+            o.n_frozen, o.frozen = len(flat) // 2, fr
         x = self._vec() if x0 is None else x0.clone()
         res = CgResult()
         self.rt.api.call("nb200_cg_solve", self._h, other._h if other is not None else None, self.rt.stream(),

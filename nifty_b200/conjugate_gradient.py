@@ -33,10 +33,20 @@ class CGResults(NamedTuple):
 class HamiltonianMetric:
     """``t -> lh.metric(pos, t) + t`` bound to a cached linearisation (evi.py:83-85 ``_ham_metric``).
 
-    ``other`` (a second linearisation) selects the geoVI operator of evi.py:167-172."""
+    ``other`` (a second linearisation) selects the geoVI operator of evi.py:167-172.  ``frozen``: ranges
+    ``[(lo, hi), ...]`` of the flat latent vector held fixed (``point_estimates`` / ``constants``,
+    likelihood.py:399-499): the operator of the frozen likelihood, written on full-length vectors -- outputs are
+    cleared on the frozen entries, inputs are expected to be zero there."""
 
-    def __init__(self, lin, other=None, likelihood=None):
+    def __init__(self, lin, other=None, likelihood=None, frozen=None):
         self.lin, self.other, self.likelihood = lin, other, likelihood
+        self.frozen = list(frozen) if frozen else None
+
+    def _clear(self, v):
+        if self.frozen:
+            for lo, hi in self.frozen:
+                v[lo:hi] = 0
+        return v
 
     @property
     def distributed(self):
@@ -44,9 +54,9 @@ class HamiltonianMetric:
 
     def __call__(self, t: torch.Tensor) -> torch.Tensor:
         if self.other is None:
-            return self.lin.metric(t, add_identity=True)
-        tm = self.other.metric_pair(self.lin, t, add_identity=True)
-        return self.lin.metric_pair(self.other, tm, add_identity=True)
+            return self._clear(self.lin.metric(t, add_identity=True))
+        tm = self._clear(self.other.metric_pair(self.lin, t, add_identity=True))
+        return self._clear(self.lin.metric_pair(self.other, tm, add_identity=True))
 
 
 def _norm(v: torch.Tensor, ord) -> float:
@@ -74,7 +84,7 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
     elif isinstance(mat, HamiltonianMetric):
         x, res = mat.lin.cg_solve(j, x0, other=mat.other, absdelta=absdelta, resnorm=resnorm, norm_ord=norm_ord, tol=tol,
                                   atol=atol, miniter=miniter, maxiter=maxiter, raise_nonposdef=_raise_nonposdef,
-                                  check_every=check_every)
+                                  check_every=check_every, frozen=mat.frozen)
         nm = "CG" if name is None else name
         if res.error == 1:
             raise ValueError(f"{nm}: zero curvature")

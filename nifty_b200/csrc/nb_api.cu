@@ -90,9 +90,22 @@ int cg_solve(Lin<T>* lin, Lin<T>* lin_b, stream_t st, const T* j, T* x, const nb
   const long maxiter_fallback = 20 * L;
   long miniter = o.miniter >= 0 ? o.miniter : std::min<long>(6, o.maxiter >= 0 ? o.maxiter : maxiter_fallback);
   long maxiter = o.maxiter >= 0 ? o.maxiter : std::max<long>(std::min<long>(200, maxiter_fallback), miniter);
+  for (int k = 0; k < o.n_frozen; ++k) {
+    if (!o.frozen || o.frozen[2 * k] < 0 || o.frozen[2 * k + 1] > L || o.frozen[2 * k] > o.frozen[2 * k + 1])
+      return fail("nb200_cg_solve: invalid frozen range");
+  }
+  // frozen entries: the operator output is cleared there after every application, so that (with j and x0 zero
+  // on them) every Krylov vector stays in the liquid subspace -- the solve of the restricted operator
+  auto clear_frozen = [&](T* v) {
+    for (int k = 0; k < o.n_frozen; ++k)
+      if (o.frozen[2 * k + 1] > o.frozen[2 * k]) dev_zero(v + o.frozen[2 * k], (size_t)(o.frozen[2 * k + 1] - o.frozen[2 * k]) * sizeof(T), st);
+  };
   auto op = [&](const T* t, T* out) {
-    if (!lin_b) lin->metric(st, lin, t, out, true);
-    else { lin_b->metric(st, lin, t, w.tm.p, true); lin->metric(st, lin_b, w.tm.p, out, true); }
+    if (!lin_b) { lin->metric(st, lin, t, out, true); clear_frozen(out); }
+    else {
+      lin_b->metric(st, lin, t, w.tm.p, true); clear_frozen(w.tm.p);
+      lin->metric(st, lin_b, w.tm.p, out, true); clear_frozen(out);
+    }
   };
   CgParams<T> p;
   std::memset(&p, 0, sizeof(p));
@@ -441,7 +454,7 @@ int nb200_normalized_residual(nb200_lin* lin, void* stream, void* out_pos) {
 
 void nb200_cg_default_opts(nb200_cg_opts* o) {
   o->absdelta = -1; o->resnorm = -1; o->tol = 1e-5; o->atol = 0; o->norm_ord = 2; o->miniter = -1; o->maxiter = -1;
-  o->raise_nonposdef = 1; o->check_every = 4; o->x0_is_zero = 0;
+  o->raise_nonposdef = 1; o->check_every = 4; o->x0_is_zero = 0; o->n_frozen = 0; o->reserved = 0; o->frozen = nullptr;
 }
 int nb200_cg_solve(nb200_lin* lin, nb200_lin* lin_b, void* stream, const void* j, void* x, const nb200_cg_opts* opts,
                    nb200_cg_result* result_host) {

@@ -125,20 +125,25 @@ def sample_likelihood(likelihood: LikelihoodWithModel, primals, key, _white_data
 def draw_linear_residual(likelihood: LikelihoodWithModel, pos, key, *, from_inverse: bool = True, point_estimates=(),
                          cg=conjugate_gradient.cg, cg_name=None, cg_kwargs: Optional[dict] = None,
                          _raise_nonposdef: bool = False, _white=None):
-    """One MGVI residual sample at ``pos`` (evi.py:88-150); returns ``(residual, info)``."""
-    if point_estimates:
-        raise NotImplementedError("point_estimates are not supported on the B200 path yet")
+    """One MGVI residual sample at ``pos`` (evi.py:88-150); returns ``(residual, info)``.
+
+    ``point_estimates``: leaves frozen at ``pos`` (:109-111, 149): the draw happens in the space of the other leaves
+    and the returned residual is zero on the frozen ones (``_process_point_estimate(..., insert=True)``)."""
+    frozen = likelihood.frozen_ranges(point_estimates)
     pos = likelihood.signal.as_flat(pos)
     lin, _ = likelihood.lin_at(pos)
     k_nll, k_prr = random_split(key, 2)
     w_data, w_prior = (None, None) if _white is None else _white
     nll_smpl = sample_likelihood(likelihood, pos, k_nll, _white_data=w_data)
-    prr_smpl = random_like(k_prr, likelihood) if w_prior is None else likelihood.signal.as_flat(w_prior)
+    prr_smpl = random_like(k_prr, likelihood) if w_prior is None else likelihood.signal.as_flat(w_prior).clone()
+    if frozen:
+        likelihood.clear_frozen(nll_smpl, frozen)
+        likelihood.clear_frozen(prr_smpl, frozen)
     smpl = nll_smpl + prr_smpl
     info = 0
     if from_inverse:
-        smpl, info = cg(HamiltonianMetric(lin, likelihood=likelihood), smpl, x0=prr_smpl, name=cg_name, _raise_nonposdef=_raise_nonposdef,
-                        **(cg_kwargs or {}))
+        smpl, info = cg(HamiltonianMetric(lin, likelihood=likelihood, frozen=frozen), smpl, x0=prr_smpl, name=cg_name,
+                        _raise_nonposdef=_raise_nonposdef, **(cg_kwargs or {}))
         if info is not None and info < 0:
             raise ValueError("conjugate gradient failed")
     return smpl, info
@@ -148,12 +153,16 @@ def draw_linear_residual(likelihood: LikelihoodWithModel, pos, key, *, from_inve
 def nonlinearly_update_residual(likelihood: LikelihoodWithModel, pos, residual_sample, metric_sample_key,
                                 metric_sample_sign=1.0, *, point_estimates=(), minimize=_newton_cg,
                                 minimize_kwargs: Optional[dict] = None, _raise_notconverged: bool = False, _white=None):
-    """geoVI update of one residual sample (evi.py:181-255); returns ``(residual, OptimizeResults|None)``."""
-    if point_estimates:
-        raise NotImplementedError("point_estimates are not supported on the B200 path yet")
+    """geoVI update of one residual sample (evi.py:181-255); returns ``(residual, OptimizeResults|None)``.
+
+    ``point_estimates``: the update runs in the space of the non-frozen leaves (:153-178 on ``likelihood.freeze``);
+    on full-length vectors this means the frozen entries of the sample stay at ``pos`` and every cotangent /
+    operator output is cleared there."""
+    frozen = likelihood.frozen_ranges(point_estimates)
+    clr = (lambda v: likelihood.clear_frozen(v, frozen)) if frozen else (lambda v: v)
     e = likelihood.signal.as_flat(pos)
-    sample = e + likelihood.signal.as_flat(residual_sample)
-    ms, _ = draw_linear_residual(likelihood, e, metric_sample_key, from_inverse=False, _white=_white)
+    sample = e + clr(likelihood.signal.as_flat(residual_sample).clone())
+    ms, _ = draw_linear_residual(likelihood, e, metric_sample_key, from_inverse=False, point_estimates=point_estimates, _white=_white)
     ms = metric_sample_sign * ms
     mk = dict(minimize_kwargs or {})
     if isinstance(mk.get("maxiter", None), int) and mk["maxiter"] == 0:
@@ -166,14 +175,14 @@ def nonlinearly_update_residual(likelihood: LikelihoodWithModel, pos, residual_s
     def residual_vg(x):  # evi.py:153-164
         lin_x.update(x)
         t = lin_x.transformation() - trafo_at_p
-        g = x - e + lin_e.lsm(t, scaled=True)
+        g = x - e + clr(lin_e.lsm(t, scaled=True))
         r = ms - g
         val = 0.5 * float(torch.dot(r, r))
-        ngrad = r + lin_x.lsm(lin_e.rsm(r, scaled=True), scaled=True)
+        ngrad = r + clr(lin_x.lsm(lin_e.rsm(r, scaled=True), scaled=True))
         return val, -ngrad
 
     def metric_at(x):  # evi.py:167-172 at the point of the last residual_vg evaluation (== x)
-        return HamiltonianMetric(lin_x, other=lin_e)
+        return HamiltonianMetric(lin_x, other=lin_e, frozen=frozen)
 
     def sampnorm(natgrad):  # evi.py:175-178
         fpp = lin_e.rsm(natgrad, scaled=True)
@@ -193,6 +202,8 @@ def nonlinearly_update_residual(likelihood: LikelihoodWithModel, pos, residual_s
             state["x"] = x
         return metric_at(x)
 
+    if frozen:       # xtol * size counts the liquid entries only (the reference minimises over the liquid vector)
+        mk.setdefault("_size", likelihood.layout.size - sum(hi - lo for lo, hi in frozen))
     opt = minimize(None, x0=sample, fun_and_grad=fg, hessp_at=op_at, custom_gradnorm=sampnorm, **mk)
     if _raise_notconverged and (opt.status is None or opt.status < 0):
         raise ValueError("S: failed to invert map")

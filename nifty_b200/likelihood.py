@@ -161,6 +161,40 @@ class LikelihoodWithModel:
     def new_lin(self) -> Lin:
         return Lin(self.handle)
 
+    # -- point estimates / constants (likelihood.py:399-499, _parse_point_estimates :57-92) ----------------------
+    def frozen_ranges(self, point_estimates):
+        """Flat-vector ranges ``[(lo, hi), ...]`` of the leaves named in ``point_estimates`` (a collection of keys of
+        the latent domain, or a dict ``{key: bool}``); merged and sorted.  The reference freezes those leaves at their
+        current value (``Likelihood.freeze``) and runs every solve in the space of the remaining ones; here the same
+        solves run on full-length vectors whose frozen entries are kept at zero / at the expansion point."""
+        if not point_estimates:
+            return []
+        if self._plan.dist:
+            raise NotImplementedError("point_estimates / constants on slab-decomposed fields are not supported yet")
+        if isinstance(point_estimates, dict):
+            keys = [k for k, v in point_estimates.items() if v]
+        elif isinstance(point_estimates, str):
+            keys = [point_estimates]
+        else:
+            keys = list(point_estimates)
+        unknown = [k for k in keys if k not in self.layout.offsets]
+        if unknown:
+            raise ValueError(f"point_estimates {unknown!r} are not leaves of the latent domain {self.layout.keys!r}")
+        rs = sorted((self.layout.offsets[k], self.layout.offsets[k] + self.layout.numel(k)) for k in set(keys))
+        merged = []
+        for lo, hi in rs:
+            if merged and merged[-1][1] == lo:
+                merged[-1] = (merged[-1][0], hi)
+            else:
+                merged.append((lo, hi))
+        return merged
+
+    @staticmethod
+    def clear_frozen(v: torch.Tensor, ranges):
+        for lo, hi in ranges:
+            v[..., lo:hi] = 0
+        return v
+
     # -- vector algebra on latent vectors (tree_math.vdot / norm); slab-decomposed: xi block summed over ranks ------
     @property
     def _plan(self):

@@ -27,7 +27,7 @@ def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reductio
                norm_ord=None, xtol=1e-5, fun_and_grad: Optional[Callable] = None, hessp: Optional[Callable] = None,
                cg=_cg, name=None, time_threshold=None, cg_kwargs=None, custom_gradnorm: Optional[Callable] = None,
                hessp_at: Optional[Callable] = None, vdot: Optional[Callable] = None,
-               vnorm: Optional[Callable] = None) -> OptimizeResults:
+               vnorm: Optional[Callable] = None, _size: Optional[int] = None) -> OptimizeResults:
     """``hessp(pos, v)`` as in the reference; ``hessp_at(pos)`` may instead return an operator object
     (e.g. a :class:`~nifty_b200.conjugate_gradient.HamiltonianMetric`) so that the inner CG runs on the device."""
     norm_ord = 1 if norm_ord is None else norm_ord
@@ -36,7 +36,7 @@ def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reductio
     miniter = 0 if miniter is None else miniter
     maxiter = 200 if maxiter is None else maxiter
     pos = x0.clone()
-    xtol = xtol * pos.numel()
+    xtol = xtol * (pos.numel() if _size is None else _size)      # _size: number of non-frozen entries (point estimates)
     cg_kwargs = {} if cg_kwargs is None else dict(cg_kwargs)
     cg_name = cg_kwargs.pop("name", None)
     gradnorm = (lambda v: _nrm(v, norm_ord)) if custom_gradnorm is None else custom_gradnorm

@@ -219,21 +219,28 @@ class OptimizeVI:
         acc = self.comm.allreduce_sum(acc)
         return (acc[1:] / float(acc[0])).to(lh.dtype)
 
-    def kl_minimize(self, samples: Samples, minimize: Callable = _newton_cg, minimize_kwargs=None, **kwargs) -> OptimizeResults:
-        """optimize_kl.py:540-591."""
+    def kl_minimize(self, samples: Samples, minimize: Callable = _newton_cg, minimize_kwargs=None, constants=(), **kwargs) -> OptimizeResults:
+        """optimize_kl.py:540-591.  ``constants``: leaves held at their current value during the minimisation (:553-573):
+        the value / gradient / metric are evaluated at full positions, the gradient and the metric output are restricted
+        to the other leaves (cleared on the constant ones), so the Newton steps never move them."""
         res = samples.residuals
         state = {"x": None}
+        frozen = self.likelihood.frozen_ranges(constants)
+        clr = (lambda v: self.likelihood.clear_frozen(v, frozen)) if frozen else (lambda v: v)
 
         def fg(x):
             state["x"] = x
-            return self.kl_value_and_grad(x, res)
+            val, grad = self.kl_value_and_grad(x, res)
+            return val, clr(grad)
 
         def hessp(x, t):
             if state["x"] is None or state["x"].data_ptr() != x.data_ptr():
                 fg(x)
-            return self.kl_metric(t)
+            return clr(self.kl_metric(t))
 
         kw = dict(minimize_kwargs or {})
+        if frozen:
+            kw.setdefault("_size", self.likelihood.layout.size - sum(hi - lo for lo, hi in frozen))
         if self.likelihood.signal.cf.plan.dist:      # slab-decomposed latent vectors: all-reduced reductions
             kw.setdefault("vdot", self.likelihood.vdot)
             kw.setdefault("vnorm", self.likelihood.vnorm)
@@ -242,8 +249,8 @@ class OptimizeVI:
     # -- driver -------------------------------------------------------------------------------------------
     def init_state(self, key, *, n_samples, draw_linear_kwargs=None, nonlinearly_update_kwargs=None, kl_kwargs=None,
                    sample_mode="nonlinear_resample", point_estimates=(), constants=()) -> OptimizeVIState:
-        if constants or point_estimates:
-            raise NotImplementedError("constants / point_estimates are not supported on the B200 path yet")
+        self.likelihood.frozen_ranges(point_estimates)      # validates the keys (and the unsupported slab case) early
+        self.likelihood.frozen_ranges(constants)
         config = dict(n_samples=n_samples, sample_mode=sample_mode, point_estimates=point_estimates, constants=constants,
                       draw_linear_kwargs=draw_linear_kwargs or dict(cg_name="SL", cg_kwargs=dict()),
                       nonlinearly_update_kwargs=nonlinearly_update_kwargs or dict(minimize_kwargs=dict(name="SN", cg_kwargs=dict(name="SNCG"))),
@@ -258,8 +265,9 @@ class OptimizeVI:
         kw = {k: _getitem_at_nit(cfg, k, nit) for k in ("n_samples", "sample_mode", "point_estimates", "draw_linear_kwargs",
                                                       "nonlinearly_update_kwargs", "kl_kwargs")}
         kl_kwargs = dict(kw.pop("kl_kwargs"))
+        constants = _getitem_at_nit(cfg, "constants", nit)
         samples, st_smpls = self.draw_samples(samples, key=sk, **kw)
-        kl_opt = self.kl_minimize(samples, **kl_kwargs)
+        kl_opt = self.kl_minimize(samples, constants=constants, **kl_kwargs)
         samples = samples.at(kl_opt.x)
         state = state._replace(nit=nit, key=key, sample_state=st_smpls, minimization_state=kl_opt._replace(x=None, jac=None))
         return samples, state

@@ -45,6 +45,7 @@ from .vi import (  # noqa: F401
     nonlinearly_update_residual,
     kl_value_and_grad,
     kl_metric,
+    kl_minimize,
     tree_size,
     Layout,
 )

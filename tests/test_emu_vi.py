@@ -27,6 +27,12 @@ def test_minisanity(rt):
     vc.check_minisanity(rt, "g3d_8x8x8")
 
 
+def test_point_estimates_and_constants(rt):
+    vc.check_point_estimates(rt)
+    vc.check_point_estimates(rt, frozen=("cfxi",))
+    vc.check_point_estimates(rt, "g3d_8x8x8", frozen=("cfzeromode", "cfax1loglogavgslope", "cfax1flexibility"))
+
+
 def test_nonlinear_update(rt):
     vc.check_nonlinear_update(rt)
 

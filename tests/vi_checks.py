@@ -141,6 +141,70 @@ def check_kl(rt, name="g2d_16x16"):
     assert abs(v0 - ov0) <= 1e-11 * abs(ov0) and rel_err(t2n(g0), lay.pack(og0)) < 1e-10
 
 
+def check_point_estimates(rt, name="g2d_16x16", frozen=("cfax1fluctuations", "cfax1spectrum")):
+    """point_estimates / constants (likelihood.py:399-499 LikelihoodPartial + partial_insert_and_remove :119-177;
+    evi.py:62-85, 109-111, 149, 224-254; optimize_kl.py:553-590).  The oracle follows the reference: every solve runs
+    on vectors with the frozen leaves REMOVED; the product keeps full-length vectors and clears the frozen entries
+    (device CG: nb200_cg_opts.frozen) -- two formulations of the same restricted operators."""
+    c, g, lh, olh, lay = _setup(rt, name)
+    rng = np.random.default_rng(77)
+    pos = {k: 0.3 * v for k, v in lay.random(rng).items()}
+    wd, wp = rng.standard_normal(c["shape"]), lay.random(rng)
+    tpos = rt.asarray(lay.pack(pos), torch.float64)
+    white = (rt.asarray(wd, torch.float64), rt.asarray(lay.pack(wp), torch.float64))
+    fr = lh.frozen_ranges(frozen)
+    assert sum(hi - lo for lo, hi in fr) == sum(int(np.prod(lay.shapes[k])) for k in frozen)
+    # MGVI draw
+    ores, oinfo, _ = oracle.draw_linear_residual(olh, pos, wd, wp, cg_kwargs=CG_KW, point_estimates=frozen)
+    res, info = nb.draw_linear_residual(lh, tpos, 0, cg_kwargs=CG_KW, point_estimates=frozen, _white=white)
+    assert info == oinfo
+    assert rel_err(t2n(res), lay.pack(ores)) < 1e-9
+    assert all(float(res[lo:hi].abs().max()) == 0.0 for lo, hi in fr)
+    full, _ = nb.draw_linear_residual(lh, tpos, 0, cg_kwargs=CG_KW, _white=white)
+    assert rel_err(t2n(res), t2n(full)) > 1e-3          # freezing changes the draw
+    # geoVI update
+    mk = dict(xtol=1e-6, maxiter=3, cg_kwargs=dict(maxiter=40))
+    for sign in (1.0, -1.0):
+        onew, oopt = oracle.nonlinearly_update_residual(olh, pos, {k: sign * v for k, v in ores.items()}, wd, wp, sign,
+                                                        minimize_kwargs=mk, point_estimates=frozen)
+        new, opt = nb.nonlinearly_update_residual(lh, tpos, sign * res, 0, sign, minimize_kwargs=mk, point_estimates=frozen,
+                                                  _white=white)
+        assert opt.nit == oopt.nit and opt.status == oopt.status
+        assert rel_err(t2n(new), lay.pack(onew)) < 1e-6
+        assert all(float(new[lo:hi].abs().max()) == 0.0 for lo, hi in fr)
+    # KL minimisation with constants: the constant leaves do not move, the others follow the oracle
+    residuals = [{k: 0.1 * v for k, v in lay.random(rng).items()} for _ in range(2)]
+    residuals = [r for pair in ((r, {k: -v for k, v in r.items()}) for r in residuals) for r in pair]
+    kmk = dict(xtol=1e-8, maxiter=3, cg_kwargs=dict(maxiter=30))
+    opos, oopt = oracle.kl_minimize(olh, pos, residuals, constants=frozen, minimize_kwargs=kmk)
+    vi = nb.OptimizeVI(lh, 1)
+    smp = nb.Samples(pos=tpos, samples=rt.asarray(np.stack([lay.pack(r) for r in residuals]), torch.float64))
+    kopt = vi.kl_minimize(smp, minimize_kwargs=kmk, constants=frozen)
+    assert kopt.nit == oopt.nit
+    assert rel_err(t2n(kopt.x), lay.pack(opos)) < 1e-7
+    assert all(torch.equal(kopt.x[lo:hi], tpos[lo:hi]) for lo, hi in fr)
+    # unknown keys are an error, as in the reference's _parse_point_estimates
+    import pytest
+    with pytest.raises(ValueError, match="not leaves"):
+        nb.draw_linear_residual(lh, tpos, 0, point_estimates=("nope",))
+    # end to end: one VI iteration; point-estimated leaves carry no sample spread, constant leaves do not move
+    pe, const = (frozen[0],), (frozen[-1],)
+    smp, st = nb.optimize_kl(lh, tpos.clone(), key=3, n_total_iterations=1, n_samples=2, point_estimates=pe, constants=const,
+                             draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=40)),
+                             nonlinearly_update_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=20))),
+                             kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=20))),
+                             sample_mode="nonlinear_resample")
+    assert st.nit == 1 and len(smp) == 4
+    for lo, hi in lh.frozen_ranges(pe):
+        assert float(smp.residuals[:, lo:hi].abs().max()) == 0.0
+    for lo, hi in lh.frozen_ranges(const):
+        assert torch.equal(smp.pos[lo:hi], tpos[lo:hi])
+    moved = torch.ones(lay.size, dtype=torch.bool)
+    for lo, hi in lh.frozen_ranges(const):
+        moved[lo:hi] = False
+    assert float((smp.pos - tpos)[moved].abs().max()) > 0
+
+
 def check_optimize_kl(rt, tmpdir, name="g2d_16x16", comm=None):
     """Two VI iterations: the KL decreases, samples are interleaved antithetic pairs, resume continues."""
     c, g, lh, olh, lay = _setup(rt, name)
