@@ -157,6 +157,9 @@ int nb200_lin_amplitude(nb200_lin* lin, void* stream, void* amp_out);
 /* signal(pos) and correlated field in natural order (Model.__call__, correlated_field.py:909-912) */
 int nb200_lin_signal(nb200_lin* lin, void* stream, void* out);
 int nb200_cf_forward(nb200_model* model, void* stream, const void* pos, void* field_out);
+/* CorrelatedFieldMaker.amplitude (correlated_field.py:824-838): amp_out[K] = [azm V, amp_1, ..., amp_{K-1}] at pos,
+ * i.e. the O(K) amplitude chain alone (power_spectrum = amp^2, normalized amplitudes = amp / azm; :807-845) */
+int nb200_cf_amplitude(nb200_model* model, void* stream, const void* pos, void* amp_out);
 
 /* LikelihoodWithModel.metric (likelihood.py:613-621) fused: out = J^T M J t (+ t if add_identity,
  * i.e. _ham_metric evi.py:83-85).  Leaves <t, out> in a device scalar for conjugate gradient. */

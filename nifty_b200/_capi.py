@@ -84,6 +84,7 @@ SIGNATURES = {
     "nb200_lin_amplitude": (C.c_int, [vp, vp, vp]),
     "nb200_lin_signal": (C.c_int, [vp, vp, vp]),
     "nb200_cf_forward": (C.c_int, [vp, vp, vp, vp]),
+    "nb200_cf_amplitude": (C.c_int, [vp, vp, vp, vp]),
     "nb200_metric": (C.c_int, [vp, vp, vp, vp, C.c_int]),
     "nb200_metric_pair": (C.c_int, [vp, vp, vp, vp, vp, C.c_int]),
     "nb200_rsm": (C.c_int, [vp, vp, vp, vp, C.c_int]),

@@ -398,6 +398,12 @@ class ModelHandle:
         self.rt.api.call("nb200_cf_forward", self._h, self.rt.stream(), self.rt.ptr(pos), self.rt.ptr(out))
         return out
 
+    def cf_amplitude(self, pos: torch.Tensor) -> torch.Tensor:
+        """``[azm V, amp_1, ..., amp_{K-1}]`` at ``pos`` (``nb200_cf_amplitude``); replicated on slab-decomposed plans."""
+        out = self.rt.empty((self.plan.K,), self.plan.dtype)
+        self.rt.api.call("nb200_cf_amplitude", self._h, self.rt.stream(), self.rt.ptr(pos), self.rt.ptr(out))
+        return out
+
 
 class Lin:
     """``nb200_lin``: cached linearisation of a model at one latent position."""

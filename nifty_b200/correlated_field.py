@@ -5,13 +5,14 @@ leaf names (``<prefix>xi``, ``<prefix>zeromode``, ``<prefix><sub>fluctuations`` 
 behaviour for malformed priors.  ``finalize()`` returns a :class:`CorrelatedField` whose forward /
 JVP / VJP run in the sm_100a kernels of libniftyb200.so; nothing is evaluated in Python.
 
-Scope of this round: one Fourier sub-grid (1-3 axes, power-of-two extents), non-parametric
-amplitude (``kind`` "amplitude" or "power").  Matern amplitudes, multiple sub-grids and
-``harmonic_type="spherical"`` raise ``NotImplementedError`` ("next").
+Scope: one Fourier sub-grid (1-3 axes, power-of-two extents), non-parametric (``kind`` "amplitude" or "power")
+or Matern amplitude.  Multiple sub-grids and ``harmonic_type="spherical"`` raise ``NotImplementedError``
+("next").
 """
 
 from __future__ import annotations
 
+from collections import namedtuple
 from typing import Optional
 
 import numpy as np
@@ -21,6 +22,11 @@ from ._capi import ModelDesc
 from ._runtime import Lin, ModelHandle, Plan, Runtime, default_runtime
 from .prior import LogNormalPrior, NormalPrior, _as_prior
 from .tree import Layout
+
+
+RegularCartesianGrid = namedtuple("RegularCartesianGrid", ("shape", "total_volume", "distances", "harmonic_grid"), defaults=(None,))
+RegularFourierGrid = namedtuple("RegularFourierGrid", ("shape", "power_distributor", "mode_multiplicity", "mode_lengths",
+                                                       "relative_log_mode_lengths", "log_volume"))
 
 
 class CorrelatedField:
@@ -80,6 +86,43 @@ class CorrelatedField:
 
     def __call__(self, pos) -> torch.Tensor:
         return self.handle().cf_forward(self.as_flat(pos))
+
+    # -- amplitude spectra (correlated_field.py:807-845) ----------------------------------------------------------
+    def _azm_value(self, flat: torch.Tensor) -> float:
+        a, b = self._desc_fields["zeromode_a"], self._desc_fields["zeromode_b"]
+        return float(torch.exp(a + b * flat[self.layout.offsets[self.prefix + "zeromode"]].to(torch.float64)))
+
+    def amplitude(self, pos) -> torch.Tensor:
+        """``CorrelatedFieldMaker.amplitude`` (:824-838): the un-normalised amplitude with the zero mode scaled by the
+        amplitude of the total offset, ``[azm V, amp_1, ..., amp_{K-1}]`` -- exactly the table the device kernels gather
+        from (evaluated by the O(K) amplitude chain on the device)."""
+        return self.handle().cf_amplitude(self.as_flat(pos))
+
+    def power_spectrum(self, pos) -> torch.Tensor:
+        """``CorrelatedFieldMaker.power_spectrum`` (:840-845): ``amplitude(p) ** 2``."""
+        return self.amplitude(pos) ** 2
+
+    @property
+    def normalized_amplitudes(self):
+        """``cf.normalized_amplitudes`` (:807-821, 918): one callable per sub-grid, ``amp(p).at[1:] / azm(p)``, ``[0] = V``."""
+        def normed_amplitude(pos):
+            flat = self.as_flat(pos)
+            amp = self.amplitude(flat).clone()
+            z = self._azm_value(flat)
+            amp /= z
+            return amp
+        return (normed_amplitude,)
+
+    @property
+    def target_grids(self):
+        """``cf.target_grids`` (:919): the position-space grid with its harmonic partner (tables built by the plan with the
+        reference's arithmetic, :134-176, 228-265)."""
+        pl = self.plan
+        hg = RegularFourierGrid(shape=tuple(pl.shape), power_distributor=pl.power_distributor, mode_multiplicity=pl.mode_multiplicity,
+                                mode_lengths=pl.mode_lengths, relative_log_mode_lengths=pl.relative_log_mode_lengths,
+                                log_volume=pl.log_volume)
+        return (RegularCartesianGrid(shape=tuple(pl.shape), total_volume=pl.total_volume, distances=tuple(pl.distances),
+                                     harmonic_grid=hg),)
 
 
 class CorrelatedFieldMaker:
@@ -142,7 +185,28 @@ class CorrelatedFieldMaker:
         self._fluct.append(dict(shape=shape, distances=distances, matern=True, scl=scl, ctf=ctf, slp=slp,
                                 renorm=bool(renormalize_amplitude), prefix=prefix, kind=kind))
 
+    # -- amplitude accessors of the maker (correlated_field.py:800-845); available after finalize() ----------------
+    def _finalized(self) -> "CorrelatedField":
+        if getattr(self, "_cf", None) is None:
+            raise ValueError("call finalize() first: the amplitude chain lives in the finalised device model")
+        return self._cf
+
+    @property
+    def amplitude(self):
+        return self._finalized().amplitude
+
+    @property
+    def power_spectrum(self):
+        return self._finalized().power_spectrum
+
+    def get_normalized_amplitudes(self):
+        return self._finalized().normalized_amplitudes
+
     def finalize(self) -> CorrelatedField:
+        self._cf = self._finalize()
+        return self._cf
+
+    def _finalize(self) -> CorrelatedField:
         """correlated_field.py:850-920: builds the grid tables (on the C side) and the model."""
         if self._azm is None:
             raise ValueError("set_amplitude_total_offset must be called before finalize")

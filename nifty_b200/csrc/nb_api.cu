@@ -412,6 +412,19 @@ int nb200_cf_forward(nb200_model* model, void* stream, const void* pos, void* fi
   return 0;
   NB_CATCH
 }
+int nb200_cf_amplitude(nb200_model* model, void* stream, const void* pos, void* amp_out) {
+  NB_TRY
+  NB_DISPATCH(model->dtype, TT, {
+    Model<TT>& m = *static_cast<Model<TT>*>(model->impl);
+    Lin<TT>& l = *m.scratch_lin;
+    stream_t st = (stream_t)stream;
+    d2d(l.pos.p, pos, (size_t)m.am.L * sizeof(TT), st);
+    l.amp_forward(st);
+    d2d(amp_out, l.amp.p, (size_t)m.am.K * sizeof(TT), st);
+  })
+  return 0;
+  NB_CATCH
+}
 int nb200_metric(nb200_lin* lin, void* stream, const void* t, void* out, int add_identity) {
   NB_TRY
   NB_DISPATCH(lin->dtype, TT, { Lin<TT>* l = static_cast<Lin<TT>*>(lin->impl); l->metric((stream_t)stream, l, (const TT*)t, (TT*)out, add_identity != 0); })

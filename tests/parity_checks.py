@@ -6,6 +6,7 @@ Tolerances: float64 1e-10 relative (north star), float32 1e-5, relative to the l
 the compared quantity (leaves that are structurally ~0 only carry cancellation noise).
 """
 import numpy as np
+import pytest
 import torch
 
 import nifty_b200 as nb
@@ -112,6 +113,36 @@ def check_golden(rt, name, dtype=torch.float64):
     lin, _ = lh.lin_at(pos)
     assert rel_err(t2n(lin.rsm(lh.signal.as_flat(tan), scaled=False)), g["field_jvp"]) < tol
     assert tree_err(lh.layout.unpack(lin.lsm(torch.as_tensor(g["cot"]), scaled=False)), g["field_vjp"]) < tol
+
+
+def check_model_surface(rt, name="g2d_16x16"):
+    """The `jft.Model` surface of the finalised field (correlated_field.py:807-845, 913-920): amplitude / power spectrum /
+    normalized amplitudes against the oracle, `target_grids` against the oracle's grid tables, `domain` / `target` / `init`."""
+    from golden_util import build_oracle
+    c, g = CASES[name], load(name)
+    cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+    cfm.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+    with pytest.raises(ValueError, match="finalize"):
+        cfm.amplitude
+    cfm.add_fluctuations(c["shape"], c["distances"], c["fluctuations"], c["loglogavgslope"], c["flexibility"], c["asperity"],
+                         prefix="ax1", non_parametric_kind="power")
+    cf = cfm.finalize()
+    ocf = build_oracle(c)
+    pos = {k: torch.as_tensor(v) for k, v in g["pos"].items()}
+    assert rel_err(t2n(cfm.amplitude(pos)), ocf.amplitude(g["pos"])) < 1e-12
+    assert rel_err(t2n(cfm.power_spectrum(pos)), ocf.amplitude(g["pos"]) ** 2) < 1e-12
+    (na,), (ona,) = cfm.get_normalized_amplitudes(), ocf.normalized_amplitudes(g["pos"])
+    assert cf.normalized_amplitudes[0] is not None and rel_err(t2n(na(pos)), ona) < 1e-12
+    (tg,), og = cf.target_grids, ocf.grids[0]
+    assert tuple(tg.shape) == tuple(c["shape"]) and abs(tg.total_volume - og.total_volume) <= 1e-14 * og.total_volume
+    hg, ohg = tg.harmonic_grid, og          # the oracle keeps both grids in one record
+    assert np.array_equal(hg.power_distributor, ohg.power_distributor) and np.array_equal(hg.mode_multiplicity, ohg.mode_multiplicity)
+    np.testing.assert_allclose(hg.mode_lengths, ohg.mode_lengths, rtol=0, atol=0)
+    np.testing.assert_allclose(hg.relative_log_mode_lengths, ohg.relative_log_mode_lengths, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(hg.log_volume, ohg.log_volume, rtol=0, atol=1e-14)
+    assert cf.domain == {k: tuple(np.shape(v)) for k, v in g["pos"].items()} and tuple(cf.target) == tuple(c["shape"])
+    p0 = cf.init(3)
+    assert sorted(p0) == sorted(cf.domain) and all(tuple(p0[k].shape) == cf.domain[k] for k in p0)
 
 
 def check_kind_and_scaling(rt, name="g2d_16x16", kind="amplitude", scaling=(3.0, 1.0)):

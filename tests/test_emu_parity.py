@@ -49,6 +49,11 @@ def test_metric_properties(rt):
     pc.check_metric_properties(rt, (8, 16, 8), 0.3, lh_kind="poisson")
 
 
+def test_model_surface(rt):
+    pc.check_model_surface(rt)
+    pc.check_model_surface(rt, "g3d_8x8x8")
+
+
 def test_cg(rt):
     pc.check_cg(rt)
 

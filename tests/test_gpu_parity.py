@@ -47,6 +47,11 @@ def test_kind_scaling_convention(rt, kind):
     pc.check_kind_and_scaling(rt, kind=kind)
 
 
+def test_model_surface(rt):
+    pc.check_model_surface(rt)
+    pc.check_model_surface(rt, "g3d_8x8x8")
+
+
 def test_cg(rt):
     pc.check_cg(rt)
 
