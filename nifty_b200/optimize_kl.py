@@ -101,10 +101,19 @@ class OptimizeVI:
     """State-less MGVI / geoVI driver (optimize_kl.py:173-741)."""
 
     def __init__(self, likelihood: LikelihoodWithModel, n_total_iterations: int, *, comm=None,
+                 jit=True, linear_minimizer_jit=True, nonlinear_minimizer_jit=False, kl_map=None, residual_map="lmap",
+                 kl_reduce=None, mirror_samples=True, devices=None,
                  _kl_value_and_grad: Optional[Callable] = None, _kl_metric: Optional[Callable] = None,
                  _draw_linear_residual: Callable = draw_linear_residual,
                  _nonlinearly_update_residual: Callable = nonlinearly_update_residual,
                  _get_status_message: Optional[Callable] = None):
+        # jit / *_map / kl_reduce select how JAX traces and batches the per-sample work (optimize_kl.py:228-246); here every
+        # sample point is a sequence of device launches and the reduction over samples is the mean, so they are accepted
+        # for call compatibility only.  The two options that would change results are refused.
+        if not mirror_samples:
+            raise NotImplementedError("mirror_samples=False is not supported on the B200 path")
+        if devices is not None:
+            raise NotImplementedError("`devices` is a JAX mesh; pass a torch.distributed group as `comm` (one process per GPU)")
         self.likelihood = likelihood
         if _get_status_message is None:        # optimize_kl.py:376-389
             plan = likelihood.signal.cf.plan
@@ -282,15 +291,21 @@ class OptimizeVI:
 def optimize_kl(likelihood: LikelihoodWithModel, position_or_samples, *, key, n_total_iterations: int, n_samples,
                 point_estimates=(), constants=(), draw_linear_kwargs=None, nonlinearly_update_kwargs=None, kl_kwargs=None,
                 sample_mode="nonlinear_resample", resume=False, callback: Optional[Callable] = None, odir: Optional[str] = None,
-                comm=None, _optimize_vi=None, _optimize_vi_state=None):
-    """``jft.optimize_kl`` (optimize_kl.py:744-879): returns ``(Samples, OptimizeVIState)``."""
-    opt_vi = _optimize_vi if _optimize_vi is not None else OptimizeVI(likelihood, n_total_iterations, comm=comm)
+                comm=None, jit=True, linear_minimizer_jit=False, nonlinear_minimizer_jit=False, kl_map=None, residual_map="lmap",
+                kl_reduce=None, mirror_samples=True, devices=None, _optimize_vi=None, _optimize_vi_state=None):
+    """``jft.optimize_kl`` (optimize_kl.py:744-879): returns ``(Samples, OptimizeVIState)``.  ``resume`` may be ``True``
+    (continue from ``odir/last.pkl``) or the path of a checkpoint (:806-839)."""
+    opt_vi = _optimize_vi if _optimize_vi is not None else OptimizeVI(
+        likelihood, n_total_iterations, comm=comm, jit=jit, linear_minimizer_jit=linear_minimizer_jit,
+        nonlinear_minimizer_jit=nonlinear_minimizer_jit, kl_map=kl_map, residual_map=residual_map, kl_reduce=kl_reduce,
+        mirror_samples=mirror_samples, devices=devices)
     rank = opt_vi.comm.rank
     last_fn = os.path.join(odir, "last.pkl") if odir is not None else None
     samples = None
     state = _optimize_vi_state
-    if resume and last_fn is not None and os.path.isfile(last_fn):
-        with open(last_fn, "rb") as f:
+    resume_fn = resume if isinstance(resume, str) else last_fn          # optimize_kl.py:830-839
+    if resume and resume_fn is not None and os.path.isfile(resume_fn):
+        with open(resume_fn, "rb") as f:
             s_pos, s_res_all, s_keys, st = pickle.load(f)
         dev, dt = likelihood.rt.device, likelihood.dtype
         pos = torch.as_tensor(s_pos, dtype=dt, device=dev)
