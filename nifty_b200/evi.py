@@ -235,25 +235,49 @@ def wiener_filter_posterior(likelihood: LikelihoodWithModel, position=None, *, k
     Signal-space branch (:453-476): ``j = J^T M (d - f(p) + J p)``, ``mean = (J^T M J + 1)^-1 j`` by conjugate
     gradient on the fused metric-vector product, then ``n_samples`` MGVI draws at the mean, mirrored
     (:502-511).  For a model that is linear in the reference's sense ``d - f(p) + J p = d``, so the same formula
-    serves ``model_is_linear=True`` (the reference then transposes ``forward`` itself).  The data-space branch
-    (``signal_space=False``) is not provided on the B200 path; ``residual_map`` / ``jit`` are accepted for
-    call compatibility (samples are drawn one after the other on the device)."""
+    serves ``model_is_linear=True`` (the reference then transposes ``forward`` itself).  Data-space branch
+    (``signal_space=False``, :477-497, Gaussian likelihoods): ``(J J^T + N) x = d'``, ``mean = J^T x``.
+    ``residual_map`` / ``jit`` are accepted for call compatibility (samples are drawn one after the other)."""
     if not isinstance(likelihood, LikelihoodWithModel):
         raise TypeError(f"likelihood must be of LikelihoodWithModel type; got {likelihood}")
     if not model_is_linear and position is None:
         raise ValueError("For nonlinear models a position to linearize must be specified.")
-    if not signal_space:
-        raise NotImplementedError("the data-space Wiener filter is not supported on the B200 path (signal_space=True is)")
     if likelihood.signal.cf.plan.dist:
         raise NotImplementedError("wiener_filter_posterior on slab-decomposed fields is not supported yet")
     kw = dict(draw_linear_kwargs or {})
     sig = likelihood.signal
     pos = torch.zeros(sig.layout.size, dtype=likelihood.dtype, device=likelihood.rt.device) if position is None else sig.as_flat(position)
     lin, _ = likelihood.lin_at(pos)
-    d_lin = lin.normalized_residual() + lin.rsm(pos, scaled=True)      # M^(1/2) (d - f(p) + J p), M diagonal
-    j = lin.lsm(d_lin, scaled=True)
     cg = kw.get("cg", conjugate_gradient.cg)
-    post_mean, post_info = cg(HamiltonianMetric(lin, likelihood=likelihood), j, name=kw.get("cg_name", None), **kw.get("cg_kwargs", {}))
+    if signal_space:
+        d_lin = lin.normalized_residual() + lin.rsm(pos, scaled=True)      # M^(1/2) (d - f(p) + J p), M diagonal
+        j = lin.lsm(d_lin, scaled=True)
+        post_mean, post_info = cg(HamiltonianMetric(lin, likelihood=likelihood), j, name=kw.get("cg_name", None), **kw.get("cg_kwargs", {}))
+    else:
+        # data-space branch (:477-497): (J J^T + N) x = d', mean = J^T x, with J = l^-1 RSM and J^T = LSM l^-1
+        # (l = N^(-1/2), diagonal); the solve runs on data-shaped vectors in the host CG loop
+        if noise_covariance is None:
+            raise ValueError("To use the Wiener filter in data space, please set the noise_covariance")
+        lk = likelihood.likelihood
+        if lk.kind != 0:
+            raise NotImplementedError("the data-space Wiener filter needs a Gaussian likelihood")
+        shape = tuple(sig.target_shape)
+        w = lk.w_scalar if lk.w_array is None else likelihood.rt.asarray(lk.w_array, likelihood.dtype)
+        l = float(np.sqrt(w)) if lk.w_array is None else torch.sqrt(w)
+
+        def jac(t):
+            return lin.rsm(t, scaled=True) / l
+
+        def jac_t(u):
+            return lin.lsm(u / l, scaled=True)
+
+        def post_dspace_cov_inv(u_flat):
+            u = u_flat.reshape(shape)
+            return (jac(jac_t(u)) + noise_covariance(u)).reshape(-1)
+
+        d_lin = lin.normalized_residual() / l + jac(pos)
+        x, post_info = cg(post_dspace_cov_inv, d_lin.reshape(-1), name=kw.get("cg_name", None), **kw.get("cg_kwargs", {}))
+        post_mean = jac_t(x.reshape(shape))
     if post_info is not None and post_info < 0:
         raise ValueError("conjugate gradient failed")
     if n_samples > 0:

@@ -71,8 +71,14 @@ def check_wiener_filter(rt, name="g2d_16x16"):
     import pytest
     with pytest.raises(ValueError, match="position to linearize"):
         nb.wiener_filter_posterior(lh, key=1, model_is_linear=False)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="noise_covariance"):
         nb.wiener_filter_posterior(lh, tpos, key=1, signal_space=False)
+    # data-space branch (evi.py:477-497): same mean, as the reference checks (test_evi.py:218-231, atol 7e-7)
+    ncov = 1.0 / float(g["noise_cov_inv"])
+    dsp, (dinfo, _) = nb.wiener_filter_posterior(lh, tpos, key=1, n_samples=0, model_is_linear=False, signal_space=False,
+                                                 noise_covariance=lambda x: ncov * x,
+                                                 draw_linear_kwargs=dict(cg_kwargs=dict(resnorm=1e-9, maxiter=600)))
+    assert dinfo == 0 and rel_err(t2n(dsp.pos), dense) < 1e-6
     with pytest.raises(TypeError):
         nb.wiener_filter_posterior(object(), tpos, key=1)
 
