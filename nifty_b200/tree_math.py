@@ -1,0 +1,95 @@
+"""Tree arithmetic helpers with the semantics of ``nifty/re/tree_math`` on this package's two latent representations:
+dicts of tensors (the reference's pytrees, sorted-key leaf order) and flat device vectors (``Layout.pack``).
+
+``vdot`` (vector_math.py:221-223), ``norm`` (:173-188: the ord-norm of the per-leaf ord-norms -- for a flat vector
+that is the plain vector norm), ``size`` (:141-144), ``zeros_like`` (:160), ``where`` (:249-281), and the sequential
+maps ``smap`` / ``lmap`` / ``get_map`` (custom_map.py:106-160, forest_math.py:136-156): on this path every sample is
+a sequence of device launches, so all maps are the same in-order Python loop with ``in_axes`` semantics.
+"""
+
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+import torch
+
+
+def _leaves(tree):
+    if isinstance(tree, dict):
+        return [tree[k] for k in sorted(tree)]
+    if isinstance(tree, (tuple, list)):
+        return [l for t in tree for l in _leaves(t)]
+    return [tree]
+
+
+def _map(f, *trees):
+    t0 = trees[0]
+    if isinstance(t0, dict):
+        return {k: _map(f, *(t[k] if isinstance(t, dict) else t for t in trees)) for k in t0}
+    if isinstance(t0, (tuple, list)):
+        return type(t0)(_map(f, *(t[i] if isinstance(t, (tuple, list)) else t for t in trees)) for i in range(len(t0)))
+    return f(*trees)
+
+
+def vdot(a, b) -> float:
+    return float(sum(torch.dot(torch.as_tensor(x).reshape(-1), torch.as_tensor(y).reshape(-1)) for x, y in zip(_leaves(a), _leaves(b))))
+
+
+def norm(tree, ord=2) -> float:
+    def el(x):
+        x = torch.as_tensor(x)
+        return float(x.abs()) if x.ndim == 0 else float(torch.linalg.vector_norm(x.reshape(-1).to(torch.float64), ord=ord))
+    return float(np.linalg.norm(np.array([el(x) for x in _leaves(tree)]), ord=ord))
+
+
+def size(tree) -> int:
+    return int(sum(int(np.prod(np.shape(x), dtype=np.int64)) if not isinstance(x, torch.Tensor) else x.numel() for x in _leaves(tree)))
+
+
+def zeros_like(tree):
+    return _map(lambda x: torch.zeros_like(torch.as_tensor(x)), tree)
+
+
+def where(condition, x, y):
+    """Leaf-wise ``torch.where``; a non-tree ``condition`` / ``x`` / ``y`` is broadcast over the leaves of the largest tree."""
+    trees = [t for t in (condition, x, y) if isinstance(t, (dict, tuple, list))]
+    if not trees:
+        return torch.where(torch.as_tensor(condition), torch.as_tensor(x), torch.as_tensor(y))
+    ref = max(trees, key=lambda t: len(_leaves(t)))
+    return _map(lambda _, c, a, b: torch.where(torch.as_tensor(c), torch.as_tensor(a), torch.as_tensor(b)), ref, condition, x, y)
+
+
+def _sequential_map(fun: Callable, in_axes=0, out_axes=0):
+    """``vmap``-like call signature, evaluated one batch element after the other (custom_map.py:106-160)."""
+    def mapped(*args):
+        axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+        n = None
+        for a, ax in zip(args, axes):
+            if ax is not None:
+                n = _leaves(a)[0].shape[ax]
+                break
+        if n is None:
+            raise ValueError("at least one argument must be mapped")
+        outs = [fun(*(a if ax is None else _map(lambda t: torch.as_tensor(t).select(ax, i), a) for a, ax in zip(args, axes))) for i in range(n)]
+        return _map(lambda *ts: torch.stack([torch.as_tensor(t) for t in ts], dim=out_axes), *outs)
+    return mapped
+
+
+def smap(fun, in_axes=0, out_axes=0, *, unroll=1):
+    return _sequential_map(fun, in_axes, out_axes)
+
+
+def lmap(fun, in_axes=0, out_axes=0):
+    return _sequential_map(fun, in_axes, out_axes)
+
+
+def get_map(map) -> Callable:
+    """forest_math.py:136-156; "vmap" / "pmap" have no separate meaning here and select the same sequential map."""
+    if isinstance(map, str):
+        if map in ("vmap", "v", "pmap", "p", "lmap", "l", "smap", "s"):
+            return lmap if map[0] in "lvp" else smap
+        raise ValueError(f"unknown `map` {map!r}")
+    if callable(map):
+        return map
+    raise TypeError(f"invalid `map` {map!r}; expected string or callable")

@@ -1,0 +1,42 @@
+"""Host-side tree arithmetic (nifty/re/tree_math semantics) -- no device needed."""
+import numpy as np
+import pytest
+import torch
+
+import nifty_b200 as nb
+
+
+def _tree(rng):
+    return {"b": torch.as_tensor(rng.standard_normal((3, 2))), "a": torch.as_tensor(rng.standard_normal(())),
+            "c": torch.as_tensor(rng.standard_normal(5))}
+
+
+def test_vdot_norm_size_zeros_where():
+    rng = np.random.default_rng(0)
+    x, y = _tree(rng), _tree(rng)
+    flat = lambda t: np.concatenate([np.ravel(t[k].numpy()) for k in sorted(t)])
+    assert abs(nb.vdot(x, y) - float(flat(x) @ flat(y))) < 1e-13
+    assert nb.size(x) == 12
+    # norm = ord-norm of the per-leaf ord-norms (vector_math.py:173-188)
+    for o in (1, 2, np.inf):
+        per_leaf = [abs(float(x["a"]))] + [np.linalg.norm(np.ravel(x[k].numpy()), ord=o) for k in ("b", "c")]
+        assert abs(nb.norm(x, ord=o) - np.linalg.norm(per_leaf, ord=o)) < 1e-13
+    assert abs(nb.norm(torch.as_tensor(flat(x)), 2) - np.linalg.norm(flat(x))) < 1e-13
+    z = nb.zeros_like(x)
+    assert all(float(z[k].abs().sum()) == 0 and z[k].shape == x[k].shape for k in x)
+    w = nb.where({k: x[k] > 0 for k in x}, x, 0.0)
+    assert all(torch.equal(w[k], torch.where(x[k] > 0, x[k], torch.zeros_like(x[k]))) for k in x)
+    w2 = nb.where(True, x, y)
+    assert all(torch.equal(w2[k], x[k]) for k in x)
+
+
+def test_sequential_maps():
+    xs = torch.arange(12.0).reshape(4, 3)
+    f = lambda row, s: {"sum": row.sum() * s, "row": row + s}
+    for m in (nb.smap, nb.lmap, nb.get_map("lmap"), nb.get_map("smap"), nb.get_map("vmap")):
+        out = m(f, in_axes=(0, None))(xs, 2.0)
+        assert torch.equal(out["sum"], xs.sum(1) * 2.0) and torch.equal(out["row"], xs + 2.0)
+    with pytest.raises(ValueError):
+        nb.get_map("nope")
+    with pytest.raises(TypeError):
+        nb.get_map(3)
