@@ -451,7 +451,8 @@ template <class T> struct Plan : PlanBase {
     }
     int grid = c.grid;
     if (omap) { if (n_o_chunk <= 0) return; grid = n_o_chunk * (p.n_r >> p.lg_R); }
-    launch<PCBody<T>>(grid, c.block, c.smem, st, p);
+    if (3 * (c.smem + 2048) <= size_t(100) * 1024) launch<PCBody<T, 3>>(grid, c.block, c.smem, st, p);
+    else launch<PCBody<T, 2>>(grid, c.block, c.smem, st, p);
   }
   template <bool FWD, bool ADJ> void run_p3(stream_t st, const PointOp<T>& op, int line0 = 0, int nlines = -1) {
     P3Params<T> p;
