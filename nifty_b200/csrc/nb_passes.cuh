@@ -815,9 +815,12 @@ template <class T, class Epi> struct P5Params {
   Epi epi;
 };
 
-template <class T, class Epi> struct P5Body {
+// MINB / PIPE (chosen by the host, profiles/r2_notes.md): long lines (64 KB CTAs) run two CTAs per SM with the pipelined
+// epilogue (128 registers; at 80 it spills: 251 vs 151 us at 4096^2); short lines run three CTAs' worth of registers
+// without the pipeline (80 registers, no spills: 121 vs 140 us at 256^3).
+template <class T, class Epi, int MINB = 2, bool PIPE = true> struct P5Body {
   typedef P5Params<T, Epi> Params;
-  static constexpr int kMinBlocks = 2;     // 128 registers: the pipelined epilogue spills at the 80 of three CTAs per SM (251 vs 151 us)
+  static constexpr int kMinBlocks = MINB;
   static NB_HD NB_INLINE void pair(const Params& p, const cplx<T>* line, const LineInfo& li, int x, int y, T& acc) {
     const T sg = p.hsign;
     const int n = 1 << p.lg_n, h = n >> 1, nmid = 1 << p.mg.lg_mid;
@@ -891,7 +894,7 @@ template <class T, class Epi> struct P5Body {
 #pragma unroll
         for (int u = 0; u < U; ++u) p.epi.gather(sl[u].pre);
       };
-      batched_loop<true, U, Slot>(ctx, cnt, issue, gather, consume);
+      batched_loop<PIPE, U, Slot>(ctx, cnt, issue, gather, consume);
       NB_FOR(ctx, i, 2 * R) {
         int r = i >> 1;
         if (li[r].active) { int x = (i & 1) ? h : 0; pair(p, s + r * p.pitch, li[r], x, x, acc); }

@@ -492,7 +492,9 @@ template <class T> struct Plan : PlanBase {
     p.lg_n = lgl; p.lg_R = c5.lg_R; p.mg = mg5(); p.hmid1 = g.hm + 1; p.pitch = c5.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = fl; p.ahead = c5.ahead;
     p.hsign = hsign; p.in = s1(); p.epi = epi;
     p.src_off = dist ? src_off5.p : nullptr; p.src_mul = dist ? src_mul5.p : nullptr;
-    launch<P5Body<T, Epi>>(grid5, c5.block, c5.smem + LINEINFO_BYTES, st, p);
+    const size_t sm5 = c5.smem + LINEINFO_BYTES;
+    if (3 * (sm5 + 2048) <= size_t(100) * 1024) launch<P5Body<T, Epi, 3, false>>(grid5, c5.block, sm5, st, p);
+    else launch<P5Body<T, Epi, 2, true>>(grid5, c5.block, sm5, st, p);
   }
   // natural (d0,d1,d2) -> reversed axes; for the T-layout <-> natural conversions
   void run_rev(stream_t st, const T* in, T* out, bool to_T) {
