@@ -1,6 +1,7 @@
 """CPU tier: the kernel sources executed sequentially on the host (tests/emu) against the oracle and
 the nifty.cl fixtures.  Checks host logic, index arithmetic and call sequences without a GPU; the
 GPU tier (test_gpu_parity.py) runs the same checks through libniftyb200.so."""
+import numpy as np
 import pytest
 import torch
 
@@ -80,6 +81,30 @@ def test_p1_mirror_quads(rt, monkeypatch, lg_r):
     pc.check_against_oracle(rt, (8, 16, 8), 0.3, lh_kind="poisson")
     monkeypatch.setenv("NB200_SCAN_E", "4")
     pc.check_against_oracle(rt, (64, 128), (0.01, 0.02))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_configurations(rt, monkeypatch, seed):
+    """Seeded random draws of the configuration space the path supports -- 1 to 3 power-of-two axes of unequal extent and
+    spacing, both likelihoods, optional flexibility / asperity, forced lines-per-CTA choices and scan chunk sizes -- each
+    checked against the oracle (energy, gradient, metric, both sqrt-metrics)."""
+    rng = np.random.default_rng(1000 + seed)
+    ndim = int(rng.integers(1, 4))
+    shape = tuple(int(2 ** rng.integers(1, 6 if ndim < 3 else 5)) for _ in range(ndim))
+    dist = tuple(float(d) for d in rng.uniform(0.05, 0.7, ndim))
+    kw = {}
+    r = rng.integers(0, 3)
+    if r == 1:
+        kw["asperity"] = None
+    elif r == 2:
+        kw["flexibility"], kw["asperity"] = None, None
+    for knob in ("NB200_LGR1", "NB200_LGR3", "NB200_LGR5", "NB200_LGRC"):
+        if rng.integers(0, 2):
+            monkeypatch.setenv(knob, str(int(rng.integers(0, 4))))
+    if rng.integers(0, 2):
+        monkeypatch.setenv("NB200_SCAN_E", "4")
+    pc.check_against_oracle(rt, shape if ndim > 1 else shape, dist if ndim > 1 else dist[0], lh_kind="gauss" if rng.integers(0, 2) else "poisson",
+                            seed=int(rng.integers(0, 1 << 30)), **kw)
 
 
 def test_unsupported_shapes_fail_loudly(rt):

@@ -97,6 +97,30 @@ def test_full_size_properties(rt, shape, dist, kind):
     pc.check_metric_properties(rt, shape, dist, lh_kind=kind)
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_random_configurations(rt, monkeypatch, seed):
+    """Seeded random draws of the configuration space the path supports -- 1 to 3 power-of-two axes of unequal extent and
+    spacing, both likelihoods, optional flexibility / asperity, forced lines-per-CTA choices and scan chunk sizes -- each
+    checked against the oracle (energy, gradient, metric, both sqrt-metrics)."""
+    rng = np.random.default_rng(1000 + seed)
+    ndim = int(rng.integers(1, 4))
+    shape = tuple(int(2 ** rng.integers(1, 6 if ndim < 3 else 5)) for _ in range(ndim))
+    dist = tuple(float(d) for d in rng.uniform(0.05, 0.7, ndim))
+    kw = {}
+    r = rng.integers(0, 3)
+    if r == 1:
+        kw["asperity"] = None
+    elif r == 2:
+        kw["flexibility"], kw["asperity"] = None, None
+    for knob in ("NB200_LGR1", "NB200_LGR3", "NB200_LGR5", "NB200_LGRC"):
+        if rng.integers(0, 2):
+            monkeypatch.setenv(knob, str(int(rng.integers(0, 4))))
+    if rng.integers(0, 2):
+        monkeypatch.setenv("NB200_SCAN_E", "4")
+    pc.check_against_oracle(rt, shape if ndim > 1 else shape, dist if ndim > 1 else dist[0], lh_kind="gauss" if rng.integers(0, 2) else "poisson",
+                            seed=int(rng.integers(0, 1 << 30)), **kw)
+
+
 def test_hartley_vs_torch_fft_large(rt):
     """Independent check of the transform arithmetic at 1024^2 against torch.fft (cuFFT), rel 1e-10."""
     shape = (1024, 1024)
