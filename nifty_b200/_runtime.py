@@ -524,12 +524,35 @@ class Lin:
 
     def metric_pair(self, other: "Lin", t, add_identity=False):
         out = self._vec()
+        if self.model.plan.dist:      # same phases as `metric`: tangent side from `other`, adjoint side from `self`
+            plan = self.model.plan
+            self._dist_buffers()
+            if plan.nchunks > 1:
+                self._phase(20, other=other, inp=t)
+                self._pipelined(1, 11, lambda c: self._phase(21, other=other, inp=t, chunk=c))
+            else:
+                self._phase(2, other=other, inp=t)
+                plan.exchange(1)
+                self._phase(3, other=other, inp=t)
+            return self._dist_adjoint_tail(t, out, add_identity, True)
         self.rt.api.call("nb200_metric_pair", self._h, other._h, self.rt.stream(), self.rt.ptr(t), self.rt.ptr(out),
                          int(add_identity))
         return out
 
     def rsm(self, t, scaled=True):
         out = self._pos()
+        if self.model.plan.dist:      # tangent chain + P1 + PCa | exchange 1 | forward-only P3 into the local planes
+            plan = self.model.plan
+            self._dist_buffers()
+            out.zero_()
+            if plan.nchunks > 1:
+                self._phase(20, inp=t)
+                self._pipelined(1, 11, lambda c: self._phase(25, inp=t, out=out, flag=int(scaled), chunk=c))
+            else:
+                self._phase(2, inp=t)
+                plan.exchange(1)
+                self._phase(7, inp=t, out=out, flag=int(scaled))
+            return out
         self.rt.api.call("nb200_rsm", self._h, self.rt.stream(), self.rt.ptr(t), self.rt.ptr(out), int(scaled))
         return out
 

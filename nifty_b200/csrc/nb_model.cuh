@@ -227,6 +227,7 @@ template <class T> struct Lin : LinBase {
   // code: 0 update.1 (amplitude, P1, PCa) | 1 update.2 (P3 linearise; local energy) | 2 metric.1 (tangent chain, P1, PCa)
   //       3 metric.2 (P3 fused, PCb) | 4 lsm.2 (P3 adjoint-only from local T-layout `in`, PCb) | 5 adjoint.3 (P5, local bin sums,
   //       xs = {p3 sum, xi dot}) | 6 adjoint.4 (finish with all-reduced abar / xs: hyper-parameter leaves, <add,out>)
+  //       7 rsm.2 (P3 forward-only into local planes; after metric.1 + exchange 1); 1x / 2x: the chunked forms
   void dist_phase(stream_t st, int code, Lin<T>* b, const T* in, T* out, T* abar, T* xs, int flag, int chunk = -1) {
     Model<T>& m = *M; Plan<T>& P = *m.P;
     if (!P.dist) throw Error{"nb200_dist_phase: not a slab-decomposed plan"};
@@ -284,6 +285,12 @@ template <class T> struct Lin : LinBase {
         P.template run_p3<false, true>(st, op, l3, n3);
         if (code == 4) P.run_pc(st, true);
       } break;
+      case 7: case 25: {     // rsm.2: forward-only P3 into the local planes `out` (chunk); flag bit 0: scaled (l * d signal)
+        PointOp<T> op = P.make_op(PM_JVP_OUT);
+        op.invV = T(1.0 / P.g.V); op.natural = 0; op.pos_out = out; op.jl_a = (flag & 1) ? jl.p : nullptr;
+        if ((flag & 1) && m.am.has_scaling) { op.cshift_ptr = in + m.am.off_scl; op.cshift_scale = m.am.scl_b; }
+        P.template run_p3<true, false>(st, op, l3, n3);
+      } break;
       case 23: P.run_p5(st, epi_adjoint(out, (flag & 1) ? in : nullptr, (flag & 1) != 0), l5, n5); break;   // P5 (chunk)
       case 5: case 24: {     // adjoint.3: (P5 for code 5) local bin sums, xs = {p3 sum, xi dot}
         if (code == 5) P.run_p5(st, epi_adjoint(out, (flag & 1) ? in : nullptr, (flag & 1) != 0));
@@ -308,9 +315,10 @@ template <class T> struct Lin : LinBase {
   void posmap(stream_t st, int mode, T* out_nat) {
     Model<T>& m = *M; Plan<T>& P = *m.P;
     if (!valid) throw Error{"nb200: linearisation not initialised (call nb200_lin_update)"};
-    PosMapParams<T> pm; pm.mode = mode; pm.lh_kind = m.lh_kind; pm.n = (long)P.g.N; pm.s = s.p; pm.data = m.data.p;
+    PosMapParams<T> pm; pm.mode = mode; pm.lh_kind = m.lh_kind; pm.s = s.p; pm.data = m.data.p;
+    pm.n = P.dist ? (long)P.planes2 * P.g.nm * P.g.n0 : (long)P.g.N;       // slab-decomposed: the local planes only
     pm.w_scalar = m.w_scalar; pm.w_arr = m.has_w_arr ? m.w_arr.p : nullptr; pm.out = m.tmp_pos.p;
-    int grid = (int)std::min<int64_t>((P.g.N + 255) / 256, 148 * 8);
+    int grid = (int)std::min<int64_t>((pm.n + 255) / 256, 148 * 8);
     if (P.dist) pm.out = out_nat;      // slab-decomposed plans hand out the local planes in the internal layout
     launch<PosMapBody<T>>(grid, 256, 0, st, pm);
     if (!P.dist) P.run_rev(st, m.tmp_pos.p, out_nat, false);

@@ -160,6 +160,14 @@ def nonlinearly_update_residual(likelihood: LikelihoodWithModel, pos, residual_s
     operator output is cleared there."""
     frozen = likelihood.frozen_ranges(point_estimates)
     clr = (lambda v: likelihood.clear_frozen(v, frozen)) if frozen else (lambda v: v)
+    dist = bool(likelihood.signal.cf.plan.dist)
+    # slab-decomposed fields: latent dot products / norms and the data-space sum are all-reduced (replicated leaves once)
+    vdot = likelihood.vdot if dist else (lambda a, b: float(torch.dot(a, b)))
+
+    def pos_sumsq(u):
+        t = (u * u).sum().to(torch.float64).reshape(1)
+        return float(likelihood.signal.cf.plan.comm.allreduce_sum(t)) if dist else float(t)
+
     e = likelihood.signal.as_flat(pos)
     sample = e + clr(likelihood.signal.as_flat(residual_sample).clone())
     ms, _ = draw_linear_residual(likelihood, e, metric_sample_key, from_inverse=False, point_estimates=point_estimates, _white=_white)
@@ -177,16 +185,16 @@ def nonlinearly_update_residual(likelihood: LikelihoodWithModel, pos, residual_s
         t = lin_x.transformation() - trafo_at_p
         g = x - e + clr(lin_e.lsm(t, scaled=True))
         r = ms - g
-        val = 0.5 * float(torch.dot(r, r))
+        val = 0.5 * vdot(r, r)
         ngrad = r + clr(lin_x.lsm(lin_e.rsm(r, scaled=True), scaled=True))
         return val, -ngrad
 
     def metric_at(x):  # evi.py:167-172 at the point of the last residual_vg evaluation (== x)
-        return HamiltonianMetric(lin_x, other=lin_e, frozen=frozen)
+        return HamiltonianMetric(lin_x, other=lin_e, likelihood=likelihood, frozen=frozen)
 
     def sampnorm(natgrad):  # evi.py:175-178
         fpp = lin_e.rsm(natgrad, scaled=True)
-        return float(torch.sqrt(torch.dot(natgrad, natgrad) + (fpp * fpp).sum()))
+        return float(np.sqrt(vdot(natgrad, natgrad) + pos_sumsq(fpp)))
 
     # Newton-CG evaluates hessp at `pos` right after fun_and_grad(pos) accepted it, so lin_x is current;
     # after a rejected line-search trial it is re-linearised by the wrapper below.
@@ -204,6 +212,10 @@ def nonlinearly_update_residual(likelihood: LikelihoodWithModel, pos, residual_s
 
     if frozen:       # xtol * size counts the liquid entries only (the reference minimises over the liquid vector)
         mk.setdefault("_size", likelihood.layout.size - sum(hi - lo for lo, hi in frozen))
+    if dist:
+        mk.setdefault("vdot", likelihood.vdot)
+        mk.setdefault("vnorm", likelihood.vnorm)
+        mk.setdefault("_size", likelihood.global_size())
     opt = minimize(None, x0=sample, fun_and_grad=fg, hessp_at=op_at, custom_gradnorm=sampnorm, **mk)
     if _raise_notconverged and (opt.status is None or opt.status < 0):
         raise ValueError("S: failed to invert map")

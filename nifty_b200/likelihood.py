@@ -232,6 +232,14 @@ class LikelihoodWithModel:
             return max(float(t), float(rep.abs().max()) if rep.numel() else 0.0)
         raise ValueError(f"unsupported norm order {ord!r} on slab-decomposed vectors")
 
+    def global_size(self) -> int:
+        """Number of latent degrees of freedom of the whole model (slab-decomposed: hyper-parameters + the GLOBAL grid) --
+        what ``xtol * size`` of the reference's Newton-CG refers to; identical on every rank."""
+        if not self._plan.dist:
+            return self.layout.size
+        lo, hi = self._xi_slice()
+        return self.layout.size - (hi - lo) + int(self._plan.N)
+
     def zero_padding(self, v: torch.Tensor) -> torch.Tensor:
         """Zero the padding rows of the xi block of a slab-decomposed latent vector (no-op otherwise)."""
         if self._plan.dist:

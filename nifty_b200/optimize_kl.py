@@ -253,6 +253,7 @@ class OptimizeVI:
         if self.likelihood.signal.cf.plan.dist:      # slab-decomposed latent vectors: all-reduced reductions
             kw.setdefault("vdot", self.likelihood.vdot)
             kw.setdefault("vnorm", self.likelihood.vnorm)
+            kw.setdefault("_size", self.likelihood.global_size())
         return minimize(None, x0=samples.pos, fun_and_grad=fg, hessp=hessp, **kw)
 
     # -- driver -------------------------------------------------------------------------------------------

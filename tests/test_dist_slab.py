@@ -88,6 +88,16 @@ def slab_check(rt, shape, dist_, lh_kind="gauss", seed=3, tol=1e-10):
     ols = olh.left_sqrt_metric(pos, u)
     scale = max(np.max(np.abs(v)) for v in ols.values())
     errs["lsm"] = max(float(np.max(np.abs(ls[k] - ols[k]))) / scale for k in ols)
+    # right sqrt-metric, transformation and residual live on the local position planes
+    rs = plan.gather_position(lin.rsm(tl, scaled=True)).cpu().numpy()
+    ors = olh.right_sqrt_metric(pos, tan)
+    errs["rsm"] = float(np.max(np.abs(rs - ors)) / np.max(np.abs(ors)))
+    tr = plan.gather_position(lin.transformation()).cpu().numpy()
+    otr = olh.transformation(pos)
+    errs["transformation"] = float(np.max(np.abs(tr - otr)) / np.max(np.abs(otr)))
+    nr = plan.gather_position(lin.normalized_residual()).cpu().numpy()
+    onr = olh.normalized_residual(pos)
+    errs["normalized_residual"] = float(np.max(np.abs(nr - onr)) / np.max(np.abs(onr)))
     ee, gg = lh.energy_and_gradient(pl, add_prior=True)
     oe2, og = olh.energy_and_gradient(pos)
     flat = lay.pack(pos)
@@ -105,6 +115,15 @@ def slab_check(rt, shape, dist_, lh_kind="gauss", seed=3, tol=1e-10):
         scale = max(np.max(np.abs(v)) for v in ores.values())
         errs["mgvi_draw"] = max(float(np.max(np.abs(got[k] - ores[k]))) / scale for k in ores)
         assert info == oinfo, (info, oinfo, errs)
+        # geoVI update of that sample (evi.py:181-255) with distributed reductions: Newton-CG on the pair operator
+        mk = dict(xtol=1e-8, maxiter=2, cg_kwargs=dict(absdelta=1e-30, maxiter=6, miniter=7))
+        onew, oopt = oracle.nonlinearly_update_residual(olh, pos, ores, wd, wp, 1.0, minimize_kwargs=mk)
+        new, opt = nb.nonlinearly_update_residual(lh, pl, res, 0, 1.0, minimize_kwargs=mk,
+                                                  _white=(plan.scatter_position(wd), localise(wp)))
+        gnew = globalise(new)
+        scale = max(np.max(np.abs(v)) for v in onew.values())
+        errs["geovi_update"] = max(float(np.max(np.abs(gnew[k] - onew[k]))) / scale for k in onew)
+        assert opt.nit == oopt.nit and opt.status == oopt.status, (opt.nit, oopt.nit, opt.status, oopt.status)
         # stochastic draw path (per-rank keys): runs, hyper-parameter leaves identical on all ranks
         r2, _ = nb.draw_linear_residual(lh, pl, 123, cg_kwargs=cgkw)
         hyp = torch.cat((r2[:lh._xi_slice()[0]], r2[lh._xi_slice()[1]:])).to(torch.float64)
@@ -120,7 +139,7 @@ def slab_check(rt, shape, dist_, lh_kind="gauss", seed=3, tol=1e-10):
         hyp = torch.cat((opt.x[:lh._xi_slice()[0]], opt.x[lh._xi_slice()[1]:])).to(torch.float64)
         allh = plan.comm.all_gather(hyp)
         assert all(torch.equal(allh[0], h) for h in allh)
-    bad = {k: v for k, v in errs.items() if not v < (1e-7 if k == "mgvi_draw" else tol)}
+    bad = {k: v for k, v in errs.items() if not v < (1e-7 if k in ("mgvi_draw", "geovi_update") else tol)}
     assert not bad, bad
     return errs
 
