@@ -210,12 +210,11 @@ def nonlinearly_update_residual(likelihood: LikelihoodWithModel, pos, residual_s
             state["x"] = x
         return metric_at(x)
 
-    if frozen:       # xtol * size counts the liquid entries only (the reference minimises over the liquid vector)
-        mk.setdefault("_size", likelihood.layout.size - sum(hi - lo for lo, hi in frozen))
+    if frozen or dist:       # xtol * size counts the liquid entries of the whole model (the reference minimises over the liquid vector)
+        mk.setdefault("_size", likelihood.global_size(frozen))
     if dist:
         mk.setdefault("vdot", likelihood.vdot)
         mk.setdefault("vnorm", likelihood.vnorm)
-        mk.setdefault("_size", likelihood.global_size())
     opt = minimize(None, x0=sample, fun_and_grad=fg, hessp_at=op_at, custom_gradnorm=sampnorm, **mk)
     if _raise_notconverged and (opt.status is None or opt.status < 0):
         raise ValueError("S: failed to invert map")

@@ -169,8 +169,6 @@ class LikelihoodWithModel:
         solves run on full-length vectors whose frozen entries are kept at zero / at the expansion point."""
         if not point_estimates:
             return []
-        if self._plan.dist:
-            raise NotImplementedError("point_estimates / constants on slab-decomposed fields are not supported yet")
         if isinstance(point_estimates, dict):
             keys = [k for k, v in point_estimates.items() if v]
         elif isinstance(point_estimates, str):
@@ -232,13 +230,19 @@ class LikelihoodWithModel:
             return max(float(t), float(rep.abs().max()) if rep.numel() else 0.0)
         raise ValueError(f"unsupported norm order {ord!r} on slab-decomposed vectors")
 
-    def global_size(self) -> int:
-        """Number of latent degrees of freedom of the whole model (slab-decomposed: hyper-parameters + the GLOBAL grid) --
-        what ``xtol * size`` of the reference's Newton-CG refers to; identical on every rank."""
-        if not self._plan.dist:
-            return self.layout.size
+    def global_size(self, frozen=()) -> int:
+        """Number of latent degrees of freedom of the whole model (slab-decomposed: hyper-parameters + the GLOBAL grid),
+        minus the entries of the ``frozen`` ranges -- what ``xtol * size`` of the reference's Newton-CG refers to;
+        identical on every rank."""
         lo, hi = self._xi_slice()
-        return self.layout.size - (hi - lo) + int(self._plan.N)
+        n = self.layout.size
+        for a, b in frozen:
+            n -= b - a
+        if self._plan.dist:
+            n += int(self._plan.N) - (hi - lo)
+            if any(a <= lo and hi <= b for a, b in frozen):      # the excitations are frozen: none of the global grid counts
+                n -= int(self._plan.N) - (hi - lo)
+        return n
 
     def zero_padding(self, v: torch.Tensor) -> torch.Tensor:
         """Zero the padding rows of the xi block of a slab-decomposed latent vector (no-op otherwise)."""

@@ -24,10 +24,15 @@ class ChiSqStats(NamedTuple):
     ndof: Any
 
 
-def _leaf_stats(plan, x: torch.Tensor):
-    """minisanity.py:17-21 for one real leaf: (mean, reduced chi^2, ndof)."""
+def _leaf_stats(plan, x: torch.Tensor, n_global=None):
+    """minisanity.py:17-21 for one real leaf: (mean, reduced chi^2, ndof).  ``n_global``: the leaf is the local part of a
+    slab-decomposed array (padding entries are zero): the two moments are all-reduced and divided by the global count."""
     n = int(x.numel())
-    s1, s2 = plan.vec_stats(x)
+    s1, s2 = plan.vec_stats(x.contiguous())
+    if n_global is not None:
+        t = torch.tensor([s1, s2], dtype=torch.float64, device=x.device)
+        s1, s2 = (float(v) for v in plan.comm.allreduce_sum(t))
+        n = int(n_global)
     return s1 / n, s2 / n, n
 
 
@@ -39,12 +44,14 @@ def _as_tree(v, layout: Optional[Layout]):
     return v
 
 
-def reduced_residual_stats(position_or_samples, func=None, *, plan, layout: Optional[Layout] = None, map="lmap"):
+def reduced_residual_stats(position_or_samples, func=None, *, plan, layout: Optional[Layout] = None, map="lmap",
+                           dist_leaves=()):
     """Tree of :class:`ChiSqStats` (one per leaf): ``mean`` and ``reduced_chisq`` are ``[sample mean, sample std]``.
 
     ``position_or_samples``: a flat latent vector, a dict of leaves or :class:`Samples`; ``func`` (optional) is
     applied to every position first (e.g. ``likelihood.normalized_residual``).  ``layout`` splits flat latent
-    vectors into their leaves; ``plan`` supplies the device reduction."""
+    vectors into their leaves; ``plan`` supplies the device reduction.  On a slab-decomposed plan ``dist_leaves`` names
+    the latent leaves of which every rank holds a part (the excitations); ``func`` outputs are position-space parts."""
     if isinstance(position_or_samples, Samples) and len(position_or_samples) > 0:
         points = [position_or_samples[i] for i in range(len(position_or_samples))]
     else:
@@ -54,10 +61,11 @@ def reduced_residual_stats(position_or_samples, func=None, *, plan, layout: Opti
     for p in points:
         v = func(p) if func is not None else p
         tree = _as_tree(v, layout if func is None else None)
+        ng = int(plan.N) if getattr(plan, "dist", False) else None
         if isinstance(tree, dict):
-            per_sample.append({k: _leaf_stats(plan, t) for k, t in tree.items()})
+            per_sample.append({k: _leaf_stats(plan, t, ng if (func is not None or k in dist_leaves) else None) for k, t in tree.items()})
         else:
-            per_sample.append(_leaf_stats(plan, tree))
+            per_sample.append(_leaf_stats(plan, tree, ng if func is not None else None))
 
     def combine(rows):
         m = np.array([r[0] for r in rows])
@@ -74,9 +82,9 @@ def _pretty(x: ChiSqStats) -> str:
     return f"reduced Chi²:{rsq[0]:8.2}±{rsq[1]:8.2}, avg:{x.mean[0]:+9.2}±{x.mean[1]:8.2}, #dof:{int(x.ndof):7d}"
 
 
-def minisanity(position_or_samples, func=None, *, plan, layout: Optional[Layout] = None, map="lmap"):
+def minisanity(position_or_samples, func=None, *, plan, layout: Optional[Layout] = None, map="lmap", dist_leaves=()):
     """``(stat_tree, report)`` (minisanity.py:110-129); one ``key:: reduced Chi² …`` line per leaf."""
-    stats = reduced_residual_stats(position_or_samples, func, plan=plan, layout=layout, map=map)
+    stats = reduced_residual_stats(position_or_samples, func, plan=plan, layout=layout, map=map, dist_leaves=dist_leaves)
     if isinstance(stats, dict):
         msg = "".join(f"{k:24s}:: {_pretty(v)}\n" for k, v in stats.items())
     else:

@@ -70,7 +70,7 @@ class _Comm:
         return out
 
 
-def get_status_message(samples, state, residual=None, *, name="", plan=None, layout=None, map="lmap") -> str:
+def get_status_message(samples, state, residual=None, *, name="", plan=None, layout=None, map="lmap", dist_leaves=()) -> str:
     """Per-iteration report (optimize_kl.py:40-61): energy, sampling status, KL steps and the minisanity tables of
     the likelihood residuals and of the latent parameters over the samples."""
     from .minisanity import minisanity
@@ -88,7 +88,7 @@ def get_status_message(samples, state, residual=None, *, name="", plan=None, lay
     mini_res = ""
     if residual is not None:
         _, mini_res = minisanity(samples, residual, plan=plan, map=map)
-    _, mini_pr = minisanity(samples, plan=plan, layout=layout, map=map)
+    _, mini_pr = minisanity(samples, plan=plan, layout=layout, map=map, dist_leaves=dist_leaves)
     return (f"{name}: Iteration {state.nit:04d} E:{energy:+2.4e}"
             f"{msg_smpl}"
             f"\n{name}: #(KL minimization steps) {state.minimization_state.nit}"
@@ -117,13 +117,9 @@ class OptimizeVI:
         self.likelihood = likelihood
         if _get_status_message is None:        # optimize_kl.py:376-389
             plan = likelihood.signal.cf.plan
-            if plan.dist:     # per-leaf moments of a slab-decomposed field would need their own reduction: tables left out
-                def _get_status_message(samples, state, *, name="", **kw):
-                    return (f"{name}: Iteration {state.nit:04d} E:{state.minimization_state.fun:+2.4e}"
-                            f"\n{name}: #(KL minimization steps) {state.minimization_state.nit}\n")
-            else:
-                _get_status_message = partial(get_status_message, residual=likelihood.normalized_residual, plan=plan,
-                                              layout=likelihood.layout)
+            dl = (likelihood.signal.cf.prefix + "xi",) if plan.dist else ()     # slab-decomposed: moments all-reduced
+            _get_status_message = partial(get_status_message, residual=likelihood.normalized_residual, plan=plan,
+                                          layout=likelihood.layout, dist_leaves=dl)
         self.get_status_message = _get_status_message
         self.n_total_iterations = n_total_iterations
         self.comm = _Comm(comm)
@@ -249,7 +245,7 @@ class OptimizeVI:
 
         kw = dict(minimize_kwargs or {})
         if frozen:
-            kw.setdefault("_size", self.likelihood.layout.size - sum(hi - lo for lo, hi in frozen))
+            kw.setdefault("_size", self.likelihood.global_size(frozen))
         if self.likelihood.signal.cf.plan.dist:      # slab-decomposed latent vectors: all-reduced reductions
             kw.setdefault("vdot", self.likelihood.vdot)
             kw.setdefault("vnorm", self.likelihood.vnorm)

@@ -124,6 +124,26 @@ def slab_check(rt, shape, dist_, lh_kind="gauss", seed=3, tol=1e-10):
         scale = max(np.max(np.abs(v)) for v in onew.values())
         errs["geovi_update"] = max(float(np.max(np.abs(gnew[k] - onew[k]))) / scale for k in onew)
         assert opt.nit == oopt.nit and opt.status == oopt.status, (opt.nit, oopt.nit, opt.status, oopt.status)
+        # minisanity on the slab-decomposed field: all-reduced moments equal the global ones
+        smp0 = nb.Samples(pos=pl, samples=torch.stack((res, -res)))
+        st_p, _ = nb.minisanity(smp0, plan=plan, layout=lh.layout, dist_leaves=("cfxi",))
+        pts = [lay.pack(pos) + sgn * lay.pack(ores) for sgn in (1.0, -1.0)]
+        xi = np.stack([lay.unpack(p)["cfxi"].reshape(-1) for p in pts])
+        rx = (xi * xi).sum(1) / xi.shape[1]
+        assert st_p["cfxi"].ndof == xi.shape[1] and abs(st_p["cfxi"].reduced_chisq[0] - rx.mean()) <= 1e-7 * rx.mean()
+        st_r, _ = nb.minisanity(smp0, lh.normalized_residual, plan=plan)
+        rr = np.stack([olh.normalized_residual(lay.unpack(p)).reshape(-1) for p in pts])
+        rr2 = (rr * rr).sum(1) / rr.shape[1]
+        assert st_r.ndof == rr.shape[1] and abs(st_r.reduced_chisq[0] - rr2.mean()) <= 1e-7 * rr2.mean()
+        # point estimates on the slab-decomposed field: a replicated leaf and (separately) the distributed excitations
+        for pe in (("cfax1fluctuations", "cfax1spectrum"), ("cfxi",)):
+            ofr, ofi, _ = oracle.draw_linear_residual(olh, pos, wd, wp, cg_kwargs=cgkw, point_estimates=pe)
+            rfr, rfi = nb.draw_linear_residual(lh, pl, 0, cg_kwargs=cgkw, point_estimates=pe,
+                                               _white=(plan.scatter_position(wd), localise(wp)))
+            gfr = globalise(rfr)
+            scale = max(np.max(np.abs(v)) for v in ofr.values())
+            errs["frozen_draw_" + pe[0]] = max(float(np.max(np.abs(gfr[k] - ofr[k]))) / scale for k in ofr)
+            assert rfi == ofi and all(float(np.max(np.abs(gfr[k]))) == 0.0 for k in pe)
         # stochastic draw path (per-rank keys): runs, hyper-parameter leaves identical on all ranks
         r2, _ = nb.draw_linear_residual(lh, pl, 123, cg_kwargs=cgkw)
         hyp = torch.cat((r2[:lh._xi_slice()[0]], r2[lh._xi_slice()[1]:])).to(torch.float64)
@@ -139,7 +159,10 @@ def slab_check(rt, shape, dist_, lh_kind="gauss", seed=3, tol=1e-10):
         hyp = torch.cat((opt.x[:lh._xi_slice()[0]], opt.x[lh._xi_slice()[1]:])).to(torch.float64)
         allh = plan.comm.all_gather(hyp)
         assert all(torch.equal(allh[0], h) for h in allh)
-    bad = {k: v for k, v in errs.items() if not v < (1e-7 if k in ("mgvi_draw", "geovi_update") else tol)}
+    # CG trajectories amplify rounding differences (8 iterations here); the hyper-parameter-only system (frozen excitations)
+    # is the worst conditioned of them
+    lim = lambda k: 1e-5 if k == "frozen_draw_cfxi" else 1e-7 if k in ("mgvi_draw", "geovi_update") or k.startswith("frozen_draw") else tol
+    bad = {k: v for k, v in errs.items() if not v < lim(k)}
     assert not bad, bad
     return errs
 
