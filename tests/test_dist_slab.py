@@ -159,6 +159,19 @@ def slab_check(rt, shape, dist_, lh_kind="gauss", seed=3, tol=1e-10):
         hyp = torch.cat((opt.x[:lh._xi_slice()[0]], opt.x[lh._xi_slice()[1]:])).to(torch.float64)
         allh = plan.comm.all_gather(hyp)
         assert all(torch.equal(allh[0], h) for h in allh)
+    if lh_kind == "gauss":
+        # whole VI iteration in the reference's default mode (geoVI) on the slab-decomposed field: runs, replicated leaves agree
+        smp_kl, st_kl = nb.optimize_kl(lh, pl.clone(), key=11, n_total_iterations=1, n_samples=1,
+                                       draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=10)),
+                                       nonlinearly_update_kwargs=dict(minimize_kwargs=dict(xtol=1e-3, maxiter=1, cg_kwargs=dict(maxiter=5))),
+                                       kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-3, maxiter=2, cg_kwargs=dict(maxiter=5))),
+                                       sample_mode="nonlinear_resample")
+        assert st_kl.nit == 1 and len(smp_kl) == 2
+        hyp = torch.cat((smp_kl.pos[:lh._xi_slice()[0]], smp_kl.pos[lh._xi_slice()[1]:])).to(torch.float64)
+        allh = plan.comm.all_gather(hyp)
+        assert all(torch.equal(allh[0], h) for h in allh)
+        msg = nb.OptimizeVI(lh, 1).get_status_message(smp_kl, st_kl, name="T")
+        assert "Likelihood residual(s)" in msg and "cfxi" in msg
     # CG trajectories amplify rounding differences (8 iterations here); the hyper-parameter-only system (frozen excitations)
     # is the worst conditioned of them
     lim = lambda k: 1e-5 if k == "frozen_draw_cfxi" else 1e-7 if k in ("mgvi_draw", "geovi_update") or k.startswith("frozen_draw") else tol
