@@ -176,7 +176,7 @@ class OptimizeVI:
         elif n_samples != n_keys and sample_mode.lower().endswith("_sample"):
             sample_mode = sample_mode.replace("_sample", "_resample")
         if n_samples == 0:
-            return Samples(pos=samples.pos, samples=None, keys=None), None
+            return samples, 0          # "Do nothing for MAP" (:530-531): the samples object passes through unchanged
         if sample_mode.lower() in ("linear_resample", "nonlinear_resample"):
             k_smpls = random_split(key, n_samples)       # :507
             samples, st_smpls = self.draw_linear_samples(samples.pos, k_smpls, point_estimates=point_estimates, **draw_linear_kwargs)

@@ -36,6 +36,10 @@ def test_point_estimates_and_constants(rt):
     vc.check_point_estimates(rt, "g3d_8x8x8", frozen=("cfzeromode", "cfax1loglogavgslope", "cfax1flexibility"))
 
 
+def test_map_and_schedules(rt):
+    vc.check_map_and_schedules(rt)
+
+
 def test_nonlinear_update(rt):
     vc.check_nonlinear_update(rt)
 

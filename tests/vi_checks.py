@@ -240,3 +240,21 @@ def check_optimize_kl(rt, tmpdir, name="g2d_16x16", comm=None):
         assert "#(Nonlinear sampling steps)" in txt and "Likelihood residual(s):" in txt and "Prior residual(s):" in txt
         assert txt.count("reduced Chi²:") == 2 * (1 + len(lh.layout.keys))
     return samples2, state2
+
+
+def check_map_and_schedules(rt, name="g2d_16x16"):
+    """n_samples = 0 is a MAP run (optimize_kl.py:488-489, 530-531); n_samples / sample_mode may be callables of the
+    iteration index (:166-170); the MAP energy agrees with the oracle's Newton-CG on the Hamiltonian."""
+    c, g, lh, olh, lay = _setup(rt, name)
+    pos0 = 0.1 * lh.layout.random(7, torch.float64, rt.device)
+    kmk = dict(xtol=1e-6, maxiter=6, cg_kwargs=dict(maxiter=30))
+    s, st = nb.optimize_kl(lh, pos0, key=1, n_total_iterations=1, n_samples=0, kl_kwargs=dict(minimize_kwargs=kmk))
+    assert st.nit == 1 and len(s) == 0 and st.sample_state == 0
+    opos, oopt = oracle.kl_minimize(olh, lay.unpack(t2n(pos0)), [], minimize_kwargs=kmk)
+    assert oopt.nit == st.minimization_state.nit
+    assert abs(st.minimization_state.fun - oopt.fun) <= 1e-9 * abs(oopt.fun)
+    assert rel_err(t2n(s.pos), lay.pack(opos)) < 1e-7
+    s, st = nb.optimize_kl(lh, pos0, key=1, n_total_iterations=2, n_samples=lambda i: 1 if i < 1 else 2,
+                           sample_mode=lambda i: "linear_resample", draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=30)),
+                           kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=20))))
+    assert st.nit == 2 and len(s) == 4
