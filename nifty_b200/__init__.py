@@ -18,3 +18,4 @@ from .evi import (Samples, concatenate_zip, draw_linear_residual, draw_residual,
 from .optimize_kl import OptimizeVI, OptimizeVIState, get_status_message, optimize_kl  # noqa: F401
 from .minisanity import ChiSqStats, minisanity, reduced_residual_stats  # noqa: F401
 from .tree_math import get_map, lmap, norm, size, smap, vdot, where, zeros_like  # noqa: F401
+from .evidence_lower_bound import estimate_evidence_lower_bound  # noqa: F401

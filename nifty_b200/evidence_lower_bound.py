@@ -1,0 +1,191 @@
+"""``estimate_evidence_lower_bound`` with the interface of ``nifty/re/evidence_lower_bound.py`` (eigenvalue path).
+
+ELBO = -<H(xi)>_samples + (N + Tr log Lambda) / 2 with Lambda the inverse of the metric ``M + 1`` at the mean
+(:414-700).  ``Tr log Lambda = -sum_i log lambda_i`` over the eigenvalues of ``M + 1``; all but ``min(#data, #latent)``
+of them equal one, the largest ones are found with ARPACK in batches, each batch on the operator projected onto the
+complement of the eigenvectors found so far (:176-411), and the unresolved tail enters ``lower_error`` (:826-832).
+
+Every operator application is one fused metric-vector product on the device (``nb200_metric`` with the identity added,
+or ``nb200_lsm`` + ``nb200_rsm`` for the data-space operator ``R M^(1/2) ... `` of :154-173); SciPy only sees a
+``LinearOperator`` on host vectors.  The stochastic-Lanczos variants of the reference (``trace_log_method="slq"``,
+``analytic_prior_term``, Gauss-Radau bounds) are not provided here and raise.
+"""
+
+from __future__ import annotations
+
+import logging
+import os
+from typing import Optional
+
+import numpy as np
+import scipy.linalg as slg
+import scipy.sparse.linalg as ssl
+import torch
+
+from .evi import Samples
+from .likelihood import LikelihoodWithModel
+
+logger = logging.getLogger("nifty_b200")
+
+
+def _orthonormality_error(vecs: np.ndarray, n_probes: int) -> float:
+    """max |V^T V p - p| over a few random p (:100-109)."""
+    if vecs.size == 0:
+        return 0.0
+    k = vecs.shape[1]
+    probes = np.random.default_rng(0).standard_normal((k, min(n_probes, k)))
+    return float(np.max(np.abs(vecs.conj().T @ (vecs @ probes) - probes)))
+
+
+def _deflated(op: ssl.LinearOperator, vecs: Optional[np.ndarray]) -> ssl.LinearOperator:
+    """P op P with P = 1 - V V^T (:28-65): the spectrum of ``op`` without the directions already found."""
+    if vecs is None:
+        return op
+
+    def proj(x):
+        return x - vecs @ (vecs.conj().T @ x)
+
+    return ssl.LinearOperator(shape=op.shape, dtype=op.dtype, matvec=lambda x: proj(op.matvec(proj(x))))
+
+
+def _largest_eigenvalues(op, size, n_eigenvalues, tot_dofs, *, min_lh_eval, eigenvalue_shift, solver_shift, n_batches, tol,
+                         early_stop, verbose, output_directory, prefix, orthonormalize, every, threshold, n_probes):
+    """The ``n_eigenvalues`` largest eigenvalues of ``op`` (:176-411): dense when all relevant ones are requested,
+    otherwise ARPACK batch by batch with deflation, stopping early once the smallest one found is within
+    ``min_lh_eval`` of the value every remaining eigenvalue has (``eigenvalue_shift``)."""
+    if n_eigenvalues > tot_dofs:
+        raise ValueError("Number of requested eigenvalues exceeds the number of relevant degrees of freedom!")
+    if n_eigenvalues <= 0:
+        return np.asarray([], dtype=np.float64), None
+
+    def save(vals, vecs):
+        if output_directory is None:
+            return
+        d = output_directory or "."
+        os.makedirs(d, exist_ok=True)
+        np.save(os.path.join(d, f"{prefix}_eigenvalues.npy"), vals)
+        if vecs is not None:
+            np.save(os.path.join(d, f"{prefix}_eigenvectors.npy"), vecs)
+
+    if tot_dofs == n_eigenvalues:
+        if verbose:
+            logger.info(f"Computing all {tot_dofs} relevant eigenvalues.")
+        dense = np.column_stack([op.matvec(e) for e in np.identity(size)])
+        vals, vecs = slg.eigh(dense, subset_by_index=[size - tot_dofs, size - 1])
+        order = np.argsort(-vals)
+        save(vals[order], vecs[:, order])
+        return vals[order], vecs[:, order]
+    base, rem = divmod(n_eigenvalues, n_batches)
+    batches = [b for b in [base + 1] * rem + [base] * (n_batches - rem) if b > 0]
+    solver_op = op if solver_shift == 0.0 else ssl.LinearOperator(shape=op.shape, dtype=op.dtype,
+                                                                   matvec=lambda x: op.matvec(x) + solver_shift * x)
+    vals, vecs = None, None
+    for count, batch in enumerate(batches, start=1):
+        if verbose:
+            logger.info(f"\nNumber of eigenvalues being computed: {batch}")
+        bv, bw = ssl.eigsh(_deflated(solver_op, vecs), k=batch, tol=tol, return_eigenvectors=True, which="LM")
+        bv = np.real_if_close(bv - solver_shift)
+        order = np.argsort(-bv)
+        bv, bw = bv[order], bw[:, order]
+        vals = bv if vals is None else np.concatenate((vals, bv))
+        vecs = bw if vecs is None else np.hstack((vecs, bw))
+        if orthonormalize:
+            err = _orthonormality_error(vecs, n_probes) if threshold is not None else None
+            if (err is not None and err > threshold) or count % every == 0:
+                vecs, _ = np.linalg.qr(vecs)
+        save(vals, vecs)
+        if verbose:
+            logger.info(f"Eigenvalue progress: {vals.size}/{n_eigenvalues}")
+        if early_stop and abs(eigenvalue_shift - np.min(vals)) < min_lh_eval:
+            break
+    return vals, vecs
+
+
+def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samples, n_eigenvalues, *, compute_all=False,
+                                  min_lh_eval=1e-3, n_batches=10, tol=0.0, verbose=True, metric_jit=True,
+                                  output_directory: Optional[str] = None, save_eigensystem_prefix="metric",
+                                  resume_eigenvectors=None, resume_eigenvalues=None, orthonormalize_eigenvectors=True,
+                                  orthonormalize_every_n_batches=8, orthonormalize_threshold=1e-6, orthonormalize_n_probes=2,
+                                  trace_log_method="eigsh", trace_log_space="signal", analytic_prior_term=False, **slq_options):
+    """Returns ``(elbo_samples, stats)`` (:414-1042, eigenvalue path).  ``stats`` holds ``elbo_mean``, ``elbo_std``,
+    ``elbo_se``, ``elbo_up``, ``elbo_lw`` and ``lower_error`` with the reference's definitions (:959-1005).
+
+    Differences from the reference's signature: ``output_directory`` defaults to ``None`` (the reference's default ``""``
+    writes the eigensystem into the working directory); resuming from a stored eigensystem and the SLQ options raise."""
+    if not isinstance(samples, Samples):
+        raise TypeError("samples attribute should be of type `Samples`.")
+    if not isinstance(likelihood, LikelihoodWithModel):
+        raise TypeError("likelhood is not an instance of `Likelihood`.")
+    trace_log_method, trace_log_space = trace_log_method.lower(), trace_log_space.lower()
+    if trace_log_method not in ("eigsh", "slq"):
+        raise ValueError("trace_log_method must be 'eigsh' or 'slq'.")
+    if trace_log_space not in ("auto", "signal", "data"):
+        raise ValueError("trace_log_space must be 'auto', 'signal', or 'data'.")
+    if trace_log_method == "slq" or analytic_prior_term or any(v is not None and v is not False for v in slq_options.values()):
+        raise NotImplementedError("the stochastic-Lanczos trace estimators are not provided on the B200 path (trace_log_method='eigsh' is)")
+    if resume_eigenvectors is not None or resume_eigenvalues is not None:
+        raise NotImplementedError("resuming from a stored eigensystem is not supported on the B200 path")
+    if likelihood.signal.cf.plan.dist:
+        raise NotImplementedError("estimate_evidence_lower_bound on slab-decomposed fields is not supported")
+    if orthonormalize_eigenvectors and (not isinstance(orthonormalize_every_n_batches, int) or orthonormalize_every_n_batches < 1):
+        raise ValueError("orthonormalize_every_n_batches must be a positive integer.")
+
+    rt, dtype = likelihood.rt, likelihood.dtype
+    pos = samples.pos
+    lin, _ = likelihood.lin_at(pos)
+    metric_size = int(likelihood.layout.size)
+    data_shape = tuple(likelihood.signal.target_shape)
+    n_data = int(np.prod(data_shape))
+    n_relevant = min(n_data, metric_size)
+    use_data = trace_log_space == "data" or (trace_log_space == "auto" and n_data <= metric_size)
+
+    def to_dev(x, shape):
+        return rt.asarray(np.ascontiguousarray(x, dtype=np.float64).reshape(shape), dtype)
+
+    if use_data:      # u -> RSM(LSM(u)) on data vectors; eigenvalues of M are those of this operator (:154-173)
+        op_size, eig_shift, solver_shift, log_np = n_data, 0.0, 1.0, np.log1p
+
+        def matvec(x):
+            return lin.rsm(lin.lsm(to_dev(x, data_shape), scaled=True), scaled=True).reshape(-1).to(torch.float64).cpu().numpy()
+    else:
+        op_size, eig_shift, solver_shift, log_np = metric_size, 1.0, 0.0, np.log
+
+        def matvec(x):
+            return lin.metric(to_dev(x, (metric_size,)), add_identity=True).to(torch.float64).cpu().numpy()
+    op = ssl.LinearOperator(shape=(op_size, op_size), dtype=np.float64, matvec=matvec)
+
+    if compute_all:
+        n_eigenvalues = n_relevant
+    if not isinstance(n_eigenvalues, (int, np.integer)):
+        raise TypeError("n_eigenvalues must be an integer.")
+    if n_eigenvalues < 0:
+        raise ValueError("n_eigenvalues must be non-negative.")
+    if n_relevant > 0 and n_eigenvalues == 0:
+        raise ValueError("trace_log_method='eigsh' requires at least one eigenvalue. "
+                         "Use trace_log_method='slq' to estimate the full trace stochastically.")
+    prefix = f"{save_eigensystem_prefix}_{'data' if use_data else 'signal'}"
+    eigenvalues, _ = _largest_eigenvalues(
+        op, op_size, int(n_eigenvalues), n_relevant, min_lh_eval=min_lh_eval, eigenvalue_shift=eig_shift, solver_shift=solver_shift,
+        n_batches=n_batches, tol=tol, early_stop=not compute_all, verbose=verbose, output_directory=output_directory, prefix=prefix,
+        orthonormalize=orthonormalize_eigenvectors, every=orthonormalize_every_n_batches, threshold=orthonormalize_threshold,
+        n_probes=orthonormalize_n_probes)
+    if verbose:
+        logger.info(f"\nComputed {eigenvalues.size} largest eigenvalues (out of {n_relevant} relevant degrees of freedom).")
+
+    log_eigs = log_np(eigenvalues)
+    tr_log_lat_cov = -0.5 * float(np.sum(log_eigs))                                             # :826-827
+    lower_error = 0.5 * (n_relevant - log_eigs.size) * float(np.min(log_eigs)) if log_eigs.size else 0.0   # :828-832
+    posterior_contribution = tr_log_lat_cov + 0.5 * metric_size                                  # :956
+    pts = [samples[i] for i in range(len(samples))]
+    ham = [likelihood.energy(s) + 0.5 * likelihood.vdot(s, s) for s in pts]                      # StandardHamiltonian (:67-87)
+    elbo_samples = np.array([posterior_contribution - h for h in ham])
+    stats = {"lower_error": lower_error}
+    mean = float(np.mean(elbo_samples)) if len(pts) else float("nan")
+    std = float(np.std(elbo_samples, ddof=1)) if len(pts) > 1 else float("nan")
+    stats["elbo_lw"], stats["elbo_mean"], stats["elbo_up"] = mean - std - lower_error, mean, mean + std
+    stats["elbo_std"] = std
+    stats["elbo_se"] = std / np.sqrt(len(pts)) if len(pts) > 0 else 0.0
+    if verbose:
+        logger.info(f"\nELBO decomposition (in log units)\nELBO mean : {mean:.4e} (lower: {stats['elbo_lw']:.4e}, "
+                    f"upper: {stats['elbo_up']:.4e})\nELBO std  : {std:.4e}")
+    return elbo_samples, stats

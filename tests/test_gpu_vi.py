@@ -40,6 +40,10 @@ def test_map_and_schedules(rt):
     vc.check_map_and_schedules(rt)
 
 
+def test_evidence_lower_bound(rt):
+    vc.check_elbo(rt, "g2d_8x32")
+
+
 def test_nonlinear_update(rt):
     vc.check_nonlinear_update(rt)
 

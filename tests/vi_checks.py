@@ -258,3 +258,51 @@ def check_map_and_schedules(rt, name="g2d_16x16"):
                            sample_mode=lambda i: "linear_resample", draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=30)),
                            kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=20))))
     assert st.nit == 2 and len(s) == 4
+
+
+def check_elbo(rt, name="g2d_16x16"):
+    """estimate_evidence_lower_bound (evidence_lower_bound.py:414-1042, eigenvalue path) against dense linear algebra on the
+    oracle's metric: ELBO_i = -1/2 sum log eig(M + 1) + L/2 - H(s_i)  (:826-832, 956-960), the unresolved tail in
+    `lower_error`; signal- and data-space operators give the same eigenvalues (:154-173)."""
+    import pytest
+    c, g, lh, olh, lay = _setup(rt, name)
+    rng = np.random.default_rng(12)
+    pos = lay.pack({k: 0.3 * v for k, v in lay.random(rng).items()})
+    res = 0.05 * np.stack([lay.pack(lay.random(rng)) for _ in range(3)])
+    smp = nb.Samples(pos=rt.asarray(pos, torch.float64), samples=rt.asarray(res, torch.float64))
+    L, nd = lay.size, int(np.prod(c["shape"]))
+    pd = lay.unpack(pos)
+    H = np.stack([lay.pack(olh.metric(pd, lay.unpack(e))) + e for e in np.eye(L)], axis=1)
+    eig = np.sort(np.linalg.eigvalsh(0.5 * (H + H.T)))[::-1]
+    nrel = min(nd, L)
+    ham = np.array([olh.energy(lay.unpack(pos + r)) + 0.5 * (pos + r) @ (pos + r) for r in res])
+    # all relevant eigenvalues: exact trace-log, no tail
+    el, st = nb.estimate_evidence_lower_bound(lh, smp, 0, compute_all=True, verbose=False)
+    want = -0.5 * np.sum(np.log(eig[:nrel])) + 0.5 * L - ham
+    np.testing.assert_allclose(el, want, rtol=1e-9)
+    assert st["lower_error"] == 0.0 and abs(st["elbo_mean"] - want.mean()) <= 1e-9 * abs(want.mean())
+    assert abs(st["elbo_std"] - want.std(ddof=1)) <= 1e-6 * want.std(ddof=1) + 1e-12
+    assert abs(st["elbo_up"] - (want.mean() + want.std(ddof=1))) < 1e-6 * abs(want.mean())
+    # the largest n by ARPACK in batches with deflation; the tail bound of :828-832
+    n = 24
+    for space in ("signal", "data"):
+        el2, st2 = nb.estimate_evidence_lower_bound(lh, smp, n, n_batches=5, min_lh_eval=1e-12, verbose=False, trace_log_space=space)
+        top = eig[:n]
+        want2 = -0.5 * np.sum(np.log(top)) + 0.5 * L - ham
+        np.testing.assert_allclose(el2, want2, rtol=1e-8)
+        assert abs(st2["lower_error"] - 0.5 * (nrel - n) * np.log(top.min())) <= 1e-7 * abs(st2["lower_error"]) + 1e-10
+        assert abs(st2["elbo_lw"] - (want2.mean() - want2.std(ddof=1) - st2["lower_error"])) <= 1e-7 * abs(want2.mean())
+    # early stop: once the smallest eigenvalue found is within min_lh_eval of 1 the remaining batches are skipped
+    el3, st3 = nb.estimate_evidence_lower_bound(lh, smp, 40, n_batches=40, min_lh_eval=float(eig[5] - 1.0 + 1e-9), verbose=False)
+    k = 6          # one eigenvalue per batch: the sixth is the first one within min_lh_eval of 1
+    want3 = -0.5 * np.sum(np.log(eig[:k])) + 0.5 * L - ham
+    np.testing.assert_allclose(el3, want3, rtol=1e-8)
+    # refused / invalid options
+    with pytest.raises(NotImplementedError):
+        nb.estimate_evidence_lower_bound(lh, smp, 4, trace_log_method="slq", verbose=False)
+    with pytest.raises(ValueError, match="at least one eigenvalue"):
+        nb.estimate_evidence_lower_bound(lh, smp, 0, verbose=False)
+    with pytest.raises(ValueError, match="exceeds"):
+        nb.estimate_evidence_lower_bound(lh, smp, nrel + 1, verbose=False)
+    with pytest.raises(TypeError):
+        nb.estimate_evidence_lower_bound(lh, t2n(smp.pos), 4, verbose=False)
