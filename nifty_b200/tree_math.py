@@ -60,6 +60,32 @@ def where(condition, x, y):
     return _map(lambda _, c, a, b: torch.where(torch.as_tensor(c), torch.as_tensor(a), torch.as_tensor(b)), ref, condition, x, y)
 
 
+def stack(arrays, axis=0):
+    """forest_math.py:115-116."""
+    return _map(lambda *el: torch.stack([torch.as_tensor(e) for e in el], dim=axis), *arrays)
+
+
+def unstack(stacked, axis=0):
+    """forest_math.py:119-127: a tuple of trees, one per entry along ``axis``."""
+    n = _leaves(stacked)[0].shape[axis]
+    return tuple(_map(lambda t: torch.as_tensor(t).select(axis, i), stacked) for i in range(n))
+
+
+def mean(forest):
+    """forest_math.py:213-223: leaf-wise mean of a sequence of trees (e.g. ``tuple(signal(s) for s in samples)``)."""
+    n = len(forest)
+    return _map(lambda *ts: sum(torch.as_tensor(t) for t in ts) / n, *forest)
+
+
+def mean_and_std(forest, correct_bias=True):
+    """forest_math.py:226-242: ``sqrt(<x^2> - <x>^2)``, times ``sqrt(n / (n - 1))`` if ``correct_bias``."""
+    n = len(forest)
+    m = mean(forest)
+    msq = mean(tuple(_map(lambda t: torch.as_tensor(t) ** 2, f) for f in forest))
+    scl = float(np.sqrt(n / (n - 1))) if correct_bias else 1.0
+    return m, _map(lambda a, b: scl * torch.sqrt(a - b ** 2), msq, m)
+
+
 def _sequential_map(fun: Callable, in_axes=0, out_axes=0):
     """``vmap``-like call signature, evaluated one batch element after the other (custom_map.py:106-160)."""
     def mapped(*args):

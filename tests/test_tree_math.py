@@ -40,3 +40,20 @@ def test_sequential_maps():
         nb.get_map("nope")
     with pytest.raises(TypeError):
         nb.get_map(3)
+
+
+def test_mean_std_stack():
+    rng = np.random.default_rng(1)
+    forest = tuple(_tree(rng) for _ in range(5))
+    m, sd = nb.mean_and_std(forest)
+    for k in forest[0]:
+        arr = np.stack([f[k].numpy() for f in forest])
+        np.testing.assert_allclose(m[k].numpy(), arr.mean(0), rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(sd[k].numpy(), arr.std(0, ddof=1), rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(nb.mean(forest)[k].numpy(), arr.mean(0), rtol=1e-13, atol=1e-15)
+    _, sd0 = nb.mean_and_std(forest, correct_bias=False)
+    np.testing.assert_allclose(sd0["c"].numpy(), np.stack([f["c"].numpy() for f in forest]).std(0), rtol=1e-10)
+    st = nb.stack(forest)
+    assert st["b"].shape == (5, 3, 2)
+    back = nb.unstack(st)
+    assert len(back) == 5 and all(torch.equal(back[i][k], forest[i][k]) for i in range(5) for k in forest[0])
