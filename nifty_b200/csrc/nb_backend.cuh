@@ -8,6 +8,7 @@
 #include <typeinfo>
 #include <vector>
 #include "nb_common.cuh"
+#include "nb_fft16.cuh"
 
 namespace nb {
 
@@ -27,6 +28,10 @@ inline void dev_zero(void* d, size_t n, stream_t) { std::memset(d, 0, n); }
 inline void stream_sync(stream_t) {}
 inline size_t max_smem_per_block() { return 227 * 1024; }
 inline int sm_count() { return 148; }
+inline void make_tma_desc(TmaDesc& d, const void* base, uint64_t row_len, uint64_t nrows, int box_rows) {
+  (void)nrows;
+  d.base = reinterpret_cast<const unsigned char*>(base); d.row_stride_bytes = (long)(row_len * 16); d.box_rows = box_rows; d.pad = 0;
+}
 
 template <class Body>
 inline void launch(int grid, int block, size_t smem, stream_t, const typename Body::Params& p) {
@@ -73,6 +78,28 @@ inline int sm_count() {
   return v;
 }
 
+// 2-D tensor map over a row-major matrix of 16-byte elements [nrows][row_len] (viewed as pairs of doubles), box =
+// one element x box_rows rows: the transposing gather of the staged passes (nb_passes2.cuh)
+inline void make_tma_desc(TmaDesc& d, const void* base, uint64_t row_len, uint64_t nrows, int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn enc = nullptr;
+  if (!enc) {
+    cudaDriverEntryPointQueryResult qr;
+    void* fn = nullptr;
+    NB_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) throw Error{"nb200: cuTensorMapEncodeTiled is not available in this driver"};
+    enc = reinterpret_cast<EncodeFn>(fn);
+  }
+  cuuint64_t dims[2] = {2 * row_len, nrows};
+  cuuint64_t strides[1] = {row_len * 16};
+  cuuint32_t box[2] = {2, (cuuint32_t)box_rows}, es[2] = {1, 1};
+  CUresult r = enc(&d.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error{"nb200: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"};
+  d.box_rows = box_rows; d.pad = 0;
+}
+
 // bodies may define `static constexpr int kMinBlocks` (register budget hint for ptxas)
 template <class B, class = void> struct MinBlocks { static constexpr int value = 1; };
 template <class B> struct MinBlocks<B, decltype((void)B::kMinBlocks)> { static constexpr int value = B::kMinBlocks; };
@@ -105,6 +132,8 @@ inline void launch(int grid, int block, size_t smem, stream_t s, const typename 
     NB_CUDA_CHECK(cudaFuncSetAttribute(nb_kernel<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[dev] = smem;
   }
+  static const bool trace = std::getenv("NB200_TRACE") != nullptr;     // developer aid: every launch on stderr
+  if (trace) std::fprintf(stderr, "[nb200] launch %s grid=%d block=%d smem=%zu\n", typeid(Body).name(), grid, block, smem);
   KernelTimer& kt = kernel_timer();
   if (kt.on) {
     KernelTimer::Rec r; r.name = typeid(Body).name();
@@ -117,6 +146,7 @@ inline void launch(int grid, int block, size_t smem, stream_t s, const typename 
     nb_kernel<Body><<<grid, block, smem, s>>>(p);
   }
   NB_CUDA_CHECK(cudaGetLastError());
+  if (trace) { cudaError_t e = cudaStreamSynchronize(s); std::fprintf(stderr, "[nb200]   -> %s\n", cudaGetErrorString(e)); }
   ++launch_counter();
 }
 #endif

@@ -179,6 +179,15 @@ template <> __device__ NB_INLINE cplx<float> ld_stream(const cplx<float>* p) {
 }
 #endif
 
+// Read-only streaming load (ld.global.nc, no L1 allocation) for data the kernel never writes: unlike ld_stream the
+// compiler may move it across stores, i.e. hoist the loads of a whole epilogue ahead of its first store.
+#if defined(NB_EMU)
+template <class T> inline T ld_ro(const T* p) { return *p; }
+#else
+__device__ NB_INLINE double ld_ro(const double* p) { double v; asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+__device__ NB_INLINE float ld_ro(const float* p) { float v; asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
+#endif
+
 // cooperative L2 prefetch of [p, p+bytes): turns the DRAM latency of a later phase into an L2 hit
 #ifdef NB_EMU
 inline void prefetch_l2(Ctx&, const void*, size_t) {}

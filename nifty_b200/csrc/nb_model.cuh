@@ -155,7 +155,7 @@ template <class T> struct Lin : LinBase {
   void amp_cotangent(stream_t st, T* out, const T* add, int p3_col, T scl_factor, bool use_p5_dot) {
     Plan<T>& P = *M->P;
     seg_sum(st, nullptr, nullptr);
-    vjp_chain(st, out, add, P.p3part.p + p3_col, P.c3.grid, P.p5part.p, use_p5_dot ? P.c5.grid : 0, scl_factor);
+    vjp_chain(st, out, add, P.p3part.p + p3_col, P.n3part, P.p5part.p, use_p5_dot ? P.n5part : 0, scl_factor);
   }
   EpiAdjoint<T> epi_adjoint(T* out, const T* add, bool want_dot) const {
     const Model<T>& m = *M;
@@ -177,7 +177,7 @@ template <class T> struct Lin : LinBase {
     op.lh_kind = m.lh_kind; op.nl_exp = m.nl_exp; op.data = m.data.p; op.w_scalar = m.w_scalar;
     op.w_arr = m.has_w_arr ? m.w_arr.p : nullptr; op.s_out = s.p; op.jl_out = jl.p; op.partials = P.p3part.p;
     if (grad) P.template run_p3<true, true>(st, op); else P.template run_p3<true, false>(st, op);
-    ReduceColsParams<T> pr; pr.partials = P.p3part.p; pr.n = P.c3.grid; pr.ncol = 2;
+    ReduceColsParams<T> pr; pr.partials = P.p3part.p; pr.n = P.n3part; pr.ncol = 2;
     pr.out0 = scal.p + SC_ENERGY; pr.out1 = scal.p + SC_SUMCOT;
     launch<ReduceColsBody<T>>(1, 256, 512, st, pr);
     if (grad) {
@@ -192,6 +192,7 @@ template <class T> struct Lin : LinBase {
   void metric(stream_t st, Lin<T>* b, const T* t, T* out, bool add_identity) {
     Model<T>& m = *M; Plan<T>& P = *m.P;
     if (!valid || !b->valid) throw Error{"nb200: linearisation not initialised (call nb200_lin_update)"};
+    ChainScope<T> chain(P, P.chain_ok);      // every pass of this sequence runs staged (row-major intermediates)
     b->amp_tangent(st, t);
     P.run_p1(st, b->pro_metric(t)); P.run_pc(st, false);
     PointOp<T> op = P.make_op(PM_METRIC);
@@ -242,7 +243,7 @@ template <class T> struct Lin : LinBase {
     const int l3 = chunk < 0 ? 0 : P.p3_line0[chunk], n3 = chunk < 0 ? -1 : P.p3_nlines[chunk];
     const int l5 = chunk < 0 ? 0 : P.p5_line0[chunk], n5 = chunk < 0 ? -1 : P.p5_nlines[chunk];
     auto reduce_p3 = [&](T* o0, T* o1) {
-      ReduceColsParams<T> pr; pr.partials = P.p3part.p; pr.n = P.c3.grid; pr.ncol = 2; pr.out0 = o0; pr.out1 = o1;
+      ReduceColsParams<T> pr; pr.partials = P.p3part.p; pr.n = P.n3part; pr.ncol = 2; pr.out0 = o0; pr.out1 = o1;
       launch<ReduceColsBody<T>>(1, 256, 512, st, pr);
     };
     switch (code) {
@@ -297,7 +298,7 @@ template <class T> struct Lin : LinBase {
         seg_sum(st, abar, nullptr);
         if (flag & 4) reduce_p3(nullptr, xs); else reduce_p3(xs, nullptr);   // bit 2: the gradient needs sum dE/df (column 1)
         if (flag & 1) {
-          ReduceColsParams<T> pd; pd.partials = P.p5part.p; pd.n = P.c5.grid; pd.ncol = 1; pd.out0 = xs + 1; pd.out1 = nullptr;
+          ReduceColsParams<T> pd; pd.partials = P.p5part.p; pd.n = P.n5part; pd.ncol = 1; pd.out0 = xs + 1; pd.out1 = nullptr;
           launch<ReduceColsBody<T>>(1, 256, 512, st, pd);
         } else {
           dev_zero(xs + 1, sizeof(T), st);

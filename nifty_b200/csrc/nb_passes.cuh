@@ -23,6 +23,7 @@
 #pragma once
 #include "nb_common.cuh"
 #include "nb_fft.cuh"
+#include "nb_fft16.cuh"
 
 namespace nb {
 
@@ -58,6 +59,7 @@ template <class T> NB_HH NB_INLINE bool ptr_aligned2(const T* p) { return (reint
 
 template <class T> struct ProPlain {
   static constexpr bool kUsesBins = false;
+  static constexpr bool kStaged = false;
   const T* x;
   bool aligned() const { return ptr_aligned2(x); }
   template <int NQ, bool AL> NB_HD NB_INLINE void batch(int, int, long off, int j, int lmr, cplx<T>* a) const {
@@ -79,6 +81,7 @@ template <class T> struct ProPlain {
 // a[b(k)] * xi_k   (forward model, correlated_field.py:911 with azm folded into the table)
 template <class T> struct ProAmp {
   static constexpr bool kUsesBins = true;
+  static constexpr bool kStaged = false;     // linearisation only (once per solve): generic body
   const T* xi; const int* idxf; const T* amp; FoldGeom fg;
   bool aligned() const { return ptr_aligned2(xi); }
   template <int NQ, bool AL> NB_HD NB_INLINE void batch(int o, int rr, long off, int j, int lmr, cplx<T>* a) const {
@@ -112,6 +115,7 @@ template <class T> struct ProAmp {
 // `ad` interleaves (A_b, du_b) so that one 2*sizeof(T) gather serves both.
 template <class T> struct ProMetric {
   static constexpr bool kUsesBins = true;
+  static constexpr bool kStaged = true;      // the tangent prologue of every metric-vector product
   const T* xi; const T* t; const int* idxf; const cplx<T>* ad; const T* scal;  // scal[0]=cj, scal[1]=da0
   T kappa; FoldGeom fg;
   bool aligned() const { return ptr_aligned2(xi) && ptr_aligned2(t); }
@@ -413,7 +417,7 @@ struct MirrorGeom {
   // half range [0, h_a] ("A" planes, stored first) and their mirrors n_a - a ("B" planes, stored behind
   // them in the same order; a = 0 and a = h_a have none).  skip = 1 if a = 0 is owned (its B is missing).
   int dist, a0, cA, skip;
-  NB_HD NB_INLINE int nlines() const { return (dist ? cA : (h_a + 1)) << lg_mid; }
+  NB_HH NB_INLINE int nlines() const { return (dist ? cA : (h_a + 1)) << lg_mid; }
   // returns false if the line is handled by its (stored) partner; lB = -1 for self-mirrored lines.
   // lA / lB index real lines of the (local) position / latent array: plane * n_mid + km.
   NB_HD NB_INLINE bool resolve(int l, int& lA, int& lB) const {
@@ -459,6 +463,22 @@ NB_HD NB_INLINE void RawLoader<T>::batch(int r, int j, int lmr, cplx<T>* a) cons
 #pragma unroll
   for (int q = 0; q < NQ; ++q) a[q] = ld_stream(lp + (q << lmr));
 }
+
+// lines already sitting in the (natural-order) line buffers: the first butterfly stage of the in-place transform reads
+// position j + q (n/R) and writes the swizzled slot of the same aligned group of 8, which only the 8 neighbouring
+// threads of the same warp touch in this stage -- all reads of the warp are ordered before its writes
+template <class T> struct SmemLoader {
+  const cplx<T>* s; int pitch; const LineInfo* li;
+  template <int NQ> NB_HD NB_INLINE void batch(int r, int j, int lmr, cplx<T>* a) const {
+    const cplx<T>* lp = s + r * pitch + j;
+    const bool act = !li || li[r].active;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) a[q] = act ? lp[q << lmr] : cmake<T>(0, 0);
+#ifndef NB_EMU
+    __syncwarp(__activemask());
+#endif
+  }
+};
 
 NB_HD NB_INLINE void fill_line_info(Ctx& ctx, LineInfo* li, const MirrorGeom& mg, int l0, int R) {
   NB_FOR(ctx, r, R) {
@@ -813,6 +833,10 @@ template <class T, class Epi> struct P5Params {
   int ahead;
   int line0;
   Epi epi;
+  // staged chain (nb_passes2.cuh): the lines are columns of the row-major output of the previous pass and are
+  // gathered into the line buffers by the TMA engine (gather != 0) instead of being read from `in`
+  int gather;
+  TmaDesc desc;
 };
 
 // MINB / PIPE (chosen by the host, profiles/r2_notes.md): long lines (64 KB CTAs) run two CTAs per SM with the pipelined
@@ -848,9 +872,34 @@ template <class T, class Epi, int MINB = 2, bool PIPE = true> struct P5Body {
     }
     if (p.ahead > 0 && ctx.bid + p.ahead < ctx.nblk)
       prefetch_l2(ctx, p.in + ((long)(ctx.bid + p.ahead) << (p.lg_R + p.lg_n)), sizeof(cplx<T>) << (p.lg_R + p.lg_n));
-    const cplx<T>* inp = p.in + (long)l0 * n;
-    RawLoader<T> ld{inp, (long)n, li, p.src_off, p.src_mul, p.in, l0};
-    fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
+    if (p.gather) {
+      // column l0 + r of the previous pass's row-major output -> line buffer r (natural order), box_rows rows per copy
+      Mbar* bar = reinterpret_cast<Mbar*>(s + (size_t)R * p.pitch);      // reduction scratch: free until the end
+      if (ctx.tid == 0) {
+        mbar_init(bar, 1);
+        const int br = p.desc.box_rows, nb = n / br;
+        unsigned bytes = 0;
+        for (int r = 0; r < R; ++r) if (li[r].active) bytes += (unsigned)(n * sizeof(cplx<T>));
+        mbar_expect(bar, bytes);
+        for (int r = 0; r < R; ++r) {
+          if (!li[r].active) continue;
+          for (int b = 0; b < nb; ++b) tma_gather(s + r * p.pitch + b * br, &p.desc, l0 + r, b * br, bar);
+        }
+      }
+      ctx.sync();
+      mbar_wait(bar, 0);
+#ifdef NB_EMU
+      std::vector<cplx<T>> copy(s, s + (size_t)R * p.pitch);      // the sequential emulation cannot order reads before writes
+      SmemLoader<T> ld{copy.data(), p.pitch, li};
+#else
+      SmemLoader<T> ld{s, p.pitch, li};
+#endif
+      fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
+    } else {
+      const cplx<T>* inp = p.in + (long)l0 * n;
+      RawLoader<T> ld{inp, (long)n, li, p.src_off, p.src_mul, p.in, l0};
+      fft_dif_load(ctx, s, p.fft, R, p.pitch, p.tw, p.lg_tw, ld);
+    }
     if (n == 1) {
       NB_FOR(ctx, r, R) if (li[r].active) pair(p, s + r * p.pitch, li[r], 0, 0, acc);
     } else if (Epi::BATCHED) {

@@ -6,6 +6,7 @@
 #include <vector>
 #include "nb_backend.cuh"
 #include "nb_passes.cuh"
+#include "nb_passes2.cuh"
 #include "nb_amp.cuh"
 
 namespace nb {
@@ -194,6 +195,17 @@ template <class T> std::vector<cplx<T>> make_twiddles(int n) {
 // L2 prefetch of later-phase / next-wave rows is OFF by default: measured on B200 it added 30-50 % DRAM
 // read traffic (lines evicted before use) for no gain (profiles/r1_notes.md); NB200_PREFETCH=1 re-enables it.
 inline bool p1m_enabled() { const char* e = std::getenv("NB200_P1M"); return !(e && e[0] == '0'); }   // developer knob: 0 = old P1 for every prologue
+// staged passes (nb_passes2.cuh) for line lengths 2^NB_FAST_LGMIN .. 4096; NB200_FAST=0 forces the generic bodies (A/B knob)
+#ifndef NB_FAST_LGMIN
+#define NB_FAST_LGMIN 5
+#endif
+inline bool fast_enabled() { const char* e = std::getenv("NB200_FAST"); return !(e && e[0] == '0'); }
+#define NB_LG_SWITCH(lg, CALL)                                                                     \
+  switch (lg) {                                                                                    \
+    case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break; case 8: CALL(8); break; \
+    case 9: CALL(9); break; case 10: CALL(10); break; case 11: CALL(11); break; case 12: CALL(12); break; \
+    default: throw Error{"nb200: internal: no staged pass for this line length"};                 \
+  }
 inline bool prefetch_disabled() { const char* e = std::getenv("NB200_PREFETCH"); return !(e && e[0] == '1'); }
 
 template <class T> struct Plan : PlanBase {
@@ -213,6 +225,15 @@ template <class T> struct Plan : PlanBase {
   FftDev f0, fm, fl, flh;   // line FFTs of length n0, nm, nl and nl/2
   DevBuf<T> W, p3part, p5part;
   PassCfg c1, cA, c3, cB, c5;
+  int n3part = 0, n5part = 0;   // number of per-CTA partial sums the last P3 / P5 launch wrote
+  bool fast = true;             // staged passes allowed (read once at plan creation)
+  bool staged_ok = false;       // float64, single GPU: the staged bodies apply
+  bool chain_ok = false;        // ... and every pass of the metric chain is covered (line lengths 32 .. 4096)
+  bool use_chain = false;       // set by the operator that runs the whole chain (ChainScope), read by run_*
+  bool p5f = false;             // NB200_P5F=1: register-resident last pass
+  bool l2_prefetch = false;     // bulk L2 prefetch of the next tile's epilogue rows: measured slower (+50 % DRAM reads); NB200_L2PF=1 enables
+  TmaDesc d_pca, d_p3, d_pcb, d_p5;
+  int sms = 148;
   int seg_lg_lpb = 2;   // lanes per mode bin in the segment sum (power of two near the mean bin population)
   int seg_grid() const { int bpb = 256 >> seg_lg_lpb; return (g.K + bpb - 1) / bpb; }
 
@@ -261,6 +282,7 @@ template <class T> struct Plan : PlanBase {
 
   void init(int device_, int ndim, const int64_t* shp, const double* dst, int hconv_, int rank_ = 0, int world_ = 1) {
     device = device_; hconv = hconv_;
+    fast = fast_enabled();
     dtype = sizeof(T) == 8 ? 1 : 0;
     hsign = hconv ? T(-1) : T(1);
     rank = rank_; world = world_; dist = world_ > 1;
@@ -356,8 +378,33 @@ template <class T> struct Plan : PlanBase {
       seg_lg_lpb = 0;
       while (seg_lg_lpb < 6 && (1 << (seg_lg_lpb + 1)) <= avg / 3.0) ++seg_lg_lpb;   // ~3-6 entries per lane
     }
-    p3part.alloc((size_t)2 * c3.grid + 64);
-    p5part.alloc((size_t)c5.grid + 32);
+    sms = sm_count();
+    p3part.alloc((size_t)2 * std::max(c3.grid, 2 * sms) + 64);
+    p5part.alloc((size_t)std::max(c5.grid, 2 * sms) + 32);
+    n3part = c3.grid; n5part = c5.grid;
+    staged_ok = fast && sizeof(T) == 8 && !dist;
+    {
+      const int lgc = lgl - 1, n_r1 = g.three ? g.nm : g.n0;
+      chain_ok = staged_ok && lgc >= NB_FAST_LGMIN && lgc <= 11 && n_r1 >= (F16_TILE >> lgc) && lg0 >= NB_FAST_LGMIN && lg0 <= 12 &&
+                 lgl >= 6 && lgl <= 12 && (!g.three || (lgm >= NB_FAST_LGMIN && lgm <= 12));
+      const bool chain_ok_shape = chain_ok;
+      // measured (profiles/r3_notes.md): the chain wins where the lines are long (4096^2: 0.623 vs 0.700 ms, 2048^2: 0.216
+      // vs 0.223); on short 3-D lines (256^3) the generic first / last passes are still faster (more resident warps for
+      // their streaming phases: 0.632 vs 0.592 ms), so those shapes keep the generic bodies
+      chain_ok = chain_ok && !g.three && lg0 >= 11 && lgl >= 11;
+      if (const char* e = std::getenv("NB200_CHAIN")) { if (e[0] == '0') chain_ok = false; else if (e[0] == '1') chain_ok = chain_ok_shape; }
+      if (const char* e = std::getenv("NB200_L2PF")) l2_prefetch = (e[0] == '1');
+      if (const char* e = std::getenv("NB200_P5F")) p5f = (e[0] == '1');
+    }
+    if (staged_ok) {
+      // gather descriptors: P3 / P5 read column l of [n_line][(h+1) n_mid]; PCa / PCb read column k of the rows of one plane
+      make_tma_desc(d_p3, g.three ? (const void*)s1() : (const void*)s0(), (uint64_t)(g.hl + 1) * g.nm, (uint64_t)g.n0, std::min(256, g.n0));
+      make_tma_desc(d_p5, s1(), (uint64_t)(g.h0 + 1) * g.nm, (uint64_t)g.nl, std::min(256, g.nl));
+      if (g.three) {
+        make_tma_desc(d_pca, s0(), (uint64_t)(g.hl + 1), (uint64_t)g.n0 * g.nm, std::min(256, g.nm));
+        make_tma_desc(d_pcb, s0(), (uint64_t)(g.h0 + 1), (uint64_t)g.nl * g.nm, std::min(256, g.nm));
+      }
+    }
     if (dist) set_chunks(1);
   }
   cplx<T>* s0() { return dist ? xS0 : S0.p; }
@@ -422,6 +469,25 @@ template <class T> struct Plan : PlanBase {
     } else {
       p.n_o = 1; p.n_r = g.n0; p.in_ostride = 0; p.in_rstride = g.nl; p.out_ostride = 0; p.out_kstride = g.n0;
     }
+    // staged chain (nb_passes2.cuh): mirror pairs of rows, register-resident half-length transform, row-major output
+    if constexpr (Pro::kStaged) {
+      if (use_chain) {
+        const int lgc = lgl - 1;
+        P1FParams<T, Pro> q;
+        q.lg_n = lgl; q.n_r = p.n_r; q.n_o = p.n_o; q.in_ostride = p.in_ostride; q.in_rstride = p.in_rstride;
+        q.tw = twl.p; q.lg_tw = lgl; q.out = s0(); q.pro = pro;
+        const int lpc = F16_TILE >> lgc;
+        q.ntiles = (g.three ? rows0 : 1) * (p.n_r / lpc);
+        const int grid = std::min(q.ntiles, 2 * sms);
+#define NB_CALL(LG) launch<P1FBody<T, Pro, LG>>(grid, F16_NT, StageLayout<T, LG>::BYTES, st, q)
+        switch (lgc) {
+          case 5: NB_CALL(5); break; case 6: NB_CALL(6); break; case 7: NB_CALL(7); break; case 8: NB_CALL(8); break;
+          case 9: NB_CALL(9); break; case 10: NB_CALL(10); break; default: NB_CALL(11); break;
+        }
+#undef NB_CALL
+        return;
+      }
+    }
     // prologues that read the mode-bin table share one lookup per mirror quad (P1MBody); needs >= 1 pair of rows per CTA
     if constexpr (Pro::kUsesBins) {
       if (c1.lg_R >= 1 && p.n_r >= 2 && p1m_enabled()) {
@@ -449,10 +515,37 @@ template <class T> struct Plan : PlanBase {
       p.n_o = g.h0 + 1; p.n_r = planes2; p.in_ostride = (long)planes2 * g.nm; p.in_rstride = g.nm;
       p.out_ostride = (long)g.nm * planes2; p.out_kstride = planes2;
     }
+    if (omap && n_o_chunk <= 0) return;
+    if (use_chain) {
+      PCFParams<T> q;
+      q.desc = second ? d_pcb : d_pca;
+      q.ncols = second ? g.h0 + 1 : g.hl + 1;
+      q.nlines = (long)(second ? g.nl : g.n0) * q.ncols;
+      q.omap = nullptr; q.tw = twm.p; q.out = s1();
+      const int lpc = F16_TILE >> lgm;
+      q.ntiles = (int)((q.nlines + lpc - 1) / lpc);
+      const int gridf = std::min(q.ntiles, 2 * sms);
+#define NB_CALL(LG) launch<PCFBody<T, LG>>(gridf, F16_NT, StageLayout<T, LG>::BYTES, st, q)
+      NB_LG_SWITCH(lgm, NB_CALL)
+#undef NB_CALL
+      return;
+    }
     int grid = c.grid;
-    if (omap) { if (n_o_chunk <= 0) return; grid = n_o_chunk * (p.n_r >> p.lg_R); }
+    if (omap) grid = n_o_chunk * (p.n_r >> p.lg_R);
     if (3 * (c.smem + 2048) <= size_t(100) * 1024) launch<PCBody<T, 3>>(grid, c.block, c.smem, st, p);
     else launch<PCBody<T, 2>>(grid, c.block, c.smem, st, p);
+  }
+  // (the staged launches live in non-template members: nvcc turned the same switch inside the run_p3 / run_p5 member
+  // templates into a host-side exit(1))
+  void launch_p3f(stream_t st, const P3FParams<T>& q, int gridf) {
+#define NB_CALL(LG) launch<P3FBody<T, LG>>(gridf, F16_NT, StageLayout<T, LG>::BYTES, st, q)
+    NB_LG_SWITCH(lg0, NB_CALL)
+#undef NB_CALL
+  }
+  void launch_p5f(stream_t st, const P5FParams<T>& q, int gridf) {
+#define NB_CALL(LG) launch<P5FBody<T, LG>>(gridf, F16_NT, StageLayout<T, LG>::BYTES, st, q)
+    NB_LG_SWITCH(lgl, NB_CALL)
+#undef NB_CALL
   }
   template <bool FWD, bool ADJ> void run_p3(stream_t st, const PointOp<T>& op, int line0 = 0, int nlines = -1) {
     P3Params<T> p;
@@ -463,7 +556,19 @@ template <class T> struct Plan : PlanBase {
     p.in = p3_in(); p.out = p3_out(); p.out_kstride = (long)planes2 * g.nm; p.op = op;
     p.src_off = dist ? src_off3.p : nullptr; p.src_mul = dist ? src_mul3.p : nullptr;
     const size_t sm = c3.smem + LINEINFO_BYTES;
+    n3part = c3.grid;
     if constexpr (FWD && ADJ) {
+      if (op.mode == PM_METRIC && use_chain) {
+        P3FParams<T> q;
+        q.desc = d_p3; q.mg = p.mg; q.tw = tw0.p; q.hsign = hsign; q.out = p.out;
+        q.line0 = line0; q.nlines = nlines >= 0 ? nlines : p.mg.nlines(); q.op = op; q.prefetch = l2_prefetch ? 1 : 0;
+        const int lpc = F16_TILE >> lg0;
+        q.ntiles = (q.nlines + lpc - 1) / lpc;
+        const int gridf = std::min(q.ntiles, 2 * sms);
+        n3part = gridf;
+        launch_p3f(st, q, gridf);
+        return;
+      }
       if (op.mode == PM_METRIC) {
         // measured: 3 CTAs/SM win for short lines (256^3: 145 vs 166 us) and for 4096-point lines (204 vs 213 us),
         // 2 CTAs/SM for two 2048-point lines per CTA (56 vs 60 us)
@@ -493,6 +598,25 @@ template <class T> struct Plan : PlanBase {
     p.hsign = hsign; p.in = s1(); p.epi = epi;
     p.src_off = dist ? src_off5.p : nullptr; p.src_mul = dist ? src_mul5.p : nullptr;
     const size_t sm5 = c5.smem + LINEINFO_BYTES;
+    n5part = c5.grid;
+    p.gather = 0;
+    if constexpr (Epi::BATCHED) {
+      // register-resident P5 (P5FBody): measured slower than the generic body (its epilogue is latency bound at 16 warps
+      // per SM), kept behind NB200_P5F=1; in a staged chain the generic body gathers its lines through the tensor map
+      if (p5f && staged_ok && lgl >= NB_FAST_LGMIN && lgl <= 12) {
+        P5FParams<T> q;
+        q.desc = d_p5; q.contig = use_chain ? nullptr : p.in;
+        q.mg = p.mg; q.hmid1 = p.hmid1; q.tw = twl.p; q.hsign = hsign; q.line0 = line0;
+        q.nlines = nlines >= 0 ? nlines : p.mg.nlines(); q.epi = epi; q.prefetch = l2_prefetch ? 1 : 0;
+        const int lpc = F16_TILE >> lgl;
+        q.ntiles = (q.nlines + lpc - 1) / lpc;
+        const int gridf = std::min(q.ntiles, 2 * sms);
+        n5part = gridf;
+        launch_p5f(st, q, gridf);
+        return;
+      }
+    }
+    if (use_chain) { p.gather = 1; p.desc = d_p5; }
     if (3 * (sm5 + 2048) <= size_t(100) * 1024) launch<P5Body<T, Epi, 3, false>>(grid5, c5.block, sm5, st, p);
     else launch<P5Body<T, Epi, 2, true>>(grid5, c5.block, sm5, st, p);
   }
@@ -518,6 +642,13 @@ template <class T> struct Plan : PlanBase {
     PointOp<T> op = make_op(PM_FIELD_OUT); op.natural = 1; op.pos_out = out; op.invV = T(1.0 / g.V); op.offset = offset;
     run_p3<true, false>(st, op);
   }
+};
+
+// marks an operator sequence whose passes all run staged (they share the row-major intermediate layouts)
+template <class T> struct ChainScope {
+  Plan<T>& P; bool prev;
+  ChainScope(Plan<T>& p, bool on) : P(p), prev(p.use_chain) { P.use_chain = on; }
+  ~ChainScope() { P.use_chain = prev; }
 };
 
 }  // namespace nb
