@@ -214,6 +214,21 @@ void nb200_cg_default_opts(nb200_cg_opts* opts);
 int nb200_cg_solve(nb200_lin* lin, nb200_lin* lin_b, void* stream, const void* j, void* x,
                    const nb200_cg_opts* opts, nb200_cg_result* result_host);
 
+/* ---- sample-averaged operator of the KL (optimize_kl.py:117-144 `_kl_met`, :90-114 `_kl_vg`) ----
+ * out = sum_i scale * J_i^T M_i J_i t  (+ t if identity_here), accumulated in place by the last-pass epilogues of the
+ * n_lins local linearisations (no extra vector passes), followed by `hook(user, out, n_elems, stream)` if given: the
+ * caller's in-stream all-reduce (SUM) over the ranks that hold the other sample points (NCCL through torch.distributed
+ * in the Python binding; XLA's all-reduce in a jax.ffi binding).  With scale = 1 / n_samples_total and identity_here
+ * on exactly one rank the all-reduced result is mean_i(metric(x_i, t) + t).  A rank without samples passes one
+ * linearisation with scale = 0. */
+typedef void (*nb200_reduce_hook)(void* user, void* buf, int64_t n_elems, void* stream);
+int nb200_metric_multi(nb200_lin** lins, int n_lins, double scale, int identity_here, void* stream, const void* t, void* out,
+                       nb200_reduce_hook hook, void* user);
+/* conjugate gradient (same rules / result as nb200_cg_solve) on that operator: the Newton-CG inner solve of
+ * kl_minimize (optimize_kl.py:540-591 -> optimize.py:335) without leaving the device; <d, q> is a fused reduction. */
+int nb200_cg_solve_multi(nb200_lin** lins, int n_lins, double scale, int identity_here, void* stream, const void* j, void* x,
+                         const nb200_cg_opts* opts, nb200_cg_result* result_host, nb200_reduce_hook hook, void* user);
+
 /* ---- fused vector algebra on flat latent vectors (tree_math vdot/norm/axpy; evi.py:136) ---------- */
 int nb200_vec_axpby(nb200_plan* plan, void* stream, int64_t n, double a, const void* x, double b, const void* y, void* out);
 int nb200_vec_dot(nb200_plan* plan, void* stream, int64_t n, const void* x, const void* y, double* out_host);

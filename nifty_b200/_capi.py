@@ -48,6 +48,8 @@ class CgResult(C.Structure):
     _fields_ = [("info", i32), ("nit", i32), ("nfev", i32), ("error", i32), ("energy", f64), ("gamma", f64)]
 
 
+REDUCE_HOOK = C.CFUNCTYPE(None, vp, vp, i64, vp)      # nb200_reduce_hook
+
 # name -> (restype, argtypes); kept in sync with include/nifty_b200.h (tests/test_abi.py checks it)
 SIGNATURES = {
     "nb200_last_error": (C.c_char_p, []),
@@ -93,6 +95,8 @@ SIGNATURES = {
     "nb200_normalized_residual": (C.c_int, [vp, vp, vp]),
     "nb200_cg_default_opts": (None, [C.POINTER(CgOpts)]),
     "nb200_cg_solve": (C.c_int, [vp, vp, vp, vp, vp, C.POINTER(CgOpts), C.POINTER(CgResult)]),
+    "nb200_metric_multi": (C.c_int, [C.POINTER(vp), C.c_int, f64, C.c_int, vp, vp, vp, vp, vp]),
+    "nb200_cg_solve_multi": (C.c_int, [C.POINTER(vp), C.c_int, f64, C.c_int, vp, vp, vp, C.POINTER(CgOpts), C.POINTER(CgResult), vp, vp]),
     "nb200_vec_axpby": (C.c_int, [vp, vp, i64, f64, vp, f64, vp, vp]),
     "nb200_vec_dot": (C.c_int, [vp, vp, i64, vp, vp, C.POINTER(f64)]),
     "nb200_vec_stats": (C.c_int, [vp, vp, i64, vp, C.POINTER(f64)]),

@@ -607,3 +607,79 @@ class Lin:
         self.rt.api.call("nb200_cg_solve", self._h, other._h if other is not None else None, self.rt.stream(),
                          self.rt.ptr(j), self.rt.ptr(x), C.byref(o), C.byref(res))
         return x, res
+
+
+# -- sample-averaged operator of the KL on the device (nb200_metric_multi / nb200_cg_solve_multi) -------------------
+class _DevView:
+    """`__cuda_array_interface__` view of a device buffer handed to a reduction hook by the library."""
+
+    def __init__(self, ptr, n, dtype):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8" if dtype == torch.float64 else "<f4",
+                                         "data": (int(ptr), False), "version": 2}
+
+
+def make_reduce_hook(rt: "Runtime", dtype, reduce_fn):
+    """ctypes callback for `nb200_reduce_hook`: `reduce_fn(tensor)` receives a tensor aliasing the library's buffer and
+    must enqueue an in-place SUM all-reduce on the current stream (torch.distributed does).  Returns None if
+    `reduce_fn` is None.  The caller keeps the returned object alive for the duration of the call."""
+    if reduce_fn is None:
+        return None
+    from ._capi import REDUCE_HOOK
+
+    def _hook(user, buf, n, stream):
+        if rt.device.type == "cuda":
+            t = torch.as_tensor(_DevView(buf, n, dtype), device=rt.device)
+        else:       # host emulation (tests): the buffer is host memory
+            import numpy as np
+            ctype = C.c_double if dtype == torch.float64 else C.c_float
+            t = torch.from_numpy(np.ctypeslib.as_array((ctype * n).from_address(buf)))
+        reduce_fn(t)
+
+    return REDUCE_HOOK(_hook)
+
+
+def _lin_array(lins):
+    arr = (C.c_void_p * len(lins))(*[l._h for l in lins])
+    return arr
+
+
+def metric_multi(lins, t, *, scale=1.0, identity_here=True, out=None, reduce_fn=None):
+    """out = sum_i scale * metric(lin_i, t) (+ t), all-reduced through `reduce_fn` -- `_kl_met` on the device."""
+    lin0 = lins[0]
+    rt = lin0.rt
+    out = lin0._vec() if out is None else out
+    hook = make_reduce_hook(rt, lin0.model.plan.dtype, reduce_fn)
+    rt.api.call("nb200_metric_multi", _lin_array(lins), len(lins), float(scale), int(identity_here), rt.stream(), rt.ptr(t), rt.ptr(out),
+                C.cast(hook, C.c_void_p) if hook is not None else None, None)
+    return out
+
+
+def cg_solve_multi(lins, j, x0=None, *, scale=1.0, identity_here=True, reduce_fn=None, absdelta=None, resnorm=None, norm_ord=None,
+                   tol=1e-5, atol=0.0, miniter=None, maxiter=None, raise_nonposdef=True, check_every=4, frozen=None):
+    """`_cg` on the sample-averaged operator, on the device (see :meth:`Lin.cg_solve` for the arguments)."""
+    lin0 = lins[0]
+    rt = lin0.rt
+    o = CgOpts()
+    rt.api.lib.nb200_cg_default_opts(C.byref(o))
+    o.absdelta = -1.0 if absdelta is None else float(absdelta)
+    o.resnorm = -1.0 if resnorm is None else float(resnorm)
+    o.tol, o.atol = float(tol), float(atol)
+    if norm_ord is None:
+        norm_ord = 2
+    o.norm_ord = {1: 1, 2: 2, np.inf: 0, float("inf"): 0}[norm_ord]
+    o.miniter = -1 if miniter is None else int(miniter)
+    o.maxiter = -1 if maxiter is None else int(maxiter)
+    o.raise_nonposdef = int(bool(raise_nonposdef))
+    o.check_every = int(check_every)
+    o.x0_is_zero = int(x0 is None)
+    fr = None
+    if frozen:
+        flat = [int(v) for r in frozen for v in r]
+        fr = (C.c_int64 * len(flat))(*flat)
+        o.n_frozen, o.frozen = len(flat) // 2, fr
+    x = lin0._vec() if x0 is None else x0.clone()
+    res = CgResult()
+    hook = make_reduce_hook(rt, lin0.model.plan.dtype, reduce_fn)
+    rt.api.call("nb200_cg_solve_multi", _lin_array(lins), len(lins), float(scale), int(identity_here), rt.stream(), rt.ptr(j), rt.ptr(x),
+                C.byref(o), C.byref(res), C.cast(hook, C.c_void_p) if hook is not None else None, None)
+    return x, res

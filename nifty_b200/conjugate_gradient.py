@@ -8,8 +8,11 @@ Two execution paths, same semantics (``info``: 0 converged, i > 0 stopped at ite
   ``nb200_cg_solve`` -- fused step kernels, curvature from the epilogue of the metric kernels, all
   stopping rules evaluated on the GPU, the host polls a status word every few iterations.  This is
   the B200 counterpart of ``static_cg`` (``lax.while_loop``).
-* any other callable: the generic host loop below (one host sync per scalar, like ``_cg``); used for
-  the sample-averaged KL metric, whose operator spans several linearisations / ranks.
+* ``mat`` is a :class:`SampleAveragedMetric` (the KL metric over several linearisations / ranks): same device
+  solve through ``nb200_cg_solve_multi`` -- the products accumulate in the last-pass epilogues, the all-reduce over the
+  ranks is enqueued in-stream by a hook, ``<d, q>`` is a fused reduction.
+* any other callable: the generic host loop below (one host sync per scalar, like ``_cg``); used for slab-decomposed
+  fields and user-supplied operators.
 """
 
 from __future__ import annotations
@@ -59,6 +62,27 @@ class HamiltonianMetric:
         return self._clear(self.lin.metric_pair(self.other, tm, add_identity=True))
 
 
+class SampleAveragedMetric:
+    """``t -> mean_i(lh.metric(x_i, t) + t)`` over the sample points of ALL ranks (``_kl_met``, optimize_kl.py:117-144):
+    the local linearisations ``lins`` are applied and accumulated on the device (``nb200_metric_multi``), ``reduce_fn``
+    is the in-stream all-reduce (None on a single rank).  ``_cg`` runs the whole solve on the device
+    (``nb200_cg_solve_multi``).  ``n_total``: number of sample points over all ranks; ``identity_here``: this rank adds
+    the ``+ t`` (exactly one rank does)."""
+
+    def __init__(self, lins, n_total, identity_here=True, reduce_fn=None, frozen=None, scale_zero=False):
+        self.lins, self.n_total, self.identity_here, self.reduce_fn = list(lins), int(n_total), bool(identity_here), reduce_fn
+        self.frozen = list(frozen) if frozen else None
+        self.scale = 0.0 if scale_zero else 1.0 / self.n_total
+
+    def __call__(self, t: torch.Tensor) -> torch.Tensor:
+        from ._runtime import metric_multi
+        out = metric_multi(self.lins, t, scale=self.scale, identity_here=self.identity_here, reduce_fn=self.reduce_fn)
+        if self.frozen:
+            for lo, hi in self.frozen:
+                out[lo:hi] = 0
+        return out
+
+
 def _norm(v: torch.Tensor, ord) -> float:
     if ord == 1:
         return float(v.abs().sum())
@@ -81,6 +105,19 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
         if mat.likelihood is None:
             raise ValueError("a slab-decomposed HamiltonianMetric needs its likelihood (for the distributed reductions)")
         vdot, vnorm = mat.likelihood.vdot, mat.likelihood.vnorm
+    elif isinstance(mat, SampleAveragedMetric):
+        from ._runtime import cg_solve_multi
+        x, res = cg_solve_multi(mat.lins, j, x0, scale=mat.scale, identity_here=mat.identity_here, reduce_fn=mat.reduce_fn,
+                                absdelta=absdelta, resnorm=resnorm, norm_ord=norm_ord, tol=tol, atol=atol, miniter=miniter, maxiter=maxiter,
+                                raise_nonposdef=_raise_nonposdef, check_every=check_every, frozen=mat.frozen)
+        nm = "CG" if name is None else name
+        if res.error == 1:
+            raise ValueError(f"{nm}: zero curvature")
+        if res.error == 2:
+            raise ValueError(f"{nm}: negative curvature")
+        if res.error == 3:
+            raise ValueError(f"{nm}: WARNING: energy increased")
+        return CGResults(x, int(res.nit), int(res.nfev), int(res.info), res.info == 0)
     elif isinstance(mat, HamiltonianMetric):
         x, res = mat.lin.cg_solve(j, x0, other=mat.other, absdelta=absdelta, resnorm=resnorm, norm_ord=norm_ord, tol=tol,
                                   atol=atol, miniter=miniter, maxiter=maxiter, raise_nonposdef=_raise_nonposdef,

@@ -78,8 +78,24 @@ template <class T> struct CgWork {
 };
 template <class T> CgWork<T>& cg_work() { static thread_local CgWork<T> w; return w; }
 
+// out = sum_i scale * M_i t (+ t on the caller that owns the identity), then the caller's reduction hook (an in-stream
+// all-reduce over the ranks that hold the other sample points): the sample-averaged metric of `_kl_met`
+// (nifty/re/optimize_kl.py:117-144) without leaving the device.  `ws` is unused scratch for future use.
 template <class T>
-int cg_solve(Lin<T>* lin, Lin<T>* lin_b, stream_t st, const T* j, T* x, const nb200_cg_opts& o, nb200_cg_result* res) {
+void multi_metric(Lin<T>** lins, int n, T scale, bool identity_here, stream_t st, const T* t, T* out, nb200_reduce_hook hook, void* user) {
+  if (n <= 0) throw Error{"nb200: multi_metric needs at least one linearisation (ranks without samples still pass one and scale 0)"};
+  const long L = lins[0]->M->am.L;
+  for (int i = 0; i < n; ++i) {
+    const T* add = (i == 0) ? (identity_here ? t : nullptr) : out;
+    lins[i]->metric_ex(st, lins[i], t, out, add, false, scale);
+  }
+  if (hook) hook(user, out, (int64_t)L, (void*)st);
+}
+
+template <class T>
+int cg_solve(Lin<T>* lin, Lin<T>* lin_b, stream_t st, const T* j, T* x, const nb200_cg_opts& o, nb200_cg_result* res,
+             Lin<T>** multi = nullptr, int n_multi = 0, T scale = T(1), bool identity_here = true, nb200_reduce_hook hook = nullptr,
+             void* user = nullptr) {
   Model<T>& m = *lin->M;
   const long L = m.am.L;
   CgWork<T>& w = cg_work<T>();
@@ -100,8 +116,10 @@ int cg_solve(Lin<T>* lin, Lin<T>* lin_b, stream_t st, const T* j, T* x, const nb
     for (int k = 0; k < o.n_frozen; ++k)
       if (o.frozen[2 * k + 1] > o.frozen[2 * k]) dev_zero(v + o.frozen[2 * k], (size_t)(o.frozen[2 * k + 1] - o.frozen[2 * k]) * sizeof(T), st);
   };
+  const bool own_dot = lin_b != nullptr || multi != nullptr;     // curvature <d, q> from a separate reduction
   auto op = [&](const T* t, T* out) {
-    if (!lin_b) { lin->metric(st, lin, t, out, true); clear_frozen(out); }
+    if (multi) { multi_metric<T>(multi, n_multi, scale, identity_here, st, t, out, hook, user); clear_frozen(out); }
+    else if (!lin_b) { lin->metric(st, lin, t, out, true); clear_frozen(out); }
     else {
       lin_b->metric(st, lin, t, w.tm.p, true); clear_frozen(w.tm.p);
       lin->metric(st, lin_b, w.tm.p, out, true); clear_frozen(out);
@@ -115,7 +133,7 @@ int cg_solve(Lin<T>* lin, Lin<T>* lin_b, stream_t st, const T* j, T* x, const nb
   p.resnorm = o.resnorm >= 0 ? (T)o.resnorm : T(-1);
   p.eps = T(6) * std::numeric_limits<T>::epsilon(); p.tiny = T(6) * std::numeric_limits<T>::min();
   p.norm_ord = norm_ord; p.miniter = (int)miniter; p.raise_nonposdef = o.raise_nonposdef;
-  p.curv_ptr = lin_b ? w.cgs.p + CG_CURV : lin->scal.p + SC_DOT;
+  p.curv_ptr = own_dot ? w.cgs.p + CG_CURV : lin->scal.p + SC_DOT;
   dev_zero(w.cgi.p, CGI_NINT * sizeof(int), st);
   dev_zero(w.cgs.p, CG_NSCAL * sizeof(T), st);
   if (o.absdelta < 0 && o.resnorm < 0) {
@@ -136,7 +154,7 @@ int cg_solve(Lin<T>* lin, Lin<T>* lin_b, stream_t st, const T* j, T* x, const nb
   if (host_cgi[CGI_STATUS] == CGS_RUNNING) {
     for (i = 1; i <= maxiter; ++i) {
       op(w.d.p, w.q.p);
-      if (lin_b) {
+      if (own_dot) {
         DotParams<T> dp; dp.n = L; dp.x = w.d.p; dp.y = w.q.p; dp.partials = w.partials.p; dp.counter = w.counter.p + 1; dp.out = w.cgs.p + CG_CURV;
         launch<DotBody<T>>(vgrid, 256, 512, st, dp);
       }
@@ -477,6 +495,33 @@ int nb200_cg_solve(nb200_lin* lin, nb200_lin* lin_b, void* stream, const void* j
   NB_DISPATCH(lin->dtype, TT, {
     return cg_solve<TT>(static_cast<Lin<TT>*>(lin->impl), lin_b ? static_cast<Lin<TT>*>(lin_b->impl) : nullptr, (stream_t)stream,
                         (const TT*)j, (TT*)x, *opts, result_host);
+  })
+  NB_CATCH
+}
+
+int nb200_metric_multi(nb200_lin** lins, int n_lins, double scale, int identity_here, void* stream, const void* t, void* out,
+                       nb200_reduce_hook hook, void* user) {
+  NB_TRY
+  if (!lins || n_lins < 1 || !t || !out) return fail("nb200_metric_multi: invalid argument");
+  for (int i = 1; i < n_lins; ++i) if (lins[i]->model != lins[0]->model) return fail("nb200_metric_multi: linearisations of different models");
+  NB_DISPATCH(lins[0]->dtype, TT, {
+    std::vector<Lin<TT>*> v(n_lins);
+    for (int i = 0; i < n_lins; ++i) v[i] = static_cast<Lin<TT>*>(lins[i]->impl);
+    multi_metric<TT>(v.data(), n_lins, (TT)scale, identity_here != 0, (stream_t)stream, (const TT*)t, (TT*)out, hook, user);
+  })
+  return 0;
+  NB_CATCH
+}
+int nb200_cg_solve_multi(nb200_lin** lins, int n_lins, double scale, int identity_here, void* stream, const void* j, void* x,
+                         const nb200_cg_opts* opts, nb200_cg_result* result_host, nb200_reduce_hook hook, void* user) {
+  NB_TRY
+  if (!lins || n_lins < 1 || !j || !x || !opts || !result_host) return fail("nb200_cg_solve_multi: invalid argument");
+  for (int i = 1; i < n_lins; ++i) if (lins[i]->model != lins[0]->model) return fail("nb200_cg_solve_multi: linearisations of different models");
+  NB_DISPATCH(lins[0]->dtype, TT, {
+    std::vector<Lin<TT>*> v(n_lins);
+    for (int i = 0; i < n_lins; ++i) v[i] = static_cast<Lin<TT>*>(lins[i]->impl);
+    return cg_solve<TT>(v[0], nullptr, (stream_t)stream, (const TT*)j, (TT*)x, *opts, result_host, v.data(), n_lins, (TT)scale,
+                        identity_here != 0, hook, user);
   })
   NB_CATCH
 }

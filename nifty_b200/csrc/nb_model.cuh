@@ -188,20 +188,26 @@ template <class T> struct Lin : LinBase {
     valid = true;
   }
 
-  // out = J_a^T l_a l_b J_b t (+ t); this == lin_a (cotangent side), b == tangent side
-  void metric(stream_t st, Lin<T>* b, const T* t, T* out, bool add_identity) {
+  // out = scale * J_a^T l_a l_b J_b t (+ add); this == lin_a (cotangent side), b == tangent side.
+  // `add` may be t (the "+ 1" of the Hamiltonian metric), `out` itself (accumulate the products of several
+  // linearisations in place: every entry is read and written by the same thread) or null; `want_dot` leaves
+  // <add, out> in scal[SC_DOT] (meaningful for add == t, scale == 1: the CG curvature).
+  void metric_ex(stream_t st, Lin<T>* b, const T* t, T* out, const T* add, bool want_dot, T scale) {
     Model<T>& m = *M; Plan<T>& P = *m.P;
     if (!valid || !b->valid) throw Error{"nb200: linearisation not initialised (call nb200_lin_update)"};
     ChainScope<T> chain(P, P.chain_ok);      // every pass of this sequence runs staged (row-major intermediates)
     b->amp_tangent(st, t);
     P.run_p1(st, b->pro_metric(t)); P.run_pc(st, false);
     PointOp<T> op = P.make_op(PM_METRIC);
-    op.invV = T(1.0 / P.g.V); op.jl_a = jl.p; op.jl_b = b->jl.p; op.partials = P.p3part.p;
-    if (m.am.has_scaling) { op.cshift_ptr = t + m.am.off_scl; op.cshift_scale = m.am.scl_b; }
+    op.invV = T(1.0 / P.g.V) * scale; op.jl_a = jl.p; op.jl_b = b->jl.p; op.partials = P.p3part.p;
+    if (m.am.has_scaling) { op.cshift_ptr = t + m.am.off_scl; op.cshift_scale = m.am.scl_b * scale; }
     P.template run_p3<true, true>(st, op);
     P.run_pc(st, true);
-    P.run_p5(st, epi_adjoint(out, add_identity ? t : nullptr, add_identity));
-    amp_cotangent(st, out, add_identity ? t : nullptr, 0, m.am.scl_b, add_identity);
+    P.run_p5(st, epi_adjoint(out, add, want_dot));
+    amp_cotangent(st, out, add, 0, m.am.scl_b, want_dot);
+  }
+  void metric(stream_t st, Lin<T>* b, const T* t, T* out, bool add_identity) {
+    metric_ex(st, b, t, out, add_identity ? t : nullptr, add_identity, T(1));
   }
 
   void rsm(stream_t st, const T* t, T* out_nat, bool scaled) {

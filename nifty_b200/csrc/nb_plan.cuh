@@ -603,7 +603,7 @@ template <class T> struct Plan : PlanBase {
     if constexpr (Epi::BATCHED) {
       // register-resident P5 (P5FBody): measured slower than the generic body (its epilogue is latency bound at 16 warps
       // per SM), kept behind NB200_P5F=1; in a staged chain the generic body gathers its lines through the tensor map
-      if (p5f && staged_ok && lgl >= NB_FAST_LGMIN && lgl <= 12) {
+      if (p5f && staged_ok && lgl >= NB_FAST_LGMIN && lgl <= 12 && epi.add != epi.out) {    // (its read-only loads must not alias the output)
         P5FParams<T> q;
         q.desc = d_p5; q.contig = use_chain ? nullptr : p.in;
         q.mg = p.mg; q.hmid1 = p.hmid1; q.tw = twl.p; q.hsign = hsign; q.line0 = line0;

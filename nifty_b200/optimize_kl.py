@@ -14,6 +14,7 @@
 
 from __future__ import annotations
 
+import inspect
 import logging
 import os
 import pickle
@@ -40,9 +41,12 @@ class OptimizeVIState(NamedTuple):
 
 
 def _getitem_at_nit(config, key, nit):
-    """Most kwargs may be callables of the iteration index (optimize_kl.py:166-170)."""
+    """Most kwargs may be callables of the iteration index (optimize_kl.py:166-170): only one-argument callables are
+    evaluated, exactly as in the reference."""
     c = config[key]
-    return c(nit) if callable(c) and not isinstance(c, (dict,)) else c
+    if callable(c) and len(inspect.getfullargspec(c).args) == 1:
+        return c(nit)
+    return c
 
 
 class _Comm:
@@ -63,11 +67,20 @@ class _Comm:
         return t
 
     def allgather(self, t: torch.Tensor):
+        """Per-rank tensors whose leading extent may differ between ranks (uneven sample sharding): the counts are
+        exchanged first, every rank pads to the maximum, the result is trimmed again."""
         if self.world == 1:
             return [t]
-        out = [torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(out, t.contiguous(), group=self.group)
-        return out
+        cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        self.dist.all_gather(cnts, cnt, group=self.group)
+        cnts = [int(c) for c in cnts]
+        m = max(cnts)
+        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[:t.shape[0]] = t
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(out, pad.contiguous(), group=self.group)
+        return [o[:c] for o, c in zip(out, cnts)]
 
 
 def get_status_message(samples, state, residual=None, *, name="", plan=None, layout=None, map="lmap", dist_leaves=()) -> str:
@@ -210,19 +223,43 @@ class OptimizeVI:
             acc[0] += lin.energy() + 0.5 * lh.vdot(x, x)
             acc[1] += 1.0
         self._n_active = len(pts)
+        for lin in self._lins[:len(pts)]:
+            lin._ever_updated = True
+        if len(pts) == 0 and not getattr(self._lins[0] if self._lins else None, "_ever_updated", False):
+            self._ensure_lins(1)                        # a rank without sample points keeps one linearisation (scale 0) for the device operator
+            self._lins[0].update(pos, want_grad=False)
+            self._lins[0]._ever_updated = True
         acc = self.comm.allreduce_sum(acc)
         n = float(acc[1])
+        self._n_total = int(round(n))
         return float(acc[0]) / n, (acc[2:] / n).to(lh.dtype)
 
+    def _kl_operator(self, frozen=None):
+        """The sample-averaged metric at the points of the last :meth:`kl_value_and_grad` as a device operator."""
+        from .conjugate_gradient import SampleAveragedMetric
+        lins = self._lins[:self._n_active]
+        none_here = len(lins) == 0                     # more ranks than sample points: contribute zero
+        if none_here:
+            self._ensure_lins(1)
+            lins = self._lins[:1]
+            if not getattr(lins[0], "_ever_updated", False):
+                raise RuntimeError("kl_metric: a rank without sample points needs one initialised linearisation")
+        reduce_fn = (lambda t: self.comm.allreduce_sum(t)) if self.comm.world > 1 else None
+        return SampleAveragedMetric(lins, self._n_total, identity_here=self.comm.rank == 0, reduce_fn=reduce_fn, frozen=frozen,
+                                    scale_zero=none_here)
+
     def kl_metric(self, tangents: torch.Tensor) -> torch.Tensor:
-        """``_kl_met`` at the points of the last :meth:`kl_value_and_grad`: mean of metric(x_i, t) + t."""
-        lh = self.likelihood
-        acc = torch.zeros(lh.layout.size + 1, dtype=torch.float64, device=lh.rt.device)
-        for lin in self._lins[:self._n_active]:
-            acc[1:] += lin.metric(tangents, add_identity=True).to(torch.float64)
-            acc[0] += 1.0
-        acc = self.comm.allreduce_sum(acc)
-        return (acc[1:] / float(acc[0])).to(lh.dtype)
+        """``_kl_met`` at the points of the last :meth:`kl_value_and_grad`: mean of metric(x_i, t) + t, accumulated on the
+        device (``nb200_metric_multi``); the all-reduce over the ranks is enqueued in-stream."""
+        if self.likelihood.signal.cf.plan.dist:         # slab-decomposed fields: phase-wise products, host accumulation
+            lh = self.likelihood
+            acc = torch.zeros(lh.layout.size + 1, dtype=torch.float64, device=lh.rt.device)
+            for lin in self._lins[:self._n_active]:
+                acc[1:] += lin.metric(tangents, add_identity=True).to(torch.float64)
+                acc[0] += 1.0
+            acc = self.comm.allreduce_sum(acc)
+            return (acc[1:] / float(acc[0])).to(lh.dtype)
+        return self._kl_operator()(tangents)
 
     def kl_minimize(self, samples: Samples, minimize: Callable = _newton_cg, minimize_kwargs=None, constants=(), **kwargs) -> OptimizeResults:
         """optimize_kl.py:540-591.  ``constants``: leaves held at their current value during the minimisation (:553-573):
@@ -243,6 +280,12 @@ class OptimizeVI:
                 fg(x)
             return clr(self.kl_metric(t))
 
+        def hessp_at(x):
+            # device operator for the inner CG of Newton-CG (optimize.py:335): linearisations of the last fg(x)
+            if state["x"] is None or state["x"].data_ptr() != x.data_ptr():
+                fg(x)
+            return self._kl_operator(frozen=frozen)
+
         kw = dict(minimize_kwargs or {})
         if frozen:
             kw.setdefault("_size", self.likelihood.global_size(frozen))
@@ -250,6 +293,8 @@ class OptimizeVI:
             kw.setdefault("vdot", self.likelihood.vdot)
             kw.setdefault("vnorm", self.likelihood.vnorm)
             kw.setdefault("_size", self.likelihood.global_size())
+        if not self.likelihood.signal.cf.plan.dist and minimize is _newton_cg:
+            kw.setdefault("hessp_at", hessp_at)          # KL-CG on the device (nb200_cg_solve_multi)
         return minimize(None, x0=samples.pos, fun_and_grad=fg, hessp=hessp, **kw)
 
     # -- driver -------------------------------------------------------------------------------------------
@@ -265,7 +310,7 @@ class OptimizeVI:
 
     def update(self, samples: Samples, state: OptimizeVIState, **kwargs):
         """One VI iteration (optimize_kl.py:672-729)."""
-        nit = state.nit + 1
+        nit = state.nit                                # schedules see the PRE-increment index (:691-701): 0 on the first iteration
         cfg = state.config
         key, sk = random_split(state.key, 2)           # :703, ticks every iteration
         kw = {k: _getitem_at_nit(cfg, k, nit) for k in ("n_samples", "sample_mode", "point_estimates", "draw_linear_kwargs",
@@ -275,7 +320,7 @@ class OptimizeVI:
         samples, st_smpls = self.draw_samples(samples, key=sk, **kw)
         kl_opt = self.kl_minimize(samples, constants=constants, **kl_kwargs)
         samples = samples.at(kl_opt.x)
-        state = state._replace(nit=nit, key=key, sample_state=st_smpls, minimization_state=kl_opt._replace(x=None, jac=None))
+        state = state._replace(nit=nit + 1, key=key, sample_state=st_smpls, minimization_state=kl_opt._replace(x=None, jac=None))
         return samples, state
 
     def run(self, samples: Samples, *, key, **kwargs):
@@ -283,6 +328,44 @@ class OptimizeVI:
         for _ in range(self.n_total_iterations):
             samples, state = self.update(samples, state)
         return samples, state
+
+
+def _samples_to_checkpoint(samples: Samples, likelihood, comm) -> Samples:
+    """``Samples`` with NumPy pytrees (the layout of the reference's pickled object, evi.py:385-396: ``pos`` a dict of
+    leaves, ``samples`` the residual leaves with a leading sample axis, ``keys``) holding the residuals of ALL ranks in
+    global sample order (rank r draws the keys r, r + W, ...; two mirrored residuals per key)."""
+    lay = likelihood.layout
+    pos = {k: v.detach().cpu().numpy() for k, v in lay.unpack(samples.pos).items()}
+    res = None
+    if samples.residuals is not None:
+        parts = comm.allgather(samples.residuals)
+        n_keys = 0 if samples.keys is None else len(samples.keys)
+        per_key = 2 if n_keys and sum(p.shape[0] for p in parts) == 2 * n_keys else 1
+        total = sum(p.shape[0] for p in parts)
+        full = np.empty((total, lay.size), dtype=parts[0].cpu().numpy().dtype)
+        for r, p in enumerate(parts):
+            pn = p.detach().cpu().numpy()
+            for i in range(pn.shape[0] // per_key):
+                g = (r + i * comm.world) * per_key
+                full[g:g + per_key] = pn[i * per_key:(i + 1) * per_key]
+        res = {k: np.stack([lay.unpack_numpy(full[i])[k] for i in range(total)]) for k in pos}
+    return Samples(pos=pos, samples=res, keys=samples.keys)
+
+
+def _samples_from_checkpoint(ck: Samples, likelihood, rank, world) -> Samples:
+    """Inverse of :func:`_samples_to_checkpoint` for THIS run's sharding (the checkpoint holds all samples, so the world
+    size may differ from the run that wrote it)."""
+    lay, dev, dt = likelihood.layout, likelihood.rt.device, likelihood.dtype
+    pos = torch.as_tensor(lay.pack_numpy(ck.pos), dtype=dt, device=dev)
+    res = None
+    if ck.residuals is not None:
+        total = next(iter(ck.residuals.values())).shape[0]
+        full = np.stack([lay.pack_numpy({k: v[i] for k, v in ck.residuals.items()}) for i in range(total)])
+        n_keys = 0 if ck.keys is None else len(ck.keys)
+        per_key = 2 if n_keys and total == 2 * n_keys else 1
+        idx = [g * per_key + s for g in range(rank, total // per_key, world) for s in range(per_key)]
+        res = torch.as_tensor(full[idx], dtype=dt, device=dev)
+    return Samples(pos=pos, samples=res, keys=ck.keys)
 
 
 def optimize_kl(likelihood: LikelihoodWithModel, position_or_samples, *, key, n_total_iterations: int, n_samples,
@@ -296,30 +379,35 @@ def optimize_kl(likelihood: LikelihoodWithModel, position_or_samples, *, key, n_
         likelihood, n_total_iterations, comm=comm, jit=jit, linear_minimizer_jit=linear_minimizer_jit,
         nonlinear_minimizer_jit=nonlinear_minimizer_jit, kl_map=kl_map, residual_map=residual_map, kl_reduce=kl_reduce,
         mirror_samples=mirror_samples, devices=devices)
-    rank = opt_vi.comm.rank
+    comm = opt_vi.comm
+    rank, world = comm.rank, comm.world
+    plan = likelihood.signal.cf.plan
+    if plan.dist and world > 1:
+        raise ValueError("a slab-decomposed field cannot be combined with sample sharding (`comm`): the slab ranks hold "
+                         "parts of ONE latent vector, not independent samples")
+    if plan.dist and odir is not None:
+        raise NotImplementedError("checkpointing (`odir`) is not available for slab-decomposed fields: every rank holds only "
+                                  "its slab of the excitations (gather them with plan.gather_latent and save explicitly)")
     last_fn = os.path.join(odir, "last.pkl") if odir is not None else None
+    # `resume` may be True/False or a path (optimize_kl.py:821-826)
+    resume_fn = resume if isinstance(resume, str) and os.path.isfile(resume) else last_fn
     samples = None
-    state = _optimize_vi_state
-    resume_fn = resume if isinstance(resume, str) else last_fn          # optimize_kl.py:830-839
+    if isinstance(position_or_samples, Samples):
+        samples = position_or_samples
+    else:
+        samples = Samples(pos=likelihood.signal.as_flat(position_or_samples), samples=None, keys=None)
+    state = None
     if resume and resume_fn is not None and os.path.isfile(resume_fn):
         with open(resume_fn, "rb") as f:
-            s_pos, s_res_all, s_keys, st = pickle.load(f)
-        dev, dt = likelihood.rt.device, likelihood.dtype
-        pos = torch.as_tensor(s_pos, dtype=dt, device=dev)
-        res = None
-        if s_res_all is not None:
-            res = torch.as_tensor(s_res_all[rank], dtype=dt, device=dev)
-        samples = Samples(pos=pos, samples=res, keys=s_keys)
-        state = st._replace(config=None)
-    if samples is None:
-        if isinstance(position_or_samples, Samples):
-            samples = position_or_samples
-        else:
-            samples = Samples(pos=likelihood.signal.as_flat(position_or_samples), samples=None, keys=None)
+            ck_samples, state = pickle.load(f)
+        samples = _samples_from_checkpoint(ck_samples, likelihood, rank, world)
     fresh = opt_vi.init_state(key, n_samples=n_samples, draw_linear_kwargs=draw_linear_kwargs,
                               nonlinearly_update_kwargs=nonlinearly_update_kwargs, kl_kwargs=kl_kwargs, sample_mode=sample_mode,
                               point_estimates=point_estimates, constants=constants)
-    state = fresh if state is None else state._replace(config=fresh.config)
+    state = _optimize_vi_state if _optimize_vi_state is not None else state      # an explicit state wins (:852)
+    state = fresh if state is None else state
+    if not state.config:                                                            # resumed / supplied states carry no config (:854-855)
+        state = state._replace(config=fresh.config)
     if odir is not None and rank == 0:
         os.makedirs(odir, exist_ok=True)
     sanity_fn = os.path.join(odir, "minisanity.txt") if odir is not None else None       # optimize_kl.py:803, 827
@@ -335,12 +423,10 @@ def optimize_kl(likelihood: LikelihoodWithModel, position_or_samples, *, key, n_
             with open(sanity_fn, "a") as f:
                 f.write("\n" + msg)
         if last_fn is not None:
-            gathered = None
-            if samples.residuals is not None:
-                gathered = [t.cpu().numpy() for t in opt_vi.comm.allgather(samples.residuals)]
+            ck = _samples_to_checkpoint(samples, likelihood, comm)
             if rank == 0:
-                with open(last_fn, "wb") as f:   # config is not pickled (callables), as in the reference (:871-875)
-                    pickle.dump((samples.pos.cpu().numpy(), gathered, samples.keys, state._replace(config={})), f)
+                with open(last_fn, "wb") as f:   # (Samples, OptimizeVIState) as in the reference; config is not pickled (:871-875)
+                    pickle.dump((ck, state._replace(config={})), f)
         if callback is not None:
             callback(samples, state)
     return samples, state

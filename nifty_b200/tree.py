@@ -40,6 +40,15 @@ class Layout:
     def unpack(self, vec: torch.Tensor) -> Dict[str, torch.Tensor]:
         return {k: vec[self.offsets[k]:self.offsets[k] + self.numel(k)].reshape(self.shapes[k]) for k in self.keys}
 
+    def unpack_numpy(self, vec: np.ndarray) -> Dict[str, np.ndarray]:
+        return {k: np.asarray(vec[self.offsets[k]:self.offsets[k] + self.numel(k)]).reshape(self.shapes[k]) for k in self.keys}
+
+    def pack_numpy(self, tree) -> np.ndarray:
+        out = np.empty(self.size, dtype=np.result_type(*[np.asarray(tree[k]).dtype for k in self.keys]))
+        for k in self.keys:
+            out[self.offsets[k]:self.offsets[k] + self.numel(k)] = np.asarray(tree[k]).reshape(-1)
+        return out
+
     def random(self, seed_or_rng, dtype, device) -> torch.Tensor:
         """Leaf-by-leaf N(0,1) draws in sorted-key order from a numpy Generator."""
         rng = seed_or_rng if isinstance(seed_or_rng, np.random.Generator) else np.random.default_rng(seed_or_rng)

@@ -296,3 +296,58 @@ def check_matern_variants(rt):
             assert abs(e - oe) <= 1e-10 * abs(oe), (kind, renorm)
             assert tree_err(grad, ograd) < 1e-10, (kind, renorm)
             assert tree_err(lh.metric(tp, tt), olh.metric(pos, tan)) < 1e-10, (kind, renorm)
+
+
+FULL_SIZE = {
+    # BASELINE.json configs at FULL size, hyper-parameters of SURVEY.md 8(d)
+    "cfg2_4096_gauss": dict(shape=(4096, 4096), distances=1.0 / 4096, offset_mean=0.0, offset_std=(1e-3, 1e-4), fluctuations=(1e-1, 5e-3),
+                            loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5), asperity=(0.5, 0.05), lh="gauss"),
+    "cfg3_256c_gauss": dict(shape=(256, 256, 256), distances=1.0 / 256, offset_mean=0.0, offset_std=(1e-3, 1e-4), fluctuations=(1e-1, 5e-3),
+                            loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5), asperity=(0.5, 0.05), lh="gauss"),
+    # misc/re/paper/minimal_benchmark.py:94-105 (the geoVI / Poisson configuration)
+    "cfg4_2048_poisson": dict(shape=(2048, 2048), distances=1.0 / 2048, offset_mean=2.0, offset_std=(0.1, 0.03), fluctuations=(1.0, 0.5),
+                              loglogavgslope=(-3.0, 0.2), flexibility=(1.0, 0.2), asperity=(0.5, 0.05), lh="poisson"),
+    # CPU-tier stand-ins of the same three configurations (the same code path of this check at oracle-friendly sizes)
+    "small_gauss": dict(shape=(64, 128), distances=1.0 / 64, offset_mean=0.0, offset_std=(1e-3, 1e-4), fluctuations=(1e-1, 5e-3),
+                        loglogavgslope=(-1.0, 1e-2), flexibility=(1.0, 0.5), asperity=(0.5, 0.05), lh="gauss"),
+    "small_poisson": dict(shape=(64, 64), distances=1.0 / 64, offset_mean=2.0, offset_std=(0.1, 0.03), fluctuations=(1.0, 0.5),
+                          loglogavgslope=(-3.0, 0.2), flexibility=(1.0, 0.2), asperity=(0.5, 0.05), lh="poisson"),
+}
+
+
+def check_config_vs_oracle(rt, name, tol=1e-10):
+    """BASELINE.json's configurations at their FULL size against the oracle on the same seeded inputs: energy, gradient,
+    metric-vector product and metric + 1 (the operator CG runs on) at 1e-10 relative -- the north-star parity bar."""
+    import time
+    c = FULL_SIZE[name]
+    shape = c["shape"]
+    t0 = time.time()
+    ocf = build_oracle(c)
+    osig = oracle.SignalOracle(ocf, "exp")
+    lay = oracle.Layout(osig.domain)
+    rng = np.random.default_rng(42)
+    truth = lay.random(rng)
+    if c["lh"] == "gauss":
+        data = osig(truth) + 0.1 * rng.standard_normal(shape)
+        olh = oracle.GaussianOracle(data, 100.0, osig)
+        g = dict(data=data, noise_cov_inv=100.0)
+    else:
+        data = rng.poisson(osig(truth)).astype(np.int64)
+        olh = oracle.PoissonianOracle(data, osig)
+        g = dict(data=data)
+    pos = {k: 0.1 * v for k, v in lay.random(np.random.default_rng(44)).items()}
+    tan = lay.random(np.random.default_rng(45))
+    lh = build_product_lh(c, g, rt)
+    tp = {k: torch.as_tensor(v) for k, v in pos.items()}
+    tt = {k: torch.as_tensor(v) for k, v in tan.items()}
+    e, grad = lh.energy_and_gradient(tp)
+    oe, ograd = olh.energy_and_gradient(pos)
+    errs = {"energy": abs(e - oe) / abs(oe), "gradient": tree_err(grad, ograd)}
+    om = olh.metric(pos, tan)
+    errs["metric"] = tree_err(lh.metric(tp, tt), om)
+    lin, _ = lh.lin_at(lh.signal.as_flat(tp))
+    m1 = lh.layout.unpack(lin.metric(lh.signal.as_flat(tt), add_identity=True))
+    errs["metric_plus_1"] = tree_err(m1, {k: om[k] + tan[k] for k in om})
+    for k, v in errs.items():
+        assert v < tol, (name, k, v)
+    return errs, time.time() - t0

@@ -112,3 +112,21 @@ def test_unsupported_shapes_fail_loudly(rt):
         nb.Plan((3, 3), 0.1, runtime=rt)
     with pytest.raises(nb.NB200Error):
         nb.Plan((4, 4, 4, 4), 0.1, runtime=rt)
+
+
+@pytest.mark.parametrize("name", ["small_gauss", "small_poisson"])
+def test_baseline_config_check_small(rt, name):
+    """The full-size check of the GPU tier (energy / gradient / metric / metric + 1 vs the oracle) at oracle-friendly sizes."""
+    pc.check_config_vs_oracle(rt, name)
+
+
+@pytest.mark.parametrize("shape,dist,kind", [((64, 128), (0.01, 0.02), "gauss"), ((512, 64), 0.1, "poisson"),
+                                             ((32, 128, 64), (0.1, 0.2, 0.3), "poisson")])
+def test_staged_chain_vs_oracle(rt, monkeypatch, shape, dist, kind):
+    """The staged metric chain (nb_passes2.cuh) forced on (the launch heuristic reserves it for long 2-D lines): P1F / PCF /
+    P3F, the tensor-map gather of the generic last pass and the register-resident last pass (NB200_P5F), 256 virtual
+    threads per block on the host."""
+    monkeypatch.setenv("NB200_CHAIN", "1")
+    pc.check_against_oracle(rt, shape, dist, lh_kind=kind)
+    monkeypatch.setenv("NB200_P5F", "1")
+    pc.check_against_oracle(rt, shape, dist, lh_kind=kind)

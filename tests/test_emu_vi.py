@@ -52,3 +52,17 @@ def test_kl_value_grad_metric(rt):
 
 def test_optimize_kl_and_resume(rt, tmp_path):
     vc.check_optimize_kl(rt, tmp_path)
+
+
+def test_final_kl_matches_oracle(rt):
+    """configs[0] in miniature: final KL of one optimize_kl iteration within 1e-10 of the oracle (north star)."""
+    assert vc.check_final_kl(rt, (32, 32), 4) <= 1e-10
+    assert vc.check_final_kl(rt, (16, 64), 2, scaling=(3.0, 1.0), noise_cov_inv=0.01) <= 1e-10
+
+
+def test_schedule_indices(rt):
+    vc.check_schedule_indices(rt)
+
+
+def test_kl_cg_on_device(rt):
+    vc.check_kl_cg_on_device(rt)

@@ -84,8 +84,8 @@ def test_p1_mirror_quads(rt, monkeypatch, lg_r):
 @pytest.mark.parametrize("shape,dist,kind", [((128, 128), 1.0 / 128, "gauss"), ((2048, 2048), 1.0 / 2048, "poisson"),
                                              ((4096, 4096), 1.0 / 4096, "gauss"), ((256, 256, 256), 1.0 / 256, "gauss")])
 def test_full_size_properties(rt, shape, dist, kind):
-    """BASELINE.json configs 1-4 at full size: Hartley round trip, metric symmetry / positivity /
-    LSM.RSM factorisation / linearity; 256^3 and 4096^2 are far beyond what the oracle can check."""
+    """BASELINE.json configs 1-4 at full size: Hartley round trip, Parseval, metric symmetry / positivity /
+    LSM.RSM factorisation / linearity (the oracle comparison at these sizes is the next test)."""
     plan = nb.Plan(shape, dist, runtime=rt)
     x = torch.randn(shape, dtype=torch.float64, device=rt.device, generator=torch.Generator(rt.device).manual_seed(1))
     back = plan.hartley(plan.hartley(x)) / x.numel()
@@ -95,6 +95,28 @@ def test_full_size_properties(rt, shape, dist, kind):
     assert abs(float((hx * hx).sum()) / x.numel() - float((x * x).sum())) < 1e-10 * float((x * x).sum())
     del plan, hx, back
     pc.check_metric_properties(rt, shape, dist, lh_kind=kind)
+
+
+@pytest.mark.parametrize("name", ["cfg2_4096_gauss", "cfg4_2048_poisson", "cfg3_256c_gauss", "small_gauss", "small_poisson"])
+def test_baseline_configs_vs_oracle_at_full_size(rt, name):
+    """BASELINE.json configs[1] (4096^2 Gaussian), configs[3] (2048^2 Poisson, geoVI hyper-parameters) and configs[2]
+    (256^3) at FULL size: energy / gradient / metric / metric + 1 against the oracle at 1e-10."""
+    errs, secs = pc.check_config_vs_oracle(rt, name)
+    print(name, {k: f"{v:.1e}" for k, v in errs.items()}, f"{secs:.0f}s")
+
+
+@pytest.mark.parametrize("shape,dist,kind", [((64, 128), (0.01, 0.02), "gauss"), ((512, 64), 0.1, "poisson"), ((2048, 64), 0.01, "gauss"),
+                                             ((64, 4096), 0.01, "gauss"), ((32, 128, 64), (0.1, 0.2, 0.3), "poisson"),
+                                             ((16, 256, 256), 0.1, "gauss")])
+def test_staged_chain_vs_oracle(rt, monkeypatch, shape, dist, kind):
+    """The staged metric chain (nb_passes2.cuh: register-resident radix-16 transforms, TMA tensor-map gathers, row-major
+    intermediates) forced on for shapes the launch heuristic would give to the generic bodies, against the oracle --
+    every line length 32 .. 4096 of P1F / PCF / P3F and the gather input of the last pass."""
+    monkeypatch.setenv("NB200_CHAIN", "1")
+    pc.check_against_oracle(rt, shape, dist, lh_kind=kind)
+    pc.check_metric_properties(rt, shape, dist, lh_kind=kind)
+    monkeypatch.setenv("NB200_P5F", "1")          # register-resident last pass (kept behind a knob)
+    pc.check_against_oracle(rt, shape, dist, lh_kind=kind)
 
 
 @pytest.mark.parametrize("seed", range(16))

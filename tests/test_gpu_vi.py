@@ -141,3 +141,22 @@ def test_config4_geovi_poisson_2048(rt):
         assert abs(objective(e + new, sign) - opt.fun) <= 1e-8 * max(1.0, abs(opt.fun))
         assert opt.fun < f0
     assert float((vals[0][0] + vals[1][0]).abs().max()) > 0.0      # non-linear updates break the exact mirror symmetry
+
+
+def test_final_kl_matches_oracle(rt):
+    """BASELINE.json configs[0] (128 x 128, 4 MGVI samples, one optimize_kl iteration, demo settings): the final KL within
+    1e-10 of the oracle's on identical white noise (north star); and the scaling-leaf variant where its solves are well
+    conditioned (see vi_checks.check_final_kl)."""
+    assert vc.check_final_kl(rt, (128, 128), 4) <= 1e-10
+    assert vc.check_final_kl(rt, (32, 64), 2, scaling=(3.0, 1.0), noise_cov_inv=0.01) <= 1e-10
+
+
+def test_schedule_indices(rt):
+    vc.check_schedule_indices(rt)
+
+
+def test_kl_cg_on_device(rt):
+    vc.check_kl_cg_on_device(rt)
+    # Poisson fixture: ill-conditioned, any two CG implementations drift apart exponentially with the iteration count
+    # (DESIGN.md section 2) -> few iterations, looser solution tolerance, identical control flow
+    vc.check_kl_cg_on_device(rt, "p2d_32x32", x_tol=1e-6, kws=(dict(absdelta=1e-30, miniter=6, maxiter=6), dict(resnorm=1e-1, norm_ord=1, maxiter=8)))
