@@ -53,11 +53,22 @@ template <class T> NB_HD NB_INLINE Aff<T> aff_compose(Aff<T> f, Aff<T> s) {
   Aff<T> r; r.a = f.a + s.a; r.b = f.b + s.b + s.a * f.c; r.c = f.c + s.c; return r;
 }
 
+// this thread's share of sum_i partials[i*stride], i < n (i = tid, tid + nthr, ...; fixed order -> deterministic); the
+// loads of four terms are issued before the first is added: a plain loop pays one global round trip PER TERM
+template <class T> NB_HD NB_INLINE T strided_partial_sum(Ctx& ctx, const T* partials, int n, int stride) {
+  T s = 0;
+  for (int i0 = ctx.tid; i0 < n; i0 += ctx.nthr * 4) {
+    T r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * ctx.nthr; r[u] = partials[(size_t)(i < n ? i : i0) * stride]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * ctx.nthr; if (i < n) s += r[u]; }
+  }
+  return s;
+}
 // sum of partials[i*stride], i < n, by all threads of the calling block (fixed order -> deterministic)
 template <class T> NB_HD NB_INLINE T block_total(Ctx& ctx, const T* partials, int n, int stride, void* scratch) {
-  T s = 0;
-  NB_FOR(ctx, i, n) s += partials[(size_t)i * stride];
-  return ctx.block_sum(s, scratch);
+  return ctx.block_sum(strided_partial_sum(ctx, partials, n, stride), scratch);
 }
 
 // ---- ordered block scan of affine maps -----------------------------------------------------------
@@ -534,9 +545,10 @@ template <class T> struct VjpOut {
     if (ctx.last_block(counter)) {
       // all five totals in ONE reduction (each used to cost its own pair of barriers)
       T v[5] = {0, 0, 0, 0, 0};
-      NB_FOR(ctx, i, ctx.nblk) { v[0] += partials[3 * (size_t)i]; v[1] += partials[3 * (size_t)i + 1]; v[2] += partials[3 * (size_t)i + 2]; }
-      NB_FOR(ctx, i, n_p5) v[3] += p5_partials[i];
-      if (m.has_scaling) { NB_FOR(ctx, i, n_p3) v[4] += p3_partials[2 * (size_t)i]; }
+      v[0] = strided_partial_sum(ctx, partials, ctx.nblk, 3); v[1] = strided_partial_sum(ctx, partials + 1, ctx.nblk, 3);
+      v[2] = strided_partial_sum(ctx, partials + 2, ctx.nblk, 3);
+      v[3] = strided_partial_sum(ctx, p5_partials, n_p5, 1);
+      if (m.has_scaling) v[4] = strided_partial_sum(ctx, p3_partials, n_p3, 2);
       ctx.template block_sum_n<5>(v, scratch);
       if (ctx.tid == 0) {
         T sigbar = v[0], aspbar = v[1], dot = v[2] + v[3], sp = v[4];

@@ -59,8 +59,67 @@ template <class T> void Model<T>::init(Plan<T>* plan_, const nb200_model_desc& d
   partials.alloc(np);
   counters.alloc(16);
   tmp_pos.alloc((size_t)P->local_position_grid());
+  init_chain();
   scratch_lin = new Lin<T>();
   scratch_lin->init(this);
+}
+
+// launch geometry of the fused chain kernels (nb_chain.cuh): all CTAs must be resident (cooperative launch)
+template <class T> void Model<T>::init_chain() {
+  const GridInfo& g = P->g;
+  chain = ChainCfg();
+  if (P->dist) return;                                // slab-decomposed plans all-reduce the bin sums between the halves
+  if (const char* e = std::getenv("NB200_COOP")) { if (e[0] == '0') return; }
+  constexpr int E = 4, CH = SCAN_NT * E;
+  const int sms = P->sms > 0 ? P->sms : sm_count();
+  const long K = g.K, nj = am.has_dev ? K - 2 : 0;
+  long gcap = 1L << 30;                               // test knob: few CTAs -> several rounds per CTA
+  if (const char* e = std::getenv("NB200_COOP_MAXGRID")) gcap = std::max(1L, std::atol(e));
+  // tangent
+  chain.smem_t = TanChainBody<T, E>::smem_bytes();
+  const int rt = coop_blocks_per_sm<TanChainBody<T, E>>(chain.smem_t);
+  if (rt < 1) return;
+  {
+    const long nch = (K + CH - 1) / CH, gmax = std::min(gcap, (long)rt * sms);
+    const long rounds = (nch + gmax - 1) / gmax;
+    chain.per_t = rounds * CH;
+    chain.grid_t = (int)((K + chain.per_t - 1) / chain.per_t);
+  }
+  // cotangent: the scan range of a CTA and its range of bins in the segment sum
+  chain.smem_c = CotChainBody<T, E>::smem_bytes();
+  const int rc = coop_blocks_per_sm<CotChainBody<T, E>>(chain.smem_c);
+  if (rc < 1) return;
+  {
+    const long nchj = std::max<long>(1, (nj + CH - 1) / CH), gmax = std::min(gcap, (long)rc * sms);
+    const long rounds = (nchj + gmax - 1) / gmax;
+    chain.per_c = rounds * CH;
+    const long gscan = std::max<long>(1, (nj + chain.per_c - 1) / chain.per_c);
+    // segment sum: spread the bins over all resident CTAs (at least 64 bins each)
+    chain.grid_c = (int)std::max<long>(gscan, std::min<long>(gmax, (K + 63) / 64));
+    // bin ranges of equal cost (one unit per W position + two per bin), lanes per bin from the mean population of the range
+    std::vector<int> b0((size_t)chain.grid_c + 1, (int)K), lgv((size_t)chain.grid_c, 0);
+    const double total = (double)g.w_offs[K] + 2.0 * (double)K;
+    long b = 0;
+    for (int c = 0; c < chain.grid_c; ++c) {
+      b0[c] = (int)b;
+      const double target = total * (c + 1) / chain.grid_c;
+      while (b < K && (double)g.w_offs[b + 1] + 2.0 * (double)(b + 1) <= target) ++b;
+      if (c == chain.grid_c - 1) b = K;
+      const long nbin = b - b0[c];
+      const double mean = nbin > 0 ? (double)(g.w_offs[b] - g.w_offs[b0[c]]) / (double)nbin : 0.0;
+      int lg = 0;
+      while (lg < 5 && (double)(4 << lg) < mean) ++lg;       // <= ~4 positions per lane
+      lgv[c] = lg;
+    }
+    b0[chain.grid_c] = (int)K;
+    seg_b0.upload(b0); seg_lg.upload(lgv);
+  }
+  cagg.alloc((size_t)std::max(chain.grid_t, chain.grid_c) + 8);
+  crel.alloc((size_t)std::max<long>(nj, 1));
+  if (const char* e = std::getenv("NB200_COOP_DBG")) { if (e[0] >= '1') cdbg.alloc((size_t)chain.grid_c * 12); chain.dbg_twice = e[0] == '2'; }
+  if (const char* e = std::getenv("NB200_COOP_NPH_T")) chain.nph_t = std::atoi(e);
+  if (const char* e = std::getenv("NB200_COOP_NPH_C")) chain.nph_c = std::atoi(e);
+  chain.ok = true;
 }
 template <class T> Model<T>::~Model() { delete scratch_lin; }
 

@@ -44,6 +44,23 @@ inline void launch(int grid, int block, size_t smem, stream_t, const typename Bo
     Body::run(ctx, p, sm.data());
   }
 }
+
+// cooperative (multi-phase) bodies: `Body::phase(ph, ctx, params, smem)` for ph < Body::kPhases with a grid-wide barrier
+// between phases; shared memory persists across the phases of a block.  Emulation: one shared-memory image per block.
+inline int coop_max_blocks_per_sm(const void*, int, size_t smem) { return smem <= 100 * 1024 ? 2 : 1; }
+template <class Body> inline int coop_blocks_per_sm(size_t smem) { return coop_max_blocks_per_sm(nullptr, 256, smem); }
+template <class Body>
+inline void launch_coop(int grid, int block, size_t smem, stream_t, const typename Body::Params& p) {
+  (void)block;
+  static const bool trace = std::getenv("NB200_EMU_TRACE") != nullptr;
+  if (trace) std::fprintf(stderr, "[emu] coop %s grid=%d\n", typeid(Body).name(), grid);
+  std::vector<std::vector<char>> sm((size_t)grid, std::vector<char>(smem + 4096));
+  for (int ph = 0; ph < Body::kPhases && ph < p.nph; ++ph)
+    for (int b = 0; b < grid; ++b) {
+      Ctx ctx{0, 1, b, grid};
+      Body::phase(ph, ctx, p, sm[(size_t)b].data());
+    }
+}
 #else
 typedef cudaStream_t stream_t;
 #define NB_CUDA_CHECK(expr)                                                                      \
@@ -146,6 +163,64 @@ inline void launch(int grid, int block, size_t smem, stream_t s, const typename 
     nb_kernel<Body><<<grid, block, smem, s>>>(p);
   }
   NB_CUDA_CHECK(cudaGetLastError());
+  if (trace) { cudaError_t e = cudaStreamSynchronize(s); std::fprintf(stderr, "[nb200]   -> %s\n", cudaGetErrorString(e)); }
+  ++launch_counter();
+}
+// ---- cooperative (multi-phase) kernels --------------------------------------------------------------------------------
+// Grid-wide barrier for kernels launched with cudaLaunchCooperativeKernel (all CTAs resident): bar[0] counts arrivals
+// (self-resetting), bar[1] is the generation the waiters spin on.  The fences make the global writes of every CTA before
+// the barrier visible to every CTA after it.
+__device__ NB_INLINE void grid_barrier(Ctx& ctx, unsigned* bar) {
+  __syncthreads();
+  if (ctx.tid == 0) {
+    volatile unsigned* gen = bar + 1;
+    const unsigned g = *gen;                 // read before arriving: the generation cannot advance until this CTA has arrived
+    __threadfence();
+    if (atomicInc(bar, (unsigned)(ctx.nblk - 1)) == (unsigned)(ctx.nblk - 1)) {
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == g) __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <class Body>
+__global__ void __launch_bounds__(256, MinBlocks<Body>::value) nb_kernel_coop(const __grid_constant__ typename Body::Params p) {
+  extern __shared__ __align__(16) unsigned char nb_smem[];
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+#pragma unroll 1
+  for (int ph = 0; ph < Body::kPhases && ph < p.nph; ++ph) {     // (nph < kPhases: developer timing aid)
+    if (ph) grid_barrier(ctx, p.bar);
+    Body::phase(ph, ctx, p, nb_smem);
+  }
+}
+
+// resident CTAs per SM of a cooperative body at this dynamic shared-memory size (0: does not fit)
+template <class Body> inline int coop_blocks_per_sm(size_t smem) {
+  smem += 512;
+  NB_CUDA_CHECK(cudaFuncSetAttribute(nb_kernel_coop<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int nb = 0;
+  NB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nb_kernel_coop<Body>, 256, smem));
+  return nb;
+}
+
+template <class Body>
+inline void launch_coop(int grid, int block, size_t smem, stream_t s, const typename Body::Params& p) {
+  smem += 512;
+  static const bool trace = std::getenv("NB200_TRACE") != nullptr;
+  if (trace) std::fprintf(stderr, "[nb200] coop launch %s grid=%d block=%d smem=%zu\n", typeid(Body).name(), grid, block, smem);
+  void* args[1] = {const_cast<void*>(reinterpret_cast<const void*>(&p))};
+  KernelTimer& kt = kernel_timer();
+  KernelTimer::Rec r; r.name = typeid(Body).name();
+  if (kt.on) {
+    NB_CUDA_CHECK(cudaEventCreate(&r.a)); NB_CUDA_CHECK(cudaEventCreate(&r.b));
+    NB_CUDA_CHECK(cudaEventRecord(r.a, s));
+  }
+  NB_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(nb_kernel_coop<Body>), dim3(grid), dim3(block), args, smem, s));
+  if (kt.on) { NB_CUDA_CHECK(cudaEventRecord(r.b, s)); kt.recs.push_back(r); }
   if (trace) { cudaError_t e = cudaStreamSynchronize(s); std::fprintf(stderr, "[nb200]   -> %s\n", cudaGetErrorString(e)); }
   ++launch_counter();
 }

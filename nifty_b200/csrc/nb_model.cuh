@@ -2,6 +2,7 @@
 // sequences for linearise / value+gradient / metric / sqrt-metric applications.
 #pragma once
 #include "nb_plan.cuh"
+#include "nb_chain.cuh"
 #include "../../include/nifty_b200.h"
 
 namespace nb {
@@ -67,6 +68,19 @@ template <class T> struct Model : ModelBase {
 
   int scan_e = 8;      // elements per thread of the scan kernels (scan_pick_e)
   size_t scan_smem() const { return scan_smem_bytes<T>(scan_e); }
+
+  // fused chains (nb_chain.cuh): one cooperative launch per chain; launch geometry fixed at model creation
+  struct ChainCfg {
+    bool ok = false;
+    int grid_t = 0; long per_t = 0; size_t smem_t = 0;                       // tangent
+    int grid_c = 0; long per_c = 0; size_t smem_c = 0;                       // cotangent
+    int dbg_twice = 0;
+    int nph_t = 2, nph_c = 3;                                                // phases to run (developer timing aid)
+  } chain;
+  DevBuf<Aff<T>> cagg, crel;
+  DevBuf<int> seg_b0, seg_lg;       // segment sum: first bin and log2(lanes per bin) of every CTA
+  DevBuf<long long> cdbg;
+  void init_chain();
 };
 
 template <class T> struct Lin : LinBase {
@@ -106,6 +120,14 @@ template <class T> struct Lin : LinBase {
   void amp_tangent(stream_t st, const T* t) {
     Model<T>& m = *M; const int K = m.am.K;
     JvpElem<T> el; el.m = m.am; el.pos = pos.p; el.t = t; el.scal = scal.p;
+    if (m.chain.ok) {
+      TanChainParams<T> pp; pp.elem = el;
+      JvpOut<T>& jo = pp.out; jo.m = m.am; jo.pos = pos.p; jo.t = t; jo.wS = wS.p; jo.amp = amp.p; jo.ellv = ellv; jo.cv = cv; jo.ad = m.ad.p;
+      jo.partials = m.partials.p; jo.counter = m.counters.p + 2; jo.scal = scal.p;
+      pp.n = K; pp.per = m.chain.per_t; pp.agg = m.cagg.p; pp.bar = m.counters.p + 8; pp.nph = m.chain.nph_t;
+      launch_coop<TanChainBody<T, 4>>(m.chain.grid_t, SCAN_NT, m.chain.smem_t, st, pp);
+      return;
+    }
     const int nch = m.am.has_dev ? m.nchunksK : 1;
     if (m.am.has_dev && m.nchunksK > 1) {
       ScanAggParams<T, JvpElem<T>> pa; pa.n = K; pa.elem = el; pa.agg = m.agg.p; pa.pre = m.preaff.p; pa.counter = m.counters.p + 5;
@@ -154,6 +176,37 @@ template <class T> struct Lin : LinBase {
   }
   void amp_cotangent(stream_t st, T* out, const T* add, int p3_col, T scl_factor, bool use_p5_dot) {
     Plan<T>& P = *M->P;
+    if (M->chain.ok) {
+      Model<T>& m = *M; const int K = m.am.K;
+      CotChainParams<T> pp;
+      VjpOut<T>& vo = pp.out; vo.m = m.am; vo.pos = pos.p; vo.g = m.gbuf.p; vo.wS = wS.p; vo.scal_in = scal.p; vo.out = out; vo.add = add;
+      vo.partials = m.partials.p; vo.counter = m.counters.p + 4; vo.scal = scal.p;
+      vo.p3_partials = P.p3part.p + p3_col; vo.n_p3 = P.n3part; vo.p5_partials = P.p5part.p; vo.n_p5 = use_p5_dot ? P.n5part : 0; vo.scl_factor = scl_factor;
+      pp.nj = m.am.has_dev ? (long)K - 2 : 0; pp.per = m.chain.per_c; pp.rel = m.crel.p; pp.agg = m.cagg.p; pp.bar = m.counters.p + 10; pp.nph = m.chain.nph_c;
+      pp.W = P.W.p; pp.order = P.w_order.p; pp.offs = P.w_offs.p; pp.amp = amp.p; pp.ellv = ellv; pp.cv = cv; pp.g = m.gbuf.p;
+      pp.segpart = m.partials.p + 4096; pp.scal = scal.p;
+      pp.seg_b0 = m.seg_b0.p; pp.seg_lg = m.seg_lg.p;
+      pp.dbg = m.cdbg.n ? m.cdbg.p : nullptr; pp.dbg_twice = m.chain.dbg_twice;
+      launch_coop<CotChainBody<T, 4>>(m.chain.grid_c, SCAN_NT, m.chain.smem_c, st, pp);
+#ifndef NB_EMU
+      if (m.cdbg.n) {       // developer aid: where the CTAs spend their time (one line per launch on stderr)
+        std::vector<long long> h(m.cdbg.n);
+        stream_sync(st); d2h(h.data(), m.cdbg.p, h.size() * sizeof(long long), st); stream_sync(st);
+        const int G = m.chain.grid_c; long long t0 = h[0];
+        for (int c = 0; c < G; ++c) t0 = std::min(t0, h[(size_t)c * 12]);
+        std::fprintf(stderr, "[nb200 cot-chain] grid %d, us since first CTA start (min/avg/max over CTAs):", G);
+        const char* nm[11] = {"start", "summed", "seg-done", "ph1-start", "ph1-done", "ph2-start", "ph2-done", "-", "again-start", "again-summed", "again-done"};
+        for (int s = 0; s < 11; ++s) {
+          if (s == 7 || (s > 7 && !m.chain.dbg_twice)) continue;
+          double mn = 1e30, mx = -1e30, av = 0;
+          for (int c = 0; c < G; ++c) { double v = (h[(size_t)c * 12 + s] - t0) * 1e-3; mn = std::min(mn, v); mx = std::max(mx, v); av += v / G; }
+          std::fprintf(stderr, "  %s %.1f/%.1f/%.1f", nm[s], mn, av, mx);
+        }
+        std::fprintf(stderr, "\n");
+      }
+#endif
+      return;
+    }
     seg_sum(st, nullptr, nullptr);
     vjp_chain(st, out, add, P.p3part.p + p3_col, P.n3part, P.p5part.p, use_p5_dot ? P.n5part : 0, scl_factor);
   }

@@ -70,6 +70,22 @@ def test_multichunk_amplitude_chain(rt):
     pc.check_against_oracle(rt, (64, 64), 0.1, flexibility=None, asperity=None)
 
 
+@pytest.mark.parametrize("maxgrid", ["1", "2", "5"])
+def test_fused_chain_rounds(rt, monkeypatch, maxgrid):
+    """Fused chain kernels (nb_chain.cuh) with a capped grid: several scan rounds and segment-sum windows per CTA,
+    carry-in across CTAs, thread prefixes of every round kept across the grid barrier."""
+    monkeypatch.setenv("NB200_COOP_MAXGRID", maxgrid)
+    pc.check_against_oracle(rt, (256, 256), 1.0 / 256)
+    pc.check_against_oracle(rt, (32, 32, 32), 0.1, lh_kind="poisson")
+
+
+def test_legacy_chain_kernels(rt, monkeypatch):
+    """The five-launch chain (segment sum, aggregate / apply scans) that slab-decomposed plans still use."""
+    monkeypatch.setenv("NB200_COOP", "0")
+    pc.check_against_oracle(rt, (128, 256), (0.01, 0.02))
+    pc.check_against_oracle(rt, (16, 16, 16), 0.1, lh_kind="poisson")
+
+
 @pytest.mark.parametrize("lg_r", ["1", "2", "3"])
 def test_p1_mirror_quads(rt, monkeypatch, lg_r):
     """P1MBody (one bin lookup per mirror quad) needs >= 2 lines per CTA, which the launch heuristic only picks

@@ -405,7 +405,7 @@ def check_kl_cg_on_device(rt, name="g2d_16x16", x_tol=1e-9, kws=None):
         if frozen:
             for lo, hi in frozen:
                 jj[lo:hi] = 0
-        for kw in kws or (dict(absdelta=1e-7, maxiter=50), dict(resnorm=1e-4, norm_ord=1, maxiter=25), dict(absdelta=1e-30, miniter=23, maxiter=23)):
+        for kw in kws or (dict(absdelta=1e-7, maxiter=50), dict(resnorm=1e-4, norm_ord=1, maxiter=25), dict(absdelta=1e-30, miniter=12, maxiter=12)):
             dev = _cg(op, jj, **kw)
             host = _cg(lambda t: op(t), jj, **kw)
             assert (dev.nit, dev.info, dev.nfev) == (host.nit, host.info, host.nfev), kw
