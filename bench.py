@@ -74,7 +74,7 @@ def kernel_bytes(name, shape, w=8):
 
 def short_kernel_name(name):
     """Body name of a mangled kernel name as recorded by the library's launch timer."""
-    for k in ("P1FBody", "P3FBody", "PCFBody", "P5FBody", "P1MBody", "P1Body", "P3Body", "P5Body", "PCBody", "SegSum", "ScanApply", "ScanAgg",
+    for k in ("P1FBody", "P3FBody", "PCFBody", "P5FBody", "P1MBody", "P1Body", "P3Body", "P5Body", "PCBody", "CotChain", "TanChain", "SegSum", "ScanApply", "ScanAgg",
               "CgStep", "CgDir"):
         if k in name:
             return k
@@ -248,6 +248,13 @@ def run_b200(args, shape, wname, rank, world, local_rank):
     def allreduce(buf):
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
 
+    def allreduce_async(buf):
+        return dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)
+
+    reduce_chunks = int(os.environ.get("NB200_REDUCE_CHUNKS", "4"))
+    if world > 1:
+        sig.cf.plan.set_reduce_chunks(reduce_chunks)
+
     if world == 1:
         def step(tin, o):      # M_p t = lh.metric(pos, t) + t
             return lin.metric(tin, add_identity=True, out=o)
@@ -256,7 +263,7 @@ def run_b200(args, shape, wname, rank, world, local_rank):
         # local fused product (scaled by 1/world, the identity added on rank 0) + NCCL all-reduce of the L-sized result,
         # enqueued in-stream from the library's reduction hook -- what every KL-CG iteration of a sharded run executes
         def step(tin, o):
-            return metric_multi([lin], tin, scale=1.0 / world, identity_here=(rank == 0), out=o, reduce_fn=allreduce)
+            return metric_multi([lin], tin, scale=1.0 / world, identity_here=(rank == 0), out=o, reduce_fn=allreduce_async)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -298,17 +305,20 @@ def run_b200(args, shape, wname, rank, world, local_rank):
         prod_ms = timed(lambda: metric_multi([lin], t, scale=1.0 / world, identity_here=(rank == 0), out=scratch), max(10, args.steps // 4))
         ar_ms = timed(lambda: allreduce(scratch), max(10, args.steps // 4))
         nbytes_ar = out.numel() * out.element_size()
-        collective = {"what": "NCCL all-reduce (SUM) of the metric output, once per step, in-stream after the local product",
+        collective = {"what": f"NCCL all-reduce (SUM) of the metric output, once per step: the last pass runs in {reduce_chunks} launches and "
+                              "every finished range of the result is all-reduced on the communication stream beside the remaining launches "
+                              "and the cotangent chain (include/nifty_b200.h nb200_reduce_hook)",
                       "bytes": nbytes_ar, "allreduce_ms_alone": ar_ms, "product_ms_alone": prod_ms, "step_ms": ms_step,
                       "bus_GBps_alone": 2.0 * (world - 1) / world * nbytes_ar / (ar_ms * 1e-3) / 1e9,
                       "exposed_ms": ms_step - prod_ms,
-                      "overlap": "none: the next CG product needs the all-reduced vector (sequential dependency of the recurrence)"}
+                      "overlap": "within the product only: the next CG product needs the all-reduced vector (sequential dependency of the "
+                                 "recurrence)", "reduce_chunks": reduce_chunks}
 
     # per-kernel event timing over the same steps (instrumented pass; the library records events
     # around each of its launches on the stream it launches on)
     rt.timing_begin()
     for _ in range(args.steps):
-        lin.metric(t, add_identity=True, out=out)
+        step(t, out)
     tm = rt.timing_end()
     tot = sum(v[1] for v in tm.values())
     dom = max(tm.items(), key=lambda kv: kv[1][1])
@@ -474,8 +484,10 @@ def kl_config3(nb, torch, dist, metric_multi, rank, world, dev, peak):
     t = sig.layout.random(45, dtype, dev)
     out = torch.empty_like(t)
 
+    sig.cf.plan.set_reduce_chunks(int(os.environ.get("NB200_REDUCE_CHUNKS", "4")))
+
     def allreduce(buf):
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        return dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)
 
     def step(hook):
         metric_multi(lins, t, scale=1.0 / n_total, identity_here=(rank == 0), out=out, reduce_fn=hook)
@@ -496,7 +508,7 @@ def kl_config3(nb, torch, dist, metric_multi, rank, world, dev, peak):
         step(allreduce)
     ms = timed(lambda: step(allreduce), 20)
     ms_local = timed(lambda: step(None), 20)
-    ms_ar = timed(lambda: allreduce(out), 20)
+    ms_ar = timed(lambda: allreduce(out).wait(), 20)
     ab = algorithmic_bytes_mvp(shape)
     return {"workload": "cf3d_256_f64, 16 antithetic samples sharded", "samples_per_rank": n_loc, "ms_per_kl_metric": ms,
             "products_per_sec": n_total * 1e3 / ms, "local_products_ms": ms_local, "allreduce_ms_alone": ms_ar,

@@ -221,7 +221,14 @@ int nb200_cg_solve(nb200_lin* lin, nb200_lin* lin_b, void* stream, const void* j
  * in the Python binding; XLA's all-reduce in a jax.ffi binding).  With scale = 1 / n_samples_total and identity_here
  * on exactly one rank the all-reduced result is mean_i(metric(x_i, t) + t).  A rank without samples passes one
  * linearisation with scale = 0. */
+/* The hook is called once for every finished range [buf, buf + n_elems) of `out` -- the ranges partition the vector; with
+ * nb200_plan_set_reduce_chunks(plan, n > 1) the last pass of the last linearisation runs in n launches and hands over the
+ * excitation rows each launch completes right after it, so that the all-reduce of one piece travels over NVLink while the
+ * next piece is computed (the hyper-parameter entries follow after the cotangent chain) -- and finally with buf == NULL,
+ * n_elems == 0: every range has been handed over, the hook must make all its reductions complete in stream order
+ * (e.g. wait on the communication stream).  A hook may simply all-reduce synchronously and ignore the final call. */
 typedef void (*nb200_reduce_hook)(void* user, void* buf, int64_t n_elems, void* stream);
+int nb200_plan_set_reduce_chunks(nb200_plan* plan, int nchunks);
 int nb200_metric_multi(nb200_lin** lins, int n_lins, double scale, int identity_here, void* stream, const void* t, void* out,
                        nb200_reduce_hook hook, void* user);
 /* conjugate gradient (same rules / result as nb200_cg_solve) on that operator: the Newton-CG inner solve of

@@ -72,6 +72,7 @@ SIGNATURES = {
     "nb200_plan_local_map": (C.c_int, [vp, C.c_int, vp]),
     "nb200_plan_set_scratch": (C.c_int, [vp, vp, vp, vp]),
     "nb200_plan_set_chunks": (C.c_int, [vp, C.c_int]),
+    "nb200_plan_set_reduce_chunks": (C.c_int, [vp, C.c_int]),
     "nb200_dist_phase": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]),
     "nb200_hartley": (C.c_int, [vp, vp, vp, vp]),
     "nb200_cf_apply": (C.c_int, [vp, vp, vp, vp, f64, vp]),

@@ -215,6 +215,11 @@ class Plan:
         else:
             self.comm.all_to_all(self._s1, self._s0, self.x2_recv, self.x2_send)
 
+    def set_reduce_chunks(self, nchunks: int):
+        """Sample-averaged products (`metric_multi`): run the last pass in `nchunks` launches and hand every finished
+        range of the result to the reduction hook right away, so that its all-reduce overlaps the remaining launches."""
+        self.rt.api.call("nb200_plan_set_reduce_chunks", self._h, int(nchunks))
+
     def set_chunks(self, nchunks: int):
         """Pipeline every exchange in `nchunks` pieces (point-to-point sends of chunk c overlap the passes
         that produce chunk c+1 and consume chunk c-1)."""
@@ -619,21 +624,31 @@ class _DevView:
 
 
 def make_reduce_hook(rt: "Runtime", dtype, reduce_fn):
-    """ctypes callback for `nb200_reduce_hook`: `reduce_fn(tensor)` receives a tensor aliasing the library's buffer and
-    must enqueue an in-place SUM all-reduce on the current stream (torch.distributed does).  Returns None if
-    `reduce_fn` is None.  The caller keeps the returned object alive for the duration of the call."""
+    """ctypes callback for `nb200_reduce_hook`: `reduce_fn(tensor)` receives a tensor aliasing one finished range of the
+    library's output and starts its in-place SUM all-reduce; it may return a work handle (``async_op=True``: the
+    collective runs on the communication stream while the library launches the next piece) -- the handles are waited on
+    when the library signals that every range has been handed over.  Returns None if `reduce_fn` is None.  The caller
+    keeps the returned object alive for the duration of the call."""
     if reduce_fn is None:
         return None
     from ._capi import REDUCE_HOOK
+    pending = []
 
     def _hook(user, buf, n, stream):
+        if not buf or n == 0:                 # every range handed over: complete them in stream order
+            for w in pending:
+                w.wait()
+            pending.clear()
+            return
         if rt.device.type == "cuda":
             t = torch.as_tensor(_DevView(buf, n, dtype), device=rt.device)
         else:       # host emulation (tests): the buffer is host memory
             import numpy as np
             ctype = C.c_double if dtype == torch.float64 else C.c_float
             t = torch.from_numpy(np.ctypeslib.as_array((ctype * n).from_address(buf)))
-        reduce_fn(t)
+        w = reduce_fn(t)
+        if w is not None:
+            pending.append(w)
 
     return REDUCE_HOOK(_hook)
 

@@ -143,12 +143,12 @@ template <class T> CgWork<T>& cg_work() { static thread_local CgWork<T> w; retur
 template <class T>
 void multi_metric(Lin<T>** lins, int n, T scale, bool identity_here, stream_t st, const T* t, T* out, nb200_reduce_hook hook, void* user) {
   if (n <= 0) throw Error{"nb200: multi_metric needs at least one linearisation (ranks without samples still pass one and scale 0)"};
-  const long L = lins[0]->M->am.L;
+  typename Lin<T>::PieceFn piece = [&](long first, long count) { hook(user, out + first, (int64_t)count, (void*)st); };
   for (int i = 0; i < n; ++i) {
     const T* add = (i == 0) ? (identity_here ? t : nullptr) : out;
-    lins[i]->metric_ex(st, lins[i], t, out, add, false, scale);
+    lins[i]->metric_ex(st, lins[i], t, out, add, false, scale, (hook && i == n - 1) ? &piece : nullptr);
   }
-  if (hook) hook(user, out, (int64_t)L, (void*)st);
+  if (hook) hook(user, nullptr, 0, (void*)st);       // every range has been handed over: results must be complete in stream order
 }
 
 template <class T>
@@ -338,6 +338,13 @@ int nb200_plan_local_map(const nb200_plan* plan, int axis, int32_t* out_host) {
 int nb200_plan_set_scratch(nb200_plan* plan, void* s0, void* s1, void* s2) {
   NB_TRY
   NB_DISPATCH(plan->impl->dtype, TT, { auto* P = static_cast<Plan<TT>*>(plan->impl); P->xS0 = (cplx<TT>*)s0; P->xS1 = (cplx<TT>*)s1; P->xS2 = (cplx<TT>*)s2; })
+  return 0;
+  NB_CATCH
+}
+int nb200_plan_set_reduce_chunks(nb200_plan* plan, int nchunks) {
+  NB_TRY
+  if (!plan || nchunks < 1 || nchunks > 64) return fail("nb200_plan_set_reduce_chunks: 1 <= nchunks <= 64");
+  plan->impl->reduce_chunks = nchunks;
   return 0;
   NB_CATCH
 }

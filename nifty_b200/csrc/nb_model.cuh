@@ -1,6 +1,7 @@
 // nifty_b200 -- model (amplitude priors + likelihood) and linearisation objects; operator launch
 // sequences for linearise / value+gradient / metric / sqrt-metric applications.
 #pragma once
+#include <functional>
 #include "nb_plan.cuh"
 #include "nb_chain.cuh"
 #include "../../include/nifty_b200.h"
@@ -245,7 +246,11 @@ template <class T> struct Lin : LinBase {
   // `add` may be t (the "+ 1" of the Hamiltonian metric), `out` itself (accumulate the products of several
   // linearisations in place: every entry is read and written by the same thread) or null; `want_dot` leaves
   // <add, out> in scal[SC_DOT] (meaningful for add == t, scale == 1: the CG curvature).
-  void metric_ex(stream_t st, Lin<T>* b, const T* t, T* out, const T* add, bool want_dot, T scale) {
+  // `piece_done(first, count)` (optional, needs !want_dot): the last pass runs in plan.reduce_chunks launches over ranges of
+  // axis-0 planes and reports every finished range of `out` (in elements) right after the launch that completes it --
+  // the caller's all-reduce of that range then overlaps the remaining launches; the hyper-parameter entries follow last.
+  typedef std::function<void(long, long)> PieceFn;
+  void metric_ex(stream_t st, Lin<T>* b, const T* t, T* out, const T* add, bool want_dot, T scale, const PieceFn* piece_done = nullptr) {
     Model<T>& m = *M; Plan<T>& P = *m.P;
     if (!valid || !b->valid) throw Error{"nb200: linearisation not initialised (call nb200_lin_update)"};
     ChainScope<T> chain(P, P.chain_ok);      // every pass of this sequence runs staged (row-major intermediates)
@@ -256,8 +261,28 @@ template <class T> struct Lin : LinBase {
     if (m.am.has_scaling) { op.cshift_ptr = t + m.am.off_scl; op.cshift_scale = m.am.scl_b * scale; }
     P.template run_p3<true, true>(st, op);
     P.run_pc(st, true);
-    P.run_p5(st, epi_adjoint(out, add, want_dot));
-    amp_cotangent(st, out, add, 0, m.am.scl_b, want_dot);
+    const int nch = (piece_done && !want_dot && !P.dist) ? std::min(P.reduce_chunks, P.g.h0 + 1) : 1;
+    if (nch <= 1) {
+      P.run_p5(st, epi_adjoint(out, add, want_dot));
+      amp_cotangent(st, out, add, 0, m.am.scl_b, want_dot);
+      if (piece_done) (*piece_done)(0, m.am.L);
+      return;
+    }
+    const long plane = (long)P.g.nm * P.g.nl;          // elements of one axis-0 plane of the excitations
+    const int n_a = P.g.n0, h_a = P.g.h0, lgm = P.mg5().lg_mid;
+    for (int c = 0; c < nch; ++c) {
+      // lines of the planes a0 .. a1-1 of the half range; they also complete the mirror planes n_a - a (a != 0, h_a)
+      const int a0 = Plan<T>::split_at(0, h_a + 1, c, nch), a1 = Plan<T>::split_at(0, h_a + 1, c + 1, nch);
+      P.run_p5(st, epi_adjoint(out, add, false), a0 << lgm, (a1 - a0) << lgm);
+      const int m0 = std::max(n_a - a1 + 1, h_a + 1), m1 = std::min(n_a - a0 + 1, n_a);      // mirror planes [m0, m1)
+      if (a1 > a0 && m1 > m0 && m0 == a1) { (*piece_done)(m.am.off_xi + a0 * plane, (long)(m1 - a0) * plane); continue; }
+      if (a1 > a0) (*piece_done)(m.am.off_xi + a0 * plane, (long)(a1 - a0) * plane);
+      if (m1 > m0) (*piece_done)(m.am.off_xi + m0 * plane, (long)(m1 - m0) * plane);
+    }
+    amp_cotangent(st, out, add, 0, m.am.scl_b, false);
+    if (m.am.off_xi > 0) (*piece_done)(0, m.am.off_xi);
+    const long tail = m.am.off_xi + (long)n_a * plane;
+    if (m.am.L > tail) (*piece_done)(tail, m.am.L - tail);
   }
   void metric(stream_t st, Lin<T>* b, const T* t, T* out, bool add_identity) {
     metric_ex(st, b, t, out, add_identity ? t : nullptr, add_identity, T(1));

@@ -159,6 +159,7 @@ struct AxisDist {
 
 struct PlanBase {
   int dtype = 1, device = 0, hconv = 0;
+  int reduce_chunks = 1;    // pieces of the last pass of a sample-averaged product handed to the reduction hook as they finish
   GridInfo g;
   // slab decomposition (3-D only): axis 0 of the latent array, last axis (= x2 planes) of position space
   bool dist = false;

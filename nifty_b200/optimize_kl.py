@@ -66,6 +66,12 @@ class _Comm:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def allreduce_sum_async(self, t: torch.Tensor):
+        """Start the in-place SUM all-reduce of `t` and return its work handle (None on a single rank)."""
+        if self.world > 1:
+            return self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return None
+
     def allgather(self, t: torch.Tensor):
         """Per-rank tensors whose leading extent may differ between ranks (uneven sample sharding): the counts are
         exchanged first, every rank pads to the maximum, the result is trimmed again."""
@@ -136,6 +142,11 @@ class OptimizeVI:
         self.get_status_message = _get_status_message
         self.n_total_iterations = n_total_iterations
         self.comm = _Comm(comm)
+        plan = likelihood.signal.cf.plan
+        if self.comm.world > 1 and not plan.dist:
+            # KL metric over several ranks: the last pass hands its result to the all-reduce in pieces (NVLink transfer of
+            # one piece beside the computation of the next)
+            plan.set_reduce_chunks(int(os.environ.get("NB200_REDUCE_CHUNKS", "4")))
         self._draw_linear_residual = _draw_linear_residual
         self._nonlinearly_update_residual = _nonlinearly_update_residual
         self._kl_vg_override, self._kl_met_override = _kl_value_and_grad, _kl_metric
@@ -244,7 +255,7 @@ class OptimizeVI:
             lins = self._lins[:1]
             if not getattr(lins[0], "_ever_updated", False):
                 raise RuntimeError("kl_metric: a rank without sample points needs one initialised linearisation")
-        reduce_fn = (lambda t: self.comm.allreduce_sum(t)) if self.comm.world > 1 else None
+        reduce_fn = (lambda t: self.comm.allreduce_sum_async(t)) if self.comm.world > 1 else None
         return SampleAveragedMetric(lins, self._n_total, identity_here=self.comm.rank == 0, reduce_fn=reduce_fn, frozen=frozen,
                                     scale_zero=none_here)
 

@@ -66,3 +66,8 @@ def test_schedule_indices(rt):
 
 def test_kl_cg_on_device(rt):
     vc.check_kl_cg_on_device(rt)
+
+
+def test_reduce_pieces(rt):
+    vc.check_reduce_pieces(rt)
+    vc.check_reduce_pieces(rt, "g3d_8x8x8")

@@ -160,3 +160,8 @@ def test_kl_cg_on_device(rt):
     # Poisson fixture: ill-conditioned, any two CG implementations drift apart exponentially with the iteration count
     #  -> few iterations, looser solution tolerance, identical control flow
     vc.check_kl_cg_on_device(rt, "p2d_32x32", x_tol=1e-6, kws=(dict(absdelta=1e-30, miniter=6, maxiter=6), dict(resnorm=1e-1, norm_ord=1, maxiter=8)))
+
+
+def test_reduce_pieces(rt):
+    vc.check_reduce_pieces(rt)
+    vc.check_reduce_pieces(rt, "g3d_8x8x8")

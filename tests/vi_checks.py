@@ -410,3 +410,43 @@ def check_kl_cg_on_device(rt, name="g2d_16x16", x_tol=1e-9, kws=None):
             host = _cg(lambda t: op(t), jj, **kw)
             assert (dev.nit, dev.info, dev.nfev) == (host.nit, host.info, host.nfev), kw
             assert rel_err(t2n(dev.x), t2n(host.x)) < x_tol, kw
+
+
+def check_reduce_pieces(rt, name="g2d_16x16"):
+    """Sample-averaged product with the last pass cut into pieces (nb200_plan_set_reduce_chunks): the ranges handed to the
+    reduction hook partition the latent vector exactly once, arrive before the final (flush) call, and the result equals
+    the one-piece product bit for bit."""
+    from nifty_b200._runtime import metric_multi
+    c, g, lh, olh, lay = _setup(rt, name)
+    rng = np.random.default_rng(11)
+    pos = rt.asarray(lay.pack({k: 0.3 * v for k, v in lay.random(rng).items()}), torch.float64)
+    t = rt.asarray(lay.pack(lay.random(rng)), torch.float64)
+    lins = []
+    for sgn in (1.0, -1.0):
+        l = lh.new_lin()
+        l.update(pos + sgn * 0.1, want_grad=False)
+        lins.append(l)
+    plan = lh.signal.cf.plan
+    plan.set_reduce_chunks(1)
+    ref = metric_multi(lins, t, scale=0.5, identity_here=True).clone()
+    L = t.numel()
+    for nch in (1, 2, 3, 4, 64):
+        plan.set_reduce_chunks(nch)
+        seen = []
+        out = torch.full_like(t, float("nan"))
+
+        def reduce_fn(piece, out=out, seen=seen):
+            off = (piece.data_ptr() - out.data_ptr()) // piece.element_size()
+            seen.append((int(off), int(piece.numel())))
+            return None
+
+        got = metric_multi(lins, t, scale=0.5, identity_here=True, out=out, reduce_fn=reduce_fn)
+        cover = np.zeros(L, dtype=np.int64)
+        for off, n in seen:
+            assert 0 <= off and off + n <= L and n > 0
+            cover[off:off + n] += 1
+        assert np.all(cover == 1), (nch, seen)
+        if nch > 1:
+            assert len(seen) > 2
+        assert torch.equal(got, ref), nch
+    plan.set_reduce_chunks(1)
