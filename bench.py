@@ -251,7 +251,7 @@ def run_b200(args, shape, wname, rank, world, local_rank):
     def allreduce_async(buf):
         return dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)
 
-    reduce_chunks = int(os.environ.get("NB200_REDUCE_CHUNKS", "4"))
+    reduce_chunks = int(os.environ.get("NB200_REDUCE_CHUNKS", "1"))
     if world > 1:
         sig.cf.plan.set_reduce_chunks(reduce_chunks)
 
@@ -484,7 +484,7 @@ def kl_config3(nb, torch, dist, metric_multi, rank, world, dev, peak):
     t = sig.layout.random(45, dtype, dev)
     out = torch.empty_like(t)
 
-    sig.cf.plan.set_reduce_chunks(int(os.environ.get("NB200_REDUCE_CHUNKS", "4")))
+    sig.cf.plan.set_reduce_chunks(int(os.environ.get("NB200_REDUCE_CHUNKS", "1")))
 
     def allreduce(buf):
         return dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)

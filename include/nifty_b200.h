@@ -99,6 +99,16 @@ int nb200_cf_apply(nb200_plan* plan, void* stream, const void* amp, const void* 
 int nb200_cf_apply_adjoint(nb200_plan* plan, void* stream, const void* amp, const void* xi, const void* cot,
                            void* xi_bar, void* amp_bar);
 
+/* Batched forms: what `jax.vmap` of the two operators above asks of the custom call (optimize_kl.py:106,135 maps over the
+ * sample axis with every leaf batched; test/test_re/test_empirical_power_spectrum.py:39 `VModel(cf, in_axes="xi")` batches
+ * the excitations only).  `batch` independent applications on consecutive grids: xi / out / cot / xi_bar advance by one
+ * grid (N elements) per item, amp / amp_bar by `amp_stride` / `amp_bar_stride` elements (K: one table per item; 0 for
+ * amp: one table shared by the batch).  amp_bar_stride must be K or amp_bar NULL. */
+int nb200_cf_apply_batch(nb200_plan* plan, void* stream, const void* amp, int64_t amp_stride, const void* xi, double offset, void* out,
+                         int64_t batch);
+int nb200_cf_apply_adjoint_batch(nb200_plan* plan, void* stream, const void* amp, int64_t amp_stride, const void* xi, const void* cot,
+                                 void* xi_bar, void* amp_bar, int64_t amp_bar_stride, int64_t batch);
+
 /* ---- model: CorrelatedFieldMaker (one sub-grid) + likelihood --------------------------------- */
 
 typedef struct nb200_model_desc {

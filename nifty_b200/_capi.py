@@ -77,6 +77,8 @@ SIGNATURES = {
     "nb200_hartley": (C.c_int, [vp, vp, vp, vp]),
     "nb200_cf_apply": (C.c_int, [vp, vp, vp, vp, f64, vp]),
     "nb200_cf_apply_adjoint": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "nb200_cf_apply_batch": (C.c_int, [vp, vp, vp, i64, vp, f64, vp, i64]),
+    "nb200_cf_apply_adjoint_batch": (C.c_int, [vp, vp, vp, i64, vp, vp, vp, vp, i64, i64]),
     "nb200_model_create": (C.c_int, [C.POINTER(vp), vp, C.POINTER(ModelDesc)]),
     "nb200_model_destroy": (None, [vp]),
     "nb200_model_set_likelihood": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, f64, vp]),

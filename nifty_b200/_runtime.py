@@ -358,6 +358,33 @@ class Plan:
                          self.rt.ptr(out))
         return out
 
+    def cf_apply_batch(self, amp: torch.Tensor, xi: torch.Tensor, offset: float = 0.0) -> torch.Tensor:
+        """`jax.vmap` form of :meth:`cf_apply`: xi [batch, *grid]; amp [K] (shared by the batch) or [batch, K]."""
+        amp, xi = self.rt.asarray(amp, self.dtype).contiguous(), self.rt.asarray(xi, self.dtype).contiguous()
+        batch = xi.shape[0]
+        if amp.ndim == 2 and amp.shape[0] != batch:
+            raise ValueError("cf_apply_batch: amp must be [K] or [batch, K]")
+        out = torch.empty_like(xi)
+        self.rt.api.call("nb200_cf_apply_batch", self._h, self.rt.stream(), self.rt.ptr(amp), self.K if amp.ndim == 2 else 0,
+                         self.rt.ptr(xi), float(offset), self.rt.ptr(out), int(batch))
+        return out
+
+    def cf_apply_adjoint_batch(self, amp, xi, cot):
+        """`jax.vmap` form of :meth:`cf_apply_adjoint`: cot / xi [batch, *grid]; amp [K] or [batch, K]; returns
+        (xi_bar [batch, *grid], amp_bar [batch, K] or None when xi is None)."""
+        amp, cot = self.rt.asarray(amp, self.dtype).contiguous(), self.rt.asarray(cot, self.dtype).contiguous()
+        batch = cot.shape[0]
+        xi_bar = torch.empty_like(cot)
+        amp_bar, xi_p = None, None
+        if xi is not None:
+            xi = self.rt.asarray(xi, self.dtype).contiguous()
+            amp_bar = self.rt.empty((batch, self.K), self.dtype)
+            xi_p = self.rt.ptr(xi)
+        self.rt.api.call("nb200_cf_apply_adjoint_batch", self._h, self.rt.stream(), self.rt.ptr(amp), self.K if amp.ndim == 2 else 0,
+                         xi_p, self.rt.ptr(cot), self.rt.ptr(xi_bar), self.rt.ptr(amp_bar) if amp_bar is not None else None,
+                         self.K, int(batch))
+        return xi_bar, amp_bar
+
     def cf_apply_adjoint(self, amp, xi, cot):
         amp, cot = self.rt.asarray(amp, self.dtype), self.rt.asarray(cot, self.dtype)
         xi_bar = torch.empty_like(cot)

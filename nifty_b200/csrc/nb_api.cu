@@ -403,6 +403,34 @@ int nb200_cf_apply_adjoint(nb200_plan* plan, void* stream, const void* amp, cons
   NB_CATCH
 }
 
+int nb200_cf_apply_batch(nb200_plan* plan, void* stream, const void* amp, int64_t amp_stride, const void* xi, double offset, void* out,
+                         int64_t batch) {
+  if (!plan || !amp || !xi || !out || batch < 0 || amp_stride < 0) return fail("nb200_cf_apply_batch: invalid argument");
+  const int64_t N = plan->impl->g.N;
+  const size_t w = plan->impl->dtype == 1 ? 8 : 4;
+  for (int64_t i = 0; i < batch; ++i) {
+    const int rc = nb200_cf_apply(plan, stream, (const char*)amp + (size_t)(i * amp_stride) * w, (const char*)xi + (size_t)(i * N) * w, offset,
+                                  (char*)out + (size_t)(i * N) * w);
+    if (rc) return rc;
+  }
+  return 0;
+}
+int nb200_cf_apply_adjoint_batch(nb200_plan* plan, void* stream, const void* amp, int64_t amp_stride, const void* xi, const void* cot,
+                                 void* xi_bar, void* amp_bar, int64_t amp_bar_stride, int64_t batch) {
+  if (!plan || !amp || !cot || !xi_bar || batch < 0 || amp_stride < 0) return fail("nb200_cf_apply_adjoint_batch: invalid argument");
+  if ((xi == nullptr) != (amp_bar == nullptr)) return fail("nb200_cf_apply_adjoint_batch: xi and amp_bar must be given together");
+  if (amp_bar && amp_bar_stride != plan->impl->g.K) return fail("nb200_cf_apply_adjoint_batch: amp_bar_stride must be K (one table of bin sums per item)");
+  const int64_t N = plan->impl->g.N;
+  const size_t w = plan->impl->dtype == 1 ? 8 : 4;
+  for (int64_t i = 0; i < batch; ++i) {
+    const int rc = nb200_cf_apply_adjoint(plan, stream, (const char*)amp + (size_t)(i * amp_stride) * w,
+                                          xi ? (const char*)xi + (size_t)(i * N) * w : nullptr, (const char*)cot + (size_t)(i * N) * w,
+                                          (char*)xi_bar + (size_t)(i * N) * w, amp_bar ? (char*)amp_bar + (size_t)(i * amp_bar_stride) * w : nullptr);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 int nb200_model_create(nb200_model** model, nb200_plan* plan, const nb200_model_desc* d) {
   NB_TRY
   if (!model || !plan || !d) return fail("nb200_model_create: null argument");

@@ -1,6 +1,7 @@
 // nifty_b200 -- launch / memory shims.  CUDA build: real kernels, cudaMalloc, streams.
 // tests/emu build (-DNB_EMU): the same bodies run block after block on the host (see nb_common.cuh).
 #pragma once
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(256, MinBlocks<Body>::value) nb_kernel(const _
 }
 
 // number of kernel launches issued by this library (bench.py reports it as gpu_launches)
-inline unsigned long long& launch_counter() { static unsigned long long c = 0; return c; }
+// (atomic: XLA / several host threads may launch concurrently, one thread per device)
+inline std::atomic<unsigned long long>& launch_counter() { static std::atomic<unsigned long long> c{0}; return c; }
 
 // optional per-kernel CUDA-event timing (instrumentation for bench.py's roofline section)
 struct KernelTimer {
@@ -137,17 +139,19 @@ struct KernelTimer {
   struct Rec { const char* name; cudaEvent_t a, b; };
   std::vector<Rec> recs;
 };
-inline KernelTimer& kernel_timer() { static KernelTimer t; return t; }
+inline KernelTimer& kernel_timer() { static thread_local KernelTimer t; return t; }      // (per host thread)
 
 template <class Body>
 inline void launch(int grid, int block, size_t smem, stream_t s, const typename Body::Params& p) {
-  static size_t configured[64] = {0};
+  static std::atomic<size_t> configured[64];          // per device: largest dynamic shared-memory size set so far
   int dev = 0;
   NB_CUDA_CHECK(cudaGetDevice(&dev));
   smem += 512;   // reduction scratch behind the line buffers
-  if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+  if (dev >= 0 && dev < 64 && smem > configured[dev].load(std::memory_order_acquire)) {
+    // (racing threads may both set the attribute: harmless, the attribute only grows)
     NB_CUDA_CHECK(cudaFuncSetAttribute(nb_kernel<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[dev] = smem;
+    size_t cur = configured[dev].load(std::memory_order_relaxed);
+    while (cur < smem && !configured[dev].compare_exchange_weak(cur, smem, std::memory_order_release)) {}
   }
   static const bool trace = std::getenv("NB200_TRACE") != nullptr;     // developer aid: every launch on stderr
   if (trace) std::fprintf(stderr, "[nb200] launch %s grid=%d block=%d smem=%zu\n", typeid(Body).name(), grid, block, smem);

@@ -94,7 +94,19 @@ class Gaussian(Likelihood):
         else:
             w = noise_std_inv
         if callable(w):
-            w = w(torch.ones(shape, dtype=torch.float64))
+            # only DIAGONAL operators are supported: the diagonal is read off a vector of ones and the
+            # callable is then checked on two random probes -- anything that is not `x -> diag * x` raises instead of being
+            # silently treated as diagonal
+            fn = w
+            w = fn(torch.ones(shape, dtype=torch.float64))
+            gen = torch.Generator().manual_seed(12345)
+            for _ in range(2):
+                probe = torch.randn(shape, dtype=torch.float64, generator=gen)
+                got = torch.as_tensor(fn(probe), dtype=torch.float64)
+                want = torch.as_tensor(w, dtype=torch.float64) * probe
+                if got.shape != want.shape or not torch.allclose(got, want, rtol=1e-10, atol=1e-12 * float(want.abs().max() + 1e-300)):
+                    raise NotImplementedError("Gaussian: the noise covariance callable is not a diagonal operator; only diagonal "
+                                              "(inverse) covariances are supported on the B200 path")
         if noise_cov_inv is None and noise_std_inv is not None:
             w = w * w
         if np.ndim(w) == 0 if not isinstance(w, torch.Tensor) else w.ndim == 0:

@@ -146,14 +146,21 @@ class OptimizeVI:
         if self.comm.world > 1 and not plan.dist:
             # KL metric over several ranks: the last pass hands its result to the all-reduce in pieces (NVLink transfer of
             # one piece beside the computation of the next)
-            plan.set_reduce_chunks(int(os.environ.get("NB200_REDUCE_CHUNKS", "4")))
+            plan.set_reduce_chunks(int(os.environ.get("NB200_REDUCE_CHUNKS", "1")))
         self._draw_linear_residual = _draw_linear_residual
         self._nonlinearly_update_residual = _nonlinearly_update_residual
         self._kl_vg_override, self._kl_met_override = _kl_value_and_grad, _kl_metric
         self._lins = []      # one linearisation per local sample point, reused across KL evaluations
 
     # -- sample bookkeeping -----------------------------------------------------------------------
+    def _mirror_split(self, n_keys) -> bool:
+        """The reference's special case `n_samples == mesh.size / 2` (optimize_kl.py:403-405, 437-439): every key is drawn by
+        TWO devices and the odd one keeps the mirrored sample, so that the 2 n_samples points of the KL land one per device."""
+        return self.comm.world > 1 and 2 * n_keys == self.comm.world
+
     def _local_keys(self, keys):
+        if keys is not None and self._mirror_split(len(keys)):
+            return keys[self.comm.rank // 2:self.comm.rank // 2 + 1]
         return keys[self.comm.rank::self.comm.world]
 
     def _n_global(self, n_local_points):
@@ -170,14 +177,22 @@ class OptimizeVI:
             infos.append(info)
         L = self.likelihood.layout.size
         smpls = torch.stack(res) if res else torch.empty((0, L), dtype=self.likelihood.dtype, device=self.likelihood.rt.device)
-        smpls = concatenate_zip(smpls, -smpls)
+        if self._mirror_split(len(keys)):
+            smpls = smpls if self.comm.rank % 2 == 0 else -smpls          # `_special_mirror_samples` (:421-423)
+        else:
+            smpls = concatenate_zip(smpls, -smpls)
         return Samples(pos=primals, samples=smpls, keys=keys), infos
 
     def nonlinearly_update_samples(self, samples: Samples, **kwargs):
         """optimize_kl.py:446-476: the same key for both signs, metric_sample_sign = +1 / -1."""
         local = self._local_keys(samples.keys)
-        assert len(samples) == 2 * len(local)
         out, states = [], []
+        if self._mirror_split(len(samples.keys)):      # one point per rank: the key's sample on even ranks, its mirror on odd ones
+            assert len(samples) == 1 and len(local) == 1
+            sign = 1.0 if self.comm.rank % 2 == 0 else -1.0
+            r, st = self._nonlinearly_update_residual(self.likelihood, samples.pos, samples.residuals[0], local[0], sign, **kwargs)
+            return Samples(pos=samples.pos, samples=torch.stack([r]), keys=samples.keys), [st]
+        assert len(samples) == 2 * len(local)
         for i, k in enumerate(local):
             for s, sign in enumerate((1.0, -1.0)):
                 r, st = self._nonlinearly_update_residual(self.likelihood, samples.pos, samples.residuals[2 * i + s], k, sign, **kwargs)
@@ -354,8 +369,12 @@ def _samples_to_checkpoint(samples: Samples, likelihood, comm) -> Samples:
         per_key = 2 if n_keys and sum(p.shape[0] for p in parts) == 2 * n_keys else 1
         total = sum(p.shape[0] for p in parts)
         full = np.empty((total, lay.size), dtype=parts[0].cpu().numpy().dtype)
+        mirror_split = comm.world > 1 and 2 * n_keys == comm.world and all(p.shape[0] == 1 for p in parts)
         for r, p in enumerate(parts):
             pn = p.detach().cpu().numpy()
+            if mirror_split:                      # rank r holds global sample r (key r // 2, sign r % 2)
+                full[r] = pn[0]
+                continue
             for i in range(pn.shape[0] // per_key):
                 g = (r + i * comm.world) * per_key
                 full[g:g + per_key] = pn[i * per_key:(i + 1) * per_key]
@@ -374,7 +393,10 @@ def _samples_from_checkpoint(ck: Samples, likelihood, rank, world) -> Samples:
         full = np.stack([lay.pack_numpy({k: v[i] for k, v in ck.residuals.items()}) for i in range(total)])
         n_keys = 0 if ck.keys is None else len(ck.keys)
         per_key = 2 if n_keys and total == 2 * n_keys else 1
-        idx = [g * per_key + s for g in range(rank, total // per_key, world) for s in range(per_key)]
+        if world > 1 and per_key == 2 and 2 * n_keys == world:
+            idx = [rank]                          # the `n_samples == n_devices / 2` layout: one point per rank
+        else:
+            idx = [g * per_key + s for g in range(rank, total // per_key, world) for s in range(per_key)]
         res = torch.as_tensor(full[idx], dtype=dt, device=dev)
     return Samples(pos=pos, samples=res, keys=ck.keys)
 

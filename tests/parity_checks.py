@@ -88,6 +88,21 @@ def check_bilinear(rt, shape, distances, dtype=torch.float64, seed=1):
     assert rel_err(t2n(ab), np.bincount(idx.ravel(), weights=(xi * g).ravel(), minlength=um.size)) < 10 * TOL[dtype]
     xb2, none = plan.cf_apply_adjoint(torch.as_tensor(amp), None, torch.as_tensor(cot))
     assert none is None and rel_err(t2n(xb2), amp[idx] * g) < TOL[dtype]
+    # batched forms (the vmap rules of a jax.ffi binding): identical to looped single calls, with the amplitude table shared
+    # by the batch (`VModel(cf, in_axes="xi")`) or batched with it (the sample axis of optimize_kl.py:106,135)
+    B = 3
+    amps = rng.standard_normal((B, um.size)) ** 2
+    xis, cots = rng.standard_normal((B,) + tuple(shape)), rng.standard_normal((B,) + tuple(shape))
+    for a_in in (amps, amps[1]):
+        ob = plan.cf_apply_batch(torch.as_tensor(a_in), torch.as_tensor(xis), 0.3)
+        xbb, abb = plan.cf_apply_adjoint_batch(torch.as_tensor(a_in), torch.as_tensor(xis), torch.as_tensor(cots))
+        xbb2, nb2 = plan.cf_apply_adjoint_batch(torch.as_tensor(a_in), None, torch.as_tensor(cots))
+        assert nb2 is None
+        for i in range(B):
+            a_i = torch.as_tensor(a_in[i] if a_in.ndim == 2 else a_in)
+            assert torch.equal(ob[i], plan.cf_apply(a_i, torch.as_tensor(xis[i]), 0.3))
+            xs, as_ = plan.cf_apply_adjoint(a_i, torch.as_tensor(xis[i]), torch.as_tensor(cots[i]))
+            assert torch.equal(xbb[i], xs) and torch.equal(abb[i], as_) and torch.equal(xbb2[i], xs)
 
 
 def check_golden(rt, name, dtype=torch.float64):

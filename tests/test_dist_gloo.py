@@ -43,8 +43,16 @@ def _worker(rank, world, port, outdir):
     s2, st = nb.optimize_kl(lh, pos, key=5, n_total_iterations=1, n_samples=2, odir=os.path.join(outdir, "ckpt"), comm=True,
                             sample_mode="linear_resample", draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=60)),
                             kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=30))))
+    # n_samples == world / 2: every key is drawn by two ranks, the odd one keeps the mirrored sample (optimize_kl.py:403-405)
+    sm, _ = vi.draw_linear_samples(pos, nb.random_split(77, 1), cg_kwargs=dict(absdelta=1e-8, maxiter=60))
+    vm, gm = vi.kl_value_and_grad(pos, sm.residuals)
+    s3, st3 = nb.optimize_kl(lh, pos, key=6, n_total_iterations=1, n_samples=1, odir=os.path.join(outdir, "ckpt_m"), comm=True,
+                             sample_mode="nonlinear_resample", draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=60)),
+                             nonlinearly_update_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=20))),
+                             kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=30))))
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), res=samples.residuals.numpy(), v=v, g=gr.numpy(), m=m.numpy(),
-             pos2=s2.pos.numpy(), nloc=len(samples))
+             pos2=s2.pos.numpy(), nloc=len(samples), res_m=sm.residuals.numpy(), vm=vm, gm=gm.numpy(), pos3=s3.pos.numpy(),
+             res3=s3.residuals.numpy())
     dist.destroy_process_group()
 
 
@@ -78,3 +86,22 @@ def test_sample_sharding_matches_single_process(tmp_path):
         np.testing.assert_allclose(r[i]["m"], m.numpy(), rtol=0, atol=1e-12 * np.abs(m.numpy()).max())
     np.testing.assert_array_equal(r[0]["pos2"], r[1]["pos2"])   # replicated position stays bit-identical across ranks
     assert os.path.isfile(tmp_path / "ckpt" / "last.pkl")
+    # mirror rule: rank 0 holds +s0, rank 1 holds -s0; the KL equals the single-process KL over [s0, -s0]
+    sm, _ = vi.draw_linear_samples(pos, nb.random_split(77, 1), cg_kwargs=dict(absdelta=1e-8, maxiter=60))
+    vm, gm = vi.kl_value_and_grad(pos, sm.residuals)
+    assert r[0]["res_m"].shape[0] == 1 and r[1]["res_m"].shape[0] == 1
+    np.testing.assert_allclose(np.concatenate([r[0]["res_m"], r[1]["res_m"]]), sm.residuals.numpy(), rtol=0, atol=1e-13)
+    for i in range(world):
+        assert abs(r[i]["vm"] - vm) <= 1e-12 * abs(vm)
+        np.testing.assert_allclose(r[i]["gm"], gm.numpy(), rtol=0, atol=1e-12 * np.abs(gm.numpy()).max())
+    s3, st3 = nb.optimize_kl(lh, pos, key=6, n_total_iterations=1, n_samples=1, sample_mode="nonlinear_resample",
+                             draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=60)),
+                             nonlinearly_update_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=20))),
+                             kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=30))))
+    np.testing.assert_allclose(r[0]["pos3"], s3.pos.numpy(), rtol=0, atol=1e-9 * np.abs(s3.pos.numpy()).max())
+    np.testing.assert_allclose(np.concatenate([r[0]["res3"], r[1]["res3"]]), s3.residuals.numpy(), rtol=0,
+                               atol=1e-8 * np.abs(s3.residuals.numpy()).max())
+    import pickle
+    with open(tmp_path / "ckpt_m" / "last.pkl", "rb") as f:
+        ck, _ = pickle.load(f)
+    assert next(iter(ck.residuals.values())).shape[0] == 2

@@ -57,3 +57,20 @@ def test_mean_std_stack():
     assert st["b"].shape == (5, 3, 2)
     back = nb.unstack(st)
     assert len(back) == 5 and all(torch.equal(back[i][k], forest[i][k]) for i in range(5) for k in forest[0])
+
+
+def test_gaussian_callable_covariance_must_be_diagonal():
+    """`Gaussian(noise_cov_inv=callable)`: a diagonal operator is accepted (its diagonal is read off), anything else raises
+    instead of being silently treated as diagonal (likelihood_impl.py:35-80 accepts arbitrary callables; this path does not)."""
+    import numpy as np
+    import pytest
+    import torch
+    from nifty_b200.likelihood import Gaussian
+    d = np.zeros((4, 6))
+    w = torch.linspace(1.0, 2.0, 24, dtype=torch.float64).reshape(4, 6)
+    lh = Gaussian(d, noise_cov_inv=lambda x: w * x)
+    assert lh.w_array is not None and torch.equal(torch.as_tensor(lh.w_array), w)
+    lh = Gaussian(d, noise_std_inv=lambda x: 3.0 * x)
+    assert torch.allclose(torch.as_tensor(lh.w_array), torch.full((4, 6), 9.0, dtype=torch.float64))
+    with pytest.raises(NotImplementedError):
+        Gaussian(d, noise_cov_inv=lambda x: x + torch.roll(x, 1, 1))          # couples neighbours
