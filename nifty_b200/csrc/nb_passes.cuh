@@ -744,6 +744,7 @@ template <class T> struct EpiPlain {
   static constexpr bool BATCHED = false;
   struct Pre {};
   NB_HD NB_INLINE void preload(long, long, long, int, int, Pre&) const {}
+  NB_HD NB_INLINE void preload_bin(long, long, int, int, int, Pre&) const {}
   NB_HD NB_INLINE void gather(Pre&) const {}
   NB_HD NB_INLINE void finish(long, long, long, int, int, T, T, T, T, const Pre&, T&) const {}
   T* out; T scale;
@@ -775,6 +776,14 @@ template <class T> struct EpiAdjoint {
     if (xi) { q.x0 = ld_stream(xi + rowA + x); q.x1 = ld_stream(xi + rowA + y); q.x2 = ld_stream(xi + rowB + x); q.x3 = ld_stream(xi + rowB + y); }
   }
   NB_HD NB_INLINE void gather(Pre& q) const { q.A = ldg(amp + q.b); }
+  // the same with the bin index already at hand (index rows staged in shared memory): the table gather goes out together
+  // with the streaming loads, no dependent second round
+  NB_HD NB_INLINE void preload_bin(long rowA, long rowB, int b, int x, int y, Pre& q) const {
+    q.b = b; q.A = ldg(amp + b);
+    q.a0 = q.a1 = q.a2 = q.a3 = q.x0 = q.x1 = q.x2 = q.x3 = 0;
+    if (add) { q.a0 = ld_stream(add + rowA + x); q.a1 = ld_stream(add + rowA + y); q.a2 = ld_stream(add + rowB + x); q.a3 = ld_stream(add + rowB + y); }
+    if (xi) { q.x0 = ld_stream(xi + rowA + x); q.x1 = ld_stream(xi + rowA + y); q.x2 = ld_stream(xi + rowB + x); q.x3 = ld_stream(xi + rowB + y); }
+  }
   NB_HD NB_INLINE void finish(long rowA, long rowB, long wbase, int x, int y, T gAx, T gAy, T gBx, T gBy, const Pre& q,
                               T& acc) const {
     gAx *= invV; gAy *= invV; gBx *= invV; gBy *= invV;
@@ -832,6 +841,7 @@ template <class T, class Epi> struct P5Params {
   const long* src_off; const int* src_mul;
   int ahead;
   int line0;
+  int sidx_off;   // byte offset of the staged bin-index rows in shared memory (0: the epilogue reads them from global memory)
   Epi epi;
   // staged chain (nb_passes2.cuh): the lines are columns of the row-major output of the previous pass and are
   // gathered into the line buffers by the TMA engine (gather != 0) instead of being read from `in`
@@ -863,6 +873,28 @@ template <class T, class Epi, int MINB = 2, bool PIPE = true> struct P5Body {
     const int pbid = (p.line0 >> p.lg_R) + ctx.bid;
     fill_line_info(ctx, li, p.mg, l0, R);
     T acc = 0;
+    // bin-index rows of the CTA's lines -> shared memory behind the line buffers (eight loads in flight per thread, landing
+    // while the lines are gathered): the epilogue then issues its amplitude gathers together with its streaming loads
+    int* sidx = nullptr;
+    if constexpr (Epi::BATCHED) {
+      if (p.sidx_off) {
+        sidx = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(smem) + p.sidx_off);
+        const int nmid = 1 << p.mg.lg_mid, tot = R * (h + 1);
+        constexpr int U = 8;
+        for (int i0 = ctx.tid; i0 < tot; i0 += ctx.nthr * U) {
+          int rv[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * ctx.nthr, ii = i < tot ? i : 0, r = ii / (h + 1), k = ii - r * (h + 1);
+            const int a = li[r].lA >> p.mg.lg_mid, km = li[r].lA & (nmid - 1);
+            const long fbase = ((long)a * p.hmid1 + fold_idx(km, nmid)) * (h + 1);
+            rv[u] = li[r].active ? ldg(p.epi.idxf + fbase + k) : 0;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) { const int i = i0 + u * ctx.nthr; if (i < tot) sidx[i] = rv[u]; }
+        }
+      }
+    }
     for (int r = 0; r < R && p.ahead > 0; ++r) {
       if (!li[r].active) continue;
       const int nmid = 1 << p.mg.lg_mid;
@@ -925,7 +957,8 @@ template <class T, class Epi, int MINB = 2, bool PIPE = true> struct P5Body {
           int a = li[r].lA >> p.mg.lg_mid, km = li[r].lA & (nmid - 1);
           long fbase = ((long)a * p.hmid1 + fold_idx(km, nmid)) * (h + 1);
           sl[u].px = ldg(p.fft.pos + x); sl[u].py = ldg(p.fft.pos + (n - x));
-          p.epi.preload((long)li[r].lA * n, (long)(li[r].lB >= 0 ? li[r].lB : li[r].lA) * n, fbase, x, n - x, sl[u].pre);
+          if (sidx) p.epi.preload_bin((long)li[r].lA * n, (long)(li[r].lB >= 0 ? li[r].lB : li[r].lA) * n, sidx[r * (h + 1) + x], x, n - x, sl[u].pre);
+          else p.epi.preload((long)li[r].lA * n, (long)(li[r].lB >= 0 ? li[r].lB : li[r].lA) * n, fbase, x, n - x, sl[u].pre);
         }
       };
       auto consume = [&](int, const Slot* sl) {
@@ -940,6 +973,7 @@ template <class T, class Epi, int MINB = 2, bool PIPE = true> struct P5Body {
         }
       };
       auto gather = [&](Slot* sl) {
+        if (sidx) return;
 #pragma unroll
         for (int u = 0; u < U; ++u) p.epi.gather(sl[u].pre);
       };

@@ -28,6 +28,10 @@
 #include "nb_passes.cuh"
 #include "nb_fft16.cuh"
 
+#ifndef NB_P5F_CHK
+#define NB_P5F_CHK 8      // amplitude gathers in flight per thread in the staged epilogue of the last pass
+#endif
+
 namespace nb {
 
 // shared-memory carve-up of a staged pass
@@ -133,12 +137,13 @@ template <class T> struct P5FParams {
   int line0, nlines;       // line range of this launch
   int ntiles;
   int prefetch;            // L2 bulk prefetch of the epilogue rows of the next tile
+  int staged_epi;          // epilogue inputs through shared memory (run_staged)
   EpiAdjoint<T> epi;
 };
 
 struct L5Info { long rowA, rowB, fbase, wbase; int active, pad; };
 
-template <class T, int LG> struct P5FBody {
+template <class T, int LG, bool SE = false> struct P5FBody {
   typedef P5FParams<T> Params;
   static constexpr int kMinBlocks = 2;
   typedef Fft16<T, LG, false> F;
@@ -173,7 +178,170 @@ template <class T, int LG> struct P5FBody {
     }
   }
 
+  // ---- epilogue with its inputs in shared memory ----------------------------------------------------------
+  // The register-resident epilogue below pays two dependent global round trips per chunk of four elements (bin index ->
+  // amplitude, beside the streaming rows): eight per tile, the largest part of the tile time at 16 warps per SM.  Here
+  //   * the bin-index rows of the tile are copied to shared memory while the gather of the tile lands,
+  //   * the `add` rows (A and B of every line: exactly the 64 KB of the staging buffer) arrive by bulk copies during the
+  //     transform, the `xi` A rows (32 KB: the exchange buffer) by bulk copies issued right after it,
+  //   * so the epilogue is two rounds of eight amplitude gathers (+ the xi B row from global memory) per thread.
+  // `add` may alias `out`: the rows of a tile are copied before any of its outputs is stored.
+  static constexpr size_t SIDX_OFF = SL::BYTES + 512;
+  static constexpr size_t SIDX_BYTES = (size_t)(F16_TILE / 2 + LPC + 8) * sizeof(int);
+  static constexpr size_t BYTES_STAGED = SL::BYTES + SIDX_BYTES;
+  static NB_HD NB_INLINE void issue_rows(const Params& p, int lane, int tile, const T* src, T* dst, bool both, Mbar* bar) {
+    const int l0 = p.line0 + tile * LPC;
+    constexpr unsigned ROW = (unsigned)(N * sizeof(T));
+    constexpr unsigned PIECE = ROW > 32768u ? 32768u : ROW;
+    for (int i = lane; i < LPC; i += 32) {
+      L5Info q;
+      if (!line_info(p, l0 + i, q)) continue;
+      const bool hasB = both && q.rowB >= 0;
+      mbar_expect_tx(bar, hasB ? 2 * ROW : ROW);
+      T* d = dst + (size_t)i * (both ? 2 * N : N);
+      for (unsigned o = 0; o < ROW; o += PIECE) {
+        bulk_g2s(reinterpret_cast<char*>(d) + o, reinterpret_cast<const char*>(src + q.rowA) + o, PIECE, bar);
+        if (hasB) bulk_g2s(reinterpret_cast<char*>(d + N) + o, reinterpret_cast<const char*>(src + q.rowB) + o, PIECE, bar);
+      }
+    }
+    warp_sync();
+    if (lane == 0) mbar_arrive(bar);
+  }
+  static NB_HD void run_staged(Ctx& ctx, const Params& p, void* smem) {
+    unsigned char* sm = reinterpret_cast<unsigned char*>(smem);
+    cplx<T>* stage = reinterpret_cast<cplx<T>*>(sm);
+    T* sadd = reinterpret_cast<T*>(sm);
+    typename F::word_t* xb = reinterpret_cast<typename F::word_t*>(sm + SL::XB_OFF);
+    T* sxi = reinterpret_cast<T*>(sm + SL::XB_OFF);
+    L5Info* li = reinterpret_cast<L5Info*>(sm + SL::INFO_OFF);
+    Mbar* bar = reinterpret_cast<Mbar*>(sm + SL::BAR_OFF);
+    Mbar* bar2 = bar + 1; Mbar* bar3 = bar + 2;
+    void* scratch = reinterpret_cast<void*>(sm + SL::SCRATCH_OFF);
+    int* sidx = reinterpret_cast<int*>(sm + SIDX_OFF);
+    Team<TS> tm(ctx);
+    tm.all([&](int vt, TS& S) { F::init(S.th, vt, p.tw, 1); S.acc = 0; });
+    tm.one([&]() { mbar_init(bar, 1); mbar_init(bar2, 1); mbar_init(bar3, 1); });
+    tm.sync();
+    int tile = ctx.bid;
+    unsigned phase = 0;
+    if (tile < p.ntiles) tm.warp0([&](int lane) { issue(p, lane, tile, stage, bar); });
+    const T sg = p.hsign, iv = p.epi.invV;
+    const EpiAdjoint<T>& E = p.epi;
+    for (; tile < p.ntiles; tile += ctx.nblk) {
+      const int l0 = p.line0 + tile * LPC;
+      tm.all([&](int vt, TS&) { if (vt < LPC) { L5Info q; line_info(p, l0 + vt, q); li[vt] = q; } });
+      tm.sync();
+      tm.coop([&](Ctx& c) {              // bin-index rows -> shared memory (eight loads in flight per thread)
+        constexpr int U = 8, TOT = LPC * (H + 1);
+        for (int i0 = c.tid; i0 < TOT; i0 += c.nthr * U) {
+          int r[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * c.nthr, ii = i < TOT ? i : 0, ln = ii / (H + 1), k = ii - ln * (H + 1);
+            r[u] = li[ln].active ? ldg(E.idxf + li[ln].fbase + k) : 0;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) { const int i = i0 + u * c.nthr; if (i < TOT) sidx[i] = r[u]; }
+        }
+      });
+      tm.all([&](int, TS& S) {
+        mbar_wait(bar, phase);
+        if (li[S.th.r].active != 0) {
+#pragma unroll
+          for (int s = 0; s < 16; ++s) S.a[s] = stage[S.th.r * N + F::elem(S.th, s)];
+        } else {
+#pragma unroll
+          for (int s = 0; s < 16; ++s) S.a[s] = cmake<T>(0, 0);
+        }
+      });
+      tm.sync();
+      if (E.add) tm.warp0([&](int lane) { if (lane == 0) fence_async_smem(); warp_sync(); issue_rows(p, lane, tile, E.add, sadd, true, bar2); });
+      tm.all([&](int vt, TS& S) { F::init(S.th, vt, p.tw, 1); });
+      F::run(tm, xb);
+      tm.sync();
+      if (E.xi && E.W) tm.warp0([&](int lane) { if (lane == 0) fence_async_smem(); warp_sync(); issue_rows(p, lane, tile, E.xi, sxi, false, bar3); });
+      tm.all([&](int, TS& S) {
+        if (E.add) mbar_wait(bar2, phase);
+        const L5Info q = li[S.th.r];
+        if (!q.active) return;
+        const bool hasB = q.rowB >= 0;
+        const T* aArow = sadd + (size_t)S.th.r * 2 * N;
+        const T* aBrow = aArow + N;
+        const int* irow = sidx + S.th.r * (H + 1);
+        constexpr int CHK = NB_P5F_CHK;
+#pragma unroll
+        for (int c = 0; c < 16; c += CHK) {
+          T A[CHK], xB[CHK];
+#pragma unroll
+          for (int u = 0; u < CHK; ++u) {
+            const int x = F::elem(S.th, c + u), y = (N - x) & (N - 1);
+            A[u] = ldg(E.amp + irow[fold_idx(x, N)]);
+            xB[u] = (E.xi && E.W && hasB) ? ld_ro(E.xi + q.rowB + y) : T(0);
+          }
+#pragma unroll
+          for (int u = 0; u < CHK; ++u) {
+            const int x = F::elem(S.th, c + u), y = (N - x) & (N - 1);
+            const cplx<T> z = S.a[c + u];
+            const T gA = (z.x + sg * z.y) * iv, gB = hasB ? (z.x - sg * z.y) * iv : T(0);
+            const T aA = E.add ? aArow[x] : T(0);
+            const T oA = A[u] * gA + aA;
+            E.out[q.rowA + x] = oA;
+            T dot = aA * oA;
+            if (hasB) {
+              const T aB = E.add ? aBrow[y] : T(0);
+              const T oB = A[u] * gB + aB;
+              E.out[q.rowB + y] = oB;
+              dot += aB * oB;
+            }
+            S.acc += dot;
+            S.a[c + u] = cmake<T>(gA, xB[u] * gB);     // kept for the mode-bin sums below
+          }
+        }
+        if (E.W) {
+          if (E.xi) mbar_wait(bar3, phase);
+          const T* xrow = sxi + (size_t)S.th.r * N;
+#pragma unroll
+          for (int s = 0; s < 16; ++s) {
+            const int x = F::elem(S.th, s);
+            S.a[s].x = (E.xi ? xrow[x] : T(0)) * S.a[s].x + S.a[s].y;      // this thread's two mirror points
+          }
+        }
+      });
+      phase ^= 1u;
+      tm.sync();          // the staged rows have been consumed: the staging buffer may take the next tile, the exchange buffer the sums
+      if (tile + ctx.nblk < p.ntiles) tm.warp0([&](int lane) { if (lane == 0) fence_async_smem(); warp_sync(); issue(p, lane, tile + ctx.nblk, stage, bar); });
+      if (E.W) {
+        tm.all([&](int, TS& S) {
+          if (!li[S.th.r].active) return;
+          T* wv = reinterpret_cast<T*>(xb);
+#pragma unroll
+          for (int s = 0; s < 16; ++s) wv[S.th.r * N + F::elem(S.th, s)] = S.a[s].x;
+        });
+        tm.sync();
+        tm.all([&](int, TS& S) {
+          const L5Info q = li[S.th.r];
+          if (!q.active) return;
+          const T* xl = reinterpret_cast<const T*>(xb) + S.th.r * N;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int xf = S.th.t + M * j;
+            T w = xl[xf];
+            if (xf != 0) w += xl[N - xf];
+            E.W[q.wbase + xf] = w;
+          }
+          if (S.th.t == 0) E.W[q.wbase + H] = xl[H];
+        });
+      }
+      tm.sync();
+    }
+    if (E.partials) {
+      T tot = team_sum(tm, scratch, [](const TS& S) { return S.acc; });
+      tm.one([&]() { E.partials[ctx.bid] = tot; });
+    }
+  }
+
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
+    if constexpr (SE) { run_staged(ctx, p, smem); return; }
     unsigned char* sm = reinterpret_cast<unsigned char*>(smem);
     cplx<T>* stage = reinterpret_cast<cplx<T>*>(sm);
     typename F::word_t* xb = reinterpret_cast<typename F::word_t*>(sm + SL::XB_OFF);
@@ -290,6 +458,7 @@ template <class T> struct P3FParams {
   cplx<T>* out;            // [position line][k in 0..n/2]
   int line0, nlines, ntiles;
   int prefetch;
+  int stage_jl;            // Jacobian weights through the staging buffer (bulk copies) instead of per-thread global loads
   PointOp<T> op;
 };
 
@@ -327,16 +496,38 @@ template <class T, int LG> struct P3FBody {
     }
   }
 
+  // the Jacobian weights of the lines of a tile -> the staging buffer (jl of line i: A row at doubles [2 N i, 2 N i + N),
+  // B row behind it), bulk copies completing on `bar`
+  static NB_HD NB_INLINE void issue_jl(const Params& p, int lane, int tile, T* sj, Mbar* bar) {
+    const int l0 = p.line0 + tile * LPC;
+    constexpr unsigned ROW = (unsigned)(N * sizeof(T));
+    constexpr unsigned PIECE = ROW > 32768u ? 32768u : ROW;
+    for (int i = lane; i < LPC; i += 32) {
+      LineInfo q;
+      if (!line_info(p, l0 + i, q)) continue;
+      mbar_expect_tx(bar, q.lB >= 0 ? 2 * ROW : ROW);
+      for (unsigned o = 0; o < ROW; o += PIECE) {
+        bulk_g2s(reinterpret_cast<char*>(sj + (size_t)i * 2 * N) + o, reinterpret_cast<const char*>(p.op.jl_a + (long)q.lA * N) + o, PIECE, bar);
+        if (q.lB >= 0)
+          bulk_g2s(reinterpret_cast<char*>(sj + (size_t)i * 2 * N + N) + o, reinterpret_cast<const char*>(p.op.jl_a + (long)q.lB * N) + o, PIECE, bar);
+      }
+    }
+    warp_sync();
+    if (lane == 0) mbar_arrive(bar);
+  }
+
   static NB_HD void run(Ctx& ctx, const Params& p, void* smem) {
     unsigned char* sm = reinterpret_cast<unsigned char*>(smem);
     cplx<T>* stage = reinterpret_cast<cplx<T>*>(sm);
+    T* sj = reinterpret_cast<T*>(sm);
     typename F::word_t* xb = reinterpret_cast<typename F::word_t*>(sm + SL::XB_OFF);
     LineInfo* li = reinterpret_cast<LineInfo*>(sm + SL::INFO_OFF);
     Mbar* bar = reinterpret_cast<Mbar*>(sm + SL::BAR_OFF);
+    Mbar* bar2 = bar + 1;
     void* scratch = reinterpret_cast<void*>(sm + SL::SCRATCH_OFF);
     Team<TS> tm(ctx);
     tm.all([&](int vt, TS& S) { F::init(S.th, vt, p.tw, 1); S.acc = 0; S.zh = cmake<T>(0, 0); });
-    tm.one([&]() { mbar_init(bar, 1); });
+    tm.one([&]() { mbar_init(bar, 1); mbar_init(bar2, 1); });
     tm.sync();
     int tile = ctx.bid;
     unsigned phase = 0;
@@ -345,6 +536,10 @@ template <class T, int LG> struct P3FBody {
     const T cshift = p.op.cshift_ptr ? p.op.cshift_scale * ldg(p.op.cshift_ptr) : T(0);
     const T* ja = p.op.jl_a; const T* jb = p.op.jl_b;
     const bool same = (ja == jb);
+    // With one set of weights (the metric of ONE linearisation) the weights of the tile travel through the staging buffer
+    // too: bulk copies issued when the spectrum has been read into registers, landing during the first transform -- the
+    // pointwise loop then reads shared memory instead of paying four dependent L2 round trips per tile.
+    const bool sjl = same && p.stage_jl != 0;
     for (; tile < p.ntiles; tile += ctx.nblk) {
       const int l0 = p.line0 + tile * LPC;
       tm.all([&](int vt, TS&) { if (vt < LPC) { LineInfo q; line_info(p, l0 + vt, q); li[vt] = q; } });
@@ -359,16 +554,19 @@ template <class T, int LG> struct P3FBody {
           for (int s = 0; s < 16; ++s) S.a[s] = cmake<T>(0, 0);
         }
       });
-      phase ^= 1u;
       tm.sync();
-      if (tile + ctx.nblk < p.ntiles) tm.warp0([&](int lane) { if (lane == 0) fence_async_smem(); warp_sync(); issue(p, lane, tile + ctx.nblk, stage, bar); });
+      if (sjl) tm.warp0([&](int lane) { if (lane == 0) fence_async_smem(); warp_sync(); issue_jl(p, lane, tile, sj, bar2); });
+      else if (tile + ctx.nblk < p.ntiles) tm.warp0([&](int lane) { if (lane == 0) fence_async_smem(); warp_sync(); issue(p, lane, tile + ctx.nblk, stage, bar); });
       F::run(tm, xb);
       // pointwise operator on Z[x] -> A[x] = Re + sg Im (line lA), B[n-x] = Re - sg Im (line lB)
       tm.all([&](int, TS& S) {
         const LineInfo q = li[S.th.r];
+        if (sjl) mbar_wait(bar2, phase);
         if (!q.active) return;
         const bool hasB = q.lB >= 0;
         const long iA = (long)q.lA * N, iB = (long)(hasB ? q.lB : q.lA) * N;
+        const T* sA = sj + (size_t)S.th.r * 2 * N;
+        const T* sB = hasB ? sA + N : sA;
         constexpr int CHK = 4;
 #pragma unroll
         for (int c = 0; c < 16; c += CHK) {
@@ -376,9 +574,12 @@ template <class T, int LG> struct P3FBody {
 #pragma unroll
           for (int u = 0; u < CHK; ++u) {
             const int x = F::elem(S.th, c + u), y = (N - x) & (N - 1);
-            mA[u] = ld_ro(ja + iA + x); mB[u] = ld_ro(ja + iB + y);
-            if (!same) { mA[u] *= ld_ro(jb + iA + x); mB[u] *= ld_ro(jb + iB + y); }
-            else { mA[u] *= mA[u]; mB[u] *= mB[u]; }
+            if (sjl) { mA[u] = sA[x]; mB[u] = sB[y]; mA[u] *= mA[u]; mB[u] *= mB[u]; }
+            else {
+              mA[u] = ld_ro(ja + iA + x); mB[u] = ld_ro(ja + iB + y);
+              if (!same) { mA[u] *= ld_ro(jb + iA + x); mB[u] *= ld_ro(jb + iB + y); }
+              else { mA[u] *= mA[u]; mB[u] *= mB[u]; }
+            }
           }
 #pragma unroll
           for (int u = 0; u < CHK; ++u) {
@@ -390,7 +591,9 @@ template <class T, int LG> struct P3FBody {
           }
         }
       });
+      phase ^= 1u;
       tm.sync();
+      if (sjl && tile + ctx.nblk < p.ntiles) tm.warp0([&](int lane) { if (lane == 0) fence_async_smem(); warp_sync(); issue(p, lane, tile + ctx.nblk, stage, bar); });
       // (recomputing the per-thread transform constants here instead of carrying them across the tile keeps the
       // kernel inside its 128-register budget: 692 bytes of spills per thread otherwise)
       tm.all([&](int vt, TS& S) { F::init(S.th, vt, p.tw, 1); });

@@ -231,7 +231,10 @@ template <class T> struct Plan : PlanBase {
   bool staged_ok = false;       // float64, single GPU: the staged bodies apply
   bool chain_ok = false;        // ... and every pass of the metric chain is covered (line lengths 32 .. 4096)
   bool use_chain = false;       // set by the operator that runs the whole chain (ChainScope), read by run_*
-  bool p5f = false;             // NB200_P5F=1: register-resident last pass
+  int p5f_forced = -1;          // NB200_P5F=1 / 0: register-resident last pass forced on / off (default: chosen per shape)
+  bool p5_sidx = true;          // NB200_P5_SIDX=0: the last pass reads the bin indices of its epilogue from global memory
+  bool p5f_staged_epi = false;    // NB200_P5F_SE=0: the register-resident last pass loads its epilogue inputs per thread
+  bool p3_stage_jl = true;      // NB200_P3_SJL=0: per-thread global loads of the Jacobian weights in the staged axis-0 pass
   bool l2_prefetch = false;     // bulk L2 prefetch of the next tile's epilogue rows: measured slower (+50 % DRAM reads); NB200_L2PF=1 enables
   TmaDesc d_pca, d_p3, d_pcb, d_p5;
   int sms = 148;
@@ -395,7 +398,10 @@ template <class T> struct Plan : PlanBase {
       chain_ok = chain_ok && !g.three && lg0 >= 11 && lgl >= 11;
       if (const char* e = std::getenv("NB200_CHAIN")) { if (e[0] == '0') chain_ok = false; else if (e[0] == '1') chain_ok = chain_ok_shape; }
       if (const char* e = std::getenv("NB200_L2PF")) l2_prefetch = (e[0] == '1');
-      if (const char* e = std::getenv("NB200_P5F")) p5f = (e[0] == '1');
+      if (const char* e = std::getenv("NB200_P5F")) p5f_forced = (e[0] == '1') ? 1 : 0;
+      if (const char* e = std::getenv("NB200_P3_SJL")) p3_stage_jl = (e[0] == '1');
+      if (const char* e = std::getenv("NB200_P5F_SE")) p5f_staged_epi = (e[0] == '1');
+      if (const char* e = std::getenv("NB200_P5_SIDX")) p5_sidx = (e[0] == '1');
     }
     if (staged_ok) {
       // gather descriptors: P3 / P5 read column l of [n_line][(h+1) n_mid]; PCa / PCb read column k of the rows of one plane
@@ -544,7 +550,13 @@ template <class T> struct Plan : PlanBase {
 #undef NB_CALL
   }
   void launch_p5f(stream_t st, const P5FParams<T>& q, int gridf) {
-#define NB_CALL(LG) launch<P5FBody<T, LG>>(gridf, F16_NT, StageLayout<T, LG>::BYTES, st, q)
+    if (q.staged_epi) {
+#define NB_CALL(LG) launch<P5FBody<T, LG, true>>(gridf, F16_NT, P5FBody<T, LG, true>::BYTES_STAGED, st, q)
+      NB_LG_SWITCH(lgl, NB_CALL)
+#undef NB_CALL
+      return;
+    }
+#define NB_CALL(LG) launch<P5FBody<T, LG, false>>(gridf, F16_NT, StageLayout<T, LG>::BYTES, st, q)
     NB_LG_SWITCH(lgl, NB_CALL)
 #undef NB_CALL
   }
@@ -563,6 +575,7 @@ template <class T> struct Plan : PlanBase {
         P3FParams<T> q;
         q.desc = d_p3; q.mg = p.mg; q.tw = tw0.p; q.hsign = hsign; q.out = p.out;
         q.line0 = line0; q.nlines = nlines >= 0 ? nlines : p.mg.nlines(); q.op = op; q.prefetch = l2_prefetch ? 1 : 0;
+        q.stage_jl = p3_stage_jl ? 1 : 0;
         const int lpc = F16_TILE >> lg0;
         q.ntiles = (q.nlines + lpc - 1) / lpc;
         const int gridf = std::min(q.ntiles, 2 * sms);
@@ -598,17 +611,28 @@ template <class T> struct Plan : PlanBase {
     p.lg_n = lgl; p.lg_R = c5.lg_R; p.mg = mg5(); p.hmid1 = g.hm + 1; p.pitch = c5.pitch; p.tw = twl.p; p.lg_tw = lgl; p.fft = fl; p.ahead = c5.ahead;
     p.hsign = hsign; p.in = s1(); p.epi = epi;
     p.src_off = dist ? src_off5.p : nullptr; p.src_mul = dist ? src_mul5.p : nullptr;
-    const size_t sm5 = c5.smem + LINEINFO_BYTES;
+    size_t sm5 = c5.smem + LINEINFO_BYTES;
     n5part = c5.grid;
     p.gather = 0;
+    p.sidx_off = 0;
+    // measured (profiles/r3_notes.md): 180.4 -> 177.8 us on 4096-point lines, nothing on 2048, a loss on short 3-D lines
+    if (Epi::BATCHED && p5_sidx && lgl >= 12) {       // bin-index rows behind the line buffers and the reduction scratch
+      p.sidx_off = (int)(sm5 + 512);
+      sm5 += (((size_t)1 << c5.lg_R) * ((1 << (lgl - 1)) + 1) * sizeof(int) + 15) & ~size_t(15);
+    }
     if constexpr (Epi::BATCHED) {
-      // register-resident P5 (P5FBody): measured slower than the generic body (its epilogue is latency bound at 16 warps
-      // per SM), kept behind NB200_P5F=1; in a staged chain the generic body gathers its lines through the tensor map
-      if (p5f && staged_ok && lgl >= NB_FAST_LGMIN && lgl <= 12 && epi.add != epi.out) {    // (its read-only loads must not alias the output)
+      // register-resident P5 (P5FBody): its epilogue is latency bound at 16 warps per SM -- measured against the generic body
+      // (which gathers its lines through the tensor map in a staged chain): 173 vs 178 us on 4096-point lines, 59 vs 58 us
+      // on 2048, 232 vs 125 us at 256^3 -> chosen for 4096-point lines only (NB200_P5F=1 / 0 forces it on / off); its
+      // variant with the epilogue rows staged in shared memory (NB200_P5F_SE=1) measured 210 us
+      const bool p5f_here = p5f_forced >= 0 ? p5f_forced == 1 : (use_chain && lgl >= 12);
+      if (p5f_here && staged_ok && lgl >= NB_FAST_LGMIN && lgl <= 12 && (p5f_staged_epi || epi.add != epi.out)) {    // (run(): read-only loads must not alias the output)
         P5FParams<T> q;
         q.desc = d_p5; q.contig = use_chain ? nullptr : p.in;
         q.mg = p.mg; q.hmid1 = p.hmid1; q.tw = twl.p; q.hsign = hsign; q.line0 = line0;
-        q.nlines = nlines >= 0 ? nlines : p.mg.nlines(); q.epi = epi; q.prefetch = l2_prefetch ? 1 : 0;
+        q.nlines = nlines >= 0 ? nlines : p.mg.nlines(); q.epi = epi; q.prefetch = l2_prefetch ? 1 : 0; // (bulk copies of the epilogue rows need 16-byte aligned rows)
+        q.staged_epi = (p5f_staged_epi && ((uintptr_t)epi.add % 16) == 0 && ((uintptr_t)epi.xi % 16) == 0) ? 1 : 0;
+        if (!q.staged_epi && epi.add == epi.out) goto generic_p5;
         const int lpc = F16_TILE >> lgl;
         q.ntiles = (q.nlines + lpc - 1) / lpc;
         const int gridf = std::min(q.ntiles, 2 * sms);
@@ -617,6 +641,7 @@ template <class T> struct Plan : PlanBase {
         return;
       }
     }
+  generic_p5:
     if (use_chain) { p.gather = 1; p.desc = d_p5; }
     if (3 * (sm5 + 2048) <= size_t(100) * 1024) launch<P5Body<T, Epi, 3, false>>(grid5, c5.block, sm5, st, p);
     else launch<P5Body<T, Epi, 2, true>>(grid5, c5.block, sm5, st, p);
