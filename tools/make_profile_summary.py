@@ -28,14 +28,14 @@ rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 lines = [f"# ncu summary `{name}` ({workload}, one B200, `ncu --set full --clock-control none`)", "",
-         "Source: `tools/gpu_prof2.sh` -> `gpurun_out/prof_%s.ncu-rep`; values per launch.  Times under ncu are cold-cache and" % tag,
+         "Source: `tools/gpu_prof2.sh` / `tools/gpu_r3_prof.sh` -> `gpurun_out/prof_%s.ncu-rep`; values per launch.  Times under ncu are cold-cache and" % tag,
          "serialised: compare SHARES with bench.py's CUDA-event timings, not absolutes.", ""]
 traffic = {}
 seen = set()
 for r in rows[2:]:
     kn = r[idx['Kernel Name']]
-    short = [k for k in ("P1MBody", "P1Body", "P3Body", "P5Body", "PCBody", "SegSum", "ScanApplyBody<double, Vjp", "ScanApplyBody<double, Jvp",
-                         "ScanAggBody<double, Vjp", "ScanAggBody<double, Jvp") if k in kn]
+    short = [k for k in ("P1FBody", "P3FBody", "P5FBody", "PCFBody", "TanChain", "CotChain", "P1MBody", "P1Body", "P3Body", "P5Body", "PCBody", "SegSum",
+                         "ScanApplyBody<double, Vjp", "ScanApplyBody<double, Jvp", "ScanAggBody<double, Vjp", "ScanAggBody<double, Jvp") if k in kn]
     if not short or short[0] in seen:
         continue
     seen.add(short[0])
