@@ -407,22 +407,6 @@ def run_b200(args, shape, wname, rank, world, local_rank):
     torch.cuda.synchronize()
     draw_s = time.perf_counter() - ts
 
-    extras = {}
-    if world > 1 and os.environ.get("NB200_BENCH_EXTRAS", "1") != "0":
-        del t_host, out_host, t_dev, out_dev
-        try:
-            extras["kl_config3"] = kl_config3(nb, torch, dist, metric_multi, rank, world, dev, peak)
-        except Exception as e:  # pragma: no cover
-            extras["kl_config3"] = {"error": repr(e)[:300]}
-        if world == 8 and os.environ.get("NB200_BENCH_SLAB", "1") != "0":
-            # BASELINE.json configs[4] / the north-star target: 1024^3 slab-decomposed product + one MGVI sample draw
-            try:
-                del lin, lh, sig
-                torch.cuda.empty_cache()
-                extras["slab_1024"] = slab_measure(nb, torch, dist, (1024, 1024, 1024), "cf3d_1024_f64_slab", rank, world, dev, 10, 3)
-            except Exception as e:  # pragma: no cover
-                extras["slab_1024"] = {"error": repr(e)[:300]}
-
     if rank == 0:
         cpu, parity = None, None
         if args.cpu_baseline and world == 1:
@@ -456,6 +440,42 @@ def run_b200(args, shape, wname, rank, world, local_rank):
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity_rel_err": parity,
                 "linearize_ms": lin_ms, "collective": collective,
                 "sample_draw": {"seconds": draw_s, "cg_iterations": int(cgres.nit), "info": int(cgres.info), "nfev": int(cgres.nfev)}}
+    else:
+        line = None
+
+    # extra measurements of the multi-GPU runs (keys of the same JSON line).  They involve further collectives; a watchdog
+    # guarantees the line: if they do not finish in time every rank leaves, rank 0 after printing the line with what it has.
+    extras = {}
+    if world > 1 and os.environ.get("NB200_BENCH_EXTRAS", "1") != "0":
+        limit = float(os.environ.get("NB200_BENCH_EXTRAS_TIMEOUT", "300"))
+
+        def give_up():
+            if rank == 0:
+                extras.setdefault("extras_error", f"extra measurements did not finish within {limit:.0f} s")
+                line.update(extras)
+                print(json.dumps(line), flush=True)
+            else:
+                time.sleep(3.0)
+            os._exit(0)
+
+        dog = threading.Timer(limit, give_up)
+        dog.daemon = True
+        dog.start()
+        del t_host, out_host, t_dev, out_dev
+        try:
+            extras["kl_config3"] = kl_config3(nb, torch, dist, metric_multi, rank, world, dev, peak)
+        except Exception as e:  # pragma: no cover
+            extras["kl_config3"] = {"error": repr(e)[:300]}
+        if world == 8 and os.environ.get("NB200_BENCH_SLAB", "1") != "0":
+            # BASELINE.json configs[4] / the north-star target: 1024^3 slab-decomposed product + one MGVI sample draw
+            try:
+                del lin, lh, sig
+                torch.cuda.empty_cache()
+                extras["slab_1024"] = slab_measure(nb, torch, dist, (1024, 1024, 1024), "cf3d_1024_f64_slab", rank, world, dev, 10, 3)
+            except Exception as e:  # pragma: no cover
+                extras["slab_1024"] = {"error": repr(e)[:300]}
+        dog.cancel()
+    if rank == 0:
         line.update(extras)
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -536,15 +556,26 @@ def slab_measure(nb, torch, dist, shape, wname, rank, world, dev, steps, warmup,
     data = torch.randn(plan.local_pos_shape, dtype=dtype, device=dev, generator=gen)
     lh = nb.Gaussian(data, noise_cov_inv=NOISE_STD**-2).amend(sig)
     L = sig.layout.size
-    hyper = torch.Generator(dev).manual_seed(7)          # hyper-parameter leaves are replicated: same seed on every rank
-    pos = 0.1 * torch.randn(L, dtype=dtype, device=dev, generator=hyper)
-    t = torch.randn(L, dtype=dtype, device=dev, generator=hyper)
     o, n_xi = sig.layout.offsets["cfxi"], sig.layout.numel("cfxi")
     rows_ok = torch.as_tensor(plan.row_map >= 0, device=dev)
-    for v in (pos, t):
+    hyper = np.random.default_rng(7)
+
+    def latent(scale_hyper, scale_xi):
+        """A local latent vector: the replicated hyper-parameter leaves from ONE host generator, leaf by leaf (bit-identical on
+        every rank whatever its local size: the reductions of a slab CG rely on it), the local excitation rows from the
+        rank's own device generator."""
+        v = torch.zeros(L, dtype=dtype, device=dev)
+        for k in sig.layout.keys:
+            if k == "cfxi":
+                continue
+            ko, kn = sig.layout.offsets[k], sig.layout.numel(k)
+            v[ko:ko + kn] = torch.as_tensor(scale_hyper * hyper.standard_normal(kn), dtype=dtype, device=dev)
         blk = v[o:o + n_xi].view(plan.local_shape)
-        blk.copy_(0.1 * torch.randn(plan.local_shape, dtype=dtype, device=dev, generator=gen))
+        blk.copy_(scale_xi * torch.randn(plan.local_shape, dtype=dtype, device=dev, generator=gen))
         blk[~rows_ok] = 0
+        return v
+
+    pos, t = latent(0.1, 0.1), latent(1.0, 0.1)
     lin, _ = lh.lin_at(pos)
     out = torch.empty_like(t)
 
@@ -589,10 +620,7 @@ def slab_measure(nb, torch, dist, shape, wname, rank, world, dev, steps, warmup,
         # MGVI sample draw on the slab-decomposed field: CG on (metric + 1) with all-reduced reductions, demo settings
         from nifty_b200.conjugate_gradient import HamiltonianMetric, _cg
         Lg = lh.global_size()
-        j = torch.randn(L, dtype=dtype, device=dev, generator=hyper)
-        blk = j[o:o + n_xi].view(plan.local_shape)
-        blk.copy_(torch.randn(plan.local_shape, dtype=dtype, device=dev, generator=gen))
-        blk[~rows_ok] = 0
+        j = latent(1.0, 1.0)
         op = HamiltonianMetric(lin, likelihood=lh)
         barrier()
         ts = time.perf_counter()
