@@ -20,3 +20,5 @@ from .minisanity import ChiSqStats, minisanity, reduced_residual_stats  # noqa: 
 from .tree_math import (get_map, lmap, mean, mean_and_std, norm, size, smap, stack, unstack, vdot, where,  # noqa: F401
                         zeros_like)
 from .evidence_lower_bound import estimate_evidence_lower_bound  # noqa: F401
+from . import lanczos  # noqa: F401
+from .lanczos import lanczos_tridiag, stochastic_logdet_from_lanczos, stochastic_lq_logdet  # noqa: F401

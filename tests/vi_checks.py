@@ -297,9 +297,21 @@ def check_elbo(rt, name="g2d_16x16"):
     k = 6          # one eigenvalue per batch: the sixth is the first one within min_lh_eval of 1
     want3 = -0.5 * np.sum(np.log(eig[:k])) + 0.5 * L - ham
     np.testing.assert_allclose(el3, want3, rtol=1e-8)
+    # stochastic Lanczos quadrature of the same trace-log (lanczos.py): full Krylov order makes every probe exact up to the
+    # probe variance; signal- and data-space operators estimate the same log-determinant
+    exact = -0.5 * np.sum(np.log(eig)) + 0.5 * L - ham
+    for space in ("signal", "data"):
+        el4, st4 = nb.estimate_evidence_lower_bound(lh, smp, 0, trace_log_method="slq", trace_log_space=space, slq_order=64,
+                                                    slq_num_samples=24, slq_key=3, verbose=False)
+        assert st4["lower_error"] == 0.0 and st4["slq_stochastic_se"] > 0
+        assert abs(st4["elbo_mean"] - exact.mean()) < 5.0 * st4["slq_stochastic_se"] + 1e-3 * abs(exact.mean())
+    tri, vecs = nb.lanczos_tridiag(lambda v: lh.lin_at(smp.pos)[0].metric(v, add_identity=True), rt.asarray(np.ones(L), torch.float64), order=8)
+    q = t2n(vecs)
+    np.testing.assert_allclose(q @ q.T, np.eye(8), atol=1e-10)                     # orthonormal Krylov basis of the device product
+    np.testing.assert_allclose(q @ (0.5 * (H + H.T)) @ q.T, t2n(tri), atol=1e-8 * np.abs(H).max())
     # refused / invalid options
     with pytest.raises(NotImplementedError):
-        nb.estimate_evidence_lower_bound(lh, smp, 4, trace_log_method="slq", verbose=False)
+        nb.estimate_evidence_lower_bound(lh, smp, 4, analytic_prior_term=True, verbose=False)
     with pytest.raises(ValueError, match="at least one eigenvalue"):
         nb.estimate_evidence_lower_bound(lh, smp, 0, verbose=False)
     with pytest.raises(ValueError, match="exceeds"):
