@@ -144,7 +144,7 @@ void nb200_model_destroy(nb200_model* model);
 
 /* Gaussian(data, noise_cov_inv).amend(signal) / Poissonian(data).amend(signal)
  * (likelihood_impl.py:83-138, 203-251; likelihood.py:546-633).  kind: 0 Gaussian, 1 Poissonian.
- * nonlinearity: 0 identity, 1 exp.  `data` natural order, plan dtype (Poisson counts converted by
+ * nonlinearity: 0 identity, 1 exp, 2 tabulated (nb200_lin_set_pointwise).  `data` natural order, plan dtype (Poisson counts converted by
  * the host).  Diagonal noise: scalar, or array if noise_cov_inv_array != NULL. */
 int nb200_model_set_likelihood(nb200_model* model, void* stream, int kind, int nonlinearity, const void* data,
                                double noise_cov_inv_scalar, const void* noise_cov_inv_array);
@@ -159,6 +159,11 @@ void nb200_lin_destroy(nb200_lin* lin);
  * If grad != NULL also writes d(likelihood energy)/d pos (+ pos if add_prior), i.e. the gradient of
  * _StandardHamiltonian (optimize_kl.py:67-87).  The energy is left on the device (nb200_lin_energy). */
 int nb200_lin_update(nb200_lin* lin, void* stream, const void* pos, void* grad, int add_prior);
+/* Models with nonlinearity = 2 ("tabulated": any pointwise map signal = f(correlated field), the `Model(lambda x: f(cf(x)))`
+ * of nifty/re/model.py:146-181): before every nb200_lin_update the host evaluates f and f' at the field of that position
+ * (nb200_model_cf_forward gives the field) and hands both over, natural order, plan dtype.  Everything after the
+ * linearisation (metric, sqrt-metrics, CG, ...) is unchanged: it only sees the cached signal and Jacobian weights. */
+int nb200_lin_set_pointwise(nb200_lin* lin, void* stream, const void* signal, const void* dsignal);
 /* likelihood energy of the last nb200_lin_update (synchronises the stream) */
 int nb200_lin_energy(nb200_lin* lin, void* stream, double* energy_host);
 

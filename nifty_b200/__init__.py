@@ -17,8 +17,9 @@ from .evi import (Samples, concatenate_zip, draw_linear_residual, draw_residual,
                   random_like, random_split, sample_likelihood, wiener_filter_posterior)
 from .optimize_kl import OptimizeVI, OptimizeVIState, get_status_message, optimize_kl  # noqa: F401
 from .minisanity import ChiSqStats, minisanity, reduced_residual_stats  # noqa: F401
-from .tree_math import (get_map, lmap, mean, mean_and_std, norm, size, smap, stack, unstack, vdot, where,  # noqa: F401
+from .tree_math import (Vector, get_map, lmap, mean, mean_and_std, norm, size, smap, stack, unstack, vdot, where,  # noqa: F401
                         zeros_like)
+from .model import Initializer, LazyModel, Model, WrappedCall  # noqa: F401
 from .evidence_lower_bound import estimate_evidence_lower_bound  # noqa: F401
 from . import lanczos  # noqa: F401
 from .lanczos import lanczos_tridiag, stochastic_logdet_from_lanczos, stochastic_lq_logdet  # noqa: F401

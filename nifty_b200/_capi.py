@@ -85,6 +85,7 @@ SIGNATURES = {
     "nb200_lin_create": (C.c_int, [C.POINTER(vp), vp]),
     "nb200_lin_destroy": (None, [vp]),
     "nb200_lin_update": (C.c_int, [vp, vp, vp, vp, C.c_int]),
+    "nb200_lin_set_pointwise": (C.c_int, [vp, vp, vp, vp]),
     "nb200_lin_energy": (C.c_int, [vp, vp, C.POINTER(f64)]),
     "nb200_lin_amplitude": (C.c_int, [vp, vp, vp]),
     "nb200_lin_signal": (C.c_int, [vp, vp, vp]),

@@ -518,6 +518,19 @@ class Lin:
             # gradient = J^T dE/ds (+ pos): the adjoint tail with `pos` as the additive term
             return self._dist_adjoint_tail(pos, grad, bool(add_prior), True, grad=True)
         grad = self._vec() if want_grad else None
+        nl_fn = getattr(self.model, "nl_fn", None)
+        if nl_fn is not None:
+            # user-supplied pointwise map of the field: evaluated here, at this position, together with its derivative
+            # (torch autograd on the host side of the boundary -- once per linearisation, not per product)
+            field = self.model.cf_forward(pos)
+            with torch.enable_grad():
+                f = field.detach().requires_grad_(True)
+                s = nl_fn(f)
+                if s.shape != f.shape:
+                    raise ValueError("the non-linearity must be a pointwise map of the correlated field (same shape in and out)")
+                (ds,) = torch.autograd.grad(s.sum(), f)
+            s, ds = s.detach().contiguous(), ds.contiguous()
+            self.rt.api.call("nb200_lin_set_pointwise", self._h, self.rt.stream(), self.rt.ptr(s), self.rt.ptr(ds))
         self.rt.api.call("nb200_lin_update", self._h, self.rt.stream(), self.rt.ptr(pos), self.rt.ptr(grad), int(add_prior))
         return grad
 

@@ -17,6 +17,8 @@ Two execution paths, same semantics (``info``: 0 converged, i > 0 stopped at ite
 
 from __future__ import annotations
 
+import os
+
 from typing import Callable, NamedTuple, Optional
 
 import numpy as np
@@ -101,9 +103,13 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
     vdot = (lambda a, b: float(torch.dot(a, b))) if vdot is None else vdot
     vnorm = _norm if vnorm is None else vnorm
     if isinstance(mat, HamiltonianMetric) and mat.distributed:
-        # slab-decomposed field: the recurrences run in the host loop below, reductions are all-reduced
+        # slab-decomposed field: the recurrence of the loop below with in-place vector updates and ONE all-reduce + host
+        # synchronisation per group of reductions
         if mat.likelihood is None:
             raise ValueError("a slab-decomposed HamiltonianMetric needs its likelihood (for the distributed reductions)")
+        if norm_ord in (1, 2) and os.environ.get("NB200_SLAB_CG", "1") != "0":
+            return _cg_slab(mat, j, x0, absdelta=absdelta, resnorm=resnorm, norm_ord=norm_ord, tol=tol, atol=atol, miniter=miniter,
+                            maxiter=maxiter, name=name, _raise_nonposdef=_raise_nonposdef)
         vdot, vnorm = mat.likelihood.vdot, mat.likelihood.vnorm
     elif isinstance(mat, SampleAveragedMetric):
         from ._runtime import cg_solve_multi
@@ -199,6 +205,119 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
             break
         energy = new_energy
         d = d * max(0.0, gamma / previous_gamma) + r
+        previous_gamma = gamma
+    info = i if info == -1 else info
+    return CGResults(pos, i, nfev, info, info == 0)
+
+
+class _SlabReductions:
+    """Dot products / 1-norms of slab-decomposed latent vectors in groups: the excitation rows are reduced locally, ALL
+    partial results of a group travel in one all-reduce, the replicated hyper-parameter entries are reduced from the
+    replicated data (identical on every rank, so every rank takes the same control-flow decisions) -- one collective and
+    one host synchronisation per group instead of one per scalar (likelihood.vdot / vnorm)."""
+
+    def __init__(self, likelihood):
+        self.lo, self.hi = likelihood._xi_slice()
+        self.comm = likelihood._plan.comm
+
+    def _rep(self, v):
+        return v[:self.lo], v[self.hi:]
+
+    def __call__(self, dots=(), norms1=()):
+        lo, hi = self.lo, self.hi
+        loc = [torch.dot(a[lo:hi], b[lo:hi]) for a, b in dots] + [torch.linalg.vector_norm(v[lo:hi], ord=1) for v in norms1]
+        t = torch.stack(loc).to(torch.float64)
+        self.comm.allreduce_sum(t)
+        rep = []
+        for a, b in dots:
+            (a0, a1), (b0, b1) = self._rep(a), self._rep(b)
+            rep.append(torch.dot(a0, b0) + torch.dot(a1, b1))
+        for v in norms1:
+            v0, v1 = self._rep(v)
+            rep.append(torch.linalg.vector_norm(v0, ord=1) + torch.linalg.vector_norm(v1, ord=1))
+        return (t + torch.stack(rep).to(torch.float64)).tolist()          # (the one host synchronisation of the group)
+
+
+def _cg_slab(mat, j, x0, *, absdelta, resnorm, norm_ord, tol, atol, miniter, maxiter, name, _raise_nonposdef) -> CGResults:
+    """The recurrence of ``_cg`` (conjugate_gradient.py:107-214, same stopping rules and ``info`` codes) for slab-decomposed
+    fields: vector updates in place (``add_`` with a scalar multiplier, no temporaries), reductions in groups
+    (:class:`_SlabReductions`).  Per iteration: one product, one curvature all-reduce, one all-reduce of
+    {<r, r>, <r - j, pos>, |r|_1}."""
+    red = _SlabReductions(mat.likelihood)
+    n_glob = mat.likelihood.global_size()
+    maxiter_fallback = 20 * n_glob
+    if miniter is None:
+        miniter = min(6, maxiter if maxiter is not None else maxiter_fallback)
+    if maxiter is None:
+        maxiter = max(min(200, maxiter_fallback), miniter)
+    if absdelta is None and resnorm is None:
+        resnorm = max(tol * mat.likelihood.vnorm(j, norm_ord), atol)
+    fi = torch.finfo(j.dtype)
+    eps, tiny = 6.0 * fi.eps, 6.0 * fi.tiny
+    nm = "CG" if name is None else name
+    tmp = torch.empty_like(j)
+    if x0 is None:
+        pos = torch.zeros_like(j)
+        r = -j
+        d = r.clone()
+        energy, nfev = 0.0, 0
+        (previous_gamma,) = red(dots=[(r, r)])
+    else:
+        pos = x0.clone()
+        r = mat(pos).sub_(j)
+        d = r.clone()
+        torch.sub(r, j, out=tmp)
+        previous_gamma, e2 = red(dots=[(r, r), (tmp, pos)])
+        energy, nfev = 0.5 * e2, 1
+    if previous_gamma == 0:
+        return CGResults(pos, 0, nfev, 0, True)
+    info, i = -1, 0
+    for i in range(1, maxiter + 1):
+        q = mat(d)
+        nfev += 1
+        (curv,) = red(dots=[(d, q)])
+        if curv == 0.0:
+            if _raise_nonposdef:
+                raise ValueError(f"{nm}: zero curvature")
+            info = 0
+            break
+        if curv < 0.0:
+            if _raise_nonposdef:
+                raise ValueError(f"{nm}: negative curvature")
+            if i == 1:
+                pos = previous_gamma / (-curv) * (-j)
+            info = 0
+            break
+        alpha = previous_gamma / curv
+        pos.add_(d, alpha=-alpha)
+        if i % N_RESET == 0:
+            r = mat(pos).sub_(j)
+            nfev += 1
+        else:
+            r.add_(q, alpha=-alpha)
+        torch.sub(r, j, out=tmp)
+        want_norm = resnorm is not None and norm_ord == 1
+        vals = red(dots=[(r, r), (tmp, pos)], norms1=[r] if want_norm else ())
+        gamma, new_energy = vals[0], 0.5 * vals[1]
+        if 0.0 <= gamma <= tiny:
+            info = 0
+            break
+        if resnorm is not None and i >= miniter:
+            rn = vals[2] if want_norm else float(np.sqrt(gamma))
+            if rn < resnorm:
+                info = 0
+                break
+        energy_diff = energy - new_energy
+        if energy_diff < -eps * abs(new_energy):
+            if _raise_nonposdef:
+                raise ValueError(f"{nm}: WARNING: energy increased")
+            info = i
+            break
+        if absdelta is not None and energy_diff < absdelta and i >= miniter:
+            info = 0
+            break
+        energy = new_energy
+        torch.add(r, d, alpha=max(0.0, gamma / previous_gamma), out=d)
         previous_gamma = gamma
     info = i if info == -1 else info
     return CGResults(pos, i, nfev, info, info == 0)

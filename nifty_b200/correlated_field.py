@@ -29,7 +29,9 @@ RegularFourierGrid = namedtuple("RegularFourierGrid", ("shape", "power_distribut
                                                        "relative_log_mode_lengths", "log_volume"))
 
 
-class CorrelatedField:
+from .model import LazyModel  # noqa: E402
+
+class CorrelatedField(LazyModel):
     """The finalised model: ``cf(pos)`` evaluates the field; mirrors ``jft.Model`` attributes."""
 
     def __init__(self, plan: Plan, domain: dict, prefix: str, sub_prefix: str, desc_fields: dict, offset_mean: float,
@@ -80,6 +82,7 @@ class CorrelatedField:
         return self._handle
 
     def as_flat(self, pos) -> torch.Tensor:
+        pos = getattr(pos, "tree", pos)          # jft.Vector
         if isinstance(pos, torch.Tensor):
             return self.rt.asarray(pos.reshape(-1), self.dtype)
         return self.layout.pack(pos, self.dtype, self.rt.device)

@@ -446,10 +446,10 @@ int nb200_model_set_likelihood(nb200_model* model, void* stream, int kind, int n
                                double noise_cov_inv_scalar, const void* noise_cov_inv_array) {
   NB_TRY
   if (kind != 0 && kind != 1) return fail("nb200_model_set_likelihood: kind must be 0 (Gaussian) or 1 (Poissonian)");
-  if (nonlinearity != 0 && nonlinearity != 1) return fail("nb200_model_set_likelihood: nonlinearity must be 0 or 1");
+  if (nonlinearity < 0 || nonlinearity > 2) return fail("nb200_model_set_likelihood: nonlinearity must be 0 (identity), 1 (exp) or 2 (tabulated)");
   NB_DISPATCH(model->dtype, TT, {
     Model<TT>& m = *static_cast<Model<TT>*>(model->impl);
-    if (nonlinearity == 0 && m.am.has_scaling) return fail("nb200: scaling requires the exp non-linearity");
+    if (nonlinearity != 1 && m.am.has_scaling) return fail("nb200: scaling requires the exp non-linearity");
     stream_t st = (stream_t)stream;
     m.lh_kind = kind; m.nl_exp = nonlinearity; m.w_scalar = (TT)noise_cov_inv_scalar;
     const size_t npos = (size_t)m.P->local_position_grid();
@@ -483,6 +483,13 @@ void nb200_lin_destroy(nb200_lin* lin) { if (lin) { delete lin->impl; delete lin
 int nb200_lin_update(nb200_lin* lin, void* stream, const void* pos, void* grad, int add_prior) {
   NB_TRY
   NB_DISPATCH(lin->dtype, TT, { static_cast<Lin<TT>*>(lin->impl)->update((stream_t)stream, (const TT*)pos, (TT*)grad, add_prior != 0); })
+  return 0;
+  NB_CATCH
+}
+int nb200_lin_set_pointwise(nb200_lin* lin, void* stream, const void* signal, const void* dsignal) {
+  NB_TRY
+  if (!lin || !signal || !dsignal) return fail("nb200_lin_set_pointwise: null argument");
+  NB_DISPATCH(lin->dtype, TT, { static_cast<Lin<TT>*>(lin->impl)->set_pointwise((stream_t)stream, (const TT*)signal, (const TT*)dsignal); })
   return 0;
   NB_CATCH
 }

@@ -87,6 +87,8 @@ template <class T> struct Model : ModelBase {
 template <class T> struct Lin : LinBase {
   Model<T>* M = nullptr;
   DevBuf<T> pos, amp, wS, Pb, s, jl, scal, ellv_buf, cv_buf;
+  DevBuf<T> nl_s, nl_ds;       // tabulated pointwise map of the field at the position of the NEXT update (nb200_lin_set_pointwise)
+  bool nl_ready = false;
   const T* ellv = nullptr; const T* cv = nullptr;   // effective du/dslope and du/dcutoff tables (Matern: per linearisation)
   bool valid = false;
 
@@ -229,6 +231,10 @@ template <class T> struct Lin : LinBase {
     PointOp<T> op = P.make_op(PM_LINEARIZE);
     op.invV = T(1.0 / P.g.V); op.offset = m.offset_mean; op.sc_ptr = scal.p + SC_SCALING;
     op.lh_kind = m.lh_kind; op.nl_exp = m.nl_exp; op.data = m.data.p; op.w_scalar = m.w_scalar;
+    if (m.nl_exp == 2) {
+      if (!nl_ready) throw Error{"nb200: this model has a tabulated non-linearity: call nb200_lin_set_pointwise before nb200_lin_update"};
+      op.nl_s = nl_s.p; op.nl_ds = nl_ds.p; nl_ready = false;       // (valid for this position only)
+    }
     op.w_arr = m.has_w_arr ? m.w_arr.p : nullptr; op.s_out = s.p; op.jl_out = jl.p; op.partials = P.p3part.p;
     if (grad) P.template run_p3<true, true>(st, op); else P.template run_p3<true, false>(st, op);
     ReduceColsParams<T> pr; pr.partials = P.p3part.p; pr.n = P.n3part; pr.ncol = 2;
@@ -333,6 +339,7 @@ template <class T> struct Lin : LinBase {
     switch (code) {
       case 0: case 10: {     // update.1: amplitude chain + P1 (+ PCa for code 0)
         if (!m.have_lh) throw Error{"nb200: likelihood not set on this model"};
+        if (m.nl_exp == 2) throw Error{"nb200: tabulated non-linearities are not available on slab-decomposed plans"};
         d2d(pos.p, in, (size_t)m.am.L * sizeof(T), st);
         amp_forward(st);
         ProAmp<T> pro; pro.xi = pos.p + m.am.off_xi; pro.idxf = P.idxf.p; pro.amp = amp.p; pro.fg = P.fold_geom();
@@ -395,6 +402,18 @@ template <class T> struct Lin : LinBase {
       } break;
       default: throw Error{"nb200_dist_phase: unknown phase code"};
     }
+  }
+
+  // signal and its derivative with respect to the field, evaluated by the host at the position of the next update
+  // (natural layout) -> T-layout tables
+  void set_pointwise(stream_t st, const T* s_nat, const T* ds_nat) {
+    Model<T>& m = *M; Plan<T>& P = *m.P;
+    if (P.dist) throw Error{"nb200: tabulated non-linearities are not available on slab-decomposed plans"};
+    if (m.nl_exp != 2) throw Error{"nb200_lin_set_pointwise: the model's non-linearity is not `tabulated` (nonlinearity = 2)"};
+    if (!nl_s.n) { nl_s.alloc((size_t)P.local_position_grid()); nl_ds.alloc((size_t)P.local_position_grid()); }
+    P.run_rev(st, s_nat, nl_s.p, true);
+    P.run_rev(st, ds_nat, nl_ds.p, true);
+    nl_ready = true;
   }
 
   void posmap(stream_t st, int mode, T* out_nat) {

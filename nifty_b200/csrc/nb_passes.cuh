@@ -504,7 +504,8 @@ enum LhKind { LH_GAUSS = 0, LH_POISSON = 1 };
 template <class T> struct PointOp {
   int mode;
   int natural;          // PM_FIELD_OUT / PM_JVP_OUT / PM_LOAD address natural-layout arrays
-  int lh_kind, nl_exp;
+  int lh_kind, nl_exp;  // nl_exp: 0 identity, 1 exp, 2 tabulated (nl_s / nl_ds: signal and d signal / d field per position, T-layout)
+  const T* nl_s; const T* nl_ds;
   T invV, offset, cshift_scale;   // cshift = cshift_scale * (*cshift_ptr) if cshift_ptr
   const T* cshift_ptr;
   T sc;                 // multiplicative scaling of the signal (1 if absent); read from sc_ptr if set
@@ -538,8 +539,9 @@ template <class T> struct PointOp {
       return r;
     } else if (MODE == PM_LINEARIZE) {
       T f = offset + v * invV;
-      T s = nl_exp ? scv * nb_exp(f) : f;
-      T jd = nl_exp ? s : T(1);
+      T s, jd;
+      if (nl_exp == 2) { s = nl_s[i]; jd = nl_ds[i]; }       // (evaluated by the host at this field: any pointwise map)
+      else { s = nl_exp ? scv * nb_exp(f) : f; jd = nl_exp ? s : T(1); }
       T e, cot, l;
       if (lh_kind == LH_GAUSS) {
         T w = w_arr ? w_arr[i] : w_scalar;

@@ -462,7 +462,7 @@ template <class T> struct Plan : PlanBase {
   PointOp<T> make_op(int mode) const {
     PointOp<T> op;
     std::memset(&op, 0, sizeof(op));
-    op.mode = mode; op.invV = T(1); op.sc = T(1); op.nl_exp = 1;
+    op.mode = mode; op.invV = T(1); op.sc = T(1); op.nl_exp = 1; op.nl_s = nullptr; op.nl_ds = nullptr;
     op.n_a_full = g.nl; op.n_mid = g.nm; op.n = g.n0;
     return op;
   }

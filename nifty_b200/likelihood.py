@@ -25,11 +25,21 @@ from .prior import LogNormalPrior, _as_prior
 from .tree import Layout
 
 
-class SignalModel:
+from .model import LazyModel  # noqa: E402
+
+class SignalModel(LazyModel):
     """``signal(p) = scaling(p) * nl(cf(p))`` with an optional log-normal ``scaling`` leaf of shape (1,)."""
 
-    def __init__(self, cf: CorrelatedField, nonlinearity: str = "exp", scaling=None, scaling_key: str = "scaling"):
-        if nonlinearity not in ("exp", "identity"):
+    def __init__(self, cf: CorrelatedField, nonlinearity="exp", scaling=None, scaling_key: str = "scaling"):
+        # `nonlinearity`: "exp", "identity", or any torch-callable POINTWISE map of the field (`Model(lambda x: f(cf(x)))` of
+        # the reference, nifty/re/model.py:146-181): f and f' are evaluated on the host side at every linearisation
+        # (torch autograd) and handed to the library as tables (nb200_lin_set_pointwise); the products never see f.
+        self.nl_fn = None
+        if callable(nonlinearity):
+            self.nl_fn, nonlinearity = nonlinearity, "tabulated"
+            if cf.plan.dist:
+                raise NotImplementedError("custom non-linearities are not available on slab-decomposed fields")
+        elif nonlinearity not in ("exp", "identity"):
             raise ValueError(f"unsupported nonlinearity {nonlinearity!r}")
         self.cf, self.nonlinearity = cf, nonlinearity
         self.scaling = _as_prior(scaling, LogNormalPrior, "scaling", optional=True)
@@ -51,6 +61,7 @@ class SignalModel:
         return self.layout.unpack(self.layout.random(seed, self.dtype, self.rt.device))
 
     def as_flat(self, pos) -> torch.Tensor:
+        pos = getattr(pos, "tree", pos)          # jft.Vector
         if isinstance(pos, torch.Tensor):
             if pos.numel() != self.layout.size:
                 raise ValueError(f"latent vector has {pos.numel()} entries, expected {self.layout.size}")
@@ -58,7 +69,12 @@ class SignalModel:
         return self.layout.pack(pos, self.dtype, self.rt.device)
 
     def like(self, template, vec):
-        return vec if isinstance(template, torch.Tensor) else self.layout.unpack(vec)
+        if isinstance(template, torch.Tensor):
+            return vec
+        if hasattr(template, "tree") and not isinstance(template, dict):      # jft.Vector in -> Vector out
+            from .tree_math import Vector
+            return Vector(self.layout.unpack(vec))
+        return self.layout.unpack(vec)
 
     def _new_handle(self) -> ModelHandle:
         return ModelHandle(self.cf.plan, self.cf._descriptor(self.layout, self.scaling, self.scaling_key))
@@ -72,7 +88,10 @@ class Likelihood:
         if isinstance(signal, CorrelatedField):
             signal = SignalModel(signal, "identity")
         if not isinstance(signal, SignalModel):
-            raise TypeError("the B200 path amends likelihoods with a `SignalModel` (or a `CorrelatedField`)")
+            raise NotImplementedError(
+                "the B200 path implements likelihoods on a correlated field followed by a pointwise map: amend with a "
+                "`CorrelatedField`, a `SignalModel(cf, 'exp' | 'identity' | <torch callable>, scaling=...)` or "
+                "`Model.pointwise(cf, fn)`; an arbitrary `Model(call, ...)` cannot be differentiated here (no tracing compiler)")
         return LikelihoodWithModel(self, signal)
 
 
@@ -139,7 +158,8 @@ class LikelihoodWithModel:
         if tuple(np.shape(likelihood.data)) != tuple(signal.target_shape):
             raise ValueError(f"data shape {np.shape(likelihood.data)} does not match the model target {signal.target_shape}")
         self.handle = signal._new_handle()
-        self.handle.set_likelihood(likelihood.kind, int(signal.nonlinearity == "exp"), likelihood.data,
+        self.handle.nl_fn = signal.nl_fn
+        self.handle.set_likelihood(likelihood.kind, {"identity": 0, "exp": 1, "tabulated": 2}[signal.nonlinearity], likelihood.data,
                                    likelihood.w_scalar, likelihood.w_array)
         self._lins = []     # small cache of linearisations: [(key, Lin)]
         self._max_lins = 3

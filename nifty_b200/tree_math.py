@@ -15,7 +15,49 @@ import numpy as np
 import torch
 
 
+class Vector:
+    """``jft.Vector`` (tree_math/vector.py:79-188): a latent tree with leaf-wise arithmetic.  ``Vector(tree)``, ``.tree``,
+    ``+ - * /`` with vectors / scalars, unary ``-``, ``abs``, ``@`` (= :func:`vdot`), ``len`` (number of leaves), ``size``."""
+    __slots__ = ("tree",)
+
+    def __init__(self, tree):
+        self.tree = tree.tree if isinstance(tree, Vector) else tree
+
+    @staticmethod
+    def _t(x):
+        return x.tree if isinstance(x, Vector) else x
+
+    def _bin(self, other, f):
+        o = self._t(other)
+        if isinstance(o, (dict, tuple, list)):
+            return Vector(_map(f, self.tree, o))
+        return Vector(_map(lambda a: f(a, o), self.tree))
+
+    def __add__(self, o): return self._bin(o, lambda a, b: a + b)
+    def __radd__(self, o): return self._bin(o, lambda a, b: b + a)
+    def __sub__(self, o): return self._bin(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._bin(o, lambda a, b: b - a)
+    def __mul__(self, o): return self._bin(o, lambda a, b: a * b)
+    def __rmul__(self, o): return self._bin(o, lambda a, b: b * a)
+    def __truediv__(self, o): return self._bin(o, lambda a, b: a / b)
+    def __rtruediv__(self, o): return self._bin(o, lambda a, b: b / a)
+    def __pow__(self, o): return self._bin(o, lambda a, b: a ** b)
+    def __neg__(self): return Vector(_map(lambda a: -a, self.tree))
+    def __abs__(self): return Vector(_map(lambda a: abs(a), self.tree))
+    def __matmul__(self, o): return vdot(self.tree, self._t(o))
+    def __len__(self): return len(_leaves(self.tree))
+    def __getitem__(self, k): return self.tree[k]
+    def __iter__(self): return iter(self.tree)
+
+    @property
+    def size(self): return size(self.tree)
+
+    def __repr__(self): return f"Vector({self.tree!r})"
+
+
 def _leaves(tree):
+    if isinstance(tree, Vector):
+        return _leaves(tree.tree)
     if isinstance(tree, dict):
         return [tree[k] for k in sorted(tree)]
     if isinstance(tree, (tuple, list)):
@@ -24,6 +66,7 @@ def _leaves(tree):
 
 
 def _map(f, *trees):
+    trees = tuple(t.tree if isinstance(t, Vector) else t for t in trees)
     t0 = trees[0]
     if isinstance(t0, dict):
         return {k: _map(f, *(t[k] if isinstance(t, dict) else t for t in trees)) for k in t0}

@@ -24,7 +24,14 @@ class SignalOracle:
 
     def __init__(self, cf: CorrelatedFieldOracle, nonlinearity="exp", scaling=None,
                  scaling_key="scaling"):
-        if nonlinearity not in ("exp", "identity"):
+        # a pair (fn, dfn) of NumPy callables: an arbitrary POINTWISE map of the field and its derivative (what jax.jvp / vjp
+        # give for `Model(lambda x: fn(cf(x)))`, nifty/re/model.py:146-181)
+        self.nl_pair = None
+        if isinstance(nonlinearity, tuple):
+            self.nl_pair, nonlinearity = nonlinearity, "custom"
+            if scaling is not None:
+                raise ValueError("scaling + custom nonlinearity")
+        elif nonlinearity not in ("exp", "identity"):
             raise ValueError(nonlinearity)
         self.cf = cf
         self.nl = nonlinearity
@@ -43,12 +50,16 @@ class SignalOracle:
 
     def __call__(self, p):
         f = self.cf(p)
+        if self.nl_pair is not None:
+            return self.nl_pair[0](f)
         y = np.exp(f) if self.nl == "exp" else f
         return self._scal(p) * y
 
     def jvp(self, p, dp):
         f = self.cf(p)
         df = self.cf.jvp(p, dp)
+        if self.nl_pair is not None:
+            return self.nl_pair[1](f) * df
         sc = self._scal(p)
         if self.nl == "exp":
             y = np.exp(f)
@@ -65,6 +76,8 @@ class SignalOracle:
         f = self.cf(p)
         sc = self._scal(p)
         c = np.asarray(c, dtype=np.float64)
+        if self.nl_pair is not None:
+            return self.cf.vjp(p, self.nl_pair[1](f) * c)
         if self.nl == "exp":
             y = np.exp(f)
             fbar = sc * y * c

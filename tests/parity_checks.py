@@ -158,6 +158,13 @@ def check_model_surface(rt, name="g2d_16x16"):
     assert cf.domain == {k: tuple(np.shape(v)) for k, v in g["pos"].items()} and tuple(cf.target) == tuple(c["shape"])
     p0 = cf.init(3)
     assert sorted(p0) == sorted(cf.domain) and all(tuple(p0[k].shape) == cf.domain[k] for k in p0)
+    # the container types of the reference's model API (model.py:32-340, tree_math/vector.py:79-188)
+    assert isinstance(cf, nb.LazyModel) and isinstance(nb.SignalModel(cf, "exp"), nb.LazyModel)
+    lh = nb.Gaussian(g["data"], noise_cov_inv=float(g["noise_cov_inv"])).amend(nb.Model.pointwise(cf, "exp"))
+    tan = {k: torch.as_tensor(v) for k, v in g["tan"].items()}
+    mv = lh.metric(nb.Vector(pos), nb.Vector(tan))            # Vector in -> Vector out, same numbers as with plain trees
+    assert isinstance(mv, nb.Vector) and tree_err(mv.tree, g["metric"]) < 1e-10
+    assert rel_err(t2n(cf(nb.Vector(pos))), g["field"]) < 1e-10
 
 
 def check_kind_and_scaling(rt, name="g2d_16x16", kind="amplitude", scaling=(3.0, 1.0)):
@@ -283,6 +290,62 @@ def check_against_oracle(rt, shape, distances, lh_kind="gauss", seed=11, tol=1e-
     u = rng.standard_normal(shape)
     assert tree_err(lh.left_sqrt_metric(tp, u), olh.left_sqrt_metric(pos, u)) < tol
     assert rel_err(t2n(lh.right_sqrt_metric(tp, tt)), olh.right_sqrt_metric(pos, tan)) < tol
+
+
+NONLINEARITIES = {
+    # name: (torch map, NumPy map, NumPy derivative)
+    "softplus": (torch.nn.functional.softplus, lambda f: np.logaddexp(0.0, f), lambda f: 1.0 / (1.0 + np.exp(-f))),
+    "sigmoid_scaled": (lambda f: 3.0 * torch.sigmoid(f) + 0.1, lambda f: 3.0 / (1.0 + np.exp(-f)) + 0.1,
+                       lambda f: 3.0 * np.exp(-f) / (1.0 + np.exp(-f)) ** 2),
+    "square_plus": (lambda f: f * f + 0.5, lambda f: f * f + 0.5, lambda f: 2.0 * f),
+}
+
+
+def check_custom_nonlinearity(rt, shape, distances, lh_kind="gauss", which="softplus", seed=5, tol=1e-10):
+    """`SignalModel(cf, nonlinearity=<torch callable>)` -- an arbitrary pointwise map of the field, f and f' evaluated on the
+    host side at every linearisation and handed over as tables (nb200_lin_set_pointwise) -- against the oracle with the
+    same map and its analytic derivative: signal, energy, gradient, metric, both sqrt-metrics, a CG solve on the metric."""
+    tfn, nfn, ndfn = NONLINEARITIES[which]
+    c = dict(shape=shape, distances=distances, offset_mean=0.3, offset_std=(0.2, 0.1), fluctuations=(0.5, 0.1),
+             loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05), lh=lh_kind)
+    ocf = build_oracle(c)
+    osig = oracle.SignalOracle(ocf, (nfn, ndfn))
+    lay = oracle.Layout(osig.domain)
+    rng = np.random.default_rng(seed)
+    pos, tan = lay.random(rng), lay.random(rng)
+    pos = {k: 0.5 * v for k, v in pos.items()}
+    sig = nb.SignalModel(build_product(c, rt), tfn)
+    if lh_kind == "gauss":
+        data = osig(pos) + 0.3 * rng.standard_normal(shape)
+        olh = oracle.GaussianOracle(data, 1.0 / 0.09, osig)
+        lh = nb.Gaussian(data, noise_cov_inv=1.0 / 0.09).amend(sig)
+    else:
+        data = rng.poisson(osig(pos)).astype(np.int64)
+        olh = oracle.PoissonianOracle(data, osig)
+        lh = nb.Poissonian(data).amend(sig)
+    tp = {k: torch.as_tensor(v) for k, v in pos.items()}
+    tt = {k: torch.as_tensor(v) for k, v in tan.items()}
+    assert rel_err(t2n(lh.signal_response(tp)), osig(pos)) < tol
+    e, grad = lh.energy_and_gradient(tp)
+    oe, ograd = olh.energy_and_gradient(pos)
+    assert abs(e - oe) <= tol * abs(oe)
+    assert tree_err(grad, ograd) < tol
+    assert tree_err(lh.metric(tp, tt), olh.metric(pos, tan)) < tol
+    u = rng.standard_normal(shape)
+    assert tree_err(lh.left_sqrt_metric(tp, u), olh.left_sqrt_metric(pos, u)) < tol
+    assert rel_err(t2n(lh.right_sqrt_metric(tp, tt)), olh.right_sqrt_metric(pos, tan)) < tol
+    lin, _ = lh.lin_at(tp)
+    j = lh.signal.layout.random(3, torch.float64, rt.device)
+    # (fixed iteration count, away from any stopping threshold: two CG implementations drift apart with the iteration count)
+    x, res = lin.cg_solve(j, None, absdelta=1e-30, miniter=6, maxiter=6)
+    ores = oracle.cg(lambda v: lay.pack(olh.metric(pos, lay.unpack(v))) + v, t2n(j), absdelta=1e-30, miniter=6, maxiter=6)
+    assert res.nit == ores.nit == 6 and rel_err(t2n(x), ores.x) < 1e-6
+    import pytest
+    with pytest.raises(ValueError):
+        nb.SignalModel(build_product(c, rt), tfn, scaling=(3.0, 1.0))
+    bad = nb.Gaussian(data.astype(np.float64), noise_cov_inv=1.0).amend(nb.SignalModel(build_product(c, rt), lambda f: f.sum()))
+    with pytest.raises(ValueError, match="pointwise"):
+        bad.energy(tp)
 
 
 def check_matern_variants(rt):

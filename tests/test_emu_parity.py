@@ -146,3 +146,9 @@ def test_staged_chain_vs_oracle(rt, monkeypatch, shape, dist, kind):
     pc.check_against_oracle(rt, shape, dist, lh_kind=kind)
     monkeypatch.setenv("NB200_P5F", "1")
     pc.check_against_oracle(rt, shape, dist, lh_kind=kind)
+
+
+@pytest.mark.parametrize("which,lh_kind,shape", [("softplus", "gauss", (16, 32)), ("sigmoid_scaled", "poisson", (32, 16)),
+                                                 ("square_plus", "gauss", (8, 8, 16))])
+def test_custom_pointwise_nonlinearity(rt, which, lh_kind, shape):
+    pc.check_custom_nonlinearity(rt, shape, 0.1, lh_kind=lh_kind, which=which)

@@ -152,3 +152,9 @@ def test_hartley_vs_torch_fft_large(rt):
     ref = f.real + f.imag
     out = plan.hartley(x)
     assert float((out - ref).abs().max()) < 1e-10 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("which,lh_kind,shape", [("softplus", "gauss", (16, 32)), ("sigmoid_scaled", "poisson", (32, 16)),
+                                                 ("square_plus", "gauss", (8, 8, 16))])
+def test_custom_pointwise_nonlinearity(rt, which, lh_kind, shape):
+    pc.check_custom_nonlinearity(rt, shape, 0.1, lh_kind=lh_kind, which=which)

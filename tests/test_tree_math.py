@@ -74,3 +74,31 @@ def test_gaussian_callable_covariance_must_be_diagonal():
     assert torch.allclose(torch.as_tensor(lh.w_array), torch.full((4, 6), 9.0, dtype=torch.float64))
     with pytest.raises(NotImplementedError):
         Gaussian(d, noise_cov_inv=lambda x: x + torch.roll(x, 1, 1))          # couples neighbours
+
+
+def test_vector_and_model_containers():
+    """`Vector`, `Model`, `WrappedCall`, `Initializer` (tree_math/vector.py:79-188, model.py:32-340): arithmetic, `@`, evaluation,
+    per-leaf key splitting of `init`, shape of `target`."""
+    import numpy as np
+    import pytest
+    import torch
+    import nifty_b200 as nb
+    a = nb.Vector({"x": torch.arange(3.0), "y": torch.ones(2, 2)})
+    b = nb.Vector({"x": torch.ones(3), "y": 2.0 * torch.ones(2, 2)})
+    c = 2.0 * a - b / 2.0 + 1.0
+    assert torch.equal(c["x"], 2.0 * torch.arange(3.0) - 0.5 + 1.0) and torch.equal(c["y"], torch.full((2, 2), 2.0))
+    assert a @ b == pytest.approx(3.0 + 8.0) and len(a) == 2 and a.size == 7
+    assert nb.vdot(a, b) == pytest.approx(11.0) and nb.norm(-a) == pytest.approx(nb.norm(a))
+    m = nb.Model(lambda p: p["x"].sum() * p["y"], domain={"x": (3,), "y": (2, 2)}, white_init=True)
+    assert m.target == (2, 2)
+    p0, p1, p0b = m.init(7), m.init(8), m.init(7)
+    assert set(p0) == {"x", "y"} and p0["x"].shape == (3,) and p0["y"].shape == (2, 2)
+    assert torch.equal(p0["x"], p0b["x"]) and not torch.equal(p0["x"], p1["x"]) and not torch.equal(p0["x"][:2], p0["y"].reshape(-1)[:2])
+    assert torch.allclose(m(nb.Vector(p0)), p0["x"].sum() * p0["y"])
+    w = nb.WrappedCall(torch.exp, name="z", shape=(4,), white_init=True)
+    z = w.init(1)
+    assert torch.allclose(w(z), torch.exp(z["z"])) and w.domain == {"z": (4,)}
+    init = nb.Initializer({"a": lambda k: torch.zeros(2), "b": lambda k: torch.ones(1)})
+    assert torch.equal(init(0)["b"], torch.ones(1))
+    with pytest.raises(NotImplementedError):
+        nb.Gaussian(np.zeros((2, 2))).amend(m)          # an arbitrary call cannot sit under a likelihood on this path
