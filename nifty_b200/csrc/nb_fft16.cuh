@@ -314,9 +314,6 @@ inline void tma_gather(void* dst, const TmaDesc* d, int col, int row, Mbar*) {
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, Mbar*) { std::memcpy(dst, src, bytes); }
 inline void bulk_prefetch_l2(const void*, unsigned) {}
 inline void fence_async_smem() {}
-inline void cp_async_i32(int* dst, const int* src) { *dst = *src; }
-inline void cp_async_commit() {}
-inline void cp_async_wait_all() {}
 #else
 typedef unsigned long long Mbar;
 __device__ NB_INLINE unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -362,13 +359,6 @@ __device__ NB_INLINE void bulk_g2s(void* dst, const void* src, unsigned bytes, M
 __device__ NB_INLINE void bulk_prefetch_l2(const void* src, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
-// 4-byte asynchronous global -> shared copies (LDGSTS: no registers held while the data is in flight); rows of 32-bit table
-// entries that start at arbitrary element offsets cannot use the 16-byte aligned bulk copies
-__device__ NB_INLINE void cp_async_i32(int* dst, const int* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ NB_INLINE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ NB_INLINE void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // orders earlier generic-proxy accesses of shared memory before later async-proxy (bulk copy) writes
 __device__ NB_INLINE void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif

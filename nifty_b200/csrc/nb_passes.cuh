@@ -153,12 +153,6 @@ template <class T> struct ProMetric {
     q.t0 = ld_stream(t + offA + e); q.t1 = ld_stream(t + offA + ne); q.t2 = ld_stream(t + offB + e); q.t3 = ld_stream(t + offB + ne);
   }
   NB_HD NB_INLINE void gather(Pre& q) const { q.g = ldg(ad + q.b); }
-  // the same with the bin index at hand (index rows staged in shared memory): the table gather goes out with the streaming loads
-  NB_HD NB_INLINE void preload_bin(long offA, long offB, int b, int e, int ne, Pre& q) const {
-    q.b = b; q.g = ldg(ad + b);
-    q.x0 = ld_stream(xi + offA + e); q.x1 = ld_stream(xi + offA + ne); q.x2 = ld_stream(xi + offB + e); q.x3 = ld_stream(xi + offB + ne);
-    q.t0 = ld_stream(t + offA + e); q.t1 = ld_stream(t + offA + ne); q.t2 = ld_stream(t + offB + e); q.t3 = ld_stream(t + offB + ne);
-  }
   NB_HD NB_INLINE void finish(const Pre& q, T* v) const {
     const T cj = ldg(scal), da0 = ldg(scal + 1);
     const T dA = (q.b == 0) ? da0 : q.g.x * (cj + kappa * q.g.y);

@@ -138,7 +138,6 @@ template <class T> struct P5FParams {
   int ntiles;
   int prefetch;            // L2 bulk prefetch of the epilogue rows of the next tile
   int staged_epi;          // epilogue inputs through shared memory (run_staged)
-  int idx_smem;            // bin-index rows of the tile in shared memory (asynchronous 4-byte copies one tile ahead)
   EpiAdjoint<T> epi;
 };
 
@@ -349,23 +348,8 @@ template <class T, int LG, bool SE = false> struct P5FBody {
     L5Info* li = reinterpret_cast<L5Info*>(sm + SL::INFO_OFF);
     Mbar* bar = reinterpret_cast<Mbar*>(sm + SL::BAR_OFF);
     void* scratch = reinterpret_cast<void*>(sm + SL::SCRATCH_OFF);
-    // bin-index rows of the tile in shared memory (p.idx_smem): the amplitude gather of the epilogue then goes out together
-    // with its streaming loads (one dependent round trip per chunk instead of two).  The rows of the NEXT tile are copied
-    // asynchronously (4-byte cp.async: no registers, rows start at arbitrary element offsets) while this tile is transformed.
-    int* sidx = reinterpret_cast<int*>(sm + SIDX_OFF);
-    auto idx_rows = [&](Ctx& c, int tile_) {
-      const int l0_ = p.line0 + tile_ * LPC;
-      constexpr int TOT = LPC * (H + 1);
-      for (int i = c.tid; i < TOT; i += c.nthr) {
-        const int ln = i / (H + 1), k = i - ln * (H + 1);
-        L5Info q;
-        if (line_info(p, l0_ + ln, q)) cp_async_i32(sidx + i, p.epi.idxf + q.fbase + k);
-      }
-      cp_async_commit();
-    };
     Team<TS> tm(ctx);
     tm.all([&](int vt, TS& S) { F::init(S.th, vt, p.tw, 1); S.acc = 0; });
-    if (p.idx_smem && ctx.bid < p.ntiles) tm.coop([&](Ctx& c) { idx_rows(c, ctx.bid); });
     tm.one([&]() { mbar_init(bar, 1); });
     tm.sync();
     int tile = ctx.bid;
@@ -379,7 +363,6 @@ template <class T, int LG, bool SE = false> struct P5FBody {
       tm.sync();
       tm.all([&](int, TS& S) {
         mbar_wait(bar, phase);
-        if (p.idx_smem) cp_async_wait_all();         // this thread's share of the tile's bin-index rows has landed
         if (li[S.th.r].active != 0) {
 #pragma unroll
           for (int s = 0; s < 16; ++s) S.a[s] = stage[S.th.r * N + F::elem(S.th, s)];
@@ -407,17 +390,14 @@ template <class T, int LG, bool SE = false> struct P5FBody {
 #pragma unroll
           for (int u = 0; u < CHK; ++u) {
             const int x = F::elem(S.th, c + u), y = (N - x) & (N - 1);
-            if (p.idx_smem) { b[u] = sidx[S.th.r * (H + 1) + fold_idx(x, N)]; A[u] = ldg(E.amp + b[u]); }
-            else b[u] = ldg(E.idxf + q.fbase + fold_idx(x, N));
+            b[u] = ldg(E.idxf + q.fbase + fold_idx(x, N));
             aA[u] = E.add ? ld_ro(E.add + q.rowA + x) : T(0);
             aB[u] = E.add ? ld_ro(E.add + rB + y) : T(0);
             xA[u] = E.xi ? ld_ro(E.xi + q.rowA + x) : T(0);
             xB[u] = E.xi ? ld_ro(E.xi + rB + y) : T(0);
           }
-          if (!p.idx_smem) {
 #pragma unroll
-            for (int u = 0; u < CHK; ++u) A[u] = ldg(E.amp + b[u]);
-          }
+          for (int u = 0; u < CHK; ++u) A[u] = ldg(E.amp + b[u]);
 #pragma unroll
           for (int u = 0; u < CHK; ++u) {
             const int x = F::elem(S.th, c + u), y = (N - x) & (N - 1);
@@ -441,10 +421,8 @@ template <class T, int LG, bool SE = false> struct P5FBody {
           for (int s = 0; s < 16; ++s) wv[S.th.r * N + F::elem(S.th, s)] = S.a[s].x;
         }
       });
-      const bool more_idx = p.idx_smem && tile + ctx.nblk < p.ntiles;
       if (E.W) {
         tm.sync();
-        if (more_idx) tm.coop([&](Ctx& c) { idx_rows(c, tile + ctx.nblk); });      // (every thread is past the epilogue)
         tm.all([&](int, TS& S) {
           const L5Info q = li[S.th.r];
           if (!q.active) return;
@@ -460,7 +438,6 @@ template <class T, int LG, bool SE = false> struct P5FBody {
         });
       }
       tm.sync();
-      if (more_idx && !E.W) tm.coop([&](Ctx& c) { idx_rows(c, tile + ctx.nblk); });
     }
     if (E.partials) {
       T tot = team_sum(tm, scratch, [](const TS& S) { return S.acc; });
@@ -749,7 +726,6 @@ template <class T, class Pro> struct P1FParams {
   const cplx<T>* tw; int lg_tw;     // table for the real length (2^lg_tw entries, lg_tw >= lg_n)
   cplx<T>* out;            // [o * n_r + row][k in 0..N]
   int ntiles;
-  int idx_smem;            // bin-index rows of the tile in shared memory (asynchronous 4-byte copies one tile ahead)
   Pro pro;
 };
 
@@ -769,21 +745,7 @@ template <class T, class Pro, int LG> struct P1FBody {
     return i == 0 ? (n_r >> 1) : n_r - i;
   }
   // the quad loop of P1MBody, writing real element x of line L to sr[L * 2 N + x]
-  static constexpr size_t SIDX_OFF = SL::BYTES + 512;
-  static constexpr size_t SIDX_BYTES = (size_t)(F16_TILE / 2 + LPC + 8) * sizeof(int);
-  static constexpr size_t BYTES_IDX = SL::BYTES + SIDX_BYTES;
-  // rows of the folded bin table of the HR mirror pairs of a tile -> shared memory, asynchronously (row rp: N + 1 entries)
-  static NB_HD NB_INLINE void idx_rows(Ctx& c, const Params& p, int* sidx, int tile) {
-    const int gpo = p.n_r / LPC, o = tile / gpo, i0 = (tile % gpo) * HR;
-    constexpr int TOT = HR * (N + 1);
-    for (int i = c.tid; i < TOT; i += c.nthr) {
-      const int rp = i / (N + 1), k = i - rp * (N + 1);
-      const int ra = (i0 + rp != 0) ? i0 + rp : 1;
-      cp_async_i32(sidx + i, p.pro.bins(o, ra) + k);
-    }
-    cp_async_commit();
-  }
-  static NB_HD NB_INLINE void prologue(Ctx& ctx, const Params& p, T* sr, int o, int i0, const int* sidx = nullptr) {
+  static NB_HD NB_INLINE void prologue(Ctx& ctx, const Params& p, T* sr, int o, int i0) {
     const int n = 2 * N, h = N, lg_h = LG;
     const long in0 = (long)o * p.in_ostride;
 #define NB_P1F_SLOT(L, x) ((L) * (2 * N) + (x))
@@ -803,8 +765,7 @@ template <class T, class Pro, int LG> struct P1FBody {
           sl[u].rp = rp; sl[u].e = e;
           e = e != 0 ? e : 1;
           int ra = (i != 0) ? i : 1, rb = p.n_r - ra;
-          if (sidx) p.pro.preload_bin(in0 + ra * p.in_rstride, in0 + rb * p.in_rstride, sidx[rp * (N + 1) + e], e, n - e, sl[u].pre);
-          else p.pro.preload(in0 + ra * p.in_rstride, in0 + rb * p.in_rstride, p.pro.bins(o, ra), e, n - e, sl[u].pre);
+          p.pro.preload(in0 + ra * p.in_rstride, in0 + rb * p.in_rstride, p.pro.bins(o, ra), e, n - e, sl[u].pre);
         }
       };
       auto consume = [&](int, const Slot* sl) {
@@ -819,7 +780,6 @@ template <class T, class Pro, int LG> struct P1FBody {
         }
       };
       auto gather = [&](Slot* sl) {
-        if (sidx) return;
 #pragma unroll
         for (int u = 0; u < U; ++u) p.pro.gather(sl[u].pre);
       };
@@ -850,15 +810,10 @@ template <class T, class Pro, int LG> struct P1FBody {
     tm.all([&](int vt, TS& S) { F::init(S.th, vt, p.tw, 2 << tsh); S.zh = cmake<T>(0, 0); });
     const int gpo = p.n_r / LPC;
     const T half = T(0.5);
-    int* sidx = reinterpret_cast<int*>(sm + SIDX_OFF);
-    if (p.idx_smem && ctx.bid < p.ntiles) tm.coop([&](Ctx& c) { idx_rows(c, p, sidx, ctx.bid); });
     for (int tile = ctx.bid; tile < p.ntiles; tile += ctx.nblk) {
       const int o = tile / gpo, i0 = (tile % gpo) * HR;
-      if (p.idx_smem) { tm.all([&](int, TS&) { cp_async_wait_all(); }); tm.sync(); }
-      tm.coop([&](Ctx& c) { prologue(c, p, reinterpret_cast<T*>(stage), o, i0, p.idx_smem ? sidx : nullptr); });
+      tm.coop([&](Ctx& c) { prologue(c, p, reinterpret_cast<T*>(stage), o, i0); });
       tm.sync();
-      // (the quad loop is done with the index rows: the rows of the next tile travel while this tile is transformed)
-      if (p.idx_smem && tile + ctx.nblk < p.ntiles) tm.coop([&](Ctx& c) { idx_rows(c, p, sidx, tile + ctx.nblk); });
       tm.all([&](int, TS& S) {
 #pragma unroll
         for (int s = 0; s < 16; ++s) S.a[s] = stage[S.th.r * N + F::elem(S.th, s)];

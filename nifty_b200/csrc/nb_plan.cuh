@@ -232,11 +232,6 @@ template <class T> struct Plan : PlanBase {
   bool chain_ok = false;        // ... and every pass of the metric chain is covered (line lengths 32 .. 4096)
   bool use_chain = false;       // set by the operator that runs the whole chain (ChainScope), read by run_*
   int p5f_forced = -1;          // NB200_P5F=1 / 0: register-resident last pass forced on / off (default: chosen per shape)
-  // bin-index rows of a tile copied to shared memory one tile ahead by 4-byte cp.async (so that the table gather goes out
-  // with the streaming loads): measured SLOWER (first pass 160 -> 227 us, last pass 175 -> 232 us at 4096^2,
-  // profiles/r3_notes.md); kept behind NB200_P1F_IDX=1 / NB200_P5F_IDX=1
-  bool p1f_idx_smem = false;
-  bool p5f_idx_smem = false;
   bool p5_sidx = true;          // NB200_P5_SIDX=0: the last pass reads the bin indices of its epilogue from global memory
   bool p5f_staged_epi = false;    // NB200_P5F_SE=0: the register-resident last pass loads its epilogue inputs per thread
   bool p3_stage_jl = true;      // NB200_P3_SJL=0: per-thread global loads of the Jacobian weights in the staged axis-0 pass
@@ -407,8 +402,6 @@ template <class T> struct Plan : PlanBase {
       if (const char* e = std::getenv("NB200_P3_SJL")) p3_stage_jl = (e[0] == '1');
       if (const char* e = std::getenv("NB200_P5F_SE")) p5f_staged_epi = (e[0] == '1');
       if (const char* e = std::getenv("NB200_P5_SIDX")) p5_sidx = (e[0] == '1');
-      if (const char* e = std::getenv("NB200_P5F_IDX")) p5f_idx_smem = (e[0] == '1');
-      if (const char* e = std::getenv("NB200_P1F_IDX")) p1f_idx_smem = (e[0] == '1');
     }
     if (staged_ok) {
       // gather descriptors: P3 / P5 read column l of [n_line][(h+1) n_mid]; PCa / PCb read column k of the rows of one plane
@@ -493,8 +486,7 @@ template <class T> struct Plan : PlanBase {
         const int lpc = F16_TILE >> lgc;
         q.ntiles = (g.three ? rows0 : 1) * (p.n_r / lpc);
         const int grid = std::min(q.ntiles, 2 * sms);
-        q.idx_smem = p1f_idx_smem ? 1 : 0;
-#define NB_CALL(LG) launch<P1FBody<T, Pro, LG>>(grid, F16_NT, q.idx_smem ? P1FBody<T, Pro, LG>::BYTES_IDX : StageLayout<T, LG>::BYTES, st, q)
+#define NB_CALL(LG) launch<P1FBody<T, Pro, LG>>(grid, F16_NT, StageLayout<T, LG>::BYTES, st, q)
         switch (lgc) {
           case 5: NB_CALL(5); break; case 6: NB_CALL(6); break; case 7: NB_CALL(7); break; case 8: NB_CALL(8); break;
           case 9: NB_CALL(9); break; case 10: NB_CALL(10); break; default: NB_CALL(11); break;
@@ -564,7 +556,7 @@ template <class T> struct Plan : PlanBase {
 #undef NB_CALL
       return;
     }
-#define NB_CALL(LG) launch<P5FBody<T, LG, false>>(gridf, F16_NT, q.idx_smem ? P5FBody<T, LG, false>::BYTES_STAGED : StageLayout<T, LG>::BYTES, st, q)
+#define NB_CALL(LG) launch<P5FBody<T, LG, false>>(gridf, F16_NT, StageLayout<T, LG>::BYTES, st, q)
     NB_LG_SWITCH(lgl, NB_CALL)
 #undef NB_CALL
   }
@@ -641,7 +633,6 @@ template <class T> struct Plan : PlanBase {
         q.nlines = nlines >= 0 ? nlines : p.mg.nlines(); q.epi = epi; q.prefetch = l2_prefetch ? 1 : 0; // (bulk copies of the epilogue rows need 16-byte aligned rows)
         q.staged_epi = (p5f_staged_epi && ((uintptr_t)epi.add % 16) == 0 && ((uintptr_t)epi.xi % 16) == 0) ? 1 : 0;
         if (!q.staged_epi && epi.add == epi.out) goto generic_p5;
-        q.idx_smem = (!q.staged_epi && p5f_idx_smem) ? 1 : 0;
         const int lpc = F16_TILE >> lgl;
         q.ntiles = (q.nlines + lpc - 1) / lpc;
         const int gridf = std::min(q.ntiles, 2 * sms);

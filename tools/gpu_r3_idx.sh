@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the variant this script measured was removed again, see profiles/r3_notes.md)
 # bin-index rows in shared memory via cp.async (first pass / register-resident last pass): A/B + staged-chain parity tests
 mkdir -p gpurun_out
 {
