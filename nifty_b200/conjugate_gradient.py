@@ -18,7 +18,7 @@ Two execution paths, same semantics (``info``: 0 converged, i > 0 stopped at ite
 from __future__ import annotations
 
 import os
-
+from datetime import datetime
 from typing import Callable, NamedTuple, Optional
 
 import numpy as np
@@ -109,8 +109,12 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
             raise ValueError("a slab-decomposed HamiltonianMetric needs its likelihood (for the distributed reductions)")
         if norm_ord in (1, 2) and os.environ.get("NB200_SLAB_CG", "1") != "0":
             return _cg_slab(mat, j, x0, absdelta=absdelta, resnorm=resnorm, norm_ord=norm_ord, tol=tol, atol=atol, miniter=miniter,
-                            maxiter=maxiter, name=name, _raise_nonposdef=_raise_nonposdef)
+                            maxiter=maxiter, name=name, _raise_nonposdef=_raise_nonposdef, time_threshold=time_threshold)
         vdot, vnorm = mat.likelihood.vdot, mat.likelihood.vnorm
+    elif isinstance(mat, (SampleAveragedMetric, HamiltonianMetric)) and time_threshold is not None:
+        # the device solves evaluate their stopping rules on the GPU; a wall-clock rule belongs to the host loop
+        raise NotImplementedError("`time_threshold` is not available for the device-resident CG (pass a plain callable `mat` for "
+                                  "the host loop, which honours it)")
     elif isinstance(mat, SampleAveragedMetric):
         from ._runtime import cg_solve_multi
         x, res = cg_solve_multi(mat.lins, j, x0, scale=mat.scale, identity_here=mat.identity_here, reduce_fn=mat.reduce_fn,
@@ -187,6 +191,9 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
         else:
             r = r - q * alpha
         gamma = vdot(r, r)
+        if time_threshold is not None and datetime.now() > time_threshold:      # conjugate_gradient.py:174-176
+            info = i
+            break
         if 0.0 <= gamma <= tiny:
             info = 0
             break
@@ -238,7 +245,7 @@ class _SlabReductions:
         return (t + torch.stack(rep).to(torch.float64)).tolist()          # (the one host synchronisation of the group)
 
 
-def _cg_slab(mat, j, x0, *, absdelta, resnorm, norm_ord, tol, atol, miniter, maxiter, name, _raise_nonposdef) -> CGResults:
+def _cg_slab(mat, j, x0, *, absdelta, resnorm, norm_ord, tol, atol, miniter, maxiter, name, _raise_nonposdef, time_threshold=None) -> CGResults:
     """The recurrence of ``_cg`` (conjugate_gradient.py:107-214, same stopping rules and ``info`` codes) for slab-decomposed
     fields: vector updates in place (``add_`` with a scalar multiplier, no temporaries), reductions in groups
     (:class:`_SlabReductions`).  Per iteration: one product, one curvature all-reduce, one all-reduce of
@@ -299,6 +306,9 @@ def _cg_slab(mat, j, x0, *, absdelta, resnorm, norm_ord, tol, atol, miniter, max
         want_norm = resnorm is not None and norm_ord == 1
         vals = red(dots=[(r, r), (tmp, pos)], norms1=[r] if want_norm else ())
         gamma, new_energy = vals[0], 0.5 * vals[1]
+        if time_threshold is not None and datetime.now() > time_threshold:
+            info = i
+            break
         if 0.0 <= gamma <= tiny:
             info = 0
             break

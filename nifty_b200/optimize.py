@@ -5,6 +5,8 @@ from __future__ import annotations
 
 from typing import Callable, NamedTuple, Optional
 
+from datetime import datetime
+
 import numpy as np
 import torch
 
@@ -38,7 +40,7 @@ def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reductio
     pos = x0.clone()
     xtol = xtol * (pos.numel() if _size is None else _size)      # _size: number of non-frozen entries (point estimates)
     cg_kwargs = {} if cg_kwargs is None else dict(cg_kwargs)
-    cg_name = cg_kwargs.pop("name", None)
+    cg_name = cg_kwargs.pop("name", name + "CG" if name is not None else None)      # optimize.py:302
     gradnorm = (lambda v: _nrm(v, norm_ord)) if custom_gradnorm is None else custom_gradnorm
     if fun_and_grad is None:
         raise ValueError("`fun_and_grad` is required on the B200 path (no automatic differentiation)")
@@ -57,6 +59,8 @@ def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reductio
         kw = dict(absdelta=cg_absdelta, resnorm=cg_resnorm, norm_ord=1, name=cg_name, _raise_nonposdef=False)
         if vdot is not None:
             kw.update(vdot=vdot, vnorm=vnorm)
+        if time_threshold is not None:
+            kw["time_threshold"] = time_threshold
         kw.update(cg_kwargs)
         op = hessp_at(pos) if hessp_at is not None else (lambda v, _p=pos: hessp(_p, v))
         res = cg(op, g, **kw)
@@ -96,6 +100,9 @@ def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reductio
             break
         if descent_norm <= xtol and i > miniter:
             status = 0
+            break
+        if time_threshold is not None and datetime.now() > time_threshold:      # optimize.py:394-396
+            status = i
             break
     else:
         status = i

@@ -102,3 +102,29 @@ def test_vector_and_model_containers():
     assert torch.equal(init(0)["b"], torch.ones(1))
     with pytest.raises(NotImplementedError):
         nb.Gaussian(np.zeros((2, 2))).amend(m)          # an arbitrary call cannot sit under a likelihood on this path
+
+
+def test_time_threshold_and_cg_name():
+    """`time_threshold` stops the host CG / Newton-CG with `info = i` / `status = i` (conjugate_gradient.py:174-176,
+    optimize.py:394-396); the inner CG of Newton-CG is named `name + "CG"` (optimize.py:302)."""
+    from datetime import datetime, timedelta
+    import torch
+    from nifty_b200.conjugate_gradient import _cg
+    from nifty_b200.optimize import _newton_cg
+    a = torch.diag(torch.linspace(1, 50, 40, dtype=torch.float64))
+    j = torch.ones(40, dtype=torch.float64)
+    past, future = datetime.now() - timedelta(seconds=1), datetime.now() + timedelta(hours=1)
+    r = _cg(lambda v: a @ v, j, absdelta=1e-30, maxiter=100, time_threshold=past)
+    assert (r.nit, r.info) == (1, 1)
+    r2 = _cg(lambda v: a @ v, j, absdelta=1e-12, maxiter=100, time_threshold=future)
+    assert r2.info == 0 and torch.allclose(a @ r2.x, j, atol=1e-5)
+    seen = {}
+
+    def spy_cg(mat, jj, **kw):
+        seen.update(kw)
+        return _cg(mat, jj, **{k: v for k, v in kw.items()})
+
+    fg = lambda x: (float(0.5 * x @ a @ x - j @ x), a @ x - j)      # noqa: E731
+    res = _newton_cg(None, x0=torch.zeros(40, dtype=torch.float64), fun_and_grad=fg, hessp=lambda p, v: a @ v, name="N", cg=spy_cg,
+                     time_threshold=past, cg_kwargs=dict(maxiter=5))
+    assert (res.nit, res.status) == (1, 1) and seen["name"] == "NCG" and seen["time_threshold"] == past
