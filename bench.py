@@ -172,8 +172,34 @@ def cpu_mvp_once(lh, lay, pos, tan):
     return {k: out[k] + tan[k] for k in out}
 
 
+def _nifty_re_leg():
+    """baseline/run_nifty_re_cpu.py when `nifty.re` on JAX-CPU is importable on this box (it is not in this image), else None."""
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("run_nifty_re_cpu", os.path.join(ROOT, "baseline", "run_nifty_re_cpu.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod if mod.available() else None
+    except Exception:
+        return None
+
+
 def run_reference(args, shape, wname, rank, world):
     if rank != 0:
+        return
+    re_leg = _nifty_re_leg()
+    if re_leg is not None:      # the reference itself (kind = "reference"); protocol of misc/re/paper/minimal_benchmark.py
+        cores = os.cpu_count() or 1
+        dt = re_leg.time_metric_products(shape, cores)
+        val = 1.0 / dt
+        line = {"impl": "reference", "metric": "metric_vector_products_per_sec", "value": val, "unit": "MVP/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wname, "shape": list(shape), "what": WORKLOADS[wname][1], "cpu_path": "nifty.re on JAX-CPU"},
+                "cpu_baseline": {"value": val, "unit": "MVP/s", "cores": cores, "kind": "reference",
+                                 "sample": f"median of 7 timeit repeats of lh.metric(pos, t) + t at {wname}"},
+                "e2e": {"value": val, "unit": "MVP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
         return
     t0 = time.time()
     lh, lay, pos, tan, cores = cpu_setup(shape)

@@ -44,10 +44,34 @@ def random_normal(key, shape, dtype, device) -> torch.Tensor:
     return torch.randn(shape, dtype=dtype, device=device, generator=gen)
 
 
-def random_like(key, lh: LikelihoodWithModel) -> torch.Tensor:
-    """``jft.random_like(key, pos)``: standard-normal latent vector (tree_math/forest_math.py:60-72).
-    Slab-decomposed fields: the replicated hyper-parameter leaves come from the shared key, the local
-    excitation rows from a per-rank child key; padding rows are zero."""
+def random_like(key, lh, dtype=torch.float64, device="cpu"):
+    """``jft.random_like(key, primals)`` (tree_math/forest_math.py:60-72).  With a latent TREE (dict / ``Vector`` of arrays or
+    shapes) as second argument: the key is split into one sub-key per leaf in sorted-key (pytree) order and every leaf is a
+    standard-normal draw of its shape -- the reference's semantics (the draws themselves come from this package's key
+    scheme, not from threefry).  With a likelihood: the flat standard-normal latent vector of its model; slab-decomposed
+    fields: the replicated hyper-parameter leaves come from the shared key, the local excitation rows from a per-rank child
+    key; padding rows are zero."""
+    if not isinstance(lh, LikelihoodWithModel):
+        from .tree_math import Vector, _leaves
+        from .model import _map_domain, _shape_of
+        tree = lh.tree if isinstance(lh, Vector) else lh
+        leaves_sorted = _leaves(_map_domain(lambda s: (s,), tree))          # one entry per leaf, sorted-key order
+        keys = iter(random_split(key, len(leaves_sorted)))
+
+        def draw(s):
+            dt = s.dtype if isinstance(s, torch.Tensor) else dtype
+            dv = s.device if isinstance(s, torch.Tensor) else device
+            return random_normal(next(keys), _shape_of(s), dt, dv)
+
+        def walk(t):
+            if isinstance(t, dict):
+                return {k: walk(t[k]) for k in sorted(t)}
+            if isinstance(t, (tuple, list)) and not all(isinstance(i, (int, np.integer)) for i in t):
+                return type(t)(walk(v) for v in t)
+            return draw(t)
+
+        out = walk(tree)
+        return Vector(out) if isinstance(lh, Vector) else out
     plan = lh.signal.cf.plan
     if not plan.dist:
         return random_normal(key, (lh.layout.size,), lh.dtype, lh.rt.device)

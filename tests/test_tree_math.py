@@ -128,3 +128,19 @@ def test_time_threshold_and_cg_name():
     res = _newton_cg(None, x0=torch.zeros(40, dtype=torch.float64), fun_and_grad=fg, hessp=lambda p, v: a @ v, name="N", cg=spy_cg,
                      time_threshold=past, cg_kwargs=dict(maxiter=5))
     assert (res.nit, res.status) == (1, 1) and seen["name"] == "NCG" and seen["time_threshold"] == past
+
+
+def test_random_like_tree_form():
+    """`random_like(key, tree)` (forest_math.py:60-72): one sub-key per leaf in sorted-key order, leaf shapes / dtypes kept,
+    reproducible, independent leaves; `Vector` in -> `Vector` out."""
+    import torch
+    import nifty_b200 as nb
+    tree = {"b": (2, 3), "a": torch.zeros(4, dtype=torch.float32)}
+    t, t2, t3 = nb.random_like(3, tree), nb.random_like(3, tree), nb.random_like(4, tree)
+    assert t["a"].shape == (4,) and t["a"].dtype == torch.float32 and t["b"].shape == (2, 3) and t["b"].dtype == torch.float64
+    assert torch.equal(t["a"], t2["a"]) and torch.equal(t["b"], t2["b"]) and not torch.equal(t["b"], t3["b"])
+    # the leaf keys follow the sorted order: leaf "a" gets the first sub-key whatever the insertion order
+    ka = nb.random_split(3, 2)[0]
+    from nifty_b200.evi import random_normal
+    assert torch.equal(t["a"], random_normal(ka, (4,), torch.float32, "cpu"))
+    assert isinstance(nb.random_like(1, nb.Vector({"x": (2,)})), nb.Vector)
