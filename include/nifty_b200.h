@@ -161,7 +161,7 @@ void nb200_lin_destroy(nb200_lin* lin);
 int nb200_lin_update(nb200_lin* lin, void* stream, const void* pos, void* grad, int add_prior);
 /* Models with nonlinearity = 2 ("tabulated": any pointwise map signal = f(correlated field), the `Model(lambda x: f(cf(x)))`
  * of nifty/re/model.py:146-181): before every nb200_lin_update the host evaluates f and f' at the field of that position
- * (nb200_model_cf_forward gives the field) and hands both over, natural order, plan dtype.  Everything after the
+ * (nb200_cf_forward gives the field) and hands both over, natural order, plan dtype.  Everything after the
  * linearisation (metric, sqrt-metrics, CG, ...) is unchanged: it only sees the cached signal and Jacobian weights. */
 int nb200_lin_set_pointwise(nb200_lin* lin, void* stream, const void* signal, const void* dsignal);
 /* likelihood energy of the last nb200_lin_update (synchronises the stream) */
