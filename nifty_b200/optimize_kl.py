@@ -72,6 +72,41 @@ class _Comm:
             return self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
         return None
 
+    def tree_sum(self, local: dict, n_global: int, owner) -> torch.Tensor:
+        """Sum of one vector per GLOBAL sample index in a fixed binary tree over the indices (level s: index g, a multiple of
+        2 s, absorbs g + s as left + right) -- the result does not depend on how many ranks hold the samples, bit for bit (the
+        pattern of the reference's MPI reduction, nifty/cl/utilities.py:349-415).  `local`: {global index: vector} of this
+        rank, `owner(g)`: rank holding index g.  Pairs on different ranks exchange point to point, every rank walks the same
+        (level, index) sequence, so the blocking sends / receives cannot deadlock.  Returns the total on every rank."""
+        vals = dict(local)
+        s = 1
+        while s < n_global:
+            for g in range(0, n_global, 2 * s):
+                h = g + s
+                if h >= n_global:
+                    continue
+                og, oh = owner(g), owner(h)
+                if og == self.rank and oh == self.rank:
+                    vals[g] = vals[g] + vals.pop(h)
+                elif oh == self.rank:
+                    self.dist.send(vals.pop(h).contiguous(), dst=self._global_rank(og), group=self.group)
+                elif og == self.rank:
+                    buf = torch.empty_like(vals[g])
+                    self.dist.recv(buf, src=self._global_rank(oh), group=self.group)
+                    vals[g] = vals[g] + buf
+            s *= 2
+        root = owner(0)
+        if self.world == 1:
+            return vals[0]
+        any_vec = next(iter(local.values())) if local else None
+        shape_src = vals[0] if root == self.rank else any_vec
+        total = vals[0] if root == self.rank else torch.empty_like(shape_src)
+        self.dist.broadcast(total, src=self._global_rank(root), group=self.group)
+        return total
+
+    def _global_rank(self, r: int) -> int:
+        return r if self.group is None else self.dist.get_global_rank(self.group, r)
+
     def allgather(self, t: torch.Tensor):
         """Per-rank tensors whose leading extent may differ between ranks (uneven sample sharding): the counts are
         exchanged first, every rank pads to the maximum, the result is trimmed again."""
@@ -129,6 +164,12 @@ class OptimizeVI:
         # jit / *_map / kl_reduce select how JAX traces and batches the per-sample work (optimize_kl.py:228-246); here every
         # sample point is a sequence of device launches and the reduction over samples is the mean, so they are accepted
         # for call compatibility only.  The two options that would change results are refused.
+        # kl_reduce="fixed_tree": the sums over the sample points of the KL (value, gradient, metric) are taken in a fixed binary
+        # tree over the GLOBAL sample indices, so the results do not depend on the number of ranks, bit for bit (slower: one
+        # vector per sample travels point to point, the KL-CG runs in the host loop).  Default: all-reduce of per-rank sums.
+        if kl_reduce not in (None, "fixed_tree") and not callable(kl_reduce):
+            raise ValueError("kl_reduce must be None, 'fixed_tree' or (ignored, for call compatibility) a callable")
+        self.fixed_tree = kl_reduce == "fixed_tree"
         if not mirror_samples:
             raise NotImplementedError("mirror_samples=False is not supported on the B200 path")
         if devices is not None:
@@ -242,6 +283,8 @@ class OptimizeVI:
         if residuals is not None and len(residuals) == 0 and self.comm.world > 1:
             pts = []
         self._ensure_lins(len(pts))
+        if self.fixed_tree:
+            return self._kl_value_and_grad_tree(pos, pts)
         acc = torch.zeros(lh.layout.size + 2, dtype=torch.float64, device=lh.rt.device)
         for lin, x in zip(self._lins, pts):
             g = lin.update(x, want_grad=True, add_prior=True)
@@ -260,8 +303,43 @@ class OptimizeVI:
         self._n_total = int(round(n))
         return float(acc[0]) / n, (acc[2:] / n).to(lh.dtype)
 
+    # -- fixed-tree reductions (kl_reduce="fixed_tree") ------------------------------------------------
+    def _global_indices(self, n_local: int):
+        """Global sample index of every local sample point and the owner map: rank r holds the mirrored pairs of the keys
+        r, r + W, ... (one point per rank when every rank holds exactly one: the `n_samples == W / 2` layout or a MAP point)."""
+        W, r = self.comm.world, self.comm.rank
+        cnt = torch.tensor([n_local], dtype=torch.int64, device=self.likelihood.rt.device)
+        cnts = [int(c[0]) for c in self.comm.allgather(cnt)]
+        n = sum(cnts)
+        if all(c == 1 for c in cnts):
+            return [r], n, (lambda g: g)
+        return [2 * (r + (i // 2) * W) + (i % 2) for i in range(n_local)], n, (lambda g: (g // 2) % W)
+
+    def _kl_value_and_grad_tree(self, pos, pts):
+        lh = self.likelihood
+        local = {}
+        idx, n, owner = self._global_indices(len(pts))
+        for lin, x, g in zip(self._lins, pts, idx):
+            grad = lin.update(x, want_grad=True, add_prior=True)
+            e = lin.energy() + 0.5 * lh.vdot(x, x)
+            local[g] = torch.cat([torch.tensor([e], dtype=torch.float64, device=lh.rt.device), grad.to(torch.float64)])
+            lin._ever_updated = True
+        self._n_active, self._n_total = len(pts), n
+        self._tree_idx, self._tree_owner = idx, owner
+        tot = self.comm.tree_sum(local, n, owner)
+        return float(tot[0]) / n, (tot[1:] / n).to(lh.dtype)
+
+    def _kl_metric_tree(self, tangents, frozen=None):
+        local = {g: lin.metric(tangents, add_identity=True).to(torch.float64) for lin, g in zip(self._lins[:self._n_active], self._tree_idx)}
+        out = (self.comm.tree_sum(local, self._n_total, self._tree_owner) / self._n_total).to(self.likelihood.dtype)
+        for lo, hi in frozen or ():
+            out[lo:hi] = 0
+        return out
+
     def _kl_operator(self, frozen=None):
         """The sample-averaged metric at the points of the last :meth:`kl_value_and_grad` as a device operator."""
+        if self.fixed_tree:
+            return lambda t: self._kl_metric_tree(t, frozen)
         from .conjugate_gradient import SampleAveragedMetric
         lins = self._lins[:self._n_active]
         none_here = len(lins) == 0                     # more ranks than sample points: contribute zero
@@ -277,6 +355,8 @@ class OptimizeVI:
     def kl_metric(self, tangents: torch.Tensor) -> torch.Tensor:
         """``_kl_met`` at the points of the last :meth:`kl_value_and_grad`: mean of metric(x_i, t) + t, accumulated on the
         device (``nb200_metric_multi``); the all-reduce over the ranks is enqueued in-stream."""
+        if self.fixed_tree:
+            return self._kl_metric_tree(tangents)
         if self.likelihood.signal.cf.plan.dist:         # slab-decomposed fields: phase-wise products, host accumulation
             lh = self.likelihood
             acc = torch.zeros(lh.layout.size + 1, dtype=torch.float64, device=lh.rt.device)

@@ -50,6 +50,15 @@ def _worker(rank, world, port, outdir):
                              sample_mode="nonlinear_resample", draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=60)),
                              nonlinearly_update_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=20))),
                              kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=30))))
+    # fixed-tree reductions: KL value / gradient / metric independent of the number of ranks, bit for bit
+    vt = nb.OptimizeVI(lh, 1, comm=True, kl_reduce="fixed_tree")
+    st_smp, _ = vt.draw_linear_samples(pos, nb.random_split(123, 4), cg_kwargs=dict(absdelta=1e-8, maxiter=60))
+    v_t, g_t = vt.kl_value_and_grad(pos, st_smp.residuals)
+    m_t = vt.kl_metric(t)
+    s4, _ = nb.optimize_kl(lh, pos, key=5, n_total_iterations=1, n_samples=2, comm=True, kl_reduce="fixed_tree",
+                           sample_mode="linear_resample", draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=60)),
+                           kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=10))))
+    np.savez(os.path.join(outdir, f"tree{rank}.npz"), v=v_t, g=g_t.numpy(), m=m_t.numpy(), pos4=s4.pos.numpy())
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), res=samples.residuals.numpy(), v=v, g=gr.numpy(), m=m.numpy(),
              pos2=s2.pos.numpy(), nloc=len(samples), res_m=sm.residuals.numpy(), vm=vm, gm=gm.numpy(), pos3=s3.pos.numpy(),
              res3=s3.residuals.numpy())
@@ -86,6 +95,21 @@ def test_sample_sharding_matches_single_process(tmp_path):
         np.testing.assert_allclose(r[i]["m"], m.numpy(), rtol=0, atol=1e-12 * np.abs(m.numpy()).max())
     np.testing.assert_array_equal(r[0]["pos2"], r[1]["pos2"])   # replicated position stays bit-identical across ranks
     assert os.path.isfile(tmp_path / "ckpt" / "last.pkl")
+    # fixed tree: world 2 == world 1, bit for bit
+    vt = nb.OptimizeVI(lh, 1, kl_reduce="fixed_tree")
+    st_smp, _ = vt.draw_linear_samples(pos, nb.random_split(123, 4), cg_kwargs=dict(absdelta=1e-8, maxiter=60))
+    v_t, g_t = vt.kl_value_and_grad(pos, st_smp.residuals)
+    m_t = vt.kl_metric(lh.layout.random(9, torch.float64, rt.device))
+    s4, _ = nb.optimize_kl(lh, pos, key=5, n_total_iterations=1, n_samples=2, kl_reduce="fixed_tree",
+                           sample_mode="linear_resample", draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=60)),
+                           kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=10))))
+    for i in range(world):
+        tr = np.load(tmp_path / f"tree{i}.npz")
+        assert float(tr["v"]) == v_t
+        np.testing.assert_array_equal(tr["g"], g_t.numpy())
+        np.testing.assert_array_equal(tr["m"], m_t.numpy())
+        np.testing.assert_array_equal(tr["pos4"], s4.pos.numpy())
+    assert abs(v_t - v) <= 1e-12 * abs(v)                 # and it is the same KL as with the all-reduce
     # mirror rule: rank 0 holds +s0, rank 1 holds -s0; the KL equals the single-process KL over [s0, -s0]
     sm, _ = vi.draw_linear_samples(pos, nb.random_split(77, 1), cg_kwargs=dict(absdelta=1e-8, maxiter=60))
     vm, gm = vi.kl_value_and_grad(pos, sm.residuals)
