@@ -19,7 +19,7 @@ from .optimize_kl import OptimizeVI, OptimizeVIState, get_status_message, optimi
 from .minisanity import ChiSqStats, minisanity, reduced_residual_stats  # noqa: F401
 from .tree_math import (Vector, get_map, lmap, mean, mean_and_std, norm, size, smap, stack, unstack, vdot, where,  # noqa: F401
                         zeros_like)
-from .model import Initializer, LazyModel, Model, WrappedCall  # noqa: F401
+from .model import Initializer, LazyModel, Model, VModel, WrappedCall  # noqa: F401
 from .evidence_lower_bound import estimate_evidence_lower_bound  # noqa: F401
 from . import lanczos  # noqa: F401
 from .lanczos import lanczos_tridiag, stochastic_logdet_from_lanczos, stochastic_lq_logdet  # noqa: F401

@@ -165,6 +165,22 @@ def check_model_surface(rt, name="g2d_16x16"):
     mv = lh.metric(nb.Vector(pos), nb.Vector(tan))            # Vector in -> Vector out, same numbers as with plain trees
     assert isinstance(mv, nb.Vector) and tree_err(mv.tree, g["metric"]) < 1e-10
     assert rel_err(t2n(cf(nb.Vector(pos))), g["field"]) < 1e-10
+    # VModel (model.py:370-417): only the excitations mapped -> one batched device call with a shared amplitude table
+    # (test/test_re/test_empirical_power_spectrum.py:39); every leaf mapped -> the in-order loop
+    xi_key = "cfxi"
+    rng = np.random.default_rng(3)
+    xis = torch.as_tensor(rng.standard_normal((3,) + tuple(c["shape"])))
+    vm = nb.VModel(cf, 3, in_axes=xi_key)
+    assert vm.domain[xi_key] == (3,) + tuple(c["shape"]) and vm.domain["cfzeromode"] == cf.domain["cfzeromode"]
+    out = vm({**pos, xi_key: xis})
+    for i in range(3):
+        assert rel_err(t2n(out[i]), t2n(cf({**pos, xi_key: xis[i]}))) < 1e-12
+    allmapped = nb.VModel(cf, 2, in_axes=0)
+    batch = {k: torch.stack([v, 0.5 * v]) for k, v in pos.items()}
+    out2 = allmapped(batch)
+    assert rel_err(t2n(out2[1]), t2n(cf({k: 0.5 * v for k, v in pos.items()}))) < 1e-12
+    p_init = vm.init(5)
+    assert tuple(p_init[xi_key].shape) == (3,) + tuple(c["shape"]) and tuple(p_init["cfzeromode"].shape) == tuple(cf.domain["cfzeromode"])
 
 
 def check_kind_and_scaling(rt, name="g2d_16x16", kind="amplitude", scaling=(3.0, 1.0)):
