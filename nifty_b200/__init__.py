@@ -21,5 +21,6 @@ from .tree_math import (Vector, get_map, lmap, mean, mean_and_std, norm, size, s
                         zeros_like)
 from .model import Initializer, LazyModel, Model, VModel, WrappedCall  # noqa: F401
 from .evidence_lower_bound import estimate_evidence_lower_bound  # noqa: F401
+from .outer import OuterCorrelatedField, OuterLikelihood  # noqa: F401
 from . import lanczos  # noqa: F401
 from .lanczos import lanczos_tridiag, stochastic_logdet_from_lanczos, stochastic_lq_logdet  # noqa: F401

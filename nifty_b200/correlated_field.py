@@ -6,7 +6,8 @@ behaviour for malformed priors.  ``finalize()`` returns a :class:`CorrelatedFiel
 JVP / VJP run in the sm_100a kernels of libniftyb200.so; nothing is evaluated in Python.
 
 Scope: one Fourier sub-grid (1-3 axes, power-of-two extents), non-parametric (``kind`` "amplitude" or "power")
-or Matern amplitude.  Multiple sub-grids and ``harmonic_type="spherical"`` raise ``NotImplementedError``
+or Matern amplitude on the fused device path; two non-parametric sub-grids give the host-composed outer-product model of
+``outer.py``.  More sub-grids and ``harmonic_type="spherical"`` raise ``NotImplementedError``
 ("next").
 """
 
@@ -120,12 +121,14 @@ class CorrelatedField(LazyModel):
     def target_grids(self):
         """``cf.target_grids`` (:919): the position-space grid with its harmonic partner (tables built by the plan with the
         reference's arithmetic, :134-176, 228-265)."""
-        pl = self.plan
-        hg = RegularFourierGrid(shape=tuple(pl.shape), power_distributor=pl.power_distributor, mode_multiplicity=pl.mode_multiplicity,
-                                mode_lengths=pl.mode_lengths, relative_log_mode_lengths=pl.relative_log_mode_lengths,
-                                log_volume=pl.log_volume)
-        return (RegularCartesianGrid(shape=tuple(pl.shape), total_volume=pl.total_volume, distances=tuple(pl.distances),
-                                     harmonic_grid=hg),)
+        return (_grid_record(self.plan),)
+
+
+def _grid_record(pl: Plan):
+    hg = RegularFourierGrid(shape=tuple(pl.shape), power_distributor=pl.power_distributor, mode_multiplicity=pl.mode_multiplicity,
+                            mode_lengths=pl.mode_lengths, relative_log_mode_lengths=pl.relative_log_mode_lengths,
+                            log_volume=pl.log_volume)
+    return RegularCartesianGrid(shape=tuple(pl.shape), total_volume=pl.total_volume, distances=tuple(pl.distances), harmonic_grid=hg)
 
 
 class CorrelatedFieldMaker:
@@ -159,8 +162,8 @@ class CorrelatedFieldMaker:
         kind = non_parametric_kind.lower()
         if kind not in ("amplitude", "power"):
             raise ValueError(f"invalid `non_parametric_kind` {non_parametric_kind!r}")
-        if self._fluct:
-            raise NotImplementedError("outer products of several sub-grids are not on the B200 hot path yet")
+        if self._fluct and self._comm is not None:
+            raise NotImplementedError("outer products of several sub-grids are not available on slab-decomposed fields")
         shape = (int(shape),) if np.ndim(shape) == 0 else tuple(int(s) for s in shape)
         flu = _as_prior(fluctuations, LogNormalPrior, "fluctuations", optional=True)
         slp = _as_prior(loglogavgslope, NormalPrior, "loglogavgslope")
@@ -180,7 +183,7 @@ class CorrelatedFieldMaker:
         if kind not in ("amplitude", "power"):
             raise ValueError(f"invalid `non_parametric_kind` {non_parametric_kind!r}")
         if self._fluct:
-            raise NotImplementedError("outer products of several sub-grids are not on the B200 hot path yet")
+            raise NotImplementedError("Matern amplitudes inside outer products of several sub-grids are not supported")
         shape = (int(shape),) if np.ndim(shape) == 0 else tuple(int(s) for s in shape)
         scl = _as_prior(scale, LogNormalPrior, "scale")
         ctf = _as_prior(cutoff, LogNormalPrior, "cutoff")
@@ -215,6 +218,11 @@ class CorrelatedFieldMaker:
             raise ValueError("set_amplitude_total_offset must be called before finalize")
         if not self._fluct:
             raise ValueError("add_fluctuations must be called before finalize")
+        if len(self._fluct) > 1:
+            # outer product of sub-grids (correlated_field.py:856-912): host-composed model around the joint device transform
+            from .outer import OuterCorrelatedField
+            return OuterCorrelatedField(self._prefix, self._offset_mean, self._azm, self._fluct, dtype=self._dtype,
+                                        convention=self._conv, runtime=self._rt)
         f = self._fluct[0]
         plan = Plan(f["shape"], f["distances"], dtype=self._dtype, hartley_convention=self._conv, runtime=self._rt,
                     comm=self._comm)

@@ -84,7 +84,14 @@ class Likelihood:
     """Data-space likelihood before ``amend``; see :class:`Gaussian`, :class:`Poissonian`."""
     kind = -1
 
-    def amend(self, signal, **kwargs) -> "LikelihoodWithModel":
+    def amend(self, signal, **kwargs):
+        from .outer import OuterCorrelatedField, OuterLikelihood
+        if isinstance(signal, OuterCorrelatedField):
+            return OuterLikelihood(self, signal, "identity")
+        if isinstance(signal, SignalModel) and isinstance(signal.cf, OuterCorrelatedField):
+            if signal.scaling is not None:
+                raise NotImplementedError("the `scaling` leaf is not supported on outer-product fields")
+            return OuterLikelihood(self, signal.cf, signal.nl_fn if signal.nl_fn is not None else signal.nonlinearity)
         if isinstance(signal, CorrelatedField):
             signal = SignalModel(signal, "identity")
         if not isinstance(signal, SignalModel):

@@ -170,5 +170,52 @@ def main():
         print("wrote", name, "L =", lay.size)
 
 
+# Outer products of two sub-grids (test/test_re/test_correlated_field.py:245-283: re == cl field values, both sub-grids with
+# non_parametric_kind="power" on the re side)
+OUTER_CASES = {
+    "o_8x16_x_4": dict(shapes=((8, 16), (4,)), distances=((0.2, 0.1), (0.5,)), offset_mean=0.3, offset_std=(0.2, 0.1), seed=21,
+                       fluct=(dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05)),
+                              dict(fluctuations=(0.3, 0.2), loglogavgslope=(-1.5, 0.2), flexibility=(0.8, 0.3), asperity=(0.2, 0.02)))),
+    "o_16_x_8x8": dict(shapes=((16,), (8, 8)), distances=((1.0,), (0.1, 0.1)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=42,
+                       fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
+                              dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
+}
+
+
+def main_outer():
+    ift = _import_nifty_cl()
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import CorrelatedFieldOracle, Layout
+    for name, c in OUTER_CASES.items():
+        cfm = ift.CorrelatedFieldMaker("cf")
+        cfm.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+        orc = CorrelatedFieldOracle("cf")
+        orc.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+        for i, (shp, dist, f) in enumerate(zip(c["shapes"], c["distances"], c["fluct"])):
+            cfm.add_fluctuations(ift.RGSpace(shp, dist), f["fluctuations"], f["flexibility"], f["asperity"], f["loglogavgslope"],
+                                 prefix=f"space{i}")
+            orc.add_fluctuations(shp, dist, prefix=f"space{i}", non_parametric_kind="power", **f)
+        cf = cfm.finalize(prior_info=0)
+        orc.finalize()
+        lay = Layout(orc.domain)
+        rng = np.random.default_rng(c["seed"])
+        pos, tan = lay.random(rng), lay.random(rng)
+        full = tuple(c["shapes"][0]) + tuple(c["shapes"][1])
+        cot = rng.standard_normal(full)
+        out = {"cot": cot}
+        for k in lay.keys:
+            out["pos/" + k] = pos[k]
+            out["tan/" + k] = tan[k]
+        npos, ntan = to_cl(ift, cf.domain, pos), to_cl(ift, cf.domain, tan)
+        lin = cf(ift.Linearization.make_var(npos))
+        out["field"] = lin.val.asnumpy()
+        out["field_jvp"] = lin.jac(ntan).asnumpy()
+        for k, v in from_cl(lin.jac.adjoint(ift.makeField(cf.target, cot))).items():
+            out["field_vjp/" + k] = v
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print("wrote", name, "L =", lay.size)
+
+
 if __name__ == "__main__":
     main()
+    main_outer()

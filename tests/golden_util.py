@@ -37,6 +37,25 @@ CASES = {
 }
 
 
+# outer products of two sub-grids (make_golden.py:OUTER_CASES; reference check test/test_re/test_correlated_field.py:245-283)
+OUTER_CASES = {
+    "o_8x16_x_4": dict(shapes=((8, 16), (4,)), distances=((0.2, 0.1), (0.5,)), offset_mean=0.3, offset_std=(0.2, 0.1), seed=21,
+                       fluct=(dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05)),
+                              dict(fluctuations=(0.3, 0.2), loglogavgslope=(-1.5, 0.2), flexibility=(0.8, 0.3), asperity=(0.2, 0.02)))),
+    "o_16_x_8x8": dict(shapes=((16,), (8, 8)), distances=((1.0,), (0.1, 0.1)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=42,
+                       fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
+                              dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
+}
+
+
+def build_outer(c, maker):
+    """Two `add_fluctuations` on a `CorrelatedFieldOracle("cf")` / `nb.CorrelatedFieldMaker("cf", ...)` (same call protocol)."""
+    maker.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
+    for i, (shp, dist, f) in enumerate(zip(c["shapes"], c["distances"], c["fluct"])):
+        maker.add_fluctuations(shp, dist, prefix=f"space{i}", non_parametric_kind="power", **f)
+    return maker.finalize()
+
+
 def load(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     out = {"pos": {}, "tan": {}, "field_vjp": {}, "grad": {}, "metric": {}}

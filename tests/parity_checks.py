@@ -445,3 +445,76 @@ def check_config_vs_oracle(rt, name, tol=1e-10):
     for k, v in errs.items():
         assert v < tol, (name, k, v)
     return errs, time.time() - t0
+
+
+def check_outer_product(rt, shapes=((8, 16), (4,)), distances=(0.2, 0.5), lh_kind="gauss", conv="non_canonical_hartley", seed=21,
+                        tol=1e-10):
+    """Correlated field on the outer product of two sub-grids (correlated_field.py:856-912; reference check
+    test/test_re/test_correlated_field.py:245-283) against the oracle: field, normalized amplitudes, and the operator-level
+    likelihood interface (energy, gradient, metric, sqrt-metrics, a CG solve on metric + 1)."""
+    kw1 = dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05))
+    kw2 = dict(fluctuations=(0.3, 0.2), loglogavgslope=(-1.5, 0.2), flexibility=(0.8, 0.3), asperity=None)
+    ocf = oracle.CorrelatedFieldOracle("cf", hartley_convention=conv)
+    ocf.set_amplitude_total_offset(0.3, (0.2, 0.1))
+    ocf.add_fluctuations(shapes[0], distances[0], prefix="space", non_parametric_kind="power", **kw1)
+    ocf.add_fluctuations(shapes[1], distances[1], prefix="freq", non_parametric_kind="amplitude", **kw2)
+    ocf.finalize()
+    cfm = nb.CorrelatedFieldMaker("cf", runtime=rt, hartley_convention=conv)
+    cfm.set_amplitude_total_offset(0.3, (0.2, 0.1))
+    cfm.add_fluctuations(shapes[0], distances[0], prefix="space", non_parametric_kind="power", **kw1)
+    cfm.add_fluctuations(shapes[1], distances[1], prefix="freq", non_parametric_kind="amplitude", **kw2)
+    cf = cfm.finalize()
+    assert isinstance(cf, nb.OuterCorrelatedField) and isinstance(cf, nb.LazyModel)
+    assert cf.domain == {k: tuple(v) for k, v in ocf.domain.items()} and tuple(cf.target) == tuple(shapes[0]) + tuple(shapes[1])
+    osig = oracle.SignalOracle(ocf, "exp")
+    lay = oracle.Layout(osig.domain)
+    rng = np.random.default_rng(seed)
+    pos, tan = lay.random(rng), lay.random(rng)
+    pos = {k: 0.5 * v for k, v in pos.items()}
+    tp = {k: torch.as_tensor(v) for k, v in pos.items()}
+    tt = {k: torch.as_tensor(v) for k, v in tan.items()}
+    assert rel_err(t2n(cf(tp)), ocf(pos)) < tol
+    for na, ona in zip(cf.normalized_amplitudes, ocf.normalized_amplitudes(pos)):
+        assert rel_err(t2n(na(tp)), ona) < 1e-12
+    assert len(cf.target_grids) == 2 and tuple(cf.target_grids[1].shape) == tuple(shapes[1])
+    full = tuple(shapes[0]) + tuple(shapes[1])
+    if lh_kind == "gauss":
+        data = osig(pos) + 0.3 * rng.standard_normal(full)
+        olh = oracle.GaussianOracle(data, 1.0 / 0.09, osig)
+        lh = nb.Gaussian(data, noise_cov_inv=1.0 / 0.09).amend(nb.SignalModel(cf, "exp"))
+    else:
+        data = rng.poisson(osig(pos)).astype(np.int64)
+        olh = oracle.PoissonianOracle(data, osig)
+        lh = nb.Poissonian(data).amend(nb.SignalModel(cf, "exp"))
+    assert isinstance(lh, nb.OuterLikelihood)
+    e, grad = lh.energy_and_gradient(tp)
+    oe, ograd = olh.energy_and_gradient(pos)
+    assert abs(e - oe) <= tol * abs(oe) and abs(lh.energy(tp) - oe) <= tol * abs(oe)
+    assert tree_err(grad, ograd) < tol
+    assert tree_err(lh.metric(tp, tt), olh.metric(pos, tan)) < tol
+    u = rng.standard_normal(full)
+    assert tree_err(lh.left_sqrt_metric(tp, u), olh.left_sqrt_metric(pos, u)) < tol
+    assert rel_err(t2n(lh.right_sqrt_metric(tp, tt)), olh.right_sqrt_metric(pos, tan)) < tol
+    j = lay.pack(lay.random(rng))
+    res = lh.cg_on_metric(tp, torch.as_tensor(j, device=rt.device), absdelta=1e-30, miniter=6, maxiter=6)
+    ores = oracle.cg(lambda v: lay.pack(olh.metric(pos, lay.unpack(v))) + v, j, absdelta=1e-30, miniter=6, maxiter=6)
+    assert res.nit == ores.nit == 6 and rel_err(t2n(res.x), ores.x) < 1e-6
+    with pytest.raises(NotImplementedError):
+        cfm3 = nb.CorrelatedFieldMaker("cf", runtime=rt)
+        cfm3.set_amplitude_total_offset(0.0, (0.1, 0.1))
+        for i in range(3):
+            cfm3.add_fluctuations((4,), 1.0, prefix=f"a{i}", **kw1)
+        cfm3.finalize()
+
+
+def check_outer_golden(rt, name):
+    """The outer-product model against the nifty.cl fixtures: field, and J t / J^T c through the likelihood-free autograd path."""
+    from golden_util import OUTER_CASES, build_outer
+    c, g = OUTER_CASES[name], load(name)
+    cf = build_outer(c, nb.CorrelatedFieldMaker("cf", runtime=rt))
+    pos = {k: torch.as_tensor(v) for k, v in g["pos"].items()}
+    assert rel_err(t2n(cf(pos)), g["field"]) < 1e-10
+    lh = nb.Gaussian(np.zeros(g["field"].shape), noise_cov_inv=1.0).amend(cf)          # identity signal: its sqrt-metrics are J, J^T
+    tan = {k: torch.as_tensor(v) for k, v in g["tan"].items()}
+    assert rel_err(t2n(lh.right_sqrt_metric(pos, tan)), g["field_jvp"]) < 1e-10
+    assert tree_err(lh.left_sqrt_metric(pos, g["cot"]), g["field_vjp"]) < 1e-10

@@ -158,3 +158,14 @@ def test_hartley_vs_torch_fft_large(rt):
                                                  ("square_plus", "gauss", (8, 8, 16))])
 def test_custom_pointwise_nonlinearity(rt, which, lh_kind, shape):
     pc.check_custom_nonlinearity(rt, shape, 0.1, lh_kind=lh_kind, which=which)
+
+
+@pytest.mark.parametrize("shapes,lh_kind,conv", [(((8, 16), (4,)), "gauss", "non_canonical_hartley"),
+                                                 (((16,), (8, 8)), "poisson", "canonical_hartley")])
+def test_outer_product_of_two_subgrids(rt, shapes, lh_kind, conv):
+    pc.check_outer_product(rt, shapes=shapes, lh_kind=lh_kind, conv=conv)
+
+
+@pytest.mark.parametrize("name", ["o_8x16_x_4", "o_16_x_8x8"])
+def test_outer_product_golden(rt, name):
+    pc.check_outer_golden(rt, name)

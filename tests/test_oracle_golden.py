@@ -4,7 +4,7 @@ reference (re == cl field values) and extends it to JVP, VJP, energy, gradient a
 import numpy as np
 import pytest
 
-from golden_util import CASES, build_oracle, build_oracle_lh, load, rel_err
+from golden_util import CASES, OUTER_CASES, build_oracle, build_oracle_lh, build_outer, load, rel_err
 
 TOL = 1e-11
 
@@ -38,3 +38,19 @@ def test_energy_grad_metric(name):
     scale = max(np.max(np.abs(v)) for v in g["metric"].values())
     for k in met:
         assert np.max(np.abs(met[k] - g["metric"][k])) < 1e-10 * scale, k
+
+
+@pytest.mark.parametrize("name", sorted(OUTER_CASES))
+def test_outer_product_field_jvp_vjp(name):
+    """Outer products of two sub-grids: the oracle against the unmodified nifty.cl (the reference's own re == cl check,
+    test/test_re/test_correlated_field.py:245-283, extended to the JVP and the VJP)."""
+    from oracle import CorrelatedFieldOracle
+    c, g = OUTER_CASES[name], load(name)
+    cf = build_outer(c, CorrelatedFieldOracle("cf"))
+    assert rel_err(cf(g["pos"]), g["field"]) < TOL
+    assert rel_err(cf.jvp(g["pos"], g["tan"]), g["field_jvp"]) < TOL
+    vjp = cf.vjp(g["pos"], g["cot"])
+    assert set(vjp) == set(g["field_vjp"])
+    scale = max(np.max(np.abs(v)) for v in g["field_vjp"].values())
+    for k in vjp:
+        assert np.max(np.abs(vjp[k] - g["field_vjp"][k])) < 1e-10 * scale, k
