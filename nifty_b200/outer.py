@@ -13,7 +13,7 @@ with the composite transform as a self-adjoint autograd function -- this is a HO
 the oracle, but not fused into the pass kernels the single-grid hot path uses and not roofline-grade (every operator application
 makes ~10 N-sized elementwise passes besides the transform).  It provides the model (``cf(p)``, ``domain``, ``init``,
 ``normalized_amplitudes``, ``target_grids``) and the operator-level likelihood interface (energy, gradient, metric,
-sqrt-metrics, a CG solve in the host loop); ``optimize_kl`` on such models is not wired up.
+sqrt-metrics, a CG solve and MGVI sample draws in the host loop); ``optimize_kl`` on such models is not wired up.
 """
 from __future__ import annotations
 
@@ -283,3 +283,28 @@ class OuterLikelihood:
             return lay.pack(self.metric(pos, lay.unpack(v)), self.dtype, self.rt.device) + v
 
         return _cg(mat, lay.pack(getattr(j, "tree", j), self.dtype, self.rt.device) if not isinstance(j, torch.Tensor) else j, **cg_kwargs)
+
+    def draw_linear_residual(self, pos, key, *, from_inverse: bool = True, cg_kwargs: Optional[dict] = None, _raise_nonposdef=False,
+                             _white=None):
+        """One MGVI residual sample at ``pos`` (evi.py:88-150): ``left_sqrt_metric(pos, N(0,1)) + N(0,1)`` as the right-hand side
+        and ``x0 = `` the prior draw of a CG on ``metric + 1`` (host loop).  Returns ``(residual tree, info)``; the mirrored
+        sample is its negative (evi.py:53-57)."""
+        from .conjugate_gradient import _cg
+        from .evi import random_normal, random_split
+        lay, dev = self.layout, self.rt.device
+        k_nll, k_prr = random_split(key, 2)
+        w_data, w_prior = (None, None) if _white is None else _white
+        white = random_normal(k_nll, self.cf.target_shape, self.dtype, dev) if w_data is None else torch.as_tensor(w_data, dtype=self.dtype, device=dev)
+        prr = random_normal(k_prr, (lay.size,), self.dtype, dev) if w_prior is None else \
+            lay.pack(getattr(w_prior, "tree", w_prior), self.dtype, dev) if not isinstance(w_prior, torch.Tensor) else w_prior.to(dev)
+        smpl = lay.pack(self.left_sqrt_metric(pos, white), self.dtype, dev) + prr
+        info = 0
+        if from_inverse:
+            def mat(v):
+                return lay.pack(self.metric(pos, lay.unpack(v)), self.dtype, dev) + v
+            res = _cg(mat, smpl, x0=prr.clone(), _raise_nonposdef=_raise_nonposdef, **(cg_kwargs or {}))
+            smpl, info = res.x, res.info
+            if info is not None and info < 0:
+                raise ValueError("conjugate gradient failed")
+        return lay.unpack(smpl), info
+

@@ -499,6 +499,15 @@ def check_outer_product(rt, shapes=((8, 16), (4,)), distances=(0.2, 0.5), lh_kin
     res = lh.cg_on_metric(tp, torch.as_tensor(j, device=rt.device), absdelta=1e-30, miniter=6, maxiter=6)
     ores = oracle.cg(lambda v: lay.pack(olh.metric(pos, lay.unpack(v))) + v, j, absdelta=1e-30, miniter=6, maxiter=6)
     assert res.nit == ores.nit == 6 and rel_err(t2n(res.x), ores.x) < 1e-6
+    # an MGVI sample draw on the outer-product model against the oracle, same white noise (evi.py:88-150)
+    wd, wp = rng.standard_normal(full), lay.random(rng)
+    cgkw = dict(absdelta=1e-30, miniter=8, maxiter=8)
+    ores_s, oinfo, _ = oracle.draw_linear_residual(olh, pos, wd, wp, cg_kwargs=cgkw)
+    smp, info = lh.draw_linear_residual(tp, 0, cg_kwargs=cgkw, _white=(wd, {k: torch.as_tensor(v) for k, v in wp.items()}))
+    assert info == oinfo and tree_err(smp, ores_s) < 1e-6
+    ms, _ = lh.draw_linear_residual(tp, 0, from_inverse=False, _white=(wd, {k: torch.as_tensor(v) for k, v in wp.items()}))
+    oms, _, _ = oracle.draw_linear_residual(olh, pos, wd, wp, from_inverse=False)
+    assert tree_err(ms, oms) < 1e-10
     with pytest.raises(NotImplementedError):
         cfm3 = nb.CorrelatedFieldMaker("cf", runtime=rt)
         cfm3.set_amplitude_total_offset(0.0, (0.1, 0.1))
