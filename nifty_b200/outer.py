@@ -13,7 +13,8 @@ with the composite transform as a self-adjoint autograd function -- this is a HO
 the oracle, but not fused into the pass kernels the single-grid hot path uses and not roofline-grade (every operator application
 makes ~10 N-sized elementwise passes besides the transform).  It provides the model (``cf(p)``, ``domain``, ``init``,
 ``normalized_amplitudes``, ``target_grids``) and the operator-level likelihood interface (energy, gradient, metric,
-sqrt-metrics, a CG solve and MGVI sample draws in the host loop); ``optimize_kl`` on such models is not wired up.
+sqrt-metrics, a CG solve and MGVI sample draws in the host loop, the sample-averaged KL and an MGVI driver ``mgvi``: linear
+samples + Newton-CG on the KL); geoVI updates and the ``optimize_kl`` state machine are not wired up for such models.
 """
 from __future__ import annotations
 
@@ -307,4 +308,57 @@ class OuterLikelihood:
             if info is not None and info < 0:
                 raise ValueError("conjugate gradient failed")
         return lay.unpack(smpl), info
+
+    # -- sample-averaged KL and MGVI iterations (optimize_kl.py:67-144, 391-444, 540-591), on flat vectors ------------------
+    def _flat(self, pos):
+        pos = getattr(pos, "tree", pos)
+        return pos.to(dtype=self.dtype, device=self.rt.device) if isinstance(pos, torch.Tensor) else self.layout.pack(pos, self.dtype, self.rt.device)
+
+    def kl_value_and_grad(self, pos, residuals):
+        """``_kl_vg``: mean over ``pos + residuals`` of value and gradient of the standard Hamiltonian ``lh(x) + <x, x> / 2``."""
+        p, lay = self._flat(pos), self.layout
+        pts = [p] if residuals is None or len(residuals) == 0 else [p + self._flat(r) for r in residuals]
+        val, grad = 0.0, torch.zeros_like(p)
+        for x in pts:
+            e, g = self.energy_and_gradient(lay.unpack(x))
+            val += e + 0.5 * float(torch.dot(x, x))
+            grad += lay.pack(g, self.dtype, self.rt.device) + x
+        return val / len(pts), grad / len(pts)
+
+    def kl_metric(self, pos, tangents, residuals):
+        """``_kl_met``: mean over the sample points of ``metric(x, t) + t``."""
+        p, t, lay = self._flat(pos), self._flat(tangents), self.layout
+        pts = [p] if residuals is None or len(residuals) == 0 else [p + self._flat(r) for r in residuals]
+        out = torch.zeros_like(p)
+        for x in pts:
+            out += lay.pack(self.metric(lay.unpack(x), lay.unpack(t)), self.dtype, self.rt.device) + t
+        return out / len(pts)
+
+    def mgvi(self, pos, *, key, n_total_iterations: int, n_samples: int, draw_linear_kwargs=None, kl_kwargs=None, _whites=None):
+        """MGVI (``optimize_kl(..., sample_mode="linear_resample")``, optimize_kl.py:672-729) on the host-composed operators:
+        per iteration ``n_samples`` residual draws (mirrored: ``[s, -s]`` interleaved, evi.py:53-57) and one Newton-CG
+        minimisation of the sample-averaged KL.  Returns ``(position tree, residuals [2 n_samples, L], list of
+        OptimizeResults)``."""
+        from .evi import random_split
+        from .optimize import _newton_cg
+        lay = self.layout
+        p = self._flat(pos).clone()
+        dkw = dict(draw_linear_kwargs or {})
+        mk = dict((kl_kwargs or {}).get("minimize_kwargs", {}))
+        states, res = [], None
+        for it in range(n_total_iterations):
+            key, sk = random_split(key, 2)
+            ks = random_split(sk, n_samples)
+            rows = []
+            for i, k in enumerate(ks):
+                w = None if _whites is None else _whites[it * n_samples + i]
+                r, _ = self.draw_linear_residual(lay.unpack(p), k, _white=w, **dkw)
+                r = lay.pack(r, self.dtype, self.rt.device)
+                rows += [r, -r]
+            res = torch.stack(rows)
+            opt = _newton_cg(None, x0=p, fun_and_grad=lambda x: self.kl_value_and_grad(x, res),
+                             hessp=lambda x, t: self.kl_metric(x, t, res), **mk)
+            p = opt.x
+            states.append(opt._replace(x=None, jac=None))
+        return lay.unpack(p), res, states
 

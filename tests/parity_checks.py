@@ -508,6 +508,23 @@ def check_outer_product(rt, shapes=((8, 16), (4,)), distances=(0.2, 0.5), lh_kin
     ms, _ = lh.draw_linear_residual(tp, 0, from_inverse=False, _white=(wd, {k: torch.as_tensor(v) for k, v in wp.items()}))
     oms, _, _ = oracle.draw_linear_residual(olh, pos, wd, wp, from_inverse=False)
     assert tree_err(ms, oms) < 1e-10
+    # sample-averaged KL (value, gradient, metric) and one MGVI iteration against the oracle on identical white noise
+    residuals = [ores_s, {k: -v for k, v in ores_s.items()}]
+    tres = [{k: torch.as_tensor(v) for k, v in r.items()} for r in residuals]
+    ov, og = oracle.kl_value_and_grad(olh, pos, residuals)
+    v, gr = lh.kl_value_and_grad(tp, tres)
+    assert abs(v - ov) <= 1e-10 * abs(ov) and rel_err(t2n(gr), lay.pack(og)) < 1e-9
+    om = oracle.kl_metric(olh, pos, tan, residuals)
+    assert rel_err(t2n(lh.kl_metric(tp, tt, tres)), lay.pack(om)) < 1e-9
+    mk = dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=6))
+    whites = [(wd, {k: torch.as_tensor(v) for k, v in wp.items()})]
+    newpos, res_rows, states = lh.mgvi(tp, key=3, n_total_iterations=1, n_samples=1, draw_linear_kwargs=dict(cg_kwargs=cgkw),
+                                       kl_kwargs=dict(minimize_kwargs=mk), _whites=whites)
+    opos, oopt = oracle.kl_minimize(olh, pos, residuals, minimize_kwargs=mk)
+    assert res_rows.shape[0] == 2 and states[0].nit == oopt.nit
+    assert tree_err(newpos, opos) < 1e-5
+    v1, _ = lh.kl_value_and_grad(newpos, res_rows)
+    assert v1 < v
     with pytest.raises(NotImplementedError):
         cfm3 = nb.CorrelatedFieldMaker("cf", runtime=rt)
         cfm3.set_amplitude_total_offset(0.0, (0.1, 0.1))
