@@ -89,6 +89,18 @@ int nb200_dist_phase(nb200_lin* lin_a, nb200_lin* lin_b, void* stream, int code,
 /* hartley(p, axes=all) (correlated_field.py:24-30): out = Re(fftn(in)) +/- Im(fftn(in)), unnormalised */
 int nb200_hartley(nb200_plan* plan, void* stream, const void* in, void* out);
 
+/* hartley(p) (correlated_field.py:24-30) on a grid whose extents are NOT powers of two -- the reference's own parity case (3, 3)
+ * (test/test_re/test_correlated_field.py:123-124) and its published 3618^2 ... 7126^2 benchmark sizes -- as a chirp convolution
+ * (Bluestein) through the power-of-two passes of `padded_plan`, whose extents must be >= 2 n - 1 along every axis.
+ *   n    : the logical extents (host, ndim of the padded plan entries)
+ *   tab  : device table of complex numbers (interleaved re, im, the plan's dtype): for each of the three right-aligned axes (missing
+ *          leading axes count one entry equal to 1) conj(c_j) = exp(-i pi j^2 / n), j < n; then for each axis the M-point DFT of the
+ *          even chirp filter g_m = c_|m| (|m| < n, zero elsewhere), the last axis scaled by 1 / prod(M)
+ *   in   : n-grid, out: n-grid, work: 2 prod(M) elements of scratch
+ * Sequence on the stream: pad + chirp, 2 in-place hartley, spectrum product on mirror pairs, 2 in-place hartley, crop + chirp. */
+int nb200_hartley_chirpz(nb200_plan* padded_plan, void* stream, const int64_t* n, const void* tab, const void* in, void* work,
+                         void* out);
+
 /* correlated_field(p) core (correlated_field.py:909-912, :882-887) as a bilinear operator:
  *   out = offset + (1/V) hartley(amp[power_distributor] * xi)
  * `amp` is the K-entry table azm * normalized_amplitude with amp[0] = zeromode * V. */

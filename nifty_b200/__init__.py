@@ -22,5 +22,6 @@ from .tree_math import (Vector, get_map, lmap, mean, mean_and_std, norm, size, s
 from .model import Initializer, LazyModel, Model, VModel, WrappedCall  # noqa: F401
 from .evidence_lower_bound import estimate_evidence_lower_bound  # noqa: F401
 from .outer import OuterCorrelatedField, OuterLikelihood  # noqa: F401
+from .bluestein import BluesteinCorrelatedField, BluesteinHartley, fourier_mode_tables  # noqa: F401
 from . import lanczos  # noqa: F401
 from .lanczos import lanczos_tridiag, stochastic_logdet_from_lanczos, stochastic_lq_logdet  # noqa: F401

@@ -75,6 +75,7 @@ SIGNATURES = {
     "nb200_plan_set_reduce_chunks": (C.c_int, [vp, C.c_int]),
     "nb200_dist_phase": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]),
     "nb200_hartley": (C.c_int, [vp, vp, vp, vp]),
+    "nb200_hartley_chirpz": (C.c_int, [vp, vp, C.POINTER(i64), vp, vp, vp, vp]),
     "nb200_cf_apply": (C.c_int, [vp, vp, vp, vp, f64, vp]),
     "nb200_cf_apply_adjoint": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "nb200_cf_apply_batch": (C.c_int, [vp, vp, vp, i64, vp, f64, vp, i64]),

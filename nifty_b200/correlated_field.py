@@ -224,6 +224,13 @@ class CorrelatedFieldMaker:
             return OuterCorrelatedField(self._prefix, self._offset_mean, self._azm, self._fluct, dtype=self._dtype,
                                         convention=self._conv, runtime=self._rt)
         f = self._fluct[0]
+        if any(n < 2 or (n & (n - 1)) for n in f["shape"]):
+            # extents that are not powers of two: host-composed model around power-of-two device transforms (Bluestein)
+            if self._comm is not None:
+                raise NotImplementedError("slab-decomposed fields need power-of-two extents")
+            from .bluestein import BluesteinCorrelatedField
+            return BluesteinCorrelatedField(self._prefix, self._offset_mean, self._azm, f, dtype=self._dtype, convention=self._conv,
+                                            runtime=self._rt)
         plan = Plan(f["shape"], f["distances"], dtype=self._dtype, hartley_convention=self._conv, runtime=self._rt,
                     comm=self._comm)
         sp = self._prefix + f["prefix"]

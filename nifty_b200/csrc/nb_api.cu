@@ -3,6 +3,7 @@
 // kernel bodies) to check host logic and index arithmetic where no GPU is available.
 #include "nb_model.cuh"
 #include "nb_vec.cuh"
+#include "nb_bluestein.cuh"
 #include <limits>
 #include <memory>
 
@@ -372,6 +373,37 @@ int nb200_dist_phase(nb200_lin* lin_a, nb200_lin* lin_b, void* stream, int code,
 int nb200_hartley(nb200_plan* plan, void* stream, const void* in, void* out) {
   NB_TRY
   NB_DISPATCH(plan->impl->dtype, TT, { static_cast<Plan<TT>*>(plan->impl)->hartley((stream_t)stream, (const TT*)in, (TT*)out); })
+  return 0;
+  NB_CATCH
+}
+int nb200_hartley_chirpz(nb200_plan* padded_plan, void* stream, const int64_t* n, const void* tab, const void* in, void* work, void* out) {
+  NB_TRY
+  if (!padded_plan || !n || !tab || !in || !work || !out) return fail("nb200_hartley_chirpz: null argument");
+  NB_DISPATCH(padded_plan->impl->dtype, TT, {
+    Plan<TT>& P = *static_cast<Plan<TT>*>(padded_plan->impl);
+    if (P.dist) return fail("nb200_hartley_chirpz: not available on slab-decomposed plans");
+    stream_t st = (stream_t)stream;
+    ChirpParams<TT> p; std::memset(&p, 0, sizeof(p));
+    const int nd = P.g.ndim, lead = 3 - nd;
+    p.ntot = 1; p.mtot = 1;
+    for (int a = 0; a < 3; ++a) {
+      p.n[a] = a < lead ? 1 : n[a - lead];
+      p.m[a] = a < lead ? 1 : P.g.shape[a - lead];
+      if (p.n[a] < 1 || (p.n[a] > 1 && p.m[a] < 2 * p.n[a] - 1)) return fail("nb200_hartley_chirpz: the padded extent must be >= 2 n - 1 along every axis");
+      p.lg_m[a] = ilog2(p.m[a]);
+      p.ntot *= p.n[a]; p.mtot *= p.m[a];
+    }
+    const cplx<TT>* t = (const cplx<TT>*)tab;
+    for (int a = 0; a < 3; ++a) { p.cc[a] = t; t += p.n[a]; }
+    for (int a = 0; a < 3; ++a) { p.G[a] = t; t += p.m[a]; }
+    p.x = (const TT*)in; p.w = (TT*)work; p.out = (TT*)out; p.s = P.hsign;
+    auto grid = [](long cnt) { return (int)std::min<long>((cnt + 1023) / 1024 + 1, 148 * 8); };
+    launch<ChirpPadBody<TT>>(grid(p.mtot), 256, 0, st, p);
+    P.hartley(st, p.w, p.w); P.hartley(st, p.w + p.mtot, p.w + p.mtot);
+    launch<ChirpFilterBody<TT>>(grid(p.mtot / 2), 256, 0, st, p);
+    P.hartley(st, p.w, p.w); P.hartley(st, p.w + p.mtot, p.w + p.mtot);
+    launch<ChirpCropBody<TT>>(grid(p.ntot), 256, 0, st, p);
+  })
   return 0;
   NB_CATCH
 }

@@ -85,12 +85,14 @@ class Likelihood:
     kind = -1
 
     def amend(self, signal, **kwargs):
+        from .bluestein import BluesteinCorrelatedField
         from .outer import OuterCorrelatedField, OuterLikelihood
-        if isinstance(signal, OuterCorrelatedField):
+        composed = (OuterCorrelatedField, BluesteinCorrelatedField)      # host-composed models (outer.py, bluestein.py)
+        if isinstance(signal, composed):
             return OuterLikelihood(self, signal, "identity")
-        if isinstance(signal, SignalModel) and isinstance(signal.cf, OuterCorrelatedField):
+        if isinstance(signal, SignalModel) and isinstance(signal.cf, composed):
             if signal.scaling is not None:
-                raise NotImplementedError("the `scaling` leaf is not supported on outer-product fields")
+                raise NotImplementedError("the `scaling` leaf is not supported on host-composed fields")
             return OuterLikelihood(self, signal.cf, signal.nl_fn if signal.nl_fn is not None else signal.nonlinearity)
         if isinstance(signal, CorrelatedField):
             signal = SignalModel(signal, "identity")

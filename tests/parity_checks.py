@@ -544,3 +544,106 @@ def check_outer_golden(rt, name):
     tan = {k: torch.as_tensor(v) for k, v in g["tan"].items()}
     assert rel_err(t2n(lh.right_sqrt_metric(pos, tan)), g["field_jvp"]) < 1e-10
     assert tree_err(lh.left_sqrt_metric(pos, g["cot"]), g["field_vjp"]) < 1e-10
+
+
+def check_nonpow2_hartley(rt, shape, dtype=torch.float64):
+    """Hartley transform on extents that are not powers of two (chirp convolution around the power-of-two device transform,
+    nifty_b200/bluestein.py) against ``oracle.hartley`` (correlated_field.py:24-30), both sign conventions, and H H = N."""
+    rng = np.random.default_rng(int(np.prod(shape)))
+    x = rng.standard_normal(shape)
+    for conv in ("non_canonical_hartley", "canonical_hartley"):
+        H = nb.BluesteinHartley(shape, dtype=dtype, convention=conv, runtime=rt)
+        got = H(torch.as_tensor(x, dtype=dtype, device=rt.device))
+        assert got.dtype == dtype and tuple(got.shape) == tuple(shape)
+        assert rel_err(t2n(got), oracle.hartley(x, convention=conv)) < 100 * TOL[dtype]
+        assert rel_err(t2n(H(got)) / np.prod(shape), x) < 100 * TOL[dtype]
+
+
+def check_nonpow2_golden(rt, name="g2d_3x3"):
+    """The reference's own (3, 3) parity case (test/test_re/test_correlated_field.py:123-124) on the device path: every quantity of
+    the nifty.cl fixture, sqrt-metrics against the oracle."""
+    c, g = CASES[name], load(name)
+    tol = 1e-10
+    lh = build_product_lh(c, g, rt)
+    assert isinstance(lh.cf, nb.BluesteinCorrelatedField)
+    pos = {k: torch.as_tensor(v) for k, v in g["pos"].items()}
+    tan = {k: torch.as_tensor(v) for k, v in g["tan"].items()}
+    assert lh.cf.domain == {k: tuple(np.shape(v)) for k, v in g["pos"].items()}
+    assert rel_err(t2n(lh.cf(pos)), g["field"]) < tol
+    assert rel_err(t2n(lh.signal_response(pos)), g["signal"]) < tol
+    e, grad = lh.energy_and_gradient(pos)
+    assert abs(e - float(g["energy"])) <= tol * abs(float(g["energy"]))
+    assert tree_err(grad, g["grad"]) < tol
+    assert tree_err(lh.metric(pos, tan), g["metric"]) < tol
+    olh = build_oracle_lh(c, g)
+    assert rel_err(t2n(lh.right_sqrt_metric(pos, tan)), olh.right_sqrt_metric(g["pos"], g["tan"])) < tol
+    assert tree_err(lh.left_sqrt_metric(pos, g["cot"]), olh.left_sqrt_metric(g["pos"], g["cot"])) < tol
+    bare = nb.Gaussian(np.zeros(c["shape"]), noise_cov_inv=1.0).amend(lh.cf)            # identity signal: its sqrt-metrics are J, J^T
+    assert rel_err(t2n(bare.right_sqrt_metric(pos, tan)), g["field_jvp"]) < tol
+    assert tree_err(bare.left_sqrt_metric(pos, g["cot"]), g["field_vjp"]) < tol
+
+
+def check_nonpow2_model(rt, shape=(6, 10), distances=(0.2, 0.3), lh_kind="gauss", conv="non_canonical_hartley", seed=5, tol=1e-10):
+    """A correlated field on a grid with non-power-of-two extents against the oracle: mode tables, field, amplitudes, the
+    operator-level likelihood interface, one MGVI sample draw and one MGVI iteration on identical white noise."""
+    kw = dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05))
+    ocf = oracle.CorrelatedFieldOracle("cf", hartley_convention=conv)
+    ocf.set_amplitude_total_offset(0.3, (0.2, 0.1))
+    ocf.add_fluctuations(shape, distances, prefix="ax1", non_parametric_kind="power", **kw)
+    ocf.finalize()
+    cfm = nb.CorrelatedFieldMaker("cf", runtime=rt, hartley_convention=conv)
+    cfm.set_amplitude_total_offset(0.3, (0.2, 0.1))
+    cfm.add_fluctuations(shape, distances, prefix="ax1", non_parametric_kind="power", **kw)
+    cf = cfm.finalize()
+    assert isinstance(cf, nb.BluesteinCorrelatedField) and isinstance(cf, nb.LazyModel)
+    assert cf.domain == {k: tuple(v) for k, v in ocf.domain.items()} and tuple(cf.target) == tuple(shape)
+    idx, um, cnt = oracle.fourier_mode_distributor(shape, distances)
+    hg = cf.target_grids[0].harmonic_grid
+    assert np.array_equal(hg.power_distributor, idx) and np.array_equal(hg.mode_lengths, um) and np.array_equal(hg.mode_multiplicity, cnt)
+    osig = oracle.SignalOracle(ocf, "exp")
+    lay = oracle.Layout(osig.domain)
+    rng = np.random.default_rng(seed)
+    pos, tan = lay.random(rng), lay.random(rng)
+    pos = {k: 0.5 * v for k, v in pos.items()}
+    tp = {k: torch.as_tensor(v) for k, v in pos.items()}
+    tt = {k: torch.as_tensor(v) for k, v in tan.items()}
+    assert rel_err(t2n(cf(tp)), ocf(pos)) < tol
+    assert rel_err(t2n(cf.normalized_amplitudes[0](tp)), ocf.normalized_amplitudes(pos)[0]) < 1e-12
+    if lh_kind == "gauss":
+        data = osig(pos) + 0.3 * rng.standard_normal(shape)
+        olh = oracle.GaussianOracle(data, 1.0 / 0.09, osig)
+        lh = nb.Gaussian(data, noise_cov_inv=1.0 / 0.09).amend(nb.SignalModel(cf, "exp"))
+    else:
+        data = rng.poisson(osig(pos)).astype(np.int64)
+        olh = oracle.PoissonianOracle(data, osig)
+        lh = nb.Poissonian(data).amend(nb.SignalModel(cf, "exp"))
+    e, grad = lh.energy_and_gradient(tp)
+    oe, ograd = olh.energy_and_gradient(pos)
+    assert abs(e - oe) <= tol * abs(oe)
+    assert tree_err(grad, ograd) < tol
+    assert tree_err(lh.metric(tp, tt), olh.metric(pos, tan)) < tol
+    wd, wp = rng.standard_normal(shape), lay.random(rng)
+    cgkw = dict(absdelta=1e-30, miniter=8, maxiter=8)
+    white = (wd, {k: torch.as_tensor(v) for k, v in wp.items()})
+    ores_s, oinfo, _ = oracle.draw_linear_residual(olh, pos, wd, wp, cg_kwargs=cgkw)
+    smp, info = lh.draw_linear_residual(tp, 0, cg_kwargs=cgkw, _white=white)
+    assert info == oinfo and tree_err(smp, ores_s) < 1e-6
+    residuals = [ores_s, {k: -v for k, v in ores_s.items()}]
+    mk = dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=6))
+    newpos, res_rows, states = lh.mgvi(tp, key=3, n_total_iterations=1, n_samples=1, draw_linear_kwargs=dict(cg_kwargs=cgkw),
+                                       kl_kwargs=dict(minimize_kwargs=mk), _whites=[white])
+    opos, oopt = oracle.kl_minimize(olh, pos, residuals, minimize_kwargs=mk)
+    assert states[0].nit == oopt.nit and tree_err(newpos, opos) < 1e-5
+
+
+def check_nonpow2_errors(rt):
+    """`nb200_hartley_chirpz` refuses a padded plan that is too short for the cyclic convolution; shapes are checked."""
+    import ctypes
+    H = nb.BluesteinHartley((5, 6), runtime=rt)
+    with pytest.raises(ValueError):
+        H(torch.zeros((6, 5), dtype=torch.float64))
+    small = nb.Plan((8, 8), 1.0, runtime=rt)                     # needs >= 9 and >= 11
+    x = torch.zeros((5, 6), dtype=torch.float64, device=rt.device)
+    with pytest.raises(nb.NB200Error):
+        rt.api.call("nb200_hartley_chirpz", small._h, rt.stream(), (ctypes.c_int64 * 2)(5, 6), rt.ptr(H._tab), rt.ptr(x),
+                    rt.ptr(torch.zeros(128, dtype=torch.float64, device=rt.device)), rt.ptr(torch.empty_like(x)))

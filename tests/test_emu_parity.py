@@ -163,3 +163,23 @@ def test_outer_product_of_two_subgrids(rt, shapes, lh_kind, conv):
 @pytest.mark.parametrize("name", ["o_8x16_x_4", "o_16_x_8x8"])
 def test_outer_product_golden(rt, name):
     pc.check_outer_golden(rt, name)
+
+
+@pytest.mark.parametrize("shape", [(3,), (6,), (3, 3), (6, 7), (5, 12), (3, 5, 7), (100, 37), (1, 5)])
+def test_nonpow2_hartley(rt, shape):
+    pc.check_nonpow2_hartley(rt, shape)
+
+
+def test_nonpow2_hartley_float32_and_errors(rt):
+    pc.check_nonpow2_hartley(rt, (12, 7), dtype=torch.float32)
+    pc.check_nonpow2_errors(rt)
+
+
+def test_nonpow2_golden_3x3(rt):
+    pc.check_nonpow2_golden(rt)
+
+
+@pytest.mark.parametrize("shape,dist,lh_kind,conv", [((6, 10), (0.2, 0.3), "gauss", "non_canonical_hartley"),
+                                                     ((5, 3, 6), 0.4, "poisson", "canonical_hartley"), ((12,), 0.4, "gauss", "non_canonical_hartley")])
+def test_nonpow2_model(rt, shape, dist, lh_kind, conv):
+    pc.check_nonpow2_model(rt, shape, dist, lh_kind, conv)
