@@ -113,7 +113,7 @@ class BluesteinCorrelatedField(LazyModel):
         self._azm = _Prior(azm_prior)
         self.shape = tuple(int(s) for s in f["shape"])
         self._ht = BluesteinHartley(self.shape, dtype=dtype, convention=convention, runtime=runtime)
-        self.rt = self._ht.rt
+        self.rt, self.plan = self._ht.rt, self._ht.plan          # `plan`: the PADDED power-of-two plan behind the transform
         dev = self.rt.device
         tb = fourier_mode_tables(self.shape, f["distances"])
         self._grid = tb
@@ -138,6 +138,8 @@ class BluesteinCorrelatedField(LazyModel):
         t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), dtype=dtype, device=dev)      # noqa: E731
         self._tabs = dict(ell=t(tb["relative_log_mode_lengths"]), mult=t(tb["mode_multiplicity"]), dt=t(tb["log_volume"]),
                           V=tb["total_volume"], pd=torch.as_tensor(tb["power_distributor"].astype(np.int64), device=dev))
+        self._vol = tb["total_volume"]
+        self._factors = [(self._tabs["pd"], tuple(range(len(self.shape))))]              # one (bin table, axes) pair (outer._FieldLin)
         field = self
 
         class Transform(torch.autograd.Function):
@@ -164,6 +166,13 @@ class BluesteinCorrelatedField(LazyModel):
             return self.layout.unpack(pos)
         return {k: torch.as_tensor(v, dtype=self.dtype, device=self.rt.device) if not isinstance(v, torch.Tensor) else v.to(self.rt.device)
                 for k, v in pos.items()}
+
+    def _raw_transform(self, x):
+        return self._ht(x)
+
+    def _factor_tables(self, small):
+        z, na = self._normalized(small)
+        return (z * na,)
 
     def _normalized(self, p):
         z = self._azm(p[self.prefix + "zeromode"])

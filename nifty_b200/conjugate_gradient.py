@@ -57,6 +57,11 @@ class HamiltonianMetric:
     def distributed(self):
         return bool(self.lin.model.plan.dist)
 
+    @property
+    def host_composed(self):
+        """Linearisation of a host-composed model (outer.HostLin): the operator is applied by the host, CG runs the host loop."""
+        return bool(getattr(self.lin, "host_composed", False))
+
     def __call__(self, t: torch.Tensor) -> torch.Tensor:
         if self.other is None:
             return self._clear(self.lin.metric(t, add_identity=True))
@@ -76,7 +81,23 @@ class SampleAveragedMetric:
         self.frozen = list(frozen) if frozen else None
         self.scale = 0.0 if scale_zero else 1.0 / self.n_total
 
+    @property
+    def host_composed(self):
+        return bool(self.lins) and bool(getattr(self.lins[0], "host_composed", False))
+
     def __call__(self, t: torch.Tensor) -> torch.Tensor:
+        if self.host_composed:
+            out = t.clone() if self.identity_here else torch.zeros_like(t)
+            for lin in self.lins:
+                out += self.scale * lin.metric(t)
+            if self.reduce_fn is not None:
+                work = self.reduce_fn(out)
+                if work is not None:
+                    work.wait()
+            if self.frozen:
+                for lo, hi in self.frozen:
+                    out[lo:hi] = 0
+            return out
         from ._runtime import metric_multi
         out = metric_multi(self.lins, t, scale=self.scale, identity_here=self.identity_here, reduce_fn=self.reduce_fn)
         if self.frozen:
@@ -102,6 +123,8 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
     norm_ord = 2 if norm_ord is None else norm_ord
     vdot = (lambda a, b: float(torch.dot(a, b))) if vdot is None else vdot
     vnorm = _norm if vnorm is None else vnorm
+    if isinstance(mat, (SampleAveragedMetric, HamiltonianMetric)) and mat.host_composed:
+        mat = mat.__call__                       # host-composed operators: the generic loop below
     if isinstance(mat, HamiltonianMetric) and mat.distributed:
         # slab-decomposed field: the recurrence of the loop below with in-place vector updates and ONE all-reduce + host
         # synchronisation per group of reductions

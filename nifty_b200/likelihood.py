@@ -37,7 +37,7 @@ class SignalModel(LazyModel):
         self.nl_fn = None
         if callable(nonlinearity):
             self.nl_fn, nonlinearity = nonlinearity, "tabulated"
-            if cf.plan.dist:
+            if getattr(cf.plan, "dist", False):
                 raise NotImplementedError("custom non-linearities are not available on slab-decomposed fields")
         elif nonlinearity not in ("exp", "identity"):
             raise ValueError(f"unsupported nonlinearity {nonlinearity!r}")

@@ -8,13 +8,17 @@ the composite ``H_2 H_1`` is obtained from the joint transform ``J`` by the refl
     H_2 H_1 x = 1/2 ( J x + (J x) o f_1 + (J x) o f_2 - (J x) o f_1 o f_2 ),      f_i : k -> -k along the axes of sub-grid i
 
 (both Hartley conventions; linear and self-adjoint like its factors).  The O(K_i) amplitude spectra, the outer product, the
-reflections and the pointwise likelihood are torch operations on the same device, and derivatives come from torch autograd
-with the composite transform as a self-adjoint autograd function -- this is a HOST-COMPOSED path: correct and checked against
-the oracle, but not fused into the pass kernels the single-grid hot path uses and not roofline-grade (every operator application
-makes ~10 N-sized elementwise passes besides the transform).  It provides the model (``cf(p)``, ``domain``, ``init``,
-``normalized_amplitudes``, ``target_grids``) and the operator-level likelihood interface (energy, gradient, metric,
-sqrt-metrics, a CG solve and MGVI sample draws in the host loop, the sample-averaged KL and an MGVI driver ``mgvi``: linear
-samples + Newton-CG on the KL); geoVI updates and the ``optimize_kl`` state machine are not wired up for such models.
+reflections and the pointwise likelihood are torch operations on the same device -- a HOST-COMPOSED path: correct and checked
+against the oracle, but not fused into the pass kernels the single-grid hot path uses and not roofline-grade.
+
+Linearisations are explicit (:class:`_FieldLin`): one forward evaluation per position, then ``J t`` and ``J^T c`` cost ONE device
+transform each plus a handful of N-sized elementwise passes; the O(K) amplitude chains are differentiated with ``torch.func``.
+:class:`HostLin` gives such a linearisation the flat-vector interface of the device ``Lin`` and :class:`OuterLikelihood` is a
+``LikelihoodWithModel``, so ``draw_linear_residual``, ``nonlinearly_update_residual`` (geoVI), ``optimize_kl`` (state machine,
+point estimates, checkpoints), ``wiener_filter_posterior`` and the minisanity message run unchanged on such models; their CG
+solves use the host loop (``conjugate_gradient._cg``).  The model itself (``cf(p)``) stays differentiable through torch
+autograd with the composite transform as a self-adjoint autograd function.  The non-power-of-two fields of ``bluestein.py``
+share all of this.
 """
 from __future__ import annotations
 
@@ -24,6 +28,7 @@ import numpy as np
 import torch
 
 from ._runtime import Plan
+from .likelihood import LikelihoodWithModel
 from .model import LazyModel
 from .tree import Layout
 
@@ -67,6 +72,110 @@ class _Prior:
     def __call__(self, xi):
         v = self.a + self.b * torch.as_tensor(xi).reshape(())
         return torch.exp(v) if self.log else v
+
+
+class _FieldLin:
+    """The field of a host-composed model linearised at one position: ``J t`` and ``J^T c`` with ONE device transform each
+    (what ``jax.linearize`` / ``jax.linear_transpose`` hand the reference, likelihood.py:613-621).  The field is
+    ``offset + T(prod_i B_i[pd_i] * xi) / V`` with O(K_i) factor tables ``B_i`` of the non-xi leaves (``cf._factor_tables``):
+    their derivatives are O(K) torch.func calls, the N-sized part is written out -- tangent ``T(ea dxi + d(ea) xi) / V``,
+    cotangent ``g = T(c) / V``, ``xi_bar = ea g``, ``B_i_bar = `` segment sum over the bins of ``xi g prod_{j != i} B_j[pd_j]``."""
+
+    def __init__(self, cf, p):
+        self.cf, self.xi_key = cf, cf.prefix + "xi"
+        self.keys = sorted(k for k in p if k != self.xi_key)
+        self.vals = tuple(p[k].detach() for k in self.keys)
+        self.xi = p[self.xi_key].detach()
+        self._fn = lambda *v: tuple(cf._factor_tables(dict(zip(self.keys, v))))
+        self.tabs, self._tab_vjp = torch.func.vjp(self._fn, *self.vals)
+        self.exp = [self._expand(i, t) for i, t in enumerate(self.tabs)]
+        self.ea = self._prod(self.exp)
+        self.field = cf.offset_mean + cf._raw_transform(self.ea * self.xi) / cf._vol
+
+    def _expand(self, i, table):
+        pd, axes = self.cf._factors[i]
+        shp = [1] * len(self.cf.target_shape)
+        for ax in axes:
+            shp[ax] = self.cf.target_shape[ax]
+        return table[pd].reshape(shp)
+
+    @staticmethod
+    def _prod(ts):
+        out = ts[0]
+        for t in ts[1:]:
+            out = out * t
+        return out
+
+    def jvp(self, t):
+        _, dts = torch.func.jvp(self._fn, self.vals, tuple(t[k].to(v.dtype).reshape(v.shape) for k, v in zip(self.keys, self.vals)))
+        dea = None
+        for i, dt in enumerate(dts):
+            term = self._prod([self._expand(i, dt)] + [e for j, e in enumerate(self.exp) if j != i])
+            dea = term if dea is None else dea + term
+        return self.cf._raw_transform(self.ea * t[self.xi_key] + dea * self.xi) / self.cf._vol
+
+    def vjp(self, c):
+        g = self.cf._raw_transform(c) / self.cf._vol
+        w = self.xi * g
+        bars = []
+        for i, tab in enumerate(self.tabs):
+            pd, axes = self.cf._factors[i]
+            wi = self._prod([w] + [e for j, e in enumerate(self.exp) if j != i])
+            other = tuple(ax for ax in range(w.ndim) if ax not in axes)
+            if other:
+                wi = wi.sum(dim=other)
+            bars.append(torch.zeros_like(tab).index_add_(0, pd.reshape(-1), wi.reshape(-1)))
+        out = dict(zip(self.keys, self._tab_vjp(tuple(bars))))
+        out[self.xi_key] = self.ea * g
+        return out
+
+
+class _HostLin:
+    """``signal = nl(field)`` under a likelihood, linearised at one position: metric and sqrt-metrics on trees."""
+
+    def __init__(self, lh, pos):
+        self.lh = lh
+        self.fl = _FieldLin(lh.cf, lh.cf._tree(pos))
+        f = self.fl.field
+        if lh.nl_name == "exp":
+            self.s = torch.exp(f)
+            self.d = self.s
+        elif lh.nl_name == "identity":
+            self.s, self.d = f, None
+        else:                                                  # pointwise callable: derivative from autograd of the sum
+            with torch.enable_grad():
+                fr = f.detach().requires_grad_(True)
+                sr = lh.nl(fr)
+                if sr.shape != fr.shape:
+                    raise ValueError("the non-linearity must be a pointwise map of the correlated field (same shape in and out)")
+                (self.d,) = torch.autograd.grad(sr.sum(), fr)
+            self.s = sr.detach()
+        self.mw = lh._lh_metric_weight(self.s)
+
+    def _t(self, tan):
+        lh = self.lh
+        return {k: torch.as_tensor(v, dtype=lh.dtype, device=lh.rt.device) for k, v in getattr(tan, "tree", tan).items()}
+
+    def jvp(self, tan):
+        jt = self.fl.jvp(self._t(tan))
+        return jt if self.d is None else self.d * jt
+
+    def vjp(self, c):
+        return self.fl.vjp(c if self.d is None else self.d * c)
+
+    def metric(self, tan):
+        return self.vjp(self.mw * self.jvp(tan))
+
+    def metric_flat(self, v):
+        lay, lh = self.lh.layout, self.lh
+        return lay.pack(self.metric(lay.unpack(v)), lh.dtype, lh.rt.device)
+
+    def right_sqrt_metric(self, tan):
+        return torch.sqrt(self.mw) * self.jvp(tan)
+
+    def left_sqrt_metric(self, u):
+        u = torch.as_tensor(u, dtype=self.lh.dtype, device=self.lh.rt.device)
+        return self.vjp(torch.sqrt(self.mw) * u)
 
 
 class OuterCorrelatedField(LazyModel):
@@ -120,6 +229,7 @@ class OuterCorrelatedField(LazyModel):
         self.layout = Layout(self.domain)
         self.target_shape = shape
         self._vol = float(np.prod([tb["V"] for tb in self._tabs]))
+        self._factors = [(tb["pd"], axes) for tb, axes in zip(self._tabs, self._axes)]     # (bin table, axes) per sub-grid (_FieldLin)
         outer = self
 
         class SepHartley(torch.autograd.Function):
@@ -145,6 +255,14 @@ class OuterCorrelatedField(LazyModel):
             return torch.roll(torch.flip(t, dims=axes), shifts=[1] * len(axes), dims=axes)
 
         return 0.5 * (J + refl(J, a1) + refl(J, a2) - refl(J, a1 + a2))
+
+    def _raw_transform(self, x):
+        return self._sep_hartley(x)
+
+    def _factor_tables(self, small):
+        """O(K_i) tables whose expanded product is the amplitude of every mode: ``z na_1`` and ``na_2``."""
+        z, nas = self._normalized(small)
+        return (z * nas[0],) + tuple(nas[1:])
 
     # -- model surface -----------------------------------------------------------------------------------------------
     @property
@@ -193,27 +311,124 @@ class OuterCorrelatedField(LazyModel):
         return self.offset_mean + self._sep.apply(h) / self._vol
 
 
-class OuterLikelihood:
-    """Operator-level likelihood interface (``likelihood.py:599-633``) of ``Gaussian`` / ``Poissonian`` data on
-    ``signal = exp(cf)`` (or ``cf`` itself) for an :class:`OuterCorrelatedField`: energy, gradient, metric, sqrt-metrics, all
-    through torch autograd around the device transform.  Trees in, trees out."""
+class HostLin:
+    """Counterpart of :class:`~nifty_b200._runtime.Lin` for host-composed models: the same flat-vector interface (``update``,
+    ``energy``, ``metric``, ``metric_pair``, sqrt-metrics, ``transformation``, ``normalized_residual``) on the explicit
+    linearisation :class:`_HostLin`, so that the sample draws, geoVI updates, the KL and ``optimize_kl`` of this package run
+    unchanged on outer-product and non-power-of-two fields.  CG solves on such operators use the host loop."""
 
-    def __init__(self, likelihood, cf: OuterCorrelatedField, nonlinearity="exp"):
+    host_composed = True
+
+    class _ModelStub:
+        def __init__(self, plan):
+            self.plan = plan
+
+    def __init__(self, lh):
+        self.lh, self.rt = lh, lh.rt
+        self.model = HostLin._ModelStub(lh.signal.cf.plan)
+        self._l, self._energy = None, None
+
+    def _pack(self, tree):
+        return self.lh.layout.pack(tree, self.lh.dtype, self.rt.device)
+
+    def update(self, pos, want_grad=False, add_prior=False):
+        lh = self.lh
+        pos = lh.signal.as_flat(pos)
+        with torch.no_grad():
+            self._l = _HostLin(lh, pos)
+            s = self._l.s
+            self._energy = float(lh._lh_energy(s))
+            if not want_grad:
+                return None
+            dE = lh.w * (s - lh.data) if lh.kind == 0 else 1.0 - lh.data / s           # likelihood_impl.py:124-126, :238-240
+            g = self._pack(self._l.vjp(dE))
+        return g + pos if add_prior else g
+
+    def energy(self) -> float:
+        return self._energy
+
+    def signal(self):
+        return self._l.s
+
+    def metric(self, t, add_identity=False, out=None):
+        with torch.no_grad():
+            r = self._l.metric_flat(t)
+            if add_identity:
+                r += t
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
+
+    def rsm(self, t, scaled=True):
+        with torch.no_grad():
+            tt = self.lh.layout.unpack(t)
+            return self._l.right_sqrt_metric(tt) if scaled else self._l.fl.jvp(tt)
+
+    def lsm(self, u, scaled=True):
+        with torch.no_grad():
+            u = torch.as_tensor(u, dtype=self.lh.dtype, device=self.rt.device)
+            return self._pack(self._l.left_sqrt_metric(u) if scaled else self._l.fl.vjp(u))
+
+    def metric_pair(self, other: "HostLin", t, add_identity=False):
+        """``lsm_self(rsm_other(t)) (+ t)``: the two halves of the geoVI operator (evi.py:167-172)."""
+        r = self.lsm(other.rsm(t))
+        return r + t if add_identity else r
+
+    def transformation(self):
+        lh, s = self.lh, self._l.s
+        return torch.sqrt(lh.w) * s if lh.kind == 0 else 2.0 * torch.sqrt(s)           # likelihood_impl.py:134-138, :248-251
+
+    def normalized_residual(self):
+        lh, s = self.lh, self._l.s
+        return torch.sqrt(lh.w) * (lh.data - s) if lh.kind == 0 else (lh.data - s) / torch.sqrt(s)
+
+
+class OuterLikelihood(LikelihoodWithModel):
+    """``Gaussian`` / ``Poissonian`` data on ``signal = nl(cf)`` for a host-composed field (:class:`OuterCorrelatedField`,
+    ``bluestein.BluesteinCorrelatedField``): the interface of :class:`~nifty_b200.likelihood.LikelihoodWithModel`
+    (likelihood.py:599-633 of the reference) with :class:`HostLin` linearisations, so ``draw_linear_residual``,
+    ``nonlinearly_update_residual``, ``optimize_kl``, ``wiener_filter_posterior`` accept it.  The N-sized transforms run on the
+    device; amplitude chains, pointwise likelihood and vector algebra are torch operations on the same device."""
+
+    def __init__(self, likelihood, cf, nonlinearity="exp"):
+        from .likelihood import SignalModel
         if nonlinearity not in ("exp", "identity") and not callable(nonlinearity):
             raise ValueError(f"unsupported nonlinearity {nonlinearity!r}")
+        self.likelihood, self.signal = likelihood, SignalModel(cf, nonlinearity)
         self.cf, self.kind, self.rt, self.dtype = cf, likelihood.kind, cf.rt, cf.dtype
+        self.layout, self.domain = cf.layout, cf.domain
+        if tuple(np.shape(likelihood.data)) != tuple(cf.target_shape):
+            raise ValueError(f"data shape {np.shape(likelihood.data)} does not match the model target {cf.target_shape}")
         self.nl = torch.exp if nonlinearity == "exp" else ((lambda f: f) if nonlinearity == "identity" else nonlinearity)
+        self.nl_name = nonlinearity if isinstance(nonlinearity, str) else "callable"
         dev = cf.rt.device
         self.data = torch.as_tensor(np.asarray(likelihood.data), dtype=cf.dtype, device=dev) if not isinstance(likelihood.data, torch.Tensor) \
             else likelihood.data.to(dtype=cf.dtype, device=dev)
         if self.kind == 0:
             w = likelihood.w_array if likelihood.w_array is not None else likelihood.w_scalar
             self.w = torch.as_tensor(w, dtype=cf.dtype, device=dev)
-        self.layout = cf.layout
+        self._lins, self._max_lins = [], 3
+        self._kl_cache = None
 
-    def signal_response(self, pos):
-        with torch.no_grad():
-            return self.nl(self.cf(pos))
+    def new_lin(self) -> HostLin:
+        return HostLin(self)
+
+    def lin_at(self, pos, want_grad=False, add_prior=False):
+        """Same contract (and cache) as ``LikelihoodWithModel.lin_at``: ``(HostLin, gradient or None)``."""
+        flat = self.signal.as_flat(pos)
+        key = self._key(flat)
+        if not want_grad:
+            for k, lin in self._lins:
+                if k == key:
+                    return lin, None
+        lin = HostLin(self)
+        grad = lin.update(flat, want_grad=want_grad, add_prior=add_prior)
+        lin._pos_ref = flat
+        self._lins.append((key, lin))
+        if len(self._lins) > self._max_lins:
+            self._lins.pop(0)
+        return lin, grad
 
     def _lh_energy(self, s):
         if self.kind == 0:                                   # Gaussian (likelihood_impl.py:124-126)
@@ -224,90 +439,21 @@ class OuterLikelihood:
     def _lh_metric_weight(self, s):
         return self.w * torch.ones_like(s) if self.kind == 0 else 1.0 / s      # :131-132, :245-246
 
-    def _leaves(self, pos, grad=True):
-        p = self.cf._tree(pos)
-        return {k: v.detach().clone().requires_grad_(grad) for k, v in p.items()}
-
-    def energy(self, pos) -> float:
+    def signal_response(self, pos):
         with torch.no_grad():
-            return float(self._lh_energy(self.nl(self.cf(pos))))
-
-    def energy_and_gradient(self, pos):
-        p = self._leaves(pos)
-        e = self._lh_energy(self.nl(self.cf(p)))
-        keys = sorted(p)
-        g = torch.autograd.grad(e, [p[k] for k in keys], allow_unused=True)
-        return float(e.detach()), {k: (torch.zeros_like(p[k]) if gi is None else gi.detach()) for k, gi in zip(keys, g)}
-
-    def _jvp(self, p, tan):
-        """J t of signal = nl(cf(p)) by the double-backward construction (the transform is its own adjoint)."""
-        keys = sorted(p)
-        s = self.nl(self.cf(p))
-        u = torch.zeros_like(s, requires_grad=True)
-        g = torch.autograd.grad(s, [p[k] for k in keys], grad_outputs=u, create_graph=True, allow_unused=True)
-        acc = sum(torch.sum(gi * tan[k]) for k, gi in zip(keys, g) if gi is not None)
-        (jt,) = torch.autograd.grad(acc, u)
-        return s.detach(), jt.detach()
-
-    def _vjp(self, p, c):
-        keys = sorted(p)
-        s = self.nl(self.cf(p))
-        g = torch.autograd.grad(s, [p[k] for k in keys], grad_outputs=c, allow_unused=True)
-        return {k: (torch.zeros_like(p[k]) if gi is None else gi.detach()) for k, gi in zip(keys, g)}
-
-    def metric(self, pos, tan):
-        """``J^T M J t`` (likelihood.py:613-621)."""
-        p = self._leaves(pos)
-        t = {k: torch.as_tensor(v, dtype=self.dtype, device=self.rt.device) for k, v in getattr(tan, "tree", tan).items()}
-        s, jt = self._jvp(p, t)
-        return self._vjp(p, self._lh_metric_weight(s) * jt)
-
-    def right_sqrt_metric(self, pos, tan):
-        p = self._leaves(pos)
-        t = {k: torch.as_tensor(v, dtype=self.dtype, device=self.rt.device) for k, v in getattr(tan, "tree", tan).items()}
-        s, jt = self._jvp(p, t)
-        return torch.sqrt(self._lh_metric_weight(s)) * jt
-
-    def left_sqrt_metric(self, pos, u):
-        p = self._leaves(pos)
-        with torch.no_grad():
-            s = self.nl(self.cf(p))
-        u = torch.as_tensor(u, dtype=self.dtype, device=self.rt.device)
-        return self._vjp(p, torch.sqrt(self._lh_metric_weight(s)) * u)
+            return self.nl(self.cf(pos))
 
     def cg_on_metric(self, pos, j, **cg_kwargs):
         """``cg(metric + 1, j)`` on flat vectors in the host loop (conjugate_gradient.py:77-214)."""
-        from .conjugate_gradient import _cg
-        lay = self.layout
+        from .conjugate_gradient import HamiltonianMetric, _cg
+        lin, _ = self.lin_at(pos)
+        return _cg(HamiltonianMetric(lin, likelihood=self), self.signal.as_flat(j), **cg_kwargs)
 
-        def mat(v):
-            return lay.pack(self.metric(pos, lay.unpack(v)), self.dtype, self.rt.device) + v
-
-        return _cg(mat, lay.pack(getattr(j, "tree", j), self.dtype, self.rt.device) if not isinstance(j, torch.Tensor) else j, **cg_kwargs)
-
-    def draw_linear_residual(self, pos, key, *, from_inverse: bool = True, cg_kwargs: Optional[dict] = None, _raise_nonposdef=False,
-                             _white=None):
-        """One MGVI residual sample at ``pos`` (evi.py:88-150): ``left_sqrt_metric(pos, N(0,1)) + N(0,1)`` as the right-hand side
-        and ``x0 = `` the prior draw of a CG on ``metric + 1`` (host loop).  Returns ``(residual tree, info)``; the mirrored
-        sample is its negative (evi.py:53-57)."""
-        from .conjugate_gradient import _cg
-        from .evi import random_normal, random_split
-        lay, dev = self.layout, self.rt.device
-        k_nll, k_prr = random_split(key, 2)
-        w_data, w_prior = (None, None) if _white is None else _white
-        white = random_normal(k_nll, self.cf.target_shape, self.dtype, dev) if w_data is None else torch.as_tensor(w_data, dtype=self.dtype, device=dev)
-        prr = random_normal(k_prr, (lay.size,), self.dtype, dev) if w_prior is None else \
-            lay.pack(getattr(w_prior, "tree", w_prior), self.dtype, dev) if not isinstance(w_prior, torch.Tensor) else w_prior.to(dev)
-        smpl = lay.pack(self.left_sqrt_metric(pos, white), self.dtype, dev) + prr
-        info = 0
-        if from_inverse:
-            def mat(v):
-                return lay.pack(self.metric(pos, lay.unpack(v)), self.dtype, dev) + v
-            res = _cg(mat, smpl, x0=prr.clone(), _raise_nonposdef=_raise_nonposdef, **(cg_kwargs or {}))
-            smpl, info = res.x, res.info
-            if info is not None and info < 0:
-                raise ValueError("conjugate gradient failed")
-        return lay.unpack(smpl), info
+    def draw_linear_residual(self, pos, key, *, _white=None, **kwargs):
+        """One MGVI residual sample at ``pos`` (evi.py:88-150) as a tree: ``evi.draw_linear_residual`` on this likelihood."""
+        from .evi import draw_linear_residual
+        r, info = draw_linear_residual(self, pos, key, _white=_white, **kwargs)
+        return self.layout.unpack(r), info
 
     # -- sample-averaged KL and MGVI iterations (optimize_kl.py:67-144, 391-444, 540-591), on flat vectors ------------------
     def _flat(self, pos):
@@ -316,29 +462,33 @@ class OuterLikelihood:
 
     def kl_value_and_grad(self, pos, residuals):
         """``_kl_vg``: mean over ``pos + residuals`` of value and gradient of the standard Hamiltonian ``lh(x) + <x, x> / 2``."""
-        p, lay = self._flat(pos), self.layout
+        p = self._flat(pos)
         pts = [p] if residuals is None or len(residuals) == 0 else [p + self._flat(r) for r in residuals]
+        lins = [HostLin(self) for _ in pts]
         val, grad = 0.0, torch.zeros_like(p)
-        for x in pts:
-            e, g = self.energy_and_gradient(lay.unpack(x))
-            val += e + 0.5 * float(torch.dot(x, x))
-            grad += lay.pack(g, self.dtype, self.rt.device) + x
+        for lin, x in zip(lins, pts):
+            grad += lin.update(x, want_grad=True, add_prior=True)
+            val += lin.energy() + 0.5 * float(torch.dot(x, x))
+        self._kl_cache = (p.clone(), residuals, lins)
         return val / len(pts), grad / len(pts)
 
     def kl_metric(self, pos, tangents, residuals):
         """``_kl_met``: mean over the sample points of ``metric(x, t) + t``."""
-        p, t, lay = self._flat(pos), self._flat(tangents), self.layout
-        pts = [p] if residuals is None or len(residuals) == 0 else [p + self._flat(r) for r in residuals]
+        p, t = self._flat(pos), self._flat(tangents)
+        c = self._kl_cache                   # the CG of one Newton step applies the metric at one (position, samples) many times
+        if c is None or c[1] is not residuals or not torch.equal(c[0], p):
+            self.kl_value_and_grad(p, residuals)
+            c = self._kl_cache
         out = torch.zeros_like(p)
-        for x in pts:
-            out += lay.pack(self.metric(lay.unpack(x), lay.unpack(t)), self.dtype, self.rt.device) + t
-        return out / len(pts)
+        for lin in c[2]:
+            out += lin.metric(t, add_identity=True)
+        return out / len(c[2])
 
     def mgvi(self, pos, *, key, n_total_iterations: int, n_samples: int, draw_linear_kwargs=None, kl_kwargs=None, _whites=None):
-        """MGVI (``optimize_kl(..., sample_mode="linear_resample")``, optimize_kl.py:672-729) on the host-composed operators:
-        per iteration ``n_samples`` residual draws (mirrored: ``[s, -s]`` interleaved, evi.py:53-57) and one Newton-CG
-        minimisation of the sample-averaged KL.  Returns ``(position tree, residuals [2 n_samples, L], list of
-        OptimizeResults)``."""
+        """MGVI (``optimize_kl(..., sample_mode="linear_resample")``, optimize_kl.py:672-729) with explicit white noise per draw
+        (``_whites``: test hook; ``optimize_kl`` itself is the general driver): per iteration ``n_samples`` residual draws
+        (mirrored: ``[s, -s]`` interleaved, evi.py:53-57) and one Newton-CG minimisation of the sample-averaged KL.  Returns
+        ``(position tree, residuals [2 n_samples, L], list of OptimizeResults)``."""
         from .evi import random_split
         from .optimize import _newton_cg
         lay = self.layout
@@ -352,7 +502,7 @@ class OuterLikelihood:
             rows = []
             for i, k in enumerate(ks):
                 w = None if _whites is None else _whites[it * n_samples + i]
-                r, _ = self.draw_linear_residual(lay.unpack(p), k, _white=w, **dkw)
+                r, _ = self.draw_linear_residual(p, k, _white=w, **dkw)
                 r = lay.pack(r, self.dtype, self.rt.device)
                 rows += [r, -r]
             res = torch.stack(rows)
@@ -361,4 +511,3 @@ class OuterLikelihood:
             p = opt.x
             states.append(opt._replace(x=None, jac=None))
         return lay.unpack(p), res, states
-

@@ -71,3 +71,8 @@ def test_kl_cg_on_device(rt):
 def test_reduce_pieces(rt):
     vc.check_reduce_pieces(rt)
     vc.check_reduce_pieces(rt, "g3d_8x8x8")
+
+
+@pytest.mark.parametrize("which,lh_kind", [("nonpow2", "gauss"), ("outer", "gauss"), ("nonpow2", "poisson"), ("outer", "poisson")])
+def test_host_composed_fields_through_the_vi_drivers(rt, which, lh_kind):
+    vc.check_host_composed_vi(rt, which, lh_kind)

@@ -462,3 +462,96 @@ def check_reduce_pieces(rt, name="g2d_16x16"):
             assert len(seen) > 2
         assert torch.equal(got, ref), nch
     plan.set_reduce_chunks(1)
+
+
+def _host_composed_pair(rt, which, lh_kind="gauss", seed=8):
+    """(likelihood of this package, oracle likelihood, oracle layout, shape) for a host-composed field: 'outer' = outer product
+    of two sub-grids, 'nonpow2' = one grid whose extents are not powers of two."""
+    kw1 = dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05))
+    kw2 = dict(fluctuations=(0.3, 0.2), loglogavgslope=(-1.5, 0.2), flexibility=(0.8, 0.3), asperity=None)
+    subs = [((8, 4), (0.2, 0.3), "space", kw1), ((4,), 0.5, "freq", kw2)] if which == "outer" else [((6, 10), (0.2, 0.3), "ax1", kw1)]
+    ocf = oracle.CorrelatedFieldOracle("cf")
+    cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+    for m in (ocf, cfm):
+        m.set_amplitude_total_offset(0.3, (0.2, 0.1))
+        for shp, dist, pf, kw in subs:
+            m.add_fluctuations(shp, dist, prefix=pf, non_parametric_kind="power", **kw)
+    ocf.finalize()
+    cf = cfm.finalize()
+    shape = sum((tuple(s[0]) for s in subs), ())
+    osig = oracle.SignalOracle(ocf, "exp")
+    lay = oracle.Layout(osig.domain)
+    rng = np.random.default_rng(seed)
+    truth = {k: 0.5 * v for k, v in lay.random(rng).items()}
+    if lh_kind == "gauss":
+        data = osig(truth) + 0.3 * rng.standard_normal(shape)
+        return nb.Gaussian(data, noise_cov_inv=1.0 / 0.09).amend(nb.SignalModel(cf, "exp")), oracle.GaussianOracle(data, 1.0 / 0.09, osig), lay, shape
+    data = rng.poisson(osig(truth)).astype(np.int64)
+    return nb.Poissonian(data).amend(nb.SignalModel(cf, "exp")), oracle.PoissonianOracle(data, osig), lay, shape
+
+
+def check_host_composed_vi(rt, which, lh_kind="gauss"):
+    """Outer-product and non-power-of-two fields through the SAME drivers as the fused single-grid path: `nb.draw_linear_residual`,
+    `nb.nonlinearly_update_residual` (geoVI) and one `nb.optimize_kl` iteration against the oracle on identical white noise
+    (optimize_kl.py:672-729, evi.py:88-255); transformation / residual / minisanity message on the way."""
+    lh, olh, lay, shape = _host_composed_pair(rt, which, lh_kind)
+    assert isinstance(lh, nb.LikelihoodWithModel) and isinstance(lh, nb.OuterLikelihood)
+    rng = np.random.default_rng(31)
+    pos = {k: 0.3 * v for k, v in lay.random(rng).items()}
+    tpos = rt.asarray(lay.pack(pos), torch.float64)
+    assert rel_err(t2n(lh.transformation(tpos)), olh.transformation(pos)) < 1e-11
+    assert rel_err(t2n(lh.normalized_residual(tpos)), olh.normalized_residual(pos)) < 1e-9
+    e, g = lh.energy_and_gradient(tpos, add_prior=True)
+    oe, og = olh.energy_and_gradient(pos)
+    assert abs(e - (oe + 0.5 * float(np.dot(lay.pack(pos), lay.pack(pos))))) <= 1e-10 * abs(e)
+    assert rel_err(t2n(g), lay.pack(og) + lay.pack(pos)) < 1e-10
+    # MGVI draw and geoVI update of both signs
+    wd, wp = rng.standard_normal(shape), lay.random(rng)
+    white = (rt.asarray(wd, torch.float64), rt.asarray(lay.pack(wp), torch.float64))
+    cgkw = dict(absdelta=1e-30, miniter=8, maxiter=8)       # fixed iteration count: trajectories, not stopping rules, are compared
+    ores, oinfo, _ = oracle.draw_linear_residual(olh, pos, wd, wp, cg_kwargs=cgkw)
+    res, info = nb.draw_linear_residual(lh, tpos, 0, cg_kwargs=cgkw, _white=white)
+    assert info == oinfo and rel_err(t2n(res), lay.pack(ores)) < 1e-6
+    mk = dict(xtol=1e-6, maxiter=3, cg_kwargs=dict(maxiter=30))
+    for sign in (1.0, -1.0):
+        onew, oopt = oracle.nonlinearly_update_residual(olh, pos, {k: sign * v for k, v in ores.items()}, wd, wp, sign, minimize_kwargs=mk)
+        new, opt = nb.nonlinearly_update_residual(lh, tpos, sign * res, 0, sign, minimize_kwargs=mk, _white=white)
+        assert opt.nit == oopt.nit and opt.status == oopt.status
+        assert rel_err(t2n(new), lay.pack(onew)) < 1e-5
+    # one optimize_kl iteration (MGVI, 2 samples) with injected white noise: residuals, Newton iterations, final KL, position
+    n_samples = 2
+    whites = [(rng.standard_normal(shape), lay.random(rng)) for _ in range(n_samples)]
+    dkw = cgkw
+    kmk = dict(xtol=1e-4, maxiter=5, cg_kwargs=dict(maxiter=30))
+    calls = []
+
+    def dlr(lh_, p, key, **kwargs):
+        wd_, wp_ = whites[len(calls)]
+        calls.append(key)
+        return nb.draw_linear_residual(lh_, p, key, _white=(rt.asarray(wd_, torch.float64), rt.asarray(lay.pack(wp_), torch.float64)), **kwargs)
+
+    vi = nb.OptimizeVI(lh, 1, _draw_linear_residual=dlr)
+    samples, state = nb.optimize_kl(lh, tpos, key=42, n_total_iterations=1, n_samples=n_samples, sample_mode="linear_resample",
+                                    draw_linear_kwargs=dict(cg_kwargs=dkw), kl_kwargs=dict(minimize_kwargs=kmk), _optimize_vi=vi)
+    assert len(calls) == n_samples and len(samples) == 2 * n_samples
+    residuals = []
+    for wd_, wp_ in whites:
+        r, _, _ = oracle.draw_linear_residual(olh, pos, wd_, wp_, cg_kwargs=dkw)
+        residuals += [r, {k: -v for k, v in r.items()}]
+    for i, r in enumerate(residuals):
+        assert rel_err(t2n(samples.residuals[i]), lay.pack(r)) < 1e-6, i
+    opos, oopt = oracle.kl_minimize(olh, pos, residuals, minimize_kwargs=kmk)
+    ms = state.minimization_state
+    assert (ms.nit, ms.status) == (oopt.nit, oopt.status)
+    assert abs(ms.fun - oopt.fun) <= 1e-7 * abs(oopt.fun)
+    assert rel_err(t2n(samples.pos), lay.pack(opos)) < 1e-5
+    msg = vi.get_status_message(samples, state, name="OPTIMIZE_KL")
+    assert "Likelihood residual(s):" in msg and "Prior residual(s):" in msg
+    # a geoVI iteration of the state machine runs (nonlinear_resample), and a point estimate is honoured
+    s2, st2 = nb.optimize_kl(lh, tpos, key=1, n_total_iterations=1, n_samples=1, sample_mode="nonlinear_resample",
+                             point_estimates=("cfzeromode",), draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-8, maxiter=40)),
+                             nonlinearly_update_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=20))),
+                             kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=20))))
+    assert st2.nit == 1 and len(s2) == 2
+    lo = lh.layout.offsets["cfzeromode"]
+    assert float(s2.residuals[:, lo].abs().max()) == 0.0
