@@ -29,7 +29,7 @@ import torch
 
 from ._runtime import Plan
 from .model import LazyModel
-from .outer import _Prior, _amplitude
+from .outer import _Prior, _amplitude_spec, _device_tables, _eval_amplitude
 from .tree import Layout
 
 
@@ -61,6 +61,31 @@ def fourier_mode_tables(shape, distances, uniqueness_rtol=1e-12):
     rel[1:] -= rel[1]
     return dict(power_distributor=idx, mode_lengths=um, mode_multiplicity=cnt, relative_log_mode_lengths=rel,
                 log_volume=rel[2:] - rel[1:-1], total_volume=float(np.prod(np.array(shape) * np.array(distances))))
+
+
+def grid_tables(shape, distances, *, dtype=torch.float64, convention="non_canonical_hartley", runtime=None):
+    """Mode tables of one (sub-)grid as a dict (keys of :func:`fourier_mode_tables` + shape, distances): from the device plan
+    (``csrc/nb_plan.cuh``, host C++) when every extent is a power of two, from the NumPy restatement otherwise."""
+    shape = tuple(int(s) for s in shape)
+    dists = tuple(float(x) for x in np.broadcast_to(distances, (len(shape),)))
+    if all(n >= 2 and not (n & (n - 1)) for n in shape):
+        pl = Plan(shape, dists, dtype=dtype, hartley_convention=convention, runtime=runtime)
+        tb = dict(power_distributor=np.asarray(pl.power_distributor), mode_lengths=np.asarray(pl.mode_lengths),
+                  mode_multiplicity=np.asarray(pl.mode_multiplicity), relative_log_mode_lengths=np.asarray(pl.relative_log_mode_lengths),
+                  log_volume=np.asarray(pl.log_volume), total_volume=float(pl.total_volume))
+    else:
+        tb = fourier_mode_tables(shape, dists)
+    tb["shape"], tb["distances"] = shape, dists
+    return tb
+
+
+def grid_record(tb):
+    """``RegularCartesianGrid`` with its harmonic grid (correlated_field.py:238-265) from a :func:`grid_tables` dict."""
+    from .correlated_field import RegularCartesianGrid, RegularFourierGrid
+    hg = RegularFourierGrid(shape=tb["shape"], power_distributor=tb["power_distributor"], mode_multiplicity=tb["mode_multiplicity"],
+                            mode_lengths=tb["mode_lengths"], relative_log_mode_lengths=tb["relative_log_mode_lengths"],
+                            log_volume=tb["log_volume"])
+    return RegularCartesianGrid(shape=tb["shape"], total_volume=tb["total_volume"], distances=tb["distances"], harmonic_grid=hg)
 
 
 class BluesteinHartley:
@@ -104,11 +129,9 @@ class BluesteinHartley:
 
 
 class BluesteinCorrelatedField(LazyModel):
-    """The finalised single-sub-grid correlated field on a grid with non-power-of-two extents (non-parametric amplitude)."""
+    """The finalised single-sub-grid correlated field on a grid with non-power-of-two extents (non-parametric or Matern amplitude)."""
 
     def __init__(self, prefix, offset_mean, azm_prior, f, *, dtype, convention, runtime):
-        if f.get("matern"):
-            raise NotImplementedError("Matern amplitudes on non-power-of-two grids are not supported")
         self.prefix, self.offset_mean, self.dtype = prefix, float(offset_mean), dtype
         self._azm = _Prior(azm_prior)
         self.shape = tuple(int(s) for s in f["shape"])
@@ -116,28 +139,15 @@ class BluesteinCorrelatedField(LazyModel):
         self.rt, self.plan = self._ht.rt, self._ht.plan          # `plan`: the PADDED power-of-two plan behind the transform
         dev = self.rt.device
         tb = fourier_mode_tables(self.shape, f["distances"])
+        tb["shape"], tb["distances"] = self.shape, tuple(float(x) for x in np.broadcast_to(f["distances"], (len(self.shape),)))
         self._grid = tb
-        K = tb["mode_lengths"].size
-        pf = prefix + f["prefix"]
-        has_dev = f["flx"] is not None and K > 2
-        self._spec = dict(kind=f["kind"], has_dev=has_dev, flu=None if f["flu"] is None else _Prior(f["flu"]), slp=_Prior(f["slp"]),
-                          flx=_Prior(f["flx"]) if has_dev else None, asp=_Prior(f["asp"]) if (has_dev and f["asp"] is not None) else None, pf=pf)
-        domain = {prefix + "zeromode": ()}
-        if f["flu"] is not None:
-            domain[pf + "fluctuations"] = ()
-        domain[pf + "loglogavgslope"] = ()
-        if has_dev:
-            domain[pf + "flexibility"] = ()
-            if f["asp"] is not None:
-                domain[pf + "asperity"] = ()
-            domain[pf + "spectrum"] = (K - 2, 2)
-        domain[prefix + "xi"] = self.shape
+        self._spec, leaves = _amplitude_spec(f, prefix + f["prefix"], tb["mode_lengths"].size)
+        domain = {prefix + "zeromode": (), prefix + "xi": self.shape}
+        domain.update(leaves)
         self.domain = dict(sorted(domain.items()))
         self.layout = Layout(self.domain)
         self.target_shape = self.shape
-        t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), dtype=dtype, device=dev)      # noqa: E731
-        self._tabs = dict(ell=t(tb["relative_log_mode_lengths"]), mult=t(tb["mode_multiplicity"]), dt=t(tb["log_volume"]),
-                          V=tb["total_volume"], pd=torch.as_tensor(tb["power_distributor"].astype(np.int64), device=dev))
+        self._tabs = _device_tables(tb, dtype, dev)
         self._vol = tb["total_volume"]
         self._factors = [(self._tabs["pd"], tuple(range(len(self.shape))))]              # one (bin table, axes) pair (outer._FieldLin)
         field = self
@@ -176,7 +186,7 @@ class BluesteinCorrelatedField(LazyModel):
 
     def _normalized(self, p):
         z = self._azm(p[self.prefix + "zeromode"])
-        a = _amplitude(self._spec, self._tabs, p, self._spec["pf"])
+        a = _eval_amplitude(self._spec, self._tabs, p)
         return z, torch.cat((a[:1], a[1:] / z))
 
     @property
@@ -185,12 +195,7 @@ class BluesteinCorrelatedField(LazyModel):
 
     @property
     def target_grids(self):
-        from .correlated_field import RegularCartesianGrid, RegularFourierGrid
-        g = self._grid
-        hg = RegularFourierGrid(shape=self.shape, power_distributor=g["power_distributor"], mode_multiplicity=g["mode_multiplicity"],
-                                mode_lengths=g["mode_lengths"], relative_log_mode_lengths=g["relative_log_mode_lengths"],
-                                log_volume=g["log_volume"])
-        return (RegularCartesianGrid(shape=self.shape, total_volume=g["total_volume"], distances=None, harmonic_grid=hg),)
+        return (grid_record(self._grid),)
 
     def __call__(self, pos) -> torch.Tensor:
         """correlated_field.py:889-912 for one sub-grid; differentiable with respect to every leaf (torch autograd)."""

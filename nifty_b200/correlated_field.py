@@ -6,9 +6,9 @@ behaviour for malformed priors.  ``finalize()`` returns a :class:`CorrelatedFiel
 JVP / VJP run in the sm_100a kernels of libniftyb200.so; nothing is evaluated in Python.
 
 Scope: one Fourier sub-grid (1-3 axes, power-of-two extents), non-parametric (``kind`` "amplitude" or "power")
-or Matern amplitude on the fused device path; two non-parametric sub-grids give the host-composed outer-product model of
-``outer.py``.  More sub-grids and ``harmonic_type="spherical"`` raise ``NotImplementedError``
-("next").
+or Matern amplitude on the fused device path; several sub-grids (at most three axes in total) give the host-composed
+outer-product model of ``outer.py``, extents that are not powers of two the chirp-z model of ``bluestein.py``.
+``harmonic_type="spherical"`` raises ``NotImplementedError`` (out of scope).
 """
 
 from __future__ import annotations
@@ -182,8 +182,8 @@ class CorrelatedFieldMaker:
         kind = non_parametric_kind.lower()
         if kind not in ("amplitude", "power"):
             raise ValueError(f"invalid `non_parametric_kind` {non_parametric_kind!r}")
-        if self._fluct:
-            raise NotImplementedError("Matern amplitudes inside outer products of several sub-grids are not supported")
+        if self._fluct and self._comm is not None:
+            raise NotImplementedError("outer products of several sub-grids are not available on slab-decomposed fields")
         shape = (int(shape),) if np.ndim(shape) == 0 else tuple(int(s) for s in shape)
         scl = _as_prior(scale, LogNormalPrior, "scale")
         ctf = _as_prior(cutoff, LogNormalPrior, "cutoff")

@@ -7,6 +7,8 @@ the composite ``H_2 H_1`` is obtained from the joint transform ``J`` by the refl
 
     H_2 H_1 x = 1/2 ( J x + (J x) o f_1 + (J x) o f_2 - (J x) o f_1 o f_2 ),      f_i : k -> -k along the axes of sub-grid i
 
+and its recursion for three sub-grids (eight reflections; at most three axes in total, so three sub-grids are three 1-D grids)
+
 (both Hartley conventions; linear and self-adjoint like its factors).  The O(K_i) amplitude spectra, the outer product, the
 reflections and the pointwise likelihood are torch operations on the same device -- a HOST-COMPOSED path: correct and checked
 against the oracle, but not fused into the pass kernels the single-grid hot path uses and not roofline-grade.
@@ -72,6 +74,54 @@ class _Prior:
     def __call__(self, xi):
         v = self.a + self.b * torch.as_tensor(xi).reshape(())
         return torch.exp(v) if self.log else v
+
+
+def _matern_amplitude(spec, tabs, p, prefix):
+    """``MaternAmplitude.__call__`` (correlated_field.py:361-395) as differentiable torch operations."""
+    um, mult, V = tabs["um"], tabs["mult"], tabs["V"]
+    scl = spec["scl"](p[prefix + "scale"])
+    ctf = spec["ctf"](p[prefix + "cutoff"])
+    slp = spec["slp"](p[prefix + "loglogslope"])
+    spectrum = torch.exp(0.25 * slp * torch.log1p((um / ctf) ** 2))
+    norm = 1.0
+    if spec["renorm"]:
+        S = torch.sum(mult[1:] * spectrum[1:] ** 2) if spec["kind"] == "amplitude" else torch.sum(mult[1:] * spectrum[1:])
+        norm = torch.sqrt(S) / np.sqrt(V)
+    if spec["kind"] == "power":
+        spectrum = torch.sqrt(spectrum)
+    spectrum = scl * (np.sqrt(V) / norm) * spectrum
+    return torch.cat((torch.full((1,), V, dtype=spectrum.dtype, device=spectrum.device), spectrum[1:]))
+
+
+def _amplitude_spec(f, pf, K):
+    """(spec, latent leaves {name: shape}) of one sub-grid's amplitude model from the maker's record ``f``
+    (``add_fluctuations`` :572-659 / ``add_fluctuations_matern`` :661-755)."""
+    if f.get("matern"):
+        spec = dict(matern=True, kind=f["kind"], renorm=f["renorm"], scl=_Prior(f["scl"]), ctf=_Prior(f["ctf"]), slp=_Prior(f["slp"]), pf=pf)
+        return spec, {pf + "scale": (), pf + "cutoff": (), pf + "loglogslope": ()}
+    has_dev = f["flx"] is not None and K > 2
+    spec = dict(matern=False, kind=f["kind"], has_dev=has_dev, flu=None if f["flu"] is None else _Prior(f["flu"]), slp=_Prior(f["slp"]),
+                flx=_Prior(f["flx"]) if has_dev else None, asp=_Prior(f["asp"]) if (has_dev and f["asp"] is not None) else None, pf=pf)
+    leaves = {}
+    if f["flu"] is not None:
+        leaves[pf + "fluctuations"] = ()
+    leaves[pf + "loglogavgslope"] = ()
+    if has_dev:
+        leaves[pf + "flexibility"] = ()
+        if f["asp"] is not None:
+            leaves[pf + "asperity"] = ()
+        leaves[pf + "spectrum"] = (K - 2, 2)
+    return spec, leaves
+
+
+def _eval_amplitude(spec, tabs, p):
+    return _matern_amplitude(spec, tabs, p, spec["pf"]) if spec["matern"] else _amplitude(spec, tabs, p, spec["pf"])
+
+
+def _device_tables(tb, dtype, dev):
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), dtype=dtype, device=dev)      # noqa: E731
+    return dict(ell=t(tb["relative_log_mode_lengths"]), mult=t(tb["mode_multiplicity"]), dt=t(tb["log_volume"]), um=t(tb["mode_lengths"]),
+                V=float(tb["total_volume"]), pd=torch.as_tensor(np.asarray(tb["power_distributor"], dtype=np.int64), device=dev))
 
 
 class _FieldLin:
@@ -184,51 +234,42 @@ class OuterCorrelatedField(LazyModel):
     def __init__(self, prefix, offset_mean, azm_prior, flucts, *, dtype, convention, runtime):
         self.prefix, self.offset_mean, self.dtype = prefix, float(offset_mean), dtype
         self._azm = _Prior(azm_prior)
-        if len(flucts) != 2:
-            raise NotImplementedError("outer products of exactly two sub-grids are supported")
+        if len(flucts) < 2:
+            raise ValueError("an outer product needs at least two sub-grids")
+        from .bluestein import BluesteinHartley, grid_tables
         shape, dists, self._axes, self._subs = (), (), [], []
         for f in flucts:
-            if f.get("matern"):
-                raise NotImplementedError("Matern amplitudes inside outer products are not supported")
-            sub_plan = Plan(f["shape"], f["distances"], dtype=dtype, hartley_convention=convention, runtime=runtime)
             n0 = len(shape)
-            shape += tuple(f["shape"])
+            shape += tuple(int(v) for v in f["shape"])
             d = f["distances"]
             dists += tuple(float(x) for x in (d if np.ndim(d) else (d,) * len(f["shape"])))
             self._axes.append(tuple(range(n0, len(shape))))
-            self._subs.append((f, sub_plan))
+            # mode tables of the sub-grid (device plan for power-of-two extents, host NumPy otherwise)
+            self._subs.append((f, grid_tables(f["shape"], f["distances"], dtype=dtype, convention=convention, runtime=runtime)))
         if len(shape) > 3:
             raise NotImplementedError("outer products with more than three axes in total are not supported")
-        self.plan = Plan(shape, dists, dtype=dtype, hartley_convention=convention, runtime=runtime)     # the JOINT transform
+        if all(n >= 2 and not (n & (n - 1)) for n in shape):
+            self.plan = Plan(shape, dists, dtype=dtype, hartley_convention=convention, runtime=runtime)     # the JOINT transform
+            self._joint = self.plan.hartley
+        else:                     # e.g. the (3, 3) x (6,) grids of the reference's own product test (test_correlated_field.py:238-283)
+            self._joint = BluesteinHartley(shape, dtype=dtype, convention=convention, runtime=runtime)
+            self.plan = self._joint.plan
         self.rt = self.plan.rt
         dev = self.rt.device
         self.shape = shape
         domain = {prefix + "zeromode": ()}
         self._tabs, self._specs = [], []
-        for f, sp in self._subs:
-            pf = prefix + f["prefix"]
-            has_dev = f["flx"] is not None and sp.K > 2
-            spec = dict(kind=f["kind"], has_dev=has_dev, flu=None if f["flu"] is None else _Prior(f["flu"]), slp=_Prior(f["slp"]),
-                        flx=_Prior(f["flx"]) if has_dev else None, asp=_Prior(f["asp"]) if (has_dev and f["asp"] is not None) else None,
-                        pf=pf)
-            if f["flu"] is not None:
-                domain[pf + "fluctuations"] = ()
-            domain[pf + "loglogavgslope"] = ()
-            if has_dev:
-                domain[pf + "flexibility"] = ()
-                if f["asp"] is not None:
-                    domain[pf + "asperity"] = ()
-                domain[pf + "spectrum"] = (sp.K - 2, 2)
-            t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), dtype=dtype, device=dev)      # noqa: E731
-            self._tabs.append(dict(ell=t(sp.relative_log_mode_lengths), mult=t(sp.mode_multiplicity), dt=t(sp.log_volume),
-                                   V=float(sp.total_volume),
-                                   pd=torch.as_tensor(np.asarray(sp.power_distributor, dtype=np.int64), device=dev)))
+        for f, tb in self._subs:
+            spec, leaves = _amplitude_spec(f, prefix + f["prefix"], tb["mode_lengths"].size)
+            domain.update(leaves)
+            self._tabs.append(_device_tables(tb, dtype, dev))
             self._specs.append(spec)
         domain[prefix + "xi"] = shape
         self.domain = dict(sorted(domain.items()))
         self.layout = Layout(self.domain)
         self.target_shape = shape
         self._vol = float(np.prod([tb["V"] for tb in self._tabs]))
+        self._coef = self._reflect_coefficients(len(flucts))
         self._factors = [(tb["pd"], axes) for tb, axes in zip(self._tabs, self._axes)]     # (bin table, axes) per sub-grid (_FieldLin)
         outer = self
 
@@ -246,15 +287,29 @@ class OuterCorrelatedField(LazyModel):
         self._sep = SepHartley
 
     # -- transform ---------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _reflect_coefficients(m):
+        """``prod_i cas(t_i) = sum_s c_s cas(sum_i s_i t_i)`` over the sign patterns ``s`` in {+1, -1}^m, from
+        ``cas(x) cas(y) = (cas(x + y) + cas(x - y) + cas(-x + y) - cas(-x - y)) / 2`` applied m - 1 times."""
+        coef = {(1,): 1.0}
+        for _ in range(m - 1):
+            nxt = {}
+            for sg, c in coef.items():
+                neg = tuple(-v for v in sg)
+                for key, w in ((sg + (1,), 0.5), (sg + (-1,), 0.5), (neg + (1,), 0.5), (neg + (-1,), -0.5)):
+                    nxt[key] = nxt.get(key, 0.0) + w * c
+            coef = nxt
+        return {k: v for k, v in coef.items() if v != 0.0}
+
     def _sep_hartley(self, x: torch.Tensor) -> torch.Tensor:
-        """The composite transform of two sub-grids by the identity of the module docstring."""
-        J = self.plan.hartley(x.detach().contiguous())
-        a1, a2 = self._axes
-
-        def refl(t, axes):
-            return torch.roll(torch.flip(t, dims=axes), shifts=[1] * len(axes), dims=axes)
-
-        return 0.5 * (J + refl(J, a1) + refl(J, a2) - refl(J, a1 + a2))
+        """The composite transform ``H_m ... H_1`` from the joint transform and its reflections (module docstring)."""
+        J = self._joint(x.detach().contiguous())
+        out = None
+        for sg, c in self._coef.items():
+            axes = sum((self._axes[i] for i, v in enumerate(sg) if v < 0), ())
+            term = torch.roll(torch.flip(J, dims=axes), shifts=[1] * len(axes), dims=axes) if axes else J
+            out = c * term if out is None else out + c * term
+        return out
 
     def _raw_transform(self, x):
         return self._sep_hartley(x)
@@ -283,7 +338,7 @@ class OuterCorrelatedField(LazyModel):
         z = self._azm(p[self.prefix + "zeromode"])
         nas = []
         for spec, tb in zip(self._specs, self._tabs):
-            a = _amplitude(spec, tb, p, spec["pf"])
+            a = _eval_amplitude(spec, tb, p)
             nas.append(torch.cat((a[:1], a[1:] / z)))                    # get_normalized_amplitudes (:807-821)
         return z, nas
 
@@ -293,8 +348,8 @@ class OuterCorrelatedField(LazyModel):
 
     @property
     def target_grids(self):
-        from .correlated_field import _grid_record
-        return tuple(_grid_record(sp) for _, sp in self._subs)
+        from .bluestein import grid_record
+        return tuple(grid_record(tb) for _, tb in self._subs)
 
     def __call__(self, pos) -> torch.Tensor:
         """correlated_field.py:889-912; differentiable with respect to every leaf (torch autograd)."""

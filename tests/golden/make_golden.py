@@ -179,14 +179,32 @@ OUTER_CASES = {
     "o_16_x_8x8": dict(shapes=((16,), (8, 8)), distances=((1.0,), (0.1, 0.1)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=42,
                        fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
                               dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
+    # the shapes of the reference's own product test (test_correlated_field.py:232-283: CFG_OFFSET, CFG_FLUCT, FLUCTUATIONS_CHOICES):
+    # sub-grids whose extents are not powers of two
+    "o_3x3_x_6": dict(shapes=((3, 3), (6,)), distances=((0.1, 0.1), (1.0,)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=0,
+                      fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
+                             dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
+    "o_6_x_3x3": dict(shapes=((6,), (3, 3)), distances=((1.0,), (0.1, 0.1)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=42,
+                      fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
+                             dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
+    "o_6_x_6": dict(shapes=((6,), (6,)), distances=((1.0,), (1.0,)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=0,
+                    fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
+                           dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
+    # three sub-grids (three 1-D grids, one of them not a power of two)
+    "o_4_x_6_x_8": dict(shapes=((4,), (6,), (8,)), distances=((0.5,), (1.0,), (0.25,)), offset_mean=0.2, offset_std=(0.1, 0.1), seed=5,
+                        fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
+                               dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05)),
+                               dict(fluctuations=(0.3, 0.2), loglogavgslope=(-1.5, 0.2), flexibility=(0.8, 0.3), asperity=(0.2, 0.02)))),
 }
 
 
-def main_outer():
+def main_outer(only=None):
     ift = _import_nifty_cl()
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
     from oracle import CorrelatedFieldOracle, Layout
     for name, c in OUTER_CASES.items():
+        if only and name not in only:
+            continue
         cfm = ift.CorrelatedFieldMaker("cf")
         cfm.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
         orc = CorrelatedFieldOracle("cf")
@@ -200,7 +218,7 @@ def main_outer():
         lay = Layout(orc.domain)
         rng = np.random.default_rng(c["seed"])
         pos, tan = lay.random(rng), lay.random(rng)
-        full = tuple(c["shapes"][0]) + tuple(c["shapes"][1])
+        full = sum((tuple(shp) for shp in c["shapes"]), ())
         cot = rng.standard_normal(full)
         out = {"cot": cot}
         for k in lay.keys:
@@ -217,5 +235,8 @@ def main_outer():
 
 
 if __name__ == "__main__":
-    main()
-    main_outer()
+    if len(sys.argv) > 1:            # `make_golden.py o_3x3_x_6 ...`: (re)write only the named outer-product fixtures
+        main_outer(only=set(sys.argv[1:]))
+    else:
+        main()
+        main_outer()

@@ -45,6 +45,22 @@ OUTER_CASES = {
     "o_16_x_8x8": dict(shapes=((16,), (8, 8)), distances=((1.0,), (0.1, 0.1)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=42,
                        fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
                               dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
+    # the shapes of the reference's own product test (test_correlated_field.py:232-283: CFG_OFFSET, CFG_FLUCT, FLUCTUATIONS_CHOICES):
+    # sub-grids whose extents are not powers of two
+    "o_3x3_x_6": dict(shapes=((3, 3), (6,)), distances=((0.1, 0.1), (1.0,)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=0,
+                      fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
+                             dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
+    "o_6_x_3x3": dict(shapes=((6,), (3, 3)), distances=((1.0,), (0.1, 0.1)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=42,
+                      fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
+                             dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
+    "o_6_x_6": dict(shapes=((6,), (6,)), distances=((1.0,), (1.0,)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=0,
+                    fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
+                           dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
+    # three sub-grids (three 1-D grids, one of them not a power of two)
+    "o_4_x_6_x_8": dict(shapes=((4,), (6,), (8,)), distances=((0.5,), (1.0,), (0.25,)), offset_mean=0.2, offset_std=(0.1, 0.1), seed=5,
+                        fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
+                               dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05)),
+                               dict(fluctuations=(0.3, 0.2), loglogavgslope=(-1.5, 0.2), flexibility=(0.8, 0.3), asperity=(0.2, 0.02)))),
 }
 
 

@@ -528,7 +528,7 @@ def check_outer_product(rt, shapes=((8, 16), (4,)), distances=(0.2, 0.5), lh_kin
     with pytest.raises(NotImplementedError):
         cfm3 = nb.CorrelatedFieldMaker("cf", runtime=rt)
         cfm3.set_amplitude_total_offset(0.0, (0.1, 0.1))
-        for i in range(3):
+        for i in range(4):                 # four axes in total
             cfm3.add_fluctuations((4,), 1.0, prefix=f"a{i}", **kw1)
         cfm3.finalize()
 
@@ -647,3 +647,46 @@ def check_nonpow2_errors(rt):
     with pytest.raises(nb.NB200Error):
         rt.api.call("nb200_hartley_chirpz", small._h, rt.stream(), (ctypes.c_int64 * 2)(5, 6), rt.ptr(H._tab), rt.ptr(x),
                     rt.ptr(torch.zeros(128, dtype=torch.float64, device=rt.device)), rt.ptr(torch.empty_like(x)))
+
+
+def check_host_composed_matern(rt, tol=1e-10):
+    """Matern amplitudes (correlated_field.py:302-395) on host-composed fields -- a grid with non-power-of-two extents and an
+    outer product Matern x non-parametric -- against the oracle: field, normalized amplitudes, energy / gradient / metric."""
+    mk = dict(scale=(1.0, 0.5), cutoff=(1.0, 0.5), loglogslope=(-3.0, 0.5))
+    kw = dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05))
+    cases = [[("m", (6, 10), (0.2, 0.3), dict(renormalize_amplitude=True, non_parametric_kind="power"))],
+             [("m", (5, 3, 4), 0.4, dict(renormalize_amplitude=False, non_parametric_kind="amplitude"))],
+             [("m", (8,), 0.5, dict(renormalize_amplitude=True, non_parametric_kind="amplitude")), ("n", (4, 4), 0.25, None)],
+             [("n", (6,), 1.0, None), ("m", (3, 3), 0.1, dict(renormalize_amplitude=False, non_parametric_kind="power"))]]
+    for ci, subs in enumerate(cases):
+        ocf = oracle.CorrelatedFieldOracle("cf")
+        cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+        for m in (ocf, cfm):
+            m.set_amplitude_total_offset(0.1, (0.2, 0.1))
+            for i, (typ, shp, dist, opt) in enumerate(subs):
+                if typ == "m":
+                    m.add_fluctuations_matern(shp, dist, prefix=f"s{i}", **mk, **opt)
+                else:
+                    m.add_fluctuations(shp, dist, prefix=f"s{i}", non_parametric_kind="power", **kw)
+        ocf.finalize()
+        cf = cfm.finalize()
+        assert isinstance(cf, (nb.OuterCorrelatedField, nb.BluesteinCorrelatedField))
+        assert cf.domain == {k: tuple(v) for k, v in ocf.domain.items()}
+        shape = sum((tuple(s[1]) for s in subs), ())
+        osig = oracle.SignalOracle(ocf, "exp")
+        lay = oracle.Layout(osig.domain)
+        rng = np.random.default_rng(100 + ci)
+        pos, tan = lay.random(rng), lay.random(rng)
+        pos = {k: 0.5 * v for k, v in pos.items()}
+        tp = {k: torch.as_tensor(v) for k, v in pos.items()}
+        tt = {k: torch.as_tensor(v) for k, v in tan.items()}
+        assert rel_err(t2n(cf(tp)), ocf(pos)) < tol, ci
+        for na, ona in zip(cf.normalized_amplitudes, ocf.normalized_amplitudes(pos)):
+            assert rel_err(t2n(na(tp)), ona) < 1e-12
+        data = rng.poisson(osig(pos)).astype(np.int64)
+        olh = oracle.PoissonianOracle(data, osig)
+        lh = nb.Poissonian(data).amend(nb.SignalModel(cf, "exp"))
+        e, grad = lh.energy_and_gradient(tp)
+        oe, ograd = olh.energy_and_gradient(pos)
+        assert abs(e - oe) <= tol * abs(oe) and tree_err(grad, ograd) < tol, ci
+        assert tree_err(lh.metric(tp, tt), olh.metric(pos, tan)) < tol, ci
