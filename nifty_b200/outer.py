@@ -7,7 +7,8 @@ the composite ``H_2 H_1`` is obtained from the joint transform ``J`` by the refl
 
     H_2 H_1 x = 1/2 ( J x + (J x) o f_1 + (J x) o f_2 - (J x) o f_1 o f_2 ),      f_i : k -> -k along the axes of sub-grid i
 
-and its recursion for three sub-grids (eight reflections; at most three axes in total, so three sub-grids are three 1-D grids)
+and its recursion for three sub-grids (three 1-D grids: a device plan has at most three axes; with more axes in total every
+sub-grid is transformed on its own axes, one device call per slice of the other axes)
 
 (both Hartley conventions; linear and self-adjoint like its factors).  The O(K_i) amplitude spectra, the outer product, the
 reflections and the pointwise likelihood are torch operations on the same device -- a HOST-COMPOSED path: correct and checked
@@ -239,6 +240,8 @@ class OuterCorrelatedField(LazyModel):
         from .bluestein import BluesteinHartley, grid_tables
         shape, dists, self._axes, self._subs = (), (), [], []
         for f in flucts:
+            if len(f["shape"]) > 3:
+                raise NotImplementedError("sub-grids with more than three axes are not supported")
             n0 = len(shape)
             shape += tuple(int(v) for v in f["shape"])
             d = f["distances"]
@@ -246,9 +249,22 @@ class OuterCorrelatedField(LazyModel):
             self._axes.append(tuple(range(n0, len(shape))))
             # mode tables of the sub-grid (device plan for power-of-two extents, host NumPy otherwise)
             self._subs.append((f, grid_tables(f["shape"], f["distances"], dtype=dtype, convention=convention, runtime=runtime)))
+        pow2 = lambda shp: all(n >= 2 and not (n & (n - 1)) for n in shp)      # noqa: E731
+        self._per_sub = None
         if len(shape) > 3:
-            raise NotImplementedError("outer products with more than three axes in total are not supported")
-        if all(n >= 2 and not (n & (n - 1)) for n in shape):
+            # more axes than one device plan holds (e.g. the (3, 3) x (3, 3) case of the reference's product test): every sub-grid is
+            # transformed on its own axes, slice by slice over the other axes -- functional, one device call per slice
+            self._per_sub = []
+            for f in flucts:
+                shp = tuple(int(v) for v in f["shape"])
+                if pow2(shp):
+                    pl = Plan(shp, 1.0, dtype=dtype, hartley_convention=convention, runtime=runtime)
+                    self._per_sub.append((pl.hartley, pl))
+                else:
+                    bh = BluesteinHartley(shp, dtype=dtype, convention=convention, runtime=runtime)
+                    self._per_sub.append((bh, bh.plan))
+            self.plan = self._per_sub[0][1]
+        elif pow2(shape):
             self.plan = Plan(shape, dists, dtype=dtype, hartley_convention=convention, runtime=runtime)     # the JOINT transform
             self._joint = self.plan.hartley
         else:                     # e.g. the (3, 3) x (6,) grids of the reference's own product test (test_correlated_field.py:238-283)
@@ -303,6 +319,8 @@ class OuterCorrelatedField(LazyModel):
 
     def _sep_hartley(self, x: torch.Tensor) -> torch.Tensor:
         """The composite transform ``H_m ... H_1`` from the joint transform and its reflections (module docstring)."""
+        if self._per_sub is not None:
+            return self._sliced_hartley(x.detach())
         J = self._joint(x.detach().contiguous())
         out = None
         for sg, c in self._coef.items():
@@ -310,6 +328,20 @@ class OuterCorrelatedField(LazyModel):
             term = torch.roll(torch.flip(J, dims=axes), shifts=[1] * len(axes), dims=axes) if axes else J
             out = c * term if out is None else out + c * term
         return out
+
+    def _sliced_hartley(self, x: torch.Tensor) -> torch.Tensor:
+        """``H_m ... H_1`` for grids with more than three axes in total: sub-grid by sub-grid on its own axes."""
+        nd = len(self.shape)
+        for (fn, _), axes in zip(self._per_sub, self._axes):
+            rest = [a for a in range(nd) if a not in axes]
+            perm = rest + list(axes)
+            xp = x.permute(perm).contiguous()
+            sub = tuple(self.shape[a] for a in axes)
+            flat = xp.reshape((-1,) + sub)
+            out = torch.stack([fn(flat[b]) for b in range(flat.shape[0])])
+            inv = [perm.index(a) for a in range(nd)]
+            x = out.reshape(xp.shape).permute(inv)
+        return x.contiguous()
 
     def _raw_transform(self, x):
         return self._sep_hartley(x)

@@ -61,6 +61,10 @@ OUTER_CASES = {
                         fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
                                dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05)),
                                dict(fluctuations=(0.3, 0.2), loglogavgslope=(-1.5, 0.2), flexibility=(0.8, 0.3), asperity=(0.2, 0.02)))),
+    # four axes in total: the (3, 3) x (3, 3) case of the reference's product test (every sub-grid transformed slice by slice)
+    "o_3x3_x_3x3": dict(shapes=((3, 3), (3, 3)), distances=((0.1, 0.1), (0.1, 0.1)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=42,
+                        fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
+                               dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
 }
 
 

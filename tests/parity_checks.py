@@ -528,8 +528,8 @@ def check_outer_product(rt, shapes=((8, 16), (4,)), distances=(0.2, 0.5), lh_kin
     with pytest.raises(NotImplementedError):
         cfm3 = nb.CorrelatedFieldMaker("cf", runtime=rt)
         cfm3.set_amplitude_total_offset(0.0, (0.1, 0.1))
-        for i in range(4):                 # four axes in total
-            cfm3.add_fluctuations((4,), 1.0, prefix=f"a{i}", **kw1)
+        cfm3.add_fluctuations((2, 2, 2, 2), 1.0, prefix="a0", **kw1)        # a sub-grid with four axes
+        cfm3.add_fluctuations((4,), 1.0, prefix="a1", **kw1)
         cfm3.finalize()
 
 

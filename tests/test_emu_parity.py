@@ -156,12 +156,13 @@ def test_custom_pointwise_nonlinearity(rt, which, lh_kind, shape):
 
 @pytest.mark.parametrize("shapes,lh_kind,conv", [(((8, 16), (4,)), "gauss", "non_canonical_hartley"),
                                                  (((16,), (8, 8)), "poisson", "canonical_hartley"),
-                                                 (((6, 5), (3,)), "poisson", "non_canonical_hartley")])
+                                                 (((6, 5), (3,)), "poisson", "non_canonical_hartley"),
+                                                 (((4, 2), (3, 2)), "gauss", "non_canonical_hartley")])
 def test_outer_product_of_two_subgrids(rt, shapes, lh_kind, conv):
     pc.check_outer_product(rt, shapes=shapes, lh_kind=lh_kind, conv=conv)
 
 
-@pytest.mark.parametrize("name", ["o_8x16_x_4", "o_16_x_8x8", "o_3x3_x_6", "o_6_x_3x3", "o_6_x_6", "o_4_x_6_x_8"])
+@pytest.mark.parametrize("name", ["o_8x16_x_4", "o_16_x_8x8", "o_3x3_x_6", "o_6_x_3x3", "o_6_x_6", "o_4_x_6_x_8", "o_3x3_x_3x3"])
 def test_outer_product_golden(rt, name):
     pc.check_outer_golden(rt, name)
 
