@@ -73,6 +73,9 @@ CASES = {
                      matern=dict(scale=(1.0, 1.0), cutoff=(1.0, 0.5), loglogslope=(-3.0, 0.5)), lh="gauss", seed=9),
     "m3d_8x4x8": dict(shape=(8, 4, 8), distances=0.5, offset_mean=0.0, offset_std=(0.1, 0.1),
                       matern=dict(scale=(3.0, 2.0), cutoff=(0.3, 0.05), loglogslope=(-4.0, 0.5)), lh="poisson", seed=10),
+    # Matern amplitude on the reference's (3, 3) grid with distances 5.0 (test_correlated_field.py:195-229)
+    "m2d_3x3": dict(shape=(3, 3), distances=5.0, offset_mean=0.0, offset_std=(0.1, 0.1),
+                    matern=dict(scale=(3.0, 2.0), cutoff=(0.1, 0.01), loglogslope=(5.0, 0.5)), lh="gauss", seed=42),
 }
 
 
@@ -109,12 +112,14 @@ def from_cl(mf):
     return out
 
 
-def main():
+def main(only=None):
     ift = _import_nifty_cl()
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
     from oracle import CorrelatedFieldOracle, Layout  # only to draw inputs in oracle key order
 
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         cf = build_cl(ift, c)
         orc = CorrelatedFieldOracle("cf")
         orc.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
@@ -239,7 +244,8 @@ def main_outer(only=None):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1:            # `make_golden.py o_3x3_x_6 ...`: (re)write only the named outer-product fixtures
+    if len(sys.argv) > 1:            # `make_golden.py o_3x3_x_6 m2d_3x3 ...`: (re)write only the named fixtures
+        main(only=set(sys.argv[1:]))
         main_outer(only=set(sys.argv[1:]))
     else:
         main()

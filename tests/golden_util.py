@@ -34,6 +34,9 @@ CASES = {
                      matern=dict(scale=(1.0, 1.0), cutoff=(1.0, 0.5), loglogslope=(-3.0, 0.5)), lh="gauss", seed=9),
     "m3d_8x4x8": dict(shape=(8, 4, 8), distances=0.5, offset_mean=0.0, offset_std=(0.1, 0.1),
                       matern=dict(scale=(3.0, 2.0), cutoff=(0.3, 0.05), loglogslope=(-4.0, 0.5)), lh="poisson", seed=10),
+    # Matern amplitude on the reference's (3, 3) grid with distances 5.0 (test_correlated_field.py:195-229)
+    "m2d_3x3": dict(shape=(3, 3), distances=5.0, offset_mean=0.0, offset_std=(0.1, 0.1),
+                    matern=dict(scale=(3.0, 2.0), cutoff=(0.1, 0.01), loglogslope=(5.0, 0.5)), lh="gauss", seed=42),
 }
 
 

@@ -690,3 +690,46 @@ def check_host_composed_matern(rt, tol=1e-10):
         oe, ograd = olh.energy_and_gradient(pos)
         assert abs(e - oe) <= tol * abs(oe) and tree_err(grad, ograd) < tol, ci
         assert tree_err(lh.metric(tp, tt), olh.metric(pos, tan)) < tol, ci
+
+
+def check_reference_cf_cases(rt):
+    """The reference's remaining correlated-field tests restated on this path (test/test_re/test_correlated_field.py):
+    :17-47 / :50-78 construction on (2,) and (3, 3) with optional asperity / flexibility and with Matern amplitudes,
+    :81-113 TypeError for malformed prior tuples, :286-322 `renormalize_amplitude=True` gives fields of standard deviation
+    `scale` (200 prior draws on a 12-point grid)."""
+    import itertools
+    for shape, asp, flx in itertools.product([(2,), (3, 3)], [None, (1.0, 1.0)], [None, (1.0, 1.0)]):
+        cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+        cfm.set_amplitude_total_offset(offset_mean=0, offset_std=(0.1, 0.1))
+        cfm.add_fluctuations(shape, distances=0.1, fluctuations=(1.0, 1.0), loglogavgslope=(1.0, 1.0), asperity=asp, flexibility=flx)
+        cf = cfm.finalize()
+        assert cf is not None and cf.domain
+        f = cf(cf.init(3))
+        assert tuple(f.shape) == shape and bool(torch.isfinite(f).all())
+    for shape in [(2,), (3, 3)]:
+        cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+        cfm.set_amplitude_total_offset(offset_mean=0, offset_std=(0.1, 0.1))
+        cfm.add_fluctuations_matern(shape, distances=0.1, scale=(1.0, 1.0), loglogslope=(1.0, 1.0), cutoff=(1.0, 1.0), renormalize_amplitude=False)
+        cf = cfm.finalize()
+        assert cf is not None and cf.domain and bool(torch.isfinite(cf(cf.init(1))).all())
+    choices = ([1e-1], [1e-1, 5e-3], [1e-1, 5e-3, 5e-3], 1e-1)
+    for flu, slp, flx, asp in itertools.product(choices, repeat=4):
+        ok = all(isinstance(el, (tuple, list)) and len(el) == 2 and all(isinstance(v, float) for v in el) for el in (flu, slp, flx, asp))
+        if ok:
+            continue
+        with pytest.raises(TypeError):
+            cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+            cfm.set_amplitude_total_offset(offset_mean=0.0, offset_std=(1e-3, 1e-4))
+            cfm.add_fluctuations(shape=(16,), distances=(1.0 / 16,), fluctuations=flu, loglogavgslope=slp, flexibility=flx, asperity=asp,
+                                 prefix="ax1", non_parametric_kind="power")
+            cfm.finalize()
+    for scale, slope, cutoff, kind in [((1.0, 1e-10), (-1.0, 1.0), (1.0, 1.0), "amplitude"), ((3.0, 1e-10), (-5.0, 0.5), (3.3, 0.01), "power"),
+                                       ((3.0, 1e-10), (-1.0, 1.0), (3.3, 0.01), "amplitude"), ((1.0, 1e-10), (-5.0, 0.5), (1.0, 1.0), "power")]:
+        cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+        cfm.set_amplitude_total_offset(offset_mean=0.0, offset_std=(0.1, 1e-10))
+        cfm.add_fluctuations_matern((12,), distances=0.1, scale=scale, cutoff=cutoff, loglogslope=slope, non_parametric_kind=kind,
+                                    renormalize_amplitude=True)
+        cf = cfm.finalize()
+        fields = np.stack([t2n(cf(cf.init(k))) for k in range(200)])
+        avg_scale = float(np.mean(np.std(fields, axis=0)))
+        assert abs(avg_scale - scale[0]) < 2e-1, (avg_scale, scale)

@@ -183,8 +183,13 @@ def test_nonpow2_hartley_float32_and_errors(rt):
     pc.check_nonpow2_errors(rt)
 
 
-def test_nonpow2_golden_3x3(rt):
-    pc.check_nonpow2_golden(rt)
+@pytest.mark.parametrize("name", ["g2d_3x3", "m2d_3x3"])
+def test_nonpow2_golden_3x3(rt, name):
+    pc.check_nonpow2_golden(rt, name)
+
+
+def test_reference_cf_cases(rt):
+    pc.check_reference_cf_cases(rt)
 
 
 @pytest.mark.parametrize("shape,dist,lh_kind,conv", [((6, 10), (0.2, 0.3), "gauss", "non_canonical_hartley"),
