@@ -170,3 +170,20 @@ def test_reduce_pieces(rt):
 @pytest.mark.parametrize("which,lh_kind", [("nonpow2", "gauss"), ("outer", "gauss"), ("nonpow2", "poisson"), ("outer", "poisson")])
 def test_host_composed_fields_through_the_vi_drivers(rt, which, lh_kind):
     vc.check_host_composed_vi(rt, which, lh_kind)
+
+
+@pytest.mark.parametrize("sample_mode,point_estimates", [("nonlinear_resample", ()), ("linear_resample", ()),
+                                                         ("nonlinear_resample", ("cfax1fluctuations", "cfzeromode")),
+                                                         ("linear_resample", ("cfax1spectrum",))])
+def test_sample_consistency(rt, sample_mode, point_estimates):
+    vc.check_sample_consistency(rt, sample_mode, point_estimates)
+
+
+def test_sample_consistency_and_constants_host_composed(rt):
+    lh = vc._host_composed_pair(rt, "nonpow2", "gauss")[0]
+    vc.check_sample_consistency(rt, "nonlinear_resample", ("cfax1loglogavgslope",), lh=lh)
+    vc.check_constants_do_not_move(rt, ("cfax1fluctuations",), lh=lh)
+
+
+def test_constants_do_not_move(rt):
+    vc.check_constants_do_not_move(rt)

@@ -555,3 +555,57 @@ def check_host_composed_vi(rt, which, lh_kind="gauss"):
     assert st2.nit == 1 and len(s2) == 2
     lo = lh.layout.offsets["cfzeromode"]
     assert float(s2.residuals[:, lo].abs().max()) == 0.0
+
+
+def check_sample_consistency(rt, sample_mode="nonlinear_resample", point_estimates=(), lh=None):
+    """test/test_re/test_optimize_kl.py:120-250 restated: `draw_residual` == `draw_linear_residual` followed by the two
+    `nonlinearly_update_residual` calls (sign +1 / -1, same key) == the samples `optimize_kl` holds after one iteration with a
+    KL minimisation of zero steps; residuals vanish on point-estimated leaves.  Linear modes run the update with maxiter = 0."""
+    if lh is None:
+        lh = _setup(rt, "g2d_16x16")[2]
+    pos = 0.1 * lh.layout.random(3, torch.float64, rt.device)
+    delta = 1e-3
+    dkw = dict(cg_name="SL", cg_kwargs=dict(miniter=2, absdelta=delta * lh.layout.size / 10.0, maxiter=100))
+    mk = dict(name="SN", xtol=delta, cg_kwargs=dict(name=None, miniter=2), maxiter=5 if sample_mode == "nonlinear_resample" else 0)
+    frozen = lh.frozen_ranges(point_estimates)
+
+    def zero_on_frozen(r):
+        for lo, hi in frozen:
+            assert float(r[..., lo:hi].abs().max()) == 0.0
+
+    key = 7
+    draw, _ = nb.draw_residual(lh, pos, key, point_estimates=point_estimates, minimize_kwargs=mk, **dkw)
+    zero_on_frozen(draw)
+    l1, _ = nb.draw_linear_residual(lh, pos, key, point_estimates=point_estimates, **dkw)
+    zero_on_frozen(l1)
+    n1, _ = nb.nonlinearly_update_residual(lh, pos, l1, key, +1.0, point_estimates=point_estimates, minimize_kwargs=mk)
+    n2, _ = nb.nonlinearly_update_residual(lh, pos, -l1, key, -1.0, point_estimates=point_estimates, minimize_kwargs=mk)
+    diy = torch.stack((n1, n2))
+    zero_on_frozen(diy)
+    np.testing.assert_allclose(t2n(draw), t2n(diy), rtol=1e-7, atol=1e-12)
+    if sample_mode != "nonlinear_resample":
+        np.testing.assert_allclose(t2n(draw), t2n(torch.stack((l1, -l1))), rtol=1e-7, atol=1e-12)
+    s, _ = nb.optimize_kl(lh, pos, key=11, n_total_iterations=1, n_samples=1, point_estimates=point_estimates, draw_linear_kwargs=dkw,
+                          nonlinearly_update_kwargs=dict(minimize_kwargs=mk), kl_kwargs=dict(minimize_kwargs=dict(name="M", maxiter=0)),
+                          sample_mode=sample_mode)
+    zero_on_frozen(s.residuals)
+    again, _ = nb.draw_residual(lh, pos, s.keys[0], point_estimates=point_estimates, minimize_kwargs=mk, **dkw)
+    np.testing.assert_allclose(t2n(s.residuals), t2n(again), rtol=1e-7, atol=1e-12)
+    np.testing.assert_array_equal(t2n(s.pos), t2n(pos))          # zero KL steps: the expansion point stays
+
+
+def check_constants_do_not_move(rt, constants=("cfax1fluctuations", "cfax1spectrum"), lh=None):
+    """test/test_re/test_optimize_kl.py:253-323 restated: after one `optimize_kl` iteration the constant leaves have not moved at
+    all and every other entry has."""
+    if lh is None:
+        lh = _setup(rt, "g2d_16x16")[2]
+    pos = 0.1 * lh.layout.random(5, torch.float64, rt.device)
+    delta = 1e-3
+    dkw = dict(cg_name="SL", cg_kwargs=dict(miniter=2, absdelta=delta * lh.layout.size / 10.0, maxiter=100))
+    s, _ = nb.optimize_kl(lh, pos, key=13, n_total_iterations=1, n_samples=1, constants=constants, draw_linear_kwargs=dkw,
+                          kl_kwargs=dict(minimize_kwargs=dict(name="M", maxiter=5)), sample_mode="linear_resample")
+    move = t2n(s.pos - pos)
+    mask = np.zeros(move.shape, dtype=bool)
+    for lo, hi in lh.frozen_ranges(constants):
+        mask[lo:hi] = True
+    assert np.all(move[mask] == 0.0) and np.all(move[~mask] != 0.0)
