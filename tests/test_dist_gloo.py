@@ -129,3 +129,49 @@ def test_sample_sharding_matches_single_process(tmp_path):
     with open(tmp_path / "ckpt_m" / "last.pkl", "rb") as f:
         ck, _ = pickle.load(f)
     assert next(iter(ck.residuals.values())).shape[0] == 2
+
+
+def _host_composed_run(comm, which="nonpow2"):
+    """KL value / gradient / metric over 4 sample points and one optimize_kl iteration on a host-composed field."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    import nifty_b200 as nb
+    from nifty_b200._capi import CApi
+    from emu.build_emu import build
+    import vi_checks as vc
+    rt = nb.Runtime(CApi(build()), "cpu")
+    lh = vc._host_composed_pair(rt, which, "gauss")[0]
+    pos = 0.1 * lh.layout.random(7, torch.float64, rt.device)
+    vi = nb.OptimizeVI(lh, 1, comm=comm)
+    cgkw = dict(absdelta=1e-30, miniter=8, maxiter=8)
+    samples, _ = vi.draw_linear_samples(pos, nb.random_split(123, 2), cg_kwargs=cgkw)
+    v, gr = vi.kl_value_and_grad(pos, samples.residuals)
+    m = vi.kl_metric(lh.layout.random(9, torch.float64, rt.device))
+    s2, _ = nb.optimize_kl(lh, pos, key=5, n_total_iterations=1, n_samples=2, comm=comm, sample_mode="linear_resample",
+                           draw_linear_kwargs=dict(cg_kwargs=cgkw),
+                           kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(absdelta=1e-30, miniter=5, maxiter=5))))
+    return dict(v=v, g=gr.numpy(), m=m.numpy(), pos2=s2.pos.numpy(), nloc=len(samples))
+
+
+def _worker_host_composed(rank, world, port, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    np.savez(os.path.join(outdir, f"hc{rank}.npz"), **_host_composed_run(True))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sample_sharding_of_host_composed_fields(tmp_path):
+    """Sample sharding over two ranks for a field on a non-power-of-two grid (host-applied operators, the KL metric summed by the
+    same all-reduce): same KL value / gradient / metric and the same new position as a single process."""
+    world = 2
+    mp.spawn(_worker_host_composed, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    one = _host_composed_run(None)
+    for i in range(world):
+        r = np.load(tmp_path / f"hc{i}.npz")
+        assert r["nloc"] == 2 and one["nloc"] == 4
+        assert abs(float(r["v"]) - one["v"]) <= 1e-12 * abs(one["v"])
+        np.testing.assert_allclose(r["g"], one["g"], rtol=0, atol=1e-12 * np.abs(one["g"]).max())
+        np.testing.assert_allclose(r["m"], one["m"], rtol=0, atol=1e-12 * np.abs(one["m"]).max())
+        np.testing.assert_allclose(r["pos2"], one["pos2"], rtol=0, atol=1e-8 * np.abs(one["pos2"]).max())
