@@ -97,6 +97,9 @@ class BluesteinHartley:
         if not 1 <= len(self.shape) <= 3:
             raise NotImplementedError("1 to 3 axes")
         self.pad = tuple(max(2, 1 << int(np.ceil(np.log2(2 * n - 1)))) for n in self.shape)
+        if max(self.pad) > (1 << 14):
+            raise NotImplementedError(f"extents above 8192 that are not powers of two are not supported (shape {self.shape} needs padded lines "
+                                      f"of {max(self.pad)} points; the passes hold one line of at most 16384 in shared memory)")
         self.plan = Plan(self.pad, 1.0, dtype=dtype, hartley_convention=convention, runtime=runtime)
         self.rt, self.dtype = self.plan.rt, dtype
         lead = 3 - len(self.shape)

@@ -649,6 +649,8 @@ def check_nonpow2_model(rt, shape=(6, 10), distances=(0.2, 0.3), lh_kind="gauss"
 def check_nonpow2_errors(rt):
     """`nb200_hartley_chirpz` refuses a padded plan that is too short for the cyclic convolution; shapes are checked."""
     import ctypes
+    with pytest.raises(NotImplementedError):
+        nb.BluesteinHartley((10000,), runtime=rt)                # padded line of 32768 points
     H = nb.BluesteinHartley((5, 6), runtime=rt)
     with pytest.raises(ValueError):
         H(torch.zeros((6, 5), dtype=torch.float64))
