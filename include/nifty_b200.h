@@ -90,7 +90,7 @@ int nb200_dist_phase(nb200_lin* lin_a, nb200_lin* lin_b, void* stream, int code,
 int nb200_hartley(nb200_plan* plan, void* stream, const void* in, void* out);
 
 /* hartley(p) (correlated_field.py:24-30) on a grid whose extents are NOT powers of two -- the reference's own parity case (3, 3)
- * (test/test_re/test_correlated_field.py:123-124) and its published 3618^2 ... 7126^2 benchmark sizes -- as a chirp convolution
+ * (test/test_re/test_correlated_field.py:123-124) and the 3618^2 point of its published benchmark (padded extents are limited to 8192 in float64, 16384 in float32) -- as a chirp convolution
  * (Bluestein) through the power-of-two passes of `padded_plan`, whose extents must be >= 2 n - 1 along every axis.
  *   n    : the logical extents (host, ndim of the padded plan entries)
  *   tab  : device table of complex numbers (interleaved re, im, the plan's dtype): for each of the three right-aligned axes (missing

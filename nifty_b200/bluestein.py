@@ -13,7 +13,7 @@ pad + chirp, two Hartley transforms, spectrum product on mirror pairs, two Hartl
 (``nb200_hartley_chirpz``, three streaming kernels of ``csrc/nb_bluestein.cuh`` around the existing passes).  Cost: four
 power-of-two transforms of the padded grid, (M / n)^d ~ 4 ... 16 times the points of the logical grid in 2-D; a mixed-radix line
 FFT inside the pass bodies would avoid the padding and is the roofline-grade answer.  Extents up to
-8192 per axis (padded 16384, the longest shared-memory line of the passes).
+4096 per axis in float64 (padded 8192, the longest line the passes hold in shared memory), 8192 in float32.
 
 The transform is linear and self-adjoint, so it enters torch autograd as one function; the O(K) amplitude chain and the
 pointwise likelihood are torch operations on the same device, and model / likelihood operators / CG / MGVI come from the
@@ -97,9 +97,10 @@ class BluesteinHartley:
         if not 1 <= len(self.shape) <= 3:
             raise NotImplementedError("1 to 3 axes")
         self.pad = tuple(max(2, 1 << int(np.ceil(np.log2(2 * n - 1)))) for n in self.shape)
-        if max(self.pad) > (1 << 14):
-            raise NotImplementedError(f"extents above 8192 that are not powers of two are not supported (shape {self.shape} needs padded lines "
-                                      f"of {max(self.pad)} points; the passes hold one line of at most 16384 in shared memory)")
+        max_line = 8192 if dtype == torch.float64 else 16384       # one complex line of the passes must fit into shared memory (227 KB)
+        if max(self.pad) > max_line:
+            raise NotImplementedError(f"non-power-of-two extents above {max_line // 2} are not supported in {dtype} (shape {self.shape} needs "
+                                      f"padded lines of {max(self.pad)} points; the passes hold one line of at most {max_line} in shared memory)")
         self.plan = Plan(self.pad, 1.0, dtype=dtype, hartley_convention=convention, runtime=runtime)
         self.rt, self.dtype = self.plan.rt, dtype
         lead = 3 - len(self.shape)
