@@ -187,3 +187,7 @@ def test_sample_consistency_and_constants_host_composed(rt):
 
 def test_constants_do_not_move(rt):
     vc.check_constants_do_not_move(rt)
+
+
+def test_host_composed_wiener_filter_and_slq(rt):
+    vc.check_host_composed_wiener_and_elbo(rt, "nonpow2")

@@ -609,3 +609,28 @@ def check_constants_do_not_move(rt, constants=("cfax1fluctuations", "cfax1spectr
     for lo, hi in lh.frozen_ranges(constants):
         mask[lo:hi] = True
     assert np.all(move[mask] == 0.0) and np.all(move[~mask] != 0.0)
+
+
+def check_host_composed_wiener_and_elbo(rt, which="nonpow2"):
+    """`wiener_filter_posterior` (both branches) and the stochastic-Lanczos ELBO accept host-composed likelihoods: the posterior
+    mean against the dense solve of the oracle's linearised problem (as check_wiener_filter does for the fused path)."""
+    lh, olh, lay, shape = _host_composed_pair(rt, which, "gauss")
+    rng = np.random.default_rng(33)
+    pos = {k: 0.3 * v for k, v in lay.random(rng).items()}
+    L, pv = lay.size, lay.pack(pos)
+    H = np.stack([lay.pack(olh.metric(pos, lay.unpack(e))) + e for e in np.eye(L)], axis=1)
+    rhs = lay.pack(olh.left_sqrt_metric(pos, olh.normalized_residual(pos) + olh.right_sqrt_metric(pos, pos)))
+    dense = np.linalg.solve(H, rhs)
+    tpos = rt.asarray(pv, torch.float64)
+    kw = dict(resnorm=1e-9, maxiter=400)
+    smp, (info, sinfo) = nb.wiener_filter_posterior(lh, tpos, key=5, n_samples=1, model_is_linear=False, draw_linear_kwargs=dict(cg_kwargs=kw))
+    assert info == 0 and sinfo == [0] and rel_err(t2n(smp.pos), dense) < 1e-7
+    assert smp.samples.shape == (2, L) and torch.equal(smp.residuals[0], -smp.residuals[1])
+    dsp, (dinfo, _) = nb.wiener_filter_posterior(lh, tpos, key=1, n_samples=0, model_is_linear=False, signal_space=False,
+                                                 noise_covariance=lambda x: 0.09 * x, draw_linear_kwargs=dict(cg_kwargs=dict(resnorm=1e-9, maxiter=600)))
+    assert dinfo == 0 and rel_err(t2n(dsp.pos), dense) < 1e-6
+    # trace-log of metric + 1 by stochastic Lanczos quadrature on the host-applied operator against the dense log-determinant
+    lin, _ = lh.lin_at(tpos)
+    est = nb.stochastic_lq_logdet(lambda v: lin.metric(v, add_identity=True), 20, 16, 3, shape0=L, dtype=torch.float64, device=rt.device)
+    want = float(np.linalg.slogdet(H)[1])
+    assert abs(float(est) - want) < 0.2 * abs(want) + 1.0
