@@ -612,7 +612,7 @@ def check_constants_do_not_move(rt, constants=("cfax1fluctuations", "cfax1spectr
 
 
 def check_host_composed_wiener_and_elbo(rt, which="nonpow2"):
-    """`wiener_filter_posterior` (both branches) and the stochastic-Lanczos ELBO accept host-composed likelihoods: the posterior
+    """`wiener_filter_posterior` (both branches), stochastic Lanczos quadrature and `estimate_evidence_lower_bound` accept host-composed likelihoods: the posterior
     mean against the dense solve of the oracle's linearised problem (as check_wiener_filter does for the fused path)."""
     lh, olh, lay, shape = _host_composed_pair(rt, which, "gauss")
     rng = np.random.default_rng(33)
@@ -634,3 +634,11 @@ def check_host_composed_wiener_and_elbo(rt, which="nonpow2"):
     est = nb.stochastic_lq_logdet(lambda v: lin.metric(v, add_identity=True), 20, 16, 3, shape0=L, dtype=torch.float64, device=rt.device)
     want = float(np.linalg.slogdet(H)[1])
     assert abs(float(est) - want) < 0.2 * abs(want) + 1.0
+    # estimate_evidence_lower_bound, all relevant eigenvalues (eigsh path) against dense eigenvalues of the oracle metric
+    res = 0.05 * np.stack([lay.pack(lay.random(rng)) for _ in range(2)])
+    smp2 = nb.Samples(pos=tpos, samples=rt.asarray(res, torch.float64))
+    el, st = nb.estimate_evidence_lower_bound(lh, smp2, 0, compute_all=True, verbose=False)
+    eig = np.sort(np.linalg.eigvalsh(0.5 * (H + H.T)))[::-1]
+    nrel = min(int(np.prod(shape)), L)
+    ham = np.array([olh.energy(lay.unpack(pv + r)) + 0.5 * (pv + r) @ (pv + r) for r in res])
+    np.testing.assert_allclose(el, -0.5 * np.sum(np.log(eig[:nrel])) + 0.5 * L - ham, rtol=1e-8)
