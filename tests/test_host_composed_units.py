@@ -1,0 +1,70 @@
+"""CPU tier: pieces of the host-composed model families (nifty_b200/outer.py, bluestein.py) that need no device."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+import nifty_b200 as nb
+import oracle
+from nifty_b200._capi import CApi
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from emu.build_emu import build
+    return nb.Runtime(CApi(build()), "cpu")
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+def test_reflect_coefficients_identity(m):
+    """prod_i cas(t_i) = sum_s c_s cas(sum_i s_i t_i): the identity behind the composite transform of an outer product."""
+    coef = nb.OuterCorrelatedField._reflect_coefficients(m)
+    cas = lambda x: np.cos(x) + np.sin(x)      # noqa: E731
+    rng = np.random.default_rng(m)
+    for _ in range(20):
+        t = rng.uniform(-10, 10, size=m)
+        lhs = np.prod(cas(t))
+        rhs = sum(c * cas(float(np.dot(s, t))) for s, c in coef.items())
+        assert abs(lhs - rhs) < 1e-12
+    assert abs(sum(coef.values()) - 1.0) < 1e-15          # t = 0
+
+
+@pytest.mark.parametrize("shape,dist", [((8,), 0.3), ((4, 16), (0.2, 0.7)), ((2, 4, 8), 0.5)])
+def test_mode_tables_numpy_restatement_matches_the_plan(rt, shape, dist):
+    """`fourier_mode_tables` (host NumPy, any extents) and the C++ tables of a power-of-two plan are the same tables."""
+    a = nb.fourier_mode_tables(shape, dist)
+    b = nb.bluestein.grid_tables(shape, dist, runtime=rt)
+    assert np.array_equal(a["power_distributor"], b["power_distributor"])
+    assert np.array_equal(a["mode_multiplicity"], b["mode_multiplicity"])
+    np.testing.assert_allclose(a["mode_lengths"], b["mode_lengths"], rtol=0, atol=0)
+    np.testing.assert_allclose(a["relative_log_mode_lengths"], b["relative_log_mode_lengths"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(a["log_volume"], b["log_volume"], rtol=0, atol=1e-14)
+    assert a["total_volume"] == b["total_volume"]
+
+
+@pytest.mark.parametrize("shape,dist", [((3,), 0.1), ((3, 3), 0.1), ((6, 10), (0.2, 0.3)), ((5, 3, 4), 0.4), ((1, 7), 1.0)])
+def test_mode_tables_numpy_restatement_matches_the_oracle(shape, dist):
+    a = nb.fourier_mode_tables(shape, dist)
+    idx, um, cnt = oracle.fourier_mode_distributor(shape, dist)
+    assert np.array_equal(a["power_distributor"], idx) and np.array_equal(a["mode_lengths"], um) and np.array_equal(a["mode_multiplicity"], cnt)
+    g = oracle.make_fourier_grid(shape, dist)
+    np.testing.assert_allclose(a["relative_log_mode_lengths"], g.relative_log_mode_lengths, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(a["log_volume"], g.log_volume, rtol=0, atol=1e-15)
+
+
+def test_differentiable_model_call(rt):
+    """`cf(p)` of a host-composed field is differentiable with torch autograd (the composite transform is a self-adjoint autograd
+    function): the gradient of a scalar function of the field against the explicit cotangent formula."""
+    cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+    cfm.set_amplitude_total_offset(0.3, (0.2, 0.1))
+    cfm.add_fluctuations((6,), 1.0, fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05), prefix="a")
+    cfm.add_fluctuations((3, 4), 0.5, fluctuations=(0.3, 0.2), loglogavgslope=(-1.5, 0.2), flexibility=(0.8, 0.3), asperity=None, prefix="b")
+    cf = cfm.finalize()
+    p = {k: v.clone().requires_grad_(True) for k, v in cf.init(4).items()}
+    c = torch.as_tensor(np.random.default_rng(0).standard_normal(cf.target))
+    (cf(p) * c).sum().backward()
+    lh = nb.Gaussian(np.zeros(cf.target), noise_cov_inv=1.0).amend(cf)           # identity signal: left sqrt-metric = J^T
+    want = lh.left_sqrt_metric({k: v.detach() for k, v in p.items()}, c)
+    for k in p:
+        np.testing.assert_allclose(p[k].grad.numpy(), want[k].numpy(), rtol=1e-10, atol=1e-12)
