@@ -91,9 +91,8 @@ class Likelihood:
         if isinstance(signal, composed):
             return OuterLikelihood(self, signal, "identity")
         if isinstance(signal, SignalModel) and isinstance(signal.cf, composed):
-            if signal.scaling is not None:
-                raise NotImplementedError("the `scaling` leaf is not supported on host-composed fields")
-            return OuterLikelihood(self, signal.cf, signal.nl_fn if signal.nl_fn is not None else signal.nonlinearity)
+            return OuterLikelihood(self, signal.cf, signal.nl_fn if signal.nl_fn is not None else signal.nonlinearity,
+                                   scaling=signal.scaling, scaling_key=signal.scaling_key)
         if isinstance(signal, CorrelatedField):
             signal = SignalModel(signal, "identity")
         if not isinstance(signal, SignalModel):

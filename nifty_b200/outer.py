@@ -186,7 +186,8 @@ class _HostLin:
 
     def __init__(self, lh, pos):
         self.lh = lh
-        self.fl = _FieldLin(lh.cf, lh.cf._tree(pos))
+        p = lh._tree(pos)
+        self.fl = _FieldLin(lh.cf, {k: p[k] for k in lh.cf.domain})
         f = self.fl.field
         if lh.nl_name == "exp":
             self.s = torch.exp(f)
@@ -201,6 +202,12 @@ class _HostLin:
                     raise ValueError("the non-linearity must be a pointwise map of the correlated field (same shape in and out)")
                 (self.d,) = torch.autograd.grad(sr.sum(), fr)
             self.s = sr.detach()
+        self.sc_b = None
+        if lh.scaling is not None:                             # signal = scaling(p) * exp(field), scaling log-normal of shape (1,)
+            sc = lh.scaling(p[lh.scaling_key])
+            self.s = sc * self.s
+            self.d = self.s
+            self.sc_b = lh.scaling.b                           # d scaling / d leaf = b * scaling
         self.mw = lh._lh_metric_weight(self.s)
 
     def _t(self, tan):
@@ -208,11 +215,18 @@ class _HostLin:
         return {k: torch.as_tensor(v, dtype=lh.dtype, device=lh.rt.device) for k, v in getattr(tan, "tree", tan).items()}
 
     def jvp(self, tan):
-        jt = self.fl.jvp(self._t(tan))
-        return jt if self.d is None else self.d * jt
+        t = self._t(tan)
+        jt = self.fl.jvp(t)
+        jt = jt if self.d is None else self.d * jt
+        if self.sc_b is not None:
+            jt = jt + self.s * (self.sc_b * t[self.lh.scaling_key].reshape(()))
+        return jt
 
     def vjp(self, c):
-        return self.fl.vjp(c if self.d is None else self.d * c)
+        out = self.fl.vjp(c if self.d is None else self.d * c)
+        if self.sc_b is not None:
+            out[self.lh.scaling_key] = (self.sc_b * torch.sum(c * self.s)).reshape(1)
+        return out
 
     def metric(self, tan):
         return self.vjp(self.mw * self.jvp(tan))
@@ -478,13 +492,15 @@ class OuterLikelihood(LikelihoodWithModel):
     ``nonlinearly_update_residual``, ``optimize_kl``, ``wiener_filter_posterior`` accept it.  The N-sized transforms run on the
     device; amplitude chains, pointwise likelihood and vector algebra are torch operations on the same device."""
 
-    def __init__(self, likelihood, cf, nonlinearity="exp"):
+    def __init__(self, likelihood, cf, nonlinearity="exp", scaling=None, scaling_key="scaling"):
         from .likelihood import SignalModel
         if nonlinearity not in ("exp", "identity") and not callable(nonlinearity):
             raise ValueError(f"unsupported nonlinearity {nonlinearity!r}")
-        self.likelihood, self.signal = likelihood, SignalModel(cf, nonlinearity)
+        self.likelihood, self.signal = likelihood, SignalModel(cf, nonlinearity, scaling=scaling, scaling_key=scaling_key)
         self.cf, self.kind, self.rt, self.dtype = cf, likelihood.kind, cf.rt, cf.dtype
-        self.layout, self.domain = cf.layout, cf.domain
+        self.layout, self.domain = self.signal.layout, self.signal.domain
+        self.scaling = None if self.signal.scaling is None else _Prior(self.signal.scaling)
+        self.scaling_key = scaling_key
         if tuple(np.shape(likelihood.data)) != tuple(cf.target_shape):
             raise ValueError(f"data shape {np.shape(likelihood.data)} does not match the model target {cf.target_shape}")
         self.nl = torch.exp if nonlinearity == "exp" else ((lambda f: f) if nonlinearity == "identity" else nonlinearity)
@@ -526,9 +542,13 @@ class OuterLikelihood(LikelihoodWithModel):
     def _lh_metric_weight(self, s):
         return self.w * torch.ones_like(s) if self.kind == 0 else 1.0 / s      # :131-132, :245-246
 
-    def signal_response(self, pos):
-        with torch.no_grad():
-            return self.nl(self.cf(pos))
+    def _tree(self, pos):
+        """Latent position (flat vector in the order of ``self.layout``, dict or ``Vector``) as a dict of device tensors."""
+        pos = getattr(pos, "tree", pos)
+        if isinstance(pos, torch.Tensor):
+            return self.layout.unpack(pos.to(dtype=self.dtype, device=self.rt.device))
+        return {k: torch.as_tensor(v, dtype=self.dtype, device=self.rt.device) if not isinstance(v, torch.Tensor)
+                else v.to(dtype=self.dtype, device=self.rt.device) for k, v in pos.items()}
 
     def cg_on_metric(self, pos, j, **cg_kwargs):
         """``cg(metric + 1, j)`` on flat vectors in the host loop (conjugate_gradient.py:77-214)."""

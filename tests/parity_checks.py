@@ -745,3 +745,41 @@ def check_reference_cf_cases(rt):
         fields = np.stack([t2n(cf(cf.init(k))) for k in range(200)])
         avg_scale = float(np.mean(np.std(fields, axis=0)))
         assert abs(avg_scale - scale[0]) < 2e-1, (avg_scale, scale)
+
+
+def check_host_composed_scaling(rt, tol=1e-10):
+    """The demo's log-normal `scaling` leaf (signal = scaling * exp(cf), demos/re/0_intro.py:39-57) on host-composed fields against
+    the oracle: energy, gradient, metric, both sqrt-metrics, on a non-power-of-two grid and on an outer product."""
+    kw = dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05))
+    for ci, subs in enumerate([[((6, 10), (0.2, 0.3))], [((8,), 0.5), ((3, 4), 0.25)]]):
+        ocf = oracle.CorrelatedFieldOracle("cf")
+        cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+        for m in (ocf, cfm):
+            m.set_amplitude_total_offset(0.1, (0.2, 0.1))
+            for i, (shp, dist) in enumerate(subs):
+                m.add_fluctuations(shp, dist, prefix=f"s{i}", non_parametric_kind="power", **kw)
+        ocf.finalize()
+        cf = cfm.finalize()
+        shape = sum((tuple(s[0]) for s in subs), ())
+        osig = oracle.SignalOracle(ocf, "exp", scaling=(1.0, 0.5))
+        sig = nb.SignalModel(cf, "exp", scaling=(1.0, 0.5))
+        assert sig.domain == {k: tuple(v) for k, v in osig.domain.items()}
+        lay = oracle.Layout(osig.domain)
+        rng = np.random.default_rng(200 + ci)
+        pos, tan = lay.random(rng), lay.random(rng)
+        pos = {k: 0.5 * v for k, v in pos.items()}
+        data = osig(pos) + 0.3 * rng.standard_normal(shape)
+        olh = oracle.GaussianOracle(data, 1.0 / 0.09, osig)
+        lh = nb.Gaussian(data, noise_cov_inv=1.0 / 0.09).amend(sig)
+        tp = {k: torch.as_tensor(v) for k, v in pos.items()}
+        tt = {k: torch.as_tensor(v) for k, v in tan.items()}
+        assert rel_err(t2n(lh.signal_response(tp)), osig(pos)) < tol
+        e, grad = lh.energy_and_gradient(tp)
+        oe, ograd = olh.energy_and_gradient(pos)
+        assert abs(e - oe) <= tol * abs(oe) and tree_err(grad, ograd) < tol
+        assert tree_err(lh.metric(tp, tt), olh.metric(pos, tan)) < tol
+        u = rng.standard_normal(shape)
+        assert tree_err(lh.left_sqrt_metric(tp, u), olh.left_sqrt_metric(pos, u)) < tol
+        assert rel_err(t2n(lh.right_sqrt_metric(tp, tt)), olh.right_sqrt_metric(pos, tan)) < tol
+        flat = rt.asarray(lay.pack(pos), torch.float64)                      # flat positions in the order of the SIGNAL layout
+        assert abs(lh.energy(flat) - oe) <= tol * abs(oe)

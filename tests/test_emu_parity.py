@@ -194,3 +194,7 @@ def test_nonpow2_model(rt, shape, dist, lh_kind, conv):
 
 def test_host_composed_matern(rt):
     pc.check_host_composed_matern(rt)
+
+
+def test_host_composed_scaling_leaf(rt):
+    pc.check_host_composed_scaling(rt)
