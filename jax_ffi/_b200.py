@@ -44,13 +44,13 @@ def available() -> bool:
 
 
 def register():
-    """``jax.ffi.register_ffi_target`` for the three handlers (idempotent)."""
+    """``jax.ffi.register_ffi_target`` for the handlers (idempotent)."""
     global _registered
     if _registered:
         return
     import jax
     lib = ctypes.CDLL(_LIB)
-    for name in ("nb200_jax_cf_apply", "nb200_jax_cf_adjoint", "nb200_jax_cf_adjoint_xi"):
+    for name in ("nb200_jax_cf_apply", "nb200_jax_cf_adjoint", "nb200_jax_cf_adjoint_xi", "nb200_jax_hartley", "nb200_jax_hartley_chirpz"):
         jax.ffi.register_ffi_target(name, jax.ffi.pycapsule(getattr(lib, name)), platform="CUDA")
     _registered = True
 
@@ -99,3 +99,38 @@ def make_correlated_field(plan_handle: int, grid_shape, n_bins: int, offset: flo
         return cf(amp, xi), lin_in_amp(xi, damp) + lin_in_xi(amp, dxi)
 
     return cf
+
+
+def make_hartley(plan_handle: int, grid_shape, dtype=np.float64, *, chirpz_tables=None, padded_shape=None):
+    """The ``hartley(p, axes=all)`` seam (nifty/re/correlated_field.py:24-30, bound with ``partial`` at :865) as a JAX function:
+    assign the result to ``nifty.re.correlated_field.hartley`` (or pass it where ``finalize`` binds it) before ``finalize()``.
+
+    The transform is linear and self-adjoint, so one ``linear_call`` whose transpose is the function itself gives jit, vmap,
+    jvp / linearize and linear_transpose.  ``chirpz_tables`` (device array of the per-axis chirp / filter tables,
+    ``nifty_b200.BluesteinHartley(...)._tab``) and ``padded_shape`` select the chirp-z form for extents that are not powers of
+    two; ``plan_handle`` is then the plan of the PADDED grid."""
+    import jax
+    from jax.custom_derivatives import linear_call
+
+    register()
+    grid_shape = tuple(int(s) for s in grid_shape)
+    rank = len(grid_shape)
+    item_bytes = int(np.prod(grid_shape)) * np.dtype(dtype).itemsize
+    attrs = dict(plan=np.int64(plan_handle), grid_rank=np.int64(rank), item_bytes=np.int64(item_bytes))
+
+    def _raw(x):
+        out = jax.ShapeDtypeStruct(x.shape, x.dtype)
+        if chirpz_tables is None:
+            return jax.ffi.ffi_call("nb200_jax_hartley", out, vmap_method="broadcast_all")(x, **attrs)
+        n = (1,) * (3 - rank) + grid_shape
+        work = jax.ShapeDtypeStruct((2 * int(np.prod(padded_shape)),), x.dtype)
+        res, _ = jax.ffi.ffi_call("nb200_jax_hartley_chirpz", (out, work), vmap_method="broadcast_all")(
+            chirpz_tables, x, n0=np.int64(n[0]), n1=np.int64(n[1]), n2=np.int64(n[2]), **attrs)
+        return res
+
+    def hartley(p, axes=None):
+        if axes is not None and tuple(sorted(a % p.ndim for a in axes)) != tuple(range(p.ndim - rank, p.ndim)):
+            raise NotImplementedError("the device transform acts on all axes of the grid")
+        return linear_call(lambda _, x: _raw(x), lambda _, c: _raw(c), (), p)
+
+    return hartley

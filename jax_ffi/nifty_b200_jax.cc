@@ -83,6 +83,35 @@ ffi::Error CfAdjointXiImpl(cudaStream_t stream, int64_t plan, int64_t grid_rank,
                                              xi_bar->untyped_data(), nullptr, K, batch));
 }
 
+// hartley(p) -- the module attribute bound at finalize() (nifty/re/correlated_field.py:24-30, :865).  Linear and self-adjoint: the
+// JVP rule and the transpose rule of the Python side are this same target.  Batch axes (vmap) are looped: one transform per item.
+ffi::Error HartleyImpl(cudaStream_t stream, int64_t plan, int64_t grid_rank, int64_t item_bytes, ffi::AnyBuffer in,
+                       ffi::Result<ffi::AnyBuffer> out) {
+  const int64_t batch = batch_of(in, (size_t)grid_rank);
+  const char* src = static_cast<const char*>(in.untyped_data());
+  char* dst = static_cast<char*>(out->untyped_data());
+  for (int64_t b = 0; b < batch; ++b) {
+    int rc = nb200_hartley(plan_of(plan), stream, src + b * item_bytes, dst + b * item_bytes);
+    if (rc != 0) return status(rc);
+  }
+  return ffi::Error::Success();
+}
+
+// the same seam on a grid whose extents are not powers of two: chirp-z around the padded plan (nb200_hartley_chirpz).  `tab` and
+// `work` are device buffers the Python side allocates once (tables) / per call (scratch, an extra XLA result that is dropped).
+ffi::Error HartleyChirpzImpl(cudaStream_t stream, int64_t plan, int64_t grid_rank, int64_t item_bytes, int64_t n0, int64_t n1, int64_t n2,
+                             ffi::AnyBuffer tab, ffi::AnyBuffer in, ffi::Result<ffi::AnyBuffer> out, ffi::Result<ffi::AnyBuffer> work) {
+  const int64_t batch = batch_of(in, (size_t)grid_rank);
+  const int64_t n[3] = {n0, n1, n2};
+  const char* src = static_cast<const char*>(in.untyped_data());
+  char* dst = static_cast<char*>(out->untyped_data());
+  for (int64_t b = 0; b < batch; ++b) {
+    int rc = nb200_hartley_chirpz(plan_of(plan), stream, n, tab.untyped_data(), src + b * item_bytes, work->untyped_data(), dst + b * item_bytes);
+    if (rc != 0) return status(rc);
+  }
+  return ffi::Error::Success();
+}
+
 }  // namespace
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(nb200_jax_cf_apply, CfApplyImpl,
@@ -114,6 +143,29 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(nb200_jax_cf_adjoint_xi, CfAdjointXiImpl,
                                   .Arg<ffi::AnyBuffer>()    // amp
                                   .Arg<ffi::AnyBuffer>()    // cot
                                   .Ret<ffi::AnyBuffer>());  // xi_bar
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(nb200_jax_hartley, HartleyImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("plan")
+                                  .Attr<int64_t>("grid_rank")
+                                  .Attr<int64_t>("item_bytes")
+                                  .Arg<ffi::AnyBuffer>()    // in
+                                  .Ret<ffi::AnyBuffer>());  // out
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(nb200_jax_hartley_chirpz, HartleyChirpzImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("plan")
+                                  .Attr<int64_t>("grid_rank")
+                                  .Attr<int64_t>("item_bytes")
+                                  .Attr<int64_t>("n0")
+                                  .Attr<int64_t>("n1")
+                                  .Attr<int64_t>("n2")
+                                  .Arg<ffi::AnyBuffer>()    // tab
+                                  .Arg<ffi::AnyBuffer>()    // in
+                                  .Ret<ffi::AnyBuffer>()    // out
+                                  .Ret<ffi::AnyBuffer>());  // work (scratch)
 
 extern "C" int nb200_jax_ffi_available() { return 1; }
 
