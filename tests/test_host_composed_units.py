@@ -68,3 +68,31 @@ def test_differentiable_model_call(rt):
     want = lh.left_sqrt_metric({k: v.detach() for k, v in p.items()}, c)
     for k in p:
         np.testing.assert_allclose(p[k].grad.numpy(), want[k].numpy(), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("subs", [[((6, 10), 0.3)], [((8,), 0.5), ((3, 4), 0.25)]])
+def test_float32_host_composed_metric(rt, subs):
+    """float32 models of both host-composed families: the metric against the float64 oracle at single-precision accuracy."""
+    kw = dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05))
+    ocf = oracle.CorrelatedFieldOracle("cf")
+    cfm = nb.CorrelatedFieldMaker("cf", runtime=rt, dtype=torch.float32)
+    for m in (ocf, cfm):
+        m.set_amplitude_total_offset(0.1, (0.2, 0.1))
+        for i, (shp, d) in enumerate(subs):
+            m.add_fluctuations(shp, d, prefix=f"s{i}", **kw)
+    ocf.finalize()
+    cf = cfm.finalize()
+    shape = sum((tuple(s[0]) for s in subs), ())
+    osig = oracle.SignalOracle(ocf, "exp")
+    lay = oracle.Layout(osig.domain)
+    rng = np.random.default_rng(0)
+    pos, tan = lay.random(rng), lay.random(rng)
+    pos = {k: 0.5 * v for k, v in pos.items()}
+    data = osig(pos) + 0.3 * rng.standard_normal(shape)
+    olh = oracle.GaussianOracle(data, 1 / 0.09, osig)
+    lh = nb.Gaussian(data, noise_cov_inv=1 / 0.09).amend(nb.SignalModel(cf, "exp"))
+    got = lh.metric({k: torch.as_tensor(v) for k, v in pos.items()}, {k: torch.as_tensor(v) for k, v in tan.items()})
+    want = olh.metric(pos, tan)
+    scale = max(np.abs(v).max() for v in want.values())
+    assert all(got[k].dtype == torch.float32 for k in got)
+    assert max(np.abs(got[k].numpy() - want[k]).max() for k in want) / scale < 2e-5
