@@ -193,6 +193,17 @@ class BluesteinCorrelatedField(LazyModel):
         a = _eval_amplitude(self._spec, self._tabs, p)
         return z, torch.cat((a[:1], a[1:] / z))
 
+    def amplitude(self, pos) -> torch.Tensor:
+        """``CorrelatedFieldMaker.amplitude`` (:824-838): ``[azm V, amp_1, ..., amp_{K-1}]``."""
+        p = self._tree(pos)
+        z = self._azm(p[self.prefix + "zeromode"])
+        a = _eval_amplitude(self._spec, self._tabs, p)
+        return torch.cat((a[:1] * z, a[1:]))
+
+    def power_spectrum(self, pos) -> torch.Tensor:
+        """``CorrelatedFieldMaker.power_spectrum`` (:840-845): ``amplitude(p) ** 2``."""
+        return self.amplitude(pos) ** 2
+
     @property
     def normalized_amplitudes(self):
         return ((lambda pos: self._normalized(self._tree(pos))[1]),)

@@ -388,6 +388,13 @@ class OuterCorrelatedField(LazyModel):
             nas.append(torch.cat((a[:1], a[1:] / z)))                    # get_normalized_amplitudes (:807-821)
         return z, nas
 
+    def amplitude(self, pos):
+        """correlated_field.py:824-833: with more than one spectrum only the relative scales are determined."""
+        raise NotImplementedError("If more than one spectrum is present in the model, no unique set of amplitudes exist because only the "
+                                  "relative scale is determined.")
+
+    power_spectrum = amplitude
+
     @property
     def normalized_amplitudes(self):
         return tuple((lambda pos, i=i: self._normalized(self._tree(pos))[1][i]) for i in range(len(self._specs)))

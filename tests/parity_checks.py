@@ -619,6 +619,7 @@ def check_nonpow2_model(rt, shape=(6, 10), distances=(0.2, 0.3), lh_kind="gauss"
     tt = {k: torch.as_tensor(v) for k, v in tan.items()}
     assert rel_err(t2n(cf(tp)), ocf(pos)) < tol
     assert rel_err(t2n(cf.normalized_amplitudes[0](tp)), ocf.normalized_amplitudes(pos)[0]) < 1e-12
+    assert rel_err(t2n(cfm.amplitude(tp)), ocf.amplitude(pos)) < 1e-12 and rel_err(t2n(cfm.power_spectrum(tp)), ocf.amplitude(pos) ** 2) < 1e-12
     if lh_kind == "gauss":
         data = osig(pos) + 0.3 * rng.standard_normal(shape)
         olh = oracle.GaussianOracle(data, 1.0 / 0.09, osig)
