@@ -208,6 +208,40 @@ class CorrelatedFieldMaker:
     def get_normalized_amplitudes(self):
         return self._finalized().normalized_amplitudes
 
+    @property
+    def amplitude_total_offset(self):
+        """correlated_field.py:785-791: the log-normal amplitude of the total offset as a callable of the latent position."""
+        if self._azm is None:
+            raise NotImplementedError("You need to set the `amplitude_total_offset` first")
+        a, b = self._azm.ab()
+        key = self._prefix + "zeromode"
+
+        def azm(pos):
+            pos = getattr(pos, "tree", pos)
+            if isinstance(pos, torch.Tensor):
+                pos = self._finalized().layout.unpack(pos)
+            return torch.exp(a + b * torch.as_tensor(pos[key], dtype=torch.float64).reshape(()))
+        return azm
+
+    @property
+    def azm(self):
+        """Alias for `amplitude_total_offset` (:793-796)."""
+        return self.amplitude_total_offset
+
+    @property
+    def fluctuations(self):
+        """correlated_field.py:798-805: the un-normalised amplitudes, one callable per sub-grid (``[0] = V``); evaluated by the
+        finalised model (its amplitude chain lives on the device), so available after ``finalize()``."""
+        nas, azm = self._finalized().normalized_amplitudes, self.amplitude_total_offset
+
+        def make(na):
+            def fluct(pos):
+                a = na(pos)
+                z = azm(pos).to(device=a.device, dtype=a.dtype)
+                return torch.cat((a[:1], a[1:] * z))
+            return fluct
+        return tuple(make(na) for na in nas)
+
     def finalize(self) -> CorrelatedField:
         self._cf = self._finalize()
         return self._cf

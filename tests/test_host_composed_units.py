@@ -96,3 +96,29 @@ def test_float32_host_composed_metric(rt, subs):
     scale = max(np.abs(v).max() for v in want.values())
     assert all(got[k].dtype == torch.float32 for k in got)
     assert max(np.abs(got[k].numpy() - want[k]).max() for k in want) / scale < 2e-5
+
+
+@pytest.mark.parametrize("subs", [[((16, 8), 0.3)], [((6, 10), 0.3)], [((8,), 0.5), ((3, 4), 0.25)]])
+def test_maker_accessors(rt, subs):
+    """`CorrelatedFieldMaker.azm` / `amplitude_total_offset` / `fluctuations` (correlated_field.py:785-805) on the fused and on both
+    host-composed model families against the oracle's amplitude models."""
+    kw = dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05))
+    ocf = oracle.CorrelatedFieldOracle("cf")
+    cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+    with pytest.raises(NotImplementedError):
+        cfm.azm
+    for m in (ocf, cfm):
+        m.set_amplitude_total_offset(0.1, (0.2, 0.1))
+        for i, (shp, d) in enumerate(subs):
+            m.add_fluctuations(shp, d, prefix=f"s{i}", **kw)
+    ocf.finalize()
+    cfm.finalize()
+    lay = oracle.Layout(ocf.domain)
+    pos = lay.random(np.random.default_rng(1))
+    tp = {k: torch.as_tensor(v) for k, v in pos.items()}
+    assert len(cfm.fluctuations) == len(subs)
+    for f, oa in zip(cfm.fluctuations, ocf.amps):
+        np.testing.assert_allclose(f(tp).numpy(), oa(pos), rtol=1e-12)
+    a, b = nb.lognormal_moments(0.2, 0.1) if hasattr(nb, "lognormal_moments") else (None, None)
+    z = float(cfm.amplitude_total_offset(tp))
+    assert z > 0 and abs(z - float(cfm.azm(tp))) == 0.0
