@@ -40,19 +40,21 @@ def fourier_mode_tables(shape, distances, uniqueness_rtol=1e-12):
     shape = tuple(int(s) for s in shape)
     distances = tuple(np.broadcast_to(distances, (len(shape),)).astype(np.float64))
     step = 1.0 / (np.array(shape) * np.array(distances))
-    m = np.arange(shape[0])
-    m = np.minimum(m, shape[0] - m) * step[0]
+    # the length of mode i along an axis is min(i, n - i) * step: every value of the full grid occurs on the FOLDED index range
+    # [0, n // 2] per axis, so lengths, unique values and bins are computed there (same arithmetic, a fraction of the elements) and
+    # expanded by indexing with the folded index of every grid point
+    fold = [np.minimum(np.arange(n), n - np.arange(n)) for n in shape]
+    m = np.arange(shape[0] // 2 + 1) * step[0]
     if len(shape) != 1:
         m = m * m
         for i in range(1, len(shape)):
-            t = np.arange(shape[i])
-            t = np.minimum(t, shape[i] - t) * step[i]
+            t = np.arange(shape[i] // 2 + 1) * step[i]
             m = np.expand_dims(m, axis=-1) + t * t
         m = np.sqrt(m)
     um = np.unique(m)
     tol = uniqueness_rtol * um[-1]
     um = um[np.diff(np.append(um, 2 * um[-1])) > tol]
-    idx = np.searchsorted(0.5 * (um[:-1] + um[1:]), m)
+    idx = np.searchsorted(0.5 * (um[:-1] + um[1:]), m)[np.ix_(*fold)]
     cnt = np.bincount(idx.ravel(), minlength=um.size)
     if np.any(cnt == 0) or um.shape != cnt.shape:
         raise RuntimeError("invalid harmonic mode(s) encountered")
