@@ -25,8 +25,6 @@ share all of this.
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import numpy as np
 import torch
 
