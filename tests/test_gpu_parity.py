@@ -158,49 +158,3 @@ def test_hartley_vs_torch_fft_large(rt):
                                                  ("square_plus", "gauss", (8, 8, 16))])
 def test_custom_pointwise_nonlinearity(rt, which, lh_kind, shape):
     pc.check_custom_nonlinearity(rt, shape, 0.1, lh_kind=lh_kind, which=which)
-
-
-@pytest.mark.parametrize("shapes,lh_kind,conv", [(((8, 16), (4,)), "gauss", "non_canonical_hartley"),
-                                                 (((16,), (8, 8)), "poisson", "canonical_hartley"),
-                                                 (((6, 5), (3,)), "poisson", "non_canonical_hartley"),
-                                                 (((4, 2), (3, 2)), "gauss", "non_canonical_hartley")])
-def test_outer_product_of_two_subgrids(rt, shapes, lh_kind, conv):
-    pc.check_outer_product(rt, shapes=shapes, lh_kind=lh_kind, conv=conv)
-
-
-@pytest.mark.parametrize("name", ["o_8x16_x_4", "o_16_x_8x8", "o_3x3_x_6", "o_6_x_3x3", "o_6_x_6", "o_4_x_6_x_8", "o_3x3_x_3x3"])
-def test_outer_product_golden(rt, name):
-    pc.check_outer_golden(rt, name)
-
-
-@pytest.mark.parametrize("shape", [(3,), (6,), (3, 3), (6, 7), (5, 12), (3, 5, 7), (100, 37), (1000, 3), (33, 65, 9), (1, 5)])
-def test_nonpow2_hartley(rt, shape):
-    pc.check_nonpow2_hartley(rt, shape)
-
-
-def test_nonpow2_hartley_float32_and_errors(rt):
-    pc.check_nonpow2_hartley(rt, (12, 7), dtype=torch.float32)
-    pc.check_nonpow2_errors(rt)
-
-
-@pytest.mark.parametrize("name", ["g2d_3x3", "m2d_3x3"])
-def test_nonpow2_golden_3x3(rt, name):
-    pc.check_nonpow2_golden(rt, name)
-
-
-def test_reference_cf_cases(rt):
-    pc.check_reference_cf_cases(rt)
-
-
-@pytest.mark.parametrize("shape,dist,lh_kind,conv", [((6, 10), (0.2, 0.3), "gauss", "non_canonical_hartley"),
-                                                     ((5, 3, 6), 0.4, "poisson", "canonical_hartley"), ((12,), 0.4, "gauss", "non_canonical_hartley")])
-def test_nonpow2_model(rt, shape, dist, lh_kind, conv):
-    pc.check_nonpow2_model(rt, shape, dist, lh_kind, conv)
-
-
-def test_host_composed_matern(rt):
-    pc.check_host_composed_matern(rt)
-
-
-def test_host_composed_scaling_leaf(rt):
-    pc.check_host_composed_scaling(rt)

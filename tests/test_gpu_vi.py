@@ -167,11 +167,6 @@ def test_reduce_pieces(rt):
     vc.check_reduce_pieces(rt, "g3d_8x8x8")
 
 
-@pytest.mark.parametrize("which,lh_kind", [("nonpow2", "gauss"), ("outer", "gauss"), ("nonpow2", "poisson"), ("outer", "poisson")])
-def test_host_composed_fields_through_the_vi_drivers(rt, which, lh_kind):
-    vc.check_host_composed_vi(rt, which, lh_kind)
-
-
 @pytest.mark.parametrize("sample_mode,point_estimates", [("nonlinear_resample", ()), ("linear_resample", ()),
                                                          ("nonlinear_resample", ("cfax1fluctuations", "cfzeromode")),
                                                          ("linear_resample", ("cfax1spectrum",))])
@@ -179,15 +174,5 @@ def test_sample_consistency(rt, sample_mode, point_estimates):
     vc.check_sample_consistency(rt, sample_mode, point_estimates)
 
 
-def test_sample_consistency_and_constants_host_composed(rt):
-    lh = vc._host_composed_pair(rt, "nonpow2", "gauss")[0]
-    vc.check_sample_consistency(rt, "nonlinear_resample", ("cfax1loglogavgslope",), lh=lh)
-    vc.check_constants_do_not_move(rt, ("cfax1fluctuations",), lh=lh)
-
-
 def test_constants_do_not_move(rt):
     vc.check_constants_do_not_move(rt)
-
-
-def test_host_composed_wiener_filter_and_slq(rt):
-    vc.check_host_composed_wiener_and_elbo(rt, "nonpow2")
