@@ -68,6 +68,10 @@ OUTER_CASES = {
     "o_3x3_x_3x3": dict(shapes=((3, 3), (3, 3)), distances=((0.1, 0.1), (0.1, 0.1)), offset_mean=0.0, offset_std=(0.1, 0.1), seed=42,
                         fluct=(dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)),
                                dict(fluctuations=(1.0, 0.1), loglogavgslope=(-1.0, 0.1), flexibility=(1.0, 0.1), asperity=(0.2, 2e-2)))),
+    # a Matern sub-grid inside an outer product (Matern x non-parametric; cl's add_fluctuations_matern = re's kind "amplitude", no renormalisation)
+    "o_m8_x_3x4": dict(shapes=((8,), (3, 4)), distances=((0.5,), (0.25, 0.25)), offset_mean=0.1, offset_std=(0.2, 0.1), seed=13,
+                       fluct=(dict(matern=dict(scale=(1.0, 0.5), cutoff=(1.0, 0.5), loglogslope=(-3.0, 0.5))),
+                              dict(fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05)))),
 }
 
 
@@ -75,7 +79,10 @@ def build_outer(c, maker):
     """Two `add_fluctuations` on a `CorrelatedFieldOracle("cf")` / `nb.CorrelatedFieldMaker("cf", ...)` (same call protocol)."""
     maker.set_amplitude_total_offset(c["offset_mean"], c["offset_std"])
     for i, (shp, dist, f) in enumerate(zip(c["shapes"], c["distances"], c["fluct"])):
-        maker.add_fluctuations(shp, dist, prefix=f"space{i}", non_parametric_kind="power", **f)
+        if "matern" in f:
+            maker.add_fluctuations_matern(shp, dist, renormalize_amplitude=False, prefix=f"space{i}", non_parametric_kind="amplitude", **f["matern"])
+        else:
+            maker.add_fluctuations(shp, dist, prefix=f"space{i}", non_parametric_kind="power", **f)
     return maker.finalize()
 
 

@@ -162,7 +162,7 @@ def test_outer_product_of_two_subgrids(rt, shapes, lh_kind, conv):
     pc.check_outer_product(rt, shapes=shapes, lh_kind=lh_kind, conv=conv)
 
 
-@pytest.mark.parametrize("name", ["o_8x16_x_4", "o_16_x_8x8", "o_3x3_x_6", "o_6_x_3x3", "o_6_x_6", "o_4_x_6_x_8", "o_3x3_x_3x3"])
+@pytest.mark.parametrize("name", ["o_8x16_x_4", "o_16_x_8x8", "o_3x3_x_6", "o_6_x_3x3", "o_6_x_6", "o_4_x_6_x_8", "o_3x3_x_3x3", "o_m8_x_3x4"])
 def test_outer_product_golden(rt, name):
     pc.check_outer_golden(rt, name)
 
