@@ -88,6 +88,8 @@ class Likelihood:
         from .bluestein import BluesteinCorrelatedField
         from .outer import OuterCorrelatedField, OuterLikelihood
         composed = (OuterCorrelatedField, BluesteinCorrelatedField)      # host-composed models (outer.py, bluestein.py)
+        if getattr(self, "cov_inv_fn", None) is not None and (isinstance(signal, composed) or isinstance(getattr(signal, "cf", None), composed)):
+            raise NotImplementedError("non-diagonal noise covariances are not available on host-composed fields")
         if isinstance(signal, composed):
             return OuterLikelihood(self, signal, "identity")
         if isinstance(signal, SignalModel) and isinstance(signal.cf, composed):
@@ -95,6 +97,8 @@ class Likelihood:
                                    scaling=signal.scaling, scaling_key=signal.scaling_key)
         if isinstance(signal, CorrelatedField):
             signal = SignalModel(signal, "identity")
+        if isinstance(signal, SignalModel) and getattr(self, "cov_inv_fn", None) is not None:
+            return OperatorLikelihood(self, signal)
         if not isinstance(signal, SignalModel):
             raise NotImplementedError(
                 "the B200 path implements likelihoods on a correlated field followed by a pointwise map: amend with a "
@@ -104,10 +108,12 @@ class Likelihood:
 
 
 class Gaussian(Likelihood):
-    """``jft.Gaussian(data, noise_cov_inv=None, noise_std_inv=None)`` with a DIAGONAL inverse covariance.
+    """``jft.Gaussian(data, noise_cov_inv=None, noise_std_inv=None)`` (likelihood_impl.py:35-138).
 
-    ``noise_cov_inv`` may be a scalar, an array, or (as in the reference) a callable ``x -> w * x``;
-    callables are probed once with ones to extract the diagonal (likelihood_impl.py:35-80).
+    ``noise_cov_inv`` may be a scalar, an array, or (as in the reference) a callable.  Diagonal callables ``x -> w * x`` are
+    recognised by probing and run on the fused path; any other (symmetric) operator is applied on the host side between the
+    device JVP and VJP of the model (:class:`OperatorLikelihood`); its ``noise_std_inv`` is needed for the sqrt-metrics,
+    ``transformation`` and ``normalized_residual`` (sample draws), not for energy / gradient / metric.
     """
     kind = 0
 
@@ -120,20 +126,30 @@ class Gaussian(Likelihood):
             w = noise_cov_inv
         else:
             w = noise_std_inv
+        self.cov_inv_fn = self.std_inv_fn = None
         if callable(w):
-            # only DIAGONAL operators are supported: the diagonal is read off a vector of ones and the
-            # callable is then checked on two random probes -- anything that is not `x -> diag * x` raises instead of being
-            # silently treated as diagonal
+            # a callable is probed: the diagonal is read off a vector of ones and checked on two random probes.  `x -> diag * x`
+            # takes the fused path (weights inside the axis-0 pass); anything else is kept as an OPERATOR and applied between the
+            # device JVP and VJP of the model (OperatorLikelihood below) -- never silently treated as diagonal
             fn = w
             w = fn(torch.ones(shape, dtype=torch.float64))
             gen = torch.Generator().manual_seed(12345)
+            diagonal = True
             for _ in range(2):
                 probe = torch.randn(shape, dtype=torch.float64, generator=gen)
                 got = torch.as_tensor(fn(probe), dtype=torch.float64)
                 want = torch.as_tensor(w, dtype=torch.float64) * probe
                 if got.shape != want.shape or not torch.allclose(got, want, rtol=1e-10, atol=1e-12 * float(want.abs().max() + 1e-300)):
-                    raise NotImplementedError("Gaussian: the noise covariance callable is not a diagonal operator; only diagonal "
-                                              "(inverse) covariances are supported on the B200 path")
+                    diagonal = False
+            if not diagonal:
+                if noise_cov_inv is None:
+                    raise NotImplementedError("Gaussian: a non-diagonal `noise_std_inv` needs `noise_cov_inv` as well (the reference would "
+                                              "assume a diagonal covariance here, likelihood_impl.py:46-55)")
+                if noise_std_inv is not None and not callable(noise_std_inv):
+                    raise NotImplementedError("Gaussian: a non-diagonal `noise_cov_inv` needs a callable `noise_std_inv` (or none)")
+                self.cov_inv_fn, self.std_inv_fn = noise_cov_inv, noise_std_inv
+                self.w_scalar, self.w_array = 1.0, None
+                return
         if noise_cov_inv is None and noise_std_inv is not None:
             w = w * w
         if np.ndim(w) == 0 if not isinstance(w, torch.Tensor) else w.ndim == 0:
@@ -330,3 +346,109 @@ class LikelihoodWithModel:
     def signal_response(self, pos):
         lin, _ = self.lin_at(pos)
         return lin.signal()
+
+
+class OpLin:
+    """Linearisation of ``Gaussian(non-diagonal N^-1)`` on ``signal = nl(cf)``: the device :class:`Lin` supplies the signal and
+    the field-level JVP / VJP (``nb200_rsm`` / ``nb200_lsm`` with ``scaled = 0``), the covariance operators are applied between
+    them on the host side (likelihood_impl.py:124-138 through likelihood.py:599-633).  Same flat-vector interface as ``Lin``; CG
+    solves on such operators run the host loop."""
+
+    host_composed = True
+
+    def __init__(self, lh: "OperatorLikelihood"):
+        self.lh, self.rt = lh, lh.rt
+        self.dev = Lin(lh.handle)
+        self.model = self.dev.model
+        self.s = self._nr = self._energy = None
+
+    def _js(self, t):
+        jf = self.dev.rsm(t, scaled=False)
+        return self.s * jf if self.lh.exp else jf
+
+    def _jst(self, c):
+        return self.dev.lsm((self.s * c if self.lh.exp else c).contiguous(), scaled=False)
+
+    def update(self, pos, want_grad=False, add_prior=False):
+        pos = self.lh.signal.as_flat(pos)
+        self.dev.update(pos)
+        self.s = self.dev.signal()
+        r = self.s - self.lh.data_t
+        self._nr = self.lh.cov_inv(r)
+        self._energy = 0.5 * float(torch.sum(r * self._nr))
+        if not want_grad:
+            return None
+        g = self._jst(self._nr)
+        return g + pos if add_prior else g
+
+    def energy(self) -> float:
+        return self._energy
+
+    def signal(self):
+        return self.s
+
+    def metric(self, t, add_identity=False, out=None):
+        r = self._jst(self.lh.cov_inv(self._js(t)))
+        if add_identity:
+            r = r + t
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
+
+    def rsm(self, t, scaled=True):
+        return self.lh.std_inv(self._js(t)) if scaled else self.dev.rsm(t, scaled=False)
+
+    def lsm(self, u, scaled=True):
+        u = self.rt.asarray(u, self.lh.dtype)
+        return self._jst(self.lh.std_inv(u)) if scaled else self.dev.lsm(u, scaled=False)
+
+    def metric_pair(self, other: "OpLin", t, add_identity=False):
+        r = self.lsm(other.rsm(t))
+        return r + t if add_identity else r
+
+    def transformation(self):
+        return self.lh.std_inv(self.s)
+
+    def normalized_residual(self):
+        return self.lh.std_inv(self.lh.data_t - self.s)
+
+
+class OperatorLikelihood(LikelihoodWithModel):
+    """``Gaussian(data, noise_cov_inv=<operator>, noise_std_inv=<operator>).amend(signal)`` for covariances that are not diagonal."""
+
+    def __init__(self, likelihood: Gaussian, signal: SignalModel):
+        if signal.nonlinearity not in ("exp", "identity") or signal.scaling is not None:
+            raise NotImplementedError("non-diagonal noise covariances: `signal` must be exp(cf) or cf (no scaling leaf, no custom map)")
+        if getattr(signal.cf.plan, "dist", False):
+            raise NotImplementedError("non-diagonal noise covariances are not available on slab-decomposed fields")
+        super().__init__(likelihood, signal)             # device model with unit weights: supplies the signal and the field JVP / VJP
+        self.exp = signal.nonlinearity == "exp"
+        self.data_t = self.rt.asarray(likelihood.data, self.dtype).reshape(signal.target_shape)
+        self._cov_fn, self._std_fn = likelihood.cov_inv_fn, likelihood.std_inv_fn
+
+    def cov_inv(self, x):
+        return torch.as_tensor(self._cov_fn(x), dtype=self.dtype, device=self.rt.device)
+
+    def std_inv(self, x):
+        if self._std_fn is None:
+            raise NotImplementedError("this operation needs `noise_std_inv` (the square root of the non-diagonal inverse covariance)")
+        return torch.as_tensor(self._std_fn(x), dtype=self.dtype, device=self.rt.device)
+
+    def new_lin(self) -> OpLin:
+        return OpLin(self)
+
+    def lin_at(self, pos, want_grad=False, add_prior=False):
+        flat = self.signal.as_flat(pos)
+        key = self._key(flat)
+        if not want_grad:
+            for k, lin in self._lins:
+                if k == key:
+                    return lin, None
+        lin = OpLin(self)
+        grad = lin.update(flat, want_grad=want_grad, add_prior=add_prior)
+        lin._pos_ref = flat
+        self._lins.append((key, lin))
+        if len(self._lins) > self._max_lins:
+            self._lins.pop(0)
+        return lin, grad

@@ -785,3 +785,68 @@ def check_host_composed_scaling(rt, tol=1e-10):
         assert rel_err(t2n(lh.right_sqrt_metric(tp, tt)), olh.right_sqrt_metric(pos, tan)) < tol
         flat = rt.asarray(lay.pack(pos), torch.float64)                      # flat positions in the order of the SIGNAL layout
         assert abs(lh.energy(flat) - oe) <= tol * abs(oe)
+
+
+def check_operator_gaussian(rt, shape=(8, 8), lh_nl="exp", seed=17):
+    """`Gaussian(data, noise_cov_inv=<non-diagonal operator>, noise_std_inv=<its square root>)` (likelihood_impl.py:35-138 accepts
+    arbitrary callables) on the fused model: energy, gradient, metric, sqrt-metrics, transformation, residual and an MGVI draw
+    against DENSE linear algebra built from the oracle's signal Jacobian."""
+    c = dict(shape=shape, distances=1.0 / shape[0], offset_mean=0.1, offset_std=(0.2, 0.1), fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3),
+             flexibility=(1.0, 0.5), asperity=(0.5, 0.05), lh="gauss")
+    from golden_util import build_oracle
+    ocf = build_oracle(c)
+    osig = oracle.SignalOracle(ocf, lh_nl)
+    lay = oracle.Layout(osig.domain)
+    rng = np.random.default_rng(seed)
+    nd, L = int(np.prod(shape)), lay.size
+    B = rng.standard_normal((nd, nd))
+    Ninv = B @ B.T / nd + 2.0 * np.eye(nd)                       # symmetric positive definite, couples every pair of pixels
+    ev, U = np.linalg.eigh(Ninv)
+    Nsq = (U * np.sqrt(ev)) @ U.T                                # symmetric square root
+    tN, tS = torch.as_tensor(Ninv), torch.as_tensor(Nsq)
+
+    def op(m):            # device-agnostic callables: they are probed on the host and applied to device tensors later
+        return lambda x: (m.to(device=x.device, dtype=x.dtype) @ x.reshape(-1)).reshape(x.shape)
+
+    pos, tan = lay.random(rng), lay.random(rng)
+    pos = {k: 0.3 * v for k, v in pos.items()}
+    data = osig(pos) + 0.3 * rng.standard_normal(shape)
+    lh = nb.Gaussian(data, noise_cov_inv=op(tN), noise_std_inv=op(tS)).amend(nb.SignalModel(build_product(c, rt), lh_nl))
+    assert isinstance(lh, nb.OperatorLikelihood) and isinstance(lh, nb.LikelihoodWithModel)
+    pv, tv = lay.pack(pos), lay.pack(tan)
+    J = np.stack([osig.jvp(pos, lay.unpack(e)).reshape(-1) for e in np.eye(L)], axis=1)          # nd x L
+    s = osig(pos).reshape(-1)
+    r = s - data.reshape(-1)
+    tp, tt = rt.asarray(pv, torch.float64), rt.asarray(tv, torch.float64)
+    tol = 1e-10
+    e, g = lh.energy_and_gradient(tp)
+    assert abs(e - 0.5 * r @ Ninv @ r) <= tol * abs(e)
+    assert rel_err(t2n(g), J.T @ Ninv @ r) < tol
+    M = J.T @ Ninv @ J
+    assert rel_err(t2n(lh.metric(tp, tt)), M @ tv) < tol
+    u = rng.standard_normal(shape)
+    assert rel_err(t2n(lh.left_sqrt_metric(tp, u)), J.T @ Nsq @ u.reshape(-1)) < tol
+    assert rel_err(t2n(lh.right_sqrt_metric(tp, tt)).reshape(-1), Nsq @ J @ tv) < tol
+    assert rel_err(t2n(lh.transformation(tp)).reshape(-1), Nsq @ s) < tol
+    assert rel_err(t2n(lh.normalized_residual(tp)).reshape(-1), Nsq @ (data.reshape(-1) - s)) < tol
+    # MGVI draw: (M + 1)^-1 (J^T N^-1/2 w_d + w_p) by CG (host loop) against the dense solve
+    wd, wp = rng.standard_normal(shape), rng.standard_normal(L)
+    res, info = nb.draw_linear_residual(lh, tp, 0, cg_kwargs=dict(resnorm=1e-10, maxiter=4 * L),
+                                        _white=(rt.asarray(wd, torch.float64), rt.asarray(wp, torch.float64)))
+    dense = np.linalg.solve(M + np.eye(L), J.T @ Nsq @ wd.reshape(-1) + wp)
+    assert info == 0 and rel_err(t2n(res), dense) < 1e-7
+    # one MGVI iteration of the standard driver on this likelihood: the KL decreases
+    kw = dict(n_samples=1, key=5, sample_mode="linear_resample", draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-8, maxiter=2 * L)),
+              kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=30))))
+    smp, st = nb.optimize_kl(lh, tp, n_total_iterations=1, **kw)
+    vi = nb.OptimizeVI(lh, 1)
+    e1, _ = vi.kl_value_and_grad(smp.pos, smp.residuals)
+    e0, _ = vi.kl_value_and_grad(tp, smp.residuals)
+    assert st.nit == 1 and np.isfinite(e1) and e1 < e0
+    # without the square root: energy / metric work, sqrt-metrics say what is missing
+    lh2 = nb.Gaussian(data, noise_cov_inv=op(tN)).amend(nb.SignalModel(build_product(c, rt), lh_nl))
+    assert rel_err(t2n(lh2.metric(tp, tt)), M @ tv) < tol
+    with pytest.raises(NotImplementedError, match="noise_std_inv"):
+        lh2.left_sqrt_metric(tp, u)
+    with pytest.raises(NotImplementedError):
+        nb.Gaussian(data, noise_std_inv=op(tS))                  # a non-diagonal square root alone

@@ -198,3 +198,8 @@ def test_host_composed_matern(rt):
 
 def test_host_composed_scaling_leaf(rt):
     pc.check_host_composed_scaling(rt)
+
+
+@pytest.mark.parametrize("shape,nl", [((8, 8), "exp"), ((4, 8, 4), "identity")])
+def test_gaussian_with_non_diagonal_covariance(rt, shape, nl):
+    pc.check_operator_gaussian(rt, shape, nl)

@@ -60,8 +60,8 @@ def test_mean_std_stack():
 
 
 def test_gaussian_callable_covariance_must_be_diagonal():
-    """`Gaussian(noise_cov_inv=callable)`: a diagonal operator is accepted (its diagonal is read off), anything else raises
-    instead of being silently treated as diagonal (likelihood_impl.py:35-80 accepts arbitrary callables; this path does not)."""
+    """`Gaussian(noise_cov_inv=callable)`: a diagonal operator is recognised (its diagonal is read off, fused path), anything else
+    is kept as an operator (likelihood_impl.py:35-80 accepts arbitrary callables) instead of being silently treated as diagonal."""
     import numpy as np
     import pytest
     import torch
@@ -72,8 +72,10 @@ def test_gaussian_callable_covariance_must_be_diagonal():
     assert lh.w_array is not None and torch.equal(torch.as_tensor(lh.w_array), w)
     lh = Gaussian(d, noise_std_inv=lambda x: 3.0 * x)
     assert torch.allclose(torch.as_tensor(lh.w_array), torch.full((4, 6), 9.0, dtype=torch.float64))
+    lh = Gaussian(d, noise_cov_inv=lambda x: x + torch.roll(x, 1, 1))      # couples neighbours: kept as an operator, never as a diagonal
+    assert lh.cov_inv_fn is not None and lh.w_array is None
     with pytest.raises(NotImplementedError):
-        Gaussian(d, noise_cov_inv=lambda x: x + torch.roll(x, 1, 1))          # couples neighbours
+        Gaussian(d, noise_std_inv=lambda x: x + torch.roll(x, 1, 1))      # a non-diagonal square root alone (the reference would assume a diagonal)
 
 
 def test_vector_and_model_containers():
