@@ -835,6 +835,11 @@ def check_operator_gaussian(rt, shape=(8, 8), lh_nl="exp", seed=17):
                                         _white=(rt.asarray(wd, torch.float64), rt.asarray(wp, torch.float64)))
     dense = np.linalg.solve(M + np.eye(L), J.T @ Nsq @ wd.reshape(-1) + wp)
     assert info == 0 and rel_err(t2n(res), dense) < 1e-7
+    # Wiener-filter posterior mean of the linearised problem (evi.py:399-476) against the dense solve
+    wf, (winfo, _) = nb.wiener_filter_posterior(lh, tp, key=5, n_samples=0, model_is_linear=False,
+                                                draw_linear_kwargs=dict(cg_kwargs=dict(resnorm=1e-10, maxiter=4 * L)))
+    wdense = np.linalg.solve(M + np.eye(L), J.T @ Ninv @ (data.reshape(-1) - s + J @ pv))
+    assert winfo == 0 and rel_err(t2n(wf.pos), wdense) < 1e-7
     # one MGVI iteration of the standard driver on this likelihood: the KL decreases
     kw = dict(n_samples=1, key=5, sample_mode="linear_resample", draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-8, maxiter=2 * L)),
               kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=30))))
