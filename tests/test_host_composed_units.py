@@ -122,3 +122,20 @@ def test_maker_accessors(rt, subs):
     a, b = nb.lognormal_moments(0.2, 0.1) if hasattr(nb, "lognormal_moments") else (None, None)
     z = float(cfm.amplitude_total_offset(tp))
     assert z > 0 and abs(z - float(cfm.azm(tp))) == 0.0
+
+
+def test_vmodel_over_host_composed_field(rt):
+    """`VModel(cf, n, in_axes="cfxi")` (model.py:370-417; test_empirical_power_spectrum.py:39) on a non-power-of-two field: the mapped
+    model equals the per-sample evaluations."""
+    cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+    cfm.set_amplitude_total_offset(0.3, (0.2, 0.1))
+    cfm.add_fluctuations((6, 5), 0.5, fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05), prefix="a")
+    cf = cfm.finalize()
+    vm = nb.VModel(cf, 3, in_axes="cfxi")
+    x = vm.init(11)
+    assert tuple(x["cfxi"].shape) == (3, 6, 5) and tuple(vm.target) == (3, 6, 5)
+    out = vm(x)
+    for i in range(3):
+        xi = dict(x)
+        xi["cfxi"] = x["cfxi"][i]
+        assert torch.equal(out[i], cf(xi))
