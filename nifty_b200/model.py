@@ -136,7 +136,7 @@ class WrappedCall(Model):
 
 class VModel(LazyModel):
     """``VModel(model, axis_size, in_axes=0, out_axes=0)`` (model.py:370-417): the model mapped over a leading sample axis of
-    (some of) its input leaves.  ``in_axes``: 0 (every leaf), a leaf name / names (those leaves only, e.g.
+    (some of) its input leaves.  ``in_axes``: an axis index (every leaf), a leaf name / names (those leaves only, e.g.
     ``VModel(cf, n, in_axes="cfxi")``: many excitation fields, one amplitude model -- test_empirical_power_spectrum.py:39) or a
     dict leaf -> 0 / None.  A :class:`~nifty_b200.correlated_field.CorrelatedField` with only its excitations mapped runs as ONE
     batched device call (``nb200_cf_apply_batch``, shared amplitude table); everything else is an in-order loop."""
@@ -146,14 +146,12 @@ class VModel(LazyModel):
             raise ValueError(f"Model {model} of invalid type")
         if not isinstance(axis_size, int) or axis_size <= 0:
             raise ValueError(f"invalid axis size {axis_size}")
-        if out_axes != 0:
-            raise NotImplementedError("out_axes other than 0 are not supported")
+        if not isinstance(out_axes, int):
+            raise ValueError(f"invalid `out_axes` {out_axes!r}")
         self.model, self.axis_size = model, axis_size
         dom = model.domain
         if isinstance(in_axes, int):
-            if in_axes != 0:
-                raise NotImplementedError("in_axes other than 0 / None are not supported")
-            axes = {k: 0 for k in dom}
+            axes = {k: in_axes for k in dom}
         else:
             if isinstance(in_axes, str):
                 in_axes = (in_axes,)
@@ -162,8 +160,17 @@ class VModel(LazyModel):
             if set(in_axes) - set(dom):
                 raise ValueError(f"Model domain structure {sorted(dom)} does not match axis structure {sorted(in_axes)}")
             axes = {k: in_axes.get(k) for k in dom}
-        self.in_axes, self.out_axes = axes, 0
-        self.domain = {k: ((axis_size,) + _shape_of(s) if axes[k] == 0 else _shape_of(s)) for k, s in dom.items()}
+        self.in_axes, self.out_axes = axes, out_axes
+
+        def with_axis(shape, a):
+            shape = tuple(shape)
+            if a is None:
+                return shape
+            if not -len(shape) - 1 <= a <= len(shape):
+                raise ValueError(f"sample axis {a} out of range for a leaf of shape {shape}")
+            a = a % (len(shape) + 1)
+            return shape[:a] + (axis_size,) + shape[a:]
+        self.domain = {k: with_axis(_shape_of(s), axes[k]) for k, s in dom.items()}
 
     def init(self, key):
         """Mapped leaves: one draw per sample from split keys, stacked (model.py:394-409); the others as in the model."""
@@ -171,18 +178,23 @@ class VModel(LazyModel):
         keys = random_split(key, self.axis_size + 1)
         base = self.model.init(keys[0])
         draws = [self.model.init(k) for k in keys[1:]]
-        return {k: (torch.stack([d[k] for d in draws]) if self.in_axes[k] == 0 else base[k]) for k in base}
+        return {k: (torch.stack([d[k] for d in draws], dim=self.in_axes[k]) if self.in_axes[k] is not None else base[k]) for k in base}
 
     @property
     def target(self):
         t = self.model.target
-        return (self.axis_size,) + tuple(t) if _is_shape(t) else t
+        if not _is_shape(t):
+            return t
+        t = tuple(t)
+        o = self.out_axes % (len(t) + 1)
+        return t[:o] + (self.axis_size,) + t[o:]
 
     def __call__(self, x):
         x = x.tree if isinstance(x, Vector) else x
-        mapped = [k for k, a in self.in_axes.items() if a == 0]
+        mapped = [k for k, a in self.in_axes.items() if a is not None]
         from .correlated_field import CorrelatedField
-        if isinstance(self.model, CorrelatedField) and mapped == [self.model.prefix + "xi"] and not self.model.plan.dist:
+        if (isinstance(self.model, CorrelatedField) and mapped == [self.model.prefix + "xi"] and not self.model.plan.dist
+                and self.in_axes[mapped[0]] == 0 and self.out_axes == 0):
             cf = self.model
             shared = {k: v for k, v in x.items() if k not in mapped}
             shared[mapped[0]] = torch.zeros(cf.domain[mapped[0]], dtype=cf.dtype, device=cf.rt.device)
@@ -190,6 +202,6 @@ class VModel(LazyModel):
             return cf.plan.cf_apply_batch(amp, x[mapped[0]], cf.offset_mean)
         outs = []
         for i in range(self.axis_size):
-            xi = {k: (v[i] if self.in_axes.get(k) == 0 else v) for k, v in x.items()}
+            xi = {k: (v.select(self.in_axes[k], i) if self.in_axes.get(k) is not None else v) for k, v in x.items()}
             outs.append(self.model(xi))
-        return torch.stack(outs)
+        return torch.stack(outs, dim=self.out_axes)

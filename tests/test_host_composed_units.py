@@ -139,3 +139,22 @@ def test_vmodel_over_host_composed_field(rt):
         xi = dict(x)
         xi["cfxi"] = x["cfxi"][i]
         assert torch.equal(out[i], cf(xi))
+
+
+def test_vmodel_axes(rt):
+    """Sample axes other than 0 (model.py:370-417 `in_axes` / `out_axes`): mapped leaf with its sample axis in the middle, output axis last."""
+    cfm = nb.CorrelatedFieldMaker("cf", runtime=rt)
+    cfm.set_amplitude_total_offset(0.3, (0.2, 0.1))
+    cfm.add_fluctuations((8, 4), 0.5, fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3), flexibility=(1.0, 0.5), asperity=(0.5, 0.05), prefix="a")
+    cf = cfm.finalize()
+    vm = nb.VModel(cf, 3, in_axes={"cfxi": 1}, out_axes=-1)
+    assert vm.domain["cfxi"] == (8, 3, 4) and vm.domain["cfzeromode"] == () and tuple(vm.target) == (8, 4, 3)
+    x = vm.init(2)
+    out = vm(x)
+    assert tuple(out.shape) == (8, 4, 3)
+    for i in range(3):
+        xi = dict(x)
+        xi["cfxi"] = x["cfxi"][:, i]
+        assert torch.equal(out[..., i], cf(xi))
+    with pytest.raises(ValueError):
+        nb.VModel(cf, 3, in_axes=1)                # scalar leaves have no axis 1
