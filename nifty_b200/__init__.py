@@ -24,4 +24,4 @@ from .evidence_lower_bound import estimate_evidence_lower_bound  # noqa: F401
 from .outer import OuterCorrelatedField, OuterLikelihood  # noqa: F401
 from .bluestein import BluesteinCorrelatedField, BluesteinHartley, fourier_mode_tables  # noqa: F401
 from . import lanczos  # noqa: F401
-from .lanczos import lanczos_tridiag, stochastic_logdet_from_lanczos, stochastic_lq_logdet  # noqa: F401
+from .lanczos import lanczos_tridiag, slq_gauss_radau, stochastic_logdet_from_lanczos, stochastic_lq_logdet  # noqa: F401

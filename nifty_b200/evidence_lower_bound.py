@@ -7,8 +7,10 @@ complement of the eigenvectors found so far (:176-411), and the unresolved tail 
 
 Every operator application is one fused metric-vector product on the device (``nb200_metric`` with the identity added,
 or ``nb200_lsm`` + ``nb200_rsm`` for the data-space operator ``R M^(1/2) ... `` of :154-173); SciPy only sees a
-``LinearOperator`` on host vectors.  The stochastic-Lanczos variants of the reference (``trace_log_method="slq"``,
-``analytic_prior_term``, Gauss-Radau bounds) are not provided here and raise.
+``LinearOperator`` on host vectors.  ``trace_log_method="slq"`` is the stochastic Lanczos quadrature of the same trace-log
+(``lanczos.py``): plain (``n_eigenvalues = 0``), or the reference's hybrid -- the largest eigenvalues exactly, the remainder on
+probes deflated by their eigenvectors, optionally bracketed by Gauss-Radau quadratures (``use_radau_as_bound=True``).  The
+``analytic_prior_term`` variant, ``slq_kwargs`` / ``slq_jit`` and resuming a stored eigensystem raise.
 """
 
 from __future__ import annotations
@@ -124,10 +126,11 @@ def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samp
     slq_order = int(slq_options.pop("slq_order", 30))
     slq_num_samples = int(slq_options.pop("slq_num_samples", 16))
     slq_key = slq_options.pop("slq_key", None)
+    use_radau_as_bound = bool(slq_options.pop("use_radau_as_bound", False))
     if analytic_prior_term or any(v is not None and v is not False for v in slq_options.values()):
-        raise NotImplementedError("analytic_prior_term / slq_kwargs / slq_jit (the Gauss-Radau remainder machinery of the reference's "
-                                  "hybrid estimator) are not provided on the B200 path; trace_log_method='eigsh' and the plain "
-                                  "stochastic Lanczos quadrature trace_log_method='slq' are")
+        raise NotImplementedError("analytic_prior_term / slq_kwargs / slq_jit are not provided on the B200 path; trace_log_method='eigsh', the "
+                                  "stochastic Lanczos quadrature trace_log_method='slq' (plain, or hybrid with n_eigenvalues exact eigenvalues "
+                                  "deflated, optionally with use_radau_as_bound=True) are")
     if resume_eigenvectors is not None or resume_eigenvalues is not None:
         raise NotImplementedError("resuming from a stored eigensystem is not supported on the B200 path")
     if likelihood.signal.cf.plan.dist:
@@ -161,28 +164,57 @@ def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samp
 
     if trace_log_method == "slq":
         # tr log M by stochastic Lanczos quadrature on the same operator (nifty_b200/lanczos.py; every Lanczos step is one fused
-        # device product): signal space log det(metric + 1), data space log det(1 + RSM LSM)
-        from .lanczos import lanczos_tridiag, stochastic_logdet_from_lanczos
+        # device product): signal space log det(metric + 1), data space log det(1 + RSM LSM).  With n_eigenvalues > 0 the HYBRID of
+        # the reference (:833-937): the largest eigenvalues exactly (ARPACK, deflation), the remainder by SLQ on probes projected
+        # onto the complement of their eigenvectors; use_radau_as_bound=True adds the Gauss-Radau bracket of the remainder with
+        # nodes at the two ends of the remaining spectrum, [1, smallest exact eigenvalue] of the shifted operator.
+        from .lanczos import slq_gauss_radau
         rng = slq_key if isinstance(slq_key, np.random.Generator) else np.random.default_rng(0 if slq_key is None else slq_key)
         shift = 0.0 if not use_data else 1.0
+        if not isinstance(n_eigenvalues, (int, np.integer)) or n_eigenvalues < 0:
+            raise ValueError("n_eigenvalues must be a non-negative integer.")
+        if n_eigenvalues > n_relevant:
+            raise ValueError("Number of requested eigenvalues exceeds the number of relevant degrees of freedom!")
+        exact_log, eigenvalues, eigenvectors = 0.0, np.asarray([]), None
+        if n_eigenvalues > 0:
+            eigenvalues, eigenvectors = _largest_eigenvalues(
+                op, op_size, int(n_eigenvalues), n_relevant, min_lh_eval=min_lh_eval, eigenvalue_shift=eig_shift, solver_shift=solver_shift,
+                n_batches=n_batches, tol=tol, early_stop=False, verbose=verbose, output_directory=output_directory,
+                prefix=f"{save_eigensystem_prefix}_{'data' if use_data else 'signal'}", orthonormalize=orthonormalize_eigenvectors,
+                every=orthonormalize_every_n_batches, threshold=orthonormalize_threshold, n_probes=orthonormalize_n_probes)
+            exact_log = float(np.sum(log_np(eigenvalues)))
+        if use_radau_as_bound and eigenvalues.size == 0:
+            raise ValueError("use_radau_as_bound=True requires a valid upper spectral endpoint from at least one exact eigenvalue.")
+        remainder, slq_se, tail_hi = 0.0, 0.0, None
+        if n_relevant - eigenvalues.size > 0:
+            if slq_num_samples < 2 and eigenvalues.size > 0:
+                raise ValueError("Estimating an SLQ remainder requires at least two probes to quantify stochastic uncertainty.")
 
-        def dev_matvec(v):
-            return torch.as_tensor(matvec(v.cpu().numpy()), dtype=torch.float64) + shift * v
+            def dev_matvec(v):
+                return torch.as_tensor(matvec(v.cpu().numpy()), dtype=torch.float64) + shift * v
 
-        per_probe = []
-        for _ in range(slq_num_samples):
-            v = torch.as_tensor(rng.integers(0, 2, size=op_size) * 2.0 - 1.0, dtype=torch.float64)
-            tri, _ = lanczos_tridiag(dev_matvec, v, order=min(slq_order, op_size))
-            per_probe.append(stochastic_logdet_from_lanczos(tri[None], op_size))
-        logdet = float(np.mean(per_probe))
-        slq_se = float(np.std(per_probe, ddof=1) / np.sqrt(len(per_probe))) if len(per_probe) > 1 else float("nan")
+            radau = {}
+            if use_radau_as_bound:
+                lam_min = 1.0                                         # eigenvalue_shift of the SHIFTED operator in both spaces
+                radau = dict(lam_min=lam_min, lam_max=max(lam_min, float(np.min(eigenvalues)) + shift), compute_radau=True)
+            out = slq_gauss_radau(dev_matvec, torch.log, min(slq_order, op_size), slq_num_samples, rng, shape0=op_size,
+                                  deflate_eigvecs=eigenvectors, **radau)
+            remainder, slq_se = out["estimate"], out["stochastic_se"]
+            if use_radau_as_bound:
+                lo, hi = out["radau_lo"], out["radau_hi"]
+                if not np.isfinite(lo) or not np.isfinite(hi):
+                    raise ValueError("Gauss-Radau quadrature failed because an endpoint is too close to the Lanczos spectrum.")
+                tail_hi = max(lo, hi)
+        logdet = exact_log + remainder
+        lower = 0.5 * max(0.0, tail_hi - remainder) if tail_hi is not None else (0.5 * slq_se if eigenvalues.size else 0.0)
         posterior_contribution = -0.5 * logdet + 0.5 * metric_size
         pts = [samples[i] for i in range(len(samples))]
         ham = [likelihood.energy(s) + 0.5 * likelihood.vdot(s, s) for s in pts]
         elbo_samples = np.array([posterior_contribution - h for h in ham])
         mean = float(np.mean(elbo_samples)) if len(pts) else float("nan")
         std = float(np.std(elbo_samples, ddof=1)) if len(pts) > 1 else float("nan")
-        stats = {"lower_error": 0.0, "slq_stochastic_se": 0.5 * slq_se, "elbo_lw": mean - std, "elbo_mean": mean, "elbo_up": mean + std,
+        stats = {"lower_error": lower, "slq_stochastic_se": 0.5 * slq_se, "slq_remainder": remainder, "exact_log": exact_log,
+                 "elbo_lw": mean - std - lower, "elbo_mean": mean, "elbo_up": mean + std,
                  "elbo_std": std, "elbo_se": std / np.sqrt(len(pts)) if len(pts) > 0 else 0.0}
         return elbo_samples, stats
     if compute_all:

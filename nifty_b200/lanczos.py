@@ -4,9 +4,11 @@
 
 ``mat`` is any callable on flat torch vectors -- typically ``lambda v: lin.metric(v, add_identity=True)``, one fused
 metric-vector product per Lanczos step; everything else (the three-term recurrence, full re-orthogonalisation against the
-stored basis, the small eigenproblems of the quadrature) is call sequencing on the same device.  The Gauss-Radau variance
-machinery of the reference's ``_slq_gauss_radau`` (:483-754) is not reproduced: ``stochastic_lq_logdet`` is the plain Gauss
-quadrature with Rademacher probes that the reference's public signature describes.
+stored basis, the small eigenproblems of the quadrature) is call sequencing on the same device.  ``slq_gauss_radau`` is the
+core of the reference's ``_slq_gauss_radau`` (:483-754): Hutchinson probes with optional deflation of known eigenvectors, the
+Gauss estimate with its stochastic standard error, and the two Gauss-Radau quadratures with a prescribed node at either end
+of the spectrum (:211-283) that bracket every probe's quadratic form; the reference's further knobs (extra functions, partial
+re-orthogonalisation, probe micro-batches, clipping) are not reproduced.
 """
 from __future__ import annotations
 
@@ -15,7 +17,7 @@ from typing import Callable, Optional, Union
 import numpy as np
 import torch
 
-__all__ = ["lanczos_tridiag", "stochastic_logdet_from_lanczos", "stochastic_lq_logdet"]
+__all__ = ["lanczos_tridiag", "stochastic_logdet_from_lanczos", "stochastic_lq_logdet", "slq_gauss_radau"]
 
 
 def _lanczos(matvec: Callable, v1: torch.Tensor, order: int, eps: float):
@@ -110,3 +112,91 @@ def stochastic_lq_logdet(mat: Union[torch.Tensor, Callable], order: int, n_sampl
         tri, _ = lanczos_tridiag(mat, v, order=min(order, shape0))
         tris.append(tri)
     return stochastic_logdet_from_lanczos(torch.stack(tris), shape0)
+
+
+def _tridiag(alpha, off):
+    return torch.diag(alpha) + torch.diag(off, 1) + torch.diag(off, -1)
+
+
+def _radau_unit(alpha, off, mu: float, func: Callable, eps: float):
+    """``e1^T f(T_hat) e1`` for the Gauss-Radau modification ``T_hat`` of the Lanczos tridiagonal that makes ``mu`` a quadrature
+    node (lanczos.py:211-283): the last diagonal entry becomes ``mu + beta^2 e_last^T (T_lead - mu)^-1 e_last`` with ``T_lead``
+    the leading block and ``beta`` the last off-diagonal.  NaN when ``mu`` is not separated from the spectrum of ``T_lead``."""
+    m = alpha.numel()
+    if m == 1:
+        return func(torch.as_tensor(mu, dtype=alpha.dtype, device=alpha.device))
+    evals, evecs = torch.linalg.eigh(_tridiag(alpha[:-1], off[:-1]))
+    den = evals - mu
+    if bool(torch.any(den.abs() <= eps * (1.0 + abs(mu)))):
+        return torch.as_tensor(float("nan"), dtype=alpha.dtype, device=alpha.device)
+    g = torch.sum(evecs[-1, :] ** 2 / den)
+    a_hat = alpha.clone()
+    a_hat[-1] = mu + off[-1] ** 2 * g
+    ev, vec = torch.linalg.eigh(_tridiag(a_hat, off))
+    return torch.sum(vec[0, :] ** 2 * func(ev))
+
+
+def slq_gauss_radau(mat: Union[torch.Tensor, Callable], func: Callable, order: int, n_samples: int, key, *, shape0: Optional[int] = None,
+                    deflate_eigvecs=None, lam_min: Optional[float] = None, lam_max: Optional[float] = None, compute_radau: bool = False,
+                    eps: float = 1e-12, dtype=torch.float64, device=None) -> dict:
+    """``tr f(A)`` of a symmetric positive definite ``A`` by stochastic Lanczos quadrature with optional Gauss-Radau bounds
+    (lanczos.py:483-754).  ``deflate_eigvecs`` (n, p), orthonormal: the probes are projected onto their orthogonal complement,
+    ``z <- z - Q Q^T z``, so the estimate is the trace over that complement (an invariant subspace when the columns are
+    eigenvectors).  ``compute_radau`` needs ``lam_min`` / ``lam_max`` enclosing the spectrum seen by the probes; for every probe the
+    two Radau values bracket ``z^T f(A) z`` when the derivatives of ``f`` have constant alternating sign (``log``).
+
+    Returns ``estimate`` / ``gauss_estimate``, ``stochastic_se`` / ``gauss_se`` (NaN for one probe), and with ``compute_radau``
+    ``radau_lo``, ``radau_hi`` (means over the probes of the node-at-``lam_min`` / node-at-``lam_max`` quadratures) and
+    ``quadrature_width``."""
+    if (lam_min is None) != (lam_max is None):
+        raise ValueError("Provide both lam_min and lam_max, or neither.")
+    if compute_radau and lam_min is None:
+        raise ValueError("compute_radau=True requires lam_min and lam_max.")
+    if order < 1:
+        raise ValueError("order must be >= 1.")
+    if n_samples < 1:
+        raise ValueError("num_samples must be >= 1.")
+    if not callable(mat):
+        m = torch.as_tensor(mat)
+        if m.ndim != 2 or m.shape[0] != m.shape[1]:
+            raise ValueError("mat must be a square matrix")
+        shape0, dtype, device = m.shape[0], m.dtype, m.device
+        mat = lambda x, m=m: m @ x       # noqa: E731
+    elif shape0 is None:
+        if deflate_eigvecs is None:
+            raise ValueError("If A is callable, provide n=... or deflate_eigvecs.")
+        shape0 = int(np.shape(deflate_eigvecs)[0])
+    Q = None if deflate_eigvecs is None else torch.as_tensor(np.asarray(deflate_eigvecs), dtype=dtype, device=device)
+    if Q is not None and Q.shape[1] == 0:
+        Q = None
+    rng = key if isinstance(key, np.random.Generator) else np.random.default_rng(key)
+    gauss, lo, hi = [], [], []
+    for _ in range(n_samples):
+        z = torch.as_tensor(rng.integers(0, 2, size=shape0) * 2.0 - 1.0, dtype=dtype, device=device)
+        if Q is not None:
+            z = z - Q @ (Q.T @ z)
+        nz2 = float(torch.dot(z, z))
+        if not nz2 > 0.0:
+            gauss.append(0.0)
+            lo.append(0.0)
+            hi.append(0.0)
+            continue
+        alpha, off, _ = _lanczos(mat, z / np.sqrt(nz2), min(order, shape0), eps)
+        m_eff = 1
+        while m_eff < alpha.numel() and float(off[m_eff - 1]) > eps:      # steps before a breakdown (zero padding afterwards)
+            m_eff += 1
+        alpha, off = alpha[:m_eff], off[:m_eff - 1]
+        ev, vec = torch.linalg.eigh(_tridiag(alpha, off))
+        gauss.append(nz2 * float(torch.sum(vec[0, :] ** 2 * func(ev))))
+        if compute_radau:
+            exhausted = m_eff < min(order, shape0)                         # Krylov space exhausted: the Gauss value is exact
+            lo.append(gauss[-1] if exhausted else nz2 * float(_radau_unit(alpha, off, float(lam_min), func, eps)))
+            hi.append(gauss[-1] if exhausted else nz2 * float(_radau_unit(alpha, off, float(lam_max), func, eps)))
+    est = float(np.mean(gauss))
+    se = float(np.std(gauss, ddof=1) / np.sqrt(len(gauss))) if len(gauss) > 1 else float("nan")
+    out = {"estimate": est, "gauss_estimate": est, "stochastic_se": se, "gauss_se": se, "per_probe": np.asarray(gauss)}
+    if compute_radau:
+        out["radau_lo"], out["radau_hi"] = float(np.mean(lo)), float(np.mean(hi))
+        out["quadrature_width"] = abs(out["radau_hi"] - out["radau_lo"])
+        out["per_probe_radau"] = np.stack((np.asarray(lo), np.asarray(hi)))
+    return out

@@ -97,3 +97,7 @@ def test_constants_do_not_move(rt):
 
 def test_host_composed_wiener_filter_and_slq(rt):
     vc.check_host_composed_wiener_and_elbo(rt, "nonpow2")
+
+
+def test_evidence_lower_bound_hybrid_slq_with_radau_bounds(rt):
+    vc.check_elbo_hybrid(rt)

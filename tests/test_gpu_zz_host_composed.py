@@ -80,3 +80,7 @@ def test_host_composed_wiener_filter_and_slq(rt):
 @pytest.mark.parametrize("shape,nl", [((8, 8), "exp"), ((4, 8, 4), "identity")])
 def test_gaussian_with_non_diagonal_covariance(rt, shape, nl):
     pc.check_operator_gaussian(rt, shape, nl)
+
+
+def test_evidence_lower_bound_hybrid_slq_with_radau_bounds(rt):
+    vc.check_elbo_hybrid(rt)

@@ -47,3 +47,37 @@ def test_stochastic_lq_logdet_against_slogdet():
     assert abs(quad - exact) < 1e-8 * abs(exact)
     with pytest.raises(ValueError):
         lanczos.stochastic_lq_logdet(lambda v: v, 4, 2, 0)
+
+
+@pytest.mark.parametrize("k", [0, 6])
+def test_slq_gauss_radau_brackets_every_probe(k):
+    """Gauss-Radau quadratures with a node at either end of the spectrum bracket the quadratic form z^T log(A) z of every probe
+    (lanczos.py:211-283, 483-754), also for probes deflated by known eigenvectors; the Gauss estimate is the Hutchinson mean."""
+    import nifty_b200 as nb
+    rng = np.random.default_rng(0)
+    n = 80
+    U, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    ev = np.sort(np.concatenate([np.linspace(1.0, 3.0, n - 6), [10, 20, 40, 80, 160, 320]]))[::-1]
+    A = torch.as_tensor((U * ev) @ U.T)
+    logA = (U * np.log(ev)) @ U.T
+    Q = U[:, :k]
+    lam_max = float(ev[k] * (1.05 if k == 0 else 1.0))
+    out = nb.slq_gauss_radau(A, torch.log, 8, 12, 5, deflate_eigvecs=Q, lam_min=1.0, lam_max=lam_max, compute_radau=True)
+    r2 = np.random.default_rng(5)                     # the same probes
+    exact = []
+    for _ in range(12):
+        z = r2.integers(0, 2, size=n) * 2.0 - 1.0
+        z = z - Q @ (Q.T @ z)
+        exact.append(z @ logA @ z)
+    exact = np.array(exact)
+    lo, hi = out["per_probe_radau"]
+    assert np.all(np.minimum(lo, hi) <= exact + 1e-9) and np.all(exact <= np.maximum(lo, hi) + 1e-9)
+    assert min(out["radau_lo"], out["radau_hi"]) <= exact.mean() <= max(out["radau_lo"], out["radau_hi"])
+    assert abs(out["estimate"] - np.sum(np.log(ev[k:]))) < 4.0 * out["stochastic_se"] + 1e-6
+    assert out["quadrature_width"] >= 0.0
+    with pytest.raises(ValueError):
+        nb.slq_gauss_radau(A, torch.log, 8, 2, 5, lam_min=1.0)
+    with pytest.raises(ValueError):
+        nb.slq_gauss_radau(A, torch.log, 8, 2, 5, compute_radau=True)
+    with pytest.raises(ValueError):
+        nb.slq_gauss_radau(lambda v: A @ v, torch.log, 8, 2, 5)

@@ -648,3 +648,40 @@ def check_host_composed_wiener_and_elbo(rt, which="nonpow2"):
     nrel = min(int(np.prod(shape)), L)
     ham = np.array([olh.energy(lay.unpack(pv + r)) + 0.5 * (pv + r) @ (pv + r) for r in res])
     np.testing.assert_allclose(el, -0.5 * np.sum(np.log(eig[:nrel])) + 0.5 * L - ham, rtol=1e-8)
+
+
+def check_elbo_hybrid(rt, name="g2d_16x16"):
+    """The hybrid trace-log estimator of estimate_evidence_lower_bound (evidence_lower_bound.py:833-937): the largest eigenvalues
+    exactly, the remainder by stochastic Lanczos quadrature on probes deflated by their eigenvectors, optionally bracketed by
+    Gauss-Radau quadratures -- against dense eigenvalues of the oracle's metric."""
+    import pytest
+    c, g, lh, olh, lay = _setup(rt, name)
+    rng = np.random.default_rng(12)
+    pos = lay.pack({k: 0.3 * v for k, v in lay.random(rng).items()})
+    res = 0.05 * np.stack([lay.pack(lay.random(rng)) for _ in range(3)])
+    smp = nb.Samples(pos=rt.asarray(pos, torch.float64), samples=rt.asarray(res, torch.float64))
+    L = lay.size
+    pd = lay.unpack(pos)
+    H = np.stack([lay.pack(olh.metric(pd, lay.unpack(e))) + e for e in np.eye(L)], axis=1)
+    eig = np.sort(np.linalg.eigvalsh(0.5 * (H + H.T)))[::-1]
+    ham = np.array([olh.energy(lay.unpack(pos + r)) + 0.5 * (pos + r) @ (pos + r) for r in res])
+    exact = -0.5 * np.sum(np.log(eig)) + 0.5 * L - ham
+    n = 24
+    for space in ("signal", "data"):
+        for radau in (False, True):
+            # (a Radau node that a Ritz value has converged onto makes the modified tridiagonal singular: the reference raises then,
+            # :930-937, and so does this path -- hence the lower order with the bound)
+            el, st = nb.estimate_evidence_lower_bound(lh, smp, n, trace_log_method="slq", trace_log_space=space, slq_order=10 if radau else 40,
+                                                      slq_num_samples=12, slq_key=3, use_radau_as_bound=radau, n_batches=4, verbose=False)
+            assert abs(st["exact_log"] - np.sum(np.log(eig[:n]))) <= 1e-8 * abs(st["exact_log"])
+            rem = float(np.sum(np.log(eig[n:])))
+            assert abs(st["slq_remainder"] - rem) <= 5.0 * 2.0 * st["slq_stochastic_se"] + 1e-3 * abs(rem) + 1e-6
+            assert st["lower_error"] >= 0.0 and np.isfinite(st["lower_error"])
+            assert abs(st["elbo_mean"] - exact.mean()) <= 5.0 * st["slq_stochastic_se"] + 1e-3 * abs(exact.mean())
+            assert st["elbo_lw"] <= st["elbo_mean"] <= st["elbo_up"]
+    with pytest.raises(ValueError, match="upper spectral endpoint"):
+        nb.estimate_evidence_lower_bound(lh, smp, 0, trace_log_method="slq", use_radau_as_bound=True, verbose=False)
+    with pytest.raises(ValueError, match="too close to the Lanczos spectrum"):
+        nb.estimate_evidence_lower_bound(lh, smp, n, trace_log_method="slq", slq_order=60, slq_num_samples=4, use_radau_as_bound=True, verbose=False)
+    with pytest.raises(ValueError, match="at least two probes"):
+        nb.estimate_evidence_lower_bound(lh, smp, 4, trace_log_method="slq", slq_num_samples=1, verbose=False)
