@@ -10,7 +10,8 @@ or ``nb200_lsm`` + ``nb200_rsm`` for the data-space operator ``R M^(1/2) ... `` 
 ``LinearOperator`` on host vectors.  ``trace_log_method="slq"`` is the stochastic Lanczos quadrature of the same trace-log
 (``lanczos.py``): plain (``n_eigenvalues = 0``), or the reference's hybrid -- the largest eigenvalues exactly, the remainder on
 probes deflated by their eigenvectors, optionally bracketed by Gauss-Radau quadratures (``use_radau_as_bound=True``).  The
-``analytic_prior_term`` variant, ``slq_kwargs`` / ``slq_jit`` and resuming a stored eigensystem raise.
+``analytic_prior_term`` evaluates the prior energy in closed form from ``tr (M + 1)^-1``; ``slq_kwargs`` / ``slq_jit`` and resuming a stored
+eigensystem raise.
 """
 
 from __future__ import annotations
@@ -103,6 +104,19 @@ def _largest_eigenvalues(op, size, n_eigenvalues, tot_dofs, *, min_lh_eval, eige
     return vals, vecs
 
 
+def _analytic_prior(likelihood, samples, eigenvalues, use_data, trace_inv_remainder, trace_inv_se, n_unit):
+    """The prior energy of the ELBO in closed form (:809-824, 953-979): ``1/2 (tr (M + 1)^-1 + <mean, mean>)`` with the trace split
+    into the exact eigenvalues, the SLQ remainder and the ``n_unit`` eigenvalues that equal one."""
+    pos = samples.pos
+    prior_mean_sq = float(likelihood.vdot(pos, pos)) if pos is not None else 0.0
+    trace_inv_exact = float(np.sum(1.0 / (eigenvalues + float(use_data)))) if eigenvalues.size else 0.0
+    total = trace_inv_exact + trace_inv_remainder + float(n_unit)
+    prior_term = 0.5 * (total + prior_mean_sq)
+    return prior_term, {"trace_inv_exact": trace_inv_exact, "trace_inv_slq": float(trace_inv_remainder), "trace_inv_const": float(n_unit),
+                        "trace_inv_se": float(trace_inv_se), "trace_inv_total": total, "prior_mean_sq": prior_mean_sq,
+                        "prior_term": prior_term}
+
+
 def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samples, n_eigenvalues, *, compute_all=False,
                                   min_lh_eval=1e-3, n_batches=10, tol=0.0, verbose=True, metric_jit=True,
                                   output_directory: Optional[str] = None, save_eigensystem_prefix="metric",
@@ -127,10 +141,10 @@ def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samp
     slq_num_samples = int(slq_options.pop("slq_num_samples", 16))
     slq_key = slq_options.pop("slq_key", None)
     use_radau_as_bound = bool(slq_options.pop("use_radau_as_bound", False))
-    if analytic_prior_term or any(v is not None and v is not False for v in slq_options.values()):
-        raise NotImplementedError("analytic_prior_term / slq_kwargs / slq_jit are not provided on the B200 path; trace_log_method='eigsh', the "
-                                  "stochastic Lanczos quadrature trace_log_method='slq' (plain, or hybrid with n_eigenvalues exact eigenvalues "
-                                  "deflated, optionally with use_radau_as_bound=True) are")
+    if any(v is not None and v is not False for v in slq_options.values()):
+        raise NotImplementedError("slq_kwargs / slq_jit are not provided on the B200 path; trace_log_method='eigsh', the stochastic Lanczos "
+                                  "quadrature trace_log_method='slq' (plain, or hybrid with n_eigenvalues exact eigenvalues deflated, optionally "
+                                  "with use_radau_as_bound=True) and analytic_prior_term are")
     if resume_eigenvectors is not None or resume_eigenvalues is not None:
         raise NotImplementedError("resuming from a stored eigensystem is not supported on the B200 path")
     if likelihood.signal.cf.plan.dist:
@@ -186,6 +200,7 @@ def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samp
         if use_radau_as_bound and eigenvalues.size == 0:
             raise ValueError("use_radau_as_bound=True requires a valid upper spectral endpoint from at least one exact eigenvalue.")
         remainder, slq_se, tail_hi = 0.0, 0.0, None
+        trace_inv_remainder, trace_inv_se = 0.0, 0.0
         if n_relevant - eigenvalues.size > 0:
             if slq_num_samples < 2 and eigenvalues.size > 0:
                 raise ValueError("Estimating an SLQ remainder requires at least two probes to quantify stochastic uncertainty.")
@@ -197,9 +212,13 @@ def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samp
             if use_radau_as_bound:
                 lam_min = 1.0                                         # eigenvalue_shift of the SHIFTED operator in both spaces
                 radau = dict(lam_min=lam_min, lam_max=max(lam_min, float(np.min(eigenvalues)) + shift), compute_radau=True)
+            extra = {"inv": lambda x: 1.0 / x - 1.0} if analytic_prior_term else None     # centred: unit eigenvalues contribute nothing
             out = slq_gauss_radau(dev_matvec, torch.log, min(slq_order, op_size), slq_num_samples, rng, shape0=op_size,
-                                  deflate_eigvecs=eigenvectors, **radau)
+                                  deflate_eigvecs=eigenvectors, extra_fns=extra, **radau)
             remainder, slq_se = out["estimate"], out["stochastic_se"]
+            if analytic_prior_term:
+                trace_inv_remainder = (n_relevant - eigenvalues.size) + out["extra_inv_estimate"]
+                trace_inv_se = out["extra_inv_se"]
             if use_radau_as_bound:
                 lo, hi = out["radau_lo"], out["radau_hi"]
                 if not np.isfinite(lo) or not np.isfinite(hi):
@@ -209,13 +228,24 @@ def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samp
         lower = 0.5 * max(0.0, tail_hi - remainder) if tail_hi is not None else (0.5 * slq_se if eigenvalues.size else 0.0)
         posterior_contribution = -0.5 * logdet + 0.5 * metric_size
         pts = [samples[i] for i in range(len(samples))]
-        ham = [likelihood.energy(s) + 0.5 * likelihood.vdot(s, s) for s in pts]
-        elbo_samples = np.array([posterior_contribution - h for h in ham])
+        stats = {}
+        prior_term = 0.0
+        if analytic_prior_term:
+            prior_term, pstats = _analytic_prior(likelihood, samples, eigenvalues, use_data, trace_inv_remainder, trace_inv_se,
+                                                 metric_size - n_relevant)
+            stats.update(pstats)
+            if trace_inv_se > 0.0:
+                lower += 0.5 * trace_inv_se
+            energies = [likelihood.energy(s) for s in pts]                     # the prior part is analytic (:959)
+        else:
+            energies = [likelihood.energy(s) + 0.5 * likelihood.vdot(s, s) for s in pts]
+        elbo_samples = np.array([posterior_contribution - h - prior_term for h in energies])
         mean = float(np.mean(elbo_samples)) if len(pts) else float("nan")
         std = float(np.std(elbo_samples, ddof=1)) if len(pts) > 1 else float("nan")
-        stats = {"lower_error": lower, "slq_stochastic_se": 0.5 * slq_se, "slq_remainder": remainder, "exact_log": exact_log,
-                 "elbo_lw": mean - std - lower, "elbo_mean": mean, "elbo_up": mean + std,
-                 "elbo_std": std, "elbo_se": std / np.sqrt(len(pts)) if len(pts) > 0 else 0.0}
+        stats.update({"lower_error": lower, "slq_stochastic_se": 0.5 * slq_se, "slq_remainder": remainder, "exact_log": exact_log,
+                      "trace_log_exact": exact_log, "trace_log_slq": remainder, "trace_log_se": slq_se,
+                      "elbo_lw": mean - std - lower, "elbo_mean": mean, "elbo_up": mean + std,
+                      "elbo_std": std, "elbo_se": std / np.sqrt(len(pts)) if len(pts) > 0 else 0.0})
         return elbo_samples, stats
     if compute_all:
         n_eigenvalues = n_relevant
@@ -240,9 +270,16 @@ def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samp
     lower_error = 0.5 * (n_relevant - log_eigs.size) * float(np.min(log_eigs)) if log_eigs.size else 0.0   # :828-832
     posterior_contribution = tr_log_lat_cov + 0.5 * metric_size                                  # :956
     pts = [samples[i] for i in range(len(samples))]
-    ham = [likelihood.energy(s) + 0.5 * likelihood.vdot(s, s) for s in pts]                      # StandardHamiltonian (:67-87)
-    elbo_samples = np.array([posterior_contribution - h for h in ham])
-    stats = {"lower_error": lower_error}
+    stats, prior_term = {}, 0.0
+    if analytic_prior_term:
+        if n_relevant > log_eigs.size:
+            raise ValueError("analytic_prior_term requires trace_log_method='slq' or compute_all=True when not all eigenvalues are computed.")
+        prior_term, stats = _analytic_prior(likelihood, samples, eigenvalues, use_data, 0.0, 0.0, metric_size - n_relevant)
+        ham = [likelihood.energy(s) for s in pts]
+    else:
+        ham = [likelihood.energy(s) + 0.5 * likelihood.vdot(s, s) for s in pts]                  # StandardHamiltonian (:67-87)
+    elbo_samples = np.array([posterior_contribution - h - prior_term for h in ham])
+    stats["lower_error"] = lower_error
     mean = float(np.mean(elbo_samples)) if len(pts) else float("nan")
     std = float(np.std(elbo_samples, ddof=1)) if len(pts) > 1 else float("nan")
     stats["elbo_lw"], stats["elbo_mean"], stats["elbo_up"] = mean - std - lower_error, mean, mean + std

@@ -138,7 +138,7 @@ def _radau_unit(alpha, off, mu: float, func: Callable, eps: float):
 
 def slq_gauss_radau(mat: Union[torch.Tensor, Callable], func: Callable, order: int, n_samples: int, key, *, shape0: Optional[int] = None,
                     deflate_eigvecs=None, lam_min: Optional[float] = None, lam_max: Optional[float] = None, compute_radau: bool = False,
-                    eps: float = 1e-12, dtype=torch.float64, device=None) -> dict:
+                    extra_fns: Optional[dict] = None, eps: float = 1e-12, dtype=torch.float64, device=None) -> dict:
     """``tr f(A)`` of a symmetric positive definite ``A`` by stochastic Lanczos quadrature with optional Gauss-Radau bounds
     (lanczos.py:483-754).  ``deflate_eigvecs`` (n, p), orthonormal: the probes are projected onto their orthogonal complement,
     ``z <- z - Q Q^T z``, so the estimate is the trace over that complement (an invariant subspace when the columns are
@@ -147,7 +147,8 @@ def slq_gauss_radau(mat: Union[torch.Tensor, Callable], func: Callable, order: i
 
     Returns ``estimate`` / ``gauss_estimate``, ``stochastic_se`` / ``gauss_se`` (NaN for one probe), and with ``compute_radau``
     ``radau_lo``, ``radau_hi`` (means over the probes of the node-at-``lam_min`` / node-at-``lam_max`` quadratures) and
-    ``quadrature_width``."""
+    ``quadrature_width``.  ``extra_fns`` (name -> scalar function): further traces from the SAME tridiagonals, Gauss quadrature
+    only, reported as ``extra_{name}_estimate`` / ``extra_{name}_se``."""
     if (lam_min is None) != (lam_max is None):
         raise ValueError("Provide both lam_min and lam_max, or neither.")
     if compute_radau and lam_min is None:
@@ -156,6 +157,9 @@ def slq_gauss_radau(mat: Union[torch.Tensor, Callable], func: Callable, order: i
         raise ValueError("order must be >= 1.")
     if n_samples < 1:
         raise ValueError("num_samples must be >= 1.")
+    if extra_fns is not None and not isinstance(extra_fns, dict):
+        raise ValueError("extra_fns must be a dict of name -> callable.")
+    extras = {name: [] for name in (extra_fns or {})}
     if not callable(mat):
         m = torch.as_tensor(mat)
         if m.ndim != 2 or m.shape[0] != m.shape[1]:
@@ -180,6 +184,8 @@ def slq_gauss_radau(mat: Union[torch.Tensor, Callable], func: Callable, order: i
             gauss.append(0.0)
             lo.append(0.0)
             hi.append(0.0)
+            for v in extras.values():
+                v.append(0.0)
             continue
         alpha, off, _ = _lanczos(mat, z / np.sqrt(nz2), min(order, shape0), eps)
         m_eff = 1
@@ -188,6 +194,8 @@ def slq_gauss_radau(mat: Union[torch.Tensor, Callable], func: Callable, order: i
         alpha, off = alpha[:m_eff], off[:m_eff - 1]
         ev, vec = torch.linalg.eigh(_tridiag(alpha, off))
         gauss.append(nz2 * float(torch.sum(vec[0, :] ** 2 * func(ev))))
+        for name, fn in (extra_fns or {}).items():
+            extras[name].append(nz2 * float(torch.sum(vec[0, :] ** 2 * fn(ev))))
         if compute_radau:
             exhausted = m_eff < min(order, shape0)                         # Krylov space exhausted: the Gauss value is exact
             lo.append(gauss[-1] if exhausted else nz2 * float(_radau_unit(alpha, off, float(lam_min), func, eps)))
@@ -195,6 +203,9 @@ def slq_gauss_radau(mat: Union[torch.Tensor, Callable], func: Callable, order: i
     est = float(np.mean(gauss))
     se = float(np.std(gauss, ddof=1) / np.sqrt(len(gauss))) if len(gauss) > 1 else float("nan")
     out = {"estimate": est, "gauss_estimate": est, "stochastic_se": se, "gauss_se": se, "per_probe": np.asarray(gauss)}
+    for name, vals in extras.items():
+        out[f"extra_{name}_estimate"] = float(np.mean(vals))
+        out[f"extra_{name}_se"] = float(np.std(vals, ddof=1) / np.sqrt(len(vals))) if len(vals) > 1 else float("nan")
     if compute_radau:
         out["radau_lo"], out["radau_hi"] = float(np.mean(lo)), float(np.mean(hi))
         out["quadrature_width"] = abs(out["radau_hi"] - out["radau_lo"])

@@ -310,8 +310,10 @@ def check_elbo(rt, name="g2d_16x16"):
     np.testing.assert_allclose(q @ q.T, np.eye(8), atol=1e-10)                     # orthonormal Krylov basis of the device product
     np.testing.assert_allclose(q @ (0.5 * (H + H.T)) @ q.T, t2n(tri), atol=1e-8 * np.abs(H).max())
     # refused / invalid options
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="analytic_prior_term requires"):
         nb.estimate_evidence_lower_bound(lh, smp, 4, analytic_prior_term=True, verbose=False)
+    with pytest.raises(NotImplementedError):
+        nb.estimate_evidence_lower_bound(lh, smp, 4, trace_log_method="slq", slq_jit=True, verbose=False)
     with pytest.raises(ValueError, match="at least one eigenvalue"):
         nb.estimate_evidence_lower_bound(lh, smp, 0, verbose=False)
     with pytest.raises(ValueError, match="exceeds"):
@@ -679,6 +681,19 @@ def check_elbo_hybrid(rt, name="g2d_16x16"):
             assert st["lower_error"] >= 0.0 and np.isfinite(st["lower_error"])
             assert abs(st["elbo_mean"] - exact.mean()) <= 5.0 * st["slq_stochastic_se"] + 1e-3 * abs(exact.mean())
             assert st["elbo_lw"] <= st["elbo_mean"] <= st["elbo_up"]
+    # analytic_prior_term (:809-824, 953-979): the prior energy in closed form, 1/2 (tr (M + 1)^-1 + <mean, mean>)
+    lh_e = np.array([olh.energy(lay.unpack(pos + r)) for r in res])
+    prior = 0.5 * (np.sum(1.0 / eig) + pos @ pos)
+    want = -0.5 * np.sum(np.log(eig)) + 0.5 * L - lh_e - prior
+    el, st = nb.estimate_evidence_lower_bound(lh, smp, 0, compute_all=True, analytic_prior_term=True, verbose=False)
+    np.testing.assert_allclose(el, want, rtol=1e-8)
+    assert abs(st["trace_inv_total"] - np.sum(1.0 / eig)) <= 1e-8 * st["trace_inv_total"] and abs(st["prior_term"] - prior) <= 1e-8 * prior
+    for space in ("signal", "data"):
+        el, st = nb.estimate_evidence_lower_bound(lh, smp, n, trace_log_method="slq", trace_log_space=space, slq_order=40, slq_num_samples=12,
+                                                  slq_key=3, analytic_prior_term=True, n_batches=4, verbose=False)
+        assert abs(st["trace_inv_total"] - np.sum(1.0 / eig)) <= 5.0 * st["trace_inv_se"] + 1e-3 * np.sum(1.0 / eig)
+        assert abs(st["elbo_mean"] - want.mean()) <= 5.0 * (st["slq_stochastic_se"] + 0.5 * st["trace_inv_se"]) + 1e-3 * abs(want.mean())
+        assert st["trace_inv_const"] == L - min(L, int(np.prod(c["shape"])))
     with pytest.raises(ValueError, match="upper spectral endpoint"):
         nb.estimate_evidence_lower_bound(lh, smp, 0, trace_log_method="slq", use_radau_as_bound=True, verbose=False)
     with pytest.raises(ValueError, match="too close to the Lanczos spectrum"):
