@@ -10,8 +10,8 @@ or ``nb200_lsm`` + ``nb200_rsm`` for the data-space operator ``R M^(1/2) ... `` 
 ``LinearOperator`` on host vectors.  ``trace_log_method="slq"`` is the stochastic Lanczos quadrature of the same trace-log
 (``lanczos.py``): plain (``n_eigenvalues = 0``), or the reference's hybrid -- the largest eigenvalues exactly, the remainder on
 probes deflated by their eigenvectors, optionally bracketed by Gauss-Radau quadratures (``use_radau_as_bound=True``).  The
-``analytic_prior_term`` evaluates the prior energy in closed form from ``tr (M + 1)^-1``; ``slq_kwargs`` / ``slq_jit`` and resuming a stored
-eigensystem raise.
+``analytic_prior_term`` evaluates the prior energy in closed form from ``tr (M + 1)^-1``; a stored eigensystem can be resumed
+(``resume_eigenvectors`` / ``resume_eigenvalues``); ``slq_kwargs`` / ``slq_jit`` raise.
 """
 
 from __future__ import annotations
@@ -52,14 +52,43 @@ def _deflated(op: ssl.LinearOperator, vecs: Optional[np.ndarray]) -> ssl.LinearO
 
 
 def _largest_eigenvalues(op, size, n_eigenvalues, tot_dofs, *, min_lh_eval, eigenvalue_shift, solver_shift, n_batches, tol,
-                         early_stop, verbose, output_directory, prefix, orthonormalize, every, threshold, n_probes):
+                         early_stop, verbose, output_directory, prefix, orthonormalize, every, threshold, n_probes,
+                         resume_eigenvectors=None, resume_eigenvalues=None):
     """The ``n_eigenvalues`` largest eigenvalues of ``op`` (:176-411): dense when all relevant ones are requested,
     otherwise ARPACK batch by batch with deflation, stopping early once the smallest one found is within
-    ``min_lh_eval`` of the value every remaining eigenvalue has (``eigenvalue_shift``)."""
+    ``min_lh_eval`` of the value every remaining eigenvalue has (``eigenvalue_shift``).  ``resume_*``: an eigensystem computed
+    earlier (:199-268) -- checked against the operator, sorted, truncated, and used as the first deflation set."""
     if n_eigenvalues > tot_dofs:
         raise ValueError("Number of requested eigenvalues exceeds the number of relevant degrees of freedom!")
+    if resume_eigenvalues is not None and resume_eigenvectors is None:
+        raise ValueError("resume_eigenvalues requires resume_eigenvectors.")
+    r_vals, r_vecs = None, None
+    if resume_eigenvectors is not None:
+        r_vecs = np.asarray(resume_eigenvectors, dtype=np.float64)
+        if r_vecs.ndim != 2:
+            raise ValueError("resume_eigenvectors must be a 2D array.")
+        if r_vecs.shape[0] != size:
+            raise ValueError("resume_eigenvectors does not match the operator size.")
+        estimated = np.array([r_vecs[:, i] @ op.matvec(r_vecs[:, i]) for i in range(r_vecs.shape[1])])      # Rayleigh quotients (:86-90)
+        r_vals = estimated if resume_eigenvalues is None else np.asarray(resume_eigenvalues, dtype=np.float64)
+        if r_vals.ndim != 1:
+            raise ValueError("resume_eigenvalues must be a 1D array.")
+        if r_vals.size != r_vecs.shape[1]:
+            raise ValueError("resume_eigenvalues and resume_eigenvectors have mismatched sizes.")
+        if not np.allclose(r_vals, estimated, rtol=1e-5, atol=1e-8):
+            raise ValueError("The resumed eigensystem does not match the selected operator. Check trace_log_space and the eigensystem source.")
+        order = np.argsort(-r_vals)
+        r_vals, r_vecs = r_vals[order][:max(n_eigenvalues, 0)], r_vecs[:, order][:, :max(n_eigenvalues, 0)]
+        if orthonormalize and threshold is not None and r_vecs.shape[1] and _orthonormality_error(r_vecs, n_probes) > threshold:
+            r_vecs, _ = np.linalg.qr(r_vecs)
+        if r_vals.size > tot_dofs:
+            raise ValueError("Number of provided eigenvectors exceeds relevant degrees of freedom.")
+        if r_vals.size == 0:
+            r_vals, r_vecs = None, None
     if n_eigenvalues <= 0:
         return np.asarray([], dtype=np.float64), None
+    if r_vals is not None and (r_vals.size >= n_eigenvalues or (early_stop and abs(eigenvalue_shift - np.min(r_vals)) < min_lh_eval)):
+        return r_vals, r_vecs
 
     def save(vals, vecs):
         if output_directory is None:
@@ -70,7 +99,7 @@ def _largest_eigenvalues(op, size, n_eigenvalues, tot_dofs, *, min_lh_eval, eige
         if vecs is not None:
             np.save(os.path.join(d, f"{prefix}_eigenvectors.npy"), vecs)
 
-    if tot_dofs == n_eigenvalues:
+    if tot_dofs == n_eigenvalues and r_vals is None:
         if verbose:
             logger.info(f"Computing all {tot_dofs} relevant eigenvalues.")
         dense = np.column_stack([op.matvec(e) for e in np.identity(size)])
@@ -78,11 +107,12 @@ def _largest_eigenvalues(op, size, n_eigenvalues, tot_dofs, *, min_lh_eval, eige
         order = np.argsort(-vals)
         save(vals[order], vecs[:, order])
         return vals[order], vecs[:, order]
-    base, rem = divmod(n_eigenvalues, n_batches)
+    n_pre = 0 if r_vals is None else r_vals.size
+    base, rem = divmod(n_eigenvalues - n_pre, n_batches)
     batches = [b for b in [base + 1] * rem + [base] * (n_batches - rem) if b > 0]
     solver_op = op if solver_shift == 0.0 else ssl.LinearOperator(shape=op.shape, dtype=op.dtype,
                                                                    matvec=lambda x: op.matvec(x) + solver_shift * x)
-    vals, vecs = None, None
+    vals, vecs = r_vals, r_vecs
     for count, batch in enumerate(batches, start=1):
         if verbose:
             logger.info(f"\nNumber of eigenvalues being computed: {batch}")
@@ -145,10 +175,10 @@ def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samp
         raise NotImplementedError("slq_kwargs / slq_jit are not provided on the B200 path; trace_log_method='eigsh', the stochastic Lanczos "
                                   "quadrature trace_log_method='slq' (plain, or hybrid with n_eigenvalues exact eigenvalues deflated, optionally "
                                   "with use_radau_as_bound=True) and analytic_prior_term are")
-    if resume_eigenvectors is not None or resume_eigenvalues is not None:
-        raise NotImplementedError("resuming from a stored eigensystem is not supported on the B200 path")
     if likelihood.signal.cf.plan.dist:
         raise NotImplementedError("estimate_evidence_lower_bound on slab-decomposed fields is not supported")
+    if orthonormalize_eigenvectors and resume_eigenvectors is not None and resume_eigenvalues is None:
+        raise ValueError("resume_eigenvalues is required when orthonormalize_eigenvectors=True.")
     if orthonormalize_eigenvectors and (not isinstance(orthonormalize_every_n_batches, int) or orthonormalize_every_n_batches < 1):
         raise ValueError("orthonormalize_every_n_batches must be a positive integer.")
 
@@ -195,7 +225,8 @@ def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samp
                 op, op_size, int(n_eigenvalues), n_relevant, min_lh_eval=min_lh_eval, eigenvalue_shift=eig_shift, solver_shift=solver_shift,
                 n_batches=n_batches, tol=tol, early_stop=False, verbose=verbose, output_directory=output_directory,
                 prefix=f"{save_eigensystem_prefix}_{'data' if use_data else 'signal'}", orthonormalize=orthonormalize_eigenvectors,
-                every=orthonormalize_every_n_batches, threshold=orthonormalize_threshold, n_probes=orthonormalize_n_probes)
+                every=orthonormalize_every_n_batches, threshold=orthonormalize_threshold, n_probes=orthonormalize_n_probes,
+                resume_eigenvectors=resume_eigenvectors, resume_eigenvalues=resume_eigenvalues)
             exact_log = float(np.sum(log_np(eigenvalues)))
         if use_radau_as_bound and eigenvalues.size == 0:
             raise ValueError("use_radau_as_bound=True requires a valid upper spectral endpoint from at least one exact eigenvalue.")
@@ -261,7 +292,7 @@ def estimate_evidence_lower_bound(likelihood: LikelihoodWithModel, samples: Samp
         op, op_size, int(n_eigenvalues), n_relevant, min_lh_eval=min_lh_eval, eigenvalue_shift=eig_shift, solver_shift=solver_shift,
         n_batches=n_batches, tol=tol, early_stop=not compute_all, verbose=verbose, output_directory=output_directory, prefix=prefix,
         orthonormalize=orthonormalize_eigenvectors, every=orthonormalize_every_n_batches, threshold=orthonormalize_threshold,
-        n_probes=orthonormalize_n_probes)
+        n_probes=orthonormalize_n_probes, resume_eigenvectors=resume_eigenvectors, resume_eigenvalues=resume_eigenvalues)
     if verbose:
         logger.info(f"\nComputed {eigenvalues.size} largest eigenvalues (out of {n_relevant} relevant degrees of freedom).")
 

@@ -1,6 +1,8 @@
 """Sampling / KL checks shared by the CPU (emulator) and GPU tiers: the product's host drivers
 (nifty_b200.evi / optimize_kl, mirrors of nifty.re) against the oracle restatement on identical
 white-noise inputs."""
+import os
+
 import numpy as np
 import torch
 
@@ -681,6 +683,23 @@ def check_elbo_hybrid(rt, name="g2d_16x16"):
             assert st["lower_error"] >= 0.0 and np.isfinite(st["lower_error"])
             assert abs(st["elbo_mean"] - exact.mean()) <= 5.0 * st["slq_stochastic_se"] + 1e-3 * abs(exact.mean())
             assert st["elbo_lw"] <= st["elbo_mean"] <= st["elbo_up"]
+    # resuming a stored eigensystem (:199-268): 10 eigenpairs written by a first call, the remaining 14 computed by the second one
+    import tempfile
+    d = tempfile.mkdtemp()
+    nb.estimate_evidence_lower_bound(lh, smp, 10, n_batches=2, min_lh_eval=1e-12, output_directory=d, verbose=False)
+    vals, vecs = np.load(os.path.join(d, "metric_signal_eigenvalues.npy")), np.load(os.path.join(d, "metric_signal_eigenvectors.npy"))
+    assert vals.shape == (10,) and vecs.shape == (L, 10)
+    el_r, st_r = nb.estimate_evidence_lower_bound(lh, smp, n, n_batches=2, min_lh_eval=1e-12, resume_eigenvectors=vecs, resume_eigenvalues=vals,
+                                                  verbose=False)
+    np.testing.assert_allclose(el_r, -0.5 * np.sum(np.log(eig[:n])) + 0.5 * L - ham, rtol=1e-8)
+    with pytest.raises(ValueError, match="does not match the selected operator"):
+        nb.estimate_evidence_lower_bound(lh, smp, n, resume_eigenvectors=vecs, resume_eigenvalues=2.0 * vals, verbose=False)
+    with pytest.raises(ValueError, match="mismatched sizes"):
+        nb.estimate_evidence_lower_bound(lh, smp, n, resume_eigenvectors=vecs, resume_eigenvalues=vals[:5], verbose=False)
+    with pytest.raises(ValueError, match="requires resume_eigenvectors"):
+        nb.estimate_evidence_lower_bound(lh, smp, n, resume_eigenvalues=vals, verbose=False)
+    with pytest.raises(ValueError, match="resume_eigenvalues is required"):
+        nb.estimate_evidence_lower_bound(lh, smp, n, resume_eigenvectors=vecs, verbose=False)
     # analytic_prior_term (:809-824, 953-979): the prior energy in closed form, 1/2 (tr (M + 1)^-1 + <mean, mean>)
     lh_e = np.array([olh.energy(lay.unpack(pos + r)) for r in res])
     prior = 0.5 * (np.sum(1.0 / eig) + pos @ pos)
