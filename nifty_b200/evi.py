@@ -118,12 +118,35 @@ class Samples:
         return 0 if self._samples is None else int(self._samples.shape[0])
 
     def __getitem__(self, i):
+        if self._samples is None:
+            raise ValueError(f"{self.__class__.__name__} has no samples")
         r = self._samples[i]
         return r if self._pos is None else self._pos + r
 
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+    def __eq__(self, other) -> bool:
+        if not isinstance(other, self.__class__):
+            return False
+        if self._samples is None or other._samples is None:
+            return self._samples is None and other._samples is None
+        a, b = self.samples, other.samples
+        return a.shape == b.shape and bool(torch.equal(a, b))
+
+    __hash__ = None
+
     def at(self, pos, old_pos=None):
-        """Same residuals around a new expansion point (evi.py:360-372)."""
-        return Samples(pos=pos, samples=self._samples, keys=self._keys)
+        """New offset for all samples (evi.py:365-376): the same residuals around ``pos``; with ``old_pos`` that offset is first
+        subtracted from the full samples."""
+        if self._pos is not None and old_pos is None:
+            smpls = self._samples
+        elif old_pos is not None:
+            smpls = self.samples - old_pos[None]
+        else:
+            raise ValueError("invalid combination of `pos` and `old_pos`")
+        return Samples(pos=pos, samples=smpls, keys=self._keys)
 
     def squeeze(self):
         return Samples(pos=self._pos, samples=None if self._samples is None else self._samples.reshape((-1,) + tuple(self._samples.shape[2:])), keys=self._keys)

@@ -146,3 +146,26 @@ def test_random_like_tree_form():
     from nifty_b200.evi import random_normal
     assert torch.equal(t["a"], random_normal(ka, (4,), torch.float32, "cpu"))
     assert isinstance(nb.random_like(1, nb.Vector({"x": (2,)})), nb.Vector)
+
+
+def test_samples_container():
+    """`Samples` (evi.py:300-396): residuals around a position, iteration, equality, re-centring."""
+    import pytest
+    import torch
+    import nifty_b200 as nb
+    pos = torch.arange(4.0)
+    res = torch.stack((torch.ones(4), -torch.ones(4), 2.0 * torch.ones(4)))
+    s = nb.Samples(pos=pos, samples=res, keys=[1, 2])
+    assert len(s) == 3 and torch.equal(s[1], pos - 1.0) and torch.equal(s.samples, pos[None] + res)
+    assert [float(x[0]) for x in s] == [1.0, -1.0, 2.0]
+    assert s == nb.Samples(pos=pos.clone(), samples=res.clone()) and s != nb.Samples(pos=pos + 1.0, samples=res) and s != 3
+    moved = s.at(pos + 10.0)
+    assert torch.equal(moved.residuals, res) and torch.equal(moved[0], pos + 11.0) and moved.keys == [1, 2]
+    raw = nb.Samples(pos=None, samples=pos[None] + res)                      # full samples without an offset
+    recentred = raw.at(pos, old_pos=pos)
+    assert torch.equal(recentred.residuals, res) and recentred == s
+    with pytest.raises(ValueError):
+        raw.at(pos)
+    with pytest.raises(ValueError):
+        nb.Samples(pos=pos, samples=None)[0]
+    assert len(nb.Samples(pos=pos, samples=None)) == 0
