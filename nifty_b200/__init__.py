@@ -12,7 +12,7 @@ from .tree import Layout  # noqa: F401
 from .correlated_field import CorrelatedField, CorrelatedFieldMaker  # noqa: F401
 from .likelihood import Gaussian, Likelihood, LikelihoodWithModel, OperatorLikelihood, Poissonian, SignalModel  # noqa: F401
 from .conjugate_gradient import CGResults, HamiltonianMetric, cg, static_cg  # noqa: F401
-from .optimize import OptimizeResults, newton_cg, static_newton_cg  # noqa: F401
+from .optimize import OptimizeResults, minimize, newton_cg, static_newton_cg  # noqa: F401
 from .evi import (Samples, concatenate_zip, draw_linear_residual, draw_residual, nonlinearly_update_residual,  # noqa: F401
                   random_like, random_split, sample_likelihood, wiener_filter_posterior)
 from .optimize_kl import OptimizeVI, OptimizeVIState, get_status_message, optimize_kl  # noqa: F401

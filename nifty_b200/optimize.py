@@ -25,8 +25,45 @@ class OptimizeResults(NamedTuple):
     nhev: int
 
 
+def _prepare_fun_vag_hessp(fun, jac, hessp, fun_and_grad):
+    """``(fun, fun_and_grad, hessp)`` from whatever the caller supplied (optimize.py:75-111).  The reference fills the gaps with
+    ``jax.value_and_grad`` / ``jvp(grad)``; here a scalar torch function of a flat tensor is differentiated with torch autograd
+    (Hessian-vector products by double backward).  The operators of the hot path always arrive as ``fun_and_grad`` / ``hessp``."""
+    if fun_and_grad is None:
+        if fun is not None and jac is not None:
+            def fun_and_grad(x):
+                return fun(x), jac(x)
+        elif fun is not None:
+            def fun_and_grad(x):
+                with torch.enable_grad():
+                    xr = x.detach().clone().requires_grad_(True)
+                    v = fun(xr)
+                    (g,) = torch.autograd.grad(v, xr)
+                return float(v.detach()), g.detach()
+        else:
+            raise ValueError("no function specified")
+    if hessp is None:
+        if jac is None and fun is None:
+            raise ValueError("`hessp` (or `fun` / `jac` to differentiate) is required")
+
+        def hessp(primals, tangents):
+            with torch.enable_grad():
+                xr = primals.detach().clone().requires_grad_(True)
+                if jac is not None:
+                    g = jac(xr)
+                else:
+                    (g,) = torch.autograd.grad(fun(xr), xr, create_graph=True)
+                (hv,) = torch.autograd.grad(g, xr, grad_outputs=tangents.detach(), allow_unused=True)
+            return torch.zeros_like(primals) if hv is None else hv.detach()
+    if fun is None:
+        def fun(primals):
+            return fun_and_grad(primals)[0]
+    return fun, fun_and_grad, hessp
+
+
 def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reduction_factor=0.1, old_fval=None, absdelta=None,
-               norm_ord=None, xtol=1e-5, fun_and_grad: Optional[Callable] = None, hessp: Optional[Callable] = None,
+               norm_ord=None, xtol=1e-5, jac: Optional[Callable] = None, fun_and_grad: Optional[Callable] = None,
+               hessp: Optional[Callable] = None,
                cg=_cg, name=None, time_threshold=None, cg_kwargs=None, custom_gradnorm: Optional[Callable] = None,
                hessp_at: Optional[Callable] = None, vdot: Optional[Callable] = None,
                vnorm: Optional[Callable] = None, _size: Optional[int] = None) -> OptimizeResults:
@@ -37,13 +74,19 @@ def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reductio
     _nrm = _norm if vnorm is None else vnorm
     miniter = 0 if miniter is None else miniter
     maxiter = 200 if maxiter is None else maxiter
+    maxiter = np.iinfo(np.int64).max if np.isinf(maxiter) else int(maxiter)
     pos = x0.clone()
     xtol = xtol * (pos.numel() if _size is None else _size)      # _size: number of non-frozen entries (point estimates)
     cg_kwargs = {} if cg_kwargs is None else dict(cg_kwargs)
     cg_name = cg_kwargs.pop("name", name + "CG" if name is not None else None)      # optimize.py:302
     gradnorm = (lambda v: _nrm(v, norm_ord)) if custom_gradnorm is None else custom_gradnorm
-    if fun_and_grad is None:
-        raise ValueError("`fun_and_grad` is required on the B200 path (no automatic differentiation)")
+    if hessp_at is None or fun_and_grad is None:
+        fun, fun_and_grad, hessp = _prepare_fun_vag_hessp(fun, jac, hessp, fun_and_grad)
+    _fg = fun_and_grad
+
+    def fun_and_grad(x):                      # user functions may return 0-d tensors: the control flow below works on floats
+        v, gr = _fg(x)
+        return float(v), gr
     energy, g = fun_and_grad(pos)
     nfev, njev, nhev = 1, 1, 0
     if np.isnan(energy):
@@ -115,3 +158,18 @@ def newton_cg(*args, **kwargs):
 
 
 static_newton_cg = newton_cg
+
+
+def minimize(fun, x0, args=(), *, method: str, tol=None, options=None) -> OptimizeResults:
+    """``jft.minimize`` (optimize.py:863-892).  Newton-CG only: the trust-region minimiser is an alternative outside the path."""
+    options = {} if options is None else dict(options)
+    if not isinstance(args, tuple):
+        raise TypeError(f"args argument must be a tuple, got {type(args)!r}")
+    fun_with_args = (lambda x: fun(x, *args)) if args else fun
+    if tol is not None:
+        raise ValueError("use solver-specific options")
+    if method.lower() in ("newton-cg", "newtoncg", "ncg"):
+        return _newton_cg(fun_with_args, x0, **options)
+    if method.lower() in ("trust-ncg", "trustncg"):
+        raise NotImplementedError("trust-ncg is outside the B200 path (SURVEY.md section 2); use method='newton-cg'")
+    raise ValueError(f"method {method} not recognized")

@@ -169,3 +169,63 @@ def test_samples_container():
     with pytest.raises(ValueError):
         nb.Samples(pos=pos, samples=None)[0]
     assert len(nb.Samples(pos=pos, samples=None)) == 0
+
+
+def _rosenbrock(x):
+    import torch
+    return torch.sum(100.0 * torch.diff(x) ** 2 + (1.0 - x[:-1]) ** 2)
+
+
+def _matyas(p):
+    return 0.26 * (p[0] ** 2 + p[1] ** 2) - 0.48 * p[0] * p[1]
+
+
+def _eggholder(p):
+    import torch
+    x, y = p[0], p[1]
+    return -(y + 47) * torch.sin(torch.sqrt(torch.abs(x / 2.0 + y + 47.0))) - x * torch.sin(torch.sqrt(torch.abs(x - (y + 47.0))))
+
+
+def test_minimize_ncg_on_plain_functions():
+    """test/test_re/test_ncg.py:225-257 restated on the product's Newton-CG: a scalar function alone (gradient and Hessian-vector
+    products from autograd), `maxiter` None / inf, against SciPy's trust-ncg at rtol 2e-6; plus the `fun` + `jac` form of :94-109
+    and the `minimize(method=...)` dispatcher (:863-892)."""
+    import numpy as np
+    import pytest
+    import torch
+    from scipy.optimize import minimize as opt_minimize
+    import nifty_b200 as nb
+    for func, x0 in ((_rosenbrock, torch.zeros(2, dtype=torch.float64)), (_matyas, 6.0 * torch.ones(2, dtype=torch.float64)),
+                     (_eggholder, 100.0 * torch.ones(2, dtype=torch.float64))):
+        def f_np(x):
+            return float(func(torch.as_tensor(x, dtype=torch.float64)))
+
+        def g_np(x):
+            xr = torch.as_tensor(x, dtype=torch.float64).requires_grad_(True)
+            return torch.autograd.grad(func(xr), xr)[0].numpy()
+
+        def h_np(x):
+            return torch.autograd.functional.hessian(func, torch.as_tensor(x, dtype=torch.float64)).numpy()
+
+        ref = opt_minimize(f_np, x0.numpy(), jac=g_np, hess=h_np, method="trust-ncg").x
+        for maxiter in (np.inf, None):
+            res = nb.newton_cg(func, x0, maxiter=maxiter, xtol=1e-6, energy_reduction_factor=None, name="N")
+            np.testing.assert_allclose(res.numpy(), ref, rtol=2e-6, atol=2e-5)
+    x = torch.as_tensor(np.random.default_rng(12).standard_normal(3))
+    diag = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)
+    fun = lambda y: torch.sum(y ** 2 / diag) / 2 - torch.dot(x, y)        # noqa: E731
+    grad = lambda y: y / diag - x                                        # noqa: E731
+    met = lambda y, t: t / diag                                          # noqa: E731
+    for kwargs in ({"fun": fun, "jac": grad}, {"fun_and_grad": lambda y: (float(fun(y)), grad(y))}, {"fun": fun}):
+        res = nb.newton_cg(x0=x, hessp=met if "jac" in kwargs or "fun_and_grad" in kwargs else None, maxiter=20, absdelta=1e-6, name="N", **kwargs)
+        np.testing.assert_allclose(res.numpy(), (diag * x).numpy(), rtol=1e-4, atol=1e-4)
+    opt = nb.minimize(fun, x, method="newton-cg", options=dict(hessp=met, maxiter=20, absdelta=1e-6))
+    np.testing.assert_allclose(opt.x.numpy(), (diag * x).numpy(), rtol=1e-4, atol=1e-4)
+    with pytest.raises(NotImplementedError):
+        nb.minimize(fun, x, method="trust-ncg")
+    with pytest.raises(ValueError):
+        nb.minimize(fun, x, method="bfgs")
+    with pytest.raises(ValueError):
+        nb.minimize(fun, x, method="ncg", tol=1e-3)
+    with pytest.raises(TypeError):
+        nb.minimize(fun, x, args=[1], method="ncg")
