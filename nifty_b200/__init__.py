@@ -17,7 +17,7 @@ from .evi import (Samples, concatenate_zip, draw_linear_residual, draw_residual,
                   random_like, random_split, sample_likelihood, wiener_filter_posterior)
 from .optimize_kl import OptimizeVI, OptimizeVIState, get_status_message, optimize_kl  # noqa: F401
 from .minisanity import ChiSqStats, minisanity, reduced_residual_stats  # noqa: F401
-from .tree_math import (Vector, get_map, lmap, mean, mean_and_std, norm, size, smap, stack, unstack, vdot, where,  # noqa: F401
+from .tree_math import (Vector, get_map, lmap, mean, mean_and_std, norm, ravel, size, smap, stack, unstack, vdot, where,  # noqa: F401
                         zeros_like)
 from .model import Initializer, LazyModel, Model, VModel, WrappedCall  # noqa: F401
 from .evidence_lower_bound import estimate_evidence_lower_bound  # noqa: F401

@@ -120,6 +120,14 @@ def _cg(mat: Callable, j: torch.Tensor, x0: Optional[torch.Tensor] = None, *, ab
         norm_ord=None, tol=1e-5, atol=0.0, miniter=None, maxiter=None, name=None, time_threshold=None,
         _raise_nonposdef=True, check_every=4, vdot=None, vnorm=None) -> CGResults:
     """``vdot`` / ``vnorm``: reductions to use in the host loop (slab-decomposed vectors: all-reduced ones)."""
+    if not isinstance(j, torch.Tensor):
+        # latent trees / Vectors (the reference's cg acts on pytrees): solve on the raveled vector with `mat` wrapped accordingly
+        from .tree_math import ravel
+        flat_j, unravel = ravel(j)
+        res = _cg(lambda v: ravel(mat(unravel(v)))[0], flat_j, None if x0 is None else ravel(x0)[0], absdelta=absdelta, resnorm=resnorm,
+                  norm_ord=norm_ord, tol=tol, atol=atol, miniter=miniter, maxiter=maxiter, name=name, time_threshold=time_threshold,
+                  _raise_nonposdef=_raise_nonposdef, check_every=check_every, vdot=vdot, vnorm=vnorm)
+        return res._replace(x=unravel(res.x))
     norm_ord = 2 if norm_ord is None else norm_ord
     vdot = (lambda a, b: float(torch.dot(a, b))) if vdot is None else vdot
     vnorm = _norm if vnorm is None else vnorm

@@ -69,6 +69,22 @@ def _newton_cg(fun=None, x0=None, *, miniter=None, maxiter=None, energy_reductio
                vnorm: Optional[Callable] = None, _size: Optional[int] = None) -> OptimizeResults:
     """``hessp(pos, v)`` as in the reference; ``hessp_at(pos)`` may instead return an operator object
     (e.g. a :class:`~nifty_b200.conjugate_gradient.HamiltonianMetric`) so that the inner CG runs on the device."""
+    if x0 is not None and not isinstance(x0, torch.Tensor):
+        # latent trees / Vectors (the reference's solvers act on pytrees, test/test_re/test_ncg.py:41-77): solve on the raveled vector
+        from .tree_math import ravel
+        flat0, unravel = ravel(x0)
+        fl = lambda t: ravel(t)[0]                                  # noqa: E731
+        wrap1 = lambda f: None if f is None else (lambda x: f(unravel(x)))                       # noqa: E731
+        res = _newton_cg(wrap1(fun), flat0, miniter=miniter, maxiter=maxiter, energy_reduction_factor=energy_reduction_factor,
+                         old_fval=old_fval, absdelta=absdelta, norm_ord=norm_ord, xtol=xtol,
+                         jac=None if jac is None else (lambda x: fl(jac(unravel(x)))),
+                         fun_and_grad=None if fun_and_grad is None else (lambda x: (lambda v, g: (v, fl(g)))(*fun_and_grad(unravel(x)))),
+                         hessp=None if hessp is None else (lambda x, t: fl(hessp(unravel(x), unravel(t)))),
+                         cg=cg, name=name, time_threshold=time_threshold, cg_kwargs=cg_kwargs,
+                         custom_gradnorm=None if custom_gradnorm is None else (lambda g: custom_gradnorm(unravel(g))),
+                         hessp_at=None if hessp_at is None else (lambda x: (lambda op: (lambda t: fl(op(unravel(t)))))(hessp_at(unravel(x)))),
+                         vdot=vdot, vnorm=vnorm, _size=_size)
+        return res._replace(x=unravel(res.x), jac=None if res.jac is None else unravel(res.jac))
     norm_ord = 1 if norm_ord is None else norm_ord
     _dot = (lambda a, b: float(torch.dot(a, b))) if vdot is None else vdot
     _nrm = _norm if vnorm is None else vnorm

@@ -75,6 +75,38 @@ def _map(f, *trees):
     return f(*trees)
 
 
+def ravel(tree):
+    """``(flat, unravel)``: the leaves of a latent tree concatenated into one vector (sorted dict keys, as everywhere in this
+    package) and the inverse map; what ``jax.flatten_util.ravel_pytree`` is to the reference's solvers, which work on pytrees
+    directly.  ``unravel`` restores structure, shapes, dtypes and the ``Vector`` wrapper."""
+    wrap = isinstance(tree, Vector)
+    t = tree.tree if wrap else tree
+    leaves = [torch.as_tensor(l) for l in _leaves(t)]
+    dt = leaves[0].dtype
+    for l in leaves[1:]:
+        dt = torch.promote_types(dt, l.dtype)
+    flat = torch.cat([l.reshape(-1).to(dt) for l in leaves]) if leaves else torch.zeros(0)
+    shapes, dtypes = [tuple(l.shape) for l in leaves], [l.dtype for l in leaves]
+
+    def unravel(v):
+        it, off = [], 0
+        for shp, d in zip(shapes, dtypes):
+            n = int(np.prod(shp)) if shp else 1
+            it.append(v[off:off + n].reshape(shp).to(d))
+            off += n
+        pieces = iter(it)
+
+        def build(node):
+            if isinstance(node, dict):
+                return {k: build(node[k]) for k in sorted(node)}
+            if isinstance(node, (tuple, list)):
+                return type(node)(build(c) for c in node)
+            return next(pieces)
+        out = build(t)
+        return Vector(out) if wrap else out
+    return flat, unravel
+
+
 def vdot(a, b) -> float:
     return float(sum(torch.dot(torch.as_tensor(x).reshape(-1), torch.as_tensor(y).reshape(-1)) for x, y in zip(_leaves(a), _leaves(b))))
 

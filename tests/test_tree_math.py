@@ -229,3 +229,38 @@ def test_minimize_ncg_on_plain_functions():
         nb.minimize(fun, x, method="ncg", tol=1e-3)
     with pytest.raises(TypeError):
         nb.minimize(fun, x, args=[1], method="ncg")
+
+
+def test_solvers_on_latent_trees():
+    """test/test_re/test_ncg.py:41-77 restated: Newton-CG on a nested position tree (`Vector` of list / tuple / dict, float32 leaves)
+    with a tree-valued metric; and `cg` on a `Vector` right-hand side (:112-124)."""
+    import numpy as np
+    import torch
+    import nifty_b200 as nb
+    from nifty_b200.tree_math import ravel
+    pos = nb.Vector([torch.tensor(0.0, dtype=torch.float32), (torch.tensor(3.0, dtype=torch.float32),), {"a": torch.tensor(5.0, dtype=torch.float32)}])
+    getters = (lambda x: x[0], lambda x: x[1][0], lambda x: x[2]["a"])
+    tgt, met = [-10.0, 1.0, 2.0], [10.0, 40.0, 2.0]
+
+    def model_and_grad(p):
+        val = sum((get(p) - tgt[i]) ** 2 * met[i] for i, get in enumerate(getters))
+        grad = nb.Vector([2 * (p[0] - tgt[0]) * met[0], (2 * (p[1][0] - tgt[1]) * met[1],), {"a": 2 * (p[2]["a"] - tgt[2]) * met[2]}])
+        return float(val), grad
+
+    def metric(p, tan):
+        return nb.Vector([tan[0] * met[0], (tan[1][0] * met[1],), {"a": tan[2]["a"] * met[2]}])
+
+    res = nb.newton_cg(fun_and_grad=model_and_grad, x0=pos, hessp=metric, maxiter=10, absdelta=1e-6)
+    assert isinstance(res, nb.Vector) and isinstance(res.tree[1], tuple) and res[0].dtype == torch.float32
+    for i, get in enumerate(getters):
+        np.testing.assert_allclose(float(get(res)), tgt[i], atol=1e-6, rtol=1e-5)
+    flat, unravel = ravel(pos)
+    assert flat.shape == (3,) and torch.equal(ravel(unravel(flat))[0], flat)
+    # cg on a Vector (diagonal operator, known answer)
+    diag = {"u": torch.tensor([1.0, 2.0], dtype=torch.float64), "v": torch.tensor([[3.0]], dtype=torch.float64)}
+    x = nb.Vector({"u": torch.tensor([0.3, -1.2], dtype=torch.float64), "v": torch.tensor([[0.7]], dtype=torch.float64)})
+    mat = lambda t: nb.Vector({k: t[k] / diag[k] for k in diag})        # noqa: E731
+    sol, info = nb.cg(mat, x, resnorm=1e-8, absdelta=1e-10)
+    assert info == 0 and isinstance(sol, nb.Vector)
+    for k in diag:
+        np.testing.assert_allclose(sol[k].numpy(), (diag[k] * x[k]).numpy(), rtol=1e-6)
