@@ -188,6 +188,10 @@ class LikelihoodWithModel:
         self._lins = []     # small cache of linearisations: [(key, Lin)]
         self._max_lins = 3
 
+    def __add__(self, other):
+        """``lh_a + lh_b`` (likelihood.py:383-384): the sum of amended likelihoods on the union of their latent domains."""
+        return LikelihoodSum(self, other)
+
     # -- linearisation cache --------------------------------------------------------------------
     @staticmethod
     def _key(flat: torch.Tensor):
@@ -452,3 +456,191 @@ class OperatorLikelihood(LikelihoodWithModel):
         if len(self._lins) > self._max_lins:
             self._lins.pop(0)
         return lin, grad
+
+
+class _SumSignal:
+    """What the drivers ask of ``likelihood.signal`` for a sum of likelihoods: the joint latent layout and a 1-D data space (the
+    summands' data vectors one after the other)."""
+
+    class _CfStub:
+        def __init__(self, plan, prefix):
+            self.plan, self.prefix = plan, prefix
+
+    def __init__(self, layout: Layout, n_data: int, rt, dtype, plan, prefix):
+        self.layout, self.domain = layout, dict(layout.shapes)
+        self.target_shape, self.rt, self.dtype = (int(n_data),), rt, dtype
+        self.cf = _SumSignal._CfStub(plan, prefix)
+        self.scaling, self.nl_fn, self.nonlinearity = None, None, "sum"
+
+    target = property(lambda self: self.target_shape)
+
+    def as_flat(self, pos) -> torch.Tensor:
+        pos = getattr(pos, "tree", pos)
+        if isinstance(pos, torch.Tensor):
+            if pos.numel() != self.layout.size:
+                raise ValueError(f"latent vector has {pos.numel()} entries, expected {self.layout.size}")
+            return self.rt.asarray(pos.reshape(-1), self.dtype)
+        return self.layout.pack(pos, self.dtype, self.rt.device)
+
+    def like(self, template, vec):
+        if isinstance(template, torch.Tensor):
+            return vec
+        if hasattr(template, "tree") and not isinstance(template, dict):
+            from .tree_math import Vector
+            return Vector(self.layout.unpack(vec))
+        return self.layout.unpack(vec)
+
+
+class SumLin:
+    """Linearisation of a sum of amended likelihoods: one child linearisation per summand, latent vectors gathered from / scattered
+    into the joint layout, data-space vectors concatenated.  Same interface as ``Lin``; CG solves run the host loop."""
+
+    host_composed = True
+
+    def __init__(self, lh: "LikelihoodSum"):
+        self.lh, self.rt = lh, lh.rt
+        self.children = [c.new_lin() for c in lh.likelihood_summands]
+        self.model = _SumSignal._CfStub(lh.signal.cf.plan, "")
+        self.model.plan = lh.signal.cf.plan
+
+    def _gather(self, i, v):
+        return v[self.lh._index[i]]
+
+    def _scatter_add(self, out, i, v):
+        out.index_add_(0, self.lh._index[i], v.to(out.dtype))
+        return out
+
+    def _split(self, u):
+        u = self.rt.asarray(u, self.lh.dtype).reshape(-1)
+        return [u[a:b].reshape(shp) for (a, b), shp in zip(self.lh._data_ranges, self.lh._data_shapes)]
+
+    def update(self, pos, want_grad=False, add_prior=False):
+        pos = self.lh.signal.as_flat(pos)
+        grad = torch.zeros_like(pos) if want_grad else None
+        for i, c in enumerate(self.children):
+            g = c.update(self._gather(i, pos).contiguous(), want_grad=want_grad, add_prior=False)
+            if want_grad:
+                self._scatter_add(grad, i, g)
+        if want_grad and add_prior:
+            grad += pos
+        return grad
+
+    def energy(self) -> float:
+        return float(sum(c.energy() for c in self.children))
+
+    def signal(self):
+        return torch.cat([c.signal().reshape(-1) for c in self.children])
+
+    def metric(self, t, add_identity=False, out=None):
+        r = t.clone() if add_identity else torch.zeros_like(t)
+        for i, c in enumerate(self.children):
+            self._scatter_add(r, i, c.metric(self._gather(i, t).contiguous()))
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
+
+    def rsm(self, t, scaled=True):
+        return torch.cat([c.rsm(self._gather(i, t).contiguous(), scaled=scaled).reshape(-1) for i, c in enumerate(self.children)])
+
+    def lsm(self, u, scaled=True):
+        r = torch.zeros(self.lh.layout.size, dtype=self.lh.dtype, device=self.rt.device)
+        for i, (c, ui) in enumerate(zip(self.children, self._split(u))):
+            self._scatter_add(r, i, c.lsm(ui.contiguous(), scaled=scaled))
+        return r
+
+    def metric_pair(self, other: "SumLin", t, add_identity=False):
+        r = self.lsm(other.rsm(t))
+        return r + t if add_identity else r
+
+    def transformation(self):
+        return torch.cat([c.transformation().reshape(-1) for c in self.children])
+
+    def normalized_residual(self):
+        return torch.cat([c.normalized_residual().reshape(-1) for c in self.children])
+
+
+class LikelihoodSum(LikelihoodWithModel):
+    """``jft.LikelihoodSum`` (likelihood.py:661-757) for amended likelihoods of this package: energies and metrics add on the union of
+    the latent domains (shared leaves -- e.g. two data sets seen through ONE correlated field -- are shared), the data spaces are kept
+    side by side (``right_sqrt_metric`` / ``transformation`` / ``normalized_residual`` return ``{"lh_0": ..., "lh_1": ...}``,
+    ``left_sqrt_metric`` takes such a dict).  Every summand keeps its own fused device products."""
+
+    def __init__(self, *likelihood_summands, _key_template="lh_{index}"):
+        flat = []
+        for i, lh in enumerate(likelihood_summands):
+            if not isinstance(lh, LikelihoodWithModel):
+                raise TypeError(f"object at position {i} which to add to this instance is of invalid type {type(lh)!r}")
+            flat += list(lh.likelihood_summands) if isinstance(lh, LikelihoodSum) else [lh]
+        self.likelihood_summands = tuple(flat)
+        self._key_template = _key_template
+        first = flat[0]
+        self.rt, self.dtype = first.rt, first.dtype
+        domain = {}
+        for lh in flat:
+            if lh.rt is not first.rt or lh.dtype != first.dtype:
+                raise ValueError("summands must share runtime and dtype")
+            if getattr(lh.signal.cf.plan, "dist", False):
+                raise NotImplementedError("sums of likelihoods on slab-decomposed fields are not supported")
+            for k, shp in lh.layout.shapes.items():
+                if k in domain and tuple(domain[k]) != tuple(shp):
+                    raise ValueError(f"leaf {k!r} has different shapes in the summands: {domain[k]} vs {shp}")
+                domain[k] = tuple(shp)
+        self.layout = Layout(domain)
+        self.domain = dict(self.layout.shapes)
+        dev = self.rt.device
+        self._index = []                                   # joint flat index of every entry of a summand's flat vector
+        for lh in flat:
+            idx = torch.cat([torch.arange(self.layout.offsets[k], self.layout.offsets[k] + self.layout.numel(k)) for k in lh.layout.keys])
+            self._index.append(idx.to(dev))
+        self._data_shapes = [tuple(lh.signal.target_shape) for lh in flat]
+        sizes = [int(np.prod(s)) for s in self._data_shapes]
+        ends = np.cumsum(sizes)
+        self._data_ranges = [(int(e - n), int(e)) for e, n in zip(ends, sizes)]
+        self.signal = _SumSignal(self.layout, int(ends[-1]), self.rt, self.dtype, first.signal.cf.plan, first.signal.cf.prefix)
+        self.likelihood = None
+        self._lins, self._max_lins = [], 3
+
+    def _items(self):
+        for i, lh in enumerate(self.likelihood_summands):
+            yield self._key_template.format(index=i, likelihood=lh), lh
+
+    def __add__(self, other):
+        return LikelihoodSum(*self.likelihood_summands, other)
+
+    def new_lin(self) -> SumLin:
+        return SumLin(self)
+
+    def lin_at(self, pos, want_grad=False, add_prior=False):
+        flat = self.signal.as_flat(pos)
+        key = self._key(flat)
+        if not want_grad:
+            for k, lin in self._lins:
+                if k == key:
+                    return lin, None
+        lin = SumLin(self)
+        grad = lin.update(flat, want_grad=want_grad, add_prior=add_prior)
+        lin._pos_ref = flat
+        self._lins.append((key, lin))
+        if len(self._lins) > self._max_lins:
+            self._lins.pop(0)
+        return lin, grad
+
+    # data-space quantities as dicts keyed like the reference's (:706-754)
+    def _as_dict(self, vec):
+        return {key: vec[a:b].reshape(shp) for (key, _), (a, b), shp in zip(self._items(), self._data_ranges, self._data_shapes)}
+
+    def right_sqrt_metric(self, pos, tangents):
+        return self._as_dict(super().right_sqrt_metric(pos, tangents))
+
+    def transformation(self, pos):
+        return self._as_dict(super().transformation(pos))
+
+    def normalized_residual(self, pos):
+        return self._as_dict(super().normalized_residual(pos))
+
+    def left_sqrt_metric(self, pos, tangents):
+        if isinstance(tangents, dict):
+            tangents = torch.cat([self.rt.asarray(tangents[key], self.dtype).reshape(-1) for key, _ in self._items()])
+        return super().left_sqrt_metric(pos, tangents)
+

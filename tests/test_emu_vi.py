@@ -101,3 +101,7 @@ def test_host_composed_wiener_filter_and_slq(rt):
 
 def test_evidence_lower_bound_hybrid_slq_with_radau_bounds(rt):
     vc.check_elbo_hybrid(rt)
+
+
+def test_likelihood_sum(rt):
+    vc.check_likelihood_sum(rt)

@@ -84,3 +84,7 @@ def test_gaussian_with_non_diagonal_covariance(rt, shape, nl):
 
 def test_evidence_lower_bound_hybrid_slq_with_radau_bounds(rt):
     vc.check_elbo_hybrid(rt)
+
+
+def test_likelihood_sum(rt):
+    vc.check_likelihood_sum(rt)

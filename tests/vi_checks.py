@@ -719,3 +719,73 @@ def check_elbo_hybrid(rt, name="g2d_16x16"):
         nb.estimate_evidence_lower_bound(lh, smp, n, trace_log_method="slq", slq_order=60, slq_num_samples=4, use_radau_as_bound=True, verbose=False)
     with pytest.raises(ValueError, match="at least two probes"):
         nb.estimate_evidence_lower_bound(lh, smp, 4, trace_log_method="slq", slq_num_samples=1, verbose=False)
+
+
+def check_likelihood_sum(rt):
+    """`lh_a + lh_b` (likelihood.py:661-757; reference check test/test_re/test_likelihood.py:103-168): (1) two data sets seen through
+    ONE correlated field against the single Gaussian they are equivalent to, (2) two different fields with different likelihoods on
+    the union of their latent domains against the summands evaluated one by one, (3) the drivers on the sum."""
+    import pytest
+    from parity_checks import build_product, tree_err
+    c = dict(shape=(16, 8), distances=(0.1, 0.2), offset_mean=0.1, offset_std=(0.2, 0.1), fluctuations=(0.5, 0.1), loglogavgslope=(-2.0, 0.3),
+             flexibility=(1.0, 0.5), asperity=(0.5, 0.05), lh="gauss")
+    rng = np.random.default_rng(9)
+    sig = nb.SignalModel(build_product(c, rt), "exp")
+    L = sig.layout.size
+    da, db = rng.standard_normal(c["shape"]) + 1.0, rng.standard_normal(c["shape"]) + 1.0
+    wa, wb = 4.0, 9.0
+    lh_a, lh_b = nb.Gaussian(da, noise_cov_inv=wa).amend(sig), nb.Gaussian(db, noise_cov_inv=wb).amend(sig)
+    lh_ab = lh_a + lh_b
+    assert isinstance(lh_ab, nb.LikelihoodSum) and lh_ab.layout.size == L and lh_ab.domain == sig.domain
+    one = nb.Gaussian((wa * da + wb * db) / (wa + wb), noise_cov_inv=wa + wb).amend(sig)
+    p1, p2, t = (0.3 * sig.layout.random(s, torch.float64, rt.device) for s in (1, 2, 3))
+    (e1, g1), (e2, _) = lh_ab.energy_and_gradient(p1), lh_ab.energy_and_gradient(p2)
+    (f1, h1), (f2, _) = one.energy_and_gradient(p1), one.energy_and_gradient(p2)
+    assert abs((e1 - f1) - (e2 - f2)) <= 1e-10 * abs(e1) and rel_err(t2n(g1), t2n(h1)) < 1e-10        # energies differ by a constant
+    assert abs(e1 - (lh_a.energy(p1) + lh_b.energy(p1))) <= 1e-12 * abs(e1)
+    assert rel_err(t2n(lh_ab.metric(p1, t)), t2n(one.metric(p1, t))) < 1e-10
+    rs = lh_ab.right_sqrt_metric(p1, t)
+    assert sorted(rs) == ["lh_0", "lh_1"] and rel_err(t2n(rs["lh_1"]), t2n(lh_b.right_sqrt_metric(p1, t))) < 1e-12
+    assert rel_err(t2n(lh_ab.left_sqrt_metric(p1, rs)), t2n(lh_ab.metric(p1, t))) < 1e-10            # metric == LSM o RSM
+    nr = lh_ab.normalized_residual(p1)
+    assert rel_err(t2n(nr["lh_0"]), t2n(lh_a.normalized_residual(p1))) < 1e-12
+    assert rel_err(t2n(lh_ab.transformation(p1)["lh_1"]), t2n(lh_b.transformation(p1))) < 1e-12
+    # (2) different fields and likelihoods: block structure on the union of the domains
+    c2 = dict(c, shape=(8, 8), distances=0.25)
+    cfm2 = nb.CorrelatedFieldMaker("other", runtime=rt)
+    cfm2.set_amplitude_total_offset(0.5, (0.2, 0.1))
+    cfm2.add_fluctuations(c2["shape"], c2["distances"], (0.3, 0.1), (-1.5, 0.3), (1.0, 0.5), None, prefix="ax", non_parametric_kind="amplitude")
+    sig2 = nb.SignalModel(cfm2.finalize(), "exp")
+    lh_c = nb.Poissonian(rng.poisson(2.0, size=c2["shape"])).amend(sig2)
+    both = lh_a + lh_c
+    assert set(both.domain) == set(sig.domain) | set(sig2.domain) and both.layout.size == L + sig2.layout.size
+    tree = {**{k: 0.3 * v for k, v in sig.layout.unpack(sig.layout.random(4, torch.float64, rt.device)).items()},
+            **{k: 0.3 * v for k, v in sig2.layout.unpack(sig2.layout.random(5, torch.float64, rt.device)).items()}}
+    tan = {**sig.layout.unpack(sig.layout.random(6, torch.float64, rt.device)), **sig2.layout.unpack(sig2.layout.random(7, torch.float64, rt.device))}
+    pa, pc = {k: tree[k] for k in sig.domain}, {k: tree[k] for k in sig2.domain}
+    e, g = both.energy_and_gradient(tree)
+    (ea, ga), (ec, gc) = lh_a.energy_and_gradient(pa), lh_c.energy_and_gradient(pc)
+    assert abs(e - (ea + ec)) <= 1e-12 * abs(e) and tree_err(g, {**{k: t2n(v) for k, v in ga.items()}, **{k: t2n(v) for k, v in gc.items()}}) < 1e-12
+    m = both.metric(tree, tan)
+    ma, mc = lh_a.metric(pa, {k: tan[k] for k in sig.domain}), lh_c.metric(pc, {k: tan[k] for k in sig2.domain})
+    assert tree_err(m, {**{k: t2n(v) for k, v in ma.items()}, **{k: t2n(v) for k, v in mc.items()}}) < 1e-12
+    assert isinstance(both + lh_b, nb.LikelihoodSum) and len((both + lh_b).likelihood_summands) == 3
+    with pytest.raises(TypeError):
+        lh_a + 3
+    # (3) the drivers: an MGVI draw solves (M + 1) x = LSM w_d + w_p, one optimize_kl iteration lowers the KL, the report lists both summands
+    pos = both.signal.as_flat(tree)
+    n_d = both.signal.target_shape[0]
+    wd, wp = rt.asarray(rng.standard_normal(n_d), torch.float64), rt.asarray(rng.standard_normal(both.layout.size), torch.float64)
+    res, info = nb.draw_linear_residual(both, pos, 0, cg_kwargs=dict(resnorm=1e-10, maxiter=4 * both.layout.size), _white=(wd, wp))
+    lin, _ = both.lin_at(pos)
+    assert info == 0 and rel_err(t2n(lin.metric(res, add_identity=True)), t2n(lin.lsm(wd) + wp)) < 1e-8
+    kw = dict(n_samples=1, key=5, sample_mode="nonlinear_resample", draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-8, maxiter=200)),
+              nonlinearly_update_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=30))),
+              kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=3, cg_kwargs=dict(maxiter=30))))
+    vi = nb.OptimizeVI(both, 1)
+    smp, st = nb.optimize_kl(both, pos, n_total_iterations=1, _optimize_vi=vi, **kw)
+    e1, _ = vi.kl_value_and_grad(smp.pos, smp.residuals)
+    e0, _ = vi.kl_value_and_grad(pos, smp.residuals)
+    assert st.nit == 1 and np.isfinite(e1) and e1 < e0
+    msg = vi.get_status_message(smp, st, name="OPTIMIZE_KL")
+    assert "lh_0" in msg and "lh_1" in msg and "otherxi" in msg
