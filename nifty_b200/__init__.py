@@ -10,7 +10,8 @@ from ._runtime import Lin, ModelHandle, Plan, Runtime, default_runtime  # noqa: 
 from .prior import LogNormalPrior, NormalPrior, lognormal_moments  # noqa: F401
 from .tree import Layout  # noqa: F401
 from .correlated_field import CorrelatedField, CorrelatedFieldMaker  # noqa: F401
-from .likelihood import (Gaussian, Likelihood, LikelihoodSum, LikelihoodWithModel, OperatorLikelihood, Poissonian,  # noqa: F401
+from .likelihood import (Gaussian, Likelihood, LikelihoodPartial, LikelihoodSum, LikelihoodWithModel, OperatorLikelihood,  # noqa: F401
+                         Poissonian,
                          SignalModel)
 from .conjugate_gradient import CGResults, HamiltonianMetric, cg, static_cg  # noqa: F401
 from .optimize import OptimizeResults, minimize, newton_cg, static_newton_cg  # noqa: F401

@@ -192,6 +192,14 @@ class LikelihoodWithModel:
         """``lh_a + lh_b`` (likelihood.py:383-384): the sum of amended likelihoods on the union of their latent domains."""
         return LikelihoodSum(self, other)
 
+    def freeze(self, *, primals, point_estimates):
+        """``(likelihood with the named leaves inserted at their value in primals, remaining liquid primals)``
+        (likelihood.py:386-393); no point estimates: ``(self, primals)``."""
+        if not point_estimates:
+            return self, primals
+        lp = LikelihoodPartial(self, primals=primals, point_estimates=point_estimates)
+        return lp, lp.splitx(primals)[0]
+
     # -- linearisation cache --------------------------------------------------------------------
     @staticmethod
     def _key(flat: torch.Tensor):
@@ -644,3 +652,64 @@ class LikelihoodSum(LikelihoodWithModel):
             tangents = torch.cat([self.rt.asarray(tangents[key], self.dtype).reshape(-1) for key, _ in self._items()])
         return super().left_sqrt_metric(pos, tangents)
 
+
+
+class LikelihoodPartial:
+    """``jft.LikelihoodPartial`` (likelihood.py:399-499, ``_parse_point_estimates`` :57-92, ``partial_insert_and_remove`` :119-177):
+    the likelihood as a function of the LIQUID leaves only, the frozen ones inserted at their value in ``primals``.  Positions and
+    tangents are dicts of the liquid leaves; every operator inserts (frozen values for positions, zeros for tangents), applies the
+    operator of the full likelihood -- the fused device products -- and removes the frozen leaves from latent-space results.  The
+    solvers of this package reach the same restriction through frozen ranges of full-length vectors instead (``frozen_ranges``)."""
+
+    def __init__(self, likelihood: LikelihoodWithModel, *, primals, point_estimates):
+        self.likelihood, self.point_estimates = likelihood, point_estimates
+        ranges = likelihood.frozen_ranges(point_estimates)           # validates the keys
+        lay = likelihood.layout
+        self.frozen_keys = [k for k in lay.keys if any(lo <= lay.offsets[k] < hi for lo, hi in ranges)]
+        self.liquid_keys = [k for k in lay.keys if k not in self.frozen_keys]
+        full = likelihood.layout.unpack(likelihood.signal.as_flat(primals))
+        self.primals_frozen = {k: full[k].clone() for k in self.frozen_keys}
+        self.domain = {k: lay.shapes[k] for k in self.liquid_keys}
+        self.rt, self.dtype = likelihood.rt, likelihood.dtype
+
+    def splitx(self, primals):
+        """``(liquid part, frozen part)`` of a full position."""
+        full = self.likelihood.layout.unpack(self.likelihood.signal.as_flat(primals))
+        return {k: full[k] for k in self.liquid_keys}, {k: full[k] for k in self.frozen_keys}
+
+    def _insert(self, liquid, zeros=False):
+        liquid = getattr(liquid, "tree", liquid)
+        if set(liquid) != set(self.liquid_keys):
+            raise ValueError(f"expected the liquid leaves {self.liquid_keys!r}, got {sorted(liquid)!r}")
+        tree = {k: torch.as_tensor(v, dtype=self.dtype, device=self.rt.device) if not isinstance(v, torch.Tensor) else v for k, v in liquid.items()}
+        for k, v in self.primals_frozen.items():
+            tree[k] = torch.zeros_like(v) if zeros else v
+        return tree
+
+    def _remove(self, tree):
+        tree = getattr(tree, "tree", tree)
+        return {k: tree[k] for k in self.liquid_keys}
+
+    def energy(self, primals) -> float:
+        return self.likelihood.energy(self._insert(primals))
+
+    __call__ = energy
+
+    def energy_and_gradient(self, primals):
+        e, g = self.likelihood.energy_and_gradient(self._insert(primals))
+        return e, self._remove(g)
+
+    def metric(self, primals, tangents):
+        return self._remove(self.likelihood.metric(self._insert(primals), self._insert(tangents, zeros=True)))
+
+    def left_sqrt_metric(self, primals, tangents):
+        return self._remove(self.likelihood.left_sqrt_metric(self._insert(primals), tangents))
+
+    def right_sqrt_metric(self, primals, tangents):
+        return self.likelihood.right_sqrt_metric(self._insert(primals), self._insert(tangents, zeros=True))
+
+    def transformation(self, primals):
+        return self.likelihood.transformation(self._insert(primals))
+
+    def normalized_residual(self, primals):
+        return self.likelihood.normalized_residual(self._insert(primals))

@@ -88,3 +88,8 @@ def test_evidence_lower_bound_hybrid_slq_with_radau_bounds(rt):
 
 def test_likelihood_sum(rt):
     vc.check_likelihood_sum(rt)
+
+
+def test_freeze_likelihood_partial(rt):
+    vc.check_freeze(rt)
+    vc.check_freeze(rt, "p2d_32x32", ("cfzeromode",))

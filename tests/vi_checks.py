@@ -789,3 +789,39 @@ def check_likelihood_sum(rt):
     assert st.nit == 1 and np.isfinite(e1) and e1 < e0
     msg = vi.get_status_message(smp, st, name="OPTIMIZE_KL")
     assert "lh_0" in msg and "lh_1" in msg and "otherxi" in msg
+
+
+def check_freeze(rt, name="g2d_16x16", frozen=("cfax1fluctuations", "cfax1spectrum")):
+    """`lh.freeze(primals=, point_estimates=)` -> (`LikelihoodPartial`, liquid primals) (likelihood.py:386-499; reference check
+    test/test_re/test_likelihood.py:53-89) against the oracle's removed-leaf formulation: energy, metric, sqrt-metrics,
+    transformation as functions of the liquid leaves only."""
+    c, g, lh, olh, lay = _setup(rt, name)
+    rng = np.random.default_rng(4)
+    pos, tan = {k: 0.3 * v for k, v in lay.random(rng).items()}, lay.random(rng)
+    tp = {k: torch.as_tensor(v) for k, v in pos.items()}
+    same, p_same = lh.freeze(primals=tp, point_estimates=())
+    assert same is lh and p_same is tp
+    lp, liquid = lh.freeze(primals=tp, point_estimates=frozen)
+    assert isinstance(lp, nb.LikelihoodPartial) and sorted(liquid) == sorted(k for k in pos if k not in frozen)
+    assert set(lp.domain) == set(liquid) and set(lp.splitx(tp)[1]) == set(frozen)
+    fz = oracle.vi._Frozen(olh, lay.pack(pos), frozen)
+    pl = fz.remove(lay.pack(pos))
+    tl = {k: torch.as_tensor(tan[k]) for k in liquid}
+
+    def pack_liquid(tree):          # liquid dict -> the oracle's packed vector with the frozen entries removed
+        full = {k: (t2n(tree[k]) if k in tree else np.zeros(lay.shapes[k])) for k in lay.keys}
+        return fz.remove(lay.pack(full))
+
+    assert abs(lp.energy(liquid) - olh.energy(pos)) <= 1e-10 * abs(olh.energy(pos))
+    assert rel_err(pack_liquid(lp.metric(liquid, tl)), fz.metric(pl, fz.remove(lay.pack(tan)))) < 1e-10
+    eta = rng.standard_normal(c["shape"])
+    assert rel_err(pack_liquid(lp.left_sqrt_metric(liquid, eta)), fz.lsm(pl, eta)) < 1e-10
+    assert rel_err(t2n(lp.right_sqrt_metric(liquid, tl)), fz.rsm(pl, fz.remove(lay.pack(tan)))) < 1e-10
+    assert rel_err(t2n(lp.transformation(liquid)), fz.trafo(pl)) < 1e-10
+    e, gr = lp.energy_and_gradient(liquid)
+    assert set(gr) == set(liquid)
+    import pytest
+    with pytest.raises(ValueError):
+        lp.energy(tp)                                   # a full position is not a liquid one
+    with pytest.raises(ValueError):
+        lh.freeze(primals=tp, point_estimates=("nope",))
