@@ -192,6 +192,24 @@ class LikelihoodWithModel:
         """``lh_a + lh_b`` (likelihood.py:383-384): the sum of amended likelihoods on the union of their latent domains."""
         return LikelihoodSum(self, other)
 
+    def init(self, seed):
+        """White latent position of the amended model (``LikelihoodWithModel`` forwards ``init`` of its model, likelihood.py:546-598)."""
+        return self.signal.init(seed)
+
+    @property
+    def left_sqrt_metric_tangents_shape(self):
+        """Shape of the data-space tangents of ``left_sqrt_metric`` (likelihood.py:352-363)."""
+        return tuple(self.signal.target_shape)
+
+    lsm_tangents_shape = left_sqrt_metric_tangents_shape
+
+    @property
+    def right_sqrt_metric_tangents_shape(self):
+        """The latent domain (likelihood.py:365-376)."""
+        return self.domain
+
+    rsm_tangents_shape = right_sqrt_metric_tangents_shape
+
     def freeze(self, *, primals, point_estimates):
         """``(likelihood with the named leaves inserted at their value in primals, remaining liquid primals)``
         (likelihood.py:386-393); no point estimates: ``(self, primals)``."""
@@ -489,6 +507,9 @@ class _SumSignal:
                 raise ValueError(f"latent vector has {pos.numel()} entries, expected {self.layout.size}")
             return self.rt.asarray(pos.reshape(-1), self.dtype)
         return self.layout.pack(pos, self.dtype, self.rt.device)
+
+    def init(self, seed):
+        return self.layout.unpack(self.layout.random(seed, self.dtype, self.rt.device))
 
     def like(self, template, vec):
         if isinstance(template, torch.Tensor):

@@ -158,3 +158,14 @@ def test_vmodel_axes(rt):
         assert torch.equal(out[..., i], cf(xi))
     with pytest.raises(ValueError):
         nb.VModel(cf, 3, in_axes=1)                # scalar leaves have no axis 1
+
+
+def test_likelihood_surface(rt):
+    """`init`, `lsm_tangents_shape`, `rsm_tangents_shape` of amended likelihoods (likelihood.py:352-376, 546-598), also on a sum."""
+    import vi_checks as vc
+    c, g, lh, olh, lay = vc._setup(rt, "g2d_16x16")
+    p = lh.init(3)
+    assert set(p) == set(lh.domain) and lh.lsm_tangents_shape == (16, 16) == lh.left_sqrt_metric_tangents_shape
+    assert lh.rsm_tangents_shape == lh.domain == lh.right_sqrt_metric_tangents_shape
+    s = lh + lh
+    assert s.lsm_tangents_shape == (512,) and abs(s.energy(s.init(3)) - 2.0 * lh.energy(p)) <= 1e-12 * abs(lh.energy(p))
