@@ -131,6 +131,41 @@ def _grid_record(pl: Plan):
     return RegularCartesianGrid(shape=tuple(pl.shape), total_volume=pl.total_volume, distances=tuple(pl.distances), harmonic_grid=hg)
 
 
+_HARTLEY_PLANS = {}
+
+
+def hartley(p, axes=None, *, hartley_convention: str = "non_canonical_hartley", runtime: Optional[Runtime] = None) -> torch.Tensor:
+    """``hartley(p, axes)`` of the reference (correlated_field.py:24-30): ``Re(fftn(p, axes)) +/- Im(fftn(p, axes))``, unnormalised,
+    on the device.  ``axes=None``: all axes; otherwise the transform runs over the named axes (at most three) for every index of
+    the others, one device call per slice.  Power-of-two extents use the fused passes (``nb200_hartley``), other extents the
+    chirp-z call (``nb200_hartley_chirpz``); plans are cached per (shape, dtype, convention, runtime)."""
+    from ._runtime import default_runtime
+    rt = runtime if runtime is not None else default_runtime()
+    x = p if isinstance(p, torch.Tensor) else torch.as_tensor(np.asarray(p))
+    dtype = x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float64
+    x = rt.asarray(x, dtype)
+    nd = x.ndim
+    axes = tuple(range(nd)) if axes is None else tuple(sorted(int(a) % nd for a in ((axes,) if np.ndim(axes) == 0 else axes)))
+    if len(set(axes)) != len(axes) or not 1 <= len(axes) <= 3:
+        raise NotImplementedError("hartley: between one and three distinct axes")
+    sub = tuple(int(x.shape[a]) for a in axes)
+    key = (sub, dtype, hartley_convention, id(rt))
+    fn = _HARTLEY_PLANS.get(key)
+    if fn is None:
+        if all(n >= 2 and not (n & (n - 1)) for n in sub):
+            fn = Plan(sub, 1.0, dtype=dtype, hartley_convention=hartley_convention, runtime=rt).hartley
+        else:
+            from .bluestein import BluesteinHartley
+            fn = BluesteinHartley(sub, dtype=dtype, convention=hartley_convention, runtime=rt)
+        _HARTLEY_PLANS[key] = fn
+    rest = [a for a in range(nd) if a not in axes]
+    perm = rest + list(axes)
+    xp = x.permute(perm).contiguous()
+    flat = xp.reshape((-1,) + sub)
+    out = torch.stack([fn(flat[b]) for b in range(flat.shape[0])]).reshape(xp.shape)
+    return out.permute([perm.index(a) for a in range(nd)]).contiguous()
+
+
 class CorrelatedFieldMaker:
     """Builder with the call protocol of ``jft.CorrelatedFieldMaker`` (correlated_field.py:519-920)."""
 

@@ -169,3 +169,15 @@ def test_likelihood_surface(rt):
     assert lh.rsm_tangents_shape == lh.domain == lh.right_sqrt_metric_tangents_shape
     s = lh + lh
     assert s.lsm_tangents_shape == (512,) and abs(s.energy(s.init(3)) - 2.0 * lh.energy(p)) <= 1e-12 * abs(lh.energy(p))
+
+
+@pytest.mark.parametrize("shape,axes", [((8, 16), None), ((6, 5), None), ((4, 8, 3), (0, 1)), ((3, 4, 5, 2), (1, 2, 3)), ((7, 4), (-1,)), ((2, 3, 4, 4), (2, 3))])
+def test_module_level_hartley(rt, shape, axes):
+    """`hartley(p, axes)` (correlated_field.py:24-30) on the device for any extents and axis subsets, both sign conventions."""
+    x = np.random.default_rng(1).standard_normal(shape)
+    for conv in ("non_canonical_hartley", "canonical_hartley"):
+        got = nb.hartley(torch.as_tensor(x), axes, hartley_convention=conv, runtime=rt)
+        want = oracle.hartley(x, axes=axes, convention=conv)
+        assert got.shape == x.shape and np.max(np.abs(got.numpy() - want)) < 1e-12 * np.max(np.abs(want))
+    with pytest.raises(NotImplementedError):
+        nb.hartley(torch.zeros((2, 2, 2, 2)), runtime=rt)
