@@ -9,7 +9,7 @@ from ._capi import NB200Error  # noqa: F401
 from ._runtime import Lin, ModelHandle, Plan, Runtime, default_runtime  # noqa: F401
 from .prior import LogNormalPrior, NormalPrior, lognormal_moments  # noqa: F401
 from .tree import Layout  # noqa: F401
-from .correlated_field import CorrelatedField, CorrelatedFieldMaker, hartley  # noqa: F401
+from .correlated_field import CorrelatedField, CorrelatedFieldMaker, get_fourier_mode_distributor, hartley, make_grid  # noqa: F401
 from .likelihood import (Gaussian, Likelihood, LikelihoodPartial, LikelihoodSum, LikelihoodWithModel, OperatorLikelihood,  # noqa: F401
                          Poissonian,
                          SignalModel)

@@ -131,6 +131,28 @@ def _grid_record(pl: Plan):
     return RegularCartesianGrid(shape=tuple(pl.shape), total_volume=pl.total_volume, distances=tuple(pl.distances), harmonic_grid=hg)
 
 
+def get_fourier_mode_distributor(shape, distances):
+    """``(power_distributor, unique mode lengths, mode multiplicity)`` of a regular grid (correlated_field.py:134-176), host NumPy
+    like there, any extents.  (The plans of the fused path build the same tables in C++ on the folded index range.)"""
+    from .bluestein import fourier_mode_tables
+    shape = (int(shape),) if np.ndim(shape) == 0 else tuple(int(s) for s in shape)
+    tb = fourier_mode_tables(shape, distances)
+    return tb["power_distributor"], tb["mode_lengths"], tb["mode_multiplicity"]
+
+
+def make_grid(shape, distances, harmonic_type: str = "fourier"):
+    """``RegularCartesianGrid`` with its harmonic partner (correlated_field.py:238-265)."""
+    if harmonic_type.lower() != "fourier":
+        if harmonic_type.lower() == "spherical":
+            raise NotImplementedError("harmonic_type='spherical' is outside the B200 hot path")
+        raise ValueError(f"invalid `harmonic_type` {harmonic_type!r}")
+    from .bluestein import fourier_mode_tables, grid_record
+    shape = (int(shape),) if np.ndim(shape) == 0 else tuple(int(s) for s in shape)
+    tb = fourier_mode_tables(shape, distances)
+    tb["shape"], tb["distances"] = shape, tuple(float(x) for x in np.broadcast_to(distances, (len(shape),)))
+    return grid_record(tb)
+
+
 _HARTLEY_PLANS = {}
 
 

@@ -181,3 +181,19 @@ def test_module_level_hartley(rt, shape, axes):
         assert got.shape == x.shape and np.max(np.abs(got.numpy() - want)) < 1e-12 * np.max(np.abs(want))
     with pytest.raises(NotImplementedError):
         nb.hartley(torch.zeros((2, 2, 2, 2)), runtime=rt)
+
+
+@pytest.mark.parametrize("shape,dist", [((16,), 0.1), ((3, 3), 0.1), ((8, 32), (0.3, 0.11)), ((5, 3, 4), 0.4)])
+def test_grid_functions_with_the_reference_names(shape, dist):
+    """`get_fourier_mode_distributor` / `make_grid` (correlated_field.py:134-176, 238-265) against the oracle."""
+    idx, um, cnt = nb.get_fourier_mode_distributor(shape, dist)
+    oidx, oum, ocnt = oracle.fourier_mode_distributor(shape, dist)
+    assert np.array_equal(idx, oidx) and np.array_equal(um, oum) and np.array_equal(cnt, ocnt)
+    g, og = nb.make_grid(shape, dist), oracle.make_fourier_grid(shape, dist)
+    assert tuple(g.shape) == tuple(shape) and g.total_volume == og.total_volume
+    np.testing.assert_allclose(g.harmonic_grid.relative_log_mode_lengths, og.relative_log_mode_lengths, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(g.harmonic_grid.log_volume, og.log_volume, rtol=0, atol=1e-15)
+    with pytest.raises(NotImplementedError):
+        nb.make_grid((4,), None, "spherical")
+    with pytest.raises(ValueError):
+        nb.make_grid((4,), 1.0, "cubic")
