@@ -14,6 +14,8 @@ from typing import Callable
 import numpy as np
 import torch
 
+builtins_max, builtins_min, builtins_all, builtins_any, builtins_sum = max, min, all, any, sum    # the module defines tree versions of these names below
+
 
 class Vector:
     """``jft.Vector`` (tree_math/vector.py:79-188): a latent tree with leaf-wise arithmetic.  ``Vector(tree)``, ``.tree``,
@@ -59,7 +61,7 @@ def _leaves(tree):
     if isinstance(tree, Vector):
         return _leaves(tree.tree)
     if isinstance(tree, dict):
-        return [tree[k] for k in sorted(tree)]
+        return [l for k in sorted(tree) for l in _leaves(tree[k])]
     if isinstance(tree, (tuple, list)):
         return [l for t in tree for l in _leaves(t)]
     return [tree]
@@ -108,7 +110,7 @@ def ravel(tree):
 
 
 def vdot(a, b) -> float:
-    return float(sum(torch.dot(torch.as_tensor(x).reshape(-1), torch.as_tensor(y).reshape(-1)) for x, y in zip(_leaves(a), _leaves(b))))
+    return float(builtins_sum(torch.dot(torch.as_tensor(x).reshape(-1), torch.as_tensor(y).reshape(-1)) for x, y in zip(_leaves(a), _leaves(b))))
 
 
 def norm(tree, ord=2) -> float:
@@ -119,7 +121,7 @@ def norm(tree, ord=2) -> float:
 
 
 def size(tree) -> int:
-    return int(sum(int(np.prod(np.shape(x), dtype=np.int64)) if not isinstance(x, torch.Tensor) else x.numel() for x in _leaves(tree)))
+    return int(builtins_sum(int(np.prod(np.shape(x), dtype=np.int64)) if not isinstance(x, torch.Tensor) else x.numel() for x in _leaves(tree)))
 
 
 def zeros_like(tree):
@@ -131,7 +133,7 @@ def where(condition, x, y):
     trees = [t for t in (condition, x, y) if isinstance(t, (dict, tuple, list))]
     if not trees:
         return torch.where(torch.as_tensor(condition), torch.as_tensor(x), torch.as_tensor(y))
-    ref = max(trees, key=lambda t: len(_leaves(t)))
+    ref = builtins_max(trees, key=lambda t: len(_leaves(t)))
     return _map(lambda _, c, a, b: torch.where(torch.as_tensor(c), torch.as_tensor(a), torch.as_tensor(b)), ref, condition, x, y)
 
 
@@ -149,7 +151,7 @@ def unstack(stacked, axis=0):
 def mean(forest):
     """forest_math.py:213-223: leaf-wise mean of a sequence of trees (e.g. ``tuple(signal(s) for s in samples)``)."""
     n = len(forest)
-    return _map(lambda *ts: sum(torch.as_tensor(t) for t in ts) / n, *forest)
+    return _map(lambda *ts: builtins_sum(torch.as_tensor(t) for t in ts) / n, *forest)
 
 
 def mean_and_std(forest, correct_bias=True):
@@ -194,3 +196,104 @@ def get_map(map) -> Callable:
     if callable(map):
         return map
     raise TypeError(f"invalid `map` {map!r}; expected string or callable")
+
+
+# ---- further leaf-wise helpers of the reference's tree_math namespace (vector_math.py, forest_math.py) ----------------------
+def ones_like(tree):
+    return _map(lambda t: torch.ones_like(torch.as_tensor(t)), tree)
+
+
+def shape(tree):
+    """Tree of leaf shapes (vector_math.py ``shape``)."""
+    return _map(lambda t: tuple(torch.as_tensor(t).shape), tree)
+
+
+tree_shape = shape
+
+
+def result_type(*trees):
+    dt = None
+    for t in trees:
+        for leaf in _leaves(t):
+            d = torch.as_tensor(leaf).dtype
+            dt = d if dt is None else torch.promote_types(dt, d)
+    return dt
+
+
+def dot(a, b) -> float:
+    """Sum over the leaves of the leaf-wise dot products (no conjugation; equals :func:`vdot` for real trees)."""
+    return vdot(a, b)
+
+
+matmul = dot
+
+
+def sum(tree) -> float:        # noqa: A001  (name of the reference)
+    total = 0.0
+    for leaf in _leaves(tree):
+        total += float(torch.as_tensor(leaf).sum())
+    return total
+
+
+def max(tree) -> float:        # noqa: A001
+    return float(builtins_max(float(torch.as_tensor(leaf).max()) for leaf in _leaves(tree)))
+
+
+def min(tree) -> float:        # noqa: A001
+    return float(builtins_min(float(torch.as_tensor(leaf).min()) for leaf in _leaves(tree)))
+
+
+def all(tree) -> bool:         # noqa: A001
+    return builtins_all(bool(torch.as_tensor(leaf).all()) for leaf in _leaves(tree))
+
+
+def any(tree) -> bool:         # noqa: A001
+    return builtins_any(bool(torch.as_tensor(leaf).any()) for leaf in _leaves(tree))
+
+
+def conj(tree):
+    return _map(lambda t: torch.conj(torch.as_tensor(t)), tree)
+
+
+conjugate = conj
+
+
+def has_arithmetics(obj, additional_methods=()) -> bool:
+    """forest_math.py:21-41: does the object support ``+ - * /`` and unary minus (``Vector``s and arrays do, bare dicts do not)."""
+    desired = ("__add__", "__sub__", "__mul__", "__truediv__", "__neg__") + tuple(additional_methods)
+    return builtins_all(hasattr(obj, m) for m in desired)
+
+
+def assert_arithmetics(obj, *args, **kwargs):
+    if not has_arithmetics(obj, *args, **kwargs):
+        raise TypeError("input of invalid type: object must support arithmetic operations; wrap trees in `Vector`")
+
+
+def map_forest(f: Callable, in_axes=0, out_axes=0, tree_transpose_output: bool = True, map="vmap", **kwargs) -> Callable:  # noqa: A002
+    """forest_math.py:159-199: ``f`` mapped over a forest (a tuple / list of trees) given for exactly one argument."""
+    if out_axes != 0:
+        raise NotImplementedError("`out_axis` not yet supported")
+    in_axes = in_axes if isinstance(in_axes, tuple) else (in_axes,)
+    mapped = [idx for idx, el in enumerate(in_axes) if el is not None]
+    if not mapped:
+        raise ValueError("must map over at least one axis")
+    if len(mapped) > 1:
+        raise NotImplementedError("mapping over more than one axis is not yet supported")
+    i = mapped[0]
+    map_f = get_map(map)(f, in_axes=in_axes, out_axes=out_axes)
+
+    def apply(*xs):
+        if not isinstance(xs[i], (list, tuple)):
+            raise TypeError(f"expected mapped axes to be a tuple; got {type(xs[i])}")
+        out = map_f(*xs[:i], stack(xs[i]), *xs[i + 1:])
+        return unstack(out) if tree_transpose_output else out
+    return apply
+
+
+def map_forest_mean(method, map="vmap", *args, **kwargs) -> Callable:        # noqa: A002
+    """forest_math.py:202-210: the mean over the forest of ``method`` applied to every tree."""
+    method_map = map_forest(method, *args, tree_transpose_output=False, map=map, **kwargs)
+
+    def meaned_apply(*xs):
+        return _map(lambda t: torch.as_tensor(t).mean(dim=0), method_map(*xs))
+    return meaned_apply

@@ -264,3 +264,26 @@ def test_solvers_on_latent_trees():
     assert info == 0 and isinstance(sol, nb.Vector)
     for k in diag:
         np.testing.assert_allclose(sol[k].numpy(), (diag[k] * x[k]).numpy(), rtol=1e-6)
+
+
+def test_tree_math_namespace():
+    """The remaining leaf-wise helpers of the reference's `tree_math` (vector_math.py, forest_math.py:21-41, 159-210)."""
+    import pytest
+    import torch
+    from nifty_b200 import tree_math as tm
+    t = {"a": torch.tensor([1.0, -2.0]), "b": (torch.tensor([[3.0]]), torch.tensor(4.0))}
+    assert tm.sum(t) == 6.0 and tm.max(t) == 4.0 and tm.min(t) == -2.0 and tm.size(t) == 4
+    assert tm.any(tm.where(True, t, t)) and not tm.all({"x": torch.tensor([True, False])})
+    assert tm.shape(t) == {"a": (2,), "b": ((1, 1), ())} and tm.result_type(t) == torch.float32
+    assert tm.dot(t, tm.ones_like(t)) == 6.0 and tm.vdot(t, t) == 30.0 and tm.norm(t) == pytest.approx(30.0 ** 0.5)
+    assert tm.has_arithmetics(tm.Vector(t)) and tm.has_arithmetics(torch.ones(2)) and not tm.has_arithmetics(t)
+    with pytest.raises(TypeError):
+        tm.assert_arithmetics(t)
+    forest = tuple({"x": torch.full((2,), float(i))} for i in range(4))
+    sq = tm.map_forest(lambda tr: {"y": tr["x"] ** 2})(forest)
+    assert len(sq) == 4 and torch.equal(sq[3]["y"], torch.full((2,), 9.0))
+    m = tm.map_forest_mean(lambda tr: {"y": tr["x"] ** 2})(forest)
+    assert torch.equal(m["y"], torch.full((2,), 3.5))
+    with pytest.raises(TypeError):
+        tm.map_forest(lambda tr: tr)({"x": torch.zeros(2)})
+    assert tm.mean(forest)["x"][0] == 1.5                      # module-level names still work after the tree versions of sum / max
