@@ -7,7 +7,8 @@ Host side (this package): the reference's names and call protocol.  Device side
 
 from ._capi import NB200Error  # noqa: F401
 from ._runtime import Lin, ModelHandle, Plan, Runtime, default_runtime  # noqa: F401
-from .prior import LogNormalPrior, NormalPrior, lognormal_moments  # noqa: F401
+from .prior import (LogNormalPrior, NormalPrior, laplace_prior, lognormal_invprior, lognormal_moments, lognormal_prior,  # noqa: F401
+                    normal_invprior, normal_prior, uniform_prior)
 from .tree import Layout  # noqa: F401
 from .correlated_field import CorrelatedField, CorrelatedFieldMaker, get_fourier_mode_distributor, hartley, make_grid  # noqa: F401
 from .likelihood import (Gaussian, Likelihood, LikelihoodPartial, LikelihoodSum, LikelihoodWithModel, OperatorLikelihood,  # noqa: F401

@@ -66,3 +66,49 @@ def _as_prior(spec, cls, name, optional=False):
             raise TypeError(f"invalid `{name}` specified; got {spec!r}")
         return cls(*spec, name=name)
     raise TypeError(f"invalid `{name}` specified; got '{type(spec)}'")
+
+
+# ---- the function-style reparametrisations of num/stats_distributions.py:20-134 on torch tensors ---------------------------------
+def normal_prior(mean, std):
+    """Standard normal -> N(mean, std) (stats_distributions.py:42-50)."""
+    return lambda xi: mean + std * xi
+
+
+def normal_invprior(mean, std):
+    """Inverse of :func:`normal_prior` (:53-59)."""
+    return lambda y: (y - mean) / std
+
+
+def lognormal_prior(mean, std, *, _log_mean=None, _log_std=None):
+    """Standard normal -> log-normal with the given mean / std (:76-93)."""
+    import torch
+    if _log_mean is None and _log_std is None:
+        _log_mean, _log_std = lognormal_moments(mean, std)
+    return lambda xi: torch.exp(_log_mean + _log_std * torch.as_tensor(xi))
+
+
+def lognormal_invprior(mean, std, *, _log_mean=None, _log_std=None):
+    """Inverse of :func:`lognormal_prior` (:96-104)."""
+    import torch
+    if _log_mean is None and _log_std is None:
+        _log_mean, _log_std = lognormal_moments(mean, std)
+    return lambda y: (torch.log(torch.as_tensor(y)) - _log_mean) / _log_std
+
+
+def uniform_prior(a_min=0.0, a_max=1.0):
+    """Standard normal -> uniform on [a_min, a_max] through the normal CDF (:107-134)."""
+    import torch
+    scale = a_max - a_min
+    return lambda xi: a_min + scale * torch.special.ndtr(torch.as_tensor(xi))
+
+
+def laplace_prior(alpha):
+    """Standard normal -> Laplace, ``P(x|a) = exp(-|x| / a) / (2 a)`` (:20-39)."""
+    import torch
+
+    def standard_to_laplace(xi):
+        xi = torch.as_tensor(xi)
+        res = (xi < 0) * (torch.special.log_ndtr(xi) + math.log(2.0))
+        res = res - (xi > 0) * (torch.special.log_ndtr(-xi) + math.log(2.0))
+        return res * alpha
+    return standard_to_laplace

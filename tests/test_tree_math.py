@@ -287,3 +287,21 @@ def test_tree_math_namespace():
     with pytest.raises(TypeError):
         tm.map_forest(lambda tr: tr)({"x": torch.zeros(2)})
     assert tm.mean(forest)["x"][0] == 1.5                      # module-level names still work after the tree versions of sum / max
+
+
+def test_function_style_priors():
+    """num/stats_distributions.py:20-134 on torch tensors: round trips, moments of the log-normal, and the push-forward of a
+    standard normal against SciPy's distributions through their quantile functions."""
+    import numpy as np
+    import torch
+    from scipy import stats
+    import nifty_b200 as nb
+    xi = torch.linspace(-3.0, 3.0, 61, dtype=torch.float64)
+    q = stats.norm.cdf(xi.numpy())
+    np.testing.assert_allclose(nb.normal_invprior(2.0, 0.5)(nb.normal_prior(2.0, 0.5)(xi)).numpy(), xi.numpy(), atol=1e-14)
+    np.testing.assert_allclose(nb.lognormal_invprior(2.0, 0.5)(nb.lognormal_prior(2.0, 0.5)(xi)).numpy(), xi.numpy(), atol=1e-13)
+    lm, ls = nb.lognormal_moments(2.0, 0.5)
+    np.testing.assert_allclose(nb.lognormal_prior(2.0, 0.5)(xi).numpy(), stats.lognorm.ppf(q, s=ls, scale=np.exp(lm)), rtol=1e-10)
+    assert abs(stats.lognorm.mean(s=ls, scale=np.exp(lm)) - 2.0) < 1e-12 and abs(stats.lognorm.std(s=ls, scale=np.exp(lm)) - 0.5) < 1e-12
+    np.testing.assert_allclose(nb.uniform_prior(-1.0, 3.0)(xi).numpy(), stats.uniform.ppf(q, loc=-1.0, scale=4.0), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(nb.laplace_prior(0.7)(xi).numpy(), stats.laplace.ppf(q, scale=0.7), rtol=1e-9, atol=1e-12)
