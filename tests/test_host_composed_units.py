@@ -197,3 +197,25 @@ def test_grid_functions_with_the_reference_names(shape, dist):
         nb.make_grid((4,), None, "spherical")
     with pytest.raises(ValueError):
         nb.make_grid((4,), 1.0, "cubic")
+
+
+def test_sum_of_a_fused_and_a_host_composed_likelihood(rt):
+    """`lh_a + lh_b` with a summand on the fused device path and one on a non-power-of-two (host-composed) field: energies and metrics add
+    on the union of the domains, and the standard driver runs on the sum."""
+    import vi_checks as vc
+    c, g, lh_a, olh, lay = vc._setup(rt, "g2d_16x16")
+    cfm = nb.CorrelatedFieldMaker("other", runtime=rt)
+    cfm.set_amplitude_total_offset(0.5, (0.2, 0.1))
+    cfm.add_fluctuations((6, 5), 0.3, (0.3, 0.1), (-1.5, 0.3), (1.0, 0.5), None, prefix="ax")
+    lh_h = nb.Poissonian(np.random.default_rng(0).poisson(2.0, size=(6, 5))).amend(nb.SignalModel(cfm.finalize(), "exp"))
+    both = lh_a + lh_h
+    pos = {k: 0.3 * v for k, v in both.init(3).items()}
+    t = both.init(4)
+    sub = lambda lh, tree: {k: tree[k] for k in lh.domain}          # noqa: E731
+    assert abs(both.energy(pos) - (lh_a.energy(sub(lh_a, pos)) + lh_h.energy(sub(lh_h, pos)))) <= 1e-12 * abs(both.energy(pos))
+    m, want = both.metric(pos, t), {**lh_a.metric(sub(lh_a, pos), sub(lh_a, t)), **lh_h.metric(sub(lh_h, pos), sub(lh_h, t))}
+    assert all(torch.allclose(m[k], want[k], rtol=1e-12, atol=1e-14) for k in m)
+    s, st = nb.optimize_kl(both, both.signal.as_flat(pos), key=1, n_total_iterations=1, n_samples=1, sample_mode="linear_resample",
+                           draw_linear_kwargs=dict(cg_kwargs=dict(absdelta=1e-6, maxiter=100)),
+                           kl_kwargs=dict(minimize_kwargs=dict(xtol=1e-4, maxiter=2, cg_kwargs=dict(maxiter=20))))
+    assert st.nit == 1 and len(s) == 2
