@@ -88,8 +88,6 @@ class Likelihood:
         from .bluestein import BluesteinCorrelatedField
         from .outer import OuterCorrelatedField, OuterLikelihood
         composed = (OuterCorrelatedField, BluesteinCorrelatedField)      # host-composed models (outer.py, bluestein.py)
-        if getattr(self, "cov_inv_fn", None) is not None and (isinstance(signal, composed) or isinstance(getattr(signal, "cf", None), composed)):
-            raise NotImplementedError("non-diagonal noise covariances are not available on host-composed fields")
         if isinstance(signal, composed):
             return OuterLikelihood(self, signal, "identity")
         if isinstance(signal, SignalModel) and isinstance(signal.cf, composed):

@@ -206,7 +206,7 @@ class _HostLin:
             self.s = sc * self.s
             self.d = self.s
             self.sc_b = lh.scaling.b                           # d scaling / d leaf = b * scaling
-        self.mw = lh._lh_metric_weight(self.s)
+        self.M, self.Msqrt = lh._metric_ops(self.s)          # the likelihood metric and its square root at this signal, as operators
 
     def _t(self, tan):
         lh = self.lh
@@ -227,18 +227,18 @@ class _HostLin:
         return out
 
     def metric(self, tan):
-        return self.vjp(self.mw * self.jvp(tan))
+        return self.vjp(self.M(self.jvp(tan)))
 
     def metric_flat(self, v):
         lay, lh = self.lh.layout, self.lh
         return lay.pack(self.metric(lay.unpack(v)), lh.dtype, lh.rt.device)
 
     def right_sqrt_metric(self, tan):
-        return torch.sqrt(self.mw) * self.jvp(tan)
+        return self.Msqrt(self.jvp(tan))
 
     def left_sqrt_metric(self, u):
         u = torch.as_tensor(u, dtype=self.lh.dtype, device=self.lh.rt.device)
-        return self.vjp(torch.sqrt(self.mw) * u)
+        return self.vjp(self.Msqrt(u))
 
 
 class OuterCorrelatedField(LazyModel):
@@ -446,7 +446,7 @@ class HostLin:
             self._energy = float(lh._lh_energy(s))
             if not want_grad:
                 return None
-            dE = lh.w * (s - lh.data) if lh.kind == 0 else 1.0 - lh.data / s           # likelihood_impl.py:124-126, :238-240
+            dE = self._l.M(s - lh.data) if lh.kind == 0 else 1.0 - lh.data / s         # likelihood_impl.py:124-126, :238-240
             g = self._pack(self._l.vjp(dE))
         return g + pos if add_prior else g
 
@@ -483,11 +483,11 @@ class HostLin:
 
     def transformation(self):
         lh, s = self.lh, self._l.s
-        return torch.sqrt(lh.w) * s if lh.kind == 0 else 2.0 * torch.sqrt(s)           # likelihood_impl.py:134-138, :248-251
+        return self._l.Msqrt(s) if lh.kind == 0 else 2.0 * torch.sqrt(s)               # likelihood_impl.py:134-138, :248-251
 
     def normalized_residual(self):
         lh, s = self.lh, self._l.s
-        return torch.sqrt(lh.w) * (lh.data - s) if lh.kind == 0 else (lh.data - s) / torch.sqrt(s)
+        return self._l.Msqrt(lh.data - s) if lh.kind == 0 else (lh.data - s) / torch.sqrt(s)
 
 
 class OuterLikelihood(LikelihoodWithModel):
@@ -513,6 +513,7 @@ class OuterLikelihood(LikelihoodWithModel):
         dev = cf.rt.device
         self.data = torch.as_tensor(np.asarray(likelihood.data), dtype=cf.dtype, device=dev) if not isinstance(likelihood.data, torch.Tensor) \
             else likelihood.data.to(dtype=cf.dtype, device=dev)
+        self._cov_fn, self._std_fn = getattr(likelihood, "cov_inv_fn", None), getattr(likelihood, "std_inv_fn", None)
         if self.kind == 0:
             w = likelihood.w_array if likelihood.w_array is not None else likelihood.w_scalar
             self.w = torch.as_tensor(w, dtype=cf.dtype, device=dev)
@@ -541,11 +542,22 @@ class OuterLikelihood(LikelihoodWithModel):
     def _lh_energy(self, s):
         if self.kind == 0:                                   # Gaussian (likelihood_impl.py:124-126)
             r = s - self.data
-            return 0.5 * torch.sum(self.w * r * r)
+            return 0.5 * torch.sum(r * self._metric_ops(s)[0](r))
         return torch.sum(s) - torch.sum(self.data * torch.log(s))      # Poissonian (:238-240)
 
-    def _lh_metric_weight(self, s):
-        return self.w * torch.ones_like(s) if self.kind == 0 else 1.0 / s      # :131-132, :245-246
+    def _metric_ops(self, s):
+        """``(M, M^(1/2))`` of the likelihood at signal ``s`` as callables on data-shaped arrays (:131-138, :245-251): Gaussian with
+        diagonal weights, Gaussian with a non-diagonal (symmetric) operator pair, Poissonian."""
+        if self.kind != 0:
+            return (lambda x: x / s), (lambda x: x / torch.sqrt(s))
+        if self._cov_fn is not None:
+            def std(x):
+                if self._std_fn is None:
+                    raise NotImplementedError("this operation needs `noise_std_inv` (the square root of the non-diagonal inverse covariance)")
+                return torch.as_tensor(self._std_fn(x), dtype=self.dtype, device=self.rt.device)
+            return (lambda x: torch.as_tensor(self._cov_fn(x), dtype=self.dtype, device=self.rt.device)), std
+        sw = torch.sqrt(self.w)
+        return (lambda x: self.w * x), (lambda x: sw * x)
 
     def _tree(self, pos):
         """Latent position (flat vector in the order of ``self.layout``, dict or ``Vector``) as a dict of device tensors."""

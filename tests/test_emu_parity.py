@@ -200,6 +200,6 @@ def test_host_composed_scaling_leaf(rt):
     pc.check_host_composed_scaling(rt)
 
 
-@pytest.mark.parametrize("shape,nl", [((8, 8), "exp"), ((4, 8, 4), "identity")])
+@pytest.mark.parametrize("shape,nl", [((8, 8), "exp"), ((4, 8, 4), "identity"), ((6, 5), "exp")])
 def test_gaussian_with_non_diagonal_covariance(rt, shape, nl):
     pc.check_operator_gaussian(rt, shape, nl)

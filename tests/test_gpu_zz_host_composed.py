@@ -77,7 +77,7 @@ def test_host_composed_wiener_filter_and_slq(rt):
     vc.check_host_composed_wiener_and_elbo(rt, "nonpow2")
 
 
-@pytest.mark.parametrize("shape,nl", [((8, 8), "exp"), ((4, 8, 4), "identity")])
+@pytest.mark.parametrize("shape,nl", [((8, 8), "exp"), ((4, 8, 4), "identity"), ((6, 5), "exp")])
 def test_gaussian_with_non_diagonal_covariance(rt, shape, nl):
     pc.check_operator_gaussian(rt, shape, nl)
 
